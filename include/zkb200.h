@@ -1,0 +1,121 @@
+/*
+ * zkb200.h -- C ABI of libzkb200.so: the B200-native (sm_100a) prover hot path of zkt-plonk.
+ *
+ * The reference (pure Rust, /root/reference) has no FFI today; its de-facto plugin seams are the
+ * generic parameters of `ZKTPlonk<F, D, PC, ..>` / `proof_system::prove` (plonk-core/src/plonk.rs:39-46,
+ * plonk-core/src/proof_system/prove.rs:59-74).  Each entry point below names the reference interface it
+ * replaces; INTEGRATION.md shows the Rust `extern "C"` crate that binds them behind `D` and `PC`.
+ *
+ * Conventions (identical to arkworks 0.3 in-memory forms, so no conversion at the boundary):
+ *   - Fr / Fq element  = 4 x uint64_t little-endian limbs, MONTGOMERY form (R = 2^256).
+ *   - MSM scalars      = 4 x uint64_t little-endian limbs, CANONICAL form (what `into_repr()` yields).
+ *   - G1 affine point  = x || y (8 x uint64_t, Montgomery Fq); the point at infinity is (0, 0).
+ *   - NTT data is in natural order on input and output.
+ *   - Every function returns 0 on success and a negative zkb_status otherwise; nothing throws or aborts.
+ *     zkb_last_error(ctx) gives a human-readable reason.  Pointers are caller-owned and not retained.
+ *   - "_dev" variants take DEVICE pointers (HBM-resident data, e.g. torch tensors' data_ptr) and enqueue on
+ *     the context's stream without synchronising; the plain variants take HOST pointers, copy in and out,
+ *     and return when the result is in the caller's buffer.
+ *   - There is no CPU fallback: without a CUDA device zkb_ctx_create fails.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ZKB_API __attribute__((visibility("default")))
+#else
+#define ZKB_API
+#endif
+
+typedef struct zkb_ctx zkb_ctx;
+
+typedef enum {
+    ZKB_OK = 0,
+    ZKB_ERR_INVALID = -1,    /* bad argument (null pointer, size not allowed ...) */
+    ZKB_ERR_DOMAIN = -2,     /* log_n > TWO_ADICITY (28): Error::InvalidEvalDomainSize, prove.rs:77-81 */
+    ZKB_ERR_CUDA = -3,       /* a CUDA runtime call failed */
+    ZKB_ERR_NO_SRS = -4,     /* MSM asked for more points than the loaded SRS holds (kzg10 TooManyCoefficients) */
+    ZKB_ERR_OOM = -5
+} zkb_status;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+/* One context per GPU and proving thread (prove() is !Send: prove.rs:62).  Owns a stream, the twiddle tables,
+ * the resident SRS and all scratch memory; everything is released by zkb_ctx_destroy. */
+ZKB_API int zkb_ctx_create(int device, zkb_ctx **out);
+ZKB_API void zkb_ctx_destroy(zkb_ctx *ctx);
+/* Use an existing cudaStream_t (e.g. torch's current stream) for all subsequent work; NULL = default stream. */
+ZKB_API int zkb_ctx_set_stream(zkb_ctx *ctx, void *cuda_stream);
+ZKB_API int zkb_ctx_sync(zkb_ctx *ctx);
+ZKB_API const char *zkb_last_error(zkb_ctx *ctx);
+ZKB_API const char *zkb_version(void);
+
+/* ---- device memory (for HBM-resident pipelines) -------------------------------------------------------------- */
+ZKB_API int zkb_dev_alloc(zkb_ctx *ctx, size_t bytes, void **dptr);
+ZKB_API int zkb_dev_free(zkb_ctx *ctx, void *dptr);
+ZKB_API int zkb_h2d(zkb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);   /* synchronous */
+ZKB_API int zkb_d2h(zkb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);   /* synchronous */
+
+/* ---- NTT: replaces D::{fft,ifft,coset_fft,coset_ifft}_in_place ------------------------------------------------- */
+/* Reference: ark-poly 0.3 Radix2EvaluationDomain via plonk-core/src/util.rs:63-140 (poly_from_evals :63-86,
+ * poly_from_coset_evals :90-100, evals_from_poly_ref :104-113, coset_evals_from_poly(_ref) :117-140).
+ * data holds 2^log_n elements of which the first `len` are input (the rest are treated as zero, as
+ * fft_in_place's resize does); inverse: multiplies by n^-1; coset: generator g = 5 (forward: scale coefficient i
+ * by g^i first; inverse: scale output i by g^-i). */
+ZKB_API int zkb_ntt(zkb_ctx *ctx, uint64_t *data_host, size_t len, unsigned log_n, int inverse, int coset);
+ZKB_API int zkb_ntt_dev(zkb_ctx *ctx, uint64_t *data_dev, size_t len, unsigned log_n, int inverse, int coset);
+/* `count` independent transforms of the same shape (the quotient round runs 9 coset FFTs on the 4n domain,
+ * quotient_poly.rs:52-96); ptrs_host[k] is a DEVICE pointer to transform k's 2^log_n elements. */
+ZKB_API int zkb_ntt_batch_dev(zkb_ctx *ctx, uint64_t *const *ptrs_host, size_t count, size_t len, unsigned log_n,
+                      int inverse, int coset);
+
+/* ---- MSM: replaces VariableBaseMSM::multi_scalar_mul / kzg10::commit's inner product ------------------------------ */
+/* Reference: ark-ec 0.3 msm::VariableBaseMSM::multi_scalar_mul, called from plonk-core/src/commitment.rs:42 and via
+ * ark-poly-commit kzg10::{commit,open} from prove.rs:134,179,250,307,374,381,427.
+ * The committer key's powers_of_g stay resident in HBM (uploaded once, like `ck` is loaded once by the CLI,
+ * bin/src/main.rs:274-281); an MSM then only moves n x 32 B of scalars in and 64 B out. */
+ZKB_API int zkb_srs_load_g1(zkb_ctx *ctx, const uint64_t *xy_mont_host, size_t n);
+ZKB_API int zkb_srs_load_g1_dev(zkb_ctx *ctx, const uint64_t *xy_mont_dev, size_t n);   /* copies; caller keeps its buffer */
+ZKB_API size_t zkb_srs_size(zkb_ctx *ctx);
+/* sum_{i<n} scalars[i] * SRS[offset + i]  ->  affine (x, y) Montgomery; *is_inf = 1 and (0,0) for the identity. */
+ZKB_API int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);
+ZKB_API int zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);
+/* Same, but returns the un-normalised XYZZ partial sum (X, Y, ZZ, ZZZ: 16 limbs) of one point-range shard. */
+ZKB_API int zkb_msm_g1_dev_partial(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xyzz[16]);
+/* Combine `count` shard results (after the NCCL all-gather of 128 B per rank) into the affine commitment. */
+ZKB_API int zkb_g1_sum_partials(const uint64_t *xyzz, size_t count, uint64_t out_xy[8], int *is_inf);
+/* Arbitrary bases: drop-in for VariableBaseMSM::multi_scalar_mul(bases, scalars) and
+ * HomomorphicCommitment::multi_scalar_mul (commitment.rs:31-46).  Uses min(len) = n pairs. */
+ZKB_API int zkb_msm_g1_bases(zkb_ctx *ctx, const uint64_t *points_host, const uint64_t *scalars_host, size_t n,
+                     uint64_t out_xy[8], int *is_inf);
+/* kzg10::commit for one polynomial resident in HBM (Montgomery coefficients, as produced by the iNTT):
+ * into_repr conversion + MSM against SRS[offset .. offset+n).  Reference: ark-poly-commit 0.3 kzg10::commit as
+ * reached from prove.rs:133-135,178-180,249-251,306-308,373-375 (the caller skips leading zero coefficients by
+ * passing offset/n, as skip_leading_zeros_and_convert_to_bigints does). */
+ZKB_API int zkb_commit_dev(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);
+/* out_points_dev[i] = scalars_dev[i] * base: builds [tau^i]G-style SRS / synthetic points directly in HBM
+ * (what PC::setup's FixedBaseMSM does once per SRS, plonk.rs:195). */
+ZKB_API int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], const uint64_t *scalars_dev, size_t n,
+                              uint64_t *out_points_dev);
+/* Force the window size c (0 = automatic cost model).  For tests and tuning. */
+ZKB_API int zkb_msm_set_window(zkb_ctx *ctx, int c);
+
+/* ---- test hooks (parity of the device field library against the oracle) ----------------------------------------- */
+/* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a).  Host pointers. */
+ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n);
+
+/* ---- measurement: integer-pipe peak (not in MEASURED_PEAKS.json; SURVEY.md 8d asks for it) ------------------------- */
+/* mode 0: 32-bit IMAD/s, mode 1: IMAD.WIDE.U32/s (the instruction the Montgomery product is made of),
+ * mode 2: Fq Montgomery products/s in a dependency-chained loop.  All 148 SMs, best of 3 timed launches. */
+ZKB_API int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

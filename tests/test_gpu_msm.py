@@ -1,0 +1,134 @@
+"""GPU: Pippenger MSM through the C ABI, bit-exact (affine x, y) against the oracle's VariableBaseMSM restatement."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cref
+from tests.util import gen_xy, gpu_points, skewed_scalars, to_dev, to_host
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "vectors.npz"))
+
+
+def test_fixed_base_mul_matches_oracle(ctx):
+    n = 300
+    k = cref.rand_fe(cref.FR, n, 3)
+    k[0] = 0
+    k[1] = [1, 0, 0, 0]
+    import torch
+    out = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+    ctx.g1_fixed_base_mul_dev(gen_xy(), to_dev(k), n, out)
+    assert np.array_equal(to_host(out), cref.g1_mul(gen_xy(), k))
+
+
+def test_golden_msm(ctx):
+    P = cref.to_mont(cref.FQ, np.ascontiguousarray(GOLD["msm_points"])).reshape(-1, 8)
+    s = np.ascontiguousarray(GOLD["msm_scalars"])
+    for c in (0, 3, 7, 13, 16):
+        ctx.set_msm_window(c)
+        out, inf = ctx.msm_bases(P, s)
+        assert not inf
+        assert np.array_equal(cref.from_mont(cref.FQ, out.reshape(2, 4)), GOLD["msm_result"]), c
+    ctx.set_msm_window(0)
+    Pc = cref.to_mont(cref.FQ, np.ascontiguousarray(GOLD["msm_cancel_points"])).reshape(-1, 8)
+    out, inf = ctx.msm_bases(Pc, np.ascontiguousarray(GOLD["msm_cancel_scalars"]))
+    assert inf and not out.any()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 1000, 1 << 14])
+def test_uniform_scalars_vs_oracle(ctx, n):
+    _, P = gpu_points(ctx, n, 40 + n)
+    s = cref.rand_fe(cref.FR, n, 41 + n)
+    exp, einf = cref.msm_g1(P, s)
+    got, inf = ctx.msm_bases(P, s)
+    assert inf == einf and np.array_equal(got, exp)
+
+
+def test_edge_cases_vs_oracle(ctx):
+    n = 2048
+    _, P = gpu_points(ctx, n, 7)
+    s = cref.rand_fe(cref.FR, n, 8)
+    s[0] = 0
+    s[1] = [1, 0, 0, 0]
+    s[2] = [0, 0, 0, 1 << 61]          # a single high bit (top window only)
+    rm1 = cref.ints_to_limbs([0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000000])[0]
+    s[3] = rm1                       # r - 1: every signed digit path incl. top window
+    s[4] = [0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0, 0]   # long carry run through the windows
+    P[10] = P[11]                    # repeated base (doubling inside a bucket when digits collide)
+    s[10] = s[11]
+    P[20] = 0                        # point at infinity in the bases
+    exp, einf = cref.msm_g1(P, s)
+    for c in (0, 4, 11, 16):
+        ctx.set_msm_window(c)
+        got, inf = ctx.msm_bases(P, s)
+        assert inf == einf and np.array_equal(got, exp), c
+    ctx.set_msm_window(0)
+    # empty input and all-zero scalars give the identity
+    got, inf = ctx.msm_bases(P[:0], s[:0])
+    assert inf and not got.any()
+    got, inf = ctx.msm_bases(P[:64], np.zeros((64, 4), dtype=np.uint64))
+    assert inf and not got.any()
+    # all-ones scalars: plain sum of the points
+    ones = np.zeros((n, 4), dtype=np.uint64)
+    ones[:, 0] = 1
+    got, inf = ctx.msm_bases(P, ones)
+    assert np.array_equal(got, cref.msm_g1(P, ones)[0])
+
+
+def test_skewed_scalars_vs_oracle(ctx):
+    """Witness-like distribution: huge buckets for digit 1 / small digits exercise the task splitting."""
+    n = 1 << 15
+    _, P = gpu_points(ctx, n, 17)
+    s = skewed_scalars(n, 18)
+    exp, einf = cref.msm_g1(P, s)
+    got, inf = ctx.msm_bases(P, s)
+    assert inf == einf and np.array_equal(got, exp)
+
+
+def test_resident_srs_offsets_partials_and_commit(ctx):
+    import zkt_plonk_b200 as z
+    n = 5000
+    dP, P = gpu_points(ctx, n, 23)
+    ctx.srs_load(dP)
+    assert ctx.srs_size() == n
+    s = cref.rand_fe(cref.FR, n, 24)
+    exp, _ = cref.msm_g1(P, s)
+    got, _ = ctx.msm(s)                                   # host scalars
+    assert np.array_equal(got, exp)
+    got, _ = ctx.msm(to_dev(s))                           # device scalars
+    assert np.array_equal(got, exp)
+    # offset window (kzg10::commit skipping leading zero coefficients)
+    exp_off, _ = cref.msm_g1(P[100:], s[:n - 100])
+    got, _ = ctx.msm(s[:n - 100], offset=100)
+    assert np.array_equal(got, exp_off)
+    # point-range shards combine to the full result (the multi-GPU path run on one device)
+    ds = to_dev(s)
+    cuts = [0, 1250, 2500, 3750, n]
+    parts = np.stack([ctx.msm_partial(ds[a:b].contiguous(), a, b - a) for a, b in zip(cuts[:-1], cuts[1:])])
+    got, inf = z.sum_partials(parts)
+    assert not inf and np.array_equal(got, exp)
+    # commit of a Montgomery-form polynomial with leading/trailing zeros
+    coeffs = cref.to_mont(cref.FR, s)
+    coeffs[:7] = 0
+    coeffs[n - 5:] = 0
+    kzg = z.GpuKZG10(ctx)
+    got, inf = kzg.commit_one(coeffs)
+    canon = s.copy()
+    canon[:7] = 0
+    canon[n - 5:] = 0
+    assert np.array_equal(got, cref.msm_g1(P, canon)[0])
+    with pytest.raises(z.ZkbError) as e:
+        ctx.msm(s, offset=1)
+    assert e.value.code == -4
+
+
+def test_msm_2_20_vs_oracle(ctx):
+    """BASELINE config 2: 2^20 random points and scalars, bit-exact against the VariableBaseMSM restatement."""
+    n = 1 << 20
+    dP, P = gpu_points(ctx, n, 101)
+    ctx.srs_load(dP)
+    for s in (cref.rand_fe(cref.FR, n, 102), skewed_scalars(n, 103)):
+        exp, einf = cref.msm_g1(P, s)
+        got, inf = ctx.msm(s)
+        assert inf == einf and np.array_equal(got, exp)

@@ -1,0 +1,79 @@
+"""Loader for libzkb200.so (the C ABI of include/zkb200.h).
+
+There is NO CPU fallback: if the shared library is missing the import fails loudly, and if no CUDA device
+is present `Context()` raises.  Nothing under oracle/ is ever imported from here.
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkb200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "zkb200.h")
+
+ZKB_OK, ZKB_ERR_INVALID, ZKB_ERR_DOMAIN, ZKB_ERR_CUDA, ZKB_ERR_NO_SRS, ZKB_ERR_OOM = 0, -1, -2, -3, -4, -5
+
+
+class ZkbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"zkb200 error {code}: {msg}")
+        self.code = code
+
+
+def declared_symbols():
+    """Every function name declared in include/zkb200.h."""
+    with open(HEADER_PATH) as f:
+        return sorted(set(re.findall(r"^ZKB_API [\w \*]*?\b(zkb_\w+)\(", f.read(), flags=re.M)))
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  zkt_plonk_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz, u, i = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_int
+    sig = {
+        "zkb_ctx_create": (i, [i, ctypes.POINTER(vp)]),
+        "zkb_ctx_destroy": (None, [vp]),
+        "zkb_ctx_set_stream": (i, [vp, vp]),
+        "zkb_ctx_sync": (i, [vp]),
+        "zkb_last_error": (ctypes.c_char_p, [vp]),
+        "zkb_version": (ctypes.c_char_p, []),
+        "zkb_dev_alloc": (i, [vp, sz, ctypes.POINTER(vp)]),
+        "zkb_dev_free": (i, [vp, vp]),
+        "zkb_h2d": (i, [vp, vp, vp, sz]),
+        "zkb_d2h": (i, [vp, vp, vp, sz]),
+        "zkb_ntt": (i, [vp, vp, sz, u, i, i]),
+        "zkb_ntt_dev": (i, [vp, vp, sz, u, i, i]),
+        "zkb_ntt_batch_dev": (i, [vp, ctypes.POINTER(vp), sz, sz, u, i, i]),
+        "zkb_srs_load_g1": (i, [vp, vp, sz]),
+        "zkb_srs_load_g1_dev": (i, [vp, vp, sz]),
+        "zkb_srs_size": (sz, [vp]),
+        "zkb_msm_g1": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
+        "zkb_msm_g1_dev": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
+        "zkb_msm_g1_dev_partial": (i, [vp, vp, sz, sz, vp]),
+        "zkb_g1_sum_partials": (i, [vp, sz, vp, ctypes.POINTER(i)]),
+        "zkb_msm_g1_bases": (i, [vp, vp, vp, sz, vp, ctypes.POINTER(i)]),
+        "zkb_commit_dev": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
+        "zkb_g1_fixed_base_mul_dev": (i, [vp, vp, vp, sz, vp]),
+        "zkb_msm_set_window": (i, [vp, i]),
+        "zkb_test_fp_binop": (i, [vp, i, i, vp, vp, vp, sz]),
+        "zkb_bench_int": (i, [vp, i, ctypes.POINTER(ctypes.c_double)]),
+    }
+    for name, (res, args) in sig.items():
+        if not hasattr(lib, name):
+            continue          # optional newer symbols are bound lazily by their wrappers
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = load()
+    return _LIB

@@ -1,0 +1,228 @@
+// api.cu -- extern "C" boundary of libzkb200.so (include/zkb200.h): context, memory, host-pointer wrappers.
+#include "ctx.h"
+#include "ff.cuh"
+
+using namespace zkb;
+
+namespace {
+
+template <class P>
+__global__ void fp_binop_kernel(int op, uint4 *out, const uint4 *a, const uint4 *b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe_t x = fload(a + 2 * i), y = fload(b + 2 * i), r;
+    switch (op) {
+        case 0: r = fmul<P>(x, y); break;
+        case 1: r = fadd<P>(x, y); break;
+        case 2: r = fsub<P>(x, y); break;
+        case 3: r = fsqr<P>(x); break;
+        case 4: r = finv<P>(x); break;
+        case 5: r = fto_mont<P>(x); break;
+        default: r = ffrom_mont<P>(x); break;
+    }
+    fstore(out + 2 * i, r);
+}
+
+
+// ---- integer-pipe microbenchmarks (roofline denominators for the MSM / NTT kernels) ----
+// mode 0: 32-bit IMAD (mad.lo.u32), mode 1: IMAD.WIDE.U32 (mad.wide.u32 + 64-bit accumulate),
+// mode 2: dependent Montgomery products (fmul<FqP>), 4 independent chains per thread.
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, uint32_t iters, int mode) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode == 0) {
+        uint32_t a[8], m = t | 1u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = t + k;
+        for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(m), "r"(a[(k + 1) & 7]));
+        }
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r ^= a[k];
+        out[t] = r;
+    } else if (mode == 1) {
+        unsigned long long a[8];
+        uint32_t m = t | 1u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = t + k;
+        for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"((uint32_t)a[(k + 1) & 7]), "r"(m));
+        }
+        unsigned long long r = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r ^= a[k];
+        out[t] = (uint32_t)(r ^ (r >> 32));
+    } else {
+        fe_t x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[k].v[j] = (t * 2654435761u + k * 40503u + j) & 0x0fffffffu;
+        }
+        for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = fmul<FqP>(x[k], x[(k + 1) & 3]);
+        }
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r ^= x[k].v[0] ^ x[k].v[7];
+        out[t] = r;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *zkb_version(void) { return "zkb200 0.1 (sm_100a)"; }
+
+int zkb_ctx_create(int device, zkb_ctx **out) {
+    if (!out) return ZKB_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return ZKB_ERR_CUDA;   // no CPU fallback
+    if (device < 0 || device >= count) return ZKB_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return ZKB_ERR_CUDA;
+    zkb_ctx *ctx = new zkb_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return ZKB_OK;
+}
+
+void zkb_ctx_destroy(zkb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->tables) cudaFree(kv.second.p);
+    DevBuf *bufs[] = {&ctx->ntt_scratch, &ctx->stage, &ctx->ptr_stage, &ctx->srs, &ctx->msm_ws, &ctx->poly_ws};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    zkb_msm_release(ctx);
+    delete ctx;
+}
+
+int zkb_ctx_set_stream(zkb_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return ZKB_OK;
+}
+
+int zkb_ctx_sync(zkb_ctx *ctx) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKB_OK;
+}
+
+const char *zkb_last_error(zkb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int zkb_dev_alloc(zkb_ctx *ctx, size_t bytes, void **dptr) {
+    if (!ctx || !dptr) return ZKB_ERR_INVALID;
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? ZKB_ERR_OOM : ZKB_ERR_CUDA;
+    }
+    return ZKB_OK;
+}
+
+int zkb_dev_free(zkb_ctx *ctx, void *dptr) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZKB_CUDA(ctx, cudaFree(dptr));
+    return ZKB_OK;
+}
+
+int zkb_h2d(zkb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    if (!ctx || (!dst_dev && bytes) || (!src_host && bytes)) return ZKB_ERR_INVALID;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKB_OK;
+}
+
+int zkb_d2h(zkb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    if (!ctx || (!dst_host && bytes) || (!src_dev && bytes)) return ZKB_ERR_INVALID;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- NTT
+int zkb_ntt_dev(zkb_ctx *ctx, uint64_t *data_dev, size_t len, unsigned log_n, int inverse, int coset) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    return zkb_ntt_run(ctx, data_dev, len, log_n, inverse, coset);
+}
+
+int zkb_ntt_batch_dev(zkb_ctx *ctx, uint64_t *const *ptrs_host, size_t count, size_t len, unsigned log_n,
+                      int inverse, int coset) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (!ptrs_host && count) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt_batch_dev: null pointer table");
+    for (size_t k = 0; k < count; ++k) {
+        int rc = zkb_ntt_run(ctx, ptrs_host[k], len, log_n, inverse, coset);
+        if (rc) return rc;
+    }
+    return ZKB_OK;
+}
+
+int zkb_ntt(zkb_ctx *ctx, uint64_t *data_host, size_t len, unsigned log_n, int inverse, int coset) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (!data_host) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: null data pointer");
+    if (log_n > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ntt: log_n exceeds Fr TWO_ADICITY (28)");
+    size_t n = (size_t)1 << log_n;
+    if (len > n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: len > 2^log_n");
+    int rc = zkb_reserve(ctx, ctx->stage, n * 32);
+    if (rc) return rc;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, data_host, len * 32, cudaMemcpyHostToDevice, ctx->stream));
+    rc = zkb_ntt_run(ctx, (uint64_t *)ctx->stage.p, len, log_n, inverse, coset);
+    if (rc) return rc;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(data_host, ctx->stage.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- test hooks
+int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n) {
+    if (!ctx || !out || !a || !b) return ZKB_ERR_INVALID;
+    int rc = zkb_reserve(ctx, ctx->stage, 3 * n * 32);
+    if (rc) return rc;
+    uint4 *da = (uint4 *)ctx->stage.p, *db = da + 2 * n, *dout = db + 2 * n;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (field == 0) fp_binop_kernel<FrP><<<blocks, 128, 0, ctx->stream>>>(op, dout, da, db, n);
+    else fp_binop_kernel<FqP><<<blocks, 128, 0, ctx->stream>>>(op, dout, da, db, n);
+    ZKB_CUDA(ctx, cudaGetLastError());
+    ZKB_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- microbenchmark
+int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec) {
+    if (!ctx || !ops_per_sec || mode < 0 || mode > 2) return ZKB_ERR_INVALID;
+    const uint32_t blocks = ctx->sm_count * 8, threads = 256, iters = mode == 2 ? 512 : 4096;
+    int rc = zkb_reserve(ctx, ctx->stage, (size_t)blocks * threads * 4);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    ZKB_CUDA(ctx, cudaEventCreate(&e0));
+    ZKB_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        ZKB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        int_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t *)ctx->stage.p, iters, mode);
+        ZKB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        ZKB_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms;
+        ZKB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double per_thread = (double)iters * (mode == 2 ? 4 : 8);
+    *ops_per_sec = per_thread * blocks * threads / (best * 1e-3);
+    return ZKB_OK;
+}
+
+}  // extern "C"

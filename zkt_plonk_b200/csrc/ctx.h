@@ -1,0 +1,81 @@
+// ctx.h -- internal runtime state behind the opaque zkb_ctx of include/zkb200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/zkb200.h"
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct zkb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // ---- NTT: cached twiddle tables, keyed by a small integer id (see ntt.cu)
+    std::map<uint64_t, DevBuf> tables;
+    DevBuf ntt_scratch;          // ping-pong buffer for multi-pass transforms
+    DevBuf stage;                // staging buffer for host-pointer entry points
+    DevBuf ptr_stage;
+
+    // ---- MSM (msm.cu)
+    DevBuf srs;                  // resident affine G1 points
+    size_t srs_n = 0;
+    DevBuf msm_ws;               // workspace
+    void *msm_pinned = nullptr;  // pinned host result buffer
+    void *msm_state = nullptr;   // opaque (owned by msm.cu)
+    int msm_force_c = 0;         // 0 = cost model picks the window size
+
+    // ---- elementwise / scan kernels (poly.cu)
+    DevBuf poly_ws;
+};
+
+#define ZKB_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            char b_[512];                                                                     \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                     __FILE__, __LINE__);                                                     \
+            (ctx)->err = b_;                                                                  \
+            return ZKB_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define ZKB_FAIL(ctx, code, msg) \
+    do {                         \
+        (ctx)->err = (msg);      \
+        return (code);           \
+    } while (0)
+
+// grow-only device buffer
+inline int zkb_reserve(zkb_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (b.bytes >= bytes) return ZKB_OK;
+    if (b.p) {
+        ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ZKB_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+        b.p = nullptr;
+        return e == cudaErrorMemoryAllocation ? ZKB_ERR_OOM : ZKB_ERR_CUDA;
+    }
+    b.bytes = bytes;
+    return ZKB_OK;
+}
+
+// implemented in ntt.cu / msm.cu / poly.cu
+int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int inverse, int coset);
+void zkb_msm_release(zkb_ctx *ctx);

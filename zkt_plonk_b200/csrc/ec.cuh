@@ -1,0 +1,156 @@
+// ec.cuh -- BN254 G1 (y^2 = x^3 + 3) group law on the device.
+//
+// Replaces ark-ec 0.3 `short_weierstrass_jacobian::{GroupAffine, GroupProjective}` for the bucket
+// method.  Accumulators use extended Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2):
+// a mixed addition costs 8M + 2S and needs no field inversion.  Only the affine image of the final
+// sum is canonical, and that is what is compared bit-for-bit against arkworks' VariableBaseMSM result
+// (plonk-core/src/commitment.rs:42), so the choice of projective system is free.
+//
+// Infinity: XYZZ with ZZ == 0; affine (x, y) == (0, 0) at the C boundary (not a curve point).
+#pragma once
+#include "ff.cuh"
+
+namespace zkb {
+
+struct g1a_t { fe_t x, y; };                 // affine, Montgomery Fq
+struct g1x_t { fe_t x, y, zz, zzz; };        // XYZZ
+
+#ifdef __CUDACC__
+typedef FqP Q;
+
+__device__ __forceinline__ bool g1a_is_inf(const g1a_t &p) { return fis_zero<Q>(p.x) && fis_zero<Q>(p.y); }
+__device__ __forceinline__ bool g1x_is_inf(const g1x_t &p) { return fis_zero<Q>(p.zz); }
+
+__device__ __forceinline__ g1x_t g1x_inf() {
+    g1x_t r;
+    r.x = fzero<Q>(); r.y = fzero<Q>(); r.zz = fzero<Q>(); r.zzz = fzero<Q>();
+    return r;
+}
+
+__device__ __forceinline__ g1x_t g1x_from_affine(const g1a_t &p) {
+    g1x_t r;
+    if (g1a_is_inf(p)) return g1x_inf();
+    r.x = p.x; r.y = p.y; r.zz = fone<Q>(); r.zzz = fone<Q>();
+    return r;
+}
+
+// 2 * (affine p), p finite  (mdbl-2008-s-1)
+__device__ __noinline__ g1x_t g1x_double_affine(const g1a_t &p) {
+    g1x_t r;
+    fe_t u = fdbl<Q>(p.y);
+    fe_t v = fsqr<Q>(u);
+    fe_t w = fmul<Q>(u, v);
+    fe_t s = fmul<Q>(p.x, v);
+    fe_t xx = fsqr<Q>(p.x);
+    fe_t m = fadd<Q>(fdbl<Q>(xx), xx);
+    r.x = fsub<Q>(fsub<Q>(fsqr<Q>(m), s), s);
+    r.y = fsub<Q>(fmul<Q>(m, fsub<Q>(s, r.x)), fmul<Q>(w, p.y));
+    r.zz = v;
+    r.zzz = w;
+    return r;
+}
+
+// 2 * p  (dbl-2008-s-1)
+__device__ __noinline__ g1x_t g1x_double(const g1x_t &p) {
+    if (g1x_is_inf(p)) return p;
+    g1x_t r;
+    fe_t u = fdbl<Q>(p.y);
+    fe_t v = fsqr<Q>(u);
+    fe_t w = fmul<Q>(u, v);
+    fe_t s = fmul<Q>(p.x, v);
+    fe_t xx = fsqr<Q>(p.x);
+    fe_t m = fadd<Q>(fdbl<Q>(xx), xx);
+    r.x = fsub<Q>(fsub<Q>(fsqr<Q>(m), s), s);
+    r.y = fsub<Q>(fmul<Q>(m, fsub<Q>(s, r.x)), fmul<Q>(w, p.y));
+    r.zz = fmul<Q>(v, p.zz);
+    r.zzz = fmul<Q>(w, p.zzz);
+    return r;
+}
+
+// acc += q (affine), all special cases handled  (madd-2008-s)
+__device__ __forceinline__ void g1x_add_mixed(g1x_t &acc, const g1a_t &q) {
+    if (g1a_is_inf(q)) return;
+    if (g1x_is_inf(acc)) { acc.x = q.x; acc.y = q.y; acc.zz = fone<Q>(); acc.zzz = fone<Q>(); return; }
+    fe_t u2 = fmul<Q>(q.x, acc.zz);
+    fe_t s2 = fmul<Q>(q.y, acc.zzz);
+    fe_t p = fsub<Q>(u2, acc.x);
+    fe_t r = fsub<Q>(s2, acc.y);
+    if (fis_zero<Q>(p)) {                         // same x: doubling or cancellation (rare)
+        if (fis_zero<Q>(r)) acc = g1x_double_affine(q);
+        else acc = g1x_inf();
+        return;
+    }
+    fe_t pp = fsqr<Q>(p);
+    fe_t ppp = fmul<Q>(p, pp);
+    fe_t qq = fmul<Q>(acc.x, pp);
+    fe_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(fsqr<Q>(r), ppp), qq), qq);
+    fe_t y3 = fsub<Q>(fmul<Q>(r, fsub<Q>(qq, x3)), fmul<Q>(acc.y, ppp));
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = fmul<Q>(acc.zz, pp);
+    acc.zzz = fmul<Q>(acc.zzz, ppp);
+}
+
+// acc += q (XYZZ)  (add-2008-s)
+__device__ __forceinline__ void g1x_add(g1x_t &acc, const g1x_t &q) {
+    if (g1x_is_inf(q)) return;
+    if (g1x_is_inf(acc)) { acc = q; return; }
+    fe_t u1 = fmul<Q>(acc.x, q.zz);
+    fe_t u2 = fmul<Q>(q.x, acc.zz);
+    fe_t s1 = fmul<Q>(acc.y, q.zzz);
+    fe_t s2 = fmul<Q>(q.y, acc.zzz);
+    fe_t p = fsub<Q>(u2, u1);
+    fe_t r = fsub<Q>(s2, s1);
+    if (fis_zero<Q>(p)) {
+        if (fis_zero<Q>(r)) acc = g1x_double(acc);
+        else acc = g1x_inf();
+        return;
+    }
+    fe_t pp = fsqr<Q>(p);
+    fe_t ppp = fmul<Q>(p, pp);
+    fe_t qq = fmul<Q>(u1, pp);
+    fe_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(fsqr<Q>(r), ppp), qq), qq);
+    fe_t y3 = fsub<Q>(fmul<Q>(r, fsub<Q>(qq, x3)), fmul<Q>(s1, ppp));
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = fmul<Q>(fmul<Q>(acc.zz, q.zz), pp);
+    acc.zzz = fmul<Q>(fmul<Q>(acc.zzz, q.zzz), ppp);
+}
+
+__device__ __forceinline__ g1a_t g1a_neg(const g1a_t &p) {
+    g1a_t r;
+    r.x = p.x;
+    r.y = fneg<Q>(p.y);
+    return r;
+}
+
+__device__ __forceinline__ g1a_t g1a_load(const void *p) {
+    g1a_t r;
+    r.x = fload_ro(p);
+    r.y = fload_ro(reinterpret_cast<const char *>(p) + 32);
+    return r;
+}
+__device__ __forceinline__ g1x_t g1x_load(const void *p) {
+    const char *c = reinterpret_cast<const char *>(p);
+    g1x_t r;
+    r.x = fload(c); r.y = fload(c + 32); r.zz = fload(c + 64); r.zzz = fload(c + 96);
+    return r;
+}
+__device__ __forceinline__ void g1x_store(void *p, const g1x_t &a) {
+    char *c = reinterpret_cast<char *>(p);
+    fstore(c, a.x); fstore(c + 32, a.y); fstore(c + 64, a.zz); fstore(c + 96, a.zzz);
+}
+
+// XYZZ -> affine on the device (one field inversion; used off the critical path and in tests)
+__device__ __noinline__ g1a_t g1x_to_affine(const g1x_t &p) {
+    g1a_t r;
+    if (g1x_is_inf(p)) { r.x = fzero<Q>(); r.y = fzero<Q>(); return r; }
+    fe_t zi = finv<Q>(p.zzz);                    // 1/ZZZ
+    fe_t zz_i = fmul<Q>(zi, p.zz);               // ZZ/ZZZ = 1/Z
+    zz_i = fsqr<Q>(zz_i);                        // 1/ZZ
+    r.x = fmul<Q>(p.x, zz_i);
+    r.y = fmul<Q>(p.y, zi);
+    return r;
+}
+#endif  // __CUDACC__
+}  // namespace zkb

@@ -1,0 +1,630 @@
+// msm.cu -- Pippenger bucket-method G1 multi-scalar multiplication for sm_100a.
+//
+// Replaces ark-ec 0.3 `VariableBaseMSM::multi_scalar_mul` (called from plonk-core/src/commitment.rs:42 and,
+// through ark-poly-commit's kzg10::commit / open, from prove.rs:134,179,250,307,374,381,427).  The reference
+// uses unsigned c-bit windows, one rayon task per window and serial bucket loops; results are only canonical
+// as affine points, so this implementation is free to differ in everything but the final (x, y):
+//
+//   1. signed-digit windows (digits in [-2^(c-1), 2^(c-1)], half the buckets), c chosen by a cost model;
+//   2. counting sort of (bucket, point|sign) pairs with global atomics (order inside a bucket is irrelevant
+//      because the group is commutative);
+//   3. buckets cut into tasks of <= SEG points; tasks are ordered by size so that every warp runs 32
+//      equally long loops; one thread accumulates one task in XYZZ coordinates (8M + 2S per point, the
+//      next point's gather is issued before the current addition);
+//   4. tasks of oversized buckets (skewed scalars: zeros/ones/small values) are combined warp-cooperatively;
+//   5. per-window weighted bucket sums: each thread owns a chunk of consecutive buckets (running-sum trick
+//      plus one small scalar multiplication), a CTA tree-reduces the chunks in shared memory;
+//   6. the W window sums (W x 128 B) go to the host, which folds them (Horner, c doublings per window)
+//      and converts to affine -- O(254) group operations, cheaper there than on one GPU thread.
+//
+// The integer pipe (IMAD.WIDE) bounds step 3; everything else is a few percent of the time.
+#include "ctx.h"
+#include "ec.cuh"
+#include "host_ff.h"
+
+#include <algorithm>
+
+using namespace zkb;
+
+namespace {
+
+constexpr uint32_t SEG = 256;            // max points per accumulation task
+constexpr uint32_t RED_CH = 32;          // buckets per thread in the window reduction
+constexpr uint32_t RED_THREADS = 128;    // threads per CTA in the window reduction
+constexpr uint32_t SIGN_BIT = 0x80000000u;
+
+struct MsmPlan {
+    uint32_t c, W, B;                    // window bits, windows, buckets per window (2^(c-1))
+    uint64_t nbuckets;                   // W * B
+    uint32_t red_ctas_per_window;
+};
+
+struct MsmWs {                           // carved out of ctx->msm_ws
+    uint32_t *counts, *starts, *cursor, *ntasks, *task_base, *sorted;
+    uint32_t *scan_tmp;                  // block sums for the scans
+    uint32_t *size_hist, *size_cursor;   // SEG + 1 bins
+    uint32_t *misc;                      // [0] = heavy bucket count, [1] = total tasks
+    uint32_t *heavy_list;
+    uint2 *task_order;
+    g1x_t *task_out;
+    g1x_t *win_partial;                  // W * red_ctas_per_window
+};
+
+struct MsmState {
+    void *pinned = nullptr;              // pinned host buffer for the window partial sums
+    size_t pinned_bytes = 0;
+};
+
+// ------------------------------------------------------------------ digits
+// Signed c-bit digits of a canonical 254-bit scalar.  Calls f(w, bucket_in_window, negative) for non-zero digits.
+template <class F>
+__device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], uint32_t c, uint32_t W, F f) {
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1), full = 1u << c;
+    for (uint32_t w = 0; w < W; ++w) {
+        uint32_t bit = w * c, limb = bit >> 5, off = bit & 31;
+        uint32_t lo = limb < 8 ? s[limb] : 0, hi = limb + 1 < 8 ? s[limb + 1] : 0;
+        uint32_t raw = (uint32_t)((((uint64_t)hi << 32) | lo) >> off) & (full - 1);
+        raw += carry;
+        if (raw > half) {
+            carry = 1;                            // digit = raw - 2^c <= 0
+            if (raw != full) f(w, full - raw - 1, true);
+        } else {
+            carry = 0;
+            if (raw) f(w, raw - 1, false);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_scalar(const uint4 *p, size_t i, uint32_t (&s)[8]) {
+    uint4 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+}
+
+__global__ void msm_count_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t B, uint32_t *counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_scalar(scalars, i, s);
+    for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool) { atomicAdd(&counts[w * B + b], 1u); });
+}
+
+__global__ void msm_scatter_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t B,
+                                   uint32_t *cursor, uint32_t *sorted) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_scalar(scalars, i, s);
+    for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool neg) {
+        uint32_t slot = atomicAdd(&cursor[w * B + b], 1u);
+        sorted[slot] = i | (neg ? SIGN_BIT : 0u);
+    });
+}
+
+// ------------------------------------------------------------------ exclusive scan of uint32 (three phases)
+constexpr uint32_t SCAN_TILE = 2048;     // elements per CTA (256 threads x 8)
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *sm, uint32_t *total) {
+    // 256 threads; returns exclusive prefix of v, *total = sum over the block
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    if (lane == 31) sm[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < 8 ? sm[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= (uint32_t)d) s += y;
+        }
+        if (lane < 8) sm[8 + lane] = s;   // inclusive warp totals
+    }
+    __syncthreads();
+    uint32_t warp_off = wid ? sm[8 + wid - 1] : 0;
+    *total = sm[15];
+    uint32_t r = warp_off + x - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256) scan_reduce_kernel(const uint32_t *in, uint32_t n, uint32_t *tile_sums) {
+    __shared__ uint32_t sm[16];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 8, s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (base + k < n) s += in[base + k];
+    uint32_t total;
+    block_exclusive_scan_256(s, sm, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of tile_sums in place; total written to *total_out (may be null)
+__global__ void __launch_bounds__(256) scan_sums_kernel(uint32_t *tile_sums, uint32_t ntiles, uint32_t *total_out) {
+    __shared__ uint32_t sm[16];
+    uint32_t running = 0;
+    for (uint32_t base = 0; base < ntiles; base += 256) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0, total;
+        uint32_t ex = block_exclusive_scan_256(v, sm, &total);
+        if (i < ntiles) tile_sums[i] = running + ex;
+        running += total;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = running;
+}
+
+__global__ void __launch_bounds__(256) scan_apply_kernel(const uint32_t *in, uint32_t n, const uint32_t *tile_sums, uint32_t *out) {
+    __shared__ uint32_t sm[16];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 8, v[8], s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan_256(s, sm, &total) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
+
+int exclusive_scan(zkb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tmp, uint32_t *total_out) {
+    uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    scan_reduce_kernel<<<ntiles, 256, 0, ctx->stream>>>(in, n, tmp);
+    scan_sums_kernel<<<1, 256, 0, ctx->stream>>>(tmp, ntiles, total_out);
+    scan_apply_kernel<<<ntiles, 256, 0, ctx->stream>>>(in, n, tmp, out);
+    ZKB_CUDA(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------------ tasks
+__global__ void msm_ntasks_kernel(const uint32_t *counts, uint32_t nb, uint32_t *ntasks, uint32_t *size_hist,
+                                  uint32_t *misc, uint32_t *heavy_list) {
+    __shared__ uint32_t h[SEG + 1];
+    for (uint32_t k = threadIdx.x; k <= SEG; k += blockDim.x) h[k] = 0;
+    __syncthreads();
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) {
+        uint32_t cnt = counts[b];
+        uint32_t nt = (cnt + SEG - 1) / SEG;
+        ntasks[b] = nt;
+        if (nt) {
+            uint32_t full = cnt / SEG, rem = cnt - full * SEG;
+            if (full) atomicAdd(&h[0], full);               // bin = SEG - size (descending size order)
+            if (rem) atomicAdd(&h[SEG - rem], 1u);
+            if (nt > 1) heavy_list[atomicAdd(&misc[0], 1u)] = b;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k <= SEG; k += blockDim.x) if (h[k]) atomicAdd(&size_hist[k], h[k]);
+}
+
+__global__ void msm_task_scatter_kernel(const uint32_t *counts, const uint32_t *ntasks, uint32_t nb,
+                                        uint32_t *size_cursor, uint2 *task_order) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t nt = ntasks[b];
+    if (!nt) return;
+    uint32_t cnt = counts[b];
+    for (uint32_t s = 0; s < nt; ++s) {
+        uint32_t size = min(SEG, cnt - s * SEG);
+        uint32_t pos = atomicAdd(&size_cursor[SEG - size], 1u);
+        task_order[pos] = make_uint2(b, s);
+    }
+}
+
+// ------------------------------------------------------------------ bucket accumulation (the hot kernel)
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__restrict__ points, const uint32_t *__restrict__ sorted,
+                                                             const uint32_t *__restrict__ counts, const uint32_t *__restrict__ starts,
+                                                             const uint32_t *__restrict__ task_base, const uint2 *__restrict__ task_order,
+                                                             const uint32_t *__restrict__ misc, g1x_t *__restrict__ task_out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= misc[1]) return;
+    uint2 task = task_order[t];
+    uint32_t b = task.x, s = task.y;
+    uint32_t cnt = min(SEG, counts[b] - s * SEG);
+    const uint32_t *idx = sorted + starts[b] + s * SEG;
+
+    g1x_t acc = g1x_inf();
+    uint32_t v = idx[0];
+    g1a_t p = g1a_load(points + (v & ~SIGN_BIT));
+    for (uint32_t k = 0; k < cnt; ++k) {
+        uint32_t vn = 0;
+        g1a_t pn;
+        if (k + 1 < cnt) {                                   // issue the next gather before the addition
+            vn = idx[k + 1];
+            pn = g1a_load(points + (vn & ~SIGN_BIT));
+        }
+        if (v & SIGN_BIT) p.y = fneg<FqP>(p.y);
+        g1x_add_mixed(acc, p);
+        v = vn;
+        p = pn;
+    }
+    g1x_store(task_out + task_base[b] + s, acc);
+}
+
+// one warp per oversized bucket: lanes stride over the bucket's task results, shuffle tree at the end
+__device__ __forceinline__ g1x_t shfl_down_g1x(const g1x_t &p, int d) {
+    g1x_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], d);
+        r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], d);
+        r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], d);
+        r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], d);
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(128) msm_combine_heavy_kernel(const uint32_t *misc, const uint32_t *heavy_list,
+                                                                const uint32_t *ntasks, const uint32_t *task_base,
+                                                                g1x_t *task_out) {
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t nheavy = misc[0];
+    for (uint32_t h = warp; h < nheavy; h += nwarps) {
+        uint32_t b = heavy_list[h], nt = ntasks[b];
+        g1x_t *base = task_out + task_base[b];
+        g1x_t acc = g1x_inf();
+        for (uint32_t k = lane; k < nt; k += 32) g1x_add(acc, g1x_load(base + k));
+        for (int d = 16; d >= 1; d >>= 1) {
+            g1x_t o = shfl_down_g1x(acc, d);
+            if (lane < (uint32_t)d) g1x_add(acc, o);
+        }
+        __syncwarp();
+        if (lane == 0) g1x_store(base, acc);
+    }
+}
+
+// ------------------------------------------------------------------ per-window weighted bucket sums
+__device__ __noinline__ g1x_t g1x_mul_small(const g1x_t &p, uint32_t k) {
+    g1x_t acc = g1x_inf();
+    if (!k) return acc;
+    for (int bit = 31 - __clz(k); bit >= 0; --bit) {
+        acc = g1x_double(acc);
+        if ((k >> bit) & 1) g1x_add(acc, p);
+    }
+    return acc;
+}
+
+// grid = W * ctas_per_window CTAs of RED_THREADS threads; thread owns RED_CH consecutive buckets of one window
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_kernel(const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_base,
+                                                                 const g1x_t *__restrict__ task_out, uint32_t B, uint32_t ctas_per_window,
+                                                                 g1x_t *__restrict__ win_partial) {
+    __shared__ g1x_t sm[RED_THREADS];
+    uint32_t w = blockIdx.x / ctas_per_window, cw = blockIdx.x % ctas_per_window;
+    uint32_t chunk = cw * RED_THREADS + threadIdx.x;          // chunk index inside the window
+    uint32_t lo = chunk * RED_CH;                               // first bucket (digit value lo + 1)
+    g1x_t run = g1x_inf(), acc = g1x_inf();
+    if (lo < B) {
+        uint32_t hi = min(lo + RED_CH, B);
+        for (uint32_t j = hi; j-- > lo;) {
+            uint32_t b = w * B + j;
+            if (ntasks[b]) g1x_add(run, g1x_load(task_out + task_base[b]));
+            g1x_add(acc, run);                                  // acc = sum_j (j - lo + 1) * bucket_j
+        }
+        g1x_t shifted = g1x_mul_small(run, lo);                // + lo * sum_j bucket_j
+        g1x_add(acc, shifted);
+    }
+    sm[threadIdx.x] = acc;
+    for (uint32_t stride = RED_THREADS / 2; stride >= 1; stride >>= 1) {
+        __syncthreads();
+        if (threadIdx.x < stride) {
+            g1x_t a = sm[threadIdx.x];
+            g1x_add(a, sm[threadIdx.x + stride]);
+            sm[threadIdx.x] = a;
+        }
+    }
+    if (threadIdx.x == 0) g1x_store(win_partial + blockIdx.x, sm[0]);
+}
+
+// ------------------------------------------------------------------ helpers: SRS generation, scalar conversion
+// out[i] = scalars[i] * base (affine), plain double-and-add.  Mirrors what PC::setup does once per SRS
+// (powers_of_g = [tau^i] G); used to build synthetic SRS / test points directly in HBM.
+__global__ void __launch_bounds__(128) g1_fixed_base_mul_kernel(g1a_t base, const uint4 *scalars, uint32_t n, g1a_t *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_scalar(scalars, i, s);
+    g1x_t acc = g1x_inf();
+    for (int bit = 255; bit >= 0; --bit) {
+        acc = g1x_double(acc);
+        if ((s[bit >> 5] >> (bit & 31)) & 1) g1x_add_mixed(acc, base);
+    }
+    g1a_t a = g1x_to_affine(acc);
+    fstore(&out[i].x, a.x);
+    fstore(&out[i].y, a.y);
+}
+
+// Fr Montgomery -> canonical (what into_repr() does before kzg10::commit hands scalars to the MSM)
+__global__ void fr_from_mont_kernel(const uint4 *in, uint4 *out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fstore(out + 2 * (size_t)i, ffrom_mont<FrP>(fload_ro(in + 2 * (size_t)i)));
+}
+
+// ------------------------------------------------------------------ host-side group law (window fold + affine)
+namespace hec {
+using host::Fe;
+using host::FQ;
+struct Pt { Fe x, y, zz, zzz; };
+inline bool is_inf(const Pt &p) { return host::is_zero(p.zz); }
+inline Pt inf() { Pt p; memset(&p, 0, sizeof p); return p; }
+inline Pt dbl(const Pt &p) {
+    if (is_inf(p)) return p;
+    Pt r;
+    Fe u = host::add(p.y, p.y, FQ), v = host::sqr(u, FQ), w = host::mul(u, v, FQ), s = host::mul(p.x, v, FQ);
+    Fe xx = host::sqr(p.x, FQ), m = host::add(host::add(xx, xx, FQ), xx, FQ);
+    r.x = host::sub(host::sub(host::sqr(m, FQ), s, FQ), s, FQ);
+    r.y = host::sub(host::mul(m, host::sub(s, r.x, FQ), FQ), host::mul(w, p.y, FQ), FQ);
+    r.zz = host::mul(v, p.zz, FQ);
+    r.zzz = host::mul(w, p.zzz, FQ);
+    return r;
+}
+inline Pt add(const Pt &a, const Pt &b) {
+    if (is_inf(a)) return b;
+    if (is_inf(b)) return a;
+    Fe u1 = host::mul(a.x, b.zz, FQ), u2 = host::mul(b.x, a.zz, FQ);
+    Fe s1 = host::mul(a.y, b.zzz, FQ), s2 = host::mul(b.y, a.zzz, FQ);
+    Fe p = host::sub(u2, u1, FQ), r = host::sub(s2, s1, FQ);
+    if (host::is_zero(p)) return host::is_zero(r) ? dbl(a) : inf();
+    Fe pp = host::sqr(p, FQ), ppp = host::mul(p, pp, FQ), q = host::mul(u1, pp, FQ);
+    Pt o;
+    o.x = host::sub(host::sub(host::sub(host::sqr(r, FQ), ppp, FQ), q, FQ), q, FQ);
+    o.y = host::sub(host::mul(r, host::sub(q, o.x, FQ), FQ), host::mul(s1, ppp, FQ), FQ);
+    o.zz = host::mul(host::mul(a.zz, b.zz, FQ), pp, FQ);
+    o.zzz = host::mul(host::mul(a.zzz, b.zzz, FQ), ppp, FQ);
+    return o;
+}
+inline void to_affine(const Pt &p, uint64_t out_xy[8], int *is_inf_out) {
+    if (is_inf(p)) { memset(out_xy, 0, 64); if (is_inf_out) *is_inf_out = 1; return; }
+    Fe zi = host::inv(p.zzz, FQ);
+    Fe zzi = host::sqr(host::mul(zi, p.zz, FQ), FQ);
+    Fe x = host::mul(p.x, zzi, FQ), y = host::mul(p.y, zi, FQ);
+    memcpy(out_xy, x.l, 32);
+    memcpy(out_xy + 4, y.l, 32);
+    if (is_inf_out) *is_inf_out = 0;
+}
+}  // namespace hec
+
+// ------------------------------------------------------------------ planning / workspace
+MsmPlan make_plan(size_t n, int force_c) {
+    MsmPlan pl;
+    uint32_t best_c = 8;
+    double best = 1e300;
+    for (uint32_t c = 6; c <= 20; ++c) {
+        uint32_t W = 254 / c + 1;
+        double cost = (double)n * W + 3.0 * W * (double)(1u << (c - 1));
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    pl.c = force_c > 0 ? (uint32_t)force_c : best_c;
+    pl.W = 254 / pl.c + 1;
+    pl.B = 1u << (pl.c - 1);
+    pl.nbuckets = (uint64_t)pl.W * pl.B;
+    uint32_t chunks = (pl.B + RED_CH - 1) / RED_CH;
+    pl.red_ctas_per_window = (chunks + RED_THREADS - 1) / RED_THREADS;
+    return pl;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int carve_ws(zkb_ctx *ctx, const MsmPlan &pl, size_t n, MsmWs &ws, uint64_t *max_tasks_out) {
+    const uint64_t nb = pl.nbuckets;
+    const uint64_t entries = (uint64_t)n * pl.W;
+    const uint64_t max_tasks = nb + entries / SEG + 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_counts = take(nb * 4), o_starts = take(nb * 4), o_cursor = take(nb * 4), o_ntasks = take(nb * 4),
+           o_tbase = take(nb * 4), o_sorted = take(entries * 4), o_scan = take((nb / SCAN_TILE + 2) * 4),
+           o_hist = take((SEG + 1) * 4), o_hcur = take((SEG + 1) * 4), o_misc = take(64), o_heavy = take(nb * 4),
+           o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)),
+           o_win = take((size_t)pl.W * pl.red_ctas_per_window * sizeof(g1x_t));
+    int rc = zkb_reserve(ctx, ctx->msm_ws, off);
+    if (rc) return rc;
+    char *p = (char *)ctx->msm_ws.p;
+    ws.counts = (uint32_t *)(p + o_counts); ws.starts = (uint32_t *)(p + o_starts); ws.cursor = (uint32_t *)(p + o_cursor);
+    ws.ntasks = (uint32_t *)(p + o_ntasks); ws.task_base = (uint32_t *)(p + o_tbase); ws.sorted = (uint32_t *)(p + o_sorted);
+    ws.scan_tmp = (uint32_t *)(p + o_scan); ws.size_hist = (uint32_t *)(p + o_hist); ws.size_cursor = (uint32_t *)(p + o_hcur);
+    ws.misc = (uint32_t *)(p + o_misc); ws.heavy_list = (uint32_t *)(p + o_heavy); ws.task_order = (uint2 *)(p + o_order);
+    ws.task_out = (g1x_t *)(p + o_out); ws.win_partial = (g1x_t *)(p + o_win);
+    *max_tasks_out = max_tasks;
+    return ZKB_OK;
+}
+
+MsmState *state(zkb_ctx *ctx) {
+    if (!ctx->msm_state) ctx->msm_state = new MsmState();
+    return (MsmState *)ctx->msm_state;
+}
+
+// Enqueue the whole MSM on ctx->stream; the W*ctas window partial sums end up in st->pinned.
+int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, size_t n, int force_c, MsmPlan *plan_out) {
+    if (n >= (1ull << 31)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n must be < 2^31");
+    MsmPlan pl = make_plan(n, force_c);
+    if ((uint64_t)n * pl.W >= (1ull << 32)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n * windows must be < 2^32");
+    MsmWs ws;
+    uint64_t max_tasks;
+    int rc = carve_ws(ctx, pl, n, ws, &max_tasks);
+    if (rc) return rc;
+    MsmState *st = state(ctx);
+    size_t out_bytes = (size_t)pl.W * pl.red_ctas_per_window * sizeof(g1x_t);
+    if (st->pinned_bytes < out_bytes) {
+        if (st->pinned) cudaFreeHost(st->pinned);
+        ZKB_CUDA(ctx, cudaMallocHost(&st->pinned, out_bytes));
+        st->pinned_bytes = out_bytes;
+    }
+    cudaStream_t s = ctx->stream;
+    const uint32_t nb = (uint32_t)pl.nbuckets, n32 = (uint32_t)n;
+
+    ZKB_CUDA(ctx, cudaMemsetAsync(ws.counts, 0, (size_t)nb * 4, s));
+    ZKB_CUDA(ctx, cudaMemsetAsync(ws.size_hist, 0, (SEG + 1) * 4, s));
+    ZKB_CUDA(ctx, cudaMemsetAsync(ws.misc, 0, 64, s));
+    if (n32) msm_count_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.B, ws.counts);
+    rc = exclusive_scan(ctx, ws.counts, ws.starts, nb, ws.scan_tmp, nullptr);
+    if (rc) return rc;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ws.cursor, ws.starts, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
+    if (n32) msm_scatter_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.B, ws.cursor, ws.sorted);
+    msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, nb, ws.ntasks, ws.size_hist, ws.misc, ws.heavy_list);
+    rc = exclusive_scan(ctx, ws.ntasks, ws.task_base, nb, ws.scan_tmp, ws.misc + 1);
+    if (rc) return rc;
+    rc = exclusive_scan(ctx, ws.size_hist, ws.size_cursor, SEG + 1, ws.scan_tmp, nullptr);
+    if (rc) return rc;
+    msm_task_scatter_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, ws.ntasks, nb, ws.size_cursor, ws.task_order);
+    msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, ws.sorted, ws.counts, ws.starts,
+                                                                             ws.task_base, ws.task_order, ws.misc, ws.task_out);
+    msm_combine_heavy_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out);
+    msm_reduce_kernel<<<pl.W * pl.red_ctas_per_window, RED_THREADS, 0, s>>>(ws.ntasks, ws.task_base, ws.task_out, pl.B,
+                                                                            pl.red_ctas_per_window, ws.win_partial);
+    ZKB_CUDA(ctx, cudaGetLastError());
+    ZKB_CUDA(ctx, cudaMemcpyAsync(st->pinned, ws.win_partial, out_bytes, cudaMemcpyDeviceToHost, s));
+    *plan_out = pl;
+    return ZKB_OK;
+}
+
+// wait for the stream, fold the window sums on the host; result in XYZZ
+int msm_finish(zkb_ctx *ctx, const MsmPlan &pl, hec::Pt *out) {
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const hec::Pt *part = (const hec::Pt *)state(ctx)->pinned;
+    hec::Pt total = hec::inf();
+    for (uint32_t w = pl.W; w-- > 0;) {
+        for (uint32_t k = 0; k < pl.c; ++k) total = hec::dbl(total);
+        for (uint32_t k = 0; k < pl.red_ctas_per_window; ++k) total = hec::add(total, part[w * pl.red_ctas_per_window + k]);
+    }
+    *out = total;
+    return ZKB_OK;
+}
+
+}  // namespace
+
+void zkb_msm_release(zkb_ctx *ctx) {
+    MsmState *st = (MsmState *)ctx->msm_state;
+    if (!st) return;
+    if (st->pinned) cudaFreeHost(st->pinned);
+    delete st;
+    ctx->msm_state = nullptr;
+}
+
+extern "C" {
+
+int zkb_srs_load_g1(zkb_ctx *ctx, const uint64_t *xy_mont_host, size_t n) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (!xy_mont_host && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_load_g1: null points");
+    int rc = zkb_reserve(ctx, ctx->srs, n * 64 + 64);
+    if (rc) return rc;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->srs.p, xy_mont_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->srs_n = n;
+    return ZKB_OK;
+}
+
+int zkb_srs_load_g1_dev(zkb_ctx *ctx, const uint64_t *xy_mont_dev, size_t n) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (!xy_mont_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_load_g1_dev: null points");
+    int rc = zkb_reserve(ctx, ctx->srs, n * 64 + 64);
+    if (rc) return rc;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->srs.p, xy_mont_dev, n * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->srs_n = n;
+    return ZKB_OK;
+}
+
+size_t zkb_srs_size(zkb_ctx *ctx) { return ctx ? ctx->srs_n : 0; }
+
+int zkb_msm_set_window(zkb_ctx *ctx, int c) {
+    if (!ctx || c < 0 || c > 24 || c == 1) return ZKB_ERR_INVALID;
+    state(ctx);
+    ctx->msm_force_c = c;
+    return ZKB_OK;
+}
+
+// scalars on the device, bases = resident SRS[offset .. offset + n); result as an XYZZ partial sum (16 limbs)
+int zkb_msm_g1_dev_partial(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xyzz[16]) {
+    if (!ctx || !out_xyzz) return ZKB_ERR_INVALID;
+    if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_msm: offset + n exceeds the loaded SRS");
+    if (!scalars_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: null scalars");
+    MsmPlan pl;
+    int rc = msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + offset, (const uint4 *)scalars_dev, n, ctx->msm_force_c, &pl);
+    if (rc) return rc;
+    hec::Pt total;
+    rc = msm_finish(ctx, pl, &total);
+    if (rc) return rc;
+    memcpy(out_xyzz, &total, 128);
+    return ZKB_OK;
+}
+
+int zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+    if (!ctx || !out_xy) return ZKB_ERR_INVALID;
+    uint64_t xyzz[16];
+    int rc = zkb_msm_g1_dev_partial(ctx, scalars_dev, offset, n, xyzz);
+    if (rc) return rc;
+    hec::Pt p;
+    memcpy(&p, xyzz, 128);
+    hec::to_affine(p, out_xy, is_inf);
+    return ZKB_OK;
+}
+
+int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+    if (!ctx || !out_xy) return ZKB_ERR_INVALID;
+    if (!scalars_host && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1: null scalars");
+    int rc = zkb_reserve(ctx, ctx->stage, n * 32 + 32);
+    if (rc) return rc;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return zkb_msm_g1_dev(ctx, (const uint64_t *)ctx->stage.p, offset, n, out_xy, is_inf);
+}
+
+// arbitrary bases (drop-in for VariableBaseMSM::multi_scalar_mul / HomomorphicCommitment::multi_scalar_mul)
+int zkb_msm_g1_bases(zkb_ctx *ctx, const uint64_t *points_host, const uint64_t *scalars_host, size_t n,
+                     uint64_t out_xy[8], int *is_inf) {
+    if (!ctx || !out_xy) return ZKB_ERR_INVALID;
+    if ((!points_host || !scalars_host) && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1_bases: null input");
+    int rc = zkb_reserve(ctx, ctx->stage, n * 96 + 96);
+    if (rc) return rc;
+    char *d_pts = (char *)ctx->stage.p, *d_sc = d_pts + n * 64;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_pts, points_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_sc, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    MsmPlan pl;
+    rc = msm_enqueue(ctx, (const g1a_t *)d_pts, (const uint4 *)d_sc, n, ctx->msm_force_c, &pl);
+    if (rc) return rc;
+    hec::Pt total;
+    rc = msm_finish(ctx, pl, &total);
+    if (rc) return rc;
+    hec::to_affine(total, out_xy, is_inf);
+    return ZKB_OK;
+}
+
+// sum of `count` XYZZ partial results (multi-GPU combine after the all-gather), affine out
+int zkb_g1_sum_partials(const uint64_t *xyzz, size_t count, uint64_t out_xy[8], int *is_inf) {
+    if ((!xyzz && count) || !out_xy) return ZKB_ERR_INVALID;
+    hec::Pt total = hec::inf();
+    for (size_t i = 0; i < count; ++i) {
+        hec::Pt p;
+        memcpy(&p, xyzz + 16 * i, 128);
+        total = hec::add(total, p);
+    }
+    hec::to_affine(total, out_xy, is_inf);
+    return ZKB_OK;
+}
+
+// kzg10::commit's inner product for one polynomial held in HBM in Montgomery form:
+// converts the coefficients to canonical integers (into_repr) and runs the MSM against SRS[offset..].
+int zkb_commit_dev(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+    if (!ctx || !out_xy) return ZKB_ERR_INVALID;
+    if (!coeffs_mont_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_dev: null coefficients");
+    if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_commit_dev: offset + n exceeds the loaded SRS");
+    int rc = zkb_reserve(ctx, ctx->stage, n * 32 + 32);
+    if (rc) return rc;
+    if (n) fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)coeffs_mont_dev, (uint4 *)ctx->stage.p, (uint32_t)n);
+    ZKB_CUDA(ctx, cudaGetLastError());
+    return zkb_msm_g1_dev(ctx, (const uint64_t *)ctx->stage.p, offset, n, out_xy, is_inf);
+}
+
+// out_points_dev[i] = scalars_dev[i] * base  (affine, Montgomery); scalars canonical.
+int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], const uint64_t *scalars_dev, size_t n, uint64_t *out_points_dev) {
+    if (!ctx || !base_xy) return ZKB_ERR_INVALID;
+    if ((!scalars_dev || !out_points_dev) && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_g1_fixed_base_mul_dev: null buffer");
+    g1a_t b;
+    memcpy(&b, base_xy, 64);
+    if (n) g1_fixed_base_mul_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(b, (const uint4 *)scalars_dev, (uint32_t)n, (g1a_t *)out_points_dev);
+    ZKB_CUDA(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+}  // extern "C"

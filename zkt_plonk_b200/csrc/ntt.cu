@@ -1,0 +1,260 @@
+// ntt.cu -- radix-2 NTT / INTT / coset variants over BN254 Fr for sm_100a.
+//
+// Replaces ark-poly 0.3 Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place as called through
+// plonk-core/src/util.rs:63-140.  Natural order in and out, Montgomery form, 32-byte elements.
+//
+// Decomposition (multi-dimensional Cooley-Tukey, "four-step" generalised to <= 3 passes).  With
+// N = T1*S1 (S1 = T2*S2 ...), a pass runs, for every inner offset c < S and outer block r, a size-T
+// transform on the elements  base + j*S  (base = r*T*S + c), entirely in shared memory, then multiplies
+// output k by the inter-pass twiddle w_{T*S}^{c*k} and writes it back to  base + k*S.  The last pass
+// (S = 1) scatters output k of block r to  digit_reverse(r) + k*(N/T), which restores natural order.
+// Because an Fr element is exactly one 32-byte sector, strided element access wastes no HBM bytes; the
+// passes move 64*N bytes each.
+//
+// In a tile the transform is decimation-in-frequency with one __syncthreads per stage; elements sit in
+// shared memory as two 16-byte planes (low / high half) so that a quarter-warp always covers all 32 banks.
+// Coset scaling and the n^-1 factor are fused into the first load / last store.
+#include "ctx.h"
+#include "ff.cuh"
+#include "host_ff.h"
+
+using namespace zkb;
+
+namespace {
+
+enum : uint32_t { M_IN_COSET = 1, M_OUT_COSET = 2, M_OUT_CONST = 4, M_LAST = 8 };
+
+struct PassArgs {
+    const uint4 *in;
+    uint4 *out;
+    const uint4 *tile_tw;   // w_T^j, j < T/2
+    const uint4 *tw2;       // two-level table of w_M (M = T*S): lo[2^tw_s] then hi[M >> tw_s]
+    const uint4 *cs2;       // two-level table of coset powers (g^e or g^-e / n): lo[2^cs_s] then hi
+    unsigned long long len; // elements >= len read as zero (first pass only)
+    uint32_t t, log_s, log_n;
+    uint32_t tw_s, cs_s;
+    uint32_t mode;
+    uint32_t t1, t2;        // bits of pass 1 and of the middle pass (digit reversal in the last pass)
+    fe_t scale;             // n^-1 for a plain inverse transform
+};
+
+__device__ __forceinline__ fe_t sm_load(const uint4 *lo, const uint4 *hi, uint32_t i) {
+    uint4 a = lo[i], b = hi[i];
+    fe_t r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sm_store(uint4 *lo, uint4 *hi, uint32_t i, const fe_t &r) {
+    lo[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    hi[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// base^e from a two-level table: lo[e & mask] * hi[e >> s]
+__device__ __forceinline__ fe_t pow2lvl(const uint4 *tab, uint32_t s, unsigned long long e) {
+    uint32_t lo = (uint32_t)(e & ((1ull << s) - 1));
+    unsigned long long hi = e >> s;
+    fe_t a = fload_ro(tab + 2 * (size_t)lo);
+    fe_t b = fload_ro(tab + 2 * ((size_t)(1u << s) + hi));
+    return fmul<FrP>(a, b);
+}
+
+__global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
+    extern __shared__ uint4 sm[];
+    const uint32_t T = 1u << a.t;
+    uint4 *s_lo = sm, *s_hi = sm + T;
+    const uint32_t tid = threadIdx.x, NT = blockDim.x;
+
+    const unsigned long long tile = blockIdx.x;
+    const unsigned long long c = tile & ((1ull << a.log_s) - 1);
+    const unsigned long long r = tile >> a.log_s;
+    const unsigned long long base = (r << (a.t + a.log_s)) + c;
+
+    // ---- load (zero padding + coset scaling fused)
+    for (uint32_t j = tid; j < T; j += NT) {
+        unsigned long long idx = base + ((unsigned long long)j << a.log_s);
+        fe_t v;
+        if (idx < a.len) {
+            v = fload(a.in + 2 * idx);
+            if (a.mode & M_IN_COSET) v = fmul<FrP>(v, pow2lvl(a.cs2, a.cs_s, idx));
+        } else {
+            v = fzero<FrP>();
+        }
+        sm_store(s_lo, s_hi, j, v);
+    }
+
+    // ---- t stages of decimation in frequency
+    for (uint32_t lh = a.t; lh-- > 0;) {              // h = 2^lh : butterfly half distance
+        __syncthreads();
+        const uint32_t h = 1u << lh;
+        const uint32_t tw_shift = a.t - 1 - lh;       // twiddle index = j * (T / 2h)
+        for (uint32_t b = tid; b < (T >> 1); b += NT) {
+            uint32_t j = b & (h - 1);
+            uint32_t i = ((b - j) << 1) + j;
+            fe_t u = sm_load(s_lo, s_hi, i);
+            fe_t v = sm_load(s_lo, s_hi, i + h);
+            fe_t s = fadd<FrP>(u, v);
+            fe_t d = fsub<FrP>(u, v);
+            if (lh) d = fmul<FrP>(d, fload_ro(a.tile_tw + 2 * (size_t)(j << tw_shift)));
+            sm_store(s_lo, s_hi, i, s);
+            sm_store(s_lo, s_hi, i + h, d);
+        }
+    }
+    __syncthreads();
+
+    // ---- store: shared index i holds output k = bitrev_t(i)
+    for (uint32_t i = tid; i < T; i += NT) {
+        uint32_t k = a.t ? (__brev(i) >> (32 - a.t)) : 0;
+        fe_t v = sm_load(s_lo, s_hi, i);
+        unsigned long long o;
+        if (!(a.mode & M_LAST)) {
+            v = fmul<FrP>(v, pow2lvl(a.tw2, a.tw_s, c * k));
+            o = base + ((unsigned long long)k << a.log_s);
+        } else {
+            // r = k1 * 2^t2 + k2  ->  K = k1 + 2^t1 * k2 + 2^(t1+t2) * k
+            unsigned long long k1 = r >> a.t2, k2 = r & ((1ull << a.t2) - 1);
+            o = k1 + (k2 << a.t1) + ((unsigned long long)k << (a.log_n - a.t));
+            if (a.mode & M_OUT_COSET) v = fmul<FrP>(v, pow2lvl(a.cs2, a.cs_s, o));
+            else if (a.mode & M_OUT_CONST) v = fmul<FrP>(v, a.scale);
+        }
+        fstore(a.out + 2 * o, v);
+    }
+}
+
+// out[j] = scale * base^(j << shift)
+__global__ void pow_table_kernel(uint4 *out, fe_t base, fe_t scale, uint32_t count, uint32_t shift) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    unsigned long long e = (unsigned long long)j << shift;
+    fe_t acc = scale, b = base;
+    while (e) {
+        if (e & 1) acc = fmul<FrP>(acc, b);
+        b = fsqr<FrP>(b);
+        e >>= 1;
+    }
+    fstore(out + 2 * (size_t)j, acc);
+}
+
+fe_t to_dev(const host::Fe &f) {
+    fe_t r;
+    memcpy(r.v, f.l, 32);
+    return r;
+}
+
+int build_pow_table(zkb_ctx *ctx, uint4 *out, const host::Fe &base, const host::Fe &scale, uint32_t count, uint32_t shift) {
+    pow_table_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(out, to_dev(base), to_dev(scale), count, shift);
+    ZKB_CUDA(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+// kind 1: tile table w_T^{+-j}, j < T/2
+int get_tile_table(zkb_ctx *ctx, unsigned t, int inverse, const uint4 **out) {
+    uint64_t key = (1ull << 32) | (t << 1) | (unsigned)inverse;
+    auto it = ctx->tables.find(key);
+    if (it == ctx->tables.end()) {
+        DevBuf b;
+        uint32_t cnt = t ? (1u << (t - 1)) : 1;
+        int rc = zkb_reserve(ctx, b, (size_t)cnt * 32);
+        if (rc) return rc;
+        host::Fe w = host::fr_root_of_unity(t);
+        if (inverse) w = host::inv(w, host::FR);
+        rc = build_pow_table(ctx, (uint4 *)b.p, w, host::one(host::FR), cnt, 0);
+        if (rc) return rc;
+        it = ctx->tables.emplace(key, b).first;
+    }
+    *out = (const uint4 *)it->second.p;
+    return ZKB_OK;
+}
+
+// two-level table of base^e, e < 2^lm: lo[e & (2^s - 1)] * hi[e >> s]; hi optionally pre-scaled
+int get_2lvl_table(zkb_ctx *ctx, uint64_t key, unsigned lm, const host::Fe &base, const host::Fe &hi_scale,
+                   const uint4 **out, uint32_t *s_out) {
+    uint32_t s = (lm + 1) / 2;
+    *s_out = s;
+    auto it = ctx->tables.find(key);
+    if (it == ctx->tables.end()) {
+        DevBuf b;
+        uint32_t nlo = 1u << s, nhi = 1u << (lm - s);
+        int rc = zkb_reserve(ctx, b, (size_t)(nlo + nhi) * 32);
+        if (rc) return rc;
+        rc = build_pow_table(ctx, (uint4 *)b.p, base, host::one(host::FR), nlo, 0);
+        if (rc) return rc;
+        rc = build_pow_table(ctx, (uint4 *)b.p + 2 * (size_t)nlo, base, hi_scale, nhi, s);
+        if (rc) return rc;
+        it = ctx->tables.emplace(key, b).first;
+    }
+    *out = (const uint4 *)it->second.p;
+    return ZKB_OK;
+}
+
+}  // namespace
+
+int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int inverse, int coset) {
+    if (!d_data) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: null data pointer");
+    if (log_n > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ntt: log_n exceeds Fr TWO_ADICITY (28)");
+    const size_t n = (size_t)1 << log_n;
+    if (len > n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: len > 2^log_n");
+    inverse = inverse ? 1 : 0;
+    coset = coset ? 1 : 0;
+
+    // split log_n into <= 3 passes of <= 11 bits
+    unsigned bits[3] = {0, 0, 0}, m;
+    if (log_n <= 11) { m = 1; bits[0] = log_n; }
+    else if (log_n <= 22) { m = 2; bits[0] = (log_n + 1) / 2; bits[1] = log_n - bits[0]; }
+    else { m = 3; bits[0] = (log_n + 2) / 3; bits[1] = (log_n - bits[0] + 1) / 2; bits[2] = log_n - bits[0] - bits[1]; }
+
+    if (m > 1) {
+        int rc = zkb_reserve(ctx, ctx->ntt_scratch, n * 32);
+        if (rc) return rc;
+    }
+
+    ZKB_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+
+    const uint4 *cs2 = nullptr;
+    uint32_t cs_s = 0;
+    host::Fe ninv = host::inv(host::from_u64((uint64_t)n, host::FR), host::FR);
+    if (coset) {
+        host::Fe g = host::from_u64(5, host::FR);
+        uint64_t key = (3ull << 32) | (log_n << 1) | (unsigned)inverse;
+        int rc = inverse ? get_2lvl_table(ctx, key, log_n, host::inv(g, host::FR), ninv, &cs2, &cs_s)
+                         : get_2lvl_table(ctx, key, log_n, g, host::one(host::FR), &cs2, &cs_s);
+        if (rc) return rc;
+    }
+
+    unsigned log_s = log_n;
+    for (unsigned p = 0; p < m; ++p) {
+        const unsigned t = bits[p];
+        log_s -= t;
+        PassArgs a;
+        memset(&a, 0, sizeof a);
+        const bool first = p == 0, last = p == m - 1;
+        uint4 *data = (uint4 *)d_data, *scr = (uint4 *)ctx->ntt_scratch.p;
+        a.in = first ? data : scr;
+        a.out = last ? data : scr;
+        a.len = first ? len : n;
+        a.t = t; a.log_s = log_s; a.log_n = log_n;
+        a.t1 = m >= 2 ? bits[0] : 0;
+        a.t2 = m == 3 ? bits[1] : 0;
+        int rc = get_tile_table(ctx, t, inverse, &a.tile_tw);
+        if (rc) return rc;
+        if (!last) {
+            unsigned lm = t + log_s;             // enclosing sub-transform size M = T*S
+            host::Fe w = host::fr_root_of_unity(lm);
+            if (inverse) w = host::inv(w, host::FR);
+            uint64_t key = (2ull << 32) | (lm << 1) | (unsigned)inverse;
+            rc = get_2lvl_table(ctx, key, lm, w, host::one(host::FR), &a.tw2, &a.tw_s);
+            if (rc) return rc;
+        }
+        a.cs2 = cs2; a.cs_s = cs_s;
+        a.mode = (last ? M_LAST : 0);
+        if (first && coset && !inverse) a.mode |= M_IN_COSET;
+        if (last && inverse) a.mode |= coset ? M_OUT_COSET : M_OUT_CONST;
+        a.scale = to_dev(ninv);
+        const size_t T = (size_t)1 << t;
+        unsigned threads = (unsigned)(T / 2 < 32 ? 32 : (T / 2 > 256 ? 256 : T / 2));
+        size_t tiles = n >> t;
+        ntt_pass_kernel<<<(unsigned)tiles, threads, T * 32, ctx->stream>>>(a);
+        ZKB_CUDA(ctx, cudaGetLastError());
+    }
+    return ZKB_OK;
+}
