@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the zkt-plonk prover hot path on B200 (see DESIGN.md "Measurement").
+
+Metric (BASELINE.json): G1 MSM points/s for a KZG commit of 2^20 random points and scalars (configs[1]).
+One "step" = one full commitment MSM over 2^20 (per GPU) synthetic points/scalars through the C ABI.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [...]                          # the reference algorithm on the host cores
+
+value      : device-timed (CUDA events on the launching stream) throughput, scalars already resident in HBM,
+             result (64-byte affine point) delivered to the host.
+e2e        : same call through the host-pointer C-ABI entry (zkb_msm_g1): pinned host scalars -> H2D -> MSM ->
+             affine point back on the host, wall clock around the synchronous call.
+roofline   : bucket-accumulation kernel (msm_accumulate_kernel) against the integer pipe measured live
+             (zkb_bench_int), plus the NTT against the HBM copy peak of MEASURED_PEAKS.json in "extra".
+N > 1      : weak scaling -- every rank owns a resident range of 2^20 SRS points and its scalar slice of one
+             N*2^20-point MSM; the 128-byte XYZZ partial sums are all-gathered over NCCL and added.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+R_LIMBS = np.array([0x43e1f593f0000001, 0x2833e84879b97091, 0xb85045b68181585d, 0x30644e72e131a029], dtype=np.uint64)
+METRIC = "g1_msm_points_per_s"
+UNIT = "points/s"
+
+
+def uniform_scalars(n, seed):
+    """n canonical scalars uniform-ish in [0, r): 254 random bits, minus r when >= r (host, numpy)."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64(0x3FFFFFFFFFFFFFFF)
+    ge = np.zeros(n, dtype=bool)
+    decided = np.zeros(n, dtype=bool)
+    for k in (3, 2, 1, 0):
+        gt, lt = a[:, k] > R_LIMBS[k], a[:, k] < R_LIMBS[k]
+        ge |= gt & ~decided
+        decided |= gt | lt
+    ge |= ~decided
+    idx = np.flatnonzero(ge)
+    borrow = np.zeros(idx.size, dtype=np.uint64)
+    for k in range(4):
+        x = a[idx, k]
+        sub = R_LIMBS[k] + borrow
+        nb = ((x < sub) | ((sub == 0) & (borrow == 1))).astype(np.uint64)
+        a[idx, k] = x - sub
+        borrow = nb
+    return a
+
+
+class ClockSampler:
+    """Samples nvidia-smi while the timed region runs (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU algorithm for this path on the host cores.
+
+    /root/reference is Rust over crates.io arkworks 0.3 and cannot be built in this image (no rustc/cargo), so
+    this arm times oracle/zkb_oracle.c: the C restatement of VariableBaseMSM::multi_scalar_mul (unsigned windows,
+    c = ln_without_floats(n) + 2, one thread per window, Jacobian mixed adds) with every host thread it can use.
+    """
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cref
+    log_n = args.log_n
+    n = 1 << log_n
+    threads = cref.num_threads()
+    G = cref.to_mont(cref.FQ, cref.ints_to_limbs([1, 2])).reshape(8)
+    ab = cref.g1_mul(G, cref.ints_to_limbs([0x1234567890ABCDEF1234567, 0xFEDCBA0987654321ABCDEF]))
+    P = cref.g1_walk(ab[0], ab[1], n)
+    sets = [uniform_scalars(n, 1000 + k) for k in range(2)]
+    for w in range(min(args.warmup, 1)):
+        cref.msm_g1(P, sets[w % 2], threads)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cref.msm_g1(P, sets[k % 2], threads)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64x4 (254-bit modular integers)", "data": "synthetic",
+        "config": {"workload": f"kzg_commit_g1_msm_2^{log_n}", "points": n, "scalars": "uniform in [0,r)",
+                   "curve": "BN254"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full 2^{log_n}-point MSMs; restated arkworks VariableBaseMSM (C), "
+                                   "not the arkworks binary"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ main arm
+def run_main(args):
+    import torch
+    import zkt_plonk_b200 as z
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    ctx = z.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream())
+
+    log_n = args.log_n
+    n = 1 << log_n
+    NSETS = 4
+
+    # ---- synthetic SRS range of this rank: P_i = k_i * G built directly in HBM
+    one_two = np.zeros((2, 4), dtype=np.uint64)
+    one_two[0, 0], one_two[1, 0] = 1, 2
+    G = ctx.fp_binop(1, 5, one_two).reshape(8)                     # (1, 2) in Montgomery form
+    k = torch.from_numpy(uniform_scalars(n, 7 + 1000 * rank).view(np.int64)).to(dev)
+    P = torch.empty((n, 8), dtype=torch.int64, device=dev)
+    ctx.g1_fixed_base_mul_dev(G, k, n, P)
+    ctx.srs_load(P)
+    del k
+    # ---- scalar sets: resident copies (value) and pinned host copies (e2e)
+    host_sets = [torch.from_numpy(uniform_scalars(n, 100 + s + 1000 * rank).view(np.int64)).pin_memory() for s in range(NSETS)]
+    dev_sets = [h.to(dev) for h in host_sets]
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.int64, device=dev)     # 256 MB > 126 MB L2
+    gather = torch.zeros((world, 16), dtype=torch.int64, device=dev) if world > 1 else None
+
+    def step(scalars_dev):
+        """One commitment MSM; returns the affine result on the host."""
+        if world == 1:
+            return ctx.msm(scalars_dev)
+        part = ctx.msm_partial(scalars_dev, 0, n)                 # this rank's point range
+        mine = torch.from_numpy(part.view(np.int64)).to(dev, non_blocking=False)
+        dist.all_gather_into_tensor(gather, mine.reshape(1, 16))
+        return z.sum_partials(gather.cpu().numpy().view(np.uint64))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    int_peak = ctx.bench_int(0)                                     # 32-bit IMAD/s, all SMs
+    for w in range(args.warmup):
+        step(dev_sets[w % NSETS])
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- timed region: K steps, each bracketed by events; L2 flushed (untimed) between steps
+    l0 = ctx.launch_count()
+    step_ms, acc_ms, tot_ms = [], [], []
+    results = []
+    for kstep in range(args.steps):
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        results.append(step(dev_sets[kstep % NSETS]))
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        tm = ctx.msm_last_timing()
+        acc_ms.append(tm["accumulate_ms"])
+        tot_ms.append(tm["total_ms"])
+    launches = ctx.launch_count() - l0
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    barrier()
+
+    # ---- e2e: host (pinned) scalars through the host-pointer entry, wall clock around the synchronous call
+    e2e_s = []
+    for kstep in range(max(3, min(args.steps, 10))):
+        flush.zero_()
+        barrier()
+        hs = host_sets[kstep % NSETS].numpy().view(np.uint64)
+        t0 = time.perf_counter()
+        if world == 1:
+            ctx.msm(hs)
+        else:
+            d = host_sets[kstep % NSETS].to(dev, non_blocking=True)
+            step(d)
+        torch.cuda.synchronize()
+        e2e_s.append(time.perf_counter() - t0)
+    e2e_t = statistics.mean(e2e_s)
+    if world > 1:
+        t = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    clocks = sampler.stop()
+
+    if rank != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    tm = ctx.msm_last_timing()
+    ms_per_step = total_ms / args.steps
+    value = world * n * args.steps / (total_ms * 1e-3)
+    peaks, peak_src = measured_peaks()
+    # roofline of the dominant kernel: one mixed addition per non-zero digit (n * W, minus a 2^-c fraction),
+    # 10 Fq products each (XYZZ madd-2008-s: 8M + 2S), 136 32x32->64 MACs per product, and an IMAD.WIDE MAC
+    # occupies the fma pipe for two 32-bit IMAD issue slots (measured: zkb_bench_int mode 1 vs 0).
+    adds = n * tm["windows"]
+    int_ops = adds * 10 * 136 * 2
+    acc_s = statistics.mean(acc_ms) * 1e-3
+    roofline = {"bound": "int32-imad (tensor cores unused: multi-precision integer work)", "kernel": "msm_accumulate_kernel",
+                "achieved": int_ops / acc_s / 1e12, "peak": int_peak / 1e12, "unit": "T int32 IMAD/s",
+                "frac": int_ops / acc_s / int_peak, "traffic": None,
+                "peak_source": "measured live by zkb_bench_int (no integer peak in MEASURED_PEAKS.json)",
+                "kernel_ms": acc_s * 1e3, "kernel_share_of_step": acc_s * 1e3 / ms_per_step,
+                "algorithmic_ops_per_launch": int_ops, "window_bits": tm["c"], "windows": tm["windows"]}
+
+    # ---- extra: the NTT half of the metric (Fr NTT elems/s), one GPU, 2^22 (= 4n for a 2^20-gate circuit)
+    extra = {}
+    try:
+        ln = 22 if log_n >= 20 else log_n + 2
+        x = torch.from_numpy(uniform_scalars(1 << ln, 5).view(np.int64)).to(dev)
+        for _ in range(3):
+            ctx.ntt_dev(x, ln, False, True)
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ctx.ntt_dev(x, ln, False, True)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t_ntt = statistics.mean(ts) * 1e-3
+        gbs = 64.0 * (1 << ln) / t_ntt / 1e9
+        extra["ntt"] = {"workload": f"coset_fft_2^{ln}", "elems_per_s": (1 << ln) / t_ntt, "ms": t_ntt * 1e3,
+                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                                     "note": "64 B/element algorithmic; the kernel is integer-pipe bound (DESIGN.md)"}}
+        del x
+    except Exception as e:  # the NTT extra must never sink the MSM line
+        extra["ntt_error"] = str(e)
+
+    # ---- CPU baseline (rank 0, N = 1): the oracle's VariableBaseMSM restatement on the same points and scalars
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cref
+        Ph = P.cpu().numpy().view(np.uint64)
+        sh = host_sets[(args.steps - 1) % NSETS].numpy().view(np.uint64)
+        threads = cref.num_threads()
+        t0 = time.perf_counter()
+        exp, einf = cref.msm_g1(Ph, sh, threads)
+        dt = time.perf_counter() - t0
+        got, inf = results[-1]
+        cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"one full 2^{log_n}-point MSM, same points and scalars as the last timed step; restated "
+                         "arkworks VariableBaseMSM (C + OpenMP, one thread per window), not the arkworks binary",
+               "seconds": dt, "bit_exact_vs_gpu": bool(inf == einf and np.array_equal(got, exp))}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
+        "config": {"workload": f"kzg_commit_g1_msm_2^{log_n}", "points_per_gpu": n, "total_points": world * n,
+                   "scalars": "uniform in [0,r), canonical", "curve": "BN254", "l2": "flushed between timed steps (256 MB write)",
+                   "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
+                   "parallelism": f"point-range x{world}" if world > 1 else "single GPU"},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": world * n / e2e_t, "unit": UNIT, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 8192 if world == 1 else 128 * world,
+                "ms_per_step": e2e_t * 1e3, "timing": "wall clock around the synchronous host-pointer call"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "phases_ms": {"sort": tm["sort_ms"], "accumulate": tm["accumulate_ms"], "heavy": tm["heavy_ms"],
+                      "reduce": tm["reduce_ms"], "device_total": tm["total_ms"]},
+        "extra": extra,
+    }
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", dest="log_n", type=int, default=int(os.environ.get("ZKB_BENCH_LOG_N", "20")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_main(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,13 @@ ZKB_API int zkb_msm_set_window(zkb_ctx *ctx, int c);
 /* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a).  Host pointers. */
 ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n);
 
+/* Kernels this context has enqueued so far (bench.py's gpu_launches is a difference of two readings). */
+ZKB_API uint64_t zkb_launch_count(zkb_ctx *ctx);
+/* Device time (CUDA events on the context's stream) of the phases of the last MSM, in ms:
+ * out_ms[0] digits + counting sort + task ordering, [1] bucket accumulation (the integer-bound kernel),
+ * [2] oversized-bucket combine, [3] window reduction, [4] total.  info[0] = n * windows, info[1] = c, info[2] = windows. */
+ZKB_API int zkb_msm_last_timing(zkb_ctx *ctx, float out_ms[5], uint64_t info[3]);
+
 /* ---- measurement: integer-pipe peak (not in MEASURED_PEAKS.json; SURVEY.md 8d asks for it) ------------------------- */
 /* mode 0: 32-bit IMAD/s, mode 1: IMAD.WIDE.U32/s (the instruction the Montgomery product is made of),
  * mode 2: Fq Montgomery products/s in a dependency-chained loop.  All 148 SMs, best of 3 timed launches. */

@@ -90,6 +90,12 @@ def g1_mul(base_xy, scalars):
     return out
 
 
+def g1_walk(start_xy, step_xy, n):
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib().zko_g1_walk(_p(start_xy), _p(step_xy), ctypes.c_size_t(n), _p(out))
+    return out
+
+
 def g1_sum(points):
     out = np.zeros(8, dtype=np.uint64)
     lib().zko_g1_sum(_p(points), ctypes.c_size_t(points.shape[0]), _p(out))

@@ -384,6 +384,26 @@ API void zko_g1_sum(const u64 *points, size_t n, u64 out_xy[8]) {
     g1j_to_affine((g1a *)out_xy, &acc);
 }
 
+/* out[i] = start + i * step (affine), i < n: cheap synthetic base points for CPU-only timing runs. */
+API void zko_g1_walk(const u64 start_xy[8], const u64 step_xy[8], size_t n, u64 *out_xy) {
+    const g1a *S = (const g1a *)start_xy, *D = (const g1a *)step_xy;
+    const size_t CH = 4096;
+    size_t nch = (n + CH - 1) / CH;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t c = 0; c < nch; ++c) {
+        /* chunk start = start + (c*CH) * step by double-and-add */
+        g1j acc; acc.z = (fe){{0, 0, 0, 0}};
+        size_t k = c * CH;
+        for (int b = 63; b >= 0; --b) { g1j_double(&acc, &acc); if ((k >> b) & 1) g1j_add_mixed(&acc, &acc, D); }
+        g1j_add_mixed(&acc, &acc, S);
+        size_t hi = (c + 1) * CH < n ? (c + 1) * CH : n;
+        for (size_t i = c * CH; i < hi; ++i) {
+            g1j_to_affine((g1a *)(out_xy + 8 * i), &acc);
+            g1j_add_mixed(&acc, &acc, D);
+        }
+    }
+}
+
 API int zko_g1_on_curve(const u64 xy[8]) {
     const g1a *p = (const g1a *)xy;
     if (g1a_is_inf(p)) return 1;

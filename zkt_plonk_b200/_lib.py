@@ -59,6 +59,8 @@ def load():
         "zkb_g1_fixed_base_mul_dev": (i, [vp, vp, vp, sz, vp]),
         "zkb_msm_set_window": (i, [vp, i]),
         "zkb_test_fp_binop": (i, [vp, i, i, vp, vp, vp, sz]),
+        "zkb_launch_count": (ctypes.c_uint64, [vp]),
+        "zkb_msm_last_timing": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),
         "zkb_bench_int": (i, [vp, i, ctypes.POINTER(ctypes.c_double)]),
     }
     for name, (res, args) in sig.items():

@@ -133,6 +133,17 @@ class Context:
                                                         _dev_ptr(out_dev)))
         return out_dev
 
+    def launch_count(self):
+        return int(self._lib.zkb_launch_count(self._h))
+
+    def msm_last_timing(self):
+        """dict of device-side phase times (ms) of the last MSM plus its plan."""
+        ms = (ctypes.c_float * 5)()
+        info = (ctypes.c_uint64 * 3)()
+        self._check(self._lib.zkb_msm_last_timing(self._h, ms, info))
+        return {"sort_ms": ms[0], "accumulate_ms": ms[1], "heavy_ms": ms[2], "reduce_ms": ms[3], "total_ms": ms[4],
+                "entries": int(info[0]), "c": int(info[1]), "windows": int(info[2])}
+
     def bench_int(self, mode):
         v = ctypes.c_double(0)
         self._check(self._lib.zkb_bench_int(self._h, int(mode), ctypes.byref(v)))

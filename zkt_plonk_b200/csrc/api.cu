@@ -116,6 +116,8 @@ int zkb_ctx_sync(zkb_ctx *ctx) {
     return ZKB_OK;
 }
 
+uint64_t zkb_launch_count(zkb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
 const char *zkb_last_error(zkb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int zkb_dev_alloc(zkb_ctx *ctx, size_t bytes, void **dptr) {

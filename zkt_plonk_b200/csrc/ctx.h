@@ -20,6 +20,7 @@ struct zkb_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     std::string err;
+    uint64_t launches = 0;       // kernels enqueued through this context (bench.py reports it)
 
     // ---- NTT: cached twiddle tables, keyed by a small integer id (see ntt.cu)
     std::map<uint64_t, DevBuf> tables;

@@ -53,6 +53,10 @@ struct MsmWs {                           // carved out of ctx->msm_ws
 struct MsmState {
     void *pinned = nullptr;              // pinned host buffer for the window partial sums
     size_t pinned_bytes = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase boundaries of the last MSM
+    bool ev_valid = false;
+    uint64_t last_entries = 0;           // n * W upper bound of bucket insertions of the last MSM
+    uint32_t last_c = 0, last_W = 0;
 };
 
 // ------------------------------------------------------------------ digits
@@ -453,6 +457,9 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     }
     cudaStream_t s = ctx->stream;
     const uint32_t nb = (uint32_t)pl.nbuckets, n32 = (uint32_t)n;
+    if (!st->ev[0]) for (int k = 0; k < 5; ++k) ZKB_CUDA(ctx, cudaEventCreate(&st->ev[k]));
+    st->last_entries = (uint64_t)n * pl.W; st->last_c = pl.c; st->last_W = pl.W;
+    ZKB_CUDA(ctx, cudaEventRecord(st->ev[0], s));
 
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.counts, 0, (size_t)nb * 4, s));
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.size_hist, 0, (SEG + 1) * 4, s));
@@ -468,12 +475,18 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     rc = exclusive_scan(ctx, ws.size_hist, ws.size_cursor, SEG + 1, ws.scan_tmp, nullptr);
     if (rc) return rc;
     msm_task_scatter_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, ws.ntasks, nb, ws.size_cursor, ws.task_order);
+    ZKB_CUDA(ctx, cudaEventRecord(st->ev[1], s));
     msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, ws.sorted, ws.counts, ws.starts,
                                                                              ws.task_base, ws.task_order, ws.misc, ws.task_out);
+    ZKB_CUDA(ctx, cudaEventRecord(st->ev[2], s));
     msm_combine_heavy_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out);
+    ZKB_CUDA(ctx, cudaEventRecord(st->ev[3], s));
     msm_reduce_kernel<<<pl.W * pl.red_ctas_per_window, RED_THREADS, 0, s>>>(ws.ntasks, ws.task_base, ws.task_out, pl.B,
                                                                             pl.red_ctas_per_window, ws.win_partial);
+    ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], s));
     ZKB_CUDA(ctx, cudaGetLastError());
+    st->ev_valid = true;
+    ctx->launches += 16;                 // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy, reduce
     ZKB_CUDA(ctx, cudaMemcpyAsync(st->pinned, ws.win_partial, out_bytes, cudaMemcpyDeviceToHost, s));
     *plan_out = pl;
     return ZKB_OK;
@@ -498,6 +511,7 @@ void zkb_msm_release(zkb_ctx *ctx) {
     MsmState *st = (MsmState *)ctx->msm_state;
     if (!st) return;
     if (st->pinned) cudaFreeHost(st->pinned);
+    for (int k = 0; k < 5; ++k) if (st->ev[k]) cudaEventDestroy(st->ev[k]);
     delete st;
     ctx->msm_state = nullptr;
 }
@@ -624,6 +638,21 @@ int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], const uin
     memcpy(&b, base_xy, 64);
     if (n) g1_fixed_base_mul_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(b, (const uint4 *)scalars_dev, (uint32_t)n, (g1a_t *)out_points_dev);
     ZKB_CUDA(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+// Device time of the phases of the last MSM on this context, in ms (call after the MSM returned):
+// out[0] digit extraction + counting sort + task ordering, out[1] bucket accumulation (the IMAD-bound kernel),
+// out[2] oversized-bucket combine, out[3] window reduction, out[4] total; info[0] = n * windows (upper bound of
+// bucket insertions), info[1] = c, info[2] = windows.
+int zkb_msm_last_timing(zkb_ctx *ctx, float out_ms[5], uint64_t info[3]) {
+    if (!ctx || !out_ms) return ZKB_ERR_INVALID;
+    MsmState *st = state(ctx);
+    if (!st->ev_valid) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_last_timing: no MSM has run on this context");
+    ZKB_CUDA(ctx, cudaEventSynchronize(st->ev[4]));
+    for (int k = 0; k < 4; ++k) ZKB_CUDA(ctx, cudaEventElapsedTime(&out_ms[k], st->ev[k], st->ev[k + 1]));
+    ZKB_CUDA(ctx, cudaEventElapsedTime(&out_ms[4], st->ev[0], st->ev[4]));
+    if (info) { info[0] = st->last_entries; info[1] = st->last_c; info[2] = st->last_W; }
     return ZKB_OK;
 }
 

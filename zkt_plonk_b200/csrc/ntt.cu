@@ -254,6 +254,7 @@ int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int 
         unsigned threads = (unsigned)(T / 2 < 32 ? 32 : (T / 2 > 256 ? 256 : T / 2));
         size_t tiles = n >> t;
         ntt_pass_kernel<<<(unsigned)tiles, threads, T * 32, ctx->stream>>>(a);
+        ctx->launches += 1;
         ZKB_CUDA(ctx, cudaGetLastError());
     }
     return ZKB_OK;
