@@ -106,6 +106,42 @@ ZKB_API int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], c
 /* Force the window size c (0 = automatic cost model).  For tests and tuning. */
 ZKB_API int zkb_msm_set_window(zkb_ctx *ctx, int c);
 
+/* ---- grand products, quotient, polynomial utilities (all device-resident, enqueue on the context's stream) -------------- */
+/* compute_z1_poly before its final iFFT (plonk-core/src/permutation/mod.rs:181-254): out[0] = 1,
+ * out[i+1] = out[i] * prod_w (w_i + beta*k_w*omega^i + gamma) / (w_i + beta*sigma_w,i + gamma), i < n-1.
+ * a,b,c,sigma1..3,out: 2^log_n Fr (Montgomery) in HBM; beta, gamma: host, Montgomery.  Follow with zkb_ntt_dev(inverse). */
+ZKB_API int zkb_z1_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t *a,
+                     const uint64_t *b, const uint64_t *c, const uint64_t *sigma1, const uint64_t *sigma2,
+                     const uint64_t *sigma3, uint64_t *out_dev);
+/* compute_z2_poly before its final iFFT (plonk-core/src/lookup/mod.rs:25-82). */
+ZKB_API int zkb_z2_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t delta[4], const uint64_t epsilon[4], const uint64_t *f,
+                     const uint64_t *t, const uint64_t *h1, const uint64_t *h2, uint64_t *out_dev);
+/* 1 if the last grand product on this context hit a zero denominator -- the reference panics there
+ * (`dominator.inverse().unwrap()`, permutation/mod.rs:242, lookup/mod.rs:73); synchronises the stream. */
+ZKB_API int zkb_grand_product_failed(zkb_ctx *ctx);
+/* quotient_poly::compute between its coset FFTs and the final coset iFFT (quotient_poly.rs:98-224):
+ * out[i] = (arith_i + perm_i + lookup_i) / zh(x_i) for i < 4n on the coset 5*<w_4n>.
+ * challenges: alpha, beta, gamma, delta, epsilon (5 x 4 limbs, host, Montgomery).
+ * wit[9]:  z1, z2, a, b, c, pi, t, h1, h2 coset evaluations (4n each, HBM).
+ * epk[11]: q_m, q_l, q_r, q_o, q_c, q_lookup, q_table, sigma1, sigma2, sigma3, l_1 coset tables (4n each, HBM);
+ *          x_coset and zh_coset of the reference's ExtendedProverKey are computed on the fly (zh takes 4 values). */
+ZKB_API int zkb_quotient_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t challenges[20], const uint64_t *const wit[9],
+                           const uint64_t *const epk[11], uint64_t *out_dev);
+/* l_1_coset of extend_prover_key (keys/mod.rs:117-119): 4n values into out_dev. */
+ZKB_API int zkb_l1_coset_dev(zkb_ctx *ctx, unsigned log_n, uint64_t *out_dev);
+/* DensePolynomial::evaluate (linearization_poly.rs:55-75): out = sum_k coeffs[k] z^k; z, out on the host. Synchronous. */
+ZKB_API int zkb_poly_eval_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, size_t n, const uint64_t z[4], uint64_t out[4]);
+/* out[i] = sum_{j<k} scalars[j] * polys[j][i], i < out_len (k <= 16; shorter polynomials are zero-extended):
+ * the axpy chains of linearization_poly.rs:77-111 and SonicKZG10::open's eta-combination. */
+ZKB_API int zkb_poly_lincomb_dev(zkb_ctx *ctx, size_t k, const uint64_t *const *polys_dev, const size_t *lens,
+                         const uint64_t *scalars_host, uint64_t *out_dev, size_t out_len);
+/* kzg10::open's witness polynomial: quot = (p(X) - p(z)) / (X - z) (n-1 coefficients), eval_out = p(z). Synchronous. */
+ZKB_API int zkb_poly_divide_linear_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, size_t n, const uint64_t z[4], uint64_t *quot_dev,
+                               uint64_t eval_out[4]);
+/* add_blinders_to_poly (prove.rs:472-483): coeffs[len+i] = b_i and coeffs[i] -= b_i for i < k (k <= 16);
+ * the buffer must have room for len + k coefficients. */
+ZKB_API int zkb_poly_add_blinders_dev(zkb_ctx *ctx, uint64_t *coeffs_dev, size_t len, const uint64_t *blinders_host, size_t k);
+
 /* ---- test hooks (parity of the device field library against the oracle) ----------------------------------------- */
 /* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a).  Host pointers. */
 ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n);

@@ -59,6 +59,15 @@ def load():
         "zkb_g1_fixed_base_mul_dev": (i, [vp, vp, vp, sz, vp]),
         "zkb_msm_set_window": (i, [vp, i]),
         "zkb_test_fp_binop": (i, [vp, i, i, vp, vp, vp, sz]),
+        "zkb_z1_evals_dev": (i, [vp, u, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "zkb_z2_evals_dev": (i, [vp, u, vp, vp, vp, vp, vp, vp, vp]),
+        "zkb_grand_product_failed": (i, [vp]),
+        "zkb_quotient_evals_dev": (i, [vp, u, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), vp]),
+        "zkb_l1_coset_dev": (i, [vp, u, vp]),
+        "zkb_poly_eval_dev": (i, [vp, vp, sz, vp, vp]),
+        "zkb_poly_lincomb_dev": (i, [vp, sz, ctypes.POINTER(vp), ctypes.POINTER(sz), vp, vp, sz]),
+        "zkb_poly_divide_linear_dev": (i, [vp, vp, sz, vp, vp, vp]),
+        "zkb_poly_add_blinders_dev": (i, [vp, vp, sz, vp, sz]),
         "zkb_launch_count": (ctypes.c_uint64, [vp]),
         "zkb_msm_last_timing": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),
         "zkb_bench_int": (i, [vp, i, ctypes.POINTER(ctypes.c_double)]),

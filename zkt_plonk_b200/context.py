@@ -133,6 +133,55 @@ class Context:
                                                         _dev_ptr(out_dev)))
         return out_dev
 
+    # -- grand products / quotient / polynomial utilities (device-resident)
+    def z1_evals_dev(self, log_n, beta, gamma, a, b, c, s1, s2, s3, out):
+        self._check(self._lib.zkb_z1_evals_dev(self._h, log_n, _host_ptr(beta), _host_ptr(gamma), _dev_ptr(a), _dev_ptr(b),
+                                               _dev_ptr(c), _dev_ptr(s1), _dev_ptr(s2), _dev_ptr(s3), _dev_ptr(out)))
+        return out
+
+    def z2_evals_dev(self, log_n, delta, epsilon, f, t, h1, h2, out):
+        self._check(self._lib.zkb_z2_evals_dev(self._h, log_n, _host_ptr(delta), _host_ptr(epsilon), _dev_ptr(f), _dev_ptr(t),
+                                               _dev_ptr(h1), _dev_ptr(h2), _dev_ptr(out)))
+        return out
+
+    def grand_product_failed(self):
+        return bool(self._lib.zkb_grand_product_failed(self._h))
+
+    def quotient_evals_dev(self, log_n, challenges, wit, epk, out):
+        """challenges: host (5,4) alpha,beta,gamma,delta,epsilon; wit: 9 device tensors (z1,z2,a,b,c,pi,t,h1,h2);
+        epk: 11 device tensors (q_m,q_l,q_r,q_o,q_c,q_lookup,q_table,sigma1,sigma2,sigma3,l1); all 4n elements."""
+        W = (ctypes.c_void_p * 9)(*[_dev_ptr(t).value for t in wit])
+        E = (ctypes.c_void_p * 11)(*[_dev_ptr(t).value for t in epk])
+        self._check(self._lib.zkb_quotient_evals_dev(self._h, log_n, _host_ptr(challenges), W, E, _dev_ptr(out)))
+        return out
+
+    def l1_coset_dev(self, log_n, out):
+        self._check(self._lib.zkb_l1_coset_dev(self._h, log_n, _dev_ptr(out)))
+        return out
+
+    def poly_eval_dev(self, coeffs, n, z):
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(self._lib.zkb_poly_eval_dev(self._h, _dev_ptr(coeffs), n, _host_ptr(z), _host_ptr(out)))
+        return out
+
+    def poly_lincomb_dev(self, polys, lens, scalars, out, out_len):
+        k = len(polys)
+        P = (ctypes.c_void_p * k)(*[_dev_ptr(t).value for t in polys])
+        L = (ctypes.c_size_t * k)(*lens)
+        self._check(self._lib.zkb_poly_lincomb_dev(self._h, k, P, L, _host_ptr(scalars), _dev_ptr(out), out_len))
+        return out
+
+    def poly_divide_linear_dev(self, coeffs, n, z, quot):
+        ev = np.zeros(4, dtype=np.uint64)
+        self._check(self._lib.zkb_poly_divide_linear_dev(self._h, _dev_ptr(coeffs), n, _host_ptr(z), _dev_ptr(quot),
+                                                         _host_ptr(ev)))
+        return ev
+
+    def poly_add_blinders_dev(self, coeffs, length, blinders):
+        self._check(self._lib.zkb_poly_add_blinders_dev(self._h, _dev_ptr(coeffs), length, _host_ptr(blinders),
+                                                        blinders.shape[0]))
+        return coeffs
+
     def launch_count(self):
         return int(self._lib.zkb_launch_count(self._h))
 

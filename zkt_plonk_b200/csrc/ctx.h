@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/zkb200.h"
+#include "host_ff.h"
 
 struct DevBuf {
     void *p = nullptr;
@@ -38,6 +39,7 @@ struct zkb_ctx {
 
     // ---- elementwise / scan kernels (poly.cu)
     DevBuf poly_ws;
+    uint32_t *gp_flag = nullptr; // device flag: a grand product met a zero denominator
 };
 
 #define ZKB_CUDA(ctx, call)                                                                   \
@@ -80,3 +82,8 @@ inline int zkb_reserve(zkb_ctx *ctx, DevBuf &b, size_t bytes) {
 // implemented in ntt.cu / msm.cu / poly.cu
 int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int inverse, int coset);
 void zkb_msm_release(zkb_ctx *ctx);
+// two-level power tables base^e = lo[e & (2^s - 1)] * hi[e >> s], e < 2^lm (Montgomery Fr); hi is pre-scaled by hi_scale
+int zkb_pow2lvl_cached(zkb_ctx *ctx, uint64_t key, unsigned lm, const zkb::host::Fe &base, const zkb::host::Fe &hi_scale,
+                       const void **out, uint32_t *s_out);
+int zkb_pow2lvl_build(zkb_ctx *ctx, void *out, unsigned lm, const zkb::host::Fe &base, const zkb::host::Fe &hi_scale,
+                      uint32_t *s_out);

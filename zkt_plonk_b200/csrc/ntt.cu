@@ -189,6 +189,24 @@ int get_2lvl_table(zkb_ctx *ctx, uint64_t key, unsigned lm, const host::Fe &base
 
 }  // namespace
 
+// shared with poly.cu: cached / caller-owned two-level power tables (lo[2^s] then hi[2^(lm-s)], s = (lm+1)/2)
+int zkb_pow2lvl_cached(zkb_ctx *ctx, uint64_t key, unsigned lm, const zkb::host::Fe &base, const zkb::host::Fe &hi_scale,
+                       const void **out, uint32_t *s_out) {
+    const uint4 *t = nullptr;
+    int rc = get_2lvl_table(ctx, key, lm, base, hi_scale, &t, s_out);
+    *out = t;
+    return rc;
+}
+
+int zkb_pow2lvl_build(zkb_ctx *ctx, void *out, unsigned lm, const zkb::host::Fe &base, const zkb::host::Fe &hi_scale,
+                      uint32_t *s_out) {
+    uint32_t s = (lm + 1) / 2, nlo = 1u << s, nhi = 1u << (lm - s);
+    *s_out = s;
+    int rc = build_pow_table(ctx, (uint4 *)out, base, host::one(host::FR), nlo, 0);
+    if (rc) return rc;
+    return build_pow_table(ctx, (uint4 *)out + 2 * (size_t)nlo, base, hi_scale, nhi, s);
+}
+
 int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int inverse, int coset) {
     if (!d_data) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: null data pointer");
     if (log_n > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ntt: log_n exceeds Fr TWO_ADICITY (28)");
