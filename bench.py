@@ -180,6 +180,11 @@ def run_main(args):
     ctx.g1_fixed_base_mul_dev(G, k, n, P)
     ctx.srs_load(P)
     del k
+    t_pre = time.perf_counter()
+    if not args.no_precompute:
+        ctx.srs_precompute(0)                                      # fixed-base window tables, once per SRS (like PC::trim)
+    torch.cuda.synchronize()
+    t_pre = time.perf_counter() - t_pre
     # ---- scalar sets: resident copies (value) and pinned host copies (e2e)
     host_sets = [torch.from_numpy(uniform_scalars(n, 100 + s + 1000 * rank).view(np.int64)).pin_memory() for s in range(NSETS)]
     dev_sets = [h.to(dev) for h in host_sets]
@@ -265,6 +270,23 @@ def run_main(args):
     # roofline of the dominant kernel: one mixed addition per non-zero digit (n * W, minus a 2^-c fraction),
     # 10 Fq products each (XYZZ madd-2008-s: 8M + 2S), 136 32x32->64 MACs per product, and an IMAD.WIDE MAC
     # occupies the fma pipe for two 32-bit IMAD issue slots (measured: zkb_bench_int mode 1 vs 0).
+    # same MSM without the fixed-base tables (arbitrary-bases path: per-window buckets + host Horner fold)
+    plain_ms = None
+    if not args.no_precompute:
+        ctx.srs_precompute(-1)
+        for w in range(3):
+            ctx.msm(dev_sets[w % NSETS])
+        ts = []
+        for kstep in range(5):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ctx.msm(dev_sets[kstep % NSETS])
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        plain_ms = statistics.mean(ts)
     adds = n * tm["windows"]
     int_ops = adds * 10 * 136 * 2
     acc_s = statistics.mean(acc_ms) * 1e-3
@@ -276,7 +298,9 @@ def run_main(args):
                 "algorithmic_ops_per_launch": int_ops, "window_bits": tm["c"], "windows": tm["windows"]}
 
     # ---- extra: the NTT half of the metric (Fr NTT elems/s), one GPU, 2^22 (= 4n for a 2^20-gate circuit)
-    extra = {}
+    extra = {"msm_fixed_base_tables": {"enabled": not args.no_precompute, "build_seconds_once_per_srs": t_pre,
+                                       "table_bytes": 0 if args.no_precompute else n * 64 * tm["windows"]},
+             "msm_plain_bases_ms_per_step": plain_ms}
     try:
         ln = 22 if log_n >= 20 else log_n + 2
         x = torch.from_numpy(uniform_scalars(1 << ln, 5).view(np.int64)).to(dev)
@@ -324,6 +348,7 @@ def run_main(args):
         "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
         "config": {"workload": f"kzg_commit_g1_msm_2^{log_n}", "points_per_gpu": n, "total_points": world * n,
                    "scalars": "uniform in [0,r), canonical", "curve": "BN254", "l2": "flushed between timed steps (256 MB write)",
+                   "bases": "resident SRS with fixed-base window tables (built once per SRS, not timed)" if not args.no_precompute else "resident SRS, plain bases",
                    "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
                    "parallelism": f"point-range x{world}" if world > 1 else "single GPU"},
         "roofline": roofline, "cpu_baseline": cpu,
@@ -348,6 +373,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", dest="log_n", type=int, default=int(os.environ.get("ZKB_BENCH_LOG_N", "20")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-precompute", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -83,6 +83,10 @@ ZKB_API int zkb_ntt_batch_dev(zkb_ctx *ctx, uint64_t *const *ptrs_host, size_t c
 ZKB_API int zkb_srs_load_g1(zkb_ctx *ctx, const uint64_t *xy_mont_host, size_t n);
 ZKB_API int zkb_srs_load_g1_dev(zkb_ctx *ctx, const uint64_t *xy_mont_dev, size_t n);   /* copies; caller keeps its buffer */
 ZKB_API size_t zkb_srs_size(zkb_ctx *ctx);
+/* Fixed-base window tables for the resident SRS: rows[w][i] = 2^(c*w) * SRS[i] (W x n x 64 B of HBM, built once per
+ * key like PC::trim).  Later MSMs against the SRS feed one shared bucket set and need no window fold.
+ * c > 0: that window size; c == 0: cost model (20 at n = 2^20); c < 0: drop the tables.  Loading a new SRS drops them. */
+ZKB_API int zkb_srs_precompute(zkb_ctx *ctx, int c);
 /* sum_{i<n} scalars[i] * SRS[offset + i]  ->  affine (x, y) Montgomery; *is_inf = 1 and (0,0) for the identity. */
 ZKB_API int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);
 ZKB_API int zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);

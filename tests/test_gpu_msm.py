@@ -123,12 +123,43 @@ def test_resident_srs_offsets_partials_and_commit(ctx):
     assert e.value.code == -4
 
 
+def test_fixed_base_tables_vs_oracle(ctx):
+    """zkb_srs_precompute: shared-bucket MSM over the tables 2^(c*w) * P_i gives the same affine point."""
+    n = 6000
+    dP, P = gpu_points(ctx, n, 61)
+    ctx.srs_load(dP)
+    s_uni, s_skew = cref.rand_fe(cref.FR, n, 62), skewed_scalars(n, 63)
+    rm1 = cref.ints_to_limbs([0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000000])[0]
+    s_uni[5] = rm1
+    s_uni[6] = [0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0]
+    exp_uni, exp_skew = cref.msm_g1(P, s_uni)[0], cref.msm_g1(P, s_skew)[0]
+    exp_off = cref.msm_g1(P[777:], s_uni[: n - 777])[0]
+    for c in (0, 5, 9, 13, 16):
+        ctx.srs_precompute(c)
+        assert np.array_equal(ctx.msm(s_uni)[0], exp_uni), c
+        assert np.array_equal(ctx.msm(to_dev(s_skew))[0], exp_skew), c
+        assert np.array_equal(ctx.msm(s_uni[: n - 777], offset=777)[0], exp_off), c
+        got, inf = ctx.msm(np.zeros((16, 4), dtype=np.uint64))
+        assert inf and not got.any()
+    # a forced window bypasses the tables; dropping them restores the plain path
+    ctx.set_msm_window(11)
+    assert np.array_equal(ctx.msm(s_uni)[0], exp_uni)
+    ctx.set_msm_window(0)
+    ctx.srs_precompute(-1)
+    assert np.array_equal(ctx.msm(s_uni)[0], exp_uni)
+
+
 def test_msm_2_20_vs_oracle(ctx):
     """BASELINE config 2: 2^20 random points and scalars, bit-exact against the VariableBaseMSM restatement."""
     n = 1 << 20
     dP, P = gpu_points(ctx, n, 101)
     ctx.srs_load(dP)
-    for s in (cref.rand_fe(cref.FR, n, 102), skewed_scalars(n, 103)):
-        exp, einf = cref.msm_g1(P, s)
+    cases = [(s, cref.msm_g1(P, s)) for s in (cref.rand_fe(cref.FR, n, 102), skewed_scalars(n, 103))]
+    for s, (exp, einf) in cases:
         got, inf = ctx.msm(s)
         assert inf == einf and np.array_equal(got, exp)
+    ctx.srs_precompute(0)                      # fixed-base tables, c from the cost model (20)
+    for s, (exp, einf) in cases:
+        got, inf = ctx.msm(s)
+        assert inf == einf and np.array_equal(got, exp)
+    ctx.srs_precompute(-1)

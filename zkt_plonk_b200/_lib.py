@@ -50,6 +50,7 @@ def load():
         "zkb_srs_load_g1": (i, [vp, vp, sz]),
         "zkb_srs_load_g1_dev": (i, [vp, vp, sz]),
         "zkb_srs_size": (sz, [vp]),
+        "zkb_srs_precompute": (i, [vp, i]),
         "zkb_msm_g1": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
         "zkb_msm_g1_dev": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
         "zkb_msm_g1_dev_partial": (i, [vp, vp, sz, sz, vp]),

@@ -89,6 +89,10 @@ class Context:
         else:
             self._check(self._lib.zkb_srs_load_g1_dev(self._h, _dev_ptr(points), points.numel() // 8))
 
+    def srs_precompute(self, c=0):
+        """Build (c >= 0) or drop (c < 0) the fixed-base window tables of the resident SRS."""
+        self._check(self._lib.zkb_srs_precompute(self._h, int(c)))
+
     def srs_size(self):
         return int(self._lib.zkb_srs_size(self._h))
 

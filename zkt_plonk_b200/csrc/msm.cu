@@ -12,10 +12,16 @@
 //      equally long loops; one thread accumulates one task in XYZZ coordinates (8M + 2S per point, the
 //      next point's gather is issued before the current addition);
 //   4. tasks of oversized buckets (skewed scalars: zeros/ones/small values) are combined warp-cooperatively;
-//   5. per-window weighted bucket sums: each thread owns a chunk of consecutive buckets (running-sum trick
-//      plus one small scalar multiplication), a CTA tree-reduces the chunks in shared memory;
-//   6. the W window sums (W x 128 B) go to the host, which folds them (Horner, c doublings per window)
+//   5. per-group weighted bucket sums over a dense bucket array: each thread owns a chunk of consecutive
+//      buckets (running-sum trick plus one small scalar multiplication), a CTA tree-reduces the chunks in
+//      shared memory, a second tiny kernel folds the CTA partials;
+//   6. the group sums (<= W x 128 B) go to the host, which folds them (Horner, c doublings per window)
 //      and converts to affine -- O(254) group operations, cheaper there than on one GPU thread.
+//
+// Fixed-base mode (zkb_srs_precompute): for the resident SRS the table T[w][i] = 2^(c*w) * P_i is built once
+// (W x N x 64 B of HBM).  Then every window feeds ONE shared set of 2^(c-1) buckets (entry id = w*N + i), a much
+// larger c pays off (c = 20 at 2^20: 13 windows instead of 16, i.e. 19 % fewer bucket insertions), and the
+// host-side Horner fold disappears.  This trades HBM capacity (180 GB) for integer work.
 //
 // The integer pipe (IMAD.WIDE) bounds step 3; everything else is a few percent of the time.
 #include "ctx.h"
@@ -29,14 +35,16 @@ using namespace zkb;
 namespace {
 
 constexpr uint32_t SEG = 256;            // max points per accumulation task
-constexpr uint32_t RED_CH = 32;          // buckets per thread in the window reduction
+constexpr uint32_t RED_CH = 16;          // buckets per thread in the window reduction
 constexpr uint32_t RED_THREADS = 128;    // threads per CTA in the window reduction
 constexpr uint32_t SIGN_BIT = 0x80000000u;
 
 struct MsmPlan {
-    uint32_t c, W, B;                    // window bits, windows, buckets per window (2^(c-1))
-    uint64_t nbuckets;                   // W * B
-    uint32_t red_ctas_per_window;
+    uint32_t c, W, B;                    // window bits, windows, buckets per group (2^(c-1))
+    uint32_t G;                          // bucket groups: W (one per window) or 1 (fixed-base tables)
+    uint64_t nbuckets;                   // G * B
+    uint32_t red_ctas_per_group;
+    uint32_t id_base, id_stride;         // fixed-base: entry id = id_base + w * id_stride + i
 };
 
 struct MsmWs {                           // carved out of ctx->msm_ws
@@ -46,8 +54,10 @@ struct MsmWs {                           // carved out of ctx->msm_ws
     uint32_t *misc;                      // [0] = heavy bucket count, [1] = total tasks
     uint32_t *heavy_list;
     uint2 *task_order;
-    g1x_t *task_out;
-    g1x_t *win_partial;                  // W * red_ctas_per_window
+    g1x_t *task_out;                     // partial sums of the tasks of multi-task buckets
+    g1x_t *bucket_val;                   // dense: one XYZZ value per bucket (zero = empty)
+    g1x_t *grp_partial;                  // G * red_ctas_per_group
+    g1x_t *grp_sum;                      // G
 };
 
 struct MsmState {
@@ -57,6 +67,7 @@ struct MsmState {
     bool ev_valid = false;
     uint64_t last_entries = 0;           // n * W upper bound of bucket insertions of the last MSM
     uint32_t last_c = 0, last_W = 0;
+    void *fixed_base = nullptr;          // FixedBase* (fixed-base window tables of the resident SRS)
 };
 
 // ------------------------------------------------------------------ digits
@@ -85,23 +96,25 @@ __device__ __forceinline__ void load_scalar(const uint4 *p, size_t i, uint32_t (
     s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
 }
 
-__global__ void msm_count_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t B, uint32_t *counts) {
+// gstride = B when every window has its own bucket group, 0 when all windows share one (fixed-base tables)
+__global__ void msm_count_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t gstride, uint32_t *counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
     load_scalar(scalars, i, s);
-    for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool) { atomicAdd(&counts[w * B + b], 1u); });
+    for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool) { atomicAdd(&counts[w * gstride + b], 1u); });
 }
 
-__global__ void msm_scatter_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t B,
-                                   uint32_t *cursor, uint32_t *sorted) {
+// entry id = id_base + w * id_stride + i  (id_stride = 0: plain bases; = SRS size: fixed-base table rows)
+__global__ void msm_scatter_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t gstride,
+                                   uint32_t id_base, uint32_t id_stride, uint32_t *cursor, uint32_t *sorted) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
     load_scalar(scalars, i, s);
     for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool neg) {
-        uint32_t slot = atomicAdd(&cursor[w * B + b], 1u);
-        sorted[slot] = i | (neg ? SIGN_BIT : 0u);
+        uint32_t slot = atomicAdd(&cursor[w * gstride + b], 1u);
+        sorted[slot] = (id_base + w * id_stride + i) | (neg ? SIGN_BIT : 0u);
     });
 }
 
@@ -202,25 +215,32 @@ __global__ void msm_ntasks_kernel(const uint32_t *counts, uint32_t nb, uint32_t 
     for (uint32_t k = threadIdx.x; k <= SEG; k += blockDim.x) if (h[k]) atomicAdd(&size_hist[k], h[k]);
 }
 
-__global__ void msm_task_scatter_kernel(const uint32_t *counts, const uint32_t *ntasks, uint32_t nb,
-                                        uint32_t *size_cursor, uint2 *task_order) {
+// Tasks ordered by descending size.  A CTA ranks its tasks per size bin in shared memory and reserves one global
+// range per (CTA, bin), so the global atomics are few and spread (a per-task atomic on ~40 hot bins cost 100 us).
+__global__ void __launch_bounds__(256) msm_task_scatter_kernel(const uint32_t *counts, const uint32_t *ntasks, uint32_t nb,
+                                                               uint32_t *size_cursor, uint2 *task_order) {
+    __shared__ uint32_t h[SEG + 1], base[SEG + 1];
+    for (uint32_t k = threadIdx.x; k <= SEG; k += blockDim.x) h[k] = 0;
+    __syncthreads();
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    uint32_t nt = ntasks[b];
-    if (!nt) return;
-    uint32_t cnt = counts[b];
-    for (uint32_t s = 0; s < nt; ++s) {
-        uint32_t size = min(SEG, cnt - s * SEG);
-        uint32_t pos = atomicAdd(&size_cursor[SEG - size], 1u);
-        task_order[pos] = make_uint2(b, s);
-    }
+    uint32_t nt = b < nb ? ntasks[b] : 0, cnt = nt ? counts[b] : 0;
+    uint32_t full = cnt / SEG, rem = cnt - full * SEG;
+    uint32_t rank_full = 0, rank_rem = 0;
+    if (full) rank_full = atomicAdd(&h[0], full);             // bin = SEG - size
+    if (rem) rank_rem = atomicAdd(&h[SEG - rem], 1u);
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k <= SEG; k += blockDim.x) base[k] = h[k] ? atomicAdd(&size_cursor[k], h[k]) : 0;
+    __syncthreads();
+    for (uint32_t s = 0; s < full; ++s) task_order[base[0] + rank_full + s] = make_uint2(b, s);
+    if (rem) task_order[base[SEG - rem] + rank_rem] = make_uint2(b, full);
 }
 
 // ------------------------------------------------------------------ bucket accumulation (the hot kernel)
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__restrict__ points, const uint32_t *__restrict__ sorted,
                                                              const uint32_t *__restrict__ counts, const uint32_t *__restrict__ starts,
-                                                             const uint32_t *__restrict__ task_base, const uint2 *__restrict__ task_order,
-                                                             const uint32_t *__restrict__ misc, g1x_t *__restrict__ task_out) {
+                                                             const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_base,
+                                                             const uint2 *__restrict__ task_order, const uint32_t *__restrict__ misc,
+                                                             g1x_t *__restrict__ task_out, g1x_t *__restrict__ bucket_val) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= misc[1]) return;
     uint2 task = task_order[t];
@@ -243,7 +263,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__rest
         v = vn;
         p = pn;
     }
-    g1x_store(task_out + task_base[b] + s, acc);
+    g1x_store(ntasks[b] == 1 ? bucket_val + b : task_out + task_base[b] + s, acc);
 }
 
 // one warp per oversized bucket: lanes stride over the bucket's task results, shuffle tree at the end
@@ -261,13 +281,13 @@ __device__ __forceinline__ g1x_t shfl_down_g1x(const g1x_t &p, int d) {
 
 __global__ void __launch_bounds__(128) msm_combine_heavy_kernel(const uint32_t *misc, const uint32_t *heavy_list,
                                                                 const uint32_t *ntasks, const uint32_t *task_base,
-                                                                g1x_t *task_out) {
+                                                                const g1x_t *task_out, g1x_t *bucket_val) {
     uint32_t lane = threadIdx.x & 31;
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     uint32_t nheavy = misc[0];
     for (uint32_t h = warp; h < nheavy; h += nwarps) {
         uint32_t b = heavy_list[h], nt = ntasks[b];
-        g1x_t *base = task_out + task_base[b];
+        const g1x_t *base = task_out + task_base[b];
         g1x_t acc = g1x_inf();
         for (uint32_t k = lane; k < nt; k += 32) g1x_add(acc, g1x_load(base + k));
         for (int d = 16; d >= 1; d >>= 1) {
@@ -275,7 +295,7 @@ __global__ void __launch_bounds__(128) msm_combine_heavy_kernel(const uint32_t *
             if (lane < (uint32_t)d) g1x_add(acc, o);
         }
         __syncwarp();
-        if (lane == 0) g1x_store(base, acc);
+        if (lane == 0) g1x_store(bucket_val + b, acc);
     }
 }
 
@@ -290,21 +310,25 @@ __device__ __noinline__ g1x_t g1x_mul_small(const g1x_t &p, uint32_t k) {
     return acc;
 }
 
-// grid = W * ctas_per_window CTAs of RED_THREADS threads; thread owns RED_CH consecutive buckets of one window
-__global__ void __launch_bounds__(RED_THREADS) msm_reduce_kernel(const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_base,
-                                                                 const g1x_t *__restrict__ task_out, uint32_t B, uint32_t ctas_per_window,
-                                                                 g1x_t *__restrict__ win_partial) {
+// grid = G * ctas_per_group CTAs of RED_THREADS threads; a thread owns RED_CH consecutive buckets of one group.
+// bucket_val is dense, so all loads of a chunk are independent of each other and issue up front.
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_kernel(const g1x_t *__restrict__ bucket_val, uint32_t B, uint32_t ctas_per_group,
+                                                                 g1x_t *__restrict__ grp_partial) {
     __shared__ g1x_t sm[RED_THREADS];
-    uint32_t w = blockIdx.x / ctas_per_window, cw = blockIdx.x % ctas_per_window;
-    uint32_t chunk = cw * RED_THREADS + threadIdx.x;          // chunk index inside the window
+    uint32_t g = blockIdx.x / ctas_per_group, cw = blockIdx.x % ctas_per_group;
+    uint32_t chunk = cw * RED_THREADS + threadIdx.x;          // chunk index inside the group
     uint32_t lo = chunk * RED_CH;                               // first bucket (digit value lo + 1)
     g1x_t run = g1x_inf(), acc = g1x_inf();
     if (lo < B) {
         uint32_t hi = min(lo + RED_CH, B);
+        const g1x_t *src = bucket_val + (size_t)g * B;
+        g1x_t cur = g1x_load(src + hi - 1);
         for (uint32_t j = hi; j-- > lo;) {
-            uint32_t b = w * B + j;
-            if (ntasks[b]) g1x_add(run, g1x_load(task_out + task_base[b]));
+            g1x_t nxt = cur;
+            if (j > lo) nxt = g1x_load(src + j - 1);            // prefetch the next bucket
+            g1x_add(run, cur);
             g1x_add(acc, run);                                  // acc = sum_j (j - lo + 1) * bucket_j
+            cur = nxt;
         }
         g1x_t shifted = g1x_mul_small(run, lo);                // + lo * sum_j bucket_j
         g1x_add(acc, shifted);
@@ -318,7 +342,43 @@ __global__ void __launch_bounds__(RED_THREADS) msm_reduce_kernel(const uint32_t 
             sm[threadIdx.x] = a;
         }
     }
-    if (threadIdx.x == 0) g1x_store(win_partial + blockIdx.x, sm[0]);
+    if (threadIdx.x == 0) g1x_store(grp_partial + blockIdx.x, sm[0]);
+}
+
+// one CTA per group: folds the group's CTA partials into one point
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_final_kernel(const g1x_t *__restrict__ grp_partial, uint32_t ctas_per_group,
+                                                                       g1x_t *__restrict__ grp_sum) {
+    __shared__ g1x_t sm[RED_THREADS];
+    const g1x_t *src = grp_partial + (size_t)blockIdx.x * ctas_per_group;
+    g1x_t acc = g1x_inf();
+    for (uint32_t k = threadIdx.x; k < ctas_per_group; k += RED_THREADS) g1x_add(acc, g1x_load(src + k));
+    sm[threadIdx.x] = acc;
+    for (uint32_t stride = RED_THREADS / 2; stride >= 1; stride >>= 1) {
+        __syncthreads();
+        if (threadIdx.x < stride && threadIdx.x + stride < ctas_per_group) {
+            g1x_t a = sm[threadIdx.x];
+            g1x_add(a, sm[threadIdx.x + stride]);
+            sm[threadIdx.x] = a;
+        }
+    }
+    if (threadIdx.x == 0) g1x_store(grp_sum + blockIdx.x, sm[0]);
+}
+
+// Fixed-base table: rows[w][i] = 2^(c*w) * P_i (affine), w < W.  One thread per point walks the windows.
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const g1a_t *__restrict__ points, uint32_t n, uint32_t c, uint32_t W,
+                                                             g1a_t *__restrict__ rows) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1a_t p = g1a_load(points + i);
+    fstore(&rows[i].x, p.x);
+    fstore(&rows[i].y, p.y);
+    g1x_t acc = g1x_from_affine(p);
+    for (uint32_t w = 1; w < W; ++w) {
+        for (uint32_t k = 0; k < c; ++k) acc = g1x_double(acc);
+        g1a_t a = g1x_to_affine(acc);
+        fstore(&rows[(size_t)w * n + i].x, a.x);
+        fstore(&rows[(size_t)w * n + i].y, a.y);
+    }
 }
 
 // ------------------------------------------------------------------ helpers: SRS generation, scalar conversion
@@ -391,37 +451,55 @@ inline void to_affine(const Pt &p, uint64_t out_xy[8], int *is_inf_out) {
 }  // namespace hec
 
 // ------------------------------------------------------------------ planning / workspace
-MsmPlan make_plan(size_t n, int force_c) {
-    MsmPlan pl;
+struct FixedBase {                       // fixed-base tables of the resident SRS (owned by MsmState)
+    DevBuf rows;                         // W x n affine points, row w = 2^(c*w) * SRS
+    uint32_t c = 0, W = 0;
+    size_t n = 0;
+};
+
+uint32_t pick_window(size_t n, bool shared_buckets) {
     uint32_t best_c = 8;
     double best = 1e300;
-    for (uint32_t c = 6; c <= 20; ++c) {
+    for (uint32_t c = 6; c <= 22; ++c) {
         uint32_t W = 254 / c + 1;
-        double cost = (double)n * W + 3.0 * W * (double)(1u << (c - 1));
+        double groups = shared_buckets ? 1.0 : (double)W;
+        double cost = (double)n * W + 3.0 * groups * (double)(1u << (c - 1));
         if (cost < best) { best = cost; best_c = c; }
     }
-    pl.c = force_c > 0 ? (uint32_t)force_c : best_c;
-    pl.W = 254 / pl.c + 1;
+    return best_c;
+}
+
+MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset) {
+    MsmPlan pl;
+    if (fb) {
+        pl.c = fb->c; pl.W = fb->W; pl.G = 1;
+        pl.id_base = (uint32_t)offset; pl.id_stride = (uint32_t)fb->n;
+    } else {
+        pl.c = force_c > 0 ? (uint32_t)force_c : pick_window(n, false);
+        pl.W = 254 / pl.c + 1; pl.G = pl.W;
+        pl.id_base = 0; pl.id_stride = 0;
+    }
     pl.B = 1u << (pl.c - 1);
-    pl.nbuckets = (uint64_t)pl.W * pl.B;
+    pl.nbuckets = (uint64_t)pl.G * pl.B;
     uint32_t chunks = (pl.B + RED_CH - 1) / RED_CH;
-    pl.red_ctas_per_window = (chunks + RED_THREADS - 1) / RED_THREADS;
+    pl.red_ctas_per_group = (chunks + RED_THREADS - 1) / RED_THREADS;
     return pl;
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int carve_ws(zkb_ctx *ctx, const MsmPlan &pl, size_t n, MsmWs &ws, uint64_t *max_tasks_out) {
+int carve_ws(zkb_ctx *ctx, const MsmPlan &pl, size_t n, MsmWs &ws, uint64_t *max_tasks_out, uint64_t *max_heavy_tasks_out) {
     const uint64_t nb = pl.nbuckets;
     const uint64_t entries = (uint64_t)n * pl.W;
     const uint64_t max_tasks = nb + entries / SEG + 1;
+    const uint64_t max_heavy_tasks = 2 * (entries / SEG) + 2;      // tasks of buckets with more than SEG points
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_counts = take(nb * 4), o_starts = take(nb * 4), o_cursor = take(nb * 4), o_ntasks = take(nb * 4),
-           o_tbase = take(nb * 4), o_sorted = take(entries * 4), o_scan = take((nb / SCAN_TILE + 2) * 4),
+           o_tbase = take(nb * 4), o_sorted = take(entries * 4 + 4), o_scan = take((nb / SCAN_TILE + 2) * 4),
            o_hist = take((SEG + 1) * 4), o_hcur = take((SEG + 1) * 4), o_misc = take(64), o_heavy = take(nb * 4),
-           o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)),
-           o_win = take((size_t)pl.W * pl.red_ctas_per_window * sizeof(g1x_t));
+           o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)), o_bval = take(nb * sizeof(g1x_t)),
+           o_part = take((size_t)pl.G * pl.red_ctas_per_group * sizeof(g1x_t)), o_sum = take((size_t)pl.G * sizeof(g1x_t));
     int rc = zkb_reserve(ctx, ctx->msm_ws, off);
     if (rc) return rc;
     char *p = (char *)ctx->msm_ws.p;
@@ -429,8 +507,10 @@ int carve_ws(zkb_ctx *ctx, const MsmPlan &pl, size_t n, MsmWs &ws, uint64_t *max
     ws.ntasks = (uint32_t *)(p + o_ntasks); ws.task_base = (uint32_t *)(p + o_tbase); ws.sorted = (uint32_t *)(p + o_sorted);
     ws.scan_tmp = (uint32_t *)(p + o_scan); ws.size_hist = (uint32_t *)(p + o_hist); ws.size_cursor = (uint32_t *)(p + o_hcur);
     ws.misc = (uint32_t *)(p + o_misc); ws.heavy_list = (uint32_t *)(p + o_heavy); ws.task_order = (uint2 *)(p + o_order);
-    ws.task_out = (g1x_t *)(p + o_out); ws.win_partial = (g1x_t *)(p + o_win);
+    ws.task_out = (g1x_t *)(p + o_out); ws.bucket_val = (g1x_t *)(p + o_bval);
+    ws.grp_partial = (g1x_t *)(p + o_part); ws.grp_sum = (g1x_t *)(p + o_sum);
     *max_tasks_out = max_tasks;
+    *max_heavy_tasks_out = max_heavy_tasks;
     return ZKB_OK;
 }
 
@@ -439,17 +519,19 @@ MsmState *state(zkb_ctx *ctx) {
     return (MsmState *)ctx->msm_state;
 }
 
-// Enqueue the whole MSM on ctx->stream; the W*ctas window partial sums end up in st->pinned.
-int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, size_t n, int force_c, MsmPlan *plan_out) {
+// Enqueue the whole MSM on ctx->stream; the G group sums end up in st->pinned.
+// fb == nullptr: bases are d_points[0..n); else: bases are fb rows, ids offset by `offset`.
+int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, size_t n, int force_c, const FixedBase *fb,
+                size_t offset, MsmPlan *plan_out) {
     if (n >= (1ull << 31)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n must be < 2^31");
-    MsmPlan pl = make_plan(n, force_c);
+    MsmPlan pl = make_plan(n, force_c, fb, offset);
     if ((uint64_t)n * pl.W >= (1ull << 32)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n * windows must be < 2^32");
     MsmWs ws;
-    uint64_t max_tasks;
-    int rc = carve_ws(ctx, pl, n, ws, &max_tasks);
+    uint64_t max_tasks, max_heavy;
+    int rc = carve_ws(ctx, pl, n, ws, &max_tasks, &max_heavy);
     if (rc) return rc;
     MsmState *st = state(ctx);
-    size_t out_bytes = (size_t)pl.W * pl.red_ctas_per_window * sizeof(g1x_t);
+    size_t out_bytes = (size_t)pl.G * sizeof(g1x_t);
     if (st->pinned_bytes < out_bytes) {
         if (st->pinned) cudaFreeHost(st->pinned);
         ZKB_CUDA(ctx, cudaMallocHost(&st->pinned, out_bytes));
@@ -457,6 +539,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     }
     cudaStream_t s = ctx->stream;
     const uint32_t nb = (uint32_t)pl.nbuckets, n32 = (uint32_t)n;
+    const uint32_t gstride = pl.G == 1 ? 0 : pl.B;
     if (!st->ev[0]) for (int k = 0; k < 5; ++k) ZKB_CUDA(ctx, cudaEventCreate(&st->ev[k]));
     st->last_entries = (uint64_t)n * pl.W; st->last_c = pl.c; st->last_W = pl.W;
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[0], s));
@@ -464,11 +547,13 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.counts, 0, (size_t)nb * 4, s));
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.size_hist, 0, (SEG + 1) * 4, s));
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.misc, 0, 64, s));
-    if (n32) msm_count_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.B, ws.counts);
+    ZKB_CUDA(ctx, cudaMemsetAsync(ws.bucket_val, 0, (size_t)nb * sizeof(g1x_t), s));
+    if (n32) msm_count_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, gstride, ws.counts);
     rc = exclusive_scan(ctx, ws.counts, ws.starts, nb, ws.scan_tmp, nullptr);
     if (rc) return rc;
     ZKB_CUDA(ctx, cudaMemcpyAsync(ws.cursor, ws.starts, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
-    if (n32) msm_scatter_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.B, ws.cursor, ws.sorted);
+    if (n32) msm_scatter_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, gstride, pl.id_base, pl.id_stride,
+                                                                  ws.cursor, ws.sorted);
     msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, nb, ws.ntasks, ws.size_hist, ws.misc, ws.heavy_list);
     rc = exclusive_scan(ctx, ws.ntasks, ws.task_base, nb, ws.scan_tmp, ws.misc + 1);
     if (rc) return rc;
@@ -476,30 +561,36 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     if (rc) return rc;
     msm_task_scatter_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, ws.ntasks, nb, ws.size_cursor, ws.task_order);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[1], s));
-    msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, ws.sorted, ws.counts, ws.starts,
-                                                                             ws.task_base, ws.task_order, ws.misc, ws.task_out);
+    msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, ws.sorted, ws.counts, ws.starts, ws.ntasks,
+                                                                             ws.task_base, ws.task_order, ws.misc, ws.task_out,
+                                                                             ws.bucket_val);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[2], s));
-    msm_combine_heavy_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out);
+    msm_combine_heavy_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out,
+                                                               ws.bucket_val);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[3], s));
-    msm_reduce_kernel<<<pl.W * pl.red_ctas_per_window, RED_THREADS, 0, s>>>(ws.ntasks, ws.task_base, ws.task_out, pl.B,
-                                                                            pl.red_ctas_per_window, ws.win_partial);
+    msm_reduce_kernel<<<pl.G * pl.red_ctas_per_group, RED_THREADS, 0, s>>>(ws.bucket_val, pl.B, pl.red_ctas_per_group, ws.grp_partial);
+    msm_reduce_final_kernel<<<pl.G, RED_THREADS, 0, s>>>(ws.grp_partial, pl.red_ctas_per_group, ws.grp_sum);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], s));
     ZKB_CUDA(ctx, cudaGetLastError());
     st->ev_valid = true;
-    ctx->launches += 16;                 // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy, reduce
-    ZKB_CUDA(ctx, cudaMemcpyAsync(st->pinned, ws.win_partial, out_bytes, cudaMemcpyDeviceToHost, s));
+    ctx->launches += 17;                 // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy, reduce x 2
+    ZKB_CUDA(ctx, cudaMemcpyAsync(st->pinned, ws.grp_sum, out_bytes, cudaMemcpyDeviceToHost, s));
     *plan_out = pl;
     return ZKB_OK;
 }
 
-// wait for the stream, fold the window sums on the host; result in XYZZ
+// wait for the stream, fold the group sums on the host; result in XYZZ
 int msm_finish(zkb_ctx *ctx, const MsmPlan &pl, hec::Pt *out) {
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const hec::Pt *part = (const hec::Pt *)state(ctx)->pinned;
     hec::Pt total = hec::inf();
-    for (uint32_t w = pl.W; w-- > 0;) {
-        for (uint32_t k = 0; k < pl.c; ++k) total = hec::dbl(total);
-        for (uint32_t k = 0; k < pl.red_ctas_per_window; ++k) total = hec::add(total, part[w * pl.red_ctas_per_window + k]);
+    if (pl.G == 1) {
+        total = part[0];
+    } else {
+        for (uint32_t w = pl.W; w-- > 0;) {
+            for (uint32_t k = 0; k < pl.c; ++k) total = hec::dbl(total);
+            total = hec::add(total, part[w]);
+        }
     }
     *out = total;
     return ZKB_OK;
@@ -512,11 +603,18 @@ void zkb_msm_release(zkb_ctx *ctx) {
     if (!st) return;
     if (st->pinned) cudaFreeHost(st->pinned);
     for (int k = 0; k < 5; ++k) if (st->ev[k]) cudaEventDestroy(st->ev[k]);
+    if (st->fixed_base) {
+        FixedBase *fb = (FixedBase *)st->fixed_base;
+        if (fb->rows.p) cudaFree(fb->rows.p);
+        delete fb;
+    }
     delete st;
     ctx->msm_state = nullptr;
 }
 
 extern "C" {
+
+int zkb_srs_precompute(zkb_ctx *ctx, int c);
 
 int zkb_srs_load_g1(zkb_ctx *ctx, const uint64_t *xy_mont_host, size_t n) {
     if (!ctx) return ZKB_ERR_INVALID;
@@ -526,6 +624,7 @@ int zkb_srs_load_g1(zkb_ctx *ctx, const uint64_t *xy_mont_host, size_t n) {
     ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->srs.p, xy_mont_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->srs_n = n;
+    zkb_srs_precompute(ctx, -1);
     return ZKB_OK;
 }
 
@@ -537,10 +636,43 @@ int zkb_srs_load_g1_dev(zkb_ctx *ctx, const uint64_t *xy_mont_dev, size_t n) {
     ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->srs.p, xy_mont_dev, n * 64, cudaMemcpyDeviceToDevice, ctx->stream));
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->srs_n = n;
+    zkb_srs_precompute(ctx, -1);
     return ZKB_OK;
 }
 
 size_t zkb_srs_size(zkb_ctx *ctx) { return ctx ? ctx->srs_n : 0; }
+
+// Build (c > 0: with that window size, c == 0: cost model) or drop (c < 0) the fixed-base tables of the resident SRS.
+int zkb_srs_precompute(zkb_ctx *ctx, int c) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    MsmState *st = state(ctx);
+    if (st->fixed_base) {
+        FixedBase *old = (FixedBase *)st->fixed_base;
+        ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (old->rows.p) cudaFree(old->rows.p);
+        delete old;
+        st->fixed_base = nullptr;
+    }
+    if (c < 0) return ZKB_OK;
+    if (c == 1 || c > 24) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_precompute: window size out of range");
+    const size_t n = ctx->srs_n;
+    if (n == 0) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_srs_precompute: no SRS loaded");
+    FixedBase *fb = new FixedBase();
+    fb->c = c > 0 ? (uint32_t)c : pick_window(n, true);
+    fb->W = 254 / fb->c + 1;
+    fb->n = n;
+    if ((uint64_t)n * fb->W >= (1ull << 31)) { delete fb; ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_precompute: n * windows must be < 2^31"); }
+    int rc = zkb_reserve(ctx, fb->rows, (size_t)fb->W * n * sizeof(g1a_t));
+    if (rc) { delete fb; return rc; }
+    msm_precompute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const g1a_t *)ctx->srs.p, (uint32_t)n, fb->c, fb->W,
+                                                                                (g1a_t *)fb->rows.p);
+    ctx->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(fb->rows.p); delete fb; ctx->err = cudaGetErrorString(e); return ZKB_ERR_CUDA; }
+    st->fixed_base = fb;
+    return ZKB_OK;
+}
 
 int zkb_msm_set_window(zkb_ctx *ctx, int c) {
     if (!ctx || c < 0 || c > 24 || c == 1) return ZKB_ERR_INVALID;
@@ -555,7 +687,10 @@ int zkb_msm_g1_dev_partial(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t off
     if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_msm: offset + n exceeds the loaded SRS");
     if (!scalars_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: null scalars");
     MsmPlan pl;
-    int rc = msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + offset, (const uint4 *)scalars_dev, n, ctx->msm_force_c, &pl);
+    const FixedBase *fb = (const FixedBase *)state(ctx)->fixed_base;
+    if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;      // forced window: plain path
+    int rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, (const uint4 *)scalars_dev, n, 0, fb, offset, &pl)
+                : msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + offset, (const uint4 *)scalars_dev, n, ctx->msm_force_c, nullptr, 0, &pl);
     if (rc) return rc;
     hec::Pt total;
     rc = msm_finish(ctx, pl, &total);
@@ -595,7 +730,7 @@ int zkb_msm_g1_bases(zkb_ctx *ctx, const uint64_t *points_host, const uint64_t *
     ZKB_CUDA(ctx, cudaMemcpyAsync(d_pts, points_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
     ZKB_CUDA(ctx, cudaMemcpyAsync(d_sc, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     MsmPlan pl;
-    rc = msm_enqueue(ctx, (const g1a_t *)d_pts, (const uint4 *)d_sc, n, ctx->msm_force_c, &pl);
+    rc = msm_enqueue(ctx, (const g1a_t *)d_pts, (const uint4 *)d_sc, n, ctx->msm_force_c, nullptr, 0, &pl);
     if (rc) return rc;
     hec::Pt total;
     rc = msm_finish(ctx, pl, &total);
