@@ -50,7 +50,7 @@ for log_n in (16, 18, 20, 22):
         best, med = timeit(lambda: ctx.msm(s), reps=5, warm=2)
         print(f"msm 2^{log_n} c={c}: {best:.3f} ms best, {med:.3f} med, {n/best/1e3:.1f} Mpts/s", flush=True)
     ctx.set_msm_window(0)
-    for c in (0, 18, 19, 21):
+    for c in (0, 16, 18, 19, 20, 22):
         t0 = time.time(); ctx.srs_precompute(c); torch.cuda.synchronize(); tp = time.time() - t0
         best, med = timeit(lambda: ctx.msm(s), reps=5, warm=2)
         tm = ctx.msm_last_timing()

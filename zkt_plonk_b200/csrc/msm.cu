@@ -42,6 +42,7 @@ constexpr uint32_t SIGN_BIT = 0x80000000u;
 struct MsmPlan {
     uint32_t c, W, B;                    // window bits, windows, buckets per group (2^(c-1))
     uint32_t G;                          // bucket groups: W (one per window) or 1 (fixed-base tables)
+    uint32_t wide;                       // windows [0, wide) are c bits wide, the others c - 1 (wide = W: uniform)
     uint64_t nbuckets;                   // G * B
     uint32_t red_ctas_per_group;
     uint32_t id_base, id_stride;         // fixed-base: entry id = id_base + w * id_stride + i
@@ -72,14 +73,18 @@ struct MsmState {
 
 // ------------------------------------------------------------------ digits
 // Signed c-bit digits of a canonical 254-bit scalar.  Calls f(w, bucket_in_window, negative) for non-zero digits.
+// Window w covers bits [start_w, start_w + width_w): the first `wide` windows are c bits wide, the rest c - 1
+// (wide = W: uniform c-bit windows).  Balanced widths keep every window's digit spread over the whole bucket range.
 template <class F>
-__device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], uint32_t c, uint32_t W, F f) {
-    uint32_t carry = 0;
-    const uint32_t half = 1u << (c - 1), full = 1u << c;
+__device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], uint32_t c, uint32_t W, uint32_t wide, F f) {
+    uint32_t carry = 0, bit = 0;
     for (uint32_t w = 0; w < W; ++w) {
-        uint32_t bit = w * c, limb = bit >> 5, off = bit & 31;
+        const uint32_t width = w < wide ? c : c - 1;
+        const uint32_t half = 1u << (width - 1), full = 1u << width;
+        uint32_t limb = bit >> 5, off = bit & 31;
         uint32_t lo = limb < 8 ? s[limb] : 0, hi = limb + 1 < 8 ? s[limb + 1] : 0;
         uint32_t raw = (uint32_t)((((uint64_t)hi << 32) | lo) >> off) & (full - 1);
+        bit += width;
         raw += carry;
         if (raw > half) {
             carry = 1;                            // digit = raw - 2^c <= 0
@@ -97,22 +102,22 @@ __device__ __forceinline__ void load_scalar(const uint4 *p, size_t i, uint32_t (
 }
 
 // gstride = B when every window has its own bucket group, 0 when all windows share one (fixed-base tables)
-__global__ void msm_count_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t gstride, uint32_t *counts) {
+__global__ void msm_count_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, uint32_t gstride, uint32_t *counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
     load_scalar(scalars, i, s);
-    for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool) { atomicAdd(&counts[w * gstride + b], 1u); });
+    for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t b, bool) { atomicAdd(&counts[w * gstride + b], 1u); });
 }
 
 // entry id = id_base + w * id_stride + i  (id_stride = 0: plain bases; = SRS size: fixed-base table rows)
-__global__ void msm_scatter_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t gstride,
+__global__ void msm_scatter_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, uint32_t gstride,
                                    uint32_t id_base, uint32_t id_stride, uint32_t *cursor, uint32_t *sorted) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
     load_scalar(scalars, i, s);
-    for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool neg) {
+    for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t b, bool neg) {
         uint32_t slot = atomicAdd(&cursor[w * gstride + b], 1u);
         sorted[slot] = (id_base + w * id_stride + i) | (neg ? SIGN_BIT : 0u);
     });
@@ -279,6 +284,9 @@ __device__ __forceinline__ g1x_t shfl_down_g1x(const g1x_t &p, int d) {
     return r;
 }
 
+constexpr uint32_t HEAVY_CTA_MIN = 64;   // buckets with more tasks than this are folded by a whole CTA
+
+// buckets with 2..HEAVY_CTA_MIN tasks: one warp each, lanes stride over the task results, shuffle tree at the end
 __global__ void __launch_bounds__(128) msm_combine_heavy_kernel(const uint32_t *misc, const uint32_t *heavy_list,
                                                                 const uint32_t *ntasks, const uint32_t *task_base,
                                                                 const g1x_t *task_out, g1x_t *bucket_val) {
@@ -287,15 +295,43 @@ __global__ void __launch_bounds__(128) msm_combine_heavy_kernel(const uint32_t *
     uint32_t nheavy = misc[0];
     for (uint32_t h = warp; h < nheavy; h += nwarps) {
         uint32_t b = heavy_list[h], nt = ntasks[b];
+        if (nt > HEAVY_CTA_MIN) continue;
         const g1x_t *base = task_out + task_base[b];
         g1x_t acc = g1x_inf();
         for (uint32_t k = lane; k < nt; k += 32) g1x_add(acc, g1x_load(base + k));
         for (int d = 16; d >= 1; d >>= 1) {
+            if ((uint32_t)d >= nt) continue;                     // uniform across the warp
             g1x_t o = shfl_down_g1x(acc, d);
             if (lane < (uint32_t)d) g1x_add(acc, o);
         }
         __syncwarp();
         if (lane == 0) g1x_store(bucket_val + b, acc);
+    }
+}
+
+// giant buckets (skewed scalars: zeros / ones / small values pile up on a few digits): one CTA each
+__global__ void __launch_bounds__(128) msm_combine_giant_kernel(const uint32_t *misc, const uint32_t *heavy_list,
+                                                                const uint32_t *ntasks, const uint32_t *task_base,
+                                                                const g1x_t *task_out, g1x_t *bucket_val) {
+    __shared__ g1x_t sm[128];
+    uint32_t nheavy = misc[0];
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        uint32_t b = heavy_list[h], nt = ntasks[b];
+        if (nt <= HEAVY_CTA_MIN) continue;                       // uniform across the CTA
+        const g1x_t *base = task_out + task_base[b];
+        g1x_t acc = g1x_inf();
+        for (uint32_t k = threadIdx.x; k < nt; k += 128) g1x_add(acc, g1x_load(base + k));
+        sm[threadIdx.x] = acc;
+        for (uint32_t stride = 64; stride >= 1; stride >>= 1) {
+            __syncthreads();
+            if (threadIdx.x < stride) {
+                g1x_t a = sm[threadIdx.x];
+                g1x_add(a, sm[threadIdx.x + stride]);
+                sm[threadIdx.x] = a;
+            }
+        }
+        if (threadIdx.x == 0) g1x_store(bucket_val + b, sm[0]);
+        __syncthreads();
     }
 }
 
@@ -366,7 +402,7 @@ __global__ void __launch_bounds__(RED_THREADS) msm_reduce_final_kernel(const g1x
 
 // Fixed-base table: rows[w][i] = 2^(c*w) * P_i (affine), w < W.  One thread per point walks the windows.
 __global__ void __launch_bounds__(128) msm_precompute_kernel(const g1a_t *__restrict__ points, uint32_t n, uint32_t c, uint32_t W,
-                                                             g1a_t *__restrict__ rows) {
+                                                             uint32_t wide, g1a_t *__restrict__ rows) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1a_t p = g1a_load(points + i);
@@ -374,7 +410,8 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const g1a_t *__rest
     fstore(&rows[i].y, p.y);
     g1x_t acc = g1x_from_affine(p);
     for (uint32_t w = 1; w < W; ++w) {
-        for (uint32_t k = 0; k < c; ++k) acc = g1x_double(acc);
+        const uint32_t width = (w - 1) < wide ? c : c - 1;      // width of the window below this row
+        for (uint32_t k = 0; k < width; ++k) acc = g1x_double(acc);
         g1a_t a = g1x_to_affine(acc);
         fstore(&rows[(size_t)w * n + i].x, a.x);
         fstore(&rows[(size_t)w * n + i].y, a.y);
@@ -453,17 +490,31 @@ inline void to_affine(const Pt &p, uint64_t out_xy[8], int *is_inf_out) {
 // ------------------------------------------------------------------ planning / workspace
 struct FixedBase {                       // fixed-base tables of the resident SRS (owned by MsmState)
     DevBuf rows;                         // W x n affine points, row w = 2^(c*w) * SRS
-    uint32_t c = 0, W = 0;
+    uint32_t c = 0, W = 0, wide = 0;
     size_t n = 0;
 };
 
+// Balanced fixed-base windows: W = ceil(255 / c) windows, the first *wide of width c and the rest c - 1, so that
+// no window is left with only a few bits (a 2-bit top window would pile n/4 points on each of 4 buckets).
+uint32_t balanced_windows(uint32_t c, uint32_t *wide) {
+    // widths must sum to >= 255: 254 scalar bits plus one spare bit, so that the top window's raw value plus the
+    // incoming carry never exceeds half of its range (no carry out of the top window)
+    const uint32_t BITS = 255;
+    uint32_t W = (BITS + c - 1) / c;                           // fewest c-bit windows that cover BITS
+    uint32_t slack = W * c - BITS;                              // bits to give back by narrowing windows to c - 1
+    *wide = W - (slack < W ? slack : W);
+    return W;
+}
+
+// Cost in units of one bucket insertion: n*W insertions plus ~8 per bucket for the weighted bucket sums (measured:
+// the reduction costs 0.7 ms for 2^19 buckets where an insertion costs 0.155 ns ... 0.16 us per 1000).
 uint32_t pick_window(size_t n, bool shared_buckets) {
     uint32_t best_c = 8;
     double best = 1e300;
     for (uint32_t c = 6; c <= 22; ++c) {
-        uint32_t W = 254 / c + 1;
+        uint32_t wide, W = shared_buckets ? balanced_windows(c, &wide) : 254 / c + 1;
         double groups = shared_buckets ? 1.0 : (double)W;
-        double cost = (double)n * W + 3.0 * groups * (double)(1u << (c - 1));
+        double cost = (double)n * W + 8.0 * groups * (double)(1u << (c - 1));
         if (cost < best) { best = cost; best_c = c; }
     }
     return best_c;
@@ -472,11 +523,11 @@ uint32_t pick_window(size_t n, bool shared_buckets) {
 MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset) {
     MsmPlan pl;
     if (fb) {
-        pl.c = fb->c; pl.W = fb->W; pl.G = 1;
+        pl.c = fb->c; pl.W = fb->W; pl.G = 1; pl.wide = fb->wide;
         pl.id_base = (uint32_t)offset; pl.id_stride = (uint32_t)fb->n;
     } else {
         pl.c = force_c > 0 ? (uint32_t)force_c : pick_window(n, false);
-        pl.W = 254 / pl.c + 1; pl.G = pl.W;
+        pl.W = 254 / pl.c + 1; pl.G = pl.W; pl.wide = pl.W;
         pl.id_base = 0; pl.id_stride = 0;
     }
     pl.B = 1u << (pl.c - 1);
@@ -548,11 +599,11 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.size_hist, 0, (SEG + 1) * 4, s));
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.misc, 0, 64, s));
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.bucket_val, 0, (size_t)nb * sizeof(g1x_t), s));
-    if (n32) msm_count_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, gstride, ws.counts);
+    if (n32) msm_count_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, ws.counts);
     rc = exclusive_scan(ctx, ws.counts, ws.starts, nb, ws.scan_tmp, nullptr);
     if (rc) return rc;
     ZKB_CUDA(ctx, cudaMemcpyAsync(ws.cursor, ws.starts, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
-    if (n32) msm_scatter_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, gstride, pl.id_base, pl.id_stride,
+    if (n32) msm_scatter_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, pl.id_base, pl.id_stride,
                                                                   ws.cursor, ws.sorted);
     msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, nb, ws.ntasks, ws.size_hist, ws.misc, ws.heavy_list);
     rc = exclusive_scan(ctx, ws.ntasks, ws.task_base, nb, ws.scan_tmp, ws.misc + 1);
@@ -567,13 +618,15 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[2], s));
     msm_combine_heavy_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out,
                                                                ws.bucket_val);
+    msm_combine_giant_kernel<<<ctx->sm_count, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out,
+                                                          ws.bucket_val);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[3], s));
     msm_reduce_kernel<<<pl.G * pl.red_ctas_per_group, RED_THREADS, 0, s>>>(ws.bucket_val, pl.B, pl.red_ctas_per_group, ws.grp_partial);
     msm_reduce_final_kernel<<<pl.G, RED_THREADS, 0, s>>>(ws.grp_partial, pl.red_ctas_per_group, ws.grp_sum);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], s));
     ZKB_CUDA(ctx, cudaGetLastError());
     st->ev_valid = true;
-    ctx->launches += 17;                 // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy, reduce x 2
+    ctx->launches += 18;                 // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduce x 2
     ZKB_CUDA(ctx, cudaMemcpyAsync(st->pinned, ws.grp_sum, out_bytes, cudaMemcpyDeviceToHost, s));
     *plan_out = pl;
     return ZKB_OK;
@@ -654,18 +707,18 @@ int zkb_srs_precompute(zkb_ctx *ctx, int c) {
         st->fixed_base = nullptr;
     }
     if (c < 0) return ZKB_OK;
-    if (c == 1 || c > 24) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_precompute: window size out of range");
+    if ((c > 0 && c < 3) || c > 24) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_precompute: window size out of range (3..24)");
     const size_t n = ctx->srs_n;
     if (n == 0) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_srs_precompute: no SRS loaded");
     FixedBase *fb = new FixedBase();
     fb->c = c > 0 ? (uint32_t)c : pick_window(n, true);
-    fb->W = 254 / fb->c + 1;
+    fb->W = balanced_windows(fb->c, &fb->wide);
     fb->n = n;
     if ((uint64_t)n * fb->W >= (1ull << 31)) { delete fb; ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_precompute: n * windows must be < 2^31"); }
     int rc = zkb_reserve(ctx, fb->rows, (size_t)fb->W * n * sizeof(g1a_t));
     if (rc) { delete fb; return rc; }
     msm_precompute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const g1a_t *)ctx->srs.p, (uint32_t)n, fb->c, fb->W,
-                                                                                (g1a_t *)fb->rows.p);
+                                                                                fb->wide, (g1a_t *)fb->rows.p);
     ctx->launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
