@@ -37,7 +37,7 @@ G = np.zeros(8, dtype=np.uint64)
 # generator (1,2) in Montgomery form via the device field library
 one_two = np.zeros((2, 4), dtype=np.uint64); one_two[0, 0] = 1; one_two[1, 0] = 2
 G = ctx.fp_binop(1, 5, one_two).reshape(8)
-for log_n in (16, 18, 20, 22):
+for log_n in (16, 18, 20, 22, 24):
     n = 1 << log_n
     k = rand_words(n, 4); k[:, 3] &= (1 << 60) - 1
     P = torch.empty((n, 8), dtype=torch.int64, device="cuda")
@@ -50,7 +50,7 @@ for log_n in (16, 18, 20, 22):
         best, med = timeit(lambda: ctx.msm(s), reps=5, warm=2)
         print(f"msm 2^{log_n} c={c}: {best:.3f} ms best, {med:.3f} med, {n/best/1e3:.1f} Mpts/s", flush=True)
     ctx.set_msm_window(0)
-    for c in (0, 16, 18, 19, 20, 22):
+    for c in (0, 17, 19, 20):
         t0 = time.time(); ctx.srs_precompute(c); torch.cuda.synchronize(); tp = time.time() - t0
         best, med = timeit(lambda: ctx.msm(s), reps=5, warm=2)
         tm = ctx.msm_last_timing()

@@ -34,8 +34,8 @@ using namespace zkb;
 
 namespace {
 
-constexpr uint32_t SEG = 256;            // max points per accumulation task
-constexpr uint32_t RED_CH = 16;          // buckets per thread in the window reduction
+constexpr uint32_t SEG_MAX = 1024;       // upper bound of the per-MSM task length `seg` (points per accumulation task)
+constexpr uint32_t RED_CH_MAX = 16;      // upper bound of buckets per thread in the window reduction
 constexpr uint32_t RED_THREADS = 128;    // threads per CTA in the window reduction
 constexpr uint32_t SIGN_BIT = 0x80000000u;
 
@@ -44,7 +44,8 @@ struct MsmPlan {
     uint32_t G;                          // bucket groups: W (one per window) or 1 (fixed-base tables)
     uint32_t wide;                       // windows [0, wide) are c bits wide, the others c - 1 (wide = W: uniform)
     uint64_t nbuckets;                   // G * B
-    uint32_t red_ctas_per_group;
+    uint32_t red_ctas_per_group, red_ch;   // reduction: CTAs per group, buckets per thread
+    uint32_t seg;                        // max points per accumulation task
     uint32_t id_base, id_stride;         // fixed-base: entry id = id_base + w * id_stride + i
 };
 
@@ -199,9 +200,9 @@ int exclusive_scan(zkb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, 
 }
 
 // ------------------------------------------------------------------ tasks
-__global__ void msm_ntasks_kernel(const uint32_t *counts, uint32_t nb, uint32_t *ntasks, uint32_t *size_hist,
+__global__ void msm_ntasks_kernel(const uint32_t *counts, uint32_t nb, uint32_t SEG, uint32_t *ntasks, uint32_t *size_hist,
                                   uint32_t *misc, uint32_t *heavy_list) {
-    __shared__ uint32_t h[SEG + 1];
+    __shared__ uint32_t h[SEG_MAX + 1];
     for (uint32_t k = threadIdx.x; k <= SEG; k += blockDim.x) h[k] = 0;
     __syncthreads();
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -222,9 +223,9 @@ __global__ void msm_ntasks_kernel(const uint32_t *counts, uint32_t nb, uint32_t 
 
 // Tasks ordered by descending size.  A CTA ranks its tasks per size bin in shared memory and reserves one global
 // range per (CTA, bin), so the global atomics are few and spread (a per-task atomic on ~40 hot bins cost 100 us).
-__global__ void __launch_bounds__(256) msm_task_scatter_kernel(const uint32_t *counts, const uint32_t *ntasks, uint32_t nb,
+__global__ void __launch_bounds__(256) msm_task_scatter_kernel(const uint32_t *counts, const uint32_t *ntasks, uint32_t nb, uint32_t SEG,
                                                                uint32_t *size_cursor, uint2 *task_order) {
-    __shared__ uint32_t h[SEG + 1], base[SEG + 1];
+    __shared__ uint32_t h[SEG_MAX + 1], base[SEG_MAX + 1];
     for (uint32_t k = threadIdx.x; k <= SEG; k += blockDim.x) h[k] = 0;
     __syncthreads();
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__rest
                                                              const uint32_t *__restrict__ counts, const uint32_t *__restrict__ starts,
                                                              const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_base,
                                                              const uint2 *__restrict__ task_order, const uint32_t *__restrict__ misc,
-                                                             g1x_t *__restrict__ task_out, g1x_t *__restrict__ bucket_val) {
+                                                             uint32_t SEG, g1x_t *__restrict__ task_out, g1x_t *__restrict__ bucket_val) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= misc[1]) return;
     uint2 task = task_order[t];
@@ -349,7 +350,7 @@ __device__ __noinline__ g1x_t g1x_mul_small(const g1x_t &p, uint32_t k) {
 // grid = G * ctas_per_group CTAs of RED_THREADS threads; a thread owns RED_CH consecutive buckets of one group.
 // bucket_val is dense, so all loads of a chunk are independent of each other and issue up front.
 __global__ void __launch_bounds__(RED_THREADS) msm_reduce_kernel(const g1x_t *__restrict__ bucket_val, uint32_t B, uint32_t ctas_per_group,
-                                                                 g1x_t *__restrict__ grp_partial) {
+                                                                 uint32_t RED_CH, g1x_t *__restrict__ grp_partial) {
     __shared__ g1x_t sm[RED_THREADS];
     uint32_t g = blockIdx.x / ctas_per_group, cw = blockIdx.x % ctas_per_group;
     uint32_t chunk = cw * RED_THREADS + threadIdx.x;          // chunk index inside the group
@@ -506,15 +507,15 @@ uint32_t balanced_windows(uint32_t c, uint32_t *wide) {
     return W;
 }
 
-// Cost in units of one bucket insertion: n*W insertions plus ~8 per bucket for the weighted bucket sums (measured:
-// the reduction costs 0.7 ms for 2^19 buckets where an insertion costs 0.155 ns ... 0.16 us per 1000).
+// Cost in units of one bucket insertion (0.155 ns measured): n*W insertions plus a per-bucket charge for the weighted
+// bucket sums (measured ~1 ns per bucket on top of a fixed latency, less when the buckets split into W groups).
 uint32_t pick_window(size_t n, bool shared_buckets) {
     uint32_t best_c = 8;
     double best = 1e300;
     for (uint32_t c = 6; c <= 22; ++c) {
         uint32_t wide, W = shared_buckets ? balanced_windows(c, &wide) : 254 / c + 1;
         double groups = shared_buckets ? 1.0 : (double)W;
-        double cost = (double)n * W + 8.0 * groups * (double)(1u << (c - 1));
+        double cost = (double)n * W + (shared_buckets ? 6.5 : 4.0) * groups * (double)(1u << (c - 1));
         if (cost < best) { best = cost; best_c = c; }
     }
     return best_c;
@@ -532,8 +533,18 @@ MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset) {
     }
     pl.B = 1u << (pl.c - 1);
     pl.nbuckets = (uint64_t)pl.G * pl.B;
-    uint32_t chunks = (pl.B + RED_CH - 1) / RED_CH;
+    // reduction: the serial depth per thread is 2 * red_ch + ~29 group operations, so use the smallest chunk that
+    // still keeps the grid near two warps per SM sub-partition (148 SMs x 4 x 2 warps x 32 lanes = 37888 threads)
+    uint32_t ch = (uint32_t)((pl.nbuckets + 37887) / 37888);
+    pl.red_ch = ch < 2 ? 2 : (ch > RED_CH_MAX ? RED_CH_MAX : ch);
+    uint32_t chunks = (pl.B + pl.red_ch - 1) / pl.red_ch;
     pl.red_ctas_per_group = (chunks + RED_THREADS - 1) / RED_THREADS;
+    // task length: twice the mean bucket load (rounded up to a power of two), so that ordinary buckets are one
+    // task and an oversized bucket's tail is bounded by about twice the typical thread's work
+    double mean = (double)n * pl.W / (double)pl.nbuckets;
+    uint32_t seg = 64;
+    while (seg < 2.0 * mean && seg < SEG_MAX) seg <<= 1;
+    pl.seg = seg;
     return pl;
 }
 
@@ -542,13 +553,13 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int carve_ws(zkb_ctx *ctx, const MsmPlan &pl, size_t n, MsmWs &ws, uint64_t *max_tasks_out, uint64_t *max_heavy_tasks_out) {
     const uint64_t nb = pl.nbuckets;
     const uint64_t entries = (uint64_t)n * pl.W;
-    const uint64_t max_tasks = nb + entries / SEG + 1;
-    const uint64_t max_heavy_tasks = 2 * (entries / SEG) + 2;      // tasks of buckets with more than SEG points
+    const uint64_t max_tasks = nb + entries / pl.seg + 1;
+    const uint64_t max_heavy_tasks = 2 * (entries / pl.seg) + 2;   // tasks of buckets with more than seg points
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_counts = take(nb * 4), o_starts = take(nb * 4), o_cursor = take(nb * 4), o_ntasks = take(nb * 4),
            o_tbase = take(nb * 4), o_sorted = take(entries * 4 + 4), o_scan = take((nb / SCAN_TILE + 2) * 4),
-           o_hist = take((SEG + 1) * 4), o_hcur = take((SEG + 1) * 4), o_misc = take(64), o_heavy = take(nb * 4),
+           o_hist = take((SEG_MAX + 1) * 4), o_hcur = take((SEG_MAX + 1) * 4), o_misc = take(64), o_heavy = take(nb * 4),
            o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)), o_bval = take(nb * sizeof(g1x_t)),
            o_part = take((size_t)pl.G * pl.red_ctas_per_group * sizeof(g1x_t)), o_sum = take((size_t)pl.G * sizeof(g1x_t));
     int rc = zkb_reserve(ctx, ctx->msm_ws, off);
@@ -596,7 +607,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[0], s));
 
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.counts, 0, (size_t)nb * 4, s));
-    ZKB_CUDA(ctx, cudaMemsetAsync(ws.size_hist, 0, (SEG + 1) * 4, s));
+    ZKB_CUDA(ctx, cudaMemsetAsync(ws.size_hist, 0, (SEG_MAX + 1) * 4, s));
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.misc, 0, 64, s));
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.bucket_val, 0, (size_t)nb * sizeof(g1x_t), s));
     if (n32) msm_count_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, ws.counts);
@@ -605,15 +616,15 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     ZKB_CUDA(ctx, cudaMemcpyAsync(ws.cursor, ws.starts, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
     if (n32) msm_scatter_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, pl.id_base, pl.id_stride,
                                                                   ws.cursor, ws.sorted);
-    msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, nb, ws.ntasks, ws.size_hist, ws.misc, ws.heavy_list);
+    msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, nb, pl.seg, ws.ntasks, ws.size_hist, ws.misc, ws.heavy_list);
     rc = exclusive_scan(ctx, ws.ntasks, ws.task_base, nb, ws.scan_tmp, ws.misc + 1);
     if (rc) return rc;
-    rc = exclusive_scan(ctx, ws.size_hist, ws.size_cursor, SEG + 1, ws.scan_tmp, nullptr);
+    rc = exclusive_scan(ctx, ws.size_hist, ws.size_cursor, pl.seg + 1, ws.scan_tmp, nullptr);
     if (rc) return rc;
-    msm_task_scatter_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, ws.ntasks, nb, ws.size_cursor, ws.task_order);
+    msm_task_scatter_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, ws.ntasks, nb, pl.seg, ws.size_cursor, ws.task_order);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[1], s));
     msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, ws.sorted, ws.counts, ws.starts, ws.ntasks,
-                                                                             ws.task_base, ws.task_order, ws.misc, ws.task_out,
+                                                                             ws.task_base, ws.task_order, ws.misc, pl.seg, ws.task_out,
                                                                              ws.bucket_val);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[2], s));
     msm_combine_heavy_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out,
@@ -621,7 +632,8 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     msm_combine_giant_kernel<<<ctx->sm_count, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out,
                                                           ws.bucket_val);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[3], s));
-    msm_reduce_kernel<<<pl.G * pl.red_ctas_per_group, RED_THREADS, 0, s>>>(ws.bucket_val, pl.B, pl.red_ctas_per_group, ws.grp_partial);
+    msm_reduce_kernel<<<pl.G * pl.red_ctas_per_group, RED_THREADS, 0, s>>>(ws.bucket_val, pl.B, pl.red_ctas_per_group, pl.red_ch,
+                                                                           ws.grp_partial);
     msm_reduce_final_kernel<<<pl.G, RED_THREADS, 0, s>>>(ws.grp_partial, pl.red_ctas_per_group, ws.grp_sum);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], s));
     ZKB_CUDA(ctx, cudaGetLastError());
