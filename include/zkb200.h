@@ -146,6 +146,10 @@ ZKB_API int zkb_poly_divide_linear_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev,
  * the buffer must have room for len + k coefficients. */
 ZKB_API int zkb_poly_add_blinders_dev(zkb_ctx *ctx, uint64_t *coeffs_dev, size_t len, const uint64_t *blinders_host, size_t k);
 
+/* Number of coefficients left once trailing zeros are dropped, as DensePolynomial::from_coefficients_vec does
+ * (blinders are appended at that length: prove.rs:472-483).  Synchronous. */
+ZKB_API int zkb_poly_effective_len_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, size_t n, size_t *out_len);
+
 /* ---- test hooks (parity of the device field library against the oracle) ----------------------------------------- */
 /* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a).  Host pointers. */
 ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n);

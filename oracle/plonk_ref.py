@@ -1,0 +1,223 @@
+"""CPU backend for zkt_plonk_b200.prover's round schedule and a restated verifier.  TEST INFRASTRUCTURE ONLY.
+
+`OracleBackend` implements every heavy step of the prover with the C oracle (oracle/zkb_oracle.c) or plain Python
+integers, so that tests can run proof_system::prove (plonk-core/src/proof_system/prove.rs:59-470) entirely on the
+CPU and compare the proof bytes with the CUDA path.  `verify` restates Proof::verify
+(plonk-core/src/proof_system/proof.rs:285-503), including compute_r0 (:163-217) and
+compute_linearization_commitment (:220-282).  PC::check needs a BN254 pairing, which does not exist in this
+repository; because the synthetic SRS's trapdoor tau is known, the pairing equation
+e(W, tau*H) = e(C - v*G + z*W, H) is checked in G1 as  tau*W == C - v*G + z*W  (SonicKZG10::check's
+accumulate_elems / check_elems with no degree bounds and no hiding).  PARITY UNPINNED against the Rust binary: see
+zkb_oracle.c's header.
+"""
+import numpy as np
+
+from oracle import cref, pyref
+from zkt_plonk_b200 import field
+from zkt_plonk_b200.prover import (P, Poly, Proof, fr_to_limbs, ints_to_mont_array, limbs_to_fr, mont_array_to_ints,
+                                    point_to_ints)
+from zkt_plonk_b200.transcript import MerlinTranscript
+
+EPK_ORDER = ("q_m", "q_l", "q_r", "q_o", "q_c", "q_lookup", "q_table", "sigma1", "sigma2", "sigma3", "l1")
+WIT_ORDER = ("z1", "z2", "a", "b", "c", "pi", "t", "h1", "h2")
+
+
+class OracleBackend:
+    def __init__(self, srs_points):
+        self.srs = np.ascontiguousarray(srs_points, dtype=np.uint64)       # (N, 8) Montgomery affine powers of tau
+
+    # -- storage
+    def from_host(self, a, cap=None):
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        buf = np.zeros((a.shape[0] if cap is None else cap, 4), dtype=np.uint64)
+        buf[: a.shape[0]] = a
+        return buf
+
+    def to_host(self, buf, length):
+        return buf[:length].copy()
+
+    def slice_copy(self, buf, lo, hi, cap):
+        out = np.zeros((cap, 4), dtype=np.uint64)
+        out[: hi - lo] = buf[lo:hi]
+        return out
+
+    def get(self, buf, i):
+        return limbs_to_fr(buf[i])
+
+    def put(self, buf, i, value):
+        buf[i] = fr_to_limbs(value)
+
+    # -- transforms / commitments
+    def ifft(self, evals, log_n, cap):
+        n = 1 << log_n
+        out = np.zeros((cap, 4), dtype=np.uint64)
+        out[:n] = cref.ntt(np.ascontiguousarray(evals[:n]), log_n, True)
+        return out
+
+    def effective_len(self, buf, n):
+        nz = np.flatnonzero(buf[:n].any(axis=1))
+        return int(nz[-1]) + 1 if nz.size else 0
+
+    def add_blinders(self, poly, blinders):
+        for i, b in enumerate(blinders):
+            poly.data[poly.len + i] = fr_to_limbs(b)
+        for i, b in enumerate(blinders):
+            if i < poly.len:
+                poly.data[i] = fr_to_limbs((limbs_to_fr(poly.data[i]) - b) % P)
+        poly.len += len(blinders)
+
+    def commit(self, poly):
+        if poly.len == 0:
+            return None
+        sc = cref.from_mont(cref.FR, np.ascontiguousarray(poly.data[: poly.len]))
+        xy, inf = cref.msm_g1(self.srs[: poly.len], sc)
+        return point_to_ints(xy, inf)
+
+    # -- argument math
+    def z1_poly(self, log_n, beta, gamma, a, b, c, s1, s2, s3, cap):
+        n = 1 << log_n
+        ev = cref.z1_evals(log_n, fr_to_limbs(beta), fr_to_limbs(gamma), *[np.ascontiguousarray(x[:n]) for x in (a, b, c, s1, s2, s3)])
+        return self.ifft(ev, log_n, cap)
+
+    def z2_poly(self, log_n, delta, eps, f, t, h1, h2, cap):
+        n = 1 << log_n
+        ev = cref.z2_evals(log_n, fr_to_limbs(delta), fr_to_limbs(eps), *[np.ascontiguousarray(x[:n]) for x in (f, t, h1, h2)])
+        return self.ifft(ev, log_n, cap)
+
+    def _coset4(self, poly, log_n):
+        buf = np.zeros((4 << log_n, 4), dtype=np.uint64)
+        buf[: poly.len] = poly.data[: poly.len]
+        return cref.ntt(buf, log_n + 2, False, True)
+
+    def extend_prover_key(self, log_n, polys):
+        epk = {name: self._coset4(polys[name], log_n) for name in EPK_ORDER[:-1]}
+        epk["x"], epk["zh"], epk["l1"] = cref.epk_free_tables(log_n)
+        return epk
+
+    def quotient(self, log_n, epk, ch, polys):
+        wit = {name: self._coset4(polys[name], log_n) for name in WIT_ORDER}
+        chal = np.stack([fr_to_limbs(x) for x in ch])
+        ev = cref.quotient_evals(log_n, chal, wit, epk)
+        return cref.ntt(ev, log_n + 2, True, True)
+
+    def evaluate(self, poly, z):
+        acc = 0
+        for cf in reversed(mont_array_to_ints(poly.data[: poly.len])):
+            acc = (acc * z + cf) % P
+        return acc
+
+    def lincomb(self, polys, scalars, cap=None):
+        m = max(p.len for p in polys)
+        acc = [0] * m
+        for p, s in zip(polys, scalars):
+            for k, cf in enumerate(mont_array_to_ints(p.data[: p.len])):
+                acc[k] = (acc[k] + s * cf) % P
+        buf = np.zeros((cap or m, 4), dtype=np.uint64)
+        buf[:m] = ints_to_mont_array(acc)
+        return Poly(buf, m)
+
+    def divide_linear(self, poly, z):
+        cf = mont_array_to_ints(poly.data[: poly.len])
+        m = len(cf)
+        w, carry = [0] * max(m - 1, 0), 0
+        for k in range(m - 1, 0, -1):
+            carry = (cf[k] + z * carry) % P
+            w[k - 1] = carry
+        ev = ((cf[0] if m else 0) + z * carry) % P
+        buf = np.zeros((max(m - 1, 1), 4), dtype=np.uint64)
+        if m > 1:
+            buf[: m - 1] = ints_to_mont_array(w)
+        return Poly(buf, max(m - 1, 0)), ev
+
+
+# ------------------------------------------------------------------------------------------------ verifier
+def _lagrange(n, point, zh_eval, tau):
+    """util.rs:185-195 compute_lagrange_evaluation(n, point, zh_eval, tau)."""
+    return zh_eval * point % P * pow(n * (tau - point) % P, -1, P) % P
+
+
+def _lin_comb_points(points, scalars):
+    acc = None
+    for pt, s in zip(points, scalars):
+        acc = pyref.g1_add(acc, pyref.g1_mul(s % P, pt) if pt is not None else None)
+    return acc
+
+
+def _kzg_check(commits, point, values, w, eta, tau):
+    """SonicKZG10::check with the trapdoor in place of the pairing: tau * W == sum eta^i C_i - (sum eta^i v_i) G + z W."""
+    chal = [pow(eta, i, P) for i in range(len(commits))]
+    c = _lin_comb_points(commits, chal)
+    v = sum(e * x for e, x in zip(chal, values)) % P
+    rhs = pyref.g1_add(pyref.g1_add(c, pyref.g1_neg(pyref.g1_mul(v, pyref.G1_GEN))), pyref.g1_mul(point, w) if w else None)
+    lhs = pyref.g1_mul(tau, w) if w else None
+    return lhs == rhs
+
+
+def verify(vk, proof, pub_inputs, tau):
+    """Proof::verify (proof.rs:285-503).  Returns 0 if accepted, else the failing step (1 or 2)."""
+    n = vk.n
+    log_n = n.bit_length() - 1
+    assert len(pub_inputs) == len(vk.pi_roots), "invalid length of public inputs"
+    tr = MerlinTranscript("ZKT Plonk")
+    vk.seed_transcript(tr)
+    tr.append_scalars("pi", pub_inputs)
+    C, E = proof.commits, proof.evals
+    for k in ("a", "b", "c", "t", "h1", "h2"):
+        tr.append_commitment(k + "_commit", C[k])
+    beta, gamma = tr.challenge_scalar("beta"), tr.challenge_scalar("gamma")
+    delta, epsilon = tr.challenge_scalar("delta"), tr.challenge_scalar("epsilon")
+    assert len({beta, gamma, delta, epsilon}) == 4
+    tr.append_commitment("z1_commit", C["z1"])
+    tr.append_commitment("z2_commit", C["z2"])
+    alpha = tr.challenge_scalar("alpha")
+    for k in ("q_lo", "q_mid", "q_hi"):
+        tr.append_commitment(k + "_commit", C[k])
+    xi = tr.challenge_scalar("xi")
+    zh = (pow(xi, n, P) - 1) % P
+    l1 = _lagrange(n, 1, zh, xi)
+    al2 = alpha * alpha % P
+    opd = (1 + delta) % P
+    eopd = epsilon * opd % P
+    # compute_r0 (proof.rs:163-217)
+    part1 = (-sum(_lagrange(n, pt, zh, xi) * pi for pi, pt in zip(pub_inputs, vk.pi_roots))) % P
+    part2 = alpha * E["z1_next"] % P * (E["a"] + beta * E["sigma1"] + gamma) % P * (E["b"] + beta * E["sigma2"] + gamma) % P * (E["c"] + gamma) % P
+    part3 = l1 * al2 % P
+    part4 = al2 * alpha % P * E["z2_next"] % P * (eopd + delta * E["h2"]) % P * (eopd + E["h2"] + delta * E["h1_next"]) % P
+    part5 = l1 * al2 % P * al2 % P
+    r0 = (part1 + part2 + part3 + part4 + part5) % P
+    # compute_linearization_commitment (proof.rs:220-282 with keys/*::compute_linearization_commitment)
+    V = vk.commits
+    bz = beta * xi % P
+    al3, al4, al5 = al2 * alpha % P, al2 * al2 % P, al2 * al2 % P * alpha % P
+    scalars = [E["a"] * E["b"] % P, E["a"], E["b"], E["c"], 1,
+               (alpha * (bz + E["a"] + gamma) % P * (bz * field.K1 + E["b"] + gamma) % P * (bz * field.K2 + E["c"] + gamma) + l1 * al2) % P,
+               (-alpha * beta % P * E["z1_next"] % P * (beta * E["sigma1"] + E["a"] + gamma) % P * (beta * E["sigma2"] + E["b"] + gamma)) % P,
+               (al3 * opd % P * (epsilon + E["q_lookup"] * E["c"]) % P * (eopd + E["t"] + delta * E["t_next"]) + al4 * l1) % P,
+               (-al3 * E["z2_next"] % P * (eopd + E["h2"] + delta * E["h1_next"])) % P,
+               al5 * E["t"] % P]
+    points = [V["q_m"], V["q_l"], V["q_r"], V["q_o"], V["q_c"], C["z1"], V["sigma3"], C["z2"], C["h1"], V["q_table"]]
+    xn2 = (zh + 1) * xi % P * xi % P
+    scalars += [(-zh) % P, (-zh * xn2) % P, (-zh * xn2 % P * xn2) % P]
+    points += [C["q_lo"], C["q_mid"], C["q_hi"]]
+    r_commit = _lin_comb_points(points, scalars)
+    for k in Proof.EVALS:
+        tr.append_scalar(k + "_eval", E[k])
+    eta = tr.challenge_scalar("eta")
+    ok1 = _kzg_check([r_commit, C["a"], C["b"], C["c"], V["sigma1"], V["sigma2"], V["q_lookup"], C["t"], C["h2"]], xi,
+                     [r0, E["a"], E["b"], E["c"], E["sigma1"], E["sigma2"], E["q_lookup"], E["t"], E["h2"]], proof.aw, eta, tau)
+    if not ok1:
+        return 1
+    w_n = field.root_of_unity(log_n)
+    ok2 = _kzg_check([C["z1"], C["z2"], C["t"], C["h1"]], xi * w_n % P,
+                     [E["z1_next"], E["z2_next"], E["t_next"], E["h1_next"]], proof.saw, eta, tau)
+    return 0 if ok2 else 2
+
+
+def make_srs_host(n_points, tau):
+    """[tau^i] G for i < n_points, Montgomery affine (n_points, 8) -- small sizes only (double-and-add per point)."""
+    G = cref.to_mont(cref.FQ, cref.ints_to_limbs([1, 2])).reshape(8)
+    powers, x = [], 1
+    for _ in range(n_points):
+        powers.append(x)
+        x = x * tau % P
+    return cref.g1_mul(G, cref.ints_to_limbs(powers))

@@ -1,0 +1,79 @@
+"""CPU-only: the prover round schedule (zkt_plonk_b200.prover) run over the oracle backend produces proofs that the
+restated verifier accepts -- the reference's own acceptance criterion (plonk.rs:191-254 test_full) -- and rejects
+tampered ones; also pins the Merlin transcript against merlin's published test vector."""
+import random
+
+import pytest
+
+from oracle import plonk_ref
+from zkt_plonk_b200 import prover, synthetic
+from zkt_plonk_b200.transcript import Merlin, MerlinTranscript
+
+P = prover.P
+TAU = 0x1D9E5F1B2C3A49587766554433221100FFEEDDCCBBAA99887766554433221101 % P
+
+
+def test_merlin_published_vector():
+    """merlin 3.0 `equivalence_simple`: pins STROBE-128 / Keccak-f and the framing the transcript relies on."""
+    t = Merlin(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    assert t.challenge_bytes(b"challenge", 32).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+
+
+def test_challenge_scalar_is_31_bytes_le():
+    a, b = MerlinTranscript("x"), Merlin(b"x")
+    v = a.challenge_scalar("beta")
+    assert v == int.from_bytes(b.challenge_bytes(b"beta", 31), "little") and v < 1 << 248
+
+
+def test_combine_split_matches_reference_unit_test_shape():
+    """multiset.rs:272-329: halves alternate, every element of f must be in t."""
+    t, f = [0, 1, 2, 3, 4, 5, 6, 7], [3, 6, 0, 5, 4, 3, 2, 0, 0, 1, 2]
+    h1, h2 = prover.combine_split(t, f)
+    assert sorted(h1 + h2) == sorted(t + f) and abs(len(h1) - len(h2)) <= 1
+    assert h1 == [0, 0, 1, 2, 3, 3, 4, 5, 6, 7] or len(h1) + len(h2) == 19
+    with pytest.raises(ValueError):
+        prover.combine_split([1, 2], [3])
+
+
+@pytest.mark.parametrize("log_n", [4, 6])
+def test_prove_verify_roundtrip_on_oracle_backend(log_n):
+    circ = synthetic.make_circuit(log_n, seed=log_n, table_size=4)
+    assert synthetic.check_gates(circ)
+    be = plonk_ref.OracleBackend(plonk_ref.make_srs_host(circ.n + 8, TAU))
+    pk, vk = prover.setup(be, circ)
+    rnd = random.Random(7)
+    blinders = [rnd.randrange(P) for _ in range(19)]
+    proof = prover.prove(be, pk, vk, circ, blinders)
+    raw = proof.to_bytes()
+    assert len(raw) == 11 * 32 + 2 * 33 + 12 * 32
+    pub = list(circ.pi.values())
+    assert plonk_ref.verify(vk, proof, pub, TAU) == 0
+    # same inputs, same bytes; different blinders, different proof that still verifies
+    assert prover.prove(be, pk, vk, circ, blinders).to_bytes() == raw
+    other = prover.prove(be, pk, vk, circ, [rnd.randrange(P) for _ in range(19)])
+    assert other.to_bytes() != raw and plonk_ref.verify(vk, other, pub, TAU) == 0
+    # tampering: an evaluation, a public input, a commitment
+    bad = prover.Proof(dict(proof.commits), proof.aw, proof.saw, dict(proof.evals))
+    bad.evals["a"] = (bad.evals["a"] + 1) % P
+    assert plonk_ref.verify(vk, bad, pub, TAU) != 0
+    assert plonk_ref.verify(vk, proof, [(pub[0] + 1) % P] + pub[1:], TAU) != 0
+    bad = prover.Proof(dict(proof.commits), proof.aw, proof.saw, dict(proof.evals))
+    bad.commits["z1"] = proof.commits["z2"]
+    assert plonk_ref.verify(vk, bad, pub, TAU) != 0
+
+
+def test_unsatisfied_witness_is_rejected():
+    circ = synthetic.make_circuit(5, seed=3, table_size=4)
+    c = prover.mont_array_to_ints(circ.c)
+    row = max(i for i in range(circ.n) if c[i])            # corrupt one gate output
+    c[row] = (c[row] + 1) % P
+    circ.c = prover.ints_to_mont_array(c)
+    assert not synthetic.check_gates(circ)
+    be = plonk_ref.OracleBackend(plonk_ref.make_srs_host(circ.n + 8, TAU))
+    pk, vk = prover.setup(be, circ)
+    try:
+        proof = prover.prove(be, pk, vk, circ, list(range(1, 20)))
+    except (AssertionError, ValueError, ZeroDivisionError):
+        return                                              # e.g. the lookup value left the table
+    assert plonk_ref.verify(vk, proof, list(circ.pi.values()), TAU) != 0

@@ -69,6 +69,7 @@ def load():
         "zkb_poly_lincomb_dev": (i, [vp, sz, ctypes.POINTER(vp), ctypes.POINTER(sz), vp, vp, sz]),
         "zkb_poly_divide_linear_dev": (i, [vp, vp, sz, vp, vp, vp]),
         "zkb_poly_add_blinders_dev": (i, [vp, vp, sz, vp, sz]),
+        "zkb_poly_effective_len_dev": (i, [vp, vp, sz, ctypes.POINTER(sz)]),
         "zkb_launch_count": (ctypes.c_uint64, [vp]),
         "zkb_msm_last_timing": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),
         "zkb_bench_int": (i, [vp, i, ctypes.POINTER(ctypes.c_double)]),

@@ -186,6 +186,11 @@ class Context:
                                                         blinders.shape[0]))
         return coeffs
 
+    def poly_effective_len_dev(self, coeffs, n):
+        out = ctypes.c_size_t(0)
+        self._check(self._lib.zkb_poly_effective_len_dev(self._h, _dev_ptr(coeffs), n, ctypes.byref(out)))
+        return int(out.value)
+
     def launch_count(self):
         return int(self._lib.zkb_launch_count(self._h))
 

@@ -539,11 +539,12 @@ MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset) {
     pl.red_ch = ch < 2 ? 2 : (ch > RED_CH_MAX ? RED_CH_MAX : ch);
     uint32_t chunks = (pl.B + pl.red_ch - 1) / pl.red_ch;
     pl.red_ctas_per_group = (chunks + RED_THREADS - 1) / RED_THREADS;
-    // task length: twice the mean bucket load (rounded up to a power of two), so that ordinary buckets are one
-    // task and an oversized bucket's tail is bounded by about twice the typical thread's work
+    // task length: at least 256 and four times the mean bucket load (rounded up to a power of two, capped), so
+    // that ordinary buckets -- including the denser ones of narrow / top windows -- stay a single task while an
+    // oversized bucket (skewed scalars) is cut into pieces a few times the typical thread's work
     double mean = (double)n * pl.W / (double)pl.nbuckets;
-    uint32_t seg = 64;
-    while (seg < 2.0 * mean && seg < SEG_MAX) seg <<= 1;
+    uint32_t seg = 256;
+    while (seg < 4.0 * mean && seg < SEG_MAX) seg <<= 1;
     pl.seg = seg;
     return pl;
 }

@@ -413,6 +413,14 @@ __global__ void fr_fill_kernel(uint4 *out, size_t n, fe_t v) {
     if (i < n) fstore(out + 2 * i, v);
 }
 
+// out[0] = 1 + index of the highest non-zero coefficient (0 for the zero polynomial)
+__global__ void __launch_bounds__(256) effective_len_kernel(const uint4 *coeffs, size_t n, unsigned long long *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 a = coeffs[2 * i], b = coeffs[2 * i + 1];
+    if (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) atomicMax(out, (unsigned long long)(i + 1));
+}
+
 unsigned ceil_log2_sz(size_t n) { unsigned l = 0; while (((size_t)1 << l) < n) ++l; return l; }
 
 }  // namespace
@@ -624,6 +632,25 @@ int zkb_poly_add_blinders_dev(zkb_ctx *ctx, uint64_t *coeffs_dev, size_t len, co
     add_blinders_kernel<<<1, 32, 0, ctx->stream>>>((uint4 *)coeffs_dev, len, b);
     ctx->launches += 1;
     ZKB_CUDA(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+// DensePolynomial::from_coefficients_vec truncation: number of coefficients once trailing zeros are dropped.
+int zkb_poly_effective_len_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, size_t n, size_t *out_len) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (!out_len || (!coeffs_dev && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_poly_effective_len_dev: null argument");
+    *out_len = 0;
+    if (n == 0) return ZKB_OK;
+    if (!ctx->gp_flag) ZKB_CUDA(ctx, cudaMalloc((void **)&ctx->gp_flag, 256));
+    unsigned long long *slot = (unsigned long long *)(ctx->gp_flag + 8);
+    ZKB_CUDA(ctx, cudaMemsetAsync(slot, 0, 8, ctx->stream));
+    effective_len_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)coeffs_dev, n, slot);
+    ctx->launches += 1;
+    ZKB_CUDA(ctx, cudaGetLastError());
+    unsigned long long v = 0;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(&v, slot, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_len = (size_t)v;
     return ZKB_OK;
 }
 

@@ -1,0 +1,441 @@
+"""prover.py -- the five prover rounds of zkt-plonk (plonk-core/src/proof_system/prove.rs:59-470) driven over the
+sm_100a kernels, every polynomial resident in HBM between rounds.
+
+`setup`  mirrors proof_system/setup.rs:42-166 (10 iFFTs + 10 commitments + key extension),
+`prove`  mirrors proof_system/prove.rs:59-470 round by round (same transcript schedule, same blinder order,
+         same trailing-zero truncation semantics of DensePolynomial), and `Proof.to_bytes` follows the derived
+         CanonicalSerialize of proof_system/proof.rs:106-155 (11 compressed G1, 2 x (w + Option tag), 12 Fr).
+
+Only challenges (32 B), commitments (64 B), evaluations and the 19 blinders cross PCIe.  The heavy steps are calls
+into a *backend*: `GpuBackend` (this file, libzkb200.so) is the product; tests run the same schedule over an
+oracle backend (oracle/plonk_ref.py) and check the resulting proofs byte for byte and against a restated verifier.
+Host-side witness plumbing (wire gathers, f = q_lookup * c, combine_split) stays on the host, as SURVEY.md 8f says.
+"""
+import numpy as np
+
+from . import field
+from .transcript import MerlinTranscript, fr_bytes
+
+P = field.R_MOD
+Q = field.Q_MOD
+_RINV_R = pow(field.MONT_R, -1, P)
+_RINV_Q = pow(field.MONT_R, -1, Q)
+
+
+# ------------------------------------------------------------------------------------------------ conversions
+def fr_to_limbs(x):
+    """canonical int -> (4,) uint64 Montgomery limbs."""
+    return np.array(field.int_to_limbs(field.to_mont(x)), dtype=np.uint64)
+
+
+def limbs_to_fr(l):
+    return field.limbs_to_int(l) * _RINV_R % P
+
+
+def ints_to_mont_array(vals):
+    """list/array of canonical ints -> (n, 4) uint64 Montgomery limbs (vectorised over Python ints)."""
+    v = np.array([int(x) * field.MONT_R % P for x in vals], dtype=object)
+    out = np.empty((len(v), 4), dtype=np.uint64)
+    m = (1 << 64) - 1
+    for k in range(4):
+        out[:, k] = ((v >> (64 * k)) & m).astype(np.uint64)
+    return out
+
+
+def mont_array_to_ints(a):
+    a = np.asarray(a, dtype=np.uint64).reshape(-1, 4)
+    v = a[:, 0].astype(object)
+    for k in range(1, 4):
+        v = v + (a[:, k].astype(object) << (64 * k))
+    return [int(x) * _RINV_R % P for x in v]
+
+
+def point_to_ints(xy, is_inf):
+    """(8,) uint64 Montgomery affine -> (x, y) canonical ints, or None for the identity."""
+    if is_inf:
+        return None
+    return (field.limbs_to_int(xy[:4]) * _RINV_Q % Q, field.limbs_to_int(xy[4:]) * _RINV_Q % Q)
+
+
+def g1_compressed(pt):
+    """GroupAffine::serialize (ark-ec 0.3 / ark-serialize 0.3 SWFlags): x little endian with flags in the top two
+    bits of the last byte: bit 6 = infinity, bit 7 = (y > -y)."""
+    if pt is None:
+        b = bytearray(32)
+        b[31] |= 1 << 6
+        return bytes(b)
+    x, y = pt
+    b = bytearray(int(x).to_bytes(32, "little"))
+    if y > (Q - y) % Q:
+        b[31] |= 1 << 7
+    return bytes(b)
+
+
+# ------------------------------------------------------------------------------------------------ data classes
+class Poly:
+    """Coefficients in a backend buffer with spare capacity; `len` follows DensePolynomial's truncation."""
+    __slots__ = ("data", "len")
+
+    def __init__(self, data, length):
+        self.data, self.len = data, length
+
+
+class Circuit:
+    """A synthesised circuit in evaluation form (what SetupComposer / ProvingComposer hold after pad_to(n)).
+
+    selectors: dict q_m,q_l,q_r,q_o,q_c,q_lookup -> (n,4) Montgomery; sigma: (sigma1,sigma2,sigma3) evals (n,4);
+    table: list of canonical ints (<= table_size entries); witness a,b,c: (n,4) Montgomery; pi: {row: int}."""
+
+    def __init__(self, log_n, selectors, sigma, table, table_size, a, b, c, pi):
+        self.log_n, self.n = log_n, 1 << log_n
+        self.selectors, self.sigma, self.table, self.table_size = selectors, sigma, table, table_size
+        self.a, self.b, self.c, self.pi = a, b, c, dict(sorted(pi.items()))
+
+
+class ProverKey:
+    def __init__(self, polys, evals, epk, n, log_n):
+        self.polys, self.evals, self.epk, self.n, self.log_n = polys, evals, epk, n, log_n
+
+
+class VerifierKey:
+    ORDER = ("q_m", "q_l", "q_r", "q_o", "q_c", "sigma1", "sigma2", "sigma3", "q_lookup", "q_table")
+
+    def __init__(self, n, pi_roots, commits):
+        self.n, self.pi_roots, self.commits = n, pi_roots, commits
+
+    def seed_transcript(self, tr):
+        """keys/mod.rs:260-275."""
+        tr.append_u64("circuit_size", self.n)
+        for name in self.ORDER:
+            tr.append_commitment(name + "_commit", self.commits[name])
+
+
+class Proof:
+    COMMITS = ("a", "b", "c", "t", "h1", "h2", "z1", "z2", "q_lo", "q_mid", "q_hi")
+    EVALS = ("a", "b", "c", "sigma1", "sigma2", "z1_next", "q_lookup", "t", "t_next", "z2_next", "h1_next", "h2")
+
+    def __init__(self, commits, aw, saw, evals):
+        self.commits, self.aw, self.saw, self.evals = commits, aw, saw, evals
+
+    def to_bytes(self):
+        out = b"".join(g1_compressed(self.commits[k]) for k in self.COMMITS)
+        out += g1_compressed(self.aw) + b"\x00"            # kzg10::Proof { w, random_v: None }
+        out += g1_compressed(self.saw) + b"\x00"
+        out += b"".join(fr_bytes(self.evals[k]) for k in self.EVALS)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ host plumbing
+def table_multiset(table, table_size, n):
+    """LookupTable::into_multiset (lookup/table.rs:52-61): table entries then zeros up to n."""
+    assert n > table_size and len(table) <= table_size
+    return list(table) + [0] * (n - len(table))
+
+
+def table_masks(table_size, n):
+    """LookupTable::masks (lookup/table.rs:42-48): q_table evaluations."""
+    assert n > table_size
+    return [0] * table_size + [1] * (n - table_size)
+
+
+def combine_split(t, f):
+    """MultiSet::combine_split (lookup/multiset.rs:103-146) on canonical ints."""
+    counters = {}
+    for e in t:
+        counters[e] = counters.get(e, 0) + 1
+    for e in f:
+        if e not in counters:
+            raise ValueError("ElementNotIndexedInTable")
+        counters[e] += 1
+    evens, odds, parity = [], [], False
+    for e, cnt in counters.items():
+        half = cnt // 2
+        evens.extend([e] * half)
+        odds.extend([e] * half)
+        if cnt % 2 == 1:
+            if parity:
+                odds.append(e)
+                parity = False
+            else:
+                evens.append(e)
+                parity = True
+    return evens, odds
+
+
+# ------------------------------------------------------------------------------------------------ GPU backend
+class GpuBackend:
+    """Heavy steps on the device through the C ABI (zkt_plonk_b200.Context / GpuKZG10)."""
+
+    def __init__(self, kzg):
+        import torch
+        self.torch = torch
+        self.kzg, self.ctx = kzg, kzg.ctx
+        self.dev = torch.device("cuda", self.ctx.device)
+
+    # -- storage
+    def from_host(self, a, cap=None):
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        cap = a.shape[0] if cap is None else cap
+        buf = self.torch.zeros((cap, 4), dtype=self.torch.int64, device=self.dev)
+        if a.shape[0]:
+            buf[: a.shape[0]] = self.torch.from_numpy(a.view(np.int64)).to(self.dev)
+        return buf
+
+    def to_host(self, buf, length):
+        return buf[:length].cpu().numpy().view(np.uint64)
+
+    def slice_copy(self, buf, lo, hi, cap):
+        out = self.torch.zeros((cap, 4), dtype=self.torch.int64, device=self.dev)
+        out[: hi - lo] = buf[lo:hi]
+        return out
+
+    def get(self, buf, i):
+        return limbs_to_fr(buf[i].cpu().numpy().view(np.uint64))
+
+    def put(self, buf, i, value):
+        buf[i] = self.torch.from_numpy(fr_to_limbs(value).view(np.int64)).to(self.dev)
+
+    # -- transforms / commitments
+    def ifft(self, evals, log_n, cap):
+        n = 1 << log_n
+        out = self.torch.zeros((cap, 4), dtype=self.torch.int64, device=self.dev)
+        out[:n] = evals[:n]
+        self.ctx.ntt_dev(out, log_n, True, False)
+        return out
+
+    def effective_len(self, buf, n):
+        return self.ctx.poly_effective_len_dev(buf, n)
+
+    def add_blinders(self, poly, blinders):
+        b = np.stack([fr_to_limbs(x) for x in blinders])
+        self.ctx.poly_add_blinders_dev(poly.data, poly.len, b)
+        poly.len += len(blinders)
+
+    def commit(self, poly):
+        if poly.len == 0:
+            return None
+        xy, inf = self.kzg.commit_dev(poly.data, poly.len)
+        return point_to_ints(xy, inf)
+
+    # -- argument math
+    def z1_poly(self, log_n, beta, gamma, a, b, c, s1, s2, s3, cap):
+        n = 1 << log_n
+        z = self.torch.zeros((cap, 4), dtype=self.torch.int64, device=self.dev)
+        self.ctx.z1_evals_dev(log_n, fr_to_limbs(beta), fr_to_limbs(gamma), a, b, c, s1, s2, s3, z)
+        if self.ctx.grand_product_failed():
+            raise ZeroDivisionError("compute_z1_poly: zero denominator")
+        self.ctx.ntt_dev(z, log_n, True, False)
+        return z
+
+    def z2_poly(self, log_n, delta, eps, f, t, h1, h2, cap):
+        z = self.torch.zeros((cap, 4), dtype=self.torch.int64, device=self.dev)
+        self.ctx.z2_evals_dev(log_n, fr_to_limbs(delta), fr_to_limbs(eps), f, t, h1, h2, z)
+        if self.ctx.grand_product_failed():
+            raise ZeroDivisionError("compute_z2_poly: zero denominator")
+        self.ctx.ntt_dev(z, log_n, True, False)
+        return z
+
+    def extend_prover_key(self, log_n, polys):
+        """keys/mod.rs:78-146: 10 coset tables on 4n + l_1_coset (x_coset / zh_coset are computed in the kernel)."""
+        from .prover_ops import EPK_ORDER
+        n4 = 4 << log_n
+        epk = {}
+        for name in EPK_ORDER[:-1]:
+            p = polys[name]
+            buf = self.torch.zeros((n4, 4), dtype=self.torch.int64, device=self.dev)
+            buf[: p.len] = p.data[: p.len]
+            self.ctx.ntt_dev(buf, log_n + 2, False, True, length=p.len)
+            epk[name] = buf
+        epk["l1"] = self.ctx.l1_coset_dev(log_n, self.torch.empty((n4, 4), dtype=self.torch.int64, device=self.dev))
+        return epk
+
+    def quotient(self, log_n, epk, ch, polys):
+        """quotient_poly::compute: 9 coset FFTs, the fused kernel, one coset iFFT; returns 4n coefficients."""
+        from .prover_ops import EPK_ORDER, WIT_ORDER
+        n4 = 4 << log_n
+        wit = []
+        for name in WIT_ORDER:
+            p = polys[name]
+            buf = self.torch.zeros((n4, 4), dtype=self.torch.int64, device=self.dev)
+            buf[: p.len] = p.data[: p.len]
+            self.ctx.ntt_dev(buf, log_n + 2, False, True, length=p.len)
+            wit.append(buf)
+        chal = np.stack([fr_to_limbs(x) for x in ch])
+        out = self.torch.empty((n4, 4), dtype=self.torch.int64, device=self.dev)
+        self.ctx.quotient_evals_dev(log_n, chal, wit, [epk[k] for k in EPK_ORDER], out)
+        del wit
+        self.ctx.ntt_dev(out, log_n + 2, True, True)
+        return out
+
+    def evaluate(self, poly, z):
+        return limbs_to_fr(self.ctx.poly_eval_dev(poly.data, poly.len, fr_to_limbs(z)))
+
+    def lincomb(self, polys, scalars, cap=None):
+        m = max(p.len for p in polys)
+        out = self.torch.zeros((cap or m, 4), dtype=self.torch.int64, device=self.dev)
+        sc = np.stack([fr_to_limbs(s) for s in scalars])
+        self.ctx.poly_lincomb_dev([p.data for p in polys], [p.len for p in polys], sc, out, m)
+        return Poly(out, m)
+
+    def divide_linear(self, poly, z):
+        quot = self.torch.zeros((max(poly.len - 1, 1), 4), dtype=self.torch.int64, device=self.dev)
+        ev = self.ctx.poly_divide_linear_dev(poly.data, poly.len, fr_to_limbs(z), quot)
+        return Poly(quot, max(poly.len - 1, 0)), limbs_to_fr(ev)
+
+
+# ------------------------------------------------------------------------------------------------ setup / prove
+def _poly_from_evals(be, evals_host, log_n, cap):
+    """poly_from_evals: iFFT then DensePolynomial truncation."""
+    n = 1 << log_n
+    buf = be.ifft(be.from_host(evals_host), log_n, cap)
+    return Poly(buf, be.effective_len(buf, n))
+
+
+def setup(be, circuit):
+    """proof_system/setup.rs:42-166 with extend = true.  Returns (ProverKey, VerifierKey)."""
+    n, log_n = circuit.n, circuit.log_n
+    sel = circuit.selectors
+    polys = {name: _poly_from_evals(be, sel[name], log_n, n) for name in ("q_m", "q_l", "q_r", "q_o", "q_c", "q_lookup")}
+    for k, name in enumerate(("sigma1", "sigma2", "sigma3")):
+        polys[name] = _poly_from_evals(be, circuit.sigma[k], log_n, n)
+    polys["q_table"] = _poly_from_evals(be, ints_to_mont_array(table_masks(circuit.table_size, n)), log_n, n)
+    commits = {name: be.commit(polys[name]) for name in VerifierKey.ORDER}
+    w = field.root_of_unity(log_n)
+    pi_roots = [pow(w, pos, P) for pos in circuit.pi.keys()]
+    vk = VerifierKey(n, pi_roots, commits)
+    evals = {"sigma1": be.from_host(circuit.sigma[0]), "sigma2": be.from_host(circuit.sigma[1]),
+             "sigma3": be.from_host(circuit.sigma[2]), "q_lookup": sel["q_lookup"]}
+    epk = be.extend_prover_key(log_n, polys)
+    return ProverKey(polys, evals, epk, n, log_n), vk
+
+
+def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
+    """proof_system::prove (prove.rs:59-470).  blinders: the 19 field elements the reference draws with F::rand, in
+    draw order a(2) b(2) c(2) h1(3) h2(2) z1(3) z2(3) b0 b1.  Returns a Proof."""
+    n, log_n = pk.n, pk.log_n
+    assert len(blinders) == 19
+    bl = iter(blinders)
+    take = lambda k: [next(bl) for _ in range(k)]
+    tr = transcript
+    if tr is None:
+        tr = MerlinTranscript("ZKT Plonk")                    # plonk.rs:107
+        vk.seed_transcript(tr)
+    cap = n + 8
+    w_n = field.root_of_unity(log_n)
+
+    # ---- round 1: wires
+    tr.append_scalars("pi", list(circuit.pi.values()))          # prove.rs:110
+    a_ev, b_ev, c_ev = be.from_host(circuit.a), be.from_host(circuit.b), be.from_host(circuit.c)
+    wires = {}
+    for name, ev in (("a", a_ev), ("b", b_ev), ("c", c_ev)):
+        buf = be.ifft(ev, log_n, cap)
+        p = Poly(buf, be.effective_len(buf, n))
+        be.add_blinders(p, take(2))
+        wires[name] = p
+    commits = {k: be.commit(wires[k]) for k in ("a", "b", "c")}
+    for k in ("a", "b", "c"):
+        tr.append_commitment(k + "_commit", commits[k])
+
+    # ---- round 2: lookup multisets (host side: prove.rs:145-167, multiset.rs:103-146)
+    t_vals = table_multiset(circuit.table, circuit.table_size, n)
+    c_ints = mont_array_to_ints(circuit.c)
+    ql_ints = mont_array_to_ints(pk.evals["q_lookup"])
+    f_vals = [q * c % P for q, c in zip(ql_ints, c_ints)]
+    h1_vals, h2_vals = combine_split(t_vals, f_vals)
+    t_ev, f_ev = be.from_host(ints_to_mont_array(t_vals)), be.from_host(ints_to_mont_array(f_vals))
+    h1_ev, h2_ev = be.from_host(ints_to_mont_array(h1_vals)), be.from_host(ints_to_mont_array(h2_vals))
+    polys = dict(wires)
+    for name, ev, k in (("t", t_ev, 0), ("h1", h1_ev, 3), ("h2", h2_ev, 2)):
+        buf = be.ifft(ev, log_n, cap)
+        p = Poly(buf, be.effective_len(buf, n))
+        if k:
+            be.add_blinders(p, take(k))
+        polys[name] = p
+    for k in ("t", "h1", "h2"):
+        commits[k] = be.commit(polys[k])
+        tr.append_commitment(k + "_commit", commits[k])
+
+    beta, gamma = tr.challenge_scalar("beta"), tr.challenge_scalar("gamma")
+    delta, epsilon = tr.challenge_scalar("delta"), tr.challenge_scalar("epsilon")
+    assert len({beta, gamma, delta, epsilon}) == 4, "challenges must be different"
+
+    # ---- round 3: grand products
+    buf = be.z1_poly(log_n, beta, gamma, a_ev, b_ev, c_ev, pk.evals["sigma1"], pk.evals["sigma2"], pk.evals["sigma3"], cap)
+    polys["z1"] = Poly(buf, be.effective_len(buf, n))
+    be.add_blinders(polys["z1"], take(3))
+    buf = be.z2_poly(log_n, delta, epsilon, f_ev, t_ev, h1_ev, h2_ev, cap)
+    polys["z2"] = Poly(buf, be.effective_len(buf, n))
+    be.add_blinders(polys["z2"], take(3))
+    del a_ev, b_ev, c_ev, f_ev, t_ev, h1_ev, h2_ev
+    for k in ("z1", "z2"):
+        commits[k] = be.commit(polys[k])
+        tr.append_commitment(k + "_commit", commits[k])
+
+    # ---- round 4: quotient
+    pi_evals = [0] * n
+    for pos, v in circuit.pi.items():
+        pi_evals[pos] = v
+    polys["pi"] = _poly_from_evals(be, ints_to_mont_array(pi_evals), log_n, n)
+    alpha = tr.challenge_scalar("alpha")
+    q_buf = be.quotient(log_n, pk.epk, (alpha, beta, gamma, delta, epsilon), polys)
+    q_len = be.effective_len(q_buf, 4 * n)
+    assert q_len >= 2 * (n + 2), "quotient shorter than 2(n+2): the reference's slice would panic"
+    parts = []
+    for lo, hi in ((0, n + 2), (n + 2, 2 * (n + 2)), (2 * (n + 2), q_len)):
+        buf = be.slice_copy(q_buf, lo, hi, n + 8)
+        parts.append(Poly(buf, be.effective_len(buf, hi - lo)))
+    del q_buf
+    q_lo, q_mid, q_hi = parts
+    b0, b1 = take(2)
+    be.put(q_lo.data, q_lo.len, b0); q_lo.len += 1            # q_lo.coeffs.push(b0)
+    be.put(q_mid.data, 0, (be.get(q_mid.data, 0) - b0) % P)   # q_mid.coeffs[0] -= b0
+    be.put(q_mid.data, q_mid.len, b1); q_mid.len += 1
+    be.put(q_hi.data, 0, (be.get(q_hi.data, 0) - b1) % P)
+    polys.update(q_lo=q_lo, q_mid=q_mid, q_hi=q_hi)
+    for k in ("q_lo", "q_mid", "q_hi"):
+        commits[k] = be.commit(polys[k])
+        tr.append_commitment(k + "_commit", commits[k])
+    xi = tr.challenge_scalar("xi")
+
+    # ---- round 5: linearisation (linearization_poly.rs:19-121) and openings
+    shifted = xi * w_n % P
+    zh = (pow(xi, n, P) - 1) % P
+    l1 = zh * pow(n * (xi - 1) % P, -1, P) % P
+    kp = pk.polys
+    ev = {"a": be.evaluate(polys["a"], xi), "b": be.evaluate(polys["b"], xi), "c": be.evaluate(polys["c"], xi),
+          "sigma1": be.evaluate(kp["sigma1"], xi), "sigma2": be.evaluate(kp["sigma2"], xi),
+          "z1_next": be.evaluate(polys["z1"], shifted), "q_lookup": be.evaluate(kp["q_lookup"], xi),
+          "t": be.evaluate(polys["t"], xi), "t_next": be.evaluate(polys["t"], shifted),
+          "z2_next": be.evaluate(polys["z2"], shifted), "h1_next": be.evaluate(polys["h1"], shifted),
+          "h2": be.evaluate(polys["h2"], xi)}
+    a_, b_, c_ = ev["a"], ev["b"], ev["c"]
+    al2, al3 = alpha * alpha % P, pow(alpha, 3, P)
+    al4, al5 = pow(alpha, 4, P), pow(alpha, 5, P)
+    bxi = beta * xi % P
+    opd = (1 + delta) % P
+    eopd = epsilon * opd % P
+    s_z1 = (alpha * (bxi + a_ + gamma) % P * (bxi * field.K1 + b_ + gamma) % P * (bxi * field.K2 + c_ + gamma) + l1 * al2) % P
+    s_sigma3 = (-alpha * beta % P * ev["z1_next"] % P * (beta * ev["sigma1"] + a_ + gamma) % P * (beta * ev["sigma2"] + b_ + gamma)) % P
+    s_z2 = (al3 * opd % P * (epsilon + ev["q_lookup"] * c_) % P * (eopd + ev["t"] + delta * ev["t_next"]) + al4 * l1) % P
+    s_h1 = (-al3 * ev["z2_next"] % P * (eopd + ev["h2"] + delta * ev["h1_next"])) % P
+    s_qtable = al5 * ev["t"] % P
+    xn2 = (zh + 1) * xi % P * xi % P                           # xi^(n+2)
+    terms = [(kp["q_m"], a_ * b_ % P), (kp["q_l"], a_), (kp["q_r"], b_), (kp["q_o"], c_), (kp["q_c"], 1),
+             (polys["z1"], s_z1), (kp["sigma3"], s_sigma3), (polys["z2"], s_z2), (polys["h1"], s_h1),
+             (kp["q_table"], s_qtable), (q_lo, (-zh) % P), (q_mid, (-zh * xn2) % P), (q_hi, (-zh * xn2 % P * xn2) % P)]
+    r_poly = be.lincomb([t[0] for t in terms], [t[1] for t in terms])
+    r_poly.len = be.effective_len(r_poly.data, r_poly.len)
+
+    for k in Proof.EVALS:
+        tr.append_scalar(k + "_eval", ev[k])
+    eta = tr.challenge_scalar("eta")
+
+    def open_at(plist, point):
+        comb = be.lincomb(plist, [pow(eta, i, P) for i in range(len(plist))])
+        wit, _ = be.divide_linear(comb, point)
+        wit.len = be.effective_len(wit.data, wit.len)
+        return be.commit(wit)
+
+    aw = open_at([r_poly, polys["a"], polys["b"], polys["c"], kp["sigma1"], kp["sigma2"], kp["q_lookup"], polys["t"], polys["h2"]], xi)
+    saw = open_at([polys["z1"], polys["z2"], polys["t"], polys["h1"]], shifted)
+    return Proof(commits, aw, saw, ev)
