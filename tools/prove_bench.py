@@ -1,0 +1,59 @@
+"""Full-prove timing on one GPU: synthetic circuit of the given size, [tau^i]G SRS built in HBM, setup once, then
+`--reps` proofs with per-round wall times (device drained at every boundary).  The proof is checked with the restated
+verifier when --verify is given (oracle/, test infrastructure).
+
+  python tools/prove_bench.py --log-n 18          # the withdraw circuit's size (n = 2^18)
+"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import zkt_plonk_b200 as z
+from zkt_plonk_b200 import prover, synthetic
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--log-n", type=int, default=18)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--verify", action="store_true")
+ap.add_argument("--no-precompute", action="store_true")
+args = ap.parse_args()
+P = prover.P
+TAU = 0x2B7E151628AED2A6ABF7158809CF4F3C762E7160F38B4DA56A784D9045190CFE % P
+n = 1 << args.log_n
+ctx = z.Context(0); ctx.set_stream(torch.cuda.current_stream())
+t0 = time.perf_counter(); circ = synthetic.make_circuit(args.log_n, seed=1); t_gen = time.perf_counter() - t0
+# SRS: powers of tau as canonical scalars, then k * G on the device
+t0 = time.perf_counter()
+pw = np.empty(n + 8, dtype=object); x = 1
+for i in range(n + 8):
+    pw[i] = x; x = x * TAU % P
+k = np.empty((n + 8, 4), dtype=np.uint64)
+for j in range(4):
+    k[:, j] = ((pw >> (64 * j)) & ((1 << 64) - 1)).astype(np.uint64)
+one_two = np.zeros((2, 4), dtype=np.uint64); one_two[0, 0] = 1; one_two[1, 0] = 2
+G = ctx.fp_binop(1, 5, one_two).reshape(8)
+srs = torch.empty((n + 8, 8), dtype=torch.int64, device="cuda")
+ctx.g1_fixed_base_mul_dev(G, torch.from_numpy(k.view(np.int64)).cuda(), n + 8, srs)
+kzg = z.GpuKZG10(ctx); kzg.load_committer_key(srs)
+if not args.no_precompute:
+    ctx.srs_precompute(0)
+torch.cuda.synchronize(); t_srs = time.perf_counter() - t0
+be = prover.GpuBackend(kzg)
+t0 = time.perf_counter(); pk, vk = prover.setup(be, circ); torch.cuda.synchronize(); t_setup = time.perf_counter() - t0
+runs = []
+for r in range(args.reps):
+    tm = {}
+    l0 = ctx.launch_count(); t0 = time.perf_counter()
+    proof = prover.prove(be, pk, vk, circ, list(range(1000 + r, 1019 + r)), timings=tm)
+    torch.cuda.synchronize()
+    tm["total_ms"] = (time.perf_counter() - t0) * 1e3
+    tm["device_rounds_ms"] = sum(v for k_, v in tm.items() if k_.startswith("round"))
+    tm["kernel_launches"] = ctx.launch_count() - l0
+    runs.append(tm)
+best = min(runs, key=lambda t: t["device_rounds_ms"])
+out = {"workload": f"plonk_plookup_prove_2^{args.log_n}", "n": n, "fixed_base_tables": not args.no_precompute,
+       "circuit_gen_s": t_gen, "srs_build_s": t_srs, "setup_s": t_setup, "best": best, "runs": runs,
+       "proof_bytes": len(proof.to_bytes())}
+if args.verify:
+    from oracle import plonk_ref
+    out["verifier_accepts"] = plonk_ref.verify(vk, proof, list(circ.pi.values()), TAU) == 0
+print(json.dumps(out))

@@ -172,6 +172,9 @@ class GpuBackend:
         self.kzg, self.ctx = kzg, kzg.ctx
         self.dev = torch.device("cuda", self.ctx.device)
 
+    def sync(self):
+        self.torch.cuda.synchronize(self.dev)
+
     # -- storage
     def from_host(self, a, cap=None):
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
@@ -312,8 +315,21 @@ def setup(be, circuit):
 def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     """proof_system::prove (prove.rs:59-470).  blinders: the 19 field elements the reference draws with F::rand, in
     draw order a(2) b(2) c(2) h1(3) h2(2) z1(3) z2(3) b0 b1.  Returns a Proof."""
+    import time
     n, log_n = pk.n, pk.log_n
     assert len(blinders) == 19
+    clock = [time.perf_counter()]
+
+    def tick(name):
+        """timings[name] += wall time since the previous tick (device work drained first)."""
+        if timings is None:
+            return
+        if hasattr(be, "sync"):
+            be.sync()
+        now = time.perf_counter()
+        timings[name] = timings.get(name, 0.0) + (now - clock[0]) * 1e3
+        clock[0] = now
+
     bl = iter(blinders)
     take = lambda k: [next(bl) for _ in range(k)]
     tr = transcript
@@ -326,6 +342,7 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     # ---- round 1: wires
     tr.append_scalars("pi", list(circuit.pi.values()))          # prove.rs:110
     a_ev, b_ev, c_ev = be.from_host(circuit.a), be.from_host(circuit.b), be.from_host(circuit.c)
+    tick("h2d_wires_ms")
     wires = {}
     for name, ev in (("a", a_ev), ("b", b_ev), ("c", c_ev)):
         buf = be.ifft(ev, log_n, cap)
@@ -335,6 +352,7 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     commits = {k: be.commit(wires[k]) for k in ("a", "b", "c")}
     for k in ("a", "b", "c"):
         tr.append_commitment(k + "_commit", commits[k])
+    tick("round1_wires_ms")
 
     # ---- round 2: lookup multisets (host side: prove.rs:145-167, multiset.rs:103-146)
     t_vals = table_multiset(circuit.table, circuit.table_size, n)
@@ -344,6 +362,7 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     h1_vals, h2_vals = combine_split(t_vals, f_vals)
     t_ev, f_ev = be.from_host(ints_to_mont_array(t_vals)), be.from_host(ints_to_mont_array(f_vals))
     h1_ev, h2_ev = be.from_host(ints_to_mont_array(h1_vals)), be.from_host(ints_to_mont_array(h2_vals))
+    tick("host_lookup_plumbing_ms")
     polys = dict(wires)
     for name, ev, k in (("t", t_ev, 0), ("h1", h1_ev, 3), ("h2", h2_ev, 2)):
         buf = be.ifft(ev, log_n, cap)
@@ -358,6 +377,7 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     beta, gamma = tr.challenge_scalar("beta"), tr.challenge_scalar("gamma")
     delta, epsilon = tr.challenge_scalar("delta"), tr.challenge_scalar("epsilon")
     assert len({beta, gamma, delta, epsilon}) == 4, "challenges must be different"
+    tick("round2_lookup_ms")
 
     # ---- round 3: grand products
     buf = be.z1_poly(log_n, beta, gamma, a_ev, b_ev, c_ev, pk.evals["sigma1"], pk.evals["sigma2"], pk.evals["sigma3"], cap)
@@ -370,6 +390,8 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     for k in ("z1", "z2"):
         commits[k] = be.commit(polys[k])
         tr.append_commitment(k + "_commit", commits[k])
+
+    tick("round3_grand_products_ms")
 
     # ---- round 4: quotient
     pi_evals = [0] * n
@@ -396,6 +418,7 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
         commits[k] = be.commit(polys[k])
         tr.append_commitment(k + "_commit", commits[k])
     xi = tr.challenge_scalar("xi")
+    tick("round4_quotient_ms")
 
     # ---- round 5: linearisation (linearization_poly.rs:19-121) and openings
     shifted = xi * w_n % P
@@ -438,4 +461,5 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
 
     aw = open_at([r_poly, polys["a"], polys["b"], polys["c"], kp["sigma1"], kp["sigma2"], kp["q_lookup"], polys["t"], polys["h2"]], xi)
     saw = open_at([polys["z1"], polys["z2"], polys["t"], polys["h1"]], shifted)
+    tick("round5_linearisation_openings_ms")
     return Proof(commits, aw, saw, ev)
