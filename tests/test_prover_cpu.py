@@ -36,6 +36,26 @@ def test_combine_split_matches_reference_unit_test_shape():
         prover.combine_split([1, 2], [3])
 
 
+def test_vectorised_host_plumbing_matches_the_reference_shaped_one():
+    rnd = random.Random(1)
+    n = 256
+    table = list(dict.fromkeys(rnd.randrange(P) for _ in range(40)))
+    t = prover.table_multiset(table, 64, n)
+    q = [rnd.choice([0, 1, 1, 5]) for _ in range(n)]
+    c = [rnd.choice(table + [0]) for _ in range(n)]
+    c = [ci if qi in (0, 1) else 0 for qi, ci in zip(q, c)]     # keep q*c inside the table
+    f = [a * b % P for a, b in zip(q, c)]
+    f_arr = prover.lookup_f_array(prover.ints_to_mont_array(q), prover.ints_to_mont_array(c))
+    assert prover.mont_array_to_ints(f_arr) == f
+    t_arr = prover.table_multiset_array(table, 64, n)
+    assert prover.mont_array_to_ints(t_arr) == t
+    h1, h2 = prover.combine_split(t, f)
+    a1, a2 = prover.combine_split_arrays(t_arr, f_arr)
+    assert prover.mont_array_to_ints(a1) == h1 and prover.mont_array_to_ints(a2) == h2
+    with pytest.raises(ValueError):
+        prover.combine_split_arrays(t_arr, prover.ints_to_mont_array([12345]))
+
+
 @pytest.mark.parametrize("log_n", [4, 6])
 def test_prove_verify_roundtrip_on_oracle_backend(log_n):
     circ = synthetic.make_circuit(log_n, seed=log_n, table_size=4)

@@ -162,6 +162,53 @@ def combine_split(t, f):
     return evens, odds
 
 
+# ---- the same plumbing on (n, 4) uint64 Montgomery limb arrays (numpy, no Python-int loop over n) -----------------
+_ONE_MONT = np.array(field.int_to_limbs(field.to_mont(1)), dtype=np.uint64)
+
+
+def table_multiset_array(table, table_size, n):
+    assert n > table_size and len(table) <= table_size
+    out = np.zeros((n, 4), dtype=np.uint64)
+    if len(table):
+        out[: len(table)] = ints_to_mont_array(table)
+    return out
+
+
+def lookup_f_array(q_lookup, c):
+    """f_i = q_lookup_i * c_i (prove.rs:157-161).  Selector values 0 and 1 are handled as masks; anything else
+    falls back to exact integer arithmetic for those rows only."""
+    q_lookup, c = np.asarray(q_lookup, dtype=np.uint64), np.asarray(c, dtype=np.uint64)
+    is_zero = ~q_lookup.any(axis=1)
+    is_one = (q_lookup == _ONE_MONT).all(axis=1)
+    f = np.where(is_one[:, None], c, np.uint64(0))
+    other = np.flatnonzero(~(is_zero | is_one))
+    if other.size:
+        qi, ci = mont_array_to_ints(q_lookup[other]), mont_array_to_ints(c[other])
+        f[other] = ints_to_mont_array([a * b % P for a, b in zip(qi, ci)])
+    return np.ascontiguousarray(f)
+
+
+def combine_split_arrays(t, f):
+    """MultiSet::combine_split (lookup/multiset.rs:103-146): buckets in order of first appearance in t, every
+    element of f must be in t, halves alternate on odd counts.  Montgomery limb rows are unique per field element,
+    so they serve as keys directly."""
+    t, f = np.ascontiguousarray(t, dtype=np.uint64), np.ascontiguousarray(f, dtype=np.uint64)
+    key_t = np.dtype((np.void, 32))
+    allk = np.concatenate([t, f]).view(key_t).reshape(-1)
+    _, first, counts = np.unique(allk, return_index=True, return_counts=True)
+    if (first >= t.shape[0]).any():
+        raise ValueError("ElementNotIndexedInTable")
+    order = np.argsort(first, kind="stable")                   # IndexMap insertion order
+    first, counts = first[order], counts[order]
+    half, odd = counts // 2, (counts % 2).astype(bool)
+    rank = np.cumsum(odd) - 1                                   # k-th odd bucket: even k -> evens, odd k -> odds
+    to_even = odd & (rank % 2 == 0)
+    keys = np.concatenate([t, f])[first]
+    evens = np.repeat(keys, half + to_even, axis=0)
+    odds = np.repeat(keys, half + (odd & ~to_even), axis=0)
+    return np.ascontiguousarray(evens), np.ascontiguousarray(odds)
+
+
 # ------------------------------------------------------------------------------------------------ GPU backend
 class GpuBackend:
     """Heavy steps on the device through the C ABI (zkt_plonk_b200.Context / GpuKZG10)."""
@@ -355,13 +402,11 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     tick("round1_wires_ms")
 
     # ---- round 2: lookup multisets (host side: prove.rs:145-167, multiset.rs:103-146)
-    t_vals = table_multiset(circuit.table, circuit.table_size, n)
-    c_ints = mont_array_to_ints(circuit.c)
-    ql_ints = mont_array_to_ints(pk.evals["q_lookup"])
-    f_vals = [q * c % P for q, c in zip(ql_ints, c_ints)]
-    h1_vals, h2_vals = combine_split(t_vals, f_vals)
-    t_ev, f_ev = be.from_host(ints_to_mont_array(t_vals)), be.from_host(ints_to_mont_array(f_vals))
-    h1_ev, h2_ev = be.from_host(ints_to_mont_array(h1_vals)), be.from_host(ints_to_mont_array(h2_vals))
+    t_arr = table_multiset_array(circuit.table, circuit.table_size, n)
+    f_arr = lookup_f_array(pk.evals["q_lookup"], circuit.c)
+    h1_arr, h2_arr = combine_split_arrays(t_arr, f_arr)
+    assert h1_arr.shape[0] == n and h2_arr.shape[0] == n
+    t_ev, f_ev, h1_ev, h2_ev = (be.from_host(x) for x in (t_arr, f_arr, h1_arr, h2_arr))
     tick("host_lookup_plumbing_ms")
     polys = dict(wires)
     for name, ev, k in (("t", t_ev, 0), ("h1", h1_ev, 3), ("h2", h2_ev, 2)):
@@ -394,10 +439,10 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     tick("round3_grand_products_ms")
 
     # ---- round 4: quotient
-    pi_evals = [0] * n
-    for pos, v in circuit.pi.items():
-        pi_evals[pos] = v
-    polys["pi"] = _poly_from_evals(be, ints_to_mont_array(pi_evals), log_n, n)
+    pi_evals = np.zeros((n, 4), dtype=np.uint64)                # PublicInputs::as_evals (pi.rs:75-82)
+    if circuit.pi:
+        pi_evals[list(circuit.pi.keys())] = ints_to_mont_array(list(circuit.pi.values()))
+    polys["pi"] = _poly_from_evals(be, pi_evals, log_n, n)
     alpha = tr.challenge_scalar("alpha")
     q_buf = be.quotient(log_n, pk.epk, (alpha, beta, gamma, delta, epsilon), polys)
     q_len = be.effective_len(q_buf, 4 * n)
