@@ -242,6 +242,11 @@ __global__ void __launch_bounds__(256) msm_task_scatter_kernel(const uint32_t *c
 }
 
 // ------------------------------------------------------------------ bucket accumulation (the hot kernel)
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + 32));
+}
+
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__restrict__ points, const uint32_t *__restrict__ sorted,
                                                              const uint32_t *__restrict__ counts, const uint32_t *__restrict__ starts,
                                                              const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_base,
@@ -255,11 +260,16 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__rest
     const uint32_t *idx = sorted + starts[b] + s * SEG;
 
     g1x_t acc = g1x_inf();
+    // Three-deep gather pipeline: L2 prefetch PF points ahead (no registers held; the fixed-base tables are far
+    // larger than L2, so every gather is an HBM access), register load one point ahead, add the current point.
+    constexpr uint32_t PF = 6;
+    for (uint32_t k = 1; k < PF && k < cnt; ++k) prefetch_l2(points + (idx[k] & ~SIGN_BIT));
     uint32_t v = idx[0];
     g1a_t p = g1a_load(points + (v & ~SIGN_BIT));
     for (uint32_t k = 0; k < cnt; ++k) {
         uint32_t vn = 0;
         g1a_t pn;
+        if (k + PF < cnt) prefetch_l2(points + (idx[k + PF] & ~SIGN_BIT));
         if (k + 1 < cnt) {                                   // issue the next gather before the addition
             vn = idx[k + 1];
             pn = g1a_load(points + (vn & ~SIGN_BIT));
@@ -515,7 +525,7 @@ uint32_t pick_window(size_t n, bool shared_buckets) {
     for (uint32_t c = 6; c <= 22; ++c) {
         uint32_t wide, W = shared_buckets ? balanced_windows(c, &wide) : 254 / c + 1;
         double groups = shared_buckets ? 1.0 : (double)W;
-        double cost = (double)n * W + (shared_buckets ? 6.5 : 4.0) * groups * (double)(1u << (c - 1));
+        double cost = (double)n * W + (shared_buckets ? 3.0 : 4.0) * groups * (double)(1u << (c - 1));
         if (cost < best) { best = cost; best_c = c; }
     }
     return best_c;
