@@ -59,6 +59,29 @@ __device__ __forceinline__ fe_t pow2lvl(const uint4 *tab, uint32_t s, unsigned l
     return fmul<FrP>(a, b);
 }
 
+// inter-pass twiddle / output scaling and the store of output k of this tile (shared by both store paths)
+__device__ __forceinline__ void emit_output(const PassArgs &a, unsigned long long c, unsigned long long r,
+                                            unsigned long long base, uint32_t k, fe_t v) {
+    unsigned long long o;
+    if (!(a.mode & M_LAST)) {
+        v = fmul<FrP>(v, pow2lvl(a.tw2, a.tw_s, c * k));
+        o = base + ((unsigned long long)k << a.log_s);
+    } else {
+        // r = k1 * 2^t2 + k2  ->  K = k1 + 2^t1 * k2 + 2^(t1+t2) * k
+        unsigned long long k1 = r >> a.t2, k2 = r & ((1ull << a.t2) - 1);
+        o = k1 + (k2 << a.t1) + ((unsigned long long)k << (a.log_n - a.t));
+        if (a.mode & M_OUT_COSET) v = fmul<FrP>(v, pow2lvl(a.cs2, a.cs_s, o));
+        else if (a.mode & M_OUT_CONST) v = fmul<FrP>(v, a.scale);
+    }
+    fstore(a.out + 2 * o, v);
+}
+
+__device__ __forceinline__ void bfly(fe_t &u, fe_t &v) {        // (u, v) <- (u + v, u - v)
+    fe_t s = fadd<FrP>(u, v);
+    v = fsub<FrP>(u, v);
+    u = s;
+}
+
 __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
     extern __shared__ uint4 sm[];
     const uint32_t T = 1u << a.t;
@@ -83,8 +106,9 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
         sm_store(s_lo, s_hi, j, v);
     }
 
-    // ---- t stages of decimation in frequency
-    for (uint32_t lh = a.t; lh-- > 0;) {              // h = 2^lh : butterfly half distance
+    // ---- decimation in frequency through shared memory, down to (not including) the last three stages
+    const uint32_t tail = a.t >= 3 ? 3 : 0;           // stages done in registers
+    for (uint32_t lh = a.t; lh-- > tail;) {           // h = 2^lh : butterfly half distance
         __syncthreads();
         const uint32_t h = 1u << lh;
         const uint32_t tw_shift = a.t - 1 - lh;       // twiddle index = j * (T / 2h)
@@ -102,22 +126,34 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
     }
     __syncthreads();
 
-    // ---- store: shared index i holds output k = bitrev_t(i)
-    for (uint32_t i = tid; i < T; i += NT) {
-        uint32_t k = a.t ? (__brev(i) >> (32 - a.t)) : 0;
-        fe_t v = sm_load(s_lo, s_hi, i);
-        unsigned long long o;
-        if (!(a.mode & M_LAST)) {
-            v = fmul<FrP>(v, pow2lvl(a.tw2, a.tw_s, c * k));
-            o = base + ((unsigned long long)k << a.log_s);
-        } else {
-            // r = k1 * 2^t2 + k2  ->  K = k1 + 2^t1 * k2 + 2^(t1+t2) * k
-            unsigned long long k1 = r >> a.t2, k2 = r & ((1ull << a.t2) - 1);
-            o = k1 + (k2 << a.t1) + ((unsigned long long)k << (a.log_n - a.t));
-            if (a.mode & M_OUT_COSET) v = fmul<FrP>(v, pow2lvl(a.cs2, a.cs_s, o));
-            else if (a.mode & M_OUT_CONST) v = fmul<FrP>(v, a.scale);
+    if (!tail) {                                       // tiny tiles: store straight from shared memory
+        for (uint32_t i = tid; i < T; i += NT) {
+            uint32_t k = a.t ? (__brev(i) >> (32 - a.t)) : 0;
+            emit_output(a, c, r, base, k, sm_load(s_lo, s_hi, i));
         }
-        fstore(a.out + 2 * o, v);
+        return;
+    }
+
+    // ---- last three stages (h = 4, 2, 1) on 8 consecutive elements held in registers: 5 twiddle products
+    // instead of 12 (w_8^0 and w_4^0 are 1, the last stage has no twiddle), no barriers, no bank conflicts,
+    // and the results go to global memory without another trip through shared memory
+    const fe_t w8_1 = fload_ro(a.tile_tw + 2 * (size_t)(T >> 3));
+    const fe_t w8_2 = fload_ro(a.tile_tw + 2 * (size_t)(T >> 2));      // = w_4
+    const fe_t w8_3 = fload_ro(a.tile_tw + 2 * (size_t)(3 * (T >> 3)));
+    for (uint32_t q = tid; q < (T >> 3); q += NT) {
+        fe_t x[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) x[p] = sm_load(s_lo, s_hi, 8 * q + p);
+        bfly(x[0], x[4]); bfly(x[1], x[5]); bfly(x[2], x[6]); bfly(x[3], x[7]);
+        x[5] = fmul<FrP>(x[5], w8_1); x[6] = fmul<FrP>(x[6], w8_2); x[7] = fmul<FrP>(x[7], w8_3);
+        bfly(x[0], x[2]); bfly(x[1], x[3]); bfly(x[4], x[6]); bfly(x[5], x[7]);
+        x[3] = fmul<FrP>(x[3], w8_2); x[7] = fmul<FrP>(x[7], w8_2);
+        bfly(x[0], x[1]); bfly(x[2], x[3]); bfly(x[4], x[5]); bfly(x[6], x[7]);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            uint32_t k = __brev(8 * q + p) >> (32 - a.t);
+            emit_output(a, c, r, base, k, x[p]);
+        }
     }
 }
 
