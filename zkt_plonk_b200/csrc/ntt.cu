@@ -38,7 +38,12 @@ struct PassArgs {
     fe_t scale;             // n^-1 for a plain inverse transform
 };
 
+// One spare 16-byte unit after every 8 elements: the register tail reads 8 consecutive elements per thread
+// (stride 8 between threads), which would otherwise put a whole quarter-warp on one bank group.
+__device__ __forceinline__ uint32_t sm_idx(uint32_t i) { return i + (i >> 3); }
+
 __device__ __forceinline__ fe_t sm_load(const uint4 *lo, const uint4 *hi, uint32_t i) {
+    i = sm_idx(i);
     uint4 a = lo[i], b = hi[i];
     fe_t r;
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
@@ -46,6 +51,7 @@ __device__ __forceinline__ fe_t sm_load(const uint4 *lo, const uint4 *hi, uint32
     return r;
 }
 __device__ __forceinline__ void sm_store(uint4 *lo, uint4 *hi, uint32_t i, const fe_t &r) {
+    i = sm_idx(i);
     lo[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
     hi[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
@@ -85,7 +91,7 @@ __device__ __forceinline__ void bfly(fe_t &u, fe_t &v) {        // (u, v) <- (u 
 __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
     extern __shared__ uint4 sm[];
     const uint32_t T = 1u << a.t;
-    uint4 *s_lo = sm, *s_hi = sm + T;
+    uint4 *s_lo = sm, *s_hi = sm + T + (T >> 3) + 1;
     const uint32_t tid = threadIdx.x, NT = blockDim.x;
 
     const unsigned long long tile = blockIdx.x;
@@ -262,7 +268,7 @@ int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int 
         if (rc) return rc;
     }
 
-    ZKB_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    ZKB_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
 
     const uint4 *cs2 = nullptr;
     uint32_t cs_s = 0;
@@ -305,9 +311,11 @@ int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int 
         if (last && inverse) a.mode |= coset ? M_OUT_COSET : M_OUT_CONST;
         a.scale = to_dev(ninv);
         const size_t T = (size_t)1 << t;
-        unsigned threads = (unsigned)(T / 2 < 32 ? 32 : (T / 2 > 256 ? 256 : T / 2));
+        // one thread per 8 elements: every thread is busy in the register tail and runs 4 butterflies per stage
+        unsigned threads = (unsigned)(T / 8 < 32 ? 32 : (T / 8 > 256 ? 256 : T / 8));
         size_t tiles = n >> t;
-        ntt_pass_kernel<<<(unsigned)tiles, threads, T * 32, ctx->stream>>>(a);
+        size_t smem = 2 * (T + T / 8 + 1) * 16;
+        ntt_pass_kernel<<<(unsigned)tiles, threads, smem, ctx->stream>>>(a);
         ctx->launches += 1;
         ZKB_CUDA(ctx, cudaGetLastError());
     }
