@@ -75,6 +75,11 @@ ZKB_API int zkb_ntt_dev(zkb_ctx *ctx, uint64_t *data_dev, size_t len, unsigned l
 ZKB_API int zkb_ntt_batch_dev(zkb_ctx *ctx, uint64_t *const *ptrs_host, size_t count, size_t len, unsigned log_n,
                       int inverse, int coset);
 
+/* Fully expanded inter-pass twiddle / coset tables (N x 32 B each per size and direction, built on first use,
+ * transforms of 2^12..2^26 elements) save one field product per element per use.  enable = 0 falls back to the
+ * two-level tables (a few KB) when HBM is needed for something else.  Default: enabled. */
+ZKB_API int zkb_ntt_set_direct_tables(zkb_ctx *ctx, int enable);
+
 /* ---- MSM: replaces VariableBaseMSM::multi_scalar_mul / kzg10::commit's inner product ------------------------------ */
 /* Reference: ark-ec 0.3 msm::VariableBaseMSM::multi_scalar_mul, called from plonk-core/src/commitment.rs:42 and via
  * ark-poly-commit kzg10::{commit,open} from prove.rs:134,179,250,307,374,381,427.

@@ -39,6 +39,18 @@ def test_large_against_oracle(ctx, log_n):
     assert np.array_equal(to_host(d), x)
 
 
+def test_two_level_tables_give_the_same_results(ctx):
+    """zkb_ntt_set_direct_tables(0): the small two-level twiddle path (used above 2^26 or when HBM is scarce)."""
+    log_n = 14
+    x = rand_fr_mont(1 << log_n, 9)
+    ctx.ntt_set_direct_tables(False)
+    try:
+        for inv, cos in MODES:
+            assert np.array_equal(ctx.ntt_host(x.copy(), log_n, inv, cos), cref.ntt(x, log_n, inv, cos))
+    finally:
+        ctx.ntt_set_direct_tables(True)
+
+
 def test_zero_padding_like_fft_in_place_resize(ctx):
     """coset_evals_from_poly on the 4n domain: a degree < n+3 polynomial in a 4n buffer (quotient_poly.rs:52-96)."""
     log_n, length = 14, (1 << 12) + 3

@@ -81,6 +81,9 @@ class Context:
                                                 int(inverse), int(coset)))
         return tensors
 
+    def ntt_set_direct_tables(self, enable):
+        self._check(self._lib.zkb_ntt_set_direct_tables(self._h, int(bool(enable))))
+
     # -- SRS / MSM
     def srs_load(self, points):
         """points: host (n, 8) uint64 array or CUDA tensor with n*8 8-byte words (affine x||y, Montgomery)."""

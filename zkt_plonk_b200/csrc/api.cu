@@ -153,6 +153,12 @@ int zkb_d2h(zkb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
 }
 
 // ---------------------------------------------------------------------------------------------- NTT
+int zkb_ntt_set_direct_tables(zkb_ctx *ctx, int enable) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    ctx->ntt_no_direct = !enable;
+    return ZKB_OK;
+}
+
 int zkb_ntt_dev(zkb_ctx *ctx, uint64_t *data_dev, size_t len, unsigned log_n, int inverse, int coset) {
     if (!ctx) return ZKB_ERR_INVALID;
     return zkb_ntt_run(ctx, data_dev, len, log_n, inverse, coset);

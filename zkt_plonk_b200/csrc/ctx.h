@@ -26,6 +26,7 @@ struct zkb_ctx {
     // ---- NTT: cached twiddle tables, keyed by a small integer id (see ntt.cu)
     std::map<uint64_t, DevBuf> tables;
     DevBuf ntt_scratch;          // ping-pong buffer for multi-pass transforms
+    bool ntt_no_direct = false;  // true: never build the fully expanded twiddle / coset tables (saves N x 32 B each)
     DevBuf stage;                // staging buffer for host-pointer entry points
     DevBuf ptr_stage;
 

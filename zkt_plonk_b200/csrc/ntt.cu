@@ -30,6 +30,8 @@ struct PassArgs {
     const uint4 *tile_tw;   // w_T^j, j < T/2
     const uint4 *tw2;       // two-level table of w_M (M = T*S): lo[2^tw_s] then hi[M >> tw_s]
     const uint4 *cs2;       // two-level table of coset powers (g^e or g^-e / n): lo[2^cs_s] then hi
+    const uint4 *tw_direct; // optional: w_M^(c*k) at [c * T + k]  (one product instead of two per element)
+    const uint4 *cs_direct; // optional: coset power of every index e at [e]
     unsigned long long len; // elements >= len read as zero (first pass only)
     uint32_t t, log_s, log_n;
     uint32_t tw_s, cs_s;
@@ -70,13 +72,13 @@ __device__ __forceinline__ void emit_output(const PassArgs &a, unsigned long lon
                                             unsigned long long base, uint32_t k, fe_t v) {
     unsigned long long o;
     if (!(a.mode & M_LAST)) {
-        v = fmul<FrP>(v, pow2lvl(a.tw2, a.tw_s, c * k));
+        v = fmul<FrP>(v, a.tw_direct ? fload_ro(a.tw_direct + 2 * ((c << a.t) + k)) : pow2lvl(a.tw2, a.tw_s, c * k));
         o = base + ((unsigned long long)k << a.log_s);
     } else {
         // r = k1 * 2^t2 + k2  ->  K = k1 + 2^t1 * k2 + 2^(t1+t2) * k
         unsigned long long k1 = r >> a.t2, k2 = r & ((1ull << a.t2) - 1);
         o = k1 + (k2 << a.t1) + ((unsigned long long)k << (a.log_n - a.t));
-        if (a.mode & M_OUT_COSET) v = fmul<FrP>(v, pow2lvl(a.cs2, a.cs_s, o));
+        if (a.mode & M_OUT_COSET) v = fmul<FrP>(v, a.cs_direct ? fload_ro(a.cs_direct + 2 * o) : pow2lvl(a.cs2, a.cs_s, o));
         else if (a.mode & M_OUT_CONST) v = fmul<FrP>(v, a.scale);
     }
     fstore(a.out + 2 * o, v);
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
         fe_t v;
         if (idx < a.len) {
             v = fload(a.in + 2 * idx);
-            if (a.mode & M_IN_COSET) v = fmul<FrP>(v, pow2lvl(a.cs2, a.cs_s, idx));
+            if (a.mode & M_IN_COSET) v = fmul<FrP>(v, a.cs_direct ? fload_ro(a.cs_direct + 2 * idx) : pow2lvl(a.cs2, a.cs_s, idx));
         } else {
             v = fzero<FrP>();
         }
@@ -177,6 +179,21 @@ __global__ void pow_table_kernel(uint4 *out, fe_t base, fe_t scale, uint32_t cou
     fstore(out + 2 * (size_t)j, acc);
 }
 
+// out[c * T + k] = w_M^(c*k) for c < S, k < T (M = T*S), expanded from the two-level table
+__global__ void expand_twiddle_kernel(uint4 *out, const uint4 *tw2, uint32_t tw_s, uint32_t t, unsigned long long count) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned long long c = i >> t, k = i & ((1ull << t) - 1);
+    fstore(out + 2 * i, pow2lvl(tw2, tw_s, c * k));
+}
+
+// out[e] = base^e (pre-scaled) for e < count, expanded from the two-level table
+__global__ void expand_powers_kernel(uint4 *out, const uint4 *tab, uint32_t s, unsigned long long count) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    fstore(out + 2 * i, pow2lvl(tab, s, i));
+}
+
 fe_t to_dev(const host::Fe &f) {
     fe_t r;
     memcpy(r.v, f.l, 32);
@@ -223,6 +240,27 @@ int get_2lvl_table(zkb_ctx *ctx, uint64_t key, unsigned lm, const host::Fe &base
         if (rc) return rc;
         rc = build_pow_table(ctx, (uint4 *)b.p + 2 * (size_t)nlo, base, hi_scale, nhi, s);
         if (rc) return rc;
+        it = ctx->tables.emplace(key, b).first;
+    }
+    *out = (const uint4 *)it->second.p;
+    return ZKB_OK;
+}
+
+// Direct (fully expanded) tables trade HBM for one field product per element per use; kept for transforms up to
+// 2^DIRECT_MAX_LOG elements (N x 32 B each), cached like the small tables.
+constexpr unsigned DIRECT_MAX_LOG = 26;
+
+int get_direct_table(zkb_ctx *ctx, uint64_t key, unsigned long long count, const uint4 *src, uint32_t s, int twiddle_t,
+                     const uint4 **out) {
+    auto it = ctx->tables.find(key);
+    if (it == ctx->tables.end()) {
+        DevBuf b;
+        int rc = zkb_reserve(ctx, b, (size_t)count * 32);
+        if (rc) return rc;
+        unsigned blocks = (unsigned)((count + 255) / 256);
+        if (twiddle_t >= 0) expand_twiddle_kernel<<<blocks, 256, 0, ctx->stream>>>((uint4 *)b.p, src, s, (uint32_t)twiddle_t, count);
+        else expand_powers_kernel<<<blocks, 256, 0, ctx->stream>>>((uint4 *)b.p, src, s, count);
+        ZKB_CUDA(ctx, cudaGetLastError());
         it = ctx->tables.emplace(key, b).first;
     }
     *out = (const uint4 *)it->second.p;
@@ -280,6 +318,13 @@ int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int 
                          : get_2lvl_table(ctx, key, log_n, g, host::one(host::FR), &cs2, &cs_s);
         if (rc) return rc;
     }
+    const bool direct = log_n >= 12 && log_n <= DIRECT_MAX_LOG && !ctx->ntt_no_direct;
+    const uint4 *cs_direct = nullptr;
+    if (coset && direct) {
+        uint64_t key = (5ull << 32) | (log_n << 1) | (unsigned)inverse;
+        int rc = get_direct_table(ctx, key, n, cs2, cs_s, -1, &cs_direct);
+        if (rc) return rc;
+    }
 
     unsigned log_s = log_n;
     for (unsigned p = 0; p < m; ++p) {
@@ -304,7 +349,13 @@ int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int 
             uint64_t key = (2ull << 32) | (lm << 1) | (unsigned)inverse;
             rc = get_2lvl_table(ctx, key, lm, w, host::one(host::FR), &a.tw2, &a.tw_s);
             if (rc) return rc;
+            if (direct) {
+                uint64_t dkey = (4ull << 32) | ((uint64_t)t << 16) | (lm << 1) | (unsigned)inverse;
+                rc = get_direct_table(ctx, dkey, 1ull << lm, a.tw2, a.tw_s, (int)t, &a.tw_direct);
+                if (rc) return rc;
+            }
         }
+        a.cs_direct = cs_direct;
         a.cs2 = cs2; a.cs_s = cs_s;
         a.mode = (last ? M_LAST : 0);
         if (first && coset && !inverse) a.mode |= M_IN_COSET;
