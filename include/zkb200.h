@@ -108,6 +108,12 @@ ZKB_API int zkb_msm_g1_bases(zkb_ctx *ctx, const uint64_t *points_host, const ui
  * reached from prove.rs:133-135,178-180,249-251,306-308,373-375 (the caller skips leading zero coefficients by
  * passing offset/n, as skip_leading_zeros_and_convert_to_bigints does). */
 ZKB_API int zkb_commit_dev(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);
+/* kzg10::commit for a batch of polynomials (PolynomialCommitment::commit commits several polynomials per call:
+ * prove.rs:133-135 a,b,c; :178-180 t,h1,h2; :249-251 z1,z2; :306-308 q_lo,q_mid,q_hi).  The MSMs are pipelined: the
+ * window reduction and download of MSM k overlap the sort and bucket accumulation of MSM k+1.
+ * coeffs_mont_dev[k]: device pointer; offsets may be NULL (all 0); out_xy: count x 8 limbs; is_inf: count (or NULL). */
+ZKB_API int zkb_commit_batch_dev(zkb_ctx *ctx, const uint64_t *const *coeffs_mont_dev, const size_t *offsets, const size_t *lens,
+                         size_t count, uint64_t *out_xy, int *is_inf);
 /* out_points_dev[i] = scalars_dev[i] * base: builds [tau^i]G-style SRS / synthetic points directly in HBM
  * (what PC::setup's FixedBaseMSM does once per SRS, plonk.rs:195). */
 ZKB_API int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], const uint64_t *scalars_dev, size_t n,

@@ -123,6 +123,26 @@ def test_resident_srs_offsets_partials_and_commit(ctx):
     assert e.value.code == -4
 
 
+def test_pipelined_batch_commit_vs_oracle(ctx):
+    """zkb_commit_batch_dev: several commitments in flight over two workspaces, plain and fixed-base bases."""
+    n = 4096
+    dP, P = gpu_points(ctx, n, 71)
+    ctx.srs_load(dP)
+    lens = [n, n - 3, 1, 17, n, 0, 2500]
+    polys = [cref.to_mont(cref.FR, cref.rand_fe(cref.FR, max(l, 1), 80 + i)) for i, l in enumerate(lens)]
+    exp = [cref.msm_g1(P[:l], cref.from_mont(cref.FR, p[:l])) if l else (np.zeros(8, dtype=np.uint64), True) for p, l in zip(polys, lens)]
+    for fixed in (False, True):
+        ctx.srs_precompute(0 if fixed else -1)
+        got = ctx.commit_batch_dev([to_dev(p) for p in polys], lens)
+        for (gxy, ginf), (exy, einf) in zip(got, exp):
+            assert ginf == einf and np.array_equal(gxy, exy)
+        # offsets (leading zero coefficients skipped by the caller)
+        got = ctx.commit_batch_dev([to_dev(polys[0][5:]), to_dev(polys[1])], [n - 5, n - 3], offsets=[5, 0])
+        sc = cref.from_mont(cref.FR, polys[0][5:])
+        assert np.array_equal(got[0][0], cref.msm_g1(P[5:], sc)[0]) and np.array_equal(got[1][0], exp[1][0])
+    ctx.srs_precompute(-1)
+
+
 def test_fixed_base_tables_vs_oracle(ctx):
     """zkb_srs_precompute: shared-bucket MSM over the tables 2^(c*w) * P_i gives the same affine point."""
     n = 6000

@@ -132,6 +132,17 @@ class Context:
                                              ctypes.byref(inf)))
         return out, bool(inf.value)
 
+    def commit_batch_dev(self, coeffs_list, lens, offsets=None):
+        """Pipelined kzg10::commit of several HBM-resident polynomials.  Returns [((8,) affine, is_inf), ...]."""
+        k = len(coeffs_list)
+        P = (ctypes.c_void_p * k)(*[_dev_ptr(t).value for t in coeffs_list])
+        L = (ctypes.c_size_t * k)(*lens)
+        O = (ctypes.c_size_t * k)(*(offsets if offsets is not None else [0] * k))
+        out = np.zeros((k, 8), dtype=np.uint64)
+        inf = (ctypes.c_int * k)()
+        self._check(self._lib.zkb_commit_batch_dev(self._h, P, O, L, k, _host_ptr(out), inf))
+        return [(out[j].copy(), bool(inf[j])) for j in range(k)]
+
     def set_msm_window(self, c):
         self._check(self._lib.zkb_msm_set_window(self._h, int(c)))
 

@@ -33,8 +33,6 @@ struct zkb_ctx {
     // ---- MSM (msm.cu)
     DevBuf srs;                  // resident affine G1 points
     size_t srs_n = 0;
-    DevBuf msm_ws;               // workspace
-    void *msm_pinned = nullptr;  // pinned host result buffer
     void *msm_state = nullptr;   // opaque (owned by msm.cu)
     int msm_force_c = 0;         // 0 = cost model picks the window size
 

@@ -62,9 +62,16 @@ struct MsmWs {                           // carved out of ctx->msm_ws
     g1x_t *grp_sum;                      // G
 };
 
-struct MsmState {
-    void *pinned = nullptr;              // pinned host buffer for the window partial sums
+struct MsmSlot {                         // one MSM in flight: its own workspace, result buffer and completion event
+    DevBuf ws;
+    void *pinned = nullptr;              // pinned host buffer for the group sums
     size_t pinned_bytes = 0;
+    cudaEvent_t acc_done = nullptr, tail_done = nullptr;
+};
+
+struct MsmState {
+    MsmSlot slot[2];                     // slot 0: single MSMs; slots 0/1 alternate in pipelined batches
+    cudaStream_t tail_stream = nullptr;  // high-priority stream for the latency-bound tail of a pipelined MSM
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase boundaries of the last MSM
     bool ev_valid = false;
     uint64_t last_entries = 0;           // n * W upper bound of bucket insertions of the last MSM
@@ -561,7 +568,7 @@ MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int carve_ws(zkb_ctx *ctx, const MsmPlan &pl, size_t n, MsmWs &ws, uint64_t *max_tasks_out, uint64_t *max_heavy_tasks_out) {
+int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, uint64_t *max_tasks_out, uint64_t *max_heavy_tasks_out) {
     const uint64_t nb = pl.nbuckets;
     const uint64_t entries = (uint64_t)n * pl.W;
     const uint64_t max_tasks = nb + entries / pl.seg + 1;
@@ -573,9 +580,9 @@ int carve_ws(zkb_ctx *ctx, const MsmPlan &pl, size_t n, MsmWs &ws, uint64_t *max
            o_hist = take((SEG_MAX + 1) * 4), o_hcur = take((SEG_MAX + 1) * 4), o_misc = take(64), o_heavy = take(nb * 4),
            o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)), o_bval = take(nb * sizeof(g1x_t)),
            o_part = take((size_t)pl.G * pl.red_ctas_per_group * sizeof(g1x_t)), o_sum = take((size_t)pl.G * sizeof(g1x_t));
-    int rc = zkb_reserve(ctx, ctx->msm_ws, off);
+    int rc = zkb_reserve(ctx, buf, off);
     if (rc) return rc;
-    char *p = (char *)ctx->msm_ws.p;
+    char *p = (char *)buf.p;
     ws.counts = (uint32_t *)(p + o_counts); ws.starts = (uint32_t *)(p + o_starts); ws.cursor = (uint32_t *)(p + o_cursor);
     ws.ntasks = (uint32_t *)(p + o_ntasks); ws.task_base = (uint32_t *)(p + o_tbase); ws.sorted = (uint32_t *)(p + o_sorted);
     ws.scan_tmp = (uint32_t *)(p + o_scan); ws.size_hist = (uint32_t *)(p + o_hist); ws.size_cursor = (uint32_t *)(p + o_hcur);
@@ -592,23 +599,36 @@ MsmState *state(zkb_ctx *ctx) {
     return (MsmState *)ctx->msm_state;
 }
 
-// Enqueue the whole MSM on ctx->stream; the G group sums end up in st->pinned.
+// Enqueue the whole MSM; the G group sums end up in the slot's pinned buffer.
 // fb == nullptr: bases are d_points[0..n); else: bases are fb rows, ids offset by `offset`.
+// pipelined == false: everything on ctx->stream.  pipelined == true: sorting + accumulation on ctx->stream, the
+// latency-bound tail (window reduction, final fold, D2H) on the high-priority tail stream so that it overlaps the
+// next MSM's sort and accumulation; the caller alternates slots and waits on slot.tail_done.
 int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, size_t n, int force_c, const FixedBase *fb,
-                size_t offset, MsmPlan *plan_out) {
+                size_t offset, MsmPlan *plan_out, int slot_id = 0, bool pipelined = false) {
     if (n >= (1ull << 31)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n must be < 2^31");
     MsmPlan pl = make_plan(n, force_c, fb, offset);
     if ((uint64_t)n * pl.W >= (1ull << 32)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n * windows must be < 2^32");
     MsmWs ws;
     uint64_t max_tasks, max_heavy;
-    int rc = carve_ws(ctx, pl, n, ws, &max_tasks, &max_heavy);
-    if (rc) return rc;
     MsmState *st = state(ctx);
+    MsmSlot &sl = st->slot[slot_id];
+    if (!sl.acc_done) {
+        ZKB_CUDA(ctx, cudaEventCreateWithFlags(&sl.acc_done, cudaEventDisableTiming));
+        ZKB_CUDA(ctx, cudaEventCreateWithFlags(&sl.tail_done, cudaEventDisableTiming));
+    }
+    if (pipelined && !st->tail_stream) {
+        int lo_prio = 0, hi_prio = 0;
+        ZKB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        ZKB_CUDA(ctx, cudaStreamCreateWithPriority(&st->tail_stream, cudaStreamNonBlocking, hi_prio));
+    }
+    int rc = carve_ws(ctx, sl.ws, pl, n, ws, &max_tasks, &max_heavy);
+    if (rc) return rc;
     size_t out_bytes = (size_t)pl.G * sizeof(g1x_t);
-    if (st->pinned_bytes < out_bytes) {
-        if (st->pinned) cudaFreeHost(st->pinned);
-        ZKB_CUDA(ctx, cudaMallocHost(&st->pinned, out_bytes));
-        st->pinned_bytes = out_bytes;
+    if (sl.pinned_bytes < out_bytes) {
+        if (sl.pinned) cudaFreeHost(sl.pinned);
+        ZKB_CUDA(ctx, cudaMallocHost(&sl.pinned, out_bytes));
+        sl.pinned_bytes = out_bytes;
     }
     cudaStream_t s = ctx->stream;
     const uint32_t nb = (uint32_t)pl.nbuckets, n32 = (uint32_t)n;
@@ -643,32 +663,41 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     msm_combine_giant_kernel<<<ctx->sm_count, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out,
                                                           ws.bucket_val);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[3], s));
-    msm_reduce_kernel<<<pl.G * pl.red_ctas_per_group, RED_THREADS, 0, s>>>(ws.bucket_val, pl.B, pl.red_ctas_per_group, pl.red_ch,
-                                                                           ws.grp_partial);
-    msm_reduce_final_kernel<<<pl.G, RED_THREADS, 0, s>>>(ws.grp_partial, pl.red_ctas_per_group, ws.grp_sum);
-    ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], s));
+    cudaStream_t ts = s;
+    if (pipelined) {
+        ts = st->tail_stream;
+        ZKB_CUDA(ctx, cudaEventRecord(sl.acc_done, s));
+        ZKB_CUDA(ctx, cudaStreamWaitEvent(ts, sl.acc_done, 0));
+    }
+    msm_reduce_kernel<<<pl.G * pl.red_ctas_per_group, RED_THREADS, 0, ts>>>(ws.bucket_val, pl.B, pl.red_ctas_per_group, pl.red_ch,
+                                                                            ws.grp_partial);
+    msm_reduce_final_kernel<<<pl.G, RED_THREADS, 0, ts>>>(ws.grp_partial, pl.red_ctas_per_group, ws.grp_sum);
+    ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], ts));
     ZKB_CUDA(ctx, cudaGetLastError());
     st->ev_valid = true;
     ctx->launches += 18;                 // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduce x 2
-    ZKB_CUDA(ctx, cudaMemcpyAsync(st->pinned, ws.grp_sum, out_bytes, cudaMemcpyDeviceToHost, s));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(sl.pinned, ws.grp_sum, out_bytes, cudaMemcpyDeviceToHost, ts));
+    ZKB_CUDA(ctx, cudaEventRecord(sl.tail_done, ts));
     *plan_out = pl;
     return ZKB_OK;
+}
+
+// fold the group sums of a finished MSM on the host; result in XYZZ
+hec::Pt msm_fold(const MsmPlan &pl, const void *pinned) {
+    const hec::Pt *part = (const hec::Pt *)pinned;
+    if (pl.G == 1) return part[0];
+    hec::Pt total = hec::inf();
+    for (uint32_t w = pl.W; w-- > 0;) {
+        for (uint32_t k = 0; k < pl.c; ++k) total = hec::dbl(total);
+        total = hec::add(total, part[w]);
+    }
+    return total;
 }
 
 // wait for the stream, fold the group sums on the host; result in XYZZ
 int msm_finish(zkb_ctx *ctx, const MsmPlan &pl, hec::Pt *out) {
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const hec::Pt *part = (const hec::Pt *)state(ctx)->pinned;
-    hec::Pt total = hec::inf();
-    if (pl.G == 1) {
-        total = part[0];
-    } else {
-        for (uint32_t w = pl.W; w-- > 0;) {
-            for (uint32_t k = 0; k < pl.c; ++k) total = hec::dbl(total);
-            total = hec::add(total, part[w]);
-        }
-    }
-    *out = total;
+    *out = msm_fold(pl, state(ctx)->slot[0].pinned);
     return ZKB_OK;
 }
 
@@ -677,7 +706,13 @@ int msm_finish(zkb_ctx *ctx, const MsmPlan &pl, hec::Pt *out) {
 void zkb_msm_release(zkb_ctx *ctx) {
     MsmState *st = (MsmState *)ctx->msm_state;
     if (!st) return;
-    if (st->pinned) cudaFreeHost(st->pinned);
+    for (MsmSlot &sl : st->slot) {
+        if (sl.pinned) cudaFreeHost(sl.pinned);
+        if (sl.ws.p) cudaFree(sl.ws.p);
+        if (sl.acc_done) cudaEventDestroy(sl.acc_done);
+        if (sl.tail_done) cudaEventDestroy(sl.tail_done);
+    }
+    if (st->tail_stream) cudaStreamDestroy(st->tail_stream);
     for (int k = 0; k < 5; ++k) if (st->ev[k]) cudaEventDestroy(st->ev[k]);
     if (st->fixed_base) {
         FixedBase *fb = (FixedBase *)st->fixed_base;
@@ -864,6 +899,48 @@ int zkb_msm_last_timing(zkb_ctx *ctx, float out_ms[5], uint64_t info[3]) {
     for (int k = 0; k < 4; ++k) ZKB_CUDA(ctx, cudaEventElapsedTime(&out_ms[k], st->ev[k], st->ev[k + 1]));
     ZKB_CUDA(ctx, cudaEventElapsedTime(&out_ms[4], st->ev[0], st->ev[4]));
     if (info) { info[0] = st->last_entries; info[1] = st->last_c; info[2] = st->last_W; }
+    return ZKB_OK;
+}
+
+// kzg10::commit for `count` polynomials resident in HBM (PolynomialCommitment::commit takes a batch: prove.rs:133-135
+// commits a, b, c together, :178-180 t, h1, h2, :249-251 z1, z2, :306-308 the three quotient parts).  The MSMs are
+// software-pipelined over two workspaces: while MSM k's latency-bound window reduction and result download run on a
+// high-priority stream, MSM k+1 already sorts and accumulates on the main stream.
+int zkb_commit_batch_dev(zkb_ctx *ctx, const uint64_t *const *coeffs_mont_dev, const size_t *offsets, const size_t *lens, size_t count,
+                         uint64_t *out_xy /* count x 8 */, int *is_inf /* count */) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if ((!coeffs_mont_dev || !lens || !out_xy) && count) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_batch_dev: null argument");
+    MsmState *st = state(ctx);
+    const FixedBase *fb = (const FixedBase *)st->fixed_base;
+    if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;
+    size_t max_len = 0;
+    for (size_t k = 0; k < count; ++k) {
+        size_t off = offsets ? offsets[k] : 0;
+        if (off + lens[k] > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_commit_batch_dev: offset + n exceeds the loaded SRS");
+        if (!coeffs_mont_dev[k] && lens[k]) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_batch_dev: null coefficients");
+        max_len = lens[k] > max_len ? lens[k] : max_len;
+    }
+    int rc = zkb_reserve(ctx, ctx->stage, 2 * (max_len * 32 + 32));     // canonical scalars, one buffer per slot
+    if (rc) return rc;
+    MsmPlan plans[2];
+    for (size_t k = 0; k <= count; ++k) {
+        if (k < count) {
+            const int slot = (int)(k & 1);
+            const size_t off = offsets ? offsets[k] : 0, n = lens[k];
+            if (k >= 2) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->slot[slot].tail_done, 0));   // slot reuse (already folded below)
+            uint4 *scal = (uint4 *)((char *)ctx->stage.p + (size_t)slot * (max_len * 32 + 32));
+            if (n) fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)coeffs_mont_dev[k], scal, (uint32_t)n);
+            rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, scal, n, 0, fb, off, &plans[slot], slot, true)
+                    : msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + off, scal, n, ctx->msm_force_c, nullptr, 0, &plans[slot], slot, true);
+            if (rc) return rc;
+        }
+        if (k >= 1) {                                       // finish MSM k-1 while MSM k runs
+            const int slot = (int)((k - 1) & 1);
+            ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[slot].tail_done));
+            hec::Pt total = msm_fold(plans[slot], st->slot[slot].pinned);
+            hec::to_affine(total, out_xy + 8 * (k - 1), is_inf ? is_inf + (k - 1) : nullptr);
+        }
+    }
     return ZKB_OK;
 }
 

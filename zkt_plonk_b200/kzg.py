@@ -53,6 +53,13 @@ class GpuKZG10:
             raise PCError(f"TooManyCoefficients: {skip + n} > {self.ctx.srs_size()}")
         return self.ctx.commit_dev(coeffs_dev, skip, n)
 
+    def commit_many_dev(self, coeffs_list, lens):
+        """PolynomialCommitment::commit for a batch of HBM-resident polynomials (pipelined MSMs)."""
+        for n in lens:
+            if n > self.ctx.srs_size():
+                raise PCError(f"TooManyCoefficients: {n} > {self.ctx.srs_size()}")
+        return self.ctx.commit_batch_dev(coeffs_list, lens)
+
     def multi_scalar_mul(self, commitments, scalars_canonical):
         """HomomorphicCommitment::multi_scalar_mul (commitment.rs:31-46): sum_i scalars[i] * commitments[i]."""
         pts = np.ascontiguousarray(commitments, dtype=np.uint64).reshape(-1, 8)

@@ -267,6 +267,19 @@ class GpuBackend:
         xy, inf = self.kzg.commit_dev(poly.data, poly.len)
         return point_to_ints(xy, inf)
 
+    def commit_many(self, polys):
+        """One PC::commit call for several polynomials: the MSMs are pipelined on the device."""
+        live = [p for p in polys if p.len]
+        res = iter(self.kzg.commit_many_dev([p.data for p in live], [p.len for p in live])) if live else iter(())
+        out = []
+        for p in polys:
+            if p.len:
+                xy, inf = next(res)
+                out.append(point_to_ints(xy, inf))
+            else:
+                out.append(None)
+        return out
+
     # -- argument math
     def z1_poly(self, log_n, beta, gamma, a, b, c, s1, s2, s3, cap):
         n = 1 << log_n
@@ -334,6 +347,13 @@ class GpuBackend:
 
 
 # ------------------------------------------------------------------------------------------------ setup / prove
+def _commit_all(be, polys):
+    """PC::commit(ck, [p_0, p_1, ...], None): batched when the backend can pipeline, else one by one."""
+    if hasattr(be, "commit_many"):
+        return be.commit_many(polys)
+    return [be.commit(p) for p in polys]
+
+
 def _poly_from_evals(be, evals_host, log_n, cap):
     """poly_from_evals: iFFT then DensePolynomial truncation."""
     n = 1 << log_n
@@ -349,7 +369,7 @@ def setup(be, circuit):
     for k, name in enumerate(("sigma1", "sigma2", "sigma3")):
         polys[name] = _poly_from_evals(be, circuit.sigma[k], log_n, n)
     polys["q_table"] = _poly_from_evals(be, ints_to_mont_array(table_masks(circuit.table_size, n)), log_n, n)
-    commits = {name: be.commit(polys[name]) for name in VerifierKey.ORDER}
+    commits = dict(zip(VerifierKey.ORDER, _commit_all(be, [polys[name] for name in VerifierKey.ORDER])))
     w = field.root_of_unity(log_n)
     pi_roots = [pow(w, pos, P) for pos in circuit.pi.keys()]
     vk = VerifierKey(n, pi_roots, commits)
@@ -396,7 +416,7 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
         p = Poly(buf, be.effective_len(buf, n))
         be.add_blinders(p, take(2))
         wires[name] = p
-    commits = {k: be.commit(wires[k]) for k in ("a", "b", "c")}
+    commits = dict(zip(("a", "b", "c"), _commit_all(be, [wires[k] for k in ("a", "b", "c")])))
     for k in ("a", "b", "c"):
         tr.append_commitment(k + "_commit", commits[k])
     tick("round1_wires_ms")
@@ -415,8 +435,8 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
         if k:
             be.add_blinders(p, take(k))
         polys[name] = p
+    commits.update(zip(("t", "h1", "h2"), _commit_all(be, [polys[k] for k in ("t", "h1", "h2")])))
     for k in ("t", "h1", "h2"):
-        commits[k] = be.commit(polys[k])
         tr.append_commitment(k + "_commit", commits[k])
 
     beta, gamma = tr.challenge_scalar("beta"), tr.challenge_scalar("gamma")
@@ -432,8 +452,8 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     polys["z2"] = Poly(buf, be.effective_len(buf, n))
     be.add_blinders(polys["z2"], take(3))
     del a_ev, b_ev, c_ev, f_ev, t_ev, h1_ev, h2_ev
+    commits.update(zip(("z1", "z2"), _commit_all(be, [polys[k] for k in ("z1", "z2")])))
     for k in ("z1", "z2"):
-        commits[k] = be.commit(polys[k])
         tr.append_commitment(k + "_commit", commits[k])
 
     tick("round3_grand_products_ms")
@@ -459,8 +479,8 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     be.put(q_mid.data, q_mid.len, b1); q_mid.len += 1
     be.put(q_hi.data, 0, (be.get(q_hi.data, 0) - b1) % P)
     polys.update(q_lo=q_lo, q_mid=q_mid, q_hi=q_hi)
+    commits.update(zip(("q_lo", "q_mid", "q_hi"), _commit_all(be, [polys[k] for k in ("q_lo", "q_mid", "q_hi")])))
     for k in ("q_lo", "q_mid", "q_hi"):
-        commits[k] = be.commit(polys[k])
         tr.append_commitment(k + "_commit", commits[k])
     xi = tr.challenge_scalar("xi")
     tick("round4_quotient_ms")
@@ -498,13 +518,14 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
         tr.append_scalar(k + "_eval", ev[k])
     eta = tr.challenge_scalar("eta")
 
-    def open_at(plist, point):
+    def witness_of(plist, point):
         comb = be.lincomb(plist, [pow(eta, i, P) for i in range(len(plist))])
         wit, _ = be.divide_linear(comb, point)
         wit.len = be.effective_len(wit.data, wit.len)
-        return be.commit(wit)
+        return wit
 
-    aw = open_at([r_poly, polys["a"], polys["b"], polys["c"], kp["sigma1"], kp["sigma2"], kp["q_lookup"], polys["t"], polys["h2"]], xi)
-    saw = open_at([polys["z1"], polys["z2"], polys["t"], polys["h1"]], shifted)
+    w1 = witness_of([r_poly, polys["a"], polys["b"], polys["c"], kp["sigma1"], kp["sigma2"], kp["q_lookup"], polys["t"], polys["h2"]], xi)
+    w2 = witness_of([polys["z1"], polys["z2"], polys["t"], polys["h1"]], shifted)
+    aw, saw = _commit_all(be, [w1, w2])                          # the two openings are independent MSMs
     tick("round5_linearisation_openings_ms")
     return Proof(commits, aw, saw, ev)
