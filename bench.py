@@ -122,7 +122,8 @@ def run_reference(args):
     from oracle import cref
     log_n = args.log_n
     n = 1 << log_n
-    threads = cref.num_threads()
+    # torchrun exports OMP_NUM_THREADS=1 for N > 1; the reference arm is entitled to every host core it can use
+    threads = max(cref.num_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     G = cref.to_mont(cref.FQ, cref.ints_to_limbs([1, 2])).reshape(8)
     ab = cref.g1_mul(G, cref.ints_to_limbs([0x1234567890ABCDEF1234567, 0xFEDCBA0987654321ABCDEF]))
     P = cref.g1_walk(ab[0], ab[1], n)
@@ -340,7 +341,7 @@ def run_main(args):
         from oracle import cref
         Ph = P.cpu().numpy().view(np.uint64)
         sh = host_sets[(args.steps - 1) % NSETS].numpy().view(np.uint64)
-        threads = cref.num_threads()
+        threads = max(cref.num_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
         t0 = time.perf_counter()
         exp, einf = cref.msm_g1(Ph, sh, threads)
         dt = time.perf_counter() - t0
