@@ -126,6 +126,7 @@ def run_reference(args):
     threads = max(cref.num_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     G = cref.to_mont(cref.FQ, cref.ints_to_limbs([1, 2])).reshape(8)
     ab = cref.g1_mul(G, cref.ints_to_limbs([0x1234567890ABCDEF1234567, 0xFEDCBA0987654321ABCDEF]))
+    cref.msm_g1(ab, uniform_scalars(2, 1), threads)               # sets the OpenMP team size for the calls below
     P = cref.g1_walk(ab[0], ab[1], n)
     sets = [uniform_scalars(n, 1000 + k) for k in range(2)]
     for w in range(min(args.warmup, 1)):
