@@ -54,6 +54,13 @@ def test_vectorised_host_plumbing_matches_the_reference_shaped_one():
     assert prover.mont_array_to_ints(a1) == h1 and prover.mont_array_to_ints(a2) == h2
     with pytest.raises(ValueError):
         prover.combine_split_arrays(t_arr, prover.ints_to_mont_array([12345]))
+    # zero handling: zero inside the table (before other entries), no zero in t at all, dense non-zero f
+    for t2, f2 in (([5, 0, 7, 0, 9, 9], [0, 0, 7, 5, 5, 9]), ([3, 4, 5, 6], [4, 4, 6, 3]), ([1, 2, 0, 0], [2, 2, 2, 1])):
+        e1, e2 = prover.combine_split(t2, f2)
+        g1, g2 = prover.combine_split_arrays(prover.ints_to_mont_array(t2), prover.ints_to_mont_array(f2))
+        assert prover.mont_array_to_ints(g1) == e1 and prover.mont_array_to_ints(g2) == e2
+    with pytest.raises(ValueError):
+        prover.combine_split_arrays(prover.ints_to_mont_array([3, 4]), prover.ints_to_mont_array([0]))
 
 
 @pytest.mark.parametrize("log_n", [4, 6])

@@ -166,6 +166,11 @@ def combine_split(t, f):
 _ONE_MONT = np.array(field.int_to_limbs(field.to_mont(1)), dtype=np.uint64)
 
 
+def _row_nonzero(a):
+    """(n, 4) limb rows -> bool mask of non-zero field elements (column ops: much faster than any(axis=1))."""
+    return (a[:, 0] | a[:, 1] | a[:, 2] | a[:, 3]) != 0
+
+
 def table_multiset_array(table, table_size, n):
     assert n > table_size and len(table) <= table_size
     out = np.zeros((n, 4), dtype=np.uint64)
@@ -178,9 +183,12 @@ def lookup_f_array(q_lookup, c):
     """f_i = q_lookup_i * c_i (prove.rs:157-161).  Selector values 0 and 1 are handled as masks; anything else
     falls back to exact integer arithmetic for those rows only."""
     q_lookup, c = np.asarray(q_lookup, dtype=np.uint64), np.asarray(c, dtype=np.uint64)
-    is_zero = ~q_lookup.any(axis=1)
-    is_one = (q_lookup == _ONE_MONT).all(axis=1)
-    f = np.where(is_one[:, None], c, np.uint64(0))
+    is_zero = ~_row_nonzero(q_lookup)
+    is_one = ((q_lookup[:, 0] == _ONE_MONT[0]) & (q_lookup[:, 1] == _ONE_MONT[1]) & (q_lookup[:, 2] == _ONE_MONT[2])
+              & (q_lookup[:, 3] == _ONE_MONT[3]))
+    f = np.zeros_like(c)
+    ones = np.flatnonzero(is_one)
+    f[ones] = c[ones]
     other = np.flatnonzero(~(is_zero | is_one))
     if other.size:
         qi, ci = mont_array_to_ints(q_lookup[other]), mont_array_to_ints(c[other])
@@ -191,19 +199,33 @@ def lookup_f_array(q_lookup, c):
 def combine_split_arrays(t, f):
     """MultiSet::combine_split (lookup/multiset.rs:103-146): buckets in order of first appearance in t, every
     element of f must be in t, halves alternate on odd counts.  Montgomery limb rows are unique per field element,
-    so they serve as keys directly."""
+    so they serve as keys directly.  Zero rows (table padding, non-lookup gates: the bulk of both multisets) are
+    counted separately so that only the non-zero rows are sorted."""
     t, f = np.ascontiguousarray(t, dtype=np.uint64), np.ascontiguousarray(f, dtype=np.uint64)
-    key_t = np.dtype((np.void, 32))
-    allk = np.concatenate([t, f]).view(key_t).reshape(-1)
-    _, first, counts = np.unique(allk, return_index=True, return_counts=True)
-    if (first >= t.shape[0]).any():
+    n_t = t.shape[0]
+    nz_t, nz_f = _row_nonzero(t), _row_nonzero(f)
+    zeros_t, zeros_f = n_t - int(nz_t.sum()), f.shape[0] - int(nz_f.sum())
+    if zeros_f and not zeros_t:
         raise ValueError("ElementNotIndexedInTable")
-    order = np.argsort(first, kind="stable")                   # IndexMap insertion order
-    first, counts = first[order], counts[order]
+    pos = np.concatenate([np.flatnonzero(nz_t), n_t + np.flatnonzero(nz_f)])     # original positions in t ++ f
+    rows = np.concatenate([t[nz_t], f[nz_f]])
+    if rows.shape[0]:
+        _, first, counts = np.unique(rows.view(np.dtype((np.void, 32))).reshape(-1), return_index=True, return_counts=True)
+        first_pos = pos[first]
+        if (first_pos >= n_t).any():
+            raise ValueError("ElementNotIndexedInTable")
+        keys = rows[first]
+    else:
+        first_pos, counts, keys = np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros((0, 4), dtype=np.uint64)
+    if zeros_t:                                                    # the zero bucket sits where 0 first appears in t
+        first_pos = np.concatenate([first_pos, [int(np.argmin(nz_t))]])
+        counts = np.concatenate([counts, [zeros_t + zeros_f]])
+        keys = np.concatenate([keys, np.zeros((1, 4), dtype=np.uint64)])
+    order = np.argsort(first_pos, kind="stable")                   # IndexMap insertion order
+    counts, keys = counts[order], keys[order]
     half, odd = counts // 2, (counts % 2).astype(bool)
-    rank = np.cumsum(odd) - 1                                   # k-th odd bucket: even k -> evens, odd k -> odds
+    rank = np.cumsum(odd) - 1                                       # k-th odd bucket: even k -> evens, odd k -> odds
     to_even = odd & (rank % 2 == 0)
-    keys = np.concatenate([t, f])[first]
     evens = np.repeat(keys, half + to_even, axis=0)
     odds = np.repeat(keys, half + (odd & ~to_even), axis=0)
     return np.ascontiguousarray(evens), np.ascontiguousarray(odds)
