@@ -48,6 +48,15 @@ def test_product_never_imports_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "zkb_oracle" not in src, f
 
 
+def test_cpp_mirror_header_is_self_contained():
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = '#include "zkb200.hpp"\nint main() { return sizeof(zkb::G1Affine) == 64 ? 0 : 1; }\n'
+    out = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(root, "include"), "-x", "c++", "-"],
+                         input=src, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+
+
 def test_domain_metadata_matches_arkworks_rules():
     from zkt_plonk_b200 import field
     D = z.GpuEvaluationDomain
