@@ -161,6 +161,31 @@ ZKB_API int zkb_poly_add_blinders_dev(zkb_ctx *ctx, uint64_t *coeffs_dev, size_t
  * (blinders are appended at that length: prove.rs:472-483).  Synchronous. */
 ZKB_API int zkb_poly_effective_len_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, size_t n, size_t *out_len);
 
+/* ---- the prover rounds behind two calls ------------------------------------------------------------------------------- */
+/* Replaces proof_system::setup (setup.rs:42-166, extend = true) and proof_system::prove (prove.rs:59-470) for
+ * BN254 / KZG10 / Merlin.  The committer key must already be resident (zkb_srs_load_g1, >= n + 8 powers; optionally
+ * zkb_srs_precompute).  All field inputs are arkworks' in-memory form (Montgomery limbs), exactly what the composer
+ * holds after pad_to(n):
+ *   selectors[6] = q_m, q_l, q_r, q_o, q_c, q_lookup evaluations (n each); sigma[3] = sigma1..3 evaluations
+ *   (compute_all_sigma_evals); table_size = the const generic TABLE_SIZE; pi_positions = sorted public-input rows.
+ * The key object owns the selector / sigma polynomials, the 11 coset tables of the ExtendedProverKey, the verifier
+ * key commitments and a scratch arena for one proof, all in HBM. */
+typedef struct zkb_plonk_pk zkb_plonk_pk;
+ZKB_API int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selectors[6], const uint64_t *const sigma[3],
+                    size_t table_size, const size_t *pi_positions, size_t n_pi, zkb_plonk_pk **out);
+ZKB_API void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk);
+/* VerifierKey commitments in seed_transcript order (keys/mod.rs:264-274): q_m q_l q_r q_o q_c sigma1 sigma2 sigma3
+ * q_lookup q_table; 10 x (x || y) Montgomery. */
+ZKB_API int zkb_plonk_vk_commitments(const zkb_plonk_pk *pk, uint64_t out_xy[80], int is_inf[10]);
+/* a, b, c: wire evaluations (n each, host); table: the lookup table's entries (table_len <= table_size);
+ * pi_values: one value per pi_position; blinders: the 19 elements the reference draws with F::rand, in draw order
+ * a(2) b(2) c(2) h1(3) h2(2) z1(3) z2(3) b0 b1; proof_out: the 802 bytes of Proof's CanonicalSerialize.
+ * timings_ms (optional, 8 floats; non-NULL drains the stream at every boundary): wire upload, round 1, host lookup
+ * plumbing, round 2, round 3, round 4, round 5, total. */
+ZKB_API int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, const uint64_t *b, const uint64_t *c,
+                    const uint64_t *table, size_t table_len, const uint64_t *pi_values, const uint64_t *blinders,
+                    uint8_t proof_out[802], float timings_ms[8]);
+
 /* ---- test hooks (parity of the device field library against the oracle) ----------------------------------------- */
 /* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a).  Host pointers. */
 ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n);

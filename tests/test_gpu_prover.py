@@ -68,3 +68,34 @@ def test_gpu_proof_2_14_verifies(ctx):
     bad.evals["t_next"] = (bad.evals["t_next"] + 1) % P
     assert plonk_ref.verify(vk, bad, list(circ.pi.values()), TAU) != 0
     ctx.srs_precompute(-1)
+
+
+@pytest.mark.parametrize("log_n,fixed_base", [(6, False), (10, True)])
+def test_native_cpp_driver_matches_python_and_oracle(ctx, log_n, fixed_base):
+    """zkb_plonk_setup / zkb_plonk_prove (the C++ round driver a Rust FFI crate would call) produce the same 802
+    bytes as the Python schedule on the GPU backend and on the oracle backend, and the verifier accepts them."""
+    import zkt_plonk_b200 as z
+    circ = synthetic.make_circuit(log_n, seed=70 + log_n, table_size=min(64, (1 << log_n) // 4))
+    d_srs, h_srs = gpu_srs(ctx, circ.n + 8)
+    kzg = z.GpuKZG10(ctx)
+    kzg.load_committer_key(d_srs)
+    if fixed_base:
+        ctx.srs_precompute(0)
+    rnd = random.Random(5)
+    blinders = [rnd.randrange(P) for _ in range(19)]
+    native = prover.NativeProver(ctx, circ)
+    raw, tm = native.prove_bytes(blinders, timings=True)
+    assert raw == native.prove_bytes(blinders)
+    obe = plonk_ref.OracleBackend(h_srs)
+    opk, ovk = prover.setup(obe, circ)
+    assert native.vk().commits == ovk.commits
+    assert raw == prover.prove(obe, opk, ovk, circ, blinders).to_bytes()
+    gbe = prover.GpuBackend(kzg)
+    gpk, gvk = prover.setup(gbe, circ)
+    assert raw == prover.prove(gbe, gpk, gvk, circ, blinders).to_bytes()
+    proof = prover.proof_from_bytes(raw)
+    assert proof.to_bytes() == raw
+    assert plonk_ref.verify(native.vk(), proof, list(circ.pi.values()), TAU) == 0
+    assert tm["total_ms"] > 0
+    native.close()
+    ctx.srs_precompute(-1)

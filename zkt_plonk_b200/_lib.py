@@ -72,6 +72,10 @@ def load():
         "zkb_poly_divide_linear_dev": (i, [vp, vp, sz, vp, vp, vp]),
         "zkb_poly_add_blinders_dev": (i, [vp, vp, sz, vp, sz]),
         "zkb_poly_effective_len_dev": (i, [vp, vp, sz, ctypes.POINTER(sz)]),
+        "zkb_plonk_setup": (i, [vp, u, ctypes.POINTER(vp), ctypes.POINTER(vp), sz, ctypes.POINTER(sz), sz, ctypes.POINTER(vp)]),
+        "zkb_plonk_pk_destroy": (None, [vp, vp]),
+        "zkb_plonk_vk_commitments": (i, [vp, vp, ctypes.POINTER(i)]),
+        "zkb_plonk_prove": (i, [vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, ctypes.POINTER(ctypes.c_float)]),
         "zkb_launch_count": (ctypes.c_uint64, [vp]),
         "zkb_msm_last_timing": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),
         "zkb_bench_int": (i, [vp, i, ctypes.POINTER(ctypes.c_double)]),

@@ -551,3 +551,85 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     aw, saw = _commit_all(be, [w1, w2])                          # the two openings are independent MSMs
     tick("round5_linearisation_openings_ms")
     return Proof(commits, aw, saw, ev)
+
+
+# ------------------------------------------------------------------------------------------------ C++ round driver
+class NativeProver:
+    """The same setup / prove behind the two C-ABI calls zkb_plonk_setup / zkb_plonk_prove (csrc/prover.cu): what a
+    Rust FFI crate would call with the composer's vectors.  The committer key must be resident in `ctx`."""
+
+    def __init__(self, ctx, circuit):
+        import ctypes
+        self.ctx, self.circuit = ctx, circuit
+        lib = ctx._lib
+        sel = [np.ascontiguousarray(circuit.selectors[k], dtype=np.uint64) for k in ("q_m", "q_l", "q_r", "q_o", "q_c", "q_lookup")]
+        sig = [np.ascontiguousarray(x, dtype=np.uint64) for x in circuit.sigma]
+        self._keep = sel + sig
+        S = (ctypes.c_void_p * 6)(*[x.ctypes.data for x in sel])
+        G = (ctypes.c_void_p * 3)(*[x.ctypes.data for x in sig])
+        pos = list(circuit.pi.keys())
+        PP = (ctypes.c_size_t * max(len(pos), 1))(*pos)
+        h = ctypes.c_void_p()
+        ctx._check(lib.zkb_plonk_setup(ctx._h, circuit.log_n, S, G, circuit.table_size, PP, len(pos), ctypes.byref(h)))
+        self._pk = h
+
+    def vk(self):
+        import ctypes
+        xy = np.zeros((10, 8), dtype=np.uint64)
+        inf = (ctypes.c_int * 10)()
+        self.ctx._check(self.ctx._lib.zkb_plonk_vk_commitments(self._pk, xy.ctypes.data_as(ctypes.c_void_p), inf))
+        commits = {name: point_to_ints(xy[k], bool(inf[k])) for k, name in enumerate(VerifierKey.ORDER)}
+        w = field.root_of_unity(self.circuit.log_n)
+        return VerifierKey(self.circuit.n, [pow(w, p, P) for p in self.circuit.pi.keys()], commits)
+
+    def prove_bytes(self, blinders, timings=False):
+        import ctypes
+        c = self.circuit
+        a, b, cc = (np.ascontiguousarray(x, dtype=np.uint64) for x in (c.a, c.b, c.c))
+        table = ints_to_mont_array(c.table) if c.table else np.zeros((1, 4), dtype=np.uint64)
+        pi = ints_to_mont_array(list(c.pi.values())) if c.pi else np.zeros((1, 4), dtype=np.uint64)
+        bl = ints_to_mont_array(blinders)
+        out = np.zeros(802, dtype=np.uint8)
+        tm = (ctypes.c_float * 8)() if timings else None
+        vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+        self.ctx._check(self.ctx._lib.zkb_plonk_prove(self.ctx._h, self._pk, vp(a), vp(b), vp(cc), vp(table), len(c.table), vp(pi),
+                                                      vp(bl), vp(out), tm))
+        raw = out.tobytes()
+        if timings:
+            names = ("h2d_wires_ms", "round1_wires_ms", "host_lookup_plumbing_ms", "round2_lookup_ms", "round3_grand_products_ms",
+                     "round4_quotient_ms", "round5_linearisation_openings_ms", "total_ms")
+            return raw, dict(zip(names, [float(x) for x in tm]))
+        return raw
+
+    def close(self):
+        if getattr(self, "_pk", None):
+            self.ctx._lib.zkb_plonk_pk_destroy(self.ctx._h, self._pk)
+            self._pk = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def proof_from_bytes(raw):
+    """Inverse of Proof.to_bytes for the verifier: decompress the 13 G1 points (y from x, sign from the flag bit)."""
+    assert len(raw) == 802
+
+    def point(b):
+        v = int.from_bytes(b, "little")
+        if (v >> 254) & 1:
+            return None
+        x = v & ((1 << 254) - 1)
+        y = pow((x * x * x + 3) % Q, (Q + 1) // 4, Q)              # q = 3 mod 4
+        assert y * y % Q == (x * x * x + 3) % Q, "x is not on the curve"
+        if (y > (Q - y) % Q) != bool((v >> 255) & 1):
+            y = (Q - y) % Q
+        return (x, y)
+
+    pts = [point(raw[32 * k: 32 * k + 32]) for k in range(11)]
+    aw, saw = point(raw[352:384]), point(raw[385:417])
+    assert raw[384] == 0 and raw[417] == 0
+    evals = [int.from_bytes(raw[418 + 32 * k: 450 + 32 * k], "little") for k in range(12)]
+    return Proof(dict(zip(Proof.COMMITS, pts)), aw, saw, dict(zip(Proof.EVALS, evals)))
