@@ -399,23 +399,23 @@ def run_prove_extra(ctx, log_n):
     kzg = z.GpuKZG10(ctx)
     kzg.load_committer_key(srs)
     ctx.srs_precompute(0)
-    be = prover.GpuBackend(kzg)
-    pk, vk = prover.setup(be, circ)
+    native = prover.NativeProver(ctx, circ)                     # zkb_plonk_setup: keys, coset tables, arena in HBM
     runs = []
-    for r in range(3):
-        tm = {}
+    for r in range(4):
         t0 = time.perf_counter()
-        proof = prover.prove(be, pk, vk, circ, list(range(1000 + r, 1019 + r)), timings=tm)
-        torch.cuda.synchronize()
-        tm["total_ms"] = (time.perf_counter() - t0) * 1e3
+        raw, tm = native.prove_bytes(list(range(1000 + r, 1019 + r)), timings=True)   # zkb_plonk_prove (C++ round driver)
+        tm["wall_ms"] = (time.perf_counter() - t0) * 1e3
         tm["device_rounds_ms"] = sum(v for k_, v in tm.items() if k_.startswith("round"))
         runs.append(tm)
-    best = min(runs, key=lambda t: t["total_ms"])
+    best = min(runs[1:], key=lambda t: t["total_ms"])
+    native.close()
     return {"workload": f"plonk_plookup_prove_n=2^{log_n} (withdraw-circuit size), 1 GPU, fixed-base SRS tables",
+            "api": "zkb_plonk_prove (C ABI): host wires/table/blinders in, 802 proof bytes out",
             "prove_ms": best["total_ms"], "device_rounds_ms": best["device_rounds_ms"],
-            "host_lookup_plumbing_ms": best.get("host_lookup_plumbing_ms"), "rounds_ms": {k_: v for k_, v in best.items() if k_.startswith("round")},
-            "proof_bytes": len(proof.to_bytes()),
-            "note": "device drained at every round boundary; host witness plumbing (combine_split) is numpy on the host"}
+            "host_lookup_plumbing_ms": best["host_lookup_plumbing_ms"], "h2d_wires_ms": best["h2d_wires_ms"],
+            "rounds_ms": {k_: v for k_, v in best.items() if k_.startswith("round")}, "proof_bytes": len(raw),
+            "note": "stream drained at every round boundary for the breakdown; proofs of this driver are byte-identical to the "
+                    "oracle-backend prover and accepted by the restated verifier (tests/test_gpu_prover.py)"}
 
 
 def main():
