@@ -180,12 +180,13 @@ struct KeyEq { bool operator()(const Fe &a, const Fe &b) const { return feq(a, b
 
 // MultiSet::combine_split on Montgomery limb rows (unique per field element): buckets in order of first appearance
 // in t; every element of f must be in t; halves alternate on odd counts.  Returns false on ElementNotIndexedInTable.
-bool combine_split(const std::vector<Fe> &t, const std::vector<Fe> &f, std::vector<Fe> &h1, std::vector<Fe> &h2) {
+bool combine_split(const Fe *t, size_t nt, const Fe *f, size_t nf, Fe *h1, Fe *h2, size_t *n1, size_t *n2) {
     std::vector<std::pair<Fe, size_t>> buckets;
     std::unordered_map<Fe, size_t, KeyHash, KeyEq> index;
     index.reserve(4096);
     size_t zero_bucket = (size_t)-1;
-    for (const Fe &e : t) {
+    for (size_t i = 0; i < nt; ++i) {
+        const Fe &e = t[i];
         if (host::is_zero(e)) {                                   // the bulk of t (padding): no hashing
             if (zero_bucket == (size_t)-1) { zero_bucket = buckets.size(); buckets.push_back({e, 0}); }
             ++buckets[zero_bucket].second;
@@ -195,7 +196,8 @@ bool combine_split(const std::vector<Fe> &t, const std::vector<Fe> &f, std::vect
         if (it == index.end()) { index.emplace(e, buckets.size()); buckets.push_back({e, 1}); }
         else ++buckets[it->second].second;
     }
-    for (const Fe &e : f) {
+    for (size_t i = 0; i < nf; ++i) {
+        const Fe &e = f[i];
         if (host::is_zero(e)) {                                   // non-lookup gates: the bulk of f
             if (zero_bucket == (size_t)-1) return false;
             ++buckets[zero_bucket].second;
@@ -205,19 +207,23 @@ bool combine_split(const std::vector<Fe> &t, const std::vector<Fe> &f, std::vect
         if (it == index.end()) return false;
         ++buckets[it->second].second;
     }
-    h1.clear(); h2.clear();
-    h1.reserve((t.size() + f.size() + 1) / 2);
-    h2.reserve((t.size() + f.size()) / 2);
+    size_t k1 = 0, k2 = 0;                                       // h1, h2 have room for (nt + nf + 1) / 2 elements each
     bool parity = false;
     for (const auto &b : buckets) {
         size_t half = b.second / 2;
-        h1.insert(h1.end(), half, b.first);
-        h2.insert(h2.end(), half, b.first);
+        if (host::is_zero(b.first)) {
+            memset(h1 + k1, 0, half * sizeof(Fe));
+            memset(h2 + k2, 0, half * sizeof(Fe));
+        } else {
+            for (size_t j = 0; j < half; ++j) { h1[k1 + j] = b.first; h2[k2 + j] = b.first; }
+        }
+        k1 += half; k2 += half;
         if (b.second & 1) {
-            if (parity) { h2.push_back(b.first); parity = false; }
-            else { h1.push_back(b.first); parity = true; }
+            if (parity) { h2[k2++] = b.first; parity = false; }
+            else { h1[k1++] = b.first; parity = true; }
         }
     }
+    *n1 = k1; *n2 = k2;
     return true;
 }
 
@@ -240,6 +246,7 @@ struct zkb_plonk_pk {
     std::vector<size_t> pi_pos;                  // sorted public-input rows
     Pt vk[10];                                   // q_m q_l q_r q_o q_c sigma1 sigma2 sigma3 q_lookup q_table (VerifierKey order)
     std::vector<void *> owned;                   // device allocations of the key
+    Fe *stage = nullptr;                         // pinned host staging: t, f, h1, h2 (4 x n elements)
     char *arena = nullptr;                       // per-proof scratch: reset at the start of every prove
     size_t arena_bytes = 0, arena_off = 0;
 };
@@ -261,8 +268,8 @@ uint64_t *arena_take(zkb_plonk_pk *pk, size_t elems) {
     size_t bytes = (elems * 32 + 255) / 256 * 256;
     if (pk->arena_off + bytes > pk->arena_bytes) return nullptr;
     uint64_t *p = (uint64_t *)(pk->arena + pk->arena_off);
-    pk->arena_off += bytes;
-    return p;
+    pk->arena_off += bytes + 9 * 512;            // skew: the quotient kernel walks ~20 buffers in lockstep; keep them off a
+    return p;                                     // common power-of-two stride
 }
 
 #define TRY(call) do { int rc_ = (call); if (rc_ != ZKB_OK) return rc_; } while (0)
@@ -307,6 +314,7 @@ void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
     if (ctx) cudaStreamSynchronize(ctx->stream);
     for (void *p : pk->owned) cudaFree(p);
     if (pk->arena) cudaFree(pk->arena);
+    if (pk->stage) cudaFreeHost(pk->stage);
     delete pk;
 }
 
@@ -367,9 +375,11 @@ int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selector
         if (rc) return fail(rc);
     }
     // scratch arena for one proof: 9 witness cosets + the quotient (4n each) and ~30 n-sized buffers
-    pk->arena_bytes = (10 * n4 + 34 * (n + 16)) * 32;
+    pk->arena_bytes = (10 * n4 + 34 * (n + 16)) * 32 + 64 * 9 * 512;
     if (cudaMalloc((void **)&pk->arena, pk->arena_bytes) != cudaSuccess)
         return fail((ctx->err = "zkb_plonk_setup: cannot allocate the prover arena", ZKB_ERR_OOM));
+    if (cudaMallocHost((void **)&pk->stage, 4 * n * sizeof(Fe)) != cudaSuccess)
+        return fail((ctx->err = "zkb_plonk_setup: cannot allocate pinned staging", ZKB_ERR_OOM));
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail((ctx->err = "zkb_plonk_setup: stream error", ZKB_ERR_CUDA));
     *out = pk;
     return ZKB_OK;
@@ -452,8 +462,9 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     tick(1);
 
     // ---- round 2: lookup multisets on the host (prove.rs:145-167)
-    std::vector<Fe> t_vals(n, Fe{{0, 0, 0, 0}}), f_vals(n), h1_vals, h2_vals;
-    if (table_len) memcpy(t_vals.data(), table, table_len * 32);        // LookupTable::into_multiset: entries then zeros
+    Fe *t_vals = pk->stage, *f_vals = pk->stage + n, *h1_vals = pk->stage + 2 * n, *h2_vals = pk->stage + 3 * n;
+    memset(t_vals, 0, n * sizeof(Fe));
+    if (table_len) memcpy(t_vals, table, table_len * 32);               // LookupTable::into_multiset: entries then zeros
     {
         const Fe one = FR_ONE();
         const Fe *cv = (const Fe *)c;
@@ -464,14 +475,16 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
             else f_vals[i] = fmul(q, cv[i]);
         }
     }
-    if (!combine_split(t_vals, f_vals, h1_vals, h2_vals)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "ElementNotIndexedInTable (lookup/multiset.rs:121)");
-    if (h1_vals.size() != n || h2_vals.size() != n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: combine_split halves are not n long");
+    size_t n_h1 = 0, n_h2 = 0;
+    if (!combine_split(t_vals, n, f_vals, n, h1_vals, h2_vals, &n_h1, &n_h2))
+        ZKB_FAIL(ctx, ZKB_ERR_INVALID, "ElementNotIndexedInTable (lookup/multiset.rs:121)");
+    if (n_h1 != n || n_h2 != n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: combine_split halves are not n long");
     uint64_t *ev_t, *ev_f, *ev_h1, *ev_h2;
     TAKE(ev_t, n); TAKE(ev_f, n); TAKE(ev_h1, n); TAKE(ev_h2, n);
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_t, t_vals.data(), n * 32, cudaMemcpyHostToDevice, s));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_f, f_vals.data(), n * 32, cudaMemcpyHostToDevice, s));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_h1, h1_vals.data(), n * 32, cudaMemcpyHostToDevice, s));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_h2, h2_vals.data(), n * 32, cudaMemcpyHostToDevice, s));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_t, t_vals, n * 32, cudaMemcpyHostToDevice, s));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_f, f_vals, n * 32, cudaMemcpyHostToDevice, s));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_h1, h1_vals, n * 32, cudaMemcpyHostToDevice, s));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_h2, h2_vals, n * 32, cudaMemcpyHostToDevice, s));
     tick(2);
     DPoly pt, ph1, ph2;
     TRY(blinded_from_dev_evals(ev_t, 0, &pt));
