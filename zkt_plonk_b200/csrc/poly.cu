@@ -413,12 +413,28 @@ __global__ void fr_fill_kernel(uint4 *out, size_t n, fe_t v) {
     if (i < n) fstore(out + 2 * i, v);
 }
 
-// out[0] = 1 + index of the highest non-zero coefficient (0 for the zero polynomial)
+// out[0] = 1 + index of the highest non-zero coefficient (0 for the zero polynomial).  One atomic per CTA (and none
+// when the CTA cannot raise the current maximum): a per-element atomicMax on one address serialises.
 __global__ void __launch_bounds__(256) effective_len_kernel(const uint4 *coeffs, size_t n, unsigned long long *out) {
+    __shared__ unsigned long long best[8];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint4 a = coeffs[2 * i], b = coeffs[2 * i + 1];
-    if (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) atomicMax(out, (unsigned long long)(i + 1));
+    unsigned long long mine = 0;
+    if (i < n) {
+        uint4 a = coeffs[2 * i], b = coeffs[2 * i + 1];
+        if (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) mine = (unsigned long long)(i + 1);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        unsigned long long o = __shfl_down_sync(0xffffffffu, mine, d);
+        mine = o > mine ? o : mine;
+    }
+    if ((threadIdx.x & 31) == 0) best[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = best[0];
+        for (int w = 1; w < 8; ++w) m = best[w] > m ? best[w] : m;
+        if (m) atomicMax(out, m);
+    }
 }
 
 unsigned ceil_log2_sz(size_t n) { unsigned l = 0; while (((size_t)1 << l) < n) ++l; return l; }
