@@ -9,8 +9,10 @@
 // host-side lookup plumbing (prove.rs:145-167: f = q_lookup * c, MultiSet::combine_split multiset.rs:103-146),
 // challenge-dependent scalars (linearization_poly.rs:19-121) and ark-serialize's compressed point / field encodings.
 // A Rust FFI crate calls these two functions with the composer's vectors.
+#include <atomic>
 #include <chrono>
 #include <cstring>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -427,6 +429,30 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     }
     tr.append_scalars("pi", (const Fe *)pi_values, n_pi);                  // prove.rs:110
 
+    // ---- round 2's host side (prove.rs:145-167) depends only on the witness and the key, not on any challenge: a
+    // worker thread builds t, f = q_lookup * c and combine_split(t, f) in pinned memory while the GPU runs round 1
+    Fe *t_vals = pk->stage, *f_vals = pk->stage + n, *h1_vals = pk->stage + 2 * n, *h2_vals = pk->stage + 3 * n;
+    std::atomic<int> lookup_status{0};
+    std::thread lookup_worker([&]() {
+        memset(t_vals, 0, n * sizeof(Fe));
+        if (table_len) memcpy(t_vals, table, table_len * 32);           // LookupTable::into_multiset: entries then zeros
+        const Fe one = FR_ONE();
+        const Fe *cv = (const Fe *)c;
+        for (size_t i = 0; i < n; ++i) {
+            const Fe &q = pk->q_lookup_host[i];
+            if (host::is_zero(q)) f_vals[i] = Fe{{0, 0, 0, 0}};
+            else if (feq(q, one)) f_vals[i] = cv[i];
+            else f_vals[i] = fmul(q, cv[i]);
+        }
+        size_t n_h1 = 0, n_h2 = 0;
+        if (!combine_split(t_vals, n, f_vals, n, h1_vals, h2_vals, &n_h1, &n_h2)) lookup_status.store(1);
+        else if (n_h1 != n || n_h2 != n) lookup_status.store(2);
+    });
+    struct Joiner {                                                     // never leave the scope with a joinable thread
+        std::thread &t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } lookup_joiner{lookup_worker};
+
     // ---- round 1: wires (prove.rs:116-140)
     uint64_t *ev_a, *ev_b, *ev_c;
     TAKE(ev_a, n); TAKE(ev_b, n); TAKE(ev_c, n);
@@ -462,23 +488,9 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     tick(1);
 
     // ---- round 2: lookup multisets on the host (prove.rs:145-167)
-    Fe *t_vals = pk->stage, *f_vals = pk->stage + n, *h1_vals = pk->stage + 2 * n, *h2_vals = pk->stage + 3 * n;
-    memset(t_vals, 0, n * sizeof(Fe));
-    if (table_len) memcpy(t_vals, table, table_len * 32);               // LookupTable::into_multiset: entries then zeros
-    {
-        const Fe one = FR_ONE();
-        const Fe *cv = (const Fe *)c;
-        for (size_t i = 0; i < n; ++i) {
-            const Fe &q = pk->q_lookup_host[i];
-            if (host::is_zero(q)) f_vals[i] = Fe{{0, 0, 0, 0}};
-            else if (feq(q, one)) f_vals[i] = cv[i];
-            else f_vals[i] = fmul(q, cv[i]);
-        }
-    }
-    size_t n_h1 = 0, n_h2 = 0;
-    if (!combine_split(t_vals, n, f_vals, n, h1_vals, h2_vals, &n_h1, &n_h2))
-        ZKB_FAIL(ctx, ZKB_ERR_INVALID, "ElementNotIndexedInTable (lookup/multiset.rs:121)");
-    if (n_h1 != n || n_h2 != n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: combine_split halves are not n long");
+    lookup_worker.join();                                               // started before round 1 (see above)
+    if (lookup_status.load() == 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "ElementNotIndexedInTable (lookup/multiset.rs:121)");
+    if (lookup_status.load() == 2) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: combine_split halves are not n long");
     uint64_t *ev_t, *ev_f, *ev_h1, *ev_h2;
     TAKE(ev_t, n); TAKE(ev_f, n); TAKE(ev_h1, n); TAKE(ev_h2, n);
     ZKB_CUDA(ctx, cudaMemcpyAsync(ev_t, t_vals, n * 32, cudaMemcpyHostToDevice, s));
