@@ -530,7 +530,8 @@ uint32_t pick_window(size_t n, bool shared_buckets) {
     uint32_t best_c = 8;
     double best = 1e300;
     for (uint32_t c = 6; c <= 22; ++c) {
-        uint32_t wide, W = shared_buckets ? balanced_windows(c, &wide) : 254 / c + 1;
+        uint32_t wide = 1, W = shared_buckets ? balanced_windows(c, &wide) : 254 / c + 1;
+        if (shared_buckets && wide == 0) continue;               // equivalent to c - 1 with uniform windows
         double groups = shared_buckets ? 1.0 : (double)W;
         double cost = (double)n * W + (shared_buckets ? 3.0 : 4.0) * groups * (double)(1u << (c - 1));
         if (cost < best) { best = cost; best_c = c; }
@@ -771,6 +772,7 @@ int zkb_srs_precompute(zkb_ctx *ctx, int c) {
     FixedBase *fb = new FixedBase();
     fb->c = c > 0 ? (uint32_t)c : pick_window(n, true);
     fb->W = balanced_windows(fb->c, &fb->wide);
+    if (fb->wide == 0 && fb->c > 3) { fb->c -= 1; fb->wide = fb->W; }   // every window narrow: that is just c - 1 (half the buckets)
     fb->n = n;
     if ((uint64_t)n * fb->W >= (1ull << 31)) { delete fb; ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_precompute: n * windows must be < 2^31"); }
     int rc = zkb_reserve(ctx, fb->rows, (size_t)fb->W * n * sizeof(g1a_t));
