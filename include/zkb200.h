@@ -186,6 +186,27 @@ ZKB_API int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t
                     const uint64_t *table, size_t table_len, const uint64_t *pi_values, const uint64_t *blinders,
                     uint8_t proof_out[802], float timings_ms[8]);
 
+/* ---- multi-GPU: one process per GPU, commitments sharded by point range ----------------------------------- */
+/* The reference is single-process (rayon threads only), so these have no reference counterpart; they carry the
+ * exchange step of a sharded kzg10::commit.  Every rank runs the same prover (SPMD) on the same witness; a rank keeps
+ * one contiguous range of powers_of_g resident (zkb_srs_load_g1* with its range, then zkb_srs_set_range), runs the
+ * bucket method on the matching slice of every polynomial, and the XYZZ partial sums (128 B per rank and
+ * commitment) are all-gathered over NCCL (NVLink / NVSwitch) and added identically on every rank, so all ranks
+ * produce the same transcript and the same proof bytes.  NCCL is dlopen'ed by zkb_comm_init.
+ *   rank 0: zkb_comm_unique_id(id); the host layer broadcasts the 128 bytes (torch.distributed, MPI, a socket ...);
+ *   all:    zkb_comm_init(ctx, id, rank, world)  (collective). */
+ZKB_API int zkb_comm_unique_id(uint8_t out[128]);
+ZKB_API int zkb_comm_init(zkb_ctx *ctx, const uint8_t id[128], int rank, int world);
+ZKB_API int zkb_comm_destroy(zkb_ctx *ctx);
+ZKB_API int zkb_comm_rank(zkb_ctx *ctx);
+ZKB_API int zkb_comm_world(zkb_ctx *ctx);
+/* recv_host[r * bytes ..] = rank r's send_host[0 .. bytes) on every rank (collective, synchronous). */
+ZKB_API int zkb_comm_allgather_host(zkb_ctx *ctx, const void *send_host, size_t bytes, void *recv_host);
+/* Declare the resident SRS to be the range [global_lo, global_lo + resident points) of a committer key of global_n
+ * powers.  zkb_commit_dev / zkb_commit_batch_dev / zkb_plonk_setup / zkb_plonk_prove then take GLOBAL offsets and
+ * lengths; zkb_msm_g1* keep addressing the resident range.  zkb_srs_size reports global_n. */
+ZKB_API int zkb_srs_set_range(zkb_ctx *ctx, size_t global_lo, size_t global_n);
+
 /* ---- test hooks (parity of the device field library against the oracle) ----------------------------------------- */
 /* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a).  Host pointers. */
 ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n);

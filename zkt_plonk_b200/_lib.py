@@ -79,6 +79,13 @@ def load():
         "zkb_launch_count": (ctypes.c_uint64, [vp]),
         "zkb_msm_last_timing": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),
         "zkb_bench_int": (i, [vp, i, ctypes.POINTER(ctypes.c_double)]),
+        "zkb_comm_unique_id": (i, [vp]),
+        "zkb_comm_init": (i, [vp, vp, i, i]),
+        "zkb_comm_destroy": (i, [vp]),
+        "zkb_comm_rank": (i, [vp]),
+        "zkb_comm_world": (i, [vp]),
+        "zkb_comm_allgather_host": (i, [vp, vp, sz, vp]),
+        "zkb_srs_set_range": (i, [vp, sz, sz]),
     }
     for name, (res, args) in sig.items():
         if not hasattr(lib, name):

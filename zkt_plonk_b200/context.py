@@ -143,6 +143,45 @@ class Context:
         self._check(self._lib.zkb_commit_batch_dev(self._h, P, O, L, k, _host_ptr(out), inf))
         return [(out[j].copy(), bool(inf[j])) for j in range(k)]
 
+    # -- multi-GPU (one process per GPU; commitments sharded by point range)
+    def comm_init(self, group=None):
+        """Collective: attach an NCCL communicator spanning `group` (default: the world) to this context.  Rank 0
+        creates the NCCL id, torch.distributed (any backend) broadcasts its 128 bytes."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        idb = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            rc = self._lib.zkb_comm_unique_id(ctypes.c_void_p(idb.ctypes.data))
+            if rc != 0:
+                raise ZkbError(rc, "zkb_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        t = torch.from_numpy(idb)
+        if dist.get_backend(group) == "nccl":
+            t = t.to(f"cuda:{self.device}")
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idb = np.ascontiguousarray(t.cpu().numpy())
+        self._check(self._lib.zkb_comm_init(self._h, ctypes.c_void_p(idb.ctypes.data), rank, world))
+        return rank, world
+
+    def comm_destroy(self):
+        self._check(self._lib.zkb_comm_destroy(self._h))
+
+    def comm_rank_world(self):
+        return int(self._lib.zkb_comm_rank(self._h)), int(self._lib.zkb_comm_world(self._h))
+
+    def comm_allgather(self, arr):
+        """arr: host numpy array (same shape on every rank) -> (world, *arr.shape)."""
+        arr = np.ascontiguousarray(arr)
+        _, world = self.comm_rank_world()
+        out = np.empty((world,) + arr.shape, dtype=arr.dtype)
+        self._check(self._lib.zkb_comm_allgather_host(self._h, ctypes.c_void_p(arr.ctypes.data), arr.nbytes,
+                                                      ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def srs_set_range(self, global_lo, global_n):
+        """The resident SRS is [global_lo, global_lo + resident) of a key of global_n powers (commitments shard)."""
+        self._check(self._lib.zkb_srs_set_range(self._h, int(global_lo), int(global_n)))
+
     def set_msm_window(self, c):
         self._check(self._lib.zkb_msm_set_window(self._h, int(c)))
 

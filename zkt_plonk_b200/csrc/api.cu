@@ -102,6 +102,7 @@ void zkb_ctx_destroy(zkb_ctx *ctx) {
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->gp_flag) cudaFree(ctx->gp_flag);
     zkb_msm_release(ctx);
+    zkb_comm_release(ctx);
     delete ctx;
 }
 

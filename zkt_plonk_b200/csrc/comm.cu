@@ -1,0 +1,160 @@
+// comm.cu -- multi-GPU plumbing: one process per GPU, NCCL over NVLink / NVSwitch.
+//
+// The reference is single-process (rayon only: SURVEY.md 2.3), so nothing here replaces reference code; it is the
+// exchange step of the point-range sharded commitments: every rank holds one contiguous range of the
+// committer key (and its fixed-base tables), runs the bucket method on the matching slice of each polynomial, and
+// the XYZZ partial sums (128 B per rank and commitment) are all-gathered and added identically on every rank.
+//
+// NCCL is loaded with dlopen at zkb_comm_init time, so libzkb200.so keeps no link-time dependency on it (a
+// single-GPU host needs no NCCL at all) and a process that already loaded torch's bundled libnccl.so.2 shares it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "ctx.h"
+
+namespace {
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+
+NcclApi *nccl_api() {
+    static NcclApi api;
+    if (api.handle || !api.err.empty()) return &api;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) {
+        api.err = std::string("cannot load libnccl.so.2: ") + dlerror();
+        return &api;
+    }
+    bool ok = true;
+    auto sym = [&](const char *name) {
+        void *p = dlsym(api.handle, name);
+        if (!p) { ok = false; api.err = std::string("libnccl lacks ") + name; }
+        return p;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) { dlclose(api.handle); api.handle = nullptr; }
+    return &api;
+}
+
+#define ZKB_NCCL(ctx, api, call)                                                                  \
+    do {                                                                                          \
+        ncclResult_t r_ = (call);                                                                 \
+        if (r_ != ncclSuccess) {                                                                  \
+            (ctx)->err = std::string(#call " failed: ") + (api)->GetErrorString(r_);              \
+            return ZKB_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+}  // namespace
+
+void zkb_comm_release(zkb_ctx *ctx) {
+    if (ctx->comm) {
+        NcclApi *api = nccl_api();
+        if (api->handle) api->CommDestroy((ncclComm_t)ctx->comm);
+        ctx->comm = nullptr;
+    }
+    if (ctx->comm_buf.p) { cudaFree(ctx->comm_buf.p); ctx->comm_buf = DevBuf(); }
+    if (ctx->comm_pinned) { cudaFreeHost(ctx->comm_pinned); ctx->comm_pinned = nullptr; ctx->comm_pinned_bytes = 0; }
+    ctx->rank = 0;
+    ctx->world = 1;
+}
+
+int zkb_comm_allgather(zkb_ctx *ctx, const void *send_host, size_t bytes, void *recv_host) {
+    if (ctx->world == 1) { memcpy(recv_host, send_host, bytes); return ZKB_OK; }
+    if (!ctx->comm) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_comm_allgather: no communicator (zkb_comm_init)");
+    NcclApi *api = nccl_api();
+    const size_t total = bytes * (size_t)(ctx->world + 1);
+    int rc = zkb_reserve(ctx, ctx->comm_buf, total);
+    if (rc) return rc;
+    if (ctx->comm_pinned_bytes < total) {
+        if (ctx->comm_pinned) cudaFreeHost(ctx->comm_pinned);
+        ctx->comm_pinned = nullptr;
+        ctx->comm_pinned_bytes = 0;
+        ZKB_CUDA(ctx, cudaMallocHost(&ctx->comm_pinned, total));
+        ctx->comm_pinned_bytes = total;
+    }
+    char *d_send = (char *)ctx->comm_buf.p, *d_recv = d_send + bytes;
+    char *h_send = (char *)ctx->comm_pinned, *h_recv = h_send + bytes;
+    memcpy(h_send, send_host, bytes);
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_send, h_send, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZKB_NCCL(ctx, api, api->AllGather(d_send, d_recv, bytes, ncclUint8, (ncclComm_t)ctx->comm, ctx->stream));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(h_recv, d_recv, bytes * (size_t)ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(recv_host, h_recv, bytes * (size_t)ctx->world);
+    return ZKB_OK;
+}
+
+extern "C" {
+
+int zkb_comm_unique_id(uint8_t out[128]) {
+    if (!out) return ZKB_ERR_INVALID;
+    NcclApi *api = nccl_api();
+    if (!api->handle) return ZKB_ERR_CUDA;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (api->GetUniqueId(&id) != ncclSuccess) return ZKB_ERR_CUDA;
+    memcpy(out, &id, 128);
+    return ZKB_OK;
+}
+
+int zkb_comm_init(zkb_ctx *ctx, const uint8_t id_bytes[128], int rank, int world) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (!id_bytes || world < 1 || rank < 0 || rank >= world) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_comm_init: bad rank / world / id");
+    zkb_comm_release(ctx);
+    if (world == 1) return ZKB_OK;
+    NcclApi *api = nccl_api();
+    if (!api->handle) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_comm_init: " + api->err);
+    ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, 128);
+    ncclComm_t comm = nullptr;
+    ZKB_NCCL(ctx, api, api->CommInitRank(&comm, world, id, rank));
+    ctx->comm = comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    return ZKB_OK;
+}
+
+int zkb_comm_destroy(zkb_ctx *ctx) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    cudaStreamSynchronize(ctx->stream);
+    zkb_comm_release(ctx);
+    return ZKB_OK;
+}
+
+int zkb_comm_rank(zkb_ctx *ctx) { return ctx ? ctx->rank : 0; }
+int zkb_comm_world(zkb_ctx *ctx) { return ctx ? ctx->world : 1; }
+
+int zkb_comm_allgather_host(zkb_ctx *ctx, const void *send_host, size_t bytes, void *recv_host) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if ((!send_host || !recv_host) && bytes) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_comm_allgather_host: null buffer");
+    return zkb_comm_allgather(ctx, send_host, bytes, recv_host);
+}
+
+// The resident SRS (zkb_srs_load_g1*: srs_n points) is the range [global_lo, global_lo + srs_n) of a committer key
+// of global_n powers.  Commitments (zkb_commit_dev / zkb_commit_batch_dev, hence zkb_plonk_setup / zkb_plonk_prove)
+// then take global offsets and lengths, run on the overlap with the resident range and all-gather the partial sums.
+int zkb_srs_set_range(zkb_ctx *ctx, size_t global_lo, size_t global_n) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (global_lo + ctx->srs_n > global_n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_set_range: the resident range exceeds the key");
+    ctx->srs_lo = global_lo;
+    ctx->srs_global_n = global_n;
+    return ZKB_OK;
+}
+
+}  // extern "C"

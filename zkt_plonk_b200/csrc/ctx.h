@@ -36,6 +36,15 @@ struct zkb_ctx {
     void *msm_state = nullptr;   // opaque (owned by msm.cu)
     int msm_force_c = 0;         // 0 = cost model picks the window size
 
+    // ---- multi-GPU (comm.cu): one process per GPU, commitments sharded by point range
+    void *comm = nullptr;        // ncclComm_t (NCCL is dlopen'ed: the library has no link-time dependency on it)
+    int rank = 0, world = 1;
+    size_t srs_lo = 0;           // global index of the first resident SRS point
+    size_t srs_global_n = 0;     // size of the whole committer key (== srs_n unless this context holds one range of it)
+    DevBuf comm_buf;             // device staging of the all-gather
+    void *comm_pinned = nullptr; // pinned host staging of the all-gather
+    size_t comm_pinned_bytes = 0;
+
     // ---- elementwise / scan kernels (poly.cu)
     DevBuf poly_ws;
     uint32_t *gp_flag = nullptr; // device flag: a grand product met a zero denominator
@@ -81,6 +90,9 @@ inline int zkb_reserve(zkb_ctx *ctx, DevBuf &b, size_t bytes) {
 // implemented in ntt.cu / msm.cu / poly.cu
 int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int inverse, int coset);
 void zkb_msm_release(zkb_ctx *ctx);
+void zkb_comm_release(zkb_ctx *ctx);
+// all ranks: recv_host[r * bytes ..] = rank r's send_host[0 .. bytes)  (NCCL all-gather on the context's stream; synchronous)
+int zkb_comm_allgather(zkb_ctx *ctx, const void *send_host, size_t bytes, void *recv_host);
 // two-level power tables base^e = lo[e & (2^s - 1)] * hi[e >> s], e < 2^lm (Montgomery Fr); hi is pre-scaled by hi_scale
 int zkb_pow2lvl_cached(zkb_ctx *ctx, uint64_t key, unsigned lm, const zkb::host::Fe &base, const zkb::host::Fe &hi_scale,
                        const void **out, uint32_t *s_out);

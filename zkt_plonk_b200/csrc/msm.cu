@@ -29,6 +29,7 @@
 #include "host_ff.h"
 
 #include <algorithm>
+#include <vector>
 
 using namespace zkb;
 
@@ -736,6 +737,8 @@ int zkb_srs_load_g1(zkb_ctx *ctx, const uint64_t *xy_mont_host, size_t n) {
     ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->srs.p, xy_mont_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->srs_n = n;
+    ctx->srs_lo = 0;
+    ctx->srs_global_n = n;
     zkb_srs_precompute(ctx, -1);
     return ZKB_OK;
 }
@@ -748,11 +751,14 @@ int zkb_srs_load_g1_dev(zkb_ctx *ctx, const uint64_t *xy_mont_dev, size_t n) {
     ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->srs.p, xy_mont_dev, n * 64, cudaMemcpyDeviceToDevice, ctx->stream));
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->srs_n = n;
+    ctx->srs_lo = 0;
+    ctx->srs_global_n = n;
     zkb_srs_precompute(ctx, -1);
     return ZKB_OK;
 }
 
-size_t zkb_srs_size(zkb_ctx *ctx) { return ctx ? ctx->srs_n : 0; }
+// size of the committer key (the whole key when this context holds one range of it: zkb_srs_set_range)
+size_t zkb_srs_size(zkb_ctx *ctx) { return ctx ? ctx->srs_global_n : 0; }
 
 // Build (c > 0: with that window size, c == 0: cost model) or drop (c < 0) the fixed-base tables of the resident SRS.
 int zkb_srs_precompute(zkb_ctx *ctx, int c) {
@@ -870,6 +876,7 @@ int zkb_g1_sum_partials(const uint64_t *xyzz, size_t count, uint64_t out_xy[8], 
 int zkb_commit_dev(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
     if (!coeffs_mont_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_dev: null coefficients");
+    if (ctx->world > 1 || ctx->srs_global_n != ctx->srs_n) return zkb_commit_batch_dev(ctx, &coeffs_mont_dev, &offset, &n, 1, out_xy, is_inf);
     if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_commit_dev: offset + n exceeds the loaded SRS");
     int rc = zkb_reserve(ctx, ctx->stage, n * 32 + 32);
     if (rc) return rc;
@@ -915,32 +922,57 @@ int zkb_commit_batch_dev(zkb_ctx *ctx, const uint64_t *const *coeffs_mont_dev, c
     MsmState *st = state(ctx);
     const FixedBase *fb = (const FixedBase *)st->fixed_base;
     if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;
+    // Point-range view: offsets / lengths are global; this context holds SRS[srs_lo, srs_lo + srs_n) and works on the
+    // overlap (the whole polynomial on a single GPU).  With world > 1 the XYZZ partial sums of all ranks are
+    // all-gathered (128 B per rank and commitment, one NCCL call per batch) and every rank adds them identically.
+    const bool sharded = ctx->world > 1;
+    std::vector<const uint64_t *> loc_ptr(count);
+    std::vector<size_t> loc_off(count), loc_n(count);
     size_t max_len = 0;
     for (size_t k = 0; k < count; ++k) {
-        size_t off = offsets ? offsets[k] : 0;
-        if (off + lens[k] > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_commit_batch_dev: offset + n exceeds the loaded SRS");
+        const size_t off = offsets ? offsets[k] : 0;
+        if (off + lens[k] > ctx->srs_global_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_commit_batch_dev: offset + n exceeds the loaded SRS");
         if (!coeffs_mont_dev[k] && lens[k]) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_batch_dev: null coefficients");
-        max_len = lens[k] > max_len ? lens[k] : max_len;
+        const size_t g_lo = std::max(off, ctx->srs_lo), g_hi = std::min(off + lens[k], ctx->srs_lo + ctx->srs_n);
+        loc_n[k] = g_hi > g_lo ? g_hi - g_lo : 0;
+        loc_off[k] = loc_n[k] ? g_lo - ctx->srs_lo : 0;
+        loc_ptr[k] = coeffs_mont_dev[k] + (loc_n[k] ? 4 * (g_lo - off) : 0);
+        max_len = loc_n[k] > max_len ? loc_n[k] : max_len;
     }
     int rc = zkb_reserve(ctx, ctx->stage, 2 * (max_len * 32 + 32));     // canonical scalars, one buffer per slot
     if (rc) return rc;
     MsmPlan plans[2];
+    std::vector<hec::Pt> partial(count);
     for (size_t k = 0; k <= count; ++k) {
-        if (k < count) {
+        if (k < count && loc_n[k]) {
             const int slot = (int)(k & 1);
-            const size_t off = offsets ? offsets[k] : 0, n = lens[k];
+            const size_t off = loc_off[k], n = loc_n[k];
             if (k >= 2) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->slot[slot].tail_done, 0));   // slot reuse (already folded below)
             uint4 *scal = (uint4 *)((char *)ctx->stage.p + (size_t)slot * (max_len * 32 + 32));
-            if (n) fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)coeffs_mont_dev[k], scal, (uint32_t)n);
+            fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)loc_ptr[k], scal, (uint32_t)n);
             rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, scal, n, 0, fb, off, &plans[slot], slot, true)
                     : msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + off, scal, n, ctx->msm_force_c, nullptr, 0, &plans[slot], slot, true);
             if (rc) return rc;
         }
         if (k >= 1) {                                       // finish MSM k-1 while MSM k runs
             const int slot = (int)((k - 1) & 1);
-            ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[slot].tail_done));
-            hec::Pt total = msm_fold(plans[slot], st->slot[slot].pinned);
-            hec::to_affine(total, out_xy + 8 * (k - 1), is_inf ? is_inf + (k - 1) : nullptr);
+            if (loc_n[k - 1]) {
+                ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[slot].tail_done));
+                partial[k - 1] = msm_fold(plans[slot], st->slot[slot].pinned);
+            } else {
+                partial[k - 1] = hec::inf();
+            }
+            if (!sharded) hec::to_affine(partial[k - 1], out_xy + 8 * (k - 1), is_inf ? is_inf + (k - 1) : nullptr);
+        }
+    }
+    if (sharded && count) {
+        std::vector<hec::Pt> all((size_t)ctx->world * count);
+        rc = zkb_comm_allgather(ctx, partial.data(), count * sizeof(hec::Pt), all.data());
+        if (rc) return rc;
+        for (size_t k = 0; k < count; ++k) {
+            hec::Pt total = hec::inf();
+            for (int r = 0; r < ctx->world; ++r) total = hec::add(total, all[(size_t)r * count + k]);
+            hec::to_affine(total, out_xy + 8 * k, is_inf ? is_inf + k : nullptr);
         }
     }
     return ZKB_OK;

@@ -328,7 +328,7 @@ int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selector
     if (log_n + 2 > 28 || log_n < 3) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_plonk_setup: need 8 <= n and 4n <= 2^28 (InvalidEvalDomainSize)");
     const size_t n = (size_t)1 << log_n, n4 = 4 * n;
     if (table_size >= n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_setup: max table size is equal or larger than n (lookup/table.rs:43)");
-    if (n + 8 > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_plonk_setup: the committer key must hold at least n + 8 powers");
+    if (n + 8 > ctx->srs_global_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_plonk_setup: the committer key must hold at least n + 8 powers");
     zkb_plonk_pk *pk = new zkb_plonk_pk();
     pk->log_n = log_n; pk->n = n; pk->table_size = table_size;
     pk->pi_pos.assign(pi_positions, pi_positions + n_pi);

@@ -30,6 +30,20 @@ def affine_to_xyzz(xy, is_inf, one_mont):
     return out
 
 
+def attach_sharded_srs(ctx, load_range, global_n, group=None, precompute=True):
+    """SPMD set-up of point-range sharded commitments behind the C ABI (csrc/comm.cu): attaches an NCCL communicator
+    to `ctx`, loads this rank's contiguous range of the committer key and declares it (zkb_srs_set_range).
+    `load_range(lo, hi)` returns powers_of_g[lo:hi] (host array or CUDA tensor).  Afterwards zkb_commit_batch_dev,
+    zkb_plonk_setup and zkb_plonk_prove run unchanged on every rank and return identical results."""
+    rank, world = ctx.comm_init(group)
+    b = shard_bounds(global_n, world)
+    ctx.srs_load(load_range(b[rank], b[rank + 1]))
+    ctx.srs_set_range(b[rank], global_n)
+    if precompute:
+        ctx.srs_precompute(0)
+    return b[rank], b[rank + 1]
+
+
 class ShardedMSM:
     """`partial_fn(scalars_shard) -> (16,) uint64 XYZZ` computes this rank's partial sum; by default it is the
     CUDA bucket method on the context's resident SRS range."""
