@@ -220,7 +220,7 @@ ZKB_API int zkb_msm_last_timing(zkb_ctx *ctx, float out_ms[5], uint64_t info[3])
 
 /* ---- measurement: integer-pipe peak (not in MEASURED_PEAKS.json; SURVEY.md 8d asks for it) ------------------------- */
 /* mode 0: 32-bit IMAD/s, mode 1: IMAD.WIDE.U32/s (the instruction the Montgomery product is made of),
- * mode 2: Fq Montgomery products/s in a dependency-chained loop.  All 148 SMs, best of 3 timed launches. */
+ * mode 2: Fq Montgomery products/s in a dependency-chained loop, mode 3: FP64 FMA/s.  All 148 SMs, best of 3 timed launches. */
 ZKB_API int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec);
 
 #ifdef __cplusplus

@@ -54,6 +54,18 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, uint32_t i
 #pragma unroll
         for (int k = 0; k < 8; ++k) r ^= a[k];
         out[t] = (uint32_t)(r ^ (r >> 32));
+    } else if (mode == 3) {                                       // FP64 FMA (the other wide multiplier on the SM)
+        double a[8], m = 1.0 + 1e-9 * (double)(t & 15);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = (double)(t + k);
+        for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[k]) : "d"(m), "d"(a[(k + 1) & 7]));
+        }
+        double r = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r += a[k];
+        out[t] = (uint32_t)__double2ll_rn(r);
     } else {
         fe_t x[4];
 #pragma unroll
@@ -211,7 +223,7 @@ int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint
 
 // ---------------------------------------------------------------------------------------------- microbenchmark
 int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec) {
-    if (!ctx || !ops_per_sec || mode < 0 || mode > 2) return ZKB_ERR_INVALID;
+    if (!ctx || !ops_per_sec || mode < 0 || mode > 3) return ZKB_ERR_INVALID;
     const uint32_t blocks = ctx->sm_count * 8, threads = 256, iters = mode == 2 ? 512 : 4096;
     int rc = zkb_reserve(ctx, ctx->stage, (size_t)blocks * threads * 4);
     if (rc) return rc;

@@ -12,11 +12,15 @@
 //      equally long loops; one thread accumulates one task in XYZZ coordinates (8M + 2S per point, the
 //      next point's gather is issued before the current addition);
 //   4. tasks of oversized buckets (skewed scalars: zeros/ones/small values) are combined warp-cooperatively;
-//   5. per-group weighted bucket sums over a dense bucket array: each thread owns a chunk of consecutive
-//      buckets (running-sum trick plus one small scalar multiplication), a CTA tree-reduces the chunks in
-//      shared memory, a second tiny kernel folds the CTA partials;
-//   6. the group sums (<= W x 128 B) go to the host, which folds them (Horner, c doublings per window)
-//      and converts to affine -- O(254) group operations, cheaper there than on one GPU thread.
+//   5. per-group weighted bucket sums sum_j (j+1) * bucket_j over a dense bucket array, by index-digit recursion:
+//      with j = R*t + b,  sum_j j*X[j] = sum_t A[t] + R * sum_t t*S[t]  where S[t] = sum_b X[R*t+b] and
+//      A[t] = sum_b b*X[R*t+b].  Level l turns X_l into X_{l+1} = S (R times shorter) and a new plain stream A_l,
+//      and shortens the older plain streams A_0..A_{l-1} by plain R-to-1 sums.  Every level is one launch of fully
+//      independent short chains (R = 8 while the arrays are long, R = 2 -- depth one -- for the tail), there is
+//      no scalar multiplication and no serial fold on the device;
+//   6. the level totals (<= W x ~20 x 128 B) go to the host, which finishes with a Horner fold (log2 R doublings per
+//      level, then c doublings per window) and converts to affine -- a few hundred group operations, cheaper there
+//      than on one GPU thread.
 //
 // Fixed-base mode (zkb_srs_precompute): for the resident SRS the table T[w][i] = 2^(c*w) * P_i is built once
 // (W x N x 64 B of HBM).  Then every window feeds ONE shared set of 2^(c-1) buckets (entry id = w*N + i), a much
@@ -36,8 +40,9 @@ using namespace zkb;
 namespace {
 
 constexpr uint32_t SEG_MAX = 1024;       // upper bound of the per-MSM task length `seg` (points per accumulation task)
-constexpr uint32_t RED_CH_MAX = 16;      // upper bound of buckets per thread in the window reduction
 constexpr uint32_t RED_THREADS = 128;    // threads per CTA in the window reduction
+constexpr uint32_t RED_MAX_LEVELS = 24;  // levels of the weighted-sum recursion (radix 8 or 2 each)
+constexpr uint32_t RED_WIDE_MIN = 16384; // arrays at least this long are shortened 8-to-1, shorter ones 2-to-1
 constexpr uint32_t SIGN_BIT = 0x80000000u;
 
 struct MsmPlan {
@@ -45,7 +50,10 @@ struct MsmPlan {
     uint32_t G;                          // bucket groups: W (one per window) or 1 (fixed-base tables)
     uint32_t wide;                       // windows [0, wide) are c bits wide, the others c - 1 (wide = W: uniform)
     uint64_t nbuckets;                   // G * B
-    uint32_t red_ctas_per_group, red_ch;   // reduction: CTAs per group, buckets per thread
+    uint32_t red_levels;                 // weighted-sum recursion: levels, radix (log2) and input length of each
+    uint8_t red_log_r[RED_MAX_LEVELS];
+    uint32_t red_m[RED_MAX_LEVELS + 1];
+    uint64_t red_buf_elems[2];           // ping-pong buffers of the recursion (levels alternate)
     uint32_t seg;                        // max points per accumulation task
     uint32_t id_base, id_stride;         // fixed-base: entry id = id_base + w * id_stride + i
 };
@@ -59,8 +67,7 @@ struct MsmWs {                           // carved out of ctx->msm_ws
     uint2 *task_order;
     g1x_t *task_out;                     // partial sums of the tasks of multi-task buckets
     g1x_t *bucket_val;                   // dense: one XYZZ value per bucket (zero = empty)
-    g1x_t *grp_partial;                  // G * red_ctas_per_group
-    g1x_t *grp_sum;                      // G
+    g1x_t *red_buf[2];                   // level outputs, [stream][group][t]
 };
 
 struct MsmSlot {                         // one MSM in flight: its own workspace, result buffer and completion event
@@ -354,69 +361,57 @@ __global__ void __launch_bounds__(128) msm_combine_giant_kernel(const uint32_t *
     }
 }
 
-// ------------------------------------------------------------------ per-window weighted bucket sums
-__device__ __noinline__ g1x_t g1x_mul_small(const g1x_t &p, uint32_t k) {
-    g1x_t acc = g1x_inf();
-    if (!k) return acc;
-    for (int bit = 31 - __clz(k); bit >= 0; --bit) {
-        acc = g1x_double(acc);
-        if ((k >> bit) & 1) g1x_add(acc, p);
+// ------------------------------------------------------------------ per-group weighted bucket sums (index-digit recursion)
+// One level.  in: [n_plain + 1 streams][G groups][M_in], out: [n_plain + 2][G][M_out], M_out = ceil(M_in / R).
+//   stream 0 (X):            out[0][g][t] = sum_b X[R*t+b]   and   out[n_plain+1][g][t] = sum_b b * X[R*t+b]  (the new A stream)
+//   stream s >= 1 (plain A): out[s][g][t] = sum_b in[s][g][R*t+b]
+// Then sum_j j*X[j] = sum_t A[t] + R * sum_t t*out[0][t]: the next level continues on out[0].  Elements past M_in read
+// as the identity.  grid = (ceil(M_out / 128), n_plain + 1, G).
+template <int R>
+__global__ void __launch_bounds__(RED_THREADS) msm_wsum_level_kernel(const g1x_t *__restrict__ in, uint32_t M_in, uint32_t M_out,
+                                                                     uint32_t n_plain, g1x_t *__restrict__ out) {
+    const uint32_t t = blockIdx.x * RED_THREADS + threadIdx.x;
+    if (t >= M_out) return;
+    const uint32_t strm = blockIdx.y, g = blockIdx.z, G = gridDim.z;
+    const g1x_t *src = in + ((size_t)strm * G + g) * M_in + (size_t)R * t;
+    const uint32_t avail = min((uint32_t)R, M_in - R * t);         // >= 1
+    g1x_t *dst = out + ((size_t)strm * G + g) * M_out + t;
+    if (R == 2) {
+        g1x_t x0 = g1x_load(src);
+        if (avail > 1) {
+            g1x_t x1 = g1x_load(src + 1);
+            if (strm == 0) g1x_store(out + ((size_t)(n_plain + 1) * G + g) * M_out + t, x1);
+            g1x_add(x0, x1);
+        } else if (strm == 0) {
+            g1x_store(out + ((size_t)(n_plain + 1) * G + g) * M_out + t, g1x_inf());
+        }
+        g1x_store(dst, x0);
+        return;
     }
-    return acc;
-}
-
-// grid = G * ctas_per_group CTAs of RED_THREADS threads; a thread owns RED_CH consecutive buckets of one group.
-// bucket_val is dense, so all loads of a chunk are independent of each other and issue up front.
-__global__ void __launch_bounds__(RED_THREADS) msm_reduce_kernel(const g1x_t *__restrict__ bucket_val, uint32_t B, uint32_t ctas_per_group,
-                                                                 uint32_t RED_CH, g1x_t *__restrict__ grp_partial) {
-    __shared__ g1x_t sm[RED_THREADS];
-    uint32_t g = blockIdx.x / ctas_per_group, cw = blockIdx.x % ctas_per_group;
-    uint32_t chunk = cw * RED_THREADS + threadIdx.x;          // chunk index inside the group
-    uint32_t lo = chunk * RED_CH;                               // first bucket (digit value lo + 1)
-    g1x_t run = g1x_inf(), acc = g1x_inf();
-    if (lo < B) {
-        uint32_t hi = min(lo + RED_CH, B);
-        const g1x_t *src = bucket_val + (size_t)g * B;
-        g1x_t cur = g1x_load(src + hi - 1);
-        for (uint32_t j = hi; j-- > lo;) {
+    if (strm != 0) {                                              // plain R-to-1 sum
+        g1x_t acc = g1x_load(src), cur = acc;
+        if (avail > 1) cur = g1x_load(src + 1);
+        for (uint32_t b = 1; b < avail; ++b) {
             g1x_t nxt = cur;
-            if (j > lo) nxt = g1x_load(src + j - 1);            // prefetch the next bucket
-            g1x_add(run, cur);
-            g1x_add(acc, run);                                  // acc = sum_j (j - lo + 1) * bucket_j
+            if (b + 1 < avail) nxt = g1x_load(src + b + 1);        // next element in flight during the addition
+            g1x_add(acc, cur);
             cur = nxt;
         }
-        g1x_t shifted = g1x_mul_small(run, lo);                // + lo * sum_j bucket_j
-        g1x_add(acc, shifted);
+        g1x_store(dst, acc);
+        return;
     }
-    sm[threadIdx.x] = acc;
-    for (uint32_t stride = RED_THREADS / 2; stride >= 1; stride >>= 1) {
-        __syncthreads();
-        if (threadIdx.x < stride) {
-            g1x_t a = sm[threadIdx.x];
-            g1x_add(a, sm[threadIdx.x + stride]);
-            sm[threadIdx.x] = a;
-        }
+    // weighted: run = X[b..], acc = sum_{k >= b} (k - b + 1) X[k], walking b from the top down to 1
+    g1x_t run = g1x_inf(), acc = g1x_inf();
+    g1x_t cur = g1x_load(src + avail - 1);
+    for (uint32_t b = avail - 1; b >= 1; --b) {
+        g1x_t nxt = g1x_load(src + b - 1);
+        g1x_add(run, cur);
+        g1x_add(acc, run);
+        cur = nxt;
     }
-    if (threadIdx.x == 0) g1x_store(grp_partial + blockIdx.x, sm[0]);
-}
-
-// one CTA per group: folds the group's CTA partials into one point
-__global__ void __launch_bounds__(RED_THREADS) msm_reduce_final_kernel(const g1x_t *__restrict__ grp_partial, uint32_t ctas_per_group,
-                                                                       g1x_t *__restrict__ grp_sum) {
-    __shared__ g1x_t sm[RED_THREADS];
-    const g1x_t *src = grp_partial + (size_t)blockIdx.x * ctas_per_group;
-    g1x_t acc = g1x_inf();
-    for (uint32_t k = threadIdx.x; k < ctas_per_group; k += RED_THREADS) g1x_add(acc, g1x_load(src + k));
-    sm[threadIdx.x] = acc;
-    for (uint32_t stride = RED_THREADS / 2; stride >= 1; stride >>= 1) {
-        __syncthreads();
-        if (threadIdx.x < stride && threadIdx.x + stride < ctas_per_group) {
-            g1x_t a = sm[threadIdx.x];
-            g1x_add(a, sm[threadIdx.x + stride]);
-            sm[threadIdx.x] = a;
-        }
-    }
-    if (threadIdx.x == 0) g1x_store(grp_sum + blockIdx.x, sm[0]);
+    g1x_add(run, cur);                                            // + X[0]: the plain sum
+    g1x_store(dst, run);
+    g1x_store(out + ((size_t)(n_plain + 1) * G + g) * M_out + t, acc);
 }
 
 // Fixed-base table: rows[w][i] = 2^(c*w) * P_i (affine), w < W.  One thread per point walks the windows.
@@ -552,12 +547,18 @@ MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset) {
     }
     pl.B = 1u << (pl.c - 1);
     pl.nbuckets = (uint64_t)pl.G * pl.B;
-    // reduction: the serial depth per thread is 2 * red_ch + ~29 group operations, so use the smallest chunk that
-    // still keeps the grid near two warps per SM sub-partition (148 SMs x 4 x 2 warps x 32 lanes = 37888 threads)
-    uint32_t ch = (uint32_t)((pl.nbuckets + 37887) / 37888);
-    pl.red_ch = ch < 2 ? 2 : (ch > RED_CH_MAX ? RED_CH_MAX : ch);
-    uint32_t chunks = (pl.B + pl.red_ch - 1) / pl.red_ch;
-    pl.red_ctas_per_group = (chunks + RED_THREADS - 1) / RED_THREADS;
+    // weighted-sum recursion: 8-to-1 while the arrays are long (throughput), 2-to-1 -- chains of depth one -- for the tail
+    pl.red_levels = 0;
+    pl.red_m[0] = pl.B;
+    pl.red_buf_elems[0] = pl.red_buf_elems[1] = 1;
+    while (pl.red_m[pl.red_levels] > 1) {
+        const uint32_t l = pl.red_levels, m = pl.red_m[l];
+        pl.red_log_r[l] = m >= RED_WIDE_MIN ? 3 : 1;
+        pl.red_m[l + 1] = (m + (1u << pl.red_log_r[l]) - 1) >> pl.red_log_r[l];
+        const uint64_t out_elems = (uint64_t)(l + 2) * pl.G * pl.red_m[l + 1];
+        pl.red_buf_elems[l & 1] = std::max(pl.red_buf_elems[l & 1], out_elems);
+        ++pl.red_levels;
+    }
     // task length: at least 256 and four times the mean bucket load (rounded up to a power of two, capped), so
     // that ordinary buckets -- including the denser ones of narrow / top windows -- stay a single task while an
     // oversized bucket (skewed scalars) is cut into pieces a few times the typical thread's work
@@ -581,7 +582,7 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
            o_tbase = take(nb * 4), o_sorted = take(entries * 4 + 4), o_scan = take((nb / SCAN_TILE + 2) * 4),
            o_hist = take((SEG_MAX + 1) * 4), o_hcur = take((SEG_MAX + 1) * 4), o_misc = take(64), o_heavy = take(nb * 4),
            o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)), o_bval = take(nb * sizeof(g1x_t)),
-           o_part = take((size_t)pl.G * pl.red_ctas_per_group * sizeof(g1x_t)), o_sum = take((size_t)pl.G * sizeof(g1x_t));
+           o_red0 = take(pl.red_buf_elems[0] * sizeof(g1x_t)), o_red1 = take(pl.red_buf_elems[1] * sizeof(g1x_t));
     int rc = zkb_reserve(ctx, buf, off);
     if (rc) return rc;
     char *p = (char *)buf.p;
@@ -590,7 +591,7 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
     ws.scan_tmp = (uint32_t *)(p + o_scan); ws.size_hist = (uint32_t *)(p + o_hist); ws.size_cursor = (uint32_t *)(p + o_hcur);
     ws.misc = (uint32_t *)(p + o_misc); ws.heavy_list = (uint32_t *)(p + o_heavy); ws.task_order = (uint2 *)(p + o_order);
     ws.task_out = (g1x_t *)(p + o_out); ws.bucket_val = (g1x_t *)(p + o_bval);
-    ws.grp_partial = (g1x_t *)(p + o_part); ws.grp_sum = (g1x_t *)(p + o_sum);
+    ws.red_buf[0] = (g1x_t *)(p + o_red0); ws.red_buf[1] = (g1x_t *)(p + o_red1);
     *max_tasks_out = max_tasks;
     *max_heavy_tasks_out = max_heavy_tasks;
     return ZKB_OK;
@@ -626,7 +627,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     }
     int rc = carve_ws(ctx, sl.ws, pl, n, ws, &max_tasks, &max_heavy);
     if (rc) return rc;
-    size_t out_bytes = (size_t)pl.G * sizeof(g1x_t);
+    size_t out_bytes = (size_t)pl.G * (pl.red_levels + 1) * sizeof(g1x_t);      // per group: total, A_0 .. A_{L-1}
     if (sl.pinned_bytes < out_bytes) {
         if (sl.pinned) cudaFreeHost(sl.pinned);
         ZKB_CUDA(ctx, cudaMallocHost(&sl.pinned, out_bytes));
@@ -671,27 +672,44 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
         ZKB_CUDA(ctx, cudaEventRecord(sl.acc_done, s));
         ZKB_CUDA(ctx, cudaStreamWaitEvent(ts, sl.acc_done, 0));
     }
-    msm_reduce_kernel<<<pl.G * pl.red_ctas_per_group, RED_THREADS, 0, ts>>>(ws.bucket_val, pl.B, pl.red_ctas_per_group, pl.red_ch,
-                                                                            ws.grp_partial);
-    msm_reduce_final_kernel<<<pl.G, RED_THREADS, 0, ts>>>(ws.grp_partial, pl.red_ctas_per_group, ws.grp_sum);
+    const g1x_t *level_in = ws.bucket_val;
+    for (uint32_t l = 0; l < pl.red_levels; ++l) {
+        const uint32_t m_in = pl.red_m[l], m_out = pl.red_m[l + 1];
+        dim3 grid((m_out + RED_THREADS - 1) / RED_THREADS, l + 1, pl.G);
+        g1x_t *level_out = ws.red_buf[l & 1];
+        if (pl.red_log_r[l] == 3) msm_wsum_level_kernel<8><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, l, level_out);
+        else msm_wsum_level_kernel<2><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, l, level_out);
+        level_in = level_out;
+    }
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], ts));
     ZKB_CUDA(ctx, cudaGetLastError());
     st->ev_valid = true;
-    ctx->launches += 18;                 // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduce x 2
-    ZKB_CUDA(ctx, cudaMemcpyAsync(sl.pinned, ws.grp_sum, out_bytes, cudaMemcpyDeviceToHost, ts));
+    ctx->launches += 16 + pl.red_levels; // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduction levels
+    // the last level's output is [stream][group][1]: stream 0 = plain total, stream 1 + k = total of A_k
+    ZKB_CUDA(ctx, cudaMemcpyAsync(sl.pinned, pl.red_levels ? (const void *)level_in : (const void *)ws.bucket_val, out_bytes,
+                                  cudaMemcpyDeviceToHost, ts));
     ZKB_CUDA(ctx, cudaEventRecord(sl.tail_done, ts));
     *plan_out = pl;
     return ZKB_OK;
 }
 
-// fold the group sums of a finished MSM on the host; result in XYZZ
+// fold the level totals of a finished MSM on the host; result in XYZZ.
+// Per group: sum_j (j+1) X[j] = total + A_0 + R_0 * (A_1 + R_1 * (A_2 + ...)); then the windows (plain bases only).
 hec::Pt msm_fold(const MsmPlan &pl, const void *pinned) {
-    const hec::Pt *part = (const hec::Pt *)pinned;
-    if (pl.G == 1) return part[0];
+    const hec::Pt *part = (const hec::Pt *)pinned;              // [stream][group]
+    auto group_sum = [&](uint32_t g) {
+        hec::Pt acc = hec::inf();
+        for (uint32_t l = pl.red_levels; l-- > 0;) {
+            for (uint32_t k = 0; k < pl.red_log_r[l]; ++k) acc = hec::dbl(acc);
+            acc = hec::add(acc, part[(size_t)(1 + l) * pl.G + g]);
+        }
+        return hec::add(acc, part[g]);
+    };
+    if (pl.G == 1) return group_sum(0);
     hec::Pt total = hec::inf();
     for (uint32_t w = pl.W; w-- > 0;) {
         for (uint32_t k = 0; k < pl.c; ++k) total = hec::dbl(total);
-        total = hec::add(total, part[w]);
+        total = hec::add(total, group_sum(w));
     }
     return total;
 }
