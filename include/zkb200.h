@@ -114,6 +114,12 @@ ZKB_API int zkb_commit_dev(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t
  * coeffs_mont_dev[k]: device pointer; offsets may be NULL (all 0); out_xy: count x 8 limbs; is_inf: count (or NULL). */
 ZKB_API int zkb_commit_batch_dev(zkb_ctx *ctx, const uint64_t *const *coeffs_mont_dev, const size_t *offsets, const size_t *lens,
                          size_t count, uint64_t *out_xy, int *is_inf);
+/* The same batch, incrementally: zkb_commit_push enqueues the MSM of one more polynomial and returns at once,
+ * zkb_commit_finish waits for the open batch and writes its commitments in push order.  Between pushes the caller
+ * may enqueue other work or block in a host copy while the GPU commits (zkb_plonk_prove uploads wire b during the
+ * commitment to wire a).  The coefficient buffers must stay untouched until zkb_commit_finish returns. */
+ZKB_API int zkb_commit_push(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset, size_t len);
+ZKB_API int zkb_commit_finish(zkb_ctx *ctx, uint64_t *out_xy, int *is_inf);
 /* out_points_dev[i] = scalars_dev[i] * base: builds [tau^i]G-style SRS / synthetic points directly in HBM
  * (what PC::setup's FixedBaseMSM does once per SRS, plonk.rs:195). */
 ZKB_API int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], const uint64_t *scalars_dev, size_t n,

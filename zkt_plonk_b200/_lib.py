@@ -59,6 +59,8 @@ def load():
         "zkb_msm_g1_bases": (i, [vp, vp, vp, sz, vp, ctypes.POINTER(i)]),
         "zkb_commit_batch_dev": (i, [vp, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, vp, ctypes.POINTER(i)]),
         "zkb_commit_dev": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
+        "zkb_commit_push": (i, [vp, vp, sz, sz]),
+        "zkb_commit_finish": (i, [vp, vp, ctypes.POINTER(i)]),
         "zkb_g1_fixed_base_mul_dev": (i, [vp, vp, vp, sz, vp]),
         "zkb_msm_set_window": (i, [vp, i]),
         "zkb_test_fp_binop": (i, [vp, i, i, vp, vp, vp, sz]),

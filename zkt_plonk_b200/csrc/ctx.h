@@ -91,6 +91,7 @@ inline int zkb_reserve(zkb_ctx *ctx, DevBuf &b, size_t bytes) {
 int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int inverse, int coset);
 void zkb_msm_release(zkb_ctx *ctx);
 void zkb_comm_release(zkb_ctx *ctx);
+void zkb_commit_abort(zkb_ctx *ctx);   // drain and drop an open zkb_commit_push batch (error recovery)
 // all ranks: recv_host[r * bytes ..] = rank r's send_host[0 .. bytes)  (NCCL all-gather on the context's stream; synchronous)
 int zkb_comm_allgather(zkb_ctx *ctx, const void *send_host, size_t bytes, void *recv_host);
 // two-level power tables base^e = lo[e & (2^s - 1)] * hi[e >> s], e < 2^lm (Montgomery Fr); hi is pre-scaled by hi_scale

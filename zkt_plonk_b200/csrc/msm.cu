@@ -33,6 +33,7 @@
 #include "host_ff.h"
 
 #include <algorithm>
+#include <array>
 #include <vector>
 
 using namespace zkb;
@@ -41,8 +42,8 @@ namespace {
 
 constexpr uint32_t SEG_MAX = 1024;       // upper bound of the per-MSM task length `seg` (points per accumulation task)
 constexpr uint32_t RED_THREADS = 128;    // threads per CTA in the window reduction
-constexpr uint32_t RED_MAX_LEVELS = 24;  // levels of the weighted-sum recursion (radix 8 or 2 each)
-constexpr uint32_t RED_WIDE_MIN = 16384; // arrays at least this long are shortened 8-to-1, shorter ones 2-to-1
+constexpr uint32_t RED_MAX_LEVELS = 26;  // levels of the weighted-sum recursion
+constexpr uint32_t RED_CTAS_PER_SM = 3;  // resident CTAs of the wide level (<= 170 registers per thread)
 constexpr uint32_t SIGN_BIT = 0x80000000u;
 
 struct MsmPlan {
@@ -50,8 +51,8 @@ struct MsmPlan {
     uint32_t G;                          // bucket groups: W (one per window) or 1 (fixed-base tables)
     uint32_t wide;                       // windows [0, wide) are c bits wide, the others c - 1 (wide = W: uniform)
     uint64_t nbuckets;                   // G * B
-    uint32_t red_levels;                 // weighted-sum recursion: levels, radix (log2) and input length of each
-    uint8_t red_log_r[RED_MAX_LEVELS];
+    uint32_t red_levels;                 // weighted-sum recursion: levels, radix and input length of each
+    uint32_t red_r[RED_MAX_LEVELS];
     uint32_t red_m[RED_MAX_LEVELS + 1];
     uint64_t red_buf_elems[2];           // ping-pong buffers of the recursion (levels alternate)
     uint32_t seg;                        // max points per accumulation task
@@ -85,6 +86,10 @@ struct MsmState {
     uint64_t last_entries = 0;           // n * W upper bound of bucket insertions of the last MSM
     uint32_t last_c = 0, last_W = 0;
     void *fixed_base = nullptr;          // FixedBase* (fixed-base window tables of the resident SRS)
+    // open batch of pipelined commitments (zkb_commit_push / zkb_commit_finish)
+    std::vector<std::array<uint64_t, 16>> pipe_partial;   // folded XYZZ partial sum of every pushed commitment
+    std::vector<char> pipe_pending;      // 1: enqueued, result still in its slot's pinned buffer
+    MsmPlan pipe_plan[2];
 };
 
 // ------------------------------------------------------------------ digits
@@ -367,16 +372,17 @@ __global__ void __launch_bounds__(128) msm_combine_giant_kernel(const uint32_t *
 //   stream s >= 1 (plain A): out[s][g][t] = sum_b in[s][g][R*t+b]
 // Then sum_j j*X[j] = sum_t A[t] + R * sum_t t*out[0][t]: the next level continues on out[0].  Elements past M_in read
 // as the identity.  grid = (ceil(M_out / 128), n_plain + 1, G).
-template <int R>
-__global__ void __launch_bounds__(RED_THREADS) msm_wsum_level_kernel(const g1x_t *__restrict__ in, uint32_t M_in, uint32_t M_out,
-                                                                     uint32_t n_plain, g1x_t *__restrict__ out) {
+template <bool WIDE>
+__global__ void __launch_bounds__(RED_THREADS, WIDE ? RED_CTAS_PER_SM : 1) msm_wsum_level_kernel(const g1x_t *__restrict__ in, uint32_t M_in,
+                                                                                                uint32_t M_out, uint32_t R, uint32_t n_plain,
+                                                                                                g1x_t *__restrict__ out) {
     const uint32_t t = blockIdx.x * RED_THREADS + threadIdx.x;
     if (t >= M_out) return;
     const uint32_t strm = blockIdx.y, g = blockIdx.z, G = gridDim.z;
     const g1x_t *src = in + ((size_t)strm * G + g) * M_in + (size_t)R * t;
-    const uint32_t avail = min((uint32_t)R, M_in - R * t);         // >= 1
+    const uint32_t avail = min(R, M_in - R * t);                   // >= 1
     g1x_t *dst = out + ((size_t)strm * G + g) * M_out + t;
-    if (R == 2) {
+    if (!WIDE) {                                                  // R == 2: chains of depth one
         g1x_t x0 = g1x_load(src);
         if (avail > 1) {
             g1x_t x1 = g1x_load(src + 1);
@@ -490,6 +496,14 @@ inline Pt add(const Pt &a, const Pt &b) {
     o.zzz = host::mul(host::mul(a.zzz, b.zzz, FQ), ppp, FQ);
     return o;
 }
+inline Pt mul_small(const Pt &p, uint32_t k) {                   // k * p, double-and-add from the top bit
+    Pt acc = inf();
+    for (int bit = 31; bit >= 0; --bit) {
+        acc = dbl(acc);
+        if ((k >> bit) & 1) acc = add(acc, p);
+    }
+    return acc;
+}
 inline void to_affine(const Pt &p, uint64_t out_xy[8], int *is_inf_out) {
     if (is_inf(p)) { memset(out_xy, 0, 64); if (is_inf_out) *is_inf_out = 1; return; }
     Fe zi = host::inv(p.zzz, FQ);
@@ -535,7 +549,7 @@ uint32_t pick_window(size_t n, bool shared_buckets) {
     return best_c;
 }
 
-MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset) {
+MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset, int sm_count) {
     MsmPlan pl;
     if (fb) {
         pl.c = fb->c; pl.W = fb->W; pl.G = 1; pl.wide = fb->wide;
@@ -547,14 +561,19 @@ MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset) {
     }
     pl.B = 1u << (pl.c - 1);
     pl.nbuckets = (uint64_t)pl.G * pl.B;
-    // weighted-sum recursion: 8-to-1 while the arrays are long (throughput), 2-to-1 -- chains of depth one -- for the tail
+    // weighted-sum recursion: the first level shortens the bucket array R0-to-1 with R0 chosen so that its grid is one
+    // full wave of resident CTAs (throughput-bound: ~2 additions per bucket), every later level is 2-to-1 (chains of
+    // depth one: the tail is latency-bound, and depth log2 is the least a tree can have)
     pl.red_levels = 0;
     pl.red_m[0] = pl.B;
     pl.red_buf_elems[0] = pl.red_buf_elems[1] = 1;
+    const uint64_t wave = (uint64_t)sm_count * RED_CTAS_PER_SM * RED_THREADS;
+    uint32_t r0 = (uint32_t)((pl.nbuckets + wave - 1) / wave);
+    if ((uint64_t)pl.G * ((pl.B + r0 - 1) / (r0 ? r0 : 1)) > wave && r0) ++r0;   // per-group rounding may spill over the wave
     while (pl.red_m[pl.red_levels] > 1) {
         const uint32_t l = pl.red_levels, m = pl.red_m[l];
-        pl.red_log_r[l] = m >= RED_WIDE_MIN ? 3 : 1;
-        pl.red_m[l + 1] = (m + (1u << pl.red_log_r[l]) - 1) >> pl.red_log_r[l];
+        pl.red_r[l] = (l == 0 && r0 >= 4) ? r0 : 2;
+        pl.red_m[l + 1] = (m + pl.red_r[l] - 1) / pl.red_r[l];
         const uint64_t out_elems = (uint64_t)(l + 2) * pl.G * pl.red_m[l + 1];
         pl.red_buf_elems[l & 1] = std::max(pl.red_buf_elems[l & 1], out_elems);
         ++pl.red_levels;
@@ -610,7 +629,7 @@ MsmState *state(zkb_ctx *ctx) {
 int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, size_t n, int force_c, const FixedBase *fb,
                 size_t offset, MsmPlan *plan_out, int slot_id = 0, bool pipelined = false) {
     if (n >= (1ull << 31)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n must be < 2^31");
-    MsmPlan pl = make_plan(n, force_c, fb, offset);
+    MsmPlan pl = make_plan(n, force_c, fb, offset, ctx->sm_count);
     if ((uint64_t)n * pl.W >= (1ull << 32)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n * windows must be < 2^32");
     MsmWs ws;
     uint64_t max_tasks, max_heavy;
@@ -677,8 +696,8 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
         const uint32_t m_in = pl.red_m[l], m_out = pl.red_m[l + 1];
         dim3 grid((m_out + RED_THREADS - 1) / RED_THREADS, l + 1, pl.G);
         g1x_t *level_out = ws.red_buf[l & 1];
-        if (pl.red_log_r[l] == 3) msm_wsum_level_kernel<8><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, l, level_out);
-        else msm_wsum_level_kernel<2><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, l, level_out);
+        if (pl.red_r[l] != 2) msm_wsum_level_kernel<true><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, pl.red_r[l], l, level_out);
+        else msm_wsum_level_kernel<false><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, 2, l, level_out);
         level_in = level_out;
     }
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], ts));
@@ -700,7 +719,7 @@ hec::Pt msm_fold(const MsmPlan &pl, const void *pinned) {
     auto group_sum = [&](uint32_t g) {
         hec::Pt acc = hec::inf();
         for (uint32_t l = pl.red_levels; l-- > 0;) {
-            for (uint32_t k = 0; k < pl.red_log_r[l]; ++k) acc = hec::dbl(acc);
+            acc = hec::mul_small(acc, pl.red_r[l]);
             acc = hec::add(acc, part[(size_t)(1 + l) * pl.G + g]);
         }
         return hec::add(acc, part[g]);
@@ -741,6 +760,15 @@ void zkb_msm_release(zkb_ctx *ctx) {
     }
     delete st;
     ctx->msm_state = nullptr;
+}
+
+void zkb_commit_abort(zkb_ctx *ctx) {
+    MsmState *st = (MsmState *)ctx->msm_state;
+    if (!st || st->pipe_partial.empty()) return;
+    for (size_t k = 0; k < st->pipe_pending.size(); ++k)
+        if (st->pipe_pending[k]) cudaEventSynchronize(st->slot[k & 1].tail_done);
+    st->pipe_partial.clear();
+    st->pipe_pending.clear();
 }
 
 extern "C" {
@@ -929,71 +957,115 @@ int zkb_msm_last_timing(zkb_ctx *ctx, float out_ms[5], uint64_t info[3]) {
     return ZKB_OK;
 }
 
+// ---- pipelined commitments: zkb_commit_push enqueues the MSM of one more HBM-resident polynomial, zkb_commit_finish waits for
+// the open batch and returns the affine commitments.  The MSMs alternate between two workspaces: while MSM k's
+// latency-bound window reduction and result download run on a high-priority stream, MSM k+1 already sorts and
+// accumulates on the main stream; between pushes the caller is free to enqueue other work or block in a host copy
+// (the prover uploads wire b while the GPU commits to wire a).
+// Point-range view: offsets / lengths are global; this context holds SRS[srs_lo, srs_lo + srs_n) and works on the
+// overlap (the whole polynomial on a single GPU).  With world > 1 the XYZZ partial sums of all ranks are all-gathered
+// (128 B per rank and commitment, one NCCL call per batch) and every rank adds them identically.
+static int commit_collect(zkb_ctx *ctx, MsmState *st, size_t k) {          // fold MSM k of the open batch on the host
+    if (!st->pipe_pending[k]) return ZKB_OK;
+    const int slot = (int)(k & 1);
+    ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[slot].tail_done));
+    hec::Pt p = msm_fold(st->pipe_plan[slot], st->slot[slot].pinned);
+    memcpy(st->pipe_partial[k].data(), &p, 128);
+    st->pipe_pending[k] = 0;
+    return ZKB_OK;
+}
+
+int zkb_commit_push(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset, size_t len) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (!coeffs_mont_dev && len) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_push: null coefficients");
+    if (offset + len > ctx->srs_global_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_commit_push: offset + n exceeds the loaded SRS");
+    MsmState *st = state(ctx);
+    const FixedBase *fb = (const FixedBase *)st->fixed_base;
+    if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;
+    const size_t k = st->pipe_partial.size();
+    const int slot = (int)(k & 1);
+    const size_t g_lo = std::max(offset, ctx->srs_lo), g_hi = std::min(offset + len, ctx->srs_lo + ctx->srs_n);
+    const size_t n = g_hi > g_lo ? g_hi - g_lo : 0;
+    int rc = ZKB_OK;
+    if (k >= 2) {                                                          // slot reuse: MSM k-2 must be folded first
+        rc = commit_collect(ctx, st, k - 2);
+        if (rc) return rc;
+    }
+    st->pipe_partial.emplace_back();
+    st->pipe_partial[k].fill(0);                                           // identity
+    st->pipe_pending.push_back(0);
+    if (!n) return ZKB_OK;
+    const size_t stride = ctx->srs_n * 32 + 32;                             // canonical scalars, one buffer per slot
+    if (ctx->stage.bytes < 2 * stride) {
+        if (k) {                                                           // growing would free memory that MSMs in flight still read
+            for (size_t j = 0; j < k; ++j) if ((rc = commit_collect(ctx, st, j))) return rc;
+        }
+        rc = zkb_reserve(ctx, ctx->stage, 2 * stride);
+        if (rc) return rc;
+    }
+    uint4 *scal = (uint4 *)((char *)ctx->stage.p + (size_t)slot * stride);
+    if (k >= 2) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->slot[slot].tail_done, 0));
+    fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)(coeffs_mont_dev + 4 * (g_lo - offset)), scal, (uint32_t)n);
+    const size_t off = g_lo - ctx->srs_lo;
+    rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, scal, n, 0, fb, off, &st->pipe_plan[slot], slot, true)
+            : msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + off, scal, n, ctx->msm_force_c, nullptr, 0, &st->pipe_plan[slot], slot, true);
+    if (rc) return rc;
+    st->pipe_pending[k] = 1;
+    return ZKB_OK;
+}
+
+int zkb_commit_finish(zkb_ctx *ctx, uint64_t *out_xy /* count x 8 */, int *is_inf /* count or NULL */) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    MsmState *st = state(ctx);
+    const size_t count = st->pipe_partial.size();
+    if (!out_xy && count) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_finish: null output");
+    int rc = ZKB_OK;
+    for (size_t k = 0; k < count && !rc; ++k) rc = commit_collect(ctx, st, k);
+    std::vector<std::array<uint64_t, 16>> part;
+    part.swap(st->pipe_partial);
+    st->pipe_pending.clear();
+    if (rc) return rc;
+    if (ctx->world > 1 && count) {
+        std::vector<std::array<uint64_t, 16>> all((size_t)ctx->world * count);
+        rc = zkb_comm_allgather(ctx, part.data(), count * 128, all.data());
+        if (rc) return rc;
+        for (size_t k = 0; k < count; ++k) {
+            hec::Pt total = hec::inf();
+            for (int r = 0; r < ctx->world; ++r) {
+                hec::Pt p;
+                memcpy(&p, all[(size_t)r * count + k].data(), 128);
+                total = hec::add(total, p);
+            }
+            hec::to_affine(total, out_xy + 8 * k, is_inf ? is_inf + k : nullptr);
+        }
+        return ZKB_OK;
+    }
+    for (size_t k = 0; k < count; ++k) {
+        hec::Pt p;
+        memcpy(&p, part[k].data(), 128);
+        hec::to_affine(p, out_xy + 8 * k, is_inf ? is_inf + k : nullptr);
+    }
+    return ZKB_OK;
+}
+
 // kzg10::commit for `count` polynomials resident in HBM (PolynomialCommitment::commit takes a batch: prove.rs:133-135
-// commits a, b, c together, :178-180 t, h1, h2, :249-251 z1, z2, :306-308 the three quotient parts).  The MSMs are
-// software-pipelined over two workspaces: while MSM k's latency-bound window reduction and result download run on a
-// high-priority stream, MSM k+1 already sorts and accumulates on the main stream.
+// commits a, b, c together, :178-180 t, h1, h2, :249-251 z1, z2, :306-308 the three quotient parts).
 int zkb_commit_batch_dev(zkb_ctx *ctx, const uint64_t *const *coeffs_mont_dev, const size_t *offsets, const size_t *lens, size_t count,
                          uint64_t *out_xy /* count x 8 */, int *is_inf /* count */) {
     if (!ctx) return ZKB_ERR_INVALID;
     if ((!coeffs_mont_dev || !lens || !out_xy) && count) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_batch_dev: null argument");
     MsmState *st = state(ctx);
-    const FixedBase *fb = (const FixedBase *)st->fixed_base;
-    if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;
-    // Point-range view: offsets / lengths are global; this context holds SRS[srs_lo, srs_lo + srs_n) and works on the
-    // overlap (the whole polynomial on a single GPU).  With world > 1 the XYZZ partial sums of all ranks are
-    // all-gathered (128 B per rank and commitment, one NCCL call per batch) and every rank adds them identically.
-    const bool sharded = ctx->world > 1;
-    std::vector<const uint64_t *> loc_ptr(count);
-    std::vector<size_t> loc_off(count), loc_n(count);
-    size_t max_len = 0;
-    for (size_t k = 0; k < count; ++k) {
-        const size_t off = offsets ? offsets[k] : 0;
-        if (off + lens[k] > ctx->srs_global_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_commit_batch_dev: offset + n exceeds the loaded SRS");
-        if (!coeffs_mont_dev[k] && lens[k]) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_batch_dev: null coefficients");
-        const size_t g_lo = std::max(off, ctx->srs_lo), g_hi = std::min(off + lens[k], ctx->srs_lo + ctx->srs_n);
-        loc_n[k] = g_hi > g_lo ? g_hi - g_lo : 0;
-        loc_off[k] = loc_n[k] ? g_lo - ctx->srs_lo : 0;
-        loc_ptr[k] = coeffs_mont_dev[k] + (loc_n[k] ? 4 * (g_lo - off) : 0);
-        max_len = loc_n[k] > max_len ? loc_n[k] : max_len;
+    if (!st->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_batch_dev: a zkb_commit_push batch is still open");
+    int rc = ZKB_OK;
+    for (size_t k = 0; k < count && !rc; ++k) rc = zkb_commit_push(ctx, coeffs_mont_dev[k], offsets ? offsets[k] : 0, lens[k]);
+    if (rc) {                                                              // drain and drop the partial batch
+        std::vector<uint64_t> scratch(8 * st->pipe_partial.size() + 8);
+        std::string err = ctx->err;
+        zkb_commit_finish(ctx, scratch.data(), nullptr);
+        ctx->err = err;
+        return rc;
     }
-    int rc = zkb_reserve(ctx, ctx->stage, 2 * (max_len * 32 + 32));     // canonical scalars, one buffer per slot
-    if (rc) return rc;
-    MsmPlan plans[2];
-    std::vector<hec::Pt> partial(count);
-    for (size_t k = 0; k <= count; ++k) {
-        if (k < count && loc_n[k]) {
-            const int slot = (int)(k & 1);
-            const size_t off = loc_off[k], n = loc_n[k];
-            if (k >= 2) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->slot[slot].tail_done, 0));   // slot reuse (already folded below)
-            uint4 *scal = (uint4 *)((char *)ctx->stage.p + (size_t)slot * (max_len * 32 + 32));
-            fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)loc_ptr[k], scal, (uint32_t)n);
-            rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, scal, n, 0, fb, off, &plans[slot], slot, true)
-                    : msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + off, scal, n, ctx->msm_force_c, nullptr, 0, &plans[slot], slot, true);
-            if (rc) return rc;
-        }
-        if (k >= 1) {                                       // finish MSM k-1 while MSM k runs
-            const int slot = (int)((k - 1) & 1);
-            if (loc_n[k - 1]) {
-                ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[slot].tail_done));
-                partial[k - 1] = msm_fold(plans[slot], st->slot[slot].pinned);
-            } else {
-                partial[k - 1] = hec::inf();
-            }
-            if (!sharded) hec::to_affine(partial[k - 1], out_xy + 8 * (k - 1), is_inf ? is_inf + (k - 1) : nullptr);
-        }
-    }
-    if (sharded && count) {
-        std::vector<hec::Pt> all((size_t)ctx->world * count);
-        rc = zkb_comm_allgather(ctx, partial.data(), count * sizeof(hec::Pt), all.data());
-        if (rc) return rc;
-        for (size_t k = 0; k < count; ++k) {
-            hec::Pt total = hec::inf();
-            for (int r = 0; r < ctx->world; ++r) total = hec::add(total, all[(size_t)r * count + k]);
-            hec::to_affine(total, out_xy + 8 * k, is_inf ? is_inf + k : nullptr);
-        }
-    }
-    return ZKB_OK;
+    return zkb_commit_finish(ctx, out_xy, is_inf);
 }
 
 }  // extern "C"

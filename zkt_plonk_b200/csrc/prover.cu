@@ -249,6 +249,8 @@ struct zkb_plonk_pk {
     Pt vk[10];                                   // q_m q_l q_r q_o q_c sigma1 sigma2 sigma3 q_lookup q_table (VerifierKey order)
     std::vector<void *> owned;                   // device allocations of the key
     Fe *stage = nullptr;                         // pinned host staging: t, f, h1, h2 (4 x n elements)
+    cudaStream_t copy_stream = nullptr;          // uploads of the lookup multisets (issued by the worker thread)
+    cudaEvent_t lookup_uploaded = nullptr, wire_uploaded = nullptr;
     char *arena = nullptr;                       // per-proof scratch: reset at the start of every prove
     size_t arena_bytes = 0, arena_off = 0;
 };
@@ -303,6 +305,26 @@ int commit_many(zkb_ctx *ctx, const DPoly *const *polys, size_t count, Pt *out) 
     return ZKB_OK;
 }
 
+// dst[pos[k]] = vals[k]  (PublicInputs::as_evals: pi.rs:75-82, a handful of rows in an otherwise zero column)
+__global__ void scatter_fe_kernel(uint4 *dst, const unsigned long long *pos, const uint4 *vals, size_t count) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    dst[2 * pos[k]] = vals[2 * k];
+    dst[2 * pos[k] + 1] = vals[2 * k + 1];
+}
+
+int commit_finish_pts(zkb_ctx *ctx, size_t count, Pt *out) {
+    std::vector<uint64_t> xy(8 * count);
+    std::vector<int> inf(count);
+    TRY(zkb_commit_finish(ctx, xy.data(), inf.data()));
+    for (size_t k = 0; k < count; ++k) {
+        out[k].inf = inf[k] != 0;
+        memcpy(out[k].x.l, &xy[8 * k], 32);
+        memcpy(out[k].y.l, &xy[8 * k + 4], 32);
+    }
+    return ZKB_OK;
+}
+
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -317,6 +339,9 @@ void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
     for (void *p : pk->owned) cudaFree(p);
     if (pk->arena) cudaFree(pk->arena);
     if (pk->stage) cudaFreeHost(pk->stage);
+    if (pk->copy_stream) cudaStreamDestroy(pk->copy_stream);
+    if (pk->lookup_uploaded) cudaEventDestroy(pk->lookup_uploaded);
+    if (pk->wire_uploaded) cudaEventDestroy(pk->wire_uploaded);
     delete pk;
 }
 
@@ -382,6 +407,10 @@ int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selector
         return fail((ctx->err = "zkb_plonk_setup: cannot allocate the prover arena", ZKB_ERR_OOM));
     if (cudaMallocHost((void **)&pk->stage, 4 * n * sizeof(Fe)) != cudaSuccess)
         return fail((ctx->err = "zkb_plonk_setup: cannot allocate pinned staging", ZKB_ERR_OOM));
+    if (cudaStreamCreateWithFlags(&pk->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pk->lookup_uploaded, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pk->wire_uploaded, cudaEventDisableTiming) != cudaSuccess)
+        return fail((ctx->err = "zkb_plonk_setup: cannot create the copy stream", ZKB_ERR_CUDA));
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail((ctx->err = "zkb_plonk_setup: stream error", ZKB_ERR_CUDA));
     *out = pk;
     return ZKB_OK;
@@ -408,6 +437,7 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     const unsigned log_n = pk->log_n;
     const size_t n = pk->n, n4 = 4 * n, cap = n + 8, n_pi = pk->pi_pos.size();
     const_cast<zkb_plonk_pk *>(pk)->arena_off = 0;
+    zkb_commit_abort(ctx);                                                 // a previous call may have failed between push and finish
     cudaStream_t s = ctx->stream;
     double t_mark = now_ms(), t_start = t_mark;
     auto tick = [&](int slot) {
@@ -431,7 +461,11 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
 
     // ---- round 2's host side (prove.rs:145-167) depends only on the witness and the key, not on any challenge: a
     // worker thread builds t, f = q_lookup * c and combine_split(t, f) in pinned memory while the GPU runs round 1
+    // and uploads the four columns on its own stream
     Fe *t_vals = pk->stage, *f_vals = pk->stage + n, *h1_vals = pk->stage + 2 * n, *h2_vals = pk->stage + 3 * n;
+    uint64_t *ev_a, *ev_b, *ev_c, *ev_t, *ev_f, *ev_h1, *ev_h2;
+    TAKE(ev_a, n); TAKE(ev_b, n); TAKE(ev_c, n);
+    TAKE(ev_t, n); TAKE(ev_f, n); TAKE(ev_h1, n); TAKE(ev_h2, n);
     std::atomic<int> lookup_status{0};
     std::thread lookup_worker([&]() {
         memset(t_vals, 0, n * sizeof(Fe));
@@ -445,21 +479,25 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
             else f_vals[i] = fmul(q, cv[i]);
         }
         size_t n_h1 = 0, n_h2 = 0;
-        if (!combine_split(t_vals, n, f_vals, n, h1_vals, h2_vals, &n_h1, &n_h2)) lookup_status.store(1);
-        else if (n_h1 != n || n_h2 != n) lookup_status.store(2);
+        if (!combine_split(t_vals, n, f_vals, n, h1_vals, h2_vals, &n_h1, &n_h2)) { lookup_status.store(1); return; }
+        if (n_h1 != n || n_h2 != n) { lookup_status.store(2); return; }
+        cudaStream_t cs = pk->copy_stream;                                // pinned -> HBM while the main stream runs round 1
+        if (cudaSetDevice(ctx->device) != cudaSuccess ||
+            cudaMemcpyAsync(ev_t, t_vals, n * 32, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+            cudaMemcpyAsync(ev_f, f_vals, n * 32, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+            cudaMemcpyAsync(ev_h1, h1_vals, n * 32, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+            cudaMemcpyAsync(ev_h2, h2_vals, n * 32, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+            cudaEventRecord(pk->lookup_uploaded, cs) != cudaSuccess)
+            lookup_status.store(3);
     });
     struct Joiner {                                                     // never leave the scope with a joinable thread
         std::thread &t;
         ~Joiner() { if (t.joinable()) t.join(); }
     } lookup_joiner{lookup_worker};
 
-    // ---- round 1: wires (prove.rs:116-140)
-    uint64_t *ev_a, *ev_b, *ev_c;
-    TAKE(ev_a, n); TAKE(ev_b, n); TAKE(ev_c, n);
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_a, a, n * 32, cudaMemcpyHostToDevice, s));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_b, b, n * 32, cudaMemcpyHostToDevice, s));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_c, c, n * 32, cudaMemcpyHostToDevice, s));
-    tick(0);
+    // ---- round 1: wires (prove.rs:116-140).  The uploads come from the caller's (pageable) vectors and block the host,
+    // so they go through the copy stream and are interleaved with the commitments: the GPU commits to wire a on the
+    // main stream while wire b crosses PCIe.
     // evals (device) -> blinded coefficient polynomial
     auto blinded_from_dev_evals = [&](const uint64_t *evals, int k_blind, DPoly *out) -> int {
         uint64_t *d;
@@ -477,11 +515,19 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
         return ZKB_OK;
     };
     DPoly pa, pb, pc;
-    TRY(blinded_from_dev_evals(ev_a, 2, &pa));
-    TRY(blinded_from_dev_evals(ev_b, 2, &pb));
-    TRY(blinded_from_dev_evals(ev_c, 2, &pc));
+    {
+        struct { const uint64_t *host; uint64_t *dev; DPoly *poly; } wires[3] = {{a, ev_a, &pa}, {b, ev_b, &pb}, {c, ev_c, &pc}};
+        for (int k = 0; k < 3; ++k) {
+            ZKB_CUDA(ctx, cudaMemcpyAsync(wires[k].dev, wires[k].host, n * 32, cudaMemcpyHostToDevice, pk->copy_stream));
+            ZKB_CUDA(ctx, cudaEventRecord(pk->wire_uploaded, pk->copy_stream));
+            ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->wire_uploaded, 0));
+            if (k == 0) tick(0);
+            TRY(blinded_from_dev_evals(wires[k].dev, 2, wires[k].poly));
+            TRY(zkb_commit_push(ctx, wires[k].poly->d, 0, wires[k].poly->len));
+        }
+    }
     Pt c_a[3];
-    { const DPoly *ps[3] = {&pa, &pb, &pc}; TRY(commit_many(ctx, ps, 3, c_a)); }
+    TRY(commit_finish_pts(ctx, 3, c_a));
     tr.append_commitment("a_commit", c_a[0]);
     tr.append_commitment("b_commit", c_a[1]);
     tr.append_commitment("c_commit", c_a[2]);
@@ -491,12 +537,8 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     lookup_worker.join();                                               // started before round 1 (see above)
     if (lookup_status.load() == 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "ElementNotIndexedInTable (lookup/multiset.rs:121)");
     if (lookup_status.load() == 2) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: combine_split halves are not n long");
-    uint64_t *ev_t, *ev_f, *ev_h1, *ev_h2;
-    TAKE(ev_t, n); TAKE(ev_f, n); TAKE(ev_h1, n); TAKE(ev_h2, n);
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_t, t_vals, n * 32, cudaMemcpyHostToDevice, s));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_f, f_vals, n * 32, cudaMemcpyHostToDevice, s));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_h1, h1_vals, n * 32, cudaMemcpyHostToDevice, s));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ev_h2, h2_vals, n * 32, cudaMemcpyHostToDevice, s));
+    if (lookup_status.load() == 3) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_prove: upload of the lookup multisets failed");
+    ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->lookup_uploaded, 0));
     tick(2);
     DPoly pt, ph1, ph2;
     TRY(blinded_from_dev_evals(ev_t, 0, &pt));
@@ -545,14 +587,23 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     // ---- round 4: quotient (prove.rs:258-308, quotient_poly.rs:20-227)
     DPoly ppi;
     {
-        std::vector<Fe> pi_evals(n, Fe{{0, 0, 0, 0}});                      // PublicInputs::as_evals (pi.rs:75-82)
-        for (size_t k = 0; k < n_pi; ++k) {
+        for (size_t k = 0; k < n_pi; ++k)
             if (pk->pi_pos[k] >= n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: public input position out of range");
-            pi_evals[pk->pi_pos[k]] = fe_from(pi_values + 4 * k);
-        }
-        uint64_t *d;
+        uint64_t *d, *d_vals = nullptr, *d_pos = nullptr;                  // PublicInputs::as_evals (pi.rs:75-82), built in HBM
         TAKE(d, n);
-        TRY(poly_from_evals_host(ctx, (const uint64_t *)pi_evals.data(), log_n, d, n, &ppi));
+        ZKB_CUDA(ctx, cudaMemsetAsync(d, 0, n * 32, s));
+        if (n_pi) {
+            std::vector<unsigned long long> pos(pk->pi_pos.begin(), pk->pi_pos.end());
+            TAKE(d_vals, n_pi); TAKE(d_pos, (n_pi + 3) / 4);
+            ZKB_CUDA(ctx, cudaMemcpyAsync(d_vals, pi_values, n_pi * 32, cudaMemcpyHostToDevice, s));
+            ZKB_CUDA(ctx, cudaMemcpyAsync(d_pos, pos.data(), n_pi * 8, cudaMemcpyHostToDevice, s));
+            ZKB_CUDA(ctx, cudaStreamSynchronize(s));                     // `pos` is a host temporary
+            scatter_fe_kernel<<<(unsigned)((n_pi + 127) / 128), 128, 0, s>>>((uint4 *)d, (const unsigned long long *)d_pos, (const uint4 *)d_vals, n_pi);
+            ZKB_CUDA(ctx, cudaGetLastError());
+        }
+        TRY(zkb_ntt_dev(ctx, d, n, log_n, 1, 0));
+        ppi.d = d; ppi.cap = n;
+        TRY(zkb_poly_effective_len_dev(ctx, d, n, &ppi.len));
     }
     const Fe alpha = tr.challenge_scalar("alpha");
     uint64_t *q_buf;
