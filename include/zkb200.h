@@ -217,6 +217,13 @@ ZKB_API int zkb_srs_set_range(zkb_ctx *ctx, size_t global_lo, size_t global_n);
 /* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a).  Host pointers. */
 ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n);
 
+/* Host only (no GPU): the round driver's MultiSet::combine_split (multiset.rs:103-146) specialised to t = table entries
+ * + zero padding up to n and f zero outside `rows`.  h1 / h2 (n elements each) are persistent staging kept zero outside
+ * the regions recorded in dirty[4] = {h1 prefix end, h1 suffix start, h2 prefix end, h2 suffix start} (start with
+ * zeroed buffers and {0, n, 0, n}).  Returns ZKB_ERR_INVALID for ElementNotIndexedInTable. */
+ZKB_API int zkb_test_combine_split(const uint64_t *table, size_t table_len, size_t n, const uint64_t *f, const uint32_t *rows,
+                           size_t n_rows, uint64_t *h1, uint64_t *h2, size_t dirty[4], size_t out_lens[2]);
+
 /* Kernels this context has enqueued so far (bench.py's gpu_launches is a difference of two readings). */
 ZKB_API uint64_t zkb_launch_count(zkb_ctx *ctx);
 /* Device time (CUDA events on the context's stream) of the phases of the last MSM, in ms:

@@ -99,3 +99,45 @@ def test_native_cpp_driver_matches_python_and_oracle(ctx, log_n, fixed_base):
     assert tm["total_ms"] > 0
     native.close()
     ctx.srs_precompute(-1)
+
+
+def test_native_driver_reuses_key_across_witnesses(ctx):
+    """One key object, several witnesses / tables in a row: the C++ driver keeps its pinned lookup staging zero outside
+    the regions a proof writes (sparse combine_split), so a proof must not see what the previous one left behind --
+    including a table that holds a zero entry (the zero bucket then sits in the middle of h1 / h2) and a shorter table."""
+    import copy
+    import zkt_plonk_b200 as z
+    log_n = 8
+    circ = synthetic.make_circuit(log_n, seed=77, table_size=64)
+    d_srs, _ = gpu_srs(ctx, circ.n + 8)
+    kzg = z.GpuKZG10(ctx)
+    kzg.load_committer_key(d_srs)
+    gbe = prover.GpuBackend(kzg)
+    gpk, gvk = prover.setup(gbe, circ)
+    native = prover.NativeProver(ctx, circ)
+    blinders = list(range(300, 319))
+    lookup_rows = [i for i, q in enumerate(prover.mont_array_to_ints(circ.selectors["q_lookup"])) if q]
+    assert lookup_rows
+
+    def with_table(table):                                                 # same witness (it must stay satisfiable), other table
+        v = copy.copy(circ)
+        v.table = list(table)
+        return v
+
+    c0 = prover.mont_array_to_ints(circ.c)
+    used = {c0[i] for i in lookup_rows}
+    only_used = [e for e in circ.table if e in used]                       # shorter table
+    # (a zero entry is only a valid Plookup table when it comes last, where the padding zeros follow it)
+    variants = [circ, with_table(circ.table + [0]), with_table(circ.table[::-1]), with_table(only_used),
+                with_table(only_used[::-1] + [0]), circ]
+    for v in variants:
+        native.circuit = v
+        raw = native.prove_bytes(blinders)
+        assert raw == prover.prove(gbe, gpk, gvk, v, blinders).to_bytes()
+        assert plonk_ref.verify(gvk, prover.proof_from_bytes(raw), list(circ.pi.values()), TAU) == 0
+    native.circuit = with_table(only_used[1:])                             # a looked-up output that is not in the table
+    with pytest.raises(Exception, match="ElementNotIndexedInTable"):
+        native.prove_bytes(blinders)
+    native.circuit = circ
+    assert native.prove_bytes(blinders) == prover.prove(gbe, gpk, gvk, circ, blinders).to_bytes()
+    native.close()

@@ -3,6 +3,8 @@ restated verifier accepts -- the reference's own acceptance criterion (plonk.rs:
 tampered ones; also pins the Merlin transcript against merlin's published test vector."""
 import random
 
+import numpy as np
+
 import pytest
 
 from oracle import plonk_ref
@@ -104,3 +106,50 @@ def test_unsatisfied_witness_is_rejected():
     except (AssertionError, ValueError, ZeroDivisionError):
         return                                              # e.g. the lookup value left the table
     assert plonk_ref.verify(vk, proof, list(circ.pi.values()), TAU) != 0
+
+
+def test_sparse_combine_split_matches_dense_across_reuse():
+    """The C++ round driver's combine_split only touches the table and the lookup rows and keeps its staging columns
+    zero elsewhere (csrc/prover.cu).  Against the dense numpy restatement of multiset.rs:103-146, over a sequence of
+    calls that reuse the same staging: tables with a zero entry first / in the middle / last, shrinking tables,
+    lookups of the zero entry, and an element that is not in the table."""
+    import ctypes
+    from zkt_plonk_b200 import _lib
+    lib = _lib.lib()
+    fn = lib.zkb_test_combine_split
+    fn.restype = ctypes.c_int
+    vp = ctypes.c_void_p
+    fn.argtypes = [vp, ctypes.c_size_t, ctypes.c_size_t, vp, vp, ctypes.c_size_t, vp, vp, vp, vp]
+    n = 256
+    rng = np.random.default_rng(3)
+    rows = np.sort(rng.choice(n, size=40, replace=False)).astype(np.uint32)
+    h1, h2 = np.zeros((n, 4), dtype=np.uint64), np.zeros((n, 4), dtype=np.uint64)
+    dirty = (ctypes.c_size_t * 4)(0, n, 0, n)
+    lens = (ctypes.c_size_t * 2)()
+    base = [int(v) for v in rng.integers(1, 1 << 60, size=30)]
+
+    def run(table, picks):
+        t = prover.table_multiset_array(table, 64, n)
+        f = np.zeros((n, 4), dtype=np.uint64)
+        f[rows] = prover.ints_to_mont_array(picks)
+        tab = prover.ints_to_mont_array(table) if table else np.zeros((1, 4), dtype=np.uint64)
+        rc = fn(tab.ctypes.data, len(table), n, f.ctypes.data, rows.ctypes.data, len(rows), h1.ctypes.data, h2.ctypes.data,
+                ctypes.addressof(dirty), ctypes.addressof(lens))
+        return rc, t, f
+
+    cases = [base, base[:3] + [0] + base[3:], [0] + base, base + [0], base[:7], base[:7][::-1], [0, base[0]], base]
+    for k, table in enumerate(cases):
+        pool = table if k % 2 == 0 else [e for e in table if e] or table
+        picks = [pool[int(j) % len(pool)] for j in rng.integers(0, 1 << 30, size=len(rows))]
+        if 0 in table:
+            picks[0] = 0                                           # a lookup of the zero entry itself
+        rc, t, f = run(table, picks)
+        assert rc == 0
+        e1, e2 = prover.combine_split_arrays(t, f)
+        assert (lens[0], lens[1]) == (e1.shape[0], e2.shape[0]) == (n, n)
+        assert np.array_equal(h1, e1) and np.array_equal(h2, e2), f"case {k}"
+    rc, _, _ = run(base[:5], [base[9]] * len(rows))               # ElementNotIndexedInTable
+    assert rc != 0
+    rc, t, f = run(base, [base[2]] * len(rows))                   # and the staging is still usable afterwards
+    e1, e2 = prover.combine_split_arrays(t, f)
+    assert rc == 0 and np.array_equal(h1, e1) and np.array_equal(h2, e2)

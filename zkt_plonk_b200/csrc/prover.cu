@@ -180,16 +180,22 @@ struct KeyHash {
 };
 struct KeyEq { bool operator()(const Fe &a, const Fe &b) const { return feq(a, b); } };
 
-// MultiSet::combine_split on Montgomery limb rows (unique per field element): buckets in order of first appearance
-// in t; every element of f must be in t; halves alternate on odd counts.  Returns false on ElementNotIndexedInTable.
-bool combine_split(const Fe *t, size_t nt, const Fe *f, size_t nf, Fe *h1, Fe *h2, size_t *n1, size_t *n2) {
+// MultiSet::combine_split (multiset.rs:103-146) on Montgomery limb rows (unique per field element): buckets in order
+// of first appearance in t, every element of f must be in t, halves alternate on odd counts; returns false on
+// ElementNotIndexedInTable.  Written for the shape the prover meets: t = table entries followed by
+// zero padding, f = q_lookup * c, which is zero outside the lookup gates.  Only the table and the lookup rows are touched: the
+// zero bucket (~2n elements) is counted arithmetically and its halves are never written, because the staging
+// columns are kept zero outside the small regions recorded in `dirty` (cleared before the next proof writes).
+// h1 / h2 come out as [prefix | zeros | suffix]; dirty[h][0] = end of the prefix, dirty[h][1] = start of the suffix.
+bool combine_split_sparse(const Fe *table, size_t table_len, size_t n, const Fe *f, const uint32_t *rows, size_t n_rows,
+                          Fe *h1, Fe *h2, size_t dirty[2][2], size_t *n1, size_t *n2) {
     std::vector<std::pair<Fe, size_t>> buckets;
     std::unordered_map<Fe, size_t, KeyHash, KeyEq> index;
-    index.reserve(4096);
+    index.reserve(2 * table_len + 16);
     size_t zero_bucket = (size_t)-1;
-    for (size_t i = 0; i < nt; ++i) {
-        const Fe &e = t[i];
-        if (host::is_zero(e)) {                                   // the bulk of t (padding): no hashing
+    for (size_t i = 0; i < table_len; ++i) {
+        const Fe &e = table[i];
+        if (host::is_zero(e)) {
             if (zero_bucket == (size_t)-1) { zero_bucket = buckets.size(); buckets.push_back({e, 0}); }
             ++buckets[zero_bucket].second;
             continue;
@@ -198,34 +204,50 @@ bool combine_split(const Fe *t, size_t nt, const Fe *f, size_t nf, Fe *h1, Fe *h
         if (it == index.end()) { index.emplace(e, buckets.size()); buckets.push_back({e, 1}); }
         else ++buckets[it->second].second;
     }
-    for (size_t i = 0; i < nf; ++i) {
-        const Fe &e = f[i];
-        if (host::is_zero(e)) {                                   // non-lookup gates: the bulk of f
-            if (zero_bucket == (size_t)-1) return false;
-            ++buckets[zero_bucket].second;
-            continue;
-        }
+    if (table_len < n) {                                           // the padding of LookupTable::into_multiset
+        if (zero_bucket == (size_t)-1) { zero_bucket = buckets.size(); buckets.push_back({Fe{{0, 0, 0, 0}}, 0}); }
+        buckets[zero_bucket].second += n - table_len;
+    }
+    size_t f_zeros = n - n_rows;                                   // rows without a lookup gate
+    for (size_t r = 0; r < n_rows; ++r) {
+        const Fe &e = f[rows[r]];
+        if (host::is_zero(e)) { ++f_zeros; continue; }
         auto it = index.find(e);
         if (it == index.end()) return false;
         ++buckets[it->second].second;
     }
-    size_t k1 = 0, k2 = 0;                                       // h1, h2 have room for (nt + nf + 1) / 2 elements each
-    bool parity = false;
-    for (const auto &b : buckets) {
-        size_t half = b.second / 2;
-        if (host::is_zero(b.first)) {
-            memset(h1 + k1, 0, half * sizeof(Fe));
-            memset(h2 + k2, 0, half * sizeof(Fe));
-        } else {
-            for (size_t j = 0; j < half; ++j) { h1[k1 + j] = b.first; h2[k2 + j] = b.first; }
-        }
-        k1 += half; k2 += half;
-        if (b.second & 1) {
-            if (parity) { h2[k2++] = b.first; parity = false; }
-            else { h1[k1++] = b.first; parity = true; }
-        }
+    if (f_zeros) {
+        if (zero_bucket == (size_t)-1) return false;               // a zero in f that the table does not hold
+        buckets[zero_bucket].second += f_zeros;
     }
-    *n1 = k1; *n2 = k2;
+    Fe *h[2] = {h1, h2};
+    for (int j = 0; j < 2; ++j) {                                  // forget what the previous proof left behind
+        memset(h[j], 0, dirty[j][0] * sizeof(Fe));
+        if (dirty[j][1] < n) memset(h[j] + dirty[j][1], 0, (n - dirty[j][1]) * sizeof(Fe));
+        dirty[j][0] = 0;
+        dirty[j][1] = n;
+    }
+    size_t k[2] = {0, 0};
+    bool parity = false, past_zero = false;
+    for (size_t b = 0; b < buckets.size(); ++b) {
+        const size_t half = buckets[b].second / 2;
+        const bool odd = buckets[b].second & 1;
+        const size_t add0 = half + ((odd && !parity) ? 1 : 0), add1 = half + ((odd && parity) ? 1 : 0);
+        if (k[0] + add0 > n || k[1] + add1 > n) return false;      // cannot happen for |t| = |f| = n; keeps the writes in bounds
+        if (b == zero_bucket) {
+            dirty[0][0] = k[0]; dirty[1][0] = k[1];
+            k[0] += add0; k[1] += add1;
+            dirty[0][1] = k[0]; dirty[1][1] = k[1];
+            past_zero = true;
+        } else {
+            for (size_t j = 0; j < add0; ++j) h1[k[0] + j] = buckets[b].first;
+            for (size_t j = 0; j < add1; ++j) h2[k[1] + j] = buckets[b].first;
+            k[0] += add0; k[1] += add1;
+        }
+        if (odd) parity = !parity;
+    }
+    if (!past_zero) { dirty[0][0] = k[0]; dirty[1][0] = k[1]; }
+    *n1 = k[0]; *n2 = k[1];
     return true;
 }
 
@@ -244,7 +266,10 @@ struct zkb_plonk_pk {
     DPoly poly[10];                              // q_m q_l q_r q_o q_c q_lookup q_table sigma1 sigma2 sigma3 (coefficients)
     uint64_t *sigma_evals[3] = {nullptr, nullptr, nullptr};
     uint64_t *epk[11] = {};                      // q_m q_l q_r q_o q_c q_lookup q_table sigma1 sigma2 sigma3 l_1 (4n cosets)
-    std::vector<Fe> q_lookup_host;               // evaluations, for f = q_lookup * c
+    std::vector<uint32_t> lookup_rows;           // rows with q_lookup != 0 (the lookup gates)
+    std::vector<Fe> lookup_q;                    // q_lookup on those rows, for f = q_lookup * c
+    size_t dirty_t = 0;                          // non-zero regions the previous proof left in the pinned staging
+    size_t dirty_h[2][2] = {{0, 0}, {0, 0}};
     std::vector<size_t> pi_pos;                  // sorted public-input rows
     Pt vk[10];                                   // q_m q_l q_r q_o q_c sigma1 sigma2 sigma3 q_lookup q_table (VerifierKey order)
     std::vector<void *> owned;                   // device allocations of the key
@@ -333,6 +358,16 @@ double now_ms() {
 
 extern "C" {
 
+// test hook (host only, no GPU): the prover's sparse combine_split on caller-owned persistent staging
+int zkb_test_combine_split(const uint64_t *table, size_t table_len, size_t n, const uint64_t *f, const uint32_t *rows, size_t n_rows,
+                           uint64_t *h1, uint64_t *h2, size_t dirty[4], size_t out_lens[2]) {
+    if ((!table && table_len) || !f || (!rows && n_rows) || !h1 || !h2 || !dirty || !out_lens) return ZKB_ERR_INVALID;
+    size_t d[2][2] = {{dirty[0], dirty[1]}, {dirty[2], dirty[3]}};
+    bool ok = combine_split_sparse((const Fe *)table, table_len, n, (const Fe *)f, rows, n_rows, (Fe *)h1, (Fe *)h2, d, &out_lens[0], &out_lens[1]);
+    dirty[0] = d[0][0]; dirty[1] = d[0][1]; dirty[2] = d[1][0]; dirty[3] = d[1][1];
+    return ok ? ZKB_OK : ZKB_ERR_INVALID;
+}
+
 void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
     if (!pk) return;
     if (ctx) cudaStreamSynchronize(ctx->stream);
@@ -378,8 +413,10 @@ int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selector
         if (cudaMemcpyAsync(pk->sigma_evals[k], sigma[k], n * 32, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
             return fail((ctx->err = "zkb_plonk_setup: H2D copy failed", ZKB_ERR_CUDA));
     }
-    pk->q_lookup_host.resize(n);
-    memcpy(pk->q_lookup_host.data(), selectors[5], n * 32);
+    for (size_t i = 0; i < n; ++i) {
+        const Fe q = fe_from(selectors[5] + 4 * i);
+        if (!host::is_zero(q)) { pk->lookup_rows.push_back((uint32_t)i); pk->lookup_q.push_back(q); }
+    }
     // verifier key commitments in VerifierKey order (setup.rs:104-121)
     const int vk_order[10] = {P_QM, P_QL, P_QR, P_QO, P_QC, P_S1, P_S2, P_S3, P_QLK, P_QT};
     const DPoly *cp[10];
@@ -407,6 +444,8 @@ int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selector
         return fail((ctx->err = "zkb_plonk_setup: cannot allocate the prover arena", ZKB_ERR_OOM));
     if (cudaMallocHost((void **)&pk->stage, 4 * n * sizeof(Fe)) != cudaSuccess)
         return fail((ctx->err = "zkb_plonk_setup: cannot allocate pinned staging", ZKB_ERR_OOM));
+    memset(pk->stage, 0, 4 * n * sizeof(Fe));                              // kept zero outside the regions a proof writes
+    pk->dirty_h[0][1] = pk->dirty_h[1][1] = n;
     if (cudaStreamCreateWithFlags(&pk->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&pk->lookup_uploaded, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&pk->wire_uploaded, cudaEventDisableTiming) != cudaSuccess)
@@ -468,18 +507,21 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     TAKE(ev_t, n); TAKE(ev_f, n); TAKE(ev_h1, n); TAKE(ev_h2, n);
     std::atomic<int> lookup_status{0};
     std::thread lookup_worker([&]() {
-        memset(t_vals, 0, n * sizeof(Fe));
+        zkb_plonk_pk *mpk = const_cast<zkb_plonk_pk *>(pk);               // staging bookkeeping of the key object
+        if (mpk->dirty_t > table_len) memset(t_vals + table_len, 0, (mpk->dirty_t - table_len) * sizeof(Fe));
         if (table_len) memcpy(t_vals, table, table_len * 32);           // LookupTable::into_multiset: entries then zeros
+        mpk->dirty_t = table_len;
         const Fe one = FR_ONE();
         const Fe *cv = (const Fe *)c;
-        for (size_t i = 0; i < n; ++i) {
-            const Fe &q = pk->q_lookup_host[i];
-            if (host::is_zero(q)) f_vals[i] = Fe{{0, 0, 0, 0}};
-            else if (feq(q, one)) f_vals[i] = cv[i];
-            else f_vals[i] = fmul(q, cv[i]);
+        const size_t n_rows = pk->lookup_rows.size();
+        for (size_t r = 0; r < n_rows; ++r) {                           // f is zero (and stays zero) outside the lookup gates
+            const size_t i = pk->lookup_rows[r];
+            const Fe &q = pk->lookup_q[r];
+            f_vals[i] = feq(q, one) ? cv[i] : fmul(q, cv[i]);
         }
         size_t n_h1 = 0, n_h2 = 0;
-        if (!combine_split(t_vals, n, f_vals, n, h1_vals, h2_vals, &n_h1, &n_h2)) { lookup_status.store(1); return; }
+        if (!combine_split_sparse((const Fe *)table, table_len, n, f_vals, pk->lookup_rows.data(), n_rows, h1_vals, h2_vals,
+                                  mpk->dirty_h, &n_h1, &n_h2)) { lookup_status.store(1); return; }
         if (n_h1 != n || n_h2 != n) { lookup_status.store(2); return; }
         cudaStream_t cs = pk->copy_stream;                                // pinned -> HBM while the main stream runs round 1
         if (cudaSetDevice(ctx->device) != cudaSuccess ||
