@@ -33,6 +33,7 @@
 #include "host_ff.h"
 
 #include <algorithm>
+#include <cmath>
 #include <array>
 #include <vector>
 
@@ -534,16 +535,22 @@ uint32_t balanced_windows(uint32_t c, uint32_t *wide) {
     return W;
 }
 
-// Cost in units of one bucket insertion (0.155 ns measured): n*W insertions plus a per-bucket charge for the weighted
-// bucket sums (measured ~1 ns per bucket on top of a fixed latency, less when the buckets split into W groups).
-uint32_t pick_window(size_t n, bool shared_buckets) {
+// Cost in units of one bucket insertion (0.155 ns measured): n*W insertions, stretched when the accumulation grid (one
+// thread per bucket) is only a few waves of the 148 x 3 x 128 resident threads (measured: x1.95 at 0.58 waves, x1.25
+// at 1.15, x1.0 from ~4 waves on), plus a per-bucket charge for the weighted bucket sums (~0.5 ns per bucket with the
+// index-digit recursion) and, beyond 2^19 buckets, for the counting sort's atomics (~0.45 ns per bucket).
+uint32_t pick_window(size_t n, bool shared_buckets, int sm_count) {
     uint32_t best_c = 8;
     double best = 1e300;
+    const double wave = (double)sm_count * 3 * 128;
     for (uint32_t c = 6; c <= 22; ++c) {
         uint32_t wide = 1, W = shared_buckets ? balanced_windows(c, &wide) : 254 / c + 1;
         if (shared_buckets && wide == 0) continue;               // equivalent to c - 1 with uniform windows
-        double groups = shared_buckets ? 1.0 : (double)W;
-        double cost = (double)n * W + (shared_buckets ? 3.0 : 4.0) * groups * (double)(1u << (c - 1));
+        const double buckets = (shared_buckets ? 1.0 : (double)W) * (double)(1u << (c - 1));
+        const double waves = buckets / wave;
+        const double stretch = waves >= 4.0 ? 1.0 : waves >= 1.0 ? 1.0 + 0.3 / waves : 1.15 / waves;
+        const double big = buckets > 524288.0 ? buckets - 524288.0 : 0.0;       // the sort's atomics stop being cache friendly
+        double cost = (double)n * W * stretch + 3.4 * buckets + 3.0 * big;
         if (cost < best) { best = cost; best_c = c; }
     }
     return best_c;
@@ -555,7 +562,7 @@ MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset, int
         pl.c = fb->c; pl.W = fb->W; pl.G = 1; pl.wide = fb->wide;
         pl.id_base = (uint32_t)offset; pl.id_stride = (uint32_t)fb->n;
     } else {
-        pl.c = force_c > 0 ? (uint32_t)force_c : pick_window(n, false);
+        pl.c = force_c > 0 ? (uint32_t)force_c : pick_window(n, false, sm_count);
         pl.W = 254 / pl.c + 1; pl.G = pl.W; pl.wide = pl.W;
         pl.id_base = 0; pl.id_stride = 0;
     }
@@ -822,7 +829,7 @@ int zkb_srs_precompute(zkb_ctx *ctx, int c) {
     const size_t n = ctx->srs_n;
     if (n == 0) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_srs_precompute: no SRS loaded");
     FixedBase *fb = new FixedBase();
-    fb->c = c > 0 ? (uint32_t)c : pick_window(n, true);
+    fb->c = c > 0 ? (uint32_t)c : pick_window(n, true, ctx->sm_count);
     fb->W = balanced_windows(fb->c, &fb->wide);
     if (fb->wide == 0 && fb->c > 3) { fb->c -= 1; fb->wide = fb->W; }   // every window narrow: that is just c - 1 (half the buckets)
     fb->n = n;
