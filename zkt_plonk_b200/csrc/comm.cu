@@ -99,6 +99,16 @@ int zkb_comm_allgather(zkb_ctx *ctx, const void *send_host, size_t bytes, void *
     return ZKB_OK;
 }
 
+// in place on the device: buf[r * bytes_per_rank ..] holds rank r's slice afterwards (this rank's slice must already be there)
+int zkb_comm_allgather_dev(zkb_ctx *ctx, void *buf_dev, size_t bytes_per_rank, cudaStream_t stream) {
+    if (ctx->world == 1) return ZKB_OK;
+    if (!ctx->comm) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_comm_allgather_dev: no communicator (zkb_comm_init)");
+    NcclApi *api = nccl_api();
+    ZKB_NCCL(ctx, api, api->AllGather((const char *)buf_dev + (size_t)ctx->rank * bytes_per_rank, buf_dev, bytes_per_rank, ncclUint8,
+                                      (ncclComm_t)ctx->comm, stream));
+    return ZKB_OK;
+}
+
 extern "C" {
 
 int zkb_comm_unique_id(uint8_t out[128]) {

@@ -94,6 +94,8 @@ void zkb_comm_release(zkb_ctx *ctx);
 void zkb_commit_abort(zkb_ctx *ctx);   // drain and drop an open zkb_commit_push batch (error recovery)
 // all ranks: recv_host[r * bytes ..] = rank r's send_host[0 .. bytes)  (NCCL all-gather on the context's stream; synchronous)
 int zkb_comm_allgather(zkb_ctx *ctx, const void *send_host, size_t bytes, void *recv_host);
+// the same in place on the device, enqueued on `stream` (no synchronisation)
+int zkb_comm_allgather_dev(zkb_ctx *ctx, void *buf_dev, size_t bytes_per_rank, cudaStream_t stream);
 // two-level power tables base^e = lo[e & (2^s - 1)] * hi[e >> s], e < 2^lm (Montgomery Fr); hi is pre-scaled by hi_scale
 int zkb_pow2lvl_cached(zkb_ctx *ctx, uint64_t key, unsigned lm, const zkb::host::Fe &base, const zkb::host::Fe &hi_scale,
                        const void **out, uint32_t *s_out);

@@ -559,8 +559,14 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     DPoly pa, pb, pc;
     {
         struct { const uint64_t *host; uint64_t *dev; DPoly *poly; } wires[3] = {{a, ev_a, &pa}, {b, ev_b, &pb}, {c, ev_c, &pc}};
+        // Several GPUs (SPMD): every rank needs the whole wire for its NTTs, but the ranks of one box share the host's
+        // memory bandwidth, so a rank uploads only its 1/world slice and the slices are all-gathered over NVLink.
+        const bool split = ctx->world > 1 && ctx->comm && n % (size_t)ctx->world == 0;
+        const size_t chunk = split ? n / (size_t)ctx->world : n, first = split ? (size_t)ctx->rank * chunk : 0;
         for (int k = 0; k < 3; ++k) {
-            ZKB_CUDA(ctx, cudaMemcpyAsync(wires[k].dev, wires[k].host, n * 32, cudaMemcpyHostToDevice, pk->copy_stream));
+            ZKB_CUDA(ctx, cudaMemcpyAsync(wires[k].dev + 4 * first, wires[k].host + 4 * first, chunk * 32, cudaMemcpyHostToDevice,
+                                          pk->copy_stream));
+            if (split) TRY(zkb_comm_allgather_dev(ctx, wires[k].dev, chunk * 32, pk->copy_stream));
             ZKB_CUDA(ctx, cudaEventRecord(pk->wire_uploaded, pk->copy_stream));
             ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->wire_uploaded, 0));
             if (k == 0) tick(0);
