@@ -214,7 +214,8 @@ ZKB_API int zkb_comm_allgather_host(zkb_ctx *ctx, const void *send_host, size_t 
 ZKB_API int zkb_srs_set_range(zkb_ctx *ctx, size_t global_lo, size_t global_n);
 
 /* ---- test hooks (parity of the device field library against the oracle) ----------------------------------------- */
-/* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a).  Host pointers. */
+/* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a), 7 = a * b * 2^-260 through the
+ * experimental FP64-pipe product (csrc/ff52.cuh).  Host pointers. */
 ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n);
 
 /* Host only (no GPU): the round driver's MultiSet::combine_split (multiset.rs:103-146) specialised to t = table entries
@@ -233,7 +234,9 @@ ZKB_API int zkb_msm_last_timing(zkb_ctx *ctx, float out_ms[5], uint64_t info[3])
 
 /* ---- measurement: integer-pipe peak (not in MEASURED_PEAKS.json; SURVEY.md 8d asks for it) ------------------------- */
 /* mode 0: 32-bit IMAD/s, mode 1: IMAD.WIDE.U32/s (the instruction the Montgomery product is made of),
- * mode 2: Fq Montgomery products/s in a dependency-chained loop, mode 3: FP64 FMA/s.  All 148 SMs, best of 3 timed launches. */
+ * mode 2: Fq Montgomery products/s in a dependency-chained loop, mode 3: FP64 FMA/s, mode 4: Fq products/s of the FP64-pipe
+ * product (ff52.cuh), mode 5: both products in alternating warps, modes 6-8: pipe-sharing probes (IMAD + DFMA, IMAD + ALU,
+ * DFMA + ALU in one thread; result = groups/s).  All 148 SMs, best of 3 timed launches. */
 ZKB_API int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec);
 
 #ifdef __cplusplus

@@ -1,6 +1,7 @@
 // api.cu -- extern "C" boundary of libzkb200.so (include/zkb200.h): context, memory, host-pointer wrappers.
 #include "ctx.h"
 #include "ff.cuh"
+#include "ff52.cuh"
 
 using namespace zkb;
 
@@ -18,6 +19,7 @@ __global__ void fp_binop_kernel(int op, uint4 *out, const uint4 *a, const uint4 
         case 3: r = fsqr<P>(x); break;
         case 4: r = finv<P>(x); break;
         case 5: r = fto_mont<P>(x); break;
+        case 7: r = fe_from_fe52(fmul52<P>(fe52_from_fe(x), fe52_from_fe(y))); break;   // a * b * 2^-260 on the FP64 pipe
         default: r = ffrom_mont<P>(x); break;
     }
     fstore(out + 2 * i, r);
@@ -66,6 +68,40 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, uint32_t i
 #pragma unroll
         for (int k = 0; k < 8; ++k) r += a[k];
         out[t] = (uint32_t)__double2ll_rn(r);
+    } else if (mode == 6 || mode == 7 || mode == 8) {            // pipe-sharing probes: IMAD + DFMA, IMAD + IADD3, DFMA + IADD3 in one thread
+        uint32_t a[4], m = t | 1u, c[4];
+        double d[4], md = 1.0 + 1e-9 * (double)(t & 15);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a[k] = t + k; c[k] = t * 3 + k; d[k] = (double)(t + k); }
+#define ZKB_PROBE_LOOP(BODY)                                  \
+        for (uint32_t i = 0; i < iters; ++i) {                \
+            _Pragma("unroll") for (int k = 0; k < 4; ++k) { BODY } \
+        }
+#define ZKB_I asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(m), "r"(a[(k + 1) & 3]));
+#define ZKB_D asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[k]) : "d"(md), "d"(d[(k + 1) & 3]));
+#define ZKB_A asm volatile("add.u32 %0, %0, %1;" : "+r"(c[k]) : "r"(c[(k + 1) & 3])); asm volatile("xor.b32 %0, %0, %1;" : "+r"(c[k]) : "r"(m));
+        if (mode == 6) { ZKB_PROBE_LOOP(ZKB_I ZKB_D) }
+        else if (mode == 7) { ZKB_PROBE_LOOP(ZKB_I ZKB_A) }
+        else { ZKB_PROBE_LOOP(ZKB_D ZKB_A) }
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r ^= a[k] ^ c[k] ^ (uint32_t)__double2ll_rn(d[k]);
+        out[t] = r;
+    } else if (mode == 4 || (mode == 5 && ((threadIdx.x >> 5) & 1))) {   // Montgomery products on the FP64 pipe (ff52.cuh)
+        fe52_t x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) x[k].v[j] = ((uint64_t)(t * 2654435761u + k * 40503u + j) * 0x9E3779B97F4A7C15ULL) & (MASK52 >> 8);
+        }
+        for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = fmul52<FqP>(x[k], x[(k + 1) & 3]);
+        }
+        uint64_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r ^= x[k].v[0] ^ x[k].v[4];
+        out[t] = (uint32_t)(r ^ (r >> 32));
     } else {
         fe_t x[4];
 #pragma unroll
@@ -223,8 +259,8 @@ int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint
 
 // ---------------------------------------------------------------------------------------------- microbenchmark
 int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec) {
-    if (!ctx || !ops_per_sec || mode < 0 || mode > 3) return ZKB_ERR_INVALID;
-    const uint32_t blocks = ctx->sm_count * 8, threads = 256, iters = mode == 2 ? 512 : 4096;
+    if (!ctx || !ops_per_sec || mode < 0 || mode > 8) return ZKB_ERR_INVALID;
+    const uint32_t blocks = ctx->sm_count * 8, threads = 256, iters = (mode == 2 || mode == 4 || mode == 5) ? 512 : 4096;
     int rc = zkb_reserve(ctx, ctx->stage, (size_t)blocks * threads * 4);
     if (rc) return rc;
     cudaEvent_t e0, e1;
@@ -242,7 +278,7 @@ int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec) {
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    double per_thread = (double)iters * (mode == 2 ? 4 : 8);
+    double per_thread = (double)iters * ((mode == 2 || mode == 4 || mode == 5) ? 4 : mode >= 6 ? 4 : 8);   // modes 6-8: per pair
     *ops_per_sec = per_thread * blocks * threads / (best * 1e-3);
     return ZKB_OK;
 }
