@@ -20,6 +20,10 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     std::string err;
 };
@@ -46,6 +50,10 @@ NcclApi *nccl_api() {
     api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
     api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
     api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.Send = (decltype(api.Send))sym("ncclSend");
+    api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     if (!ok) { dlclose(api.handle); api.handle = nullptr; }
     return &api;
@@ -106,6 +114,42 @@ int zkb_comm_allgather_dev(zkb_ctx *ctx, void *buf_dev, size_t bytes_per_rank, c
     NcclApi *api = nccl_api();
     ZKB_NCCL(ctx, api, api->AllGather((const char *)buf_dev + (size_t)ctx->rank * bytes_per_rank, buf_dev, bytes_per_rank, ncclUint8,
                                       (ncclComm_t)ctx->comm, stream));
+    return ZKB_OK;
+}
+
+// Round 4 of a sharded proof: the nine coset NTTs are spread over the ranks (array k is transformed by rank k % world),
+// every rank then needs only the slice of each result that its part of the quotient reads, plus a halo of 4 elements
+// for the "next row" accesses.  One grouped exchange: the owner of an array sends every other rank its slice.
+int zkb_comm_spread_slices(zkb_ctx *ctx, uint64_t *const bufs[], int count, size_t n_elems, size_t halo, cudaStream_t stream) {
+    if (ctx->world == 1) return ZKB_OK;
+    if (!ctx->comm) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_comm_spread_slices: no communicator (zkb_comm_init)");
+    const size_t world = (size_t)ctx->world, chunk = n_elems / world;
+    if (n_elems % world || halo > chunk) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_comm_spread_slices: the ranks must divide the array");
+    NcclApi *api = nccl_api();
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    ZKB_NCCL(ctx, api, api->GroupStart());
+    ncclResult_t bad = ncclSuccess;
+    auto note = [&](ncclResult_t r) { if (r != ncclSuccess && bad == ncclSuccess) bad = r; };
+    for (int k = 0; k < count; ++k) {
+        const int owner = k % ctx->world;
+        char *base = (char *)bufs[k];
+        for (size_t r = 0; r < world; ++r) {
+            if ((int)r == owner) continue;
+            const size_t lo = r * chunk, hlo = ((r + 1) * chunk) % n_elems;       // slice and (cyclic) halo of rank r
+            if (ctx->rank == owner) {
+                note(api->Send(base + lo * 32, chunk * 32, ncclUint8, (int)r, comm, stream));
+                if (halo) note(api->Send(base + hlo * 32, halo * 32, ncclUint8, (int)r, comm, stream));
+            } else if ((size_t)ctx->rank == r) {
+                note(api->Recv(base + lo * 32, chunk * 32, ncclUint8, owner, comm, stream));
+                if (halo) note(api->Recv(base + hlo * 32, halo * 32, ncclUint8, owner, comm, stream));
+            }
+        }
+    }
+    ncclResult_t end = api->GroupEnd();
+    if (bad != ncclSuccess || end != ncclSuccess) {
+        ctx->err = std::string("zkb_comm_spread_slices: ") + api->GetErrorString(bad != ncclSuccess ? bad : end);
+        return ZKB_ERR_CUDA;
+    }
     return ZKB_OK;
 }
 

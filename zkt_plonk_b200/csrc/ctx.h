@@ -87,6 +87,11 @@ inline int zkb_reserve(zkb_ctx *ctx, DevBuf &b, size_t bytes) {
     return ZKB_OK;
 }
 
+// Array k (n_elems field elements) is complete on rank k % world; afterwards every rank holds elements
+// [rank * chunk, (rank + 1) * chunk + halo) (cyclically, chunk = n_elems / world) of every array in its own buffer k.
+int zkb_comm_spread_slices(zkb_ctx *ctx, uint64_t *const bufs[], int count, size_t n_elems, size_t halo, cudaStream_t stream);
+extern "C" int zkb_quotient_evals_range_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t challenges[20], const uint64_t *const wit[9],
+                                            const uint64_t *const epk[11], uint64_t *out_dev, size_t lo, size_t hi);   // internal (hidden visibility)
 // implemented in ntt.cu / msm.cu / poly.cu
 int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int inverse, int coset);
 void zkb_msm_release(zkb_ctx *ctx);

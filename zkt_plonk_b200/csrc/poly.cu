@@ -254,13 +254,14 @@ struct QuotArgs {
     const uint4 *qm, *ql, *qr, *qo, *qc, *qlk, *qt, *s1, *s2, *s3, *l1;                // static epk cosets (4n)
     const uint4 *xtab;                                                                 // two-level table of w_4n
     uint32_t xtab_s, n4;
+    uint32_t i_lo, i_hi;                                                               // elements [i_lo, i_hi) of the coset (a slice when several GPUs share the round)
     fe_t alpha, alpha2, alpha3, alpha4, alpha5, beta, gamma, delta, eps, opd, eopd, gen, k1, k2;
     fe_t zh_inv[4];                                                                    // 1 / zh on the coset, by i mod 4
 };
 
 __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotArgs p, uint4 *out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n4) return;
+    uint32_t i = p.i_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.i_hi) return;
     uint32_t j = i + 4 < p.n4 ? i + 4 : i + 4 - p.n4;           // "next": x * w_n  (quotient_poly.rs:53-94)
     const size_t I = 2 * (size_t)i, J = 2 * (size_t)j;
     fe_t a = fload_ro(p.a + I), b = fload_ro(p.b + I), c = fload_ro(p.c + I);
@@ -504,6 +505,13 @@ int zkb_grand_product_failed(zkb_ctx *ctx) {
 
 int zkb_quotient_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t challenges[20], const uint64_t *const wit[9],
                            const uint64_t *const epk[11], uint64_t *out_dev) {
+    return zkb_quotient_evals_range_dev(ctx, log_n, challenges, wit, epk, out_dev, 0, (size_t)4 << log_n);
+}
+
+// elements [lo, hi) only: the inputs must be valid on [lo, hi + 4) (cyclically) -- the slice a rank evaluates when the
+// ranks of a box share round 4
+int zkb_quotient_evals_range_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t challenges[20], const uint64_t *const wit[9],
+                                 const uint64_t *const epk[11], uint64_t *out_dev, size_t lo, size_t hi) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!challenges || !wit || !epk || !out_dev) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_quotient_evals_dev: null argument");
     if (log_n + 2 > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_quotient_evals_dev: 4n exceeds 2^28 (InvalidEvalDomainSize)");
@@ -517,6 +525,8 @@ int zkb_quotient_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t challeng
     const uint4 **ep[11] = {&p.qm, &p.ql, &p.qr, &p.qo, &p.qc, &p.qlk, &p.qt, &p.s1, &p.s2, &p.s3, &p.l1};
     for (int k = 0; k < 11; ++k) *ep[k] = (const uint4 *)epk[k];
     p.n4 = (uint32_t)n4;
+    if (lo > hi || hi > n4) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_quotient_evals_range_dev: bad element range");
+    p.i_lo = (uint32_t)lo; p.i_hi = (uint32_t)hi;
     using namespace host;
     Fe al = host_fe(challenges), be = host_fe(challenges + 4), ga = host_fe(challenges + 8), de = host_fe(challenges + 12),
        ep_ = host_fe(challenges + 16);
@@ -535,7 +545,7 @@ int zkb_quotient_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t challeng
     int rc = zkb_pow2lvl_cached(ctx, (2ull << 32) | ((log_n + 2) << 1), log_n + 2, fr_root_of_unity(log_n + 2), one(FR), &tab, &p.xtab_s);
     if (rc) return rc;
     p.xtab = (const uint4 *)tab;
-    quotient_kernel<<<(unsigned)((n4 + 127) / 128), 128, 0, ctx->stream>>>(p, (uint4 *)out_dev);
+    if (hi > lo) quotient_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, ctx->stream>>>(p, (uint4 *)out_dev);
     ctx->launches += 1;
     ZKB_CUDA(ctx, cudaGetLastError());
     return ZKB_OK;

@@ -657,20 +657,35 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     uint64_t *q_buf;
     {
         const DPoly *wit_p[9] = {&pz1, &pz2, &pa, &pb, &pc, &ppi, &pt, &ph1, &ph2};
+        uint64_t *wit_w[9];
         const uint64_t *wit[9];
+        // Several GPUs (SPMD): the nine coset NTTs are independent, so rank k % world transforms polynomial k, every
+        // rank receives the slice (+ 4 halo elements for the "next row" reads) its part of the quotient needs, evaluates
+        // that part, and the quotient slices are all-gathered before the (replicated) coset iNTT.
+        const size_t world = (size_t)ctx->world;
+        const bool fan = world > 1 && ctx->comm && n4 % world == 0 && n4 / world >= 4;
         for (int k = 0; k < 9; ++k) {
             uint64_t *d;
             TAKE(d, n4);
+            wit_w[k] = d;
+            wit[k] = d;
+            if (fan && (size_t)k % world != (size_t)ctx->rank) continue;
             ZKB_CUDA(ctx, cudaMemsetAsync(d, 0, n4 * 32, s));
             ZKB_CUDA(ctx, cudaMemcpyAsync(d, wit_p[k]->d, wit_p[k]->len * 32, cudaMemcpyDeviceToDevice, s));
             TRY(zkb_ntt_dev(ctx, d, wit_p[k]->len, log_n + 2, 0, 1));
-            wit[k] = d;
         }
         uint64_t ch[20];
         const Fe *cs[5] = {&alpha, &beta, &gamma, &delta, &epsilon};
         for (int k = 0; k < 5; ++k) memcpy(ch + 4 * k, cs[k]->l, 32);
         TAKE(q_buf, n4);
-        TRY(zkb_quotient_evals_dev(ctx, log_n, ch, wit, (const uint64_t *const *)pk->epk, q_buf));
+        if (fan) {
+            const size_t chunk = n4 / world, lo = (size_t)ctx->rank * chunk;
+            TRY(zkb_comm_spread_slices(ctx, wit_w, 9, n4, 4, s));
+            TRY(zkb_quotient_evals_range_dev(ctx, log_n, ch, wit, (const uint64_t *const *)pk->epk, q_buf, lo, lo + chunk));
+            TRY(zkb_comm_allgather_dev(ctx, q_buf, chunk * 32, s));
+        } else {
+            TRY(zkb_quotient_evals_dev(ctx, log_n, ch, wit, (const uint64_t *const *)pk->epk, q_buf));
+        }
         TRY(zkb_ntt_dev(ctx, q_buf, n4, log_n + 2, 1, 1));
     }
     size_t q_len = 0;
