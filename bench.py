@@ -12,9 +12,13 @@ value      : device-timed (CUDA events on the launching stream) throughput, scal
 e2e        : same call through the host-pointer C-ABI entry (zkb_msm_g1): pinned host scalars -> H2D -> MSM ->
              affine point back on the host, wall clock around the synchronous call.
 roofline   : bucket-accumulation kernel (msm_accumulate_kernel) against the integer pipe measured live
-             (zkb_bench_int), plus the NTT against the HBM copy peak of MEASURED_PEAKS.json in "extra".
+             (zkb_bench_int), traffic from the committed ncu capture (profiles/ncu_traffic.json), plus the NTT
+             against the HBM copy peak of MEASURED_PEAKS.json in "extra".
+extra      : coset NTT 2^22; the full proof through zkb_plonk_prove (host wires in, 802 proof bytes out) for synthetic
+             circuits of 2^18 (withdraw-circuit size) and 2^20 gates.
 N > 1      : weak scaling -- every rank owns a resident range of 2^20 SRS points and its scalar slice of one
-             N*2^20-point MSM; the 128-byte XYZZ partial sums are all-gathered over NCCL and added.
+             N*2^20-point MSM; the 128-byte XYZZ partial sums are all-gathered over NCCL and added.  extra: the 2^20-gate
+             proof run SPMD on the N GPUs (commitments sharded by point range, round 4 fanned out).
 """
 import argparse
 import json
@@ -217,13 +221,14 @@ def run_main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi samples every 100 ms: start it before the warm-up so that it is settled when the (short) timed region
+    # begins; it keeps sampling through the timed steps and the e2e loop, all of them under load
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     int_peak = ctx.bench_int(0)                                     # 32-bit IMAD/s, all SMs
     for w in range(args.warmup):
         step(dev_sets[w % NSETS])
     barrier()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     # ---- timed region: K steps, each bracketed by events; L2 flushed (untimed) between steps
     l0 = ctx.launch_count()
     step_ms, acc_ms, tot_ms = [], [], []

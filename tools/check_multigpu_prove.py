@@ -60,9 +60,11 @@ for _ in range(args.reps):
 digest = np.frombuffer(hashlib.sha256(raw).digest(), dtype=np.uint8)
 alld = ctx.comm_allgather(digest)
 assert all(np.array_equal(alld[r], digest) for r in range(world)), "ranks disagree on the proof bytes"
+_, rounds = native.prove_bytes(blinders, timings=True)
 tmax = torch.tensor([min(times)], device="cuda"); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
 if rank == 0:
-    res = {"world": world, "log_n": args.log_n, "range": [lo, hi], "prove_ms_sharded": float(tmax.item()), "ranks_agree": True}
+    res = {"world": world, "log_n": args.log_n, "range": [lo, hi], "prove_ms_sharded": float(tmax.item()), "ranks_agree": True,
+           "rounds_ms_rank0_with_syncs": {k: round(v, 3) for k, v in rounds.items()}}
     ref_ctx = z.Context(local); ref_ctx.set_stream(torch.cuda.current_stream())
     ref_ctx.srs_load(srs_range(ref_ctx, 0, n + 8)); ref_ctx.srs_precompute(0)
     ref = prover.NativeProver(ref_ctx, circ)

@@ -23,3 +23,15 @@ for mode, name in ((0, "IMAD/s"), (3, "DFMA/s"), (2, "Fq products/s, integer pip
     print(f"{name}: {ctx.bench_int(mode):.4e}", flush=True)
 for mode, name in ((6, "pairs/s of (IMAD + DFMA) in one thread"), (7, "groups/s of (IMAD + ADD + XOR)"), (8, "groups/s of (DFMA + ADD + XOR)")):
     print(f"{name}: {ctx.bench_int(mode):.4e}", flush=True)
+for field, F in ((1, cref.FQ), (0, cref.FR)):
+    n = 50000
+    a = cref.to_mont(F, cref.rand_fe(F, n, 31)); b = cref.to_mont(F, cref.rand_fe(F, n, 32))
+    pm1 = cref.normalize(F, np.full((1, 4), 0xFFFFFFFFFFFFFFFF, dtype=np.uint64))
+    a[0] = pm1[0]; b[0] = pm1[0]; a[1] = 0; b[2] = 0; a[3] = pm1[0]; b[3, :] = 0; b[3, 0] = 1
+    a[4] = np.array([0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0, 0], dtype=np.uint64); b[4] = a[4]
+    a[5] = np.array([0, 0, 0xFFFFFFFFFFFFFFFF, 0x0FFFFFFFFFFFFFFF], dtype=np.uint64); b[5] = a[4]
+    same = np.array_equal(ctx.fp_binop(field, 8, a, b), ctx.fp_binop(field, 0, a, b))
+    print("field", field, "Karatsuba product == CIOS product:", same, flush=True)
+    assert same
+print(f"Fq products/s, Karatsuba (ff_kara.cuh): {ctx.bench_int(9):.4e}", flush=True)
+print(f"Fq products/s, CIOS (ff.cuh): {ctx.bench_int(2):.4e}", flush=True)

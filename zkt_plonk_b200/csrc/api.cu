@@ -2,6 +2,7 @@
 #include "ctx.h"
 #include "ff.cuh"
 #include "ff52.cuh"
+#include "ff_kara.cuh"
 
 using namespace zkb;
 
@@ -19,6 +20,7 @@ __global__ void fp_binop_kernel(int op, uint4 *out, const uint4 *a, const uint4 
         case 3: r = fsqr<P>(x); break;
         case 4: r = finv<P>(x); break;
         case 5: r = fto_mont<P>(x); break;
+        case 8: r = fmul_kara<P>(x, y); break;                                            // must equal op 0
         case 7: r = fe_from_fe52(fmul52<P>(fe52_from_fe(x), fe52_from_fe(y))); break;   // a * b * 2^-260 on the FP64 pipe
         default: r = ffrom_mont<P>(x); break;
     }
@@ -102,6 +104,21 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, uint32_t i
 #pragma unroll
         for (int k = 0; k < 4; ++k) r ^= x[k].v[0] ^ x[k].v[4];
         out[t] = (uint32_t)(r ^ (r >> 32));
+    } else if (mode == 9) {                                       // Karatsuba product chain (ff_kara.cuh)
+        fe_t x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[k].v[j] = (t * 2654435761u + k * 40503u + j) & 0x0fffffffu;
+        }
+        for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = fmul_kara<FqP>(x[k], x[(k + 1) & 3]);
+        }
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r ^= x[k].v[0] ^ x[k].v[7];
+        out[t] = r;
     } else {
         fe_t x[4];
 #pragma unroll
@@ -259,8 +276,8 @@ int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint
 
 // ---------------------------------------------------------------------------------------------- microbenchmark
 int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec) {
-    if (!ctx || !ops_per_sec || mode < 0 || mode > 8) return ZKB_ERR_INVALID;
-    const uint32_t blocks = ctx->sm_count * 8, threads = 256, iters = (mode == 2 || mode == 4 || mode == 5) ? 512 : 4096;
+    if (!ctx || !ops_per_sec || mode < 0 || mode > 9) return ZKB_ERR_INVALID;
+    const uint32_t blocks = ctx->sm_count * 8, threads = 256, iters = (mode == 2 || mode == 4 || mode == 5 || mode == 9) ? 512 : 4096;
     int rc = zkb_reserve(ctx, ctx->stage, (size_t)blocks * threads * 4);
     if (rc) return rc;
     cudaEvent_t e0, e1;
@@ -278,7 +295,7 @@ int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec) {
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    double per_thread = (double)iters * ((mode == 2 || mode == 4 || mode == 5) ? 4 : mode >= 6 ? 4 : 8);   // modes 6-8: per pair
+    double per_thread = (double)iters * ((mode == 2 || mode == 4 || mode == 5 || mode == 9) ? 4 : mode >= 6 ? 4 : 8);   // modes 6-8: per pair
     *ops_per_sec = per_thread * blocks * threads / (best * 1e-3);
     return ZKB_OK;
 }
