@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import cref
-from tests.util import gen_xy, gpu_points, skewed_scalars, to_dev, to_host
+from tests.util import gen_xy, gpu_points, rand_fr_mont, skewed_scalars, to_dev, to_host
 
 pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "vectors.npz"))
@@ -182,4 +182,40 @@ def test_msm_2_20_vs_oracle(ctx):
     for s, (exp, einf) in cases:
         got, inf = ctx.msm(s)
         assert inf == einf and np.array_equal(got, exp)
+    ctx.srs_precompute(-1)
+
+
+def test_commit_push_finish_matches_batch(ctx):
+    """zkb_commit_push / zkb_commit_finish (the incremental form of zkb_commit_batch_dev the round driver uses to
+    overlap uploads with commitments): same commitments as the batch call and as the oracle, for more pushes than
+    there are workspaces, an empty polynomial, an offset, with other work enqueued between pushes; an open batch
+    blocks the batch entry point until it is finished."""
+    import torch
+    from zkt_plonk_b200._lib import ZkbError
+    n = 3000
+    d_pts, h_pts = gpu_points(ctx, n, 61)
+    ctx.srs_load(d_pts)
+    ctx.srs_precompute(0)
+    polys = [rand_fr_mont(m, 70 + k) for k, m in enumerate((n, 1, 777, n - 5, 2048))]
+    devs = [to_dev(p) for p in polys]
+    lens = [p.shape[0] for p in polys]
+    offs = [0, 5, 100, 0, 952]
+    want = ctx.commit_batch_dev(devs, lens, offs)
+    for k in range(len(polys)):
+        ctx.commit_push(devs[k], lens[k], offs[k])
+        if k == 1:
+            ctx.commit_push(devs[0], 0, 0)                      # empty polynomial: the identity
+        junk = torch.zeros(1 << 16, dtype=torch.int64, device="cuda") + k   # unrelated work between pushes
+    with pytest.raises(ZkbError):
+        ctx.commit_batch_dev(devs[:1], lens[:1])                # a push batch is open
+    got = ctx.commit_finish(len(polys) + 1)
+    empty = got.pop(2)
+    assert empty[1] and not empty[0].any()
+    for k in range(len(polys)):
+        assert got[k][1] == want[k][1] and np.array_equal(got[k][0], want[k][0])
+        exp, einf = cref.msm_g1(h_pts[offs[k]:offs[k] + lens[k]], cref.from_mont(cref.FR, polys[k]))
+        assert got[k][1] == einf and np.array_equal(got[k][0], exp)
+    assert ctx.commit_finish(0) == []
+    again = ctx.commit_batch_dev(devs, lens, offs)              # and the batch entry point works again
+    assert all(np.array_equal(a[0], b[0]) for a, b in zip(again, want))
     ctx.srs_precompute(-1)

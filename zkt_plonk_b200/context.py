@@ -182,6 +182,17 @@ class Context:
         """The resident SRS is [global_lo, global_lo + resident) of a key of global_n powers (commitments shard)."""
         self._check(self._lib.zkb_srs_set_range(self._h, int(global_lo), int(global_n)))
 
+    def commit_push(self, coeffs_dev, length, offset=0):
+        """Enqueue the MSM of one more HBM-resident polynomial of the open batch (returns at once)."""
+        self._check(self._lib.zkb_commit_push(self._h, _dev_ptr(coeffs_dev), offset, length))
+
+    def commit_finish(self, count):
+        """Wait for the open batch of `count` pushed polynomials; [((8,) affine, is_inf), ...] in push order."""
+        out = np.zeros((max(count, 1), 8), dtype=np.uint64)
+        inf = (ctypes.c_int * max(count, 1))()
+        self._check(self._lib.zkb_commit_finish(self._h, _host_ptr(out), inf))
+        return [(out[j].copy(), bool(inf[j])) for j in range(count)]
+
     def set_msm_window(self, c):
         self._check(self._lib.zkb_msm_set_window(self._h, int(c)))
 
