@@ -187,7 +187,7 @@ struct KeyEq { bool operator()(const Fe &a, const Fe &b) const { return feq(a, b
 // zero bucket (~2n elements) is counted arithmetically and its halves are never written, because the staging
 // columns are kept zero outside the small regions recorded in `dirty` (cleared before the next proof writes).
 // h1 / h2 come out as [prefix | zeros | suffix]; dirty[h][0] = end of the prefix, dirty[h][1] = start of the suffix.
-bool combine_split_sparse(const Fe *table, size_t table_len, size_t n, const Fe *f, const uint32_t *rows, size_t n_rows,
+bool combine_split_sparse(const Fe *table, size_t table_len, size_t n, const Fe *f_rows /* f on the lookup rows */, size_t n_rows,
                           Fe *h1, Fe *h2, size_t dirty[2][2], size_t *n1, size_t *n2) {
     std::vector<std::pair<Fe, size_t>> buckets;
     std::unordered_map<Fe, size_t, KeyHash, KeyEq> index;
@@ -210,7 +210,7 @@ bool combine_split_sparse(const Fe *table, size_t table_len, size_t n, const Fe 
     }
     size_t f_zeros = n - n_rows;                                   // rows without a lookup gate
     for (size_t r = 0; r < n_rows; ++r) {
-        const Fe &e = f[rows[r]];
+        const Fe &e = f_rows[r];
         if (host::is_zero(e)) { ++f_zeros; continue; }
         auto it = index.find(e);
         if (it == index.end()) return false;
@@ -268,13 +268,17 @@ struct zkb_plonk_pk {
     uint64_t *epk[11] = {};                      // q_m q_l q_r q_o q_c q_lookup q_table sigma1 sigma2 sigma3 l_1 (4n cosets)
     std::vector<uint32_t> lookup_rows;           // rows with q_lookup != 0 (the lookup gates)
     std::vector<Fe> lookup_q;                    // q_lookup on those rows, for f = q_lookup * c
+    uint32_t *d_lookup_rows = nullptr;           // the same rows in HBM (f is scattered there from its compact upload)
+    uint64_t *d_lookup_vals = nullptr;
     size_t dirty_t = 0;                          // non-zero regions the previous proof left in the pinned staging
     size_t dirty_h[2][2] = {{0, 0}, {0, 0}};
     std::vector<size_t> pi_pos;                  // sorted public-input rows
     Pt vk[10];                                   // q_m q_l q_r q_o q_c sigma1 sigma2 sigma3 q_lookup q_table (VerifierKey order)
     std::vector<void *> owned;                   // device allocations of the key
     Fe *stage = nullptr;                         // pinned host staging: t, f, h1, h2 (4 x n elements)
-    cudaStream_t copy_stream = nullptr;          // uploads of the lookup multisets (issued by the worker thread)
+    cudaStream_t copy_stream = nullptr;          // wire uploads (+ their all-gather on several GPUs), issued by the proving thread
+    cudaStream_t lookup_stream = nullptr;        // uploads of the lookup multisets, issued by the worker thread: a stream of
+                                                 // their own, so that 4n pinned elements never queue in front of a wire
     cudaEvent_t lookup_uploaded = nullptr, wire_uploaded = nullptr;
     char *arena = nullptr;                       // per-proof scratch: reset at the start of every prove
     size_t arena_bytes = 0, arena_off = 0;
@@ -338,6 +342,13 @@ __global__ void scatter_fe_kernel(uint4 *dst, const unsigned long long *pos, con
     dst[2 * pos[k] + 1] = vals[2 * k + 1];
 }
 
+__global__ void scatter_fe_rows_kernel(uint4 *dst, const uint32_t *rows, const uint4 *vals, size_t count) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    dst[2 * (size_t)rows[k]] = vals[2 * k];
+    dst[2 * (size_t)rows[k] + 1] = vals[2 * k + 1];
+}
+
 int commit_finish_pts(zkb_ctx *ctx, size_t count, Pt *out) {
     std::vector<uint64_t> xy(8 * count);
     std::vector<int> inf(count);
@@ -363,7 +374,12 @@ int zkb_test_combine_split(const uint64_t *table, size_t table_len, size_t n, co
                            uint64_t *h1, uint64_t *h2, size_t dirty[4], size_t out_lens[2]) {
     if ((!table && table_len) || !f || (!rows && n_rows) || !h1 || !h2 || !dirty || !out_lens) return ZKB_ERR_INVALID;
     size_t d[2][2] = {{dirty[0], dirty[1]}, {dirty[2], dirty[3]}};
-    bool ok = combine_split_sparse((const Fe *)table, table_len, n, (const Fe *)f, rows, n_rows, (Fe *)h1, (Fe *)h2, d, &out_lens[0], &out_lens[1]);
+    std::vector<Fe> f_rows(n_rows);
+    for (size_t r = 0; r < n_rows; ++r) {
+        if (rows[r] >= n) return ZKB_ERR_INVALID;
+        f_rows[r] = fe_from(f + 4 * (size_t)rows[r]);
+    }
+    bool ok = combine_split_sparse((const Fe *)table, table_len, n, f_rows.data(), n_rows, (Fe *)h1, (Fe *)h2, d, &out_lens[0], &out_lens[1]);
     dirty[0] = d[0][0]; dirty[1] = d[0][1]; dirty[2] = d[1][0]; dirty[3] = d[1][1];
     return ok ? ZKB_OK : ZKB_ERR_INVALID;
 }
@@ -375,6 +391,7 @@ void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
     if (pk->arena) cudaFree(pk->arena);
     if (pk->stage) cudaFreeHost(pk->stage);
     if (pk->copy_stream) cudaStreamDestroy(pk->copy_stream);
+    if (pk->lookup_stream) cudaStreamDestroy(pk->lookup_stream);
     if (pk->lookup_uploaded) cudaEventDestroy(pk->lookup_uploaded);
     if (pk->wire_uploaded) cudaEventDestroy(pk->wire_uploaded);
     delete pk;
@@ -417,6 +434,18 @@ int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selector
         const Fe q = fe_from(selectors[5] + 4 * i);
         if (!host::is_zero(q)) { pk->lookup_rows.push_back((uint32_t)i); pk->lookup_q.push_back(q); }
     }
+    {
+        uint64_t *rows_dev, *vals_dev;
+        const size_t n_rows = pk->lookup_rows.size();
+        int rc = dev_alloc_owned(ctx, pk, n_rows * 4 + 32, &rows_dev);
+        if (rc) return fail(rc);
+        rc = dev_alloc_owned(ctx, pk, n_rows * 32 + 32, &vals_dev);
+        if (rc) return fail(rc);
+        pk->d_lookup_rows = (uint32_t *)rows_dev;
+        pk->d_lookup_vals = vals_dev;
+        if (n_rows && cudaMemcpy(pk->d_lookup_rows, pk->lookup_rows.data(), n_rows * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail((ctx->err = "zkb_plonk_setup: H2D copy failed", ZKB_ERR_CUDA));
+    }
     // verifier key commitments in VerifierKey order (setup.rs:104-121)
     const int vk_order[10] = {P_QM, P_QL, P_QR, P_QO, P_QC, P_S1, P_S2, P_S3, P_QLK, P_QT};
     const DPoly *cp[10];
@@ -447,6 +476,7 @@ int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selector
     memset(pk->stage, 0, 4 * n * sizeof(Fe));                              // kept zero outside the regions a proof writes
     pk->dirty_h[0][1] = pk->dirty_h[1][1] = n;
     if (cudaStreamCreateWithFlags(&pk->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&pk->lookup_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&pk->lookup_uploaded, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&pk->wire_uploaded, cudaEventDisableTiming) != cudaSuccess)
         return fail((ctx->err = "zkb_plonk_setup: cannot create the copy stream", ZKB_ERR_CUDA));
@@ -514,23 +544,38 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
         const Fe one = FR_ONE();
         const Fe *cv = (const Fe *)c;
         const size_t n_rows = pk->lookup_rows.size();
-        for (size_t r = 0; r < n_rows; ++r) {                           // f is zero (and stays zero) outside the lookup gates
+        for (size_t r = 0; r < n_rows; ++r) {                           // f is zero outside the lookup gates: kept as a compact list
             const size_t i = pk->lookup_rows[r];
             const Fe &q = pk->lookup_q[r];
-            f_vals[i] = feq(q, one) ? cv[i] : fmul(q, cv[i]);
+            f_vals[r] = feq(q, one) ? cv[i] : fmul(q, cv[i]);
         }
         size_t n_h1 = 0, n_h2 = 0;
-        if (!combine_split_sparse((const Fe *)table, table_len, n, f_vals, pk->lookup_rows.data(), n_rows, h1_vals, h2_vals,
-                                  mpk->dirty_h, &n_h1, &n_h2)) { lookup_status.store(1); return; }
+        if (!combine_split_sparse((const Fe *)table, table_len, n, f_vals, n_rows, h1_vals, h2_vals, mpk->dirty_h, &n_h1, &n_h2)) {
+            lookup_status.store(1);
+            return;
+        }
         if (n_h1 != n || n_h2 != n) { lookup_status.store(2); return; }
-        cudaStream_t cs = pk->copy_stream;                                // pinned -> HBM while the main stream runs round 1
-        if (cudaSetDevice(ctx->device) != cudaSuccess ||
-            cudaMemcpyAsync(ev_t, t_vals, n * 32, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
-            cudaMemcpyAsync(ev_f, f_vals, n * 32, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
-            cudaMemcpyAsync(ev_h1, h1_vals, n * 32, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
-            cudaMemcpyAsync(ev_h2, h2_vals, n * 32, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
-            cudaEventRecord(pk->lookup_uploaded, cs) != cudaSuccess)
-            lookup_status.store(3);
+        // pinned -> HBM while the main stream runs round 1.  The four columns are zero almost everywhere, so they are
+        // cleared in HBM and only their non-zero regions cross PCIe (t: the table; h1, h2: prefix and suffix around
+        // the zero bucket; f: the compact list, scattered to the lookup rows by a kernel)
+        cudaStream_t cs = pk->lookup_stream;
+        bool ok = cudaSetDevice(ctx->device) == cudaSuccess;
+        auto clear = [&](uint64_t *d) { ok = ok && cudaMemsetAsync(d, 0, n * 32, cs) == cudaSuccess; };
+        auto put = [&](uint64_t *d, const Fe *h, size_t lo, size_t hi) {
+            if (hi > lo) ok = ok && cudaMemcpyAsync(d + 4 * lo, h + lo, (hi - lo) * 32, cudaMemcpyHostToDevice, cs) == cudaSuccess;
+        };
+        clear(ev_t); clear(ev_f); clear(ev_h1); clear(ev_h2);
+        put(ev_t, t_vals, 0, table_len);
+        put(ev_h1, h1_vals, 0, mpk->dirty_h[0][0]); put(ev_h1, h1_vals, mpk->dirty_h[0][1], n);
+        put(ev_h2, h2_vals, 0, mpk->dirty_h[1][0]); put(ev_h2, h2_vals, mpk->dirty_h[1][1], n);
+        if (n_rows) {
+            ok = ok && cudaMemcpyAsync(pk->d_lookup_vals, f_vals, n_rows * 32, cudaMemcpyHostToDevice, cs) == cudaSuccess;
+            if (ok) scatter_fe_rows_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, cs>>>((uint4 *)ev_f, pk->d_lookup_rows,
+                                                                                          (const uint4 *)pk->d_lookup_vals, n_rows);
+            ok = ok && cudaGetLastError() == cudaSuccess;
+        }
+        ok = ok && cudaEventRecord(pk->lookup_uploaded, cs) == cudaSuccess;
+        if (!ok) lookup_status.store(3);
     });
     struct Joiner {                                                     // never leave the scope with a joinable thread
         std::thread &t;
