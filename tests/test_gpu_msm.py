@@ -219,3 +219,22 @@ def test_commit_push_finish_matches_batch(ctx):
     again = ctx.commit_batch_dev(devs, lens, offs)              # and the batch entry point works again
     assert all(np.array_equal(a[0], b[0]) for a, b in zip(again, want))
     ctx.srs_precompute(-1)
+
+
+@pytest.mark.parametrize("tables", [False, True])
+def test_host_scalar_msm_two_halves(ctx, tables):
+    """zkb_msm_g1 with host scalars splits large MSMs into two point-range halves (the second half uploads while the
+    first is accumulated): same point as the device-scalar entry and as the oracle, with an offset into the SRS."""
+    n, off = (1 << 18) + 3, 5
+    d_pts, h_pts = gpu_points(ctx, n + off, 81)
+    ctx.srs_load(d_pts)
+    if tables:
+        ctx.srs_precompute(0)
+    s = cref.rand_fe(cref.FR, n, 82)
+    s[:1000] = 0
+    got, inf = ctx.msm(s, offset=off)
+    want, winf = ctx.msm(to_dev(s), offset=off, n=n)
+    assert inf == winf and np.array_equal(got, want)
+    exp, einf = cref.msm_g1(h_pts[off:], s)
+    assert inf == einf and np.array_equal(got, exp)
+    ctx.srs_precompute(-1)

@@ -82,6 +82,8 @@ struct MsmSlot {                         // one MSM in flight: its own workspace
 struct MsmState {
     MsmSlot slot[2];                     // slot 0: single MSMs; slots 0/1 alternate in pipelined batches
     cudaStream_t tail_stream = nullptr;  // high-priority stream for the latency-bound tail of a pipelined MSM
+    cudaStream_t copy_stream = nullptr;  // uploads of host scalars, overlapped with the MSM of the previous part
+    cudaEvent_t part_uploaded[2] = {nullptr, nullptr};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase boundaries of the last MSM
     bool ev_valid = false;
     uint64_t last_entries = 0;           // n * W upper bound of bucket insertions of the last MSM
@@ -759,6 +761,8 @@ void zkb_msm_release(zkb_ctx *ctx) {
         if (sl.tail_done) cudaEventDestroy(sl.tail_done);
     }
     if (st->tail_stream) cudaStreamDestroy(st->tail_stream);
+    if (st->copy_stream) cudaStreamDestroy(st->copy_stream);
+    for (cudaEvent_t e : st->part_uploaded) if (e) cudaEventDestroy(e);
     for (int k = 0; k < 5; ++k) if (st->ev[k]) cudaEventDestroy(st->ev[k]);
     if (st->fixed_base) {
         FixedBase *fb = (FixedBase *)st->fixed_base;
@@ -882,13 +886,48 @@ int zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, siz
     return ZKB_OK;
 }
 
+// Host scalars.  From 2^18 points on the MSM runs as two point-range halves through the two pipelined workspaces: the
+// second half of the scalars crosses PCIe (copy stream) while the first half is sorted and accumulated, and the first
+// half's window reduction overlaps the second half's accumulation; the two partial sums are added on the host.
 int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
     if (!scalars_host && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1: null scalars");
+    if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_msm: offset + n exceeds the loaded SRS");
     int rc = zkb_reserve(ctx, ctx->stage, n * 32 + 32);
     if (rc) return rc;
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    return zkb_msm_g1_dev(ctx, (const uint64_t *)ctx->stage.p, offset, n, out_xy, is_inf);
+    MsmState *st = state(ctx);
+    if (n < ((size_t)1 << 18) || !st->pipe_partial.empty()) {
+        ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        return zkb_msm_g1_dev(ctx, (const uint64_t *)ctx->stage.p, offset, n, out_xy, is_inf);
+    }
+    if (!st->copy_stream) {
+        ZKB_CUDA(ctx, cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : st->part_uploaded) ZKB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const FixedBase *fb = (const FixedBase *)st->fixed_base;
+    if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;
+    // the staging buffer may still be read by work enqueued earlier on the main stream: the copies wait for it
+    ZKB_CUDA(ctx, cudaEventRecord(st->part_uploaded[0], ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamWaitEvent(st->copy_stream, st->part_uploaded[0], 0));
+    const size_t part_n[2] = {n / 2, n - n / 2}, part_lo[2] = {0, n / 2};
+    MsmPlan plans[2];
+    for (int k = 0; k < 2; ++k) {
+        char *dst = (char *)ctx->stage.p + part_lo[k] * 32;
+        ZKB_CUDA(ctx, cudaMemcpyAsync(dst, scalars_host + 4 * part_lo[k], part_n[k] * 32, cudaMemcpyHostToDevice, st->copy_stream));
+        ZKB_CUDA(ctx, cudaEventRecord(st->part_uploaded[k], st->copy_stream));
+        ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->part_uploaded[k], 0));
+        const size_t off = offset + part_lo[k];
+        rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, (const uint4 *)dst, part_n[k], 0, fb, off, &plans[k], k, true)
+                : msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + off, (const uint4 *)dst, part_n[k], ctx->msm_force_c, nullptr, 0, &plans[k], k, true);
+        if (rc) return rc;
+    }
+    hec::Pt total = hec::inf();
+    for (int k = 0; k < 2; ++k) {
+        ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[k].tail_done));
+        total = hec::add(total, msm_fold(plans[k], st->slot[k].pinned));
+    }
+    hec::to_affine(total, out_xy, is_inf);
+    return ZKB_OK;
 }
 
 // arbitrary bases (drop-in for VariableBaseMSM::multi_scalar_mul / HomomorphicCommitment::multi_scalar_mul)
