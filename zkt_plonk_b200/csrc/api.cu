@@ -234,11 +234,7 @@ int zkb_ntt_batch_dev(zkb_ctx *ctx, uint64_t *const *ptrs_host, size_t count, si
                       int inverse, int coset) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!ptrs_host && count) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt_batch_dev: null pointer table");
-    for (size_t k = 0; k < count; ++k) {
-        int rc = zkb_ntt_run(ctx, ptrs_host[k], len, log_n, inverse, coset);
-        if (rc) return rc;
-    }
-    return ZKB_OK;
+    return zkb_ntt_run_batch(ctx, ptrs_host, count, len, log_n, inverse, coset);
 }
 
 int zkb_ntt(zkb_ctx *ctx, uint64_t *data_host, size_t len, unsigned log_n, int inverse, int coset) {

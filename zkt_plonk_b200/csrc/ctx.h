@@ -94,6 +94,7 @@ extern "C" int zkb_quotient_evals_range_dev(zkb_ctx *ctx, unsigned log_n, const 
                                             const uint64_t *const epk[11], uint64_t *out_dev, size_t lo, size_t hi);   // internal (hidden visibility)
 // implemented in ntt.cu / msm.cu / poly.cu
 int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int inverse, int coset);
+int zkb_ntt_run_batch(zkb_ctx *ctx, uint64_t *const *d_ptrs, size_t count, size_t len, unsigned log_n, int inverse, int coset);
 void zkb_msm_release(zkb_ctx *ctx);
 void zkb_comm_release(zkb_ctx *ctx);
 void zkb_commit_abort(zkb_ctx *ctx);   // drain and drop an open zkb_commit_push batch (error recovery)

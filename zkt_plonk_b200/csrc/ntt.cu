@@ -14,6 +14,8 @@
 // In a tile the transform is decimation-in-frequency with one __syncthreads per stage; elements sit in
 // shared memory as two 16-byte planes (low / high half) so that a quarter-warp always covers all 32 banks.
 // Coset scaling and the n^-1 factor are fused into the first load / last store.
+#include <algorithm>
+
 #include "ctx.h"
 #include "ff.cuh"
 #include "host_ff.h"
@@ -22,11 +24,14 @@ using namespace zkb;
 
 namespace {
 
-enum : uint32_t { M_IN_COSET = 1, M_OUT_COSET = 2, M_OUT_CONST = 4, M_LAST = 8 };
+enum : uint32_t { M_IN_COSET = 1, M_OUT_COSET = 2, M_OUT_CONST = 4, M_LAST = 8, M_FIRST = 16 };
+
+constexpr unsigned NTT_MAX_BATCH = 16;   // transforms of one launch (blockIdx.y)
 
 struct PassArgs {
-    const uint4 *in;
-    uint4 *out;
+    uint4 *data[NTT_MAX_BATCH];   // the transforms' own buffers: input of the first pass, output of the last
+    uint4 *scr;                   // ping-pong scratch of the middle passes: transform y at scr + y * scr_stride
+    unsigned long long scr_stride;
     const uint4 *tile_tw;   // w_T^j, j < T/2
     const uint4 *tw2;       // two-level table of w_M (M = T*S): lo[2^tw_s] then hi[M >> tw_s]
     const uint4 *cs2;       // two-level table of coset powers (g^e or g^-e / n): lo[2^cs_s] then hi
@@ -68,7 +73,7 @@ __device__ __forceinline__ fe_t pow2lvl(const uint4 *tab, uint32_t s, unsigned l
 }
 
 // inter-pass twiddle / output scaling and the store of output k of this tile (shared by both store paths)
-__device__ __forceinline__ void emit_output(const PassArgs &a, unsigned long long c, unsigned long long r,
+__device__ __forceinline__ void emit_output(const PassArgs &a, uint4 *out, unsigned long long c, unsigned long long r,
                                             unsigned long long base, uint32_t k, fe_t v) {
     unsigned long long o;
     if (!(a.mode & M_LAST)) {
@@ -81,7 +86,7 @@ __device__ __forceinline__ void emit_output(const PassArgs &a, unsigned long lon
         if (a.mode & M_OUT_COSET) v = fmul<FrP>(v, a.cs_direct ? fload_ro(a.cs_direct + 2 * o) : pow2lvl(a.cs2, a.cs_s, o));
         else if (a.mode & M_OUT_CONST) v = fmul<FrP>(v, a.scale);
     }
-    fstore(a.out + 2 * o, v);
+    fstore(out + 2 * o, v);
 }
 
 __device__ __forceinline__ void bfly(fe_t &u, fe_t &v) {        // (u, v) <- (u + v, u - v)
@@ -90,8 +95,11 @@ __device__ __forceinline__ void bfly(fe_t &u, fe_t &v) {        // (u, v) <- (u 
     u = s;
 }
 
-__global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
+__global__ void __launch_bounds__(256) ntt_pass_kernel(const __grid_constant__ PassArgs a) {
     extern __shared__ uint4 sm[];
+    uint4 *const mine = a.data[blockIdx.y], *const scr = a.scr + blockIdx.y * a.scr_stride;
+    const uint4 *const in = (a.mode & M_FIRST) ? mine : scr;
+    uint4 *const out = (a.mode & M_LAST) ? mine : scr;
     const uint32_t T = 1u << a.t;
     uint4 *s_lo = sm, *s_hi = sm + T + (T >> 3) + 1;
     const uint32_t tid = threadIdx.x, NT = blockDim.x;
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
         unsigned long long idx = base + ((unsigned long long)j << a.log_s);
         fe_t v;
         if (idx < a.len) {
-            v = fload(a.in + 2 * idx);
+            v = fload(in + 2 * idx);
             if (a.mode & M_IN_COSET) v = fmul<FrP>(v, a.cs_direct ? fload_ro(a.cs_direct + 2 * idx) : pow2lvl(a.cs2, a.cs_s, idx));
         } else {
             v = fzero<FrP>();
@@ -137,7 +145,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
     if (!tail) {                                       // tiny tiles: store straight from shared memory
         for (uint32_t i = tid; i < T; i += NT) {
             uint32_t k = a.t ? (__brev(i) >> (32 - a.t)) : 0;
-            emit_output(a, c, r, base, k, sm_load(s_lo, s_hi, i));
+            emit_output(a, out, c, r, base, k, sm_load(s_lo, s_hi, i));
         }
         return;
     }
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
             uint32_t k = __brev(8 * q + p) >> (32 - a.t);
-            emit_output(a, c, r, base, k, x[p]);
+            emit_output(a, out, c, r, base, k, x[p]);
         }
     }
 }
@@ -288,7 +296,22 @@ int zkb_pow2lvl_build(zkb_ctx *ctx, void *out, unsigned lm, const zkb::host::Fe 
 }
 
 int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int inverse, int coset) {
-    if (!d_data) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: null data pointer");
+    return zkb_ntt_run_batch(ctx, &d_data, 1, len, log_n, inverse, coset);
+}
+
+// `count` transforms of the same shape in one launch per pass (blockIdx.y selects the transform): a single 2^20 pass is
+// 512 tiles = 1.15 waves of the 444 resident CTAs, nine of them are 10.4
+int zkb_ntt_run_batch(zkb_ctx *ctx, uint64_t *const *d_ptrs, size_t count, size_t len, unsigned log_n, int inverse, int coset) {
+    if (!count) return ZKB_OK;
+    if (!d_ptrs) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: null pointer table");
+    for (size_t k = 0; k < count; ++k) if (!d_ptrs[k]) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: null data pointer");
+    if (count > NTT_MAX_BATCH) {
+        for (size_t k = 0; k < count; k += NTT_MAX_BATCH) {
+            int rc = zkb_ntt_run_batch(ctx, d_ptrs + k, std::min<size_t>(NTT_MAX_BATCH, count - k), len, log_n, inverse, coset);
+            if (rc) return rc;
+        }
+        return ZKB_OK;
+    }
     if (log_n > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ntt: log_n exceeds Fr TWO_ADICITY (28)");
     const size_t n = (size_t)1 << log_n;
     if (len > n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: len > 2^log_n");
@@ -302,7 +325,7 @@ int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int 
     else { m = 3; bits[0] = (log_n + 2) / 3; bits[1] = (log_n - bits[0] + 1) / 2; bits[2] = log_n - bits[0] - bits[1]; }
 
     if (m > 1) {
-        int rc = zkb_reserve(ctx, ctx->ntt_scratch, n * 32);
+        int rc = zkb_reserve(ctx, ctx->ntt_scratch, count * n * 32);
         if (rc) return rc;
     }
 
@@ -333,9 +356,9 @@ int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int 
         PassArgs a;
         memset(&a, 0, sizeof a);
         const bool first = p == 0, last = p == m - 1;
-        uint4 *data = (uint4 *)d_data, *scr = (uint4 *)ctx->ntt_scratch.p;
-        a.in = first ? data : scr;
-        a.out = last ? data : scr;
+        for (size_t k = 0; k < count; ++k) a.data[k] = (uint4 *)d_ptrs[k];
+        a.scr = (uint4 *)ctx->ntt_scratch.p;
+        a.scr_stride = 2 * (unsigned long long)n;                 // in uint4 units
         a.len = first ? len : n;
         a.t = t; a.log_s = log_s; a.log_n = log_n;
         a.t1 = m >= 2 ? bits[0] : 0;
@@ -357,7 +380,7 @@ int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int 
         }
         a.cs_direct = cs_direct;
         a.cs2 = cs2; a.cs_s = cs_s;
-        a.mode = (last ? M_LAST : 0);
+        a.mode = (last ? M_LAST : 0) | (first ? M_FIRST : 0);
         if (first && coset && !inverse) a.mode |= M_IN_COSET;
         if (last && inverse) a.mode |= coset ? M_OUT_COSET : M_OUT_CONST;
         a.scale = to_dev(ninv);
@@ -366,7 +389,7 @@ int zkb_ntt_run(zkb_ctx *ctx, uint64_t *d_data, size_t len, unsigned log_n, int 
         unsigned threads = (unsigned)(T / 8 < 32 ? 32 : (T / 8 > 256 ? 256 : T / 8));
         size_t tiles = n >> t;
         size_t smem = 2 * (T + T / 8 + 1) * 16;
-        ntt_pass_kernel<<<(unsigned)tiles, threads, smem, ctx->stream>>>(a);
+        ntt_pass_kernel<<<dim3((unsigned)tiles, (unsigned)count), threads, smem, ctx->stream>>>(a);
         ctx->launches += 1;
         ZKB_CUDA(ctx, cudaGetLastError());
     }

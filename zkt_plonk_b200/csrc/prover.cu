@@ -624,6 +624,26 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
         }
         return ZKB_OK;
     };
+    // several evaluation vectors at once: one batched iNTT launch per pass (a lone 2^18 transform is 0.3 waves of CTAs)
+    auto blinded_from_dev_evals_many = [&](const uint64_t *const *evals, const int *k_blind, DPoly *const *out, int count) -> int {
+        uint64_t *bufs[8];
+        for (int k = 0; k < count; ++k) {
+            TAKE(bufs[k], cap);
+            ZKB_CUDA(ctx, cudaMemsetAsync(bufs[k] + 4 * n, 0, (cap - n) * 32, s));
+            if (evals[k] != bufs[k]) ZKB_CUDA(ctx, cudaMemcpyAsync(bufs[k], evals[k], n * 32, cudaMemcpyDeviceToDevice, s));
+        }
+        TRY(zkb_ntt_batch_dev(ctx, bufs, (size_t)count, n, log_n, 1, 0));
+        for (int k = 0; k < count; ++k) {
+            out[k]->d = bufs[k]; out[k]->cap = cap;
+            TRY(zkb_poly_effective_len_dev(ctx, bufs[k], n, &out[k]->len));
+            if (k_blind[k]) {
+                TRY(zkb_poly_add_blinders_dev(ctx, bufs[k], out[k]->len, (const uint64_t *)(bl + bl_used), (size_t)k_blind[k]));
+                out[k]->len += k_blind[k];
+                bl_used += k_blind[k];
+            }
+        }
+        return ZKB_OK;
+    };
     DPoly pa, pb, pc;
     {
         struct { const uint64_t *host; uint64_t *dev; DPoly *poly; } wires[3] = {{a, ev_a, &pa}, {b, ev_b, &pb}, {c, ev_c, &pc}};
@@ -662,9 +682,12 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->lookup_uploaded, 0));
     tick(2);
     DPoly pt, ph1, ph2;
-    TRY(blinded_from_dev_evals(ev_t, 0, &pt));
-    TRY(blinded_from_dev_evals(ev_h1, 3, &ph1));
-    TRY(blinded_from_dev_evals(ev_h2, 2, &ph2));
+    {
+        const uint64_t *evs[3] = {ev_t, ev_h1, ev_h2};
+        const int kb[3] = {0, 3, 2};
+        DPoly *outs[3] = {&pt, &ph1, &ph2};
+        TRY(blinded_from_dev_evals_many(evs, kb, outs, 3));
+    }
     Pt c_t[3];
     { const DPoly *ps[3] = {&pt, &ph1, &ph2}; TRY(commit_many(ctx, ps, 3, c_t)); }
     tr.append_commitment("t_commit", c_t[0]);
@@ -679,25 +702,16 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     // ---- round 3: grand products (prove.rs:209-251)
     DPoly pz1, pz2;
     {
-        uint64_t *d;
-        TAKE(d, cap);
-        ZKB_CUDA(ctx, cudaMemsetAsync(d + 4 * n, 0, (cap - n) * 32, s));
-        TRY(zkb_z1_evals_dev(ctx, log_n, beta.l, gamma.l, ev_a, ev_b, ev_c, pk->sigma_evals[0], pk->sigma_evals[1], pk->sigma_evals[2], d));
+        uint64_t *z1e, *z2e;
+        TAKE(z1e, n); TAKE(z2e, n);
+        TRY(zkb_z1_evals_dev(ctx, log_n, beta.l, gamma.l, ev_a, ev_b, ev_c, pk->sigma_evals[0], pk->sigma_evals[1], pk->sigma_evals[2], z1e));
         if (zkb_grand_product_failed(ctx)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "compute_z1_poly: zero denominator (permutation/mod.rs:242)");
-        TRY(zkb_ntt_dev(ctx, d, n, log_n, 1, 0));
-        pz1.d = d; pz1.cap = cap;
-        TRY(zkb_poly_effective_len_dev(ctx, d, n, &pz1.len));
-        TRY(zkb_poly_add_blinders_dev(ctx, d, pz1.len, (const uint64_t *)(bl + bl_used), 3));
-        pz1.len += 3; bl_used += 3;
-        TAKE(d, cap);
-        ZKB_CUDA(ctx, cudaMemsetAsync(d + 4 * n, 0, (cap - n) * 32, s));
-        TRY(zkb_z2_evals_dev(ctx, log_n, delta.l, epsilon.l, ev_f, ev_t, ev_h1, ev_h2, d));
+        TRY(zkb_z2_evals_dev(ctx, log_n, delta.l, epsilon.l, ev_f, ev_t, ev_h1, ev_h2, z2e));
         if (zkb_grand_product_failed(ctx)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "compute_z2_poly: zero denominator (lookup/mod.rs:73)");
-        TRY(zkb_ntt_dev(ctx, d, n, log_n, 1, 0));
-        pz2.d = d; pz2.cap = cap;
-        TRY(zkb_poly_effective_len_dev(ctx, d, n, &pz2.len));
-        TRY(zkb_poly_add_blinders_dev(ctx, d, pz2.len, (const uint64_t *)(bl + bl_used), 3));
-        pz2.len += 3; bl_used += 3;
+        const uint64_t *evs[2] = {z1e, z2e};
+        const int kb[2] = {3, 3};
+        DPoly *outs[2] = {&pz1, &pz2};
+        TRY(blinded_from_dev_evals_many(evs, kb, outs, 2));
     }
     Pt c_z[2];
     { const DPoly *ps[2] = {&pz1, &pz2}; TRY(commit_many(ctx, ps, 2, c_z)); }
@@ -737,6 +751,8 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
         // that part, and the quotient slices are all-gathered before the (replicated) coset iNTT.
         const size_t world = (size_t)ctx->world;
         const bool fan = world > 1 && ctx->comm && n4 % world == 0 && n4 / world >= 4;
+        uint64_t *own[9];
+        size_t n_own = 0, max_len = 0;
         for (int k = 0; k < 9; ++k) {
             uint64_t *d;
             TAKE(d, n4);
@@ -745,8 +761,10 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
             if (fan && (size_t)k % world != (size_t)ctx->rank) continue;
             ZKB_CUDA(ctx, cudaMemsetAsync(d, 0, n4 * 32, s));
             ZKB_CUDA(ctx, cudaMemcpyAsync(d, wit_p[k]->d, wit_p[k]->len * 32, cudaMemcpyDeviceToDevice, s));
-            TRY(zkb_ntt_dev(ctx, d, wit_p[k]->len, log_n + 2, 0, 1));
+            own[n_own++] = d;
+            max_len = wit_p[k]->len > max_len ? wit_p[k]->len : max_len;
         }
+        TRY(zkb_ntt_batch_dev(ctx, own, n_own, max_len, log_n + 2, 0, 1));   // the buffers are zero beyond their own lengths
         uint64_t ch[20];
         const Fe *cs[5] = {&alpha, &beta, &gamma, &delta, &epsilon};
         for (int k = 0; k < 5; ++k) memcpy(ch + 4 * k, cs[k]->l, 32);
