@@ -65,12 +65,39 @@ def uniform_scalars(n, seed):
 
 
 class ClockSampler:
-    """Samples nvidia-smi while the timed region runs (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons of one GPU sampled every ~5 ms through NVML (pynvml) on a thread while the timed
+    region runs; falls back to `nvidia-smi -lms 100` (B200_PROFILING.md clocks line) when NVML is not importable.
+    Only samples taken after mark_begin() count."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self._stop = threading.Event()
+        self.t_begin = 0.0
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.rows.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), float(mx),
+                                          int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -82,27 +109,38 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
+        names = list(self.REASONS.items())
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
             if len(r) < 6:
                 continue
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                mask = 0
+                for (bit, _), v in zip([(0x8, 0), (0x40, 0), (0x20, 0), (0x4, 0)], r[2:6]):
+                    if v.lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((time.perf_counter(), float(r[0]), float(r[1]), mask))
             except ValueError:
                 continue
-            for name, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+        if not self.thread and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"]}
+        rows = [r for r in self.rows if r[0] >= self.t_begin] or self.rows[-1:]
+        reasons = set()
+        for r in rows:
+            for bit, name in self.REASONS.items():
+                if r[3] & bit:
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(r[2] for r in rows) if rows else None,
+                "reasons": sorted(reasons), "samples": len(rows), "source": "nvml, 5 ms period" if self.thread else "nvidia-smi -lms 100"}
 
 
 def ncu_traffic(kernel, key):
@@ -222,8 +260,8 @@ def run_main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # nvidia-smi samples every 100 ms: start it before the warm-up so that it is settled when the (short) timed region
-    # begins; it keeps sampling through the timed steps and the e2e loop, all of them under load
+    # clocks / throttle reasons are sampled on a thread (NVML, every ~5 ms) from the start of the timed region
+    # (mark_begin below) to the end of the e2e loop, all of it under load
     sampler = ClockSampler(local_rank)
     sampler.start()
     int_peak = ctx.bench_int(0)                                     # 32-bit IMAD/s, all SMs
@@ -231,6 +269,7 @@ def run_main(args):
         step(dev_sets[w % NSETS])
     barrier()
     # ---- timed region: K steps, each bracketed by events; L2 flushed (untimed) between steps
+    sampler.mark_begin()
     l0 = ctx.launch_count()
     step_ms, acc_ms, tot_ms = [], [], []
     results = []
