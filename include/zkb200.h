@@ -180,6 +180,10 @@ typedef struct zkb_plonk_pk zkb_plonk_pk;
 ZKB_API int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selectors[6], const uint64_t *const sigma[3],
                     size_t table_size, const size_t *pi_positions, size_t n_pi, zkb_plonk_pk **out);
 ZKB_API void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk);
+/* The `T: TranscriptProtocol` parameter of ZKTPlonk (plonk.rs:39-46).  kind 0: MerlinTranscript (transcript.rs:49-109,
+ * the default binary's); kind 1: EthereumTranscript (gadgets/src/transcript.rs:8-90, bin feature "ethereum-transcript":
+ * two chained Keccak-256 states, big-endian items, challenges below 2^253).  Applies to later zkb_plonk_prove calls. */
+ZKB_API int zkb_plonk_pk_set_transcript(zkb_plonk_pk *pk, int kind);
 /* VerifierKey commitments in seed_transcript order (keys/mod.rs:264-274): q_m q_l q_r q_o q_c sigma1 sigma2 sigma3
  * q_lookup q_table; 10 x (x || y) Montgomery. */
 ZKB_API int zkb_plonk_vk_commitments(const zkb_plonk_pk *pk, uint64_t out_xy[80], int is_inf[10]);
@@ -224,6 +228,12 @@ ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, co
  * zeroed buffers and {0, n, 0, n}).  Returns ZKB_ERR_INVALID for ElementNotIndexedInTable. */
 ZKB_API int zkb_test_combine_split(const uint64_t *table, size_t table_len, size_t n, const uint64_t *f, const uint32_t *rows,
                            size_t n_rows, uint64_t *h1, uint64_t *h2, size_t dirty[4], size_t out_lens[2]);
+
+/* Host only (no GPU): run a scripted transcript and return its challenges (32 B canonical little-endian each).
+ * ops[i]: 0 append_u64(args[9i]), 1 append_scalar(args[9i..9i+4), Montgomery Fr), 2 append_commitment(x = args[9i..],
+ * y = args[9i+4..], Montgomery Fq; args[9i+8] != 0: identity), 3 challenge_scalar.  The Merlin transcript is created
+ * with the label "test".  Pins the C++ EthereumTranscript against gadgets/src/transcript.rs:100-127. */
+ZKB_API int zkb_test_transcript(int kind, const uint8_t *ops, size_t n_ops, const uint64_t *args, uint8_t *challenges_out);
 
 /* Kernels this context has enqueued so far (bench.py's gpu_launches is a difference of two readings). */
 ZKB_API uint64_t zkb_launch_count(zkb_ctx *ctx);

@@ -16,7 +16,7 @@ from oracle import cref, pyref
 from zkt_plonk_b200 import field
 from zkt_plonk_b200.prover import (P, Poly, Proof, fr_to_limbs, ints_to_mont_array, limbs_to_fr, mont_array_to_ints,
                                     point_to_ints)
-from zkt_plonk_b200.transcript import MerlinTranscript
+from zkt_plonk_b200.transcript import TRANSCRIPTS
 
 EPK_ORDER = ("q_m", "q_l", "q_r", "q_o", "q_c", "q_lookup", "q_table", "sigma1", "sigma2", "sigma3", "l1")
 WIT_ORDER = ("z1", "z2", "a", "b", "c", "pi", "t", "h1", "h2")
@@ -153,12 +153,13 @@ def _kzg_check(commits, point, values, w, eta, tau):
     return lhs == rhs
 
 
-def verify(vk, proof, pub_inputs, tau):
-    """Proof::verify (proof.rs:285-503).  Returns 0 if accepted, else the failing step (1 or 2)."""
+def verify(vk, proof, pub_inputs, tau, transcript="merlin"):
+    """Proof::verify (proof.rs:285-503).  Returns 0 if accepted, else the failing step (1 or 2).
+    transcript: "merlin" (transcript.rs:49-109) or "ethereum" (gadgets/src/transcript.rs:8-90)."""
     n = vk.n
     log_n = n.bit_length() - 1
     assert len(pub_inputs) == len(vk.pi_roots), "invalid length of public inputs"
-    tr = MerlinTranscript("ZKT Plonk")
+    tr = TRANSCRIPTS[transcript][1]("ZKT Plonk")
     vk.seed_transcript(tr)
     tr.append_scalars("pi", pub_inputs)
     C, E = proof.commits, proof.evals

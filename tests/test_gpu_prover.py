@@ -101,6 +101,28 @@ def test_native_cpp_driver_matches_python_and_oracle(ctx, log_n, fixed_base):
     ctx.srs_precompute(-1)
 
 
+def test_native_driver_with_the_ethereum_transcript(ctx):
+    """zkb_plonk_pk_set_transcript(1): the C++ driver with `T = EthereumTranscript` (gadgets/src/transcript.rs:8-90) gives
+    the bytes of the Python schedule over the oracle backend with the same transcript; switching back restores Merlin."""
+    import zkt_plonk_b200 as z
+    circ = synthetic.make_circuit(6, seed=21, table_size=16)
+    d_srs, h_srs = gpu_srs(ctx, circ.n + 8)
+    kzg = z.GpuKZG10(ctx)
+    kzg.load_committer_key(d_srs)
+    blinders = list(range(500, 519))
+    native = prover.NativeProver(ctx, circ)
+    merlin_raw = native.prove_bytes(blinders)
+    native.set_transcript("ethereum")
+    raw = native.prove_bytes(blinders)
+    obe = plonk_ref.OracleBackend(h_srs)
+    opk, ovk = prover.setup(obe, circ)
+    assert raw == prover.prove(obe, opk, ovk, circ, blinders, transcript="ethereum").to_bytes() and raw != merlin_raw
+    assert plonk_ref.verify(native.vk(), prover.proof_from_bytes(raw), list(circ.pi.values()), TAU, transcript="ethereum") == 0
+    native.set_transcript("merlin")
+    assert native.prove_bytes(blinders) == merlin_raw
+    native.close()
+
+
 def test_native_driver_reuses_key_across_witnesses(ctx):
     """One key object, several witnesses / tables in a row: the C++ driver keeps its pinned lookup staging zero outside
     the regions a proof writes (sparse combine_split), so a proof must not see what the previous one left behind --

@@ -92,6 +92,21 @@ def test_prove_verify_roundtrip_on_oracle_backend(log_n):
     assert plonk_ref.verify(vk, bad, pub, TAU) != 0
 
 
+def test_prove_verify_with_the_ethereum_transcript():
+    """`T = EthereumTranscript` (bin feature "ethereum-transcript"): same schedule, other challenges; a proof made with
+    one transcript is rejected under the other."""
+    circ = synthetic.make_circuit(4, seed=11, table_size=4)
+    be = plonk_ref.OracleBackend(plonk_ref.make_srs_host(circ.n + 8, TAU))
+    pk, vk = prover.setup(be, circ)
+    blinders = list(range(7, 26))
+    pub = list(circ.pi.values())
+    eth = prover.prove(be, pk, vk, circ, blinders, transcript="ethereum")
+    mer = prover.prove(be, pk, vk, circ, blinders)
+    assert eth.to_bytes() != mer.to_bytes()
+    assert plonk_ref.verify(vk, eth, pub, TAU, transcript="ethereum") == 0
+    assert plonk_ref.verify(vk, eth, pub, TAU) != 0 and plonk_ref.verify(vk, mer, pub, TAU, transcript="ethereum") != 0
+
+
 def test_unsatisfied_witness_is_rejected():
     circ = synthetic.make_circuit(5, seed=3, table_size=4)
     c = prover.mont_array_to_ints(circ.c)

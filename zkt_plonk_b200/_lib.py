@@ -76,6 +76,8 @@ def load():
         "zkb_poly_effective_len_dev": (i, [vp, vp, sz, ctypes.POINTER(sz)]),
         "zkb_plonk_setup": (i, [vp, u, ctypes.POINTER(vp), ctypes.POINTER(vp), sz, ctypes.POINTER(sz), sz, ctypes.POINTER(vp)]),
         "zkb_plonk_pk_destroy": (None, [vp, vp]),
+        "zkb_plonk_pk_set_transcript": (i, [vp, i]),
+        "zkb_test_transcript": (i, [i, vp, sz, vp, vp]),
         "zkb_plonk_vk_commitments": (i, [vp, vp, ctypes.POINTER(i)]),
         "zkb_plonk_prove": (i, [vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, ctypes.POINTER(ctypes.c_float)]),
         "zkb_launch_count": (ctypes.c_uint64, [vp]),

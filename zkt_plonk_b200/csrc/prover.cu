@@ -102,10 +102,60 @@ struct Pt {                                   // affine G1, Montgomery; inf = id
     bool inf;
 };
 
-struct Transcript {                           // TranscriptProtocol for MerlinTranscript (transcript.rs:49-109)
+// Keccak-256 (the pre-NIST padding 0x01 .. 0x80, rate 136) on the same permutation: sha3::Keccak256 of
+// gadgets/src/transcript.rs:4
+void keccak256(const uint8_t *data, size_t n, uint8_t out[32]) {
+    uint8_t st[200];
+    memset(st, 0, 200);
+    const size_t rate = 136;
+    while (n >= rate) {
+        for (size_t i = 0; i < rate; ++i) st[i] ^= data[i];
+        keccak_f1600(st);
+        data += rate;
+        n -= rate;
+    }
+    for (size_t i = 0; i < n; ++i) st[i] ^= data[i];
+    st[n] ^= 0x01;
+    st[rate - 1] ^= 0x80;
+    keccak_f1600(st);
+    memcpy(out, st, 32);
+}
+
+// canonical BIG-endian bytes (into_repr().to_bytes_be())
+void fe_bytes_be(const Fe &m, const host::Params &P, uint8_t out[32]) {
+    uint8_t le[32];
+    fe_bytes(m, P, le);
+    for (int i = 0; i < 32; ++i) out[i] = le[31 - i];
+}
+
+// TranscriptProtocol for the reference's two transcripts.  kind 0: MerlinTranscript (plonk-core/src/transcript.rs:49-109,
+// the default binary's); kind 1: EthereumTranscript (gadgets/src/transcript.rs:8-90: two chained Keccak-256 states,
+// labels ignored, every item big-endian, challenges = digest mod 2^253), pinned by the reference's own known-answer
+// test (gadgets/src/transcript.rs:100-127) through zkb_test_transcript.
+struct Transcript {
+    int kind;
     Strobe128 s;
-    explicit Transcript(const char *label) : s("Merlin v1.0") { append_message("dom-sep", (const uint8_t *)label, strlen(label)); }
-    void append_message(const char *label, const uint8_t *msg, size_t n) {
+    uint8_t st0[32], st1[32];
+    uint32_t counter = 0;
+    explicit Transcript(const char *label, int kind_ = 0) : kind(kind_), s("Merlin v1.0") {
+        memset(st0, 0, 32);
+        memset(st1, 0, 32);
+        if (kind == 0) append_message("dom-sep", (const uint8_t *)label, strlen(label));
+    }
+    void eth_append(const uint8_t *item, size_t n) {              // append_bytes_without_label (transcript.rs:19-36)
+        std::vector<uint8_t> d(65 + n);
+        memcpy(d.data() + 1, st0, 32);
+        memcpy(d.data() + 33, st1, 32);
+        if (n) memcpy(d.data() + 65, item, n);
+        uint8_t n0[32], n1[32];
+        d[0] = 0;
+        keccak256(d.data(), d.size(), n0);
+        d[0] = 1;
+        keccak256(d.data(), d.size(), n1);
+        memcpy(st0, n0, 32);
+        memcpy(st1, n1, 32);
+    }
+    void append_message(const char *label, const uint8_t *msg, size_t n) {    // Merlin only
         s.meta_ad((const uint8_t *)label, strlen(label), false);
         uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
         s.meta_ad(len, 4, true);
@@ -113,33 +163,62 @@ struct Transcript {                           // TranscriptProtocol for MerlinTr
     }
     void append_u64(const char *label, uint64_t v) {
         uint8_t b[8];
+        if (kind == 1) {
+            for (int i = 0; i < 8; ++i) b[i] = (uint8_t)(v >> (56 - 8 * i));
+            eth_append(b, 8);
+            return;
+        }
         memcpy(b, &v, 8);
         append_message(label, b, 8);
     }
     void append_scalar(const char *label, const Fe &v) {
         uint8_t b[32];
+        if (kind == 1) { fe_bytes_be(v, host::FR, b); eth_append(b, 32); return; }
         fe_bytes(v, host::FR, b);
         append_message(label, b, 32);
     }
     void append_scalars(const char *label, const Fe *v, size_t n) {
+        if (kind == 1) { for (size_t i = 0; i < n; ++i) append_scalar(label, v[i]); return; }
         std::vector<uint8_t> b(32 * n);
         for (size_t i = 0; i < n; ++i) fe_bytes(v[i], host::FR, b.data() + 32 * i);
         append_message(label, b.data(), b.size());
     }
-    void append_commitment(const char *label, const Pt &p) {      // GroupAffine::write: x || y || infinity
-        uint8_t b[65];
+    void append_commitment(const char *label, const Pt &p) {
+        if (kind == 1) {                                           // x then y, each its own item; arkworks' zero is (0, 1, true)
+            uint8_t bx[32], by[32];
+            memset(bx, 0, 32);
+            memset(by, 0, 32);
+            if (p.inf) by[31] = 1;
+            else { fe_bytes_be(p.x, host::FQ, bx); fe_bytes_be(p.y, host::FQ, by); }
+            eth_append(bx, 32);
+            eth_append(by, 32);
+            return;
+        }
+        uint8_t b[65];                                             // GroupAffine::write: x || y || infinity
         memset(b, 0, 65);
-        if (p.inf) { b[32] = 1; b[64] = 1; }                       // arkworks' zero is (0, 1, true)
+        if (p.inf) { b[32] = 1; b[64] = 1; }
         else { fe_bytes(p.x, host::FQ, b); fe_bytes(p.y, host::FQ, b + 32); }
         append_message(label, b, 65);
     }
-    Fe challenge_scalar(const char *label) {                        // 31 squeezed bytes -> from_random_bytes
-        s.meta_ad((const uint8_t *)label, strlen(label), false);
-        uint8_t len[4] = {31, 0, 0, 0};
-        s.meta_ad(len, 4, true);
+    Fe challenge_scalar(const char *label) {
         uint8_t b[32];
         memset(b, 0, 32);
-        s.prf(b, 31);
+        if (kind == 1) {                                           // transcript.rs:76-89
+            uint8_t d[69], dig[32];
+            d[0] = 2;
+            memcpy(d + 1, st0, 32);
+            memcpy(d + 33, st1, 32);
+            d[65] = (uint8_t)(counter >> 24); d[66] = (uint8_t)(counter >> 16); d[67] = (uint8_t)(counter >> 8); d[68] = (uint8_t)counter;
+            ++counter;
+            keccak256(d, 69, dig);
+            for (int i = 0; i < 32; ++i) b[i] = dig[31 - i];
+            b[31] &= 0x1f;
+        } else {                                                   // 31 squeezed bytes -> from_random_bytes
+            s.meta_ad((const uint8_t *)label, strlen(label), false);
+            uint8_t len[4] = {31, 0, 0, 0};
+            s.meta_ad(len, 4, true);
+            s.prf(b, 31);
+        }
         Fe canon, r2;
         memcpy(canon.l, b, 32);
         memcpy(r2.l, host::FR.r2, 32);
@@ -283,6 +362,7 @@ struct zkb_plonk_pk {
     cudaEvent_t lookup_uploaded = nullptr, wire_uploaded = nullptr;
     char *arena = nullptr;                       // per-proof scratch: reset at the start of every prove
     size_t arena_bytes = 0, arena_off = 0;
+    int transcript_kind = 0;                     // 0 MerlinTranscript (default binary), 1 EthereumTranscript
 };
 
 namespace {
@@ -402,6 +482,29 @@ int zkb_test_combine_split(const uint64_t *table, size_t table_len, size_t n, co
     bool ok = combine_split_sparse((const Fe *)table, table_len, n, f_rows.data(), n_rows, (Fe *)h1, (Fe *)h2, d, &out_lens[0], &out_lens[1]);
     dirty[0] = d[0][0]; dirty[1] = d[0][1]; dirty[2] = d[1][0]; dirty[3] = d[1][1];
     return ok ? ZKB_OK : ZKB_ERR_INVALID;
+}
+
+int zkb_test_transcript(int kind, const uint8_t *ops, size_t n_ops, const uint64_t *args, uint8_t *challenges_out) {
+    if ((kind != 0 && kind != 1) || (!ops && n_ops) || !args || !challenges_out) return ZKB_ERR_INVALID;
+    Transcript tr("test", kind);
+    size_t n_ch = 0;
+    for (size_t i = 0; i < n_ops; ++i) {
+        const uint64_t *a = args + 9 * i;
+        switch (ops[i]) {
+            case 0: tr.append_u64("a", a[0]); break;
+            case 1: tr.append_scalar("b", fe_from(a)); break;
+            case 2: { Pt p; p.x = fe_from(a); p.y = fe_from(a + 4); p.inf = a[8] != 0; tr.append_commitment("c", p); break; }
+            case 3: { Fe c = tr.challenge_scalar("a"); fe_bytes(c, host::FR, challenges_out + 32 * n_ch++); break; }
+            default: return ZKB_ERR_INVALID;
+        }
+    }
+    return ZKB_OK;
+}
+
+int zkb_plonk_pk_set_transcript(zkb_plonk_pk *pk, int kind) {
+    if (!pk || (kind != 0 && kind != 1)) return ZKB_ERR_INVALID;
+    pk->transcript_kind = kind;
+    return ZKB_OK;
 }
 
 void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
@@ -542,7 +645,7 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     const Fe *bl = (const Fe *)blinders;
     int bl_used = 0;
 
-    Transcript tr("ZKT Plonk");                                            // plonk.rs:107
+    Transcript tr("ZKT Plonk", pk->transcript_kind);                       // plonk.rs:107
     tr.append_u64("circuit_size", (uint64_t)n);                           // VerifierKey::seed_transcript (keys/mod.rs:260-275)
     {
         const char *labels[10] = {"q_m_commit", "q_l_commit", "q_r_commit", "q_o_commit", "q_c_commit", "sigma1_commit",

@@ -14,7 +14,7 @@ Host-side witness plumbing (wire gathers, f = q_lookup * c, combine_split) stays
 import numpy as np
 
 from . import field
-from .transcript import MerlinTranscript, fr_bytes
+from .transcript import TRANSCRIPTS, MerlinTranscript, fr_bytes
 
 P = field.R_MOD
 Q = field.Q_MOD
@@ -422,8 +422,8 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     bl = iter(blinders)
     take = lambda k: [next(bl) for _ in range(k)]
     tr = transcript
-    if tr is None:
-        tr = MerlinTranscript("ZKT Plonk")                    # plonk.rs:107
+    if tr is None or isinstance(tr, str):                      # the `T: TranscriptProtocol` parameter (plonk.rs:39-46)
+        tr = TRANSCRIPTS[tr or "merlin"][1]("ZKT Plonk")      # plonk.rs:107
         vk.seed_transcript(tr)
     cap = n + 8
     w_n = field.root_of_unity(log_n)
@@ -572,6 +572,10 @@ class NativeProver:
         h = ctypes.c_void_p()
         ctx._check(lib.zkb_plonk_setup(ctx._h, circuit.log_n, S, G, circuit.table_size, PP, len(pos), ctypes.byref(h)))
         self._pk = h
+
+    def set_transcript(self, name):
+        """"merlin" (default) or "ethereum": which TranscriptProtocol later proofs use (zkb_plonk_pk_set_transcript)."""
+        self.ctx._check(self.ctx._lib.zkb_plonk_pk_set_transcript(self._pk, TRANSCRIPTS[name][0]))
 
     def vk(self):
         import ctypes

@@ -1,4 +1,6 @@
-"""Merlin transcript (merlin 3.0 over STROBE-128 / Keccak-f[1600]) and the reference's `TranscriptProtocol` on top.
+"""Merlin transcript (merlin 3.0 over STROBE-128 / Keccak-f[1600]) and the reference's `TranscriptProtocol` on top;
+also the reference's alternative `EthereumTranscript` (gadgets/src/transcript.rs:8-90, Keccak-256 over the same
+permutation), which is pinned by the reference's own known-answer test (gadgets/src/transcript.rs:100-127).
 
 Host-side, bytes-scale (a few dozen absorb/squeeze calls per proof), so it stays in Python.  Restates
 plonk-core/src/transcript.rs:49-109 (`MerlinTranscript`): scalars are appended as `ToBytes::write` output
@@ -162,3 +164,61 @@ class MerlinTranscript:
     def challenge_scalar(self, label):
         num_bytes = (254 + 7) // 8 - 1                      # (F::size_in_bits() + 7) / 8 - 1 = 31
         return int.from_bytes(self.t.challenge_bytes(label.encode(), num_bytes), "little")   # from_random_bytes
+
+
+def keccak256(data):
+    """sha3::Keccak256 (original Keccak padding 0x01 .. 0x80, rate 136), as gadgets/src/transcript.rs:4 imports it."""
+    rate, st = 136, bytearray(200)
+    data = bytes(data)
+    off = 0
+    while len(data) - off >= rate:
+        for i in range(rate):
+            st[i] ^= data[off + i]
+        keccak_f1600(st)
+        off += rate
+    for i, byte in enumerate(data[off:]):
+        st[i] ^= byte
+    st[len(data) - off] ^= 0x01
+    st[rate - 1] ^= 0x80
+    keccak_f1600(st)
+    return bytes(st[:32])
+
+
+class EthereumTranscript:
+    """TranscriptProtocol<Fr, KZG10Commitment<Bn254>> for EthereumTranscript (gadgets/src/transcript.rs:8-90): labels are
+    ignored, two 32-byte states are re-hashed with domain bytes 0 / 1 on every item, items are big-endian, a
+    challenge is Keccak-256(2 || state_0 || state_1 || counter_be32) read big-endian with the top three bits cleared."""
+
+    def __init__(self, label=None):
+        self.state_0, self.state_1, self.counter = bytes(32), bytes(32), 0
+
+    def _append(self, item):
+        body = self.state_0 + self.state_1 + bytes(item)
+        self.state_0, self.state_1 = keccak256(b"\x00" + body), keccak256(b"\x01" + body)
+
+    def append_u64(self, label, item):
+        self._append(int(item).to_bytes(8, "big"))
+
+    def append_scalar(self, label, item):
+        self._append(int(item % field.R_MOD).to_bytes(32, "big"))
+
+    def append_scalars(self, label, items):
+        for x in items:
+            self.append_scalar(label, x)
+
+    def append_commitment(self, label, pt):
+        x, y = (0, 1) if pt is None else pt               # arkworks' zero is (0, 1, true)
+        self._append(int(x).to_bytes(32, "big"))
+        self._append(int(y).to_bytes(32, "big"))
+
+    def append_commitments(self, label, pts):
+        for p in pts:
+            self.append_commitment(label, p)
+
+    def challenge_scalar(self, label):
+        digest = keccak256(b"\x02" + self.state_0 + self.state_1 + self.counter.to_bytes(4, "big"))
+        self.counter += 1
+        return int.from_bytes(digest, "big") & ((1 << 253) - 1)   # query.reverse(); query[31] &= 0x1f; Fr::read
+
+
+TRANSCRIPTS = {"merlin": (0, MerlinTranscript), "ethereum": (1, EthereumTranscript)}
