@@ -196,6 +196,43 @@ ZKB_API int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t
                     const uint64_t *table, size_t table_len, const uint64_t *pi_values, const uint64_t *blinders,
                     uint8_t proof_out[802], float timings_ms[8]);
 
+/* ---- the reference CLI's key files ---------------------------------------------------------------------- */
+/* `compile` writes ck / cvk / pk / epk / vk with ark-serialize 0.3 serialize_unchecked (bin/src/parser.rs:16-29,
+ * main.rs:96-113); `prove-withdraw` reads them back before every proof (parser.rs:5-14, main.rs:274-281).  Byte
+ * layout: csrc/keyfile.cu's header.  File side: canonical little-endian integers, identity = (0, 1) + flag bit;
+ * memory side: this library's forms (Montgomery limbs, identity = (0, 0)).  The *_file_* functions are host code
+ * and need no GPU.  The epk file is never read: its coset tables are rebuilt in HBM (10 coset NTTs).
+ * ck = sonic_pc::CommitterKey<Bn254> as PC::trim(pp, 4n, 0, None) leaves it (plonk.rs:79-85): powers_of_g,
+ * powers_of_gamma_g, three `None`s, max_degree. */
+ZKB_API int zkb_ck_file_info(const char *path, size_t *n_powers, size_t *max_degree);
+ZKB_API int zkb_ck_file_read(const char *path, size_t first, size_t count, uint64_t *xy_mont_out);
+ZKB_API int zkb_ck_file_write(const char *path, const uint64_t *xy_mont, size_t n_powers, const uint64_t *gamma_xy_mont, size_t n_gamma,
+                      size_t max_degree);
+/* deserialize_from_file::<CommitterKey>(ck_path) + keeping powers_of_g resident: the first min(max_points, all) powers
+ * become the context's SRS (max_points = 0: all). */
+ZKB_API int zkb_srs_load_ck_file(zkb_ctx *ctx, const char *path, size_t max_points);
+/* ProverKey<Fr> (keys/mod.rs:29-40): ten LabeledPolynomials in the order q_m q_l q_r q_o q_c sigma1 sigma2 sigma3
+ * q_lookup q_table, labels as setup.rs:93-102, no degree or hiding bounds.  lens: coefficients per polynomial. */
+ZKB_API int zkb_pk_file_info(const char *path, size_t lens[10]);
+ZKB_API int zkb_pk_file_read(const char *path, uint64_t *const coeffs_mont_out[10], const size_t caps[10], size_t lens[10]);
+ZKB_API int zkb_pk_file_write(const char *path, const uint64_t *const coeffs_mont[10], const size_t lens[10]);
+/* VerifierKey<Fr, KZG10<Bn254>> (keys/mod.rs:180-203): n, pi_roots, ten commitments in seed_transcript order.
+ * pi_roots_mont may be NULL (only *n_roots is reported); at most cap_roots roots are stored. */
+ZKB_API int zkb_vk_file_read(const char *path, size_t *n, uint64_t *pi_roots_mont, size_t cap_roots, size_t *n_roots,
+                     uint64_t commits_xy[80], int is_inf[10]);
+ZKB_API int zkb_vk_file_write(const char *path, size_t n, const uint64_t *pi_roots_mont, size_t n_roots, const uint64_t commits_xy[80],
+                      const int is_inf[10]);
+/* A proving key from the ProverKey's coefficient-form polynomials (host, Montgomery, pk-file order) instead of the
+ * composer's evaluation columns; vk_xy (10 x 8 limbs, may be NULL: the commitments are recomputed) and vk_inf (may be
+ * NULL) are the VerifierKey's commitments.  Proves byte-identically to the key zkb_plonk_setup builds. */
+ZKB_API int zkb_plonk_pk_from_polys(zkb_ctx *ctx, unsigned log_n, const uint64_t *const polys[10], const size_t lens[10],
+                            size_t table_size, const size_t *pi_positions, size_t n_pi, const uint64_t *vk_xy, const int *vk_inf,
+                            zkb_plonk_pk **out);
+/* pk + vk files -> proving key (public-input rows are recovered from vk.pi_roots = omega^row, setup.rs:123);
+ * proving key -> pk + vk files the reference CLI can read (either path may be NULL). */
+ZKB_API int zkb_plonk_load_keys(zkb_ctx *ctx, const char *pk_path, const char *vk_path, size_t table_size, zkb_plonk_pk **out);
+ZKB_API int zkb_plonk_save_keys(zkb_ctx *ctx, const zkb_plonk_pk *pk, const char *pk_path, const char *vk_path);
+
 /* ---- multi-GPU: one process per GPU, commitments sharded by point range ----------------------------------- */
 /* The reference is single-process (rayon threads only), so these have no reference counterpart; they carry the
  * exchange step of a sharded kzg10::commit.  Every rank runs the same prover (SPMD) on the same witness; a rank keeps

@@ -123,6 +123,50 @@ def test_native_driver_with_the_ethereum_transcript(ctx):
     native.close()
 
 
+def test_native_driver_from_the_reference_cli_key_files(ctx, tmp_path):
+    """ck / pk / vk files in the reference CLI's format (ark-serialize unchecked).  The files the GPU key
+    writes are byte-identical to the independent Python serialisation of the oracle-backend keys; a key loaded back
+    from files (committer key included) proves byte-identically to the key set up from the composer's columns."""
+    import zkt_plonk_b200 as z
+    from oracle import arkser
+    circ = synthetic.make_circuit(7, seed=33, table_size=16)
+    n_powers = 4 * circ.n + 1                                              # PC::trim(pp, 4n, 0, None): plonk.rs:79-85
+    d_srs, h_srs = gpu_srs(ctx, n_powers)
+    kzg = z.GpuKZG10(ctx)
+    kzg.load_committer_key(d_srs)
+    blinders = list(range(900, 919))
+    native = prover.NativeProver(ctx, circ)
+    raw = native.prove_bytes(blinders)
+    pk_path, vk_path, ck_path = tmp_path / "pk", tmp_path / "vk", tmp_path / "ck"
+    native.save_keys(pk_path, vk_path)
+    obe = plonk_ref.OracleBackend(h_srs)
+    opk, ovk = prover.setup(obe, circ)
+    polys = {name: prover.mont_array_to_ints(opk.polys[name].data[: opk.polys[name].len]) for name in arkser.PK_ORDER}
+    assert pk_path.read_bytes() == arkser.prover_key(polys)
+    assert vk_path.read_bytes() == arkser.verifier_key(ovk.n, ovk.pi_roots, ovk.commits)
+    pts = [prover.point_to_ints(row, not row.any()) for row in h_srs]
+    ck_path.write_bytes(arkser.committer_key(pts, pts[:2], n_powers - 1))
+    native.close()
+    ctx.srs_load(d_srs[:8].contiguous())                                   # forget the key, then read it from the file
+    kzg.load_committer_key_file(ck_path)
+    assert ctx.srs_size() == n_powers
+    loaded = prover.NativeProver(ctx, circ, key_files=(pk_path, vk_path))
+    assert loaded.vk().commits == ovk.commits and loaded.vk().pi_roots == ovk.pi_roots
+    assert loaded.prove_bytes(blinders) == raw
+    out_pk, out_vk = tmp_path / "pk2", tmp_path / "vk2"
+    loaded.save_keys(out_pk, out_vk)
+    assert out_pk.read_bytes() == pk_path.read_bytes() and out_vk.read_bytes() == vk_path.read_bytes()
+    loaded.close()
+    # without the vk file's commitments (zkb_plonk_pk_from_polys with vk_xy = NULL) they are recomputed
+    recomputed = prover.NativeProver(ctx, circ, key_polys=z.keyfile.pk_read(pk_path))
+    assert recomputed.vk().commits == ovk.commits and recomputed.prove_bytes(blinders) == raw
+    recomputed.close()
+    bad = tmp_path / "bad"
+    bad.write_bytes(pk_path.read_bytes()[:-7])
+    with pytest.raises(Exception, match="ProverKey"):
+        prover.NativeProver(ctx, circ, key_files=(bad, vk_path))
+
+
 def test_native_driver_reuses_key_across_witnesses(ctx):
     """One key object, several witnesses / tables in a row: the C++ driver keeps its pinned lookup staging zero outside
     the regions a proof writes (sparse combine_split), so a proof must not see what the previous one left behind --

@@ -9,4 +9,4 @@ from ._lib import LIB_PATH, ZkbError, declared_symbols  # noqa: F401
 from .context import Context, sum_partials  # noqa: F401
 from .domain import GpuEvaluationDomain  # noqa: F401
 from .kzg import GpuKZG10, PCError  # noqa: F401
-from . import prover_ops  # noqa: F401,E402
+from . import keyfile, prover_ops  # noqa: F401,E402

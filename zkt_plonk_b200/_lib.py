@@ -80,6 +80,19 @@ def load():
         "zkb_test_transcript": (i, [i, vp, sz, vp, vp]),
         "zkb_plonk_vk_commitments": (i, [vp, vp, ctypes.POINTER(i)]),
         "zkb_plonk_prove": (i, [vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, ctypes.POINTER(ctypes.c_float)]),
+        "zkb_ck_file_info": (i, [ctypes.c_char_p, ctypes.POINTER(sz), ctypes.POINTER(sz)]),
+        "zkb_ck_file_read": (i, [ctypes.c_char_p, sz, sz, vp]),
+        "zkb_ck_file_write": (i, [ctypes.c_char_p, vp, sz, vp, sz, sz]),
+        "zkb_srs_load_ck_file": (i, [vp, ctypes.c_char_p, sz]),
+        "zkb_pk_file_info": (i, [ctypes.c_char_p, ctypes.POINTER(sz)]),
+        "zkb_pk_file_read": (i, [ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz)]),
+        "zkb_pk_file_write": (i, [ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(sz)]),
+        "zkb_vk_file_read": (i, [ctypes.c_char_p, ctypes.POINTER(sz), vp, sz, ctypes.POINTER(sz), vp, ctypes.POINTER(i)]),
+        "zkb_vk_file_write": (i, [ctypes.c_char_p, sz, vp, sz, vp, ctypes.POINTER(i)]),
+        "zkb_plonk_pk_from_polys": (i, [vp, u, ctypes.POINTER(vp), ctypes.POINTER(sz), sz, ctypes.POINTER(sz), sz, vp,
+                                    ctypes.POINTER(i), ctypes.POINTER(vp)]),
+        "zkb_plonk_load_keys": (i, [vp, ctypes.c_char_p, ctypes.c_char_p, sz, ctypes.POINTER(vp)]),
+        "zkb_plonk_save_keys": (i, [vp, vp, ctypes.c_char_p, ctypes.c_char_p]),
         "zkb_launch_count": (ctypes.c_uint64, [vp]),
         "zkb_msm_last_timing": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),
         "zkb_bench_int": (i, [vp, i, ctypes.POINTER(ctypes.c_double)]),

@@ -92,6 +92,11 @@ class Context:
         else:
             self._check(self._lib.zkb_srs_load_g1_dev(self._h, _dev_ptr(points), points.numel() // 8))
 
+    def srs_load_ck_file(self, path, max_points=0):
+        """powers_of_g of the reference CLI's committer-key file (`ck`, bin/src/main.rs:274) become the resident SRS."""
+        import os
+        self._check(self._lib.zkb_srs_load_ck_file(self._h, os.fsencode(path), int(max_points)))
+
     def srs_precompute(self, c=0):
         """Build (c >= 0) or drop (c < 0) the fixed-base window tables of the resident SRS."""
         self._check(self._lib.zkb_srs_precompute(self._h, int(c)))

@@ -521,18 +521,93 @@ void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
     delete pk;
 }
 
+namespace {
+
+// shared head of the two ways to build a key: argument checks and the empty key object
+int key_begin(zkb_ctx *ctx, unsigned log_n, size_t table_size, const size_t *pi_positions, size_t n_pi, zkb_plonk_pk **pk_out) {
+    if (log_n + 2 > 28 || log_n < 3) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_plonk_setup: need 8 <= n and 4n <= 2^28 (InvalidEvalDomainSize)");
+    const size_t n = (size_t)1 << log_n;
+    if (table_size >= n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_setup: max table size is equal or larger than n (lookup/table.rs:43)");
+    if (n + 8 > ctx->srs_global_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_plonk_setup: the committer key must hold at least n + 8 powers");
+    for (size_t i = 0; i < n_pi; ++i)
+        if (pi_positions[i] >= n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_setup: public-input row outside the domain");
+    zkb_plonk_pk *pk = new zkb_plonk_pk();
+    pk->log_n = log_n; pk->n = n; pk->table_size = table_size;
+    pk->pi_pos.assign(pi_positions, pi_positions + n_pi);
+    *pk_out = pk;
+    return ZKB_OK;
+}
+
+// shared tail: lookup rows to HBM, verifier-key commitments (unless given), the extended key, arena, staging, streams.
+// Expects pk->poly[], pk->sigma_evals[], pk->lookup_rows / lookup_q to be in place.
+int key_finish(zkb_ctx *ctx, zkb_plonk_pk *pk, bool have_vk) {
+    const unsigned log_n = pk->log_n;
+    const size_t n = pk->n, n4 = 4 * n;
+    {
+        uint64_t *rows_dev, *vals_dev;
+        const size_t n_rows = pk->lookup_rows.size();
+        int rc = dev_alloc_owned(ctx, pk, n_rows * 4 + 32, &rows_dev);
+        if (rc) return rc;
+        rc = dev_alloc_owned(ctx, pk, n_rows * 32 + 32, &vals_dev);
+        if (rc) return rc;
+        pk->d_lookup_rows = (uint32_t *)rows_dev;
+        pk->d_lookup_vals = vals_dev;
+        if (n_rows && cudaMemcpy(pk->d_lookup_rows, pk->lookup_rows.data(), n_rows * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+            ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_setup: H2D copy failed");
+    }
+    int rc;
+    if (!have_vk) {                                                        // verifier key commitments in VerifierKey order (setup.rs:104-121)
+        const int vk_order[10] = {P_QM, P_QL, P_QR, P_QO, P_QC, P_S1, P_S2, P_S3, P_QLK, P_QT};
+        const DPoly *cp[10];
+        for (int k = 0; k < 10; ++k) cp[k] = &pk->poly[vk_order[k]];
+        rc = commit_many(ctx, cp, 10, pk->vk);
+        if (rc) return rc;
+    }
+    // extended key: 10 coset tables on 4n + l_1 (keys/mod.rs:96-119); x_coset / zh_coset live inside the quotient kernel
+    for (int k = 0; k < 11; ++k) {
+        rc = dev_alloc_owned(ctx, pk, n4 * 32, &pk->epk[k]);
+        if (rc) return rc;
+        if (k < 10) {
+            const DPoly &p = pk->poly[k];
+            if (cudaMemsetAsync(pk->epk[k], 0, n4 * 32, ctx->stream) != cudaSuccess ||
+                cudaMemcpyAsync(pk->epk[k], p.d, p.len * 32, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+                ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_setup: device copy failed");
+            rc = zkb_ntt_dev(ctx, pk->epk[k], p.len, log_n + 2, 0, 1);
+        } else {
+            rc = zkb_l1_coset_dev(ctx, log_n, pk->epk[k]);
+        }
+        if (rc) return rc;
+    }
+    // scratch arena for one proof: 9 witness cosets + the quotient (4n each) and ~30 n-sized buffers
+    pk->arena_bytes = (10 * n4 + 34 * (n + 16)) * 32 + 64 * 9 * 512;
+    if (cudaMalloc((void **)&pk->arena, pk->arena_bytes) != cudaSuccess)
+        ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_plonk_setup: cannot allocate the prover arena");
+    if (cudaMallocHost((void **)&pk->stage, 4 * n * sizeof(Fe)) != cudaSuccess)
+        ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_plonk_setup: cannot allocate pinned staging");
+    if (cudaMallocHost((void **)&pk->wire_stage, 3 * n * sizeof(Fe)) != cudaSuccess)
+        ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_plonk_setup: cannot allocate pinned staging");
+    memset(pk->stage, 0, 4 * n * sizeof(Fe));                              // kept zero outside the regions a proof writes
+    pk->dirty_h[0][1] = pk->dirty_h[1][1] = n;
+    if (cudaStreamCreateWithFlags(&pk->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&pk->lookup_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pk->lookup_uploaded, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pk->wire_uploaded, cudaEventDisableTiming) != cudaSuccess)
+        ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_setup: cannot create the copy stream");
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_setup: stream error");
+    return ZKB_OK;
+}
+
+}  // namespace
+
 int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selectors[6], const uint64_t *const sigma[3],
                     size_t table_size, const size_t *pi_positions, size_t n_pi, zkb_plonk_pk **out) {
     if (!ctx || !out) return ZKB_ERR_INVALID;
     *out = nullptr;
     if (!selectors || !sigma || (!pi_positions && n_pi)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_setup: null argument");
-    if (log_n + 2 > 28 || log_n < 3) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_plonk_setup: need 8 <= n and 4n <= 2^28 (InvalidEvalDomainSize)");
-    const size_t n = (size_t)1 << log_n, n4 = 4 * n;
-    if (table_size >= n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_setup: max table size is equal or larger than n (lookup/table.rs:43)");
-    if (n + 8 > ctx->srs_global_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_plonk_setup: the committer key must hold at least n + 8 powers");
-    zkb_plonk_pk *pk = new zkb_plonk_pk();
-    pk->log_n = log_n; pk->n = n; pk->table_size = table_size;
-    pk->pi_pos.assign(pi_positions, pi_positions + n_pi);
+    zkb_plonk_pk *pk = nullptr;
+    int rc = key_begin(ctx, log_n, table_size, pi_positions, n_pi, &pk);
+    if (rc) return rc;
+    const size_t n = pk->n;
     auto fail = [&](int rc) { zkb_plonk_pk_destroy(ctx, pk); return rc; };
     // selector / sigma polynomials (setup.rs:72-90) and the q_table mask (lookup/table.rs:42-48)
     const uint64_t *src[10] = {selectors[0], selectors[1], selectors[2], selectors[3], selectors[4], selectors[5], nullptr,
@@ -543,13 +618,13 @@ int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selector
     for (int k = 0; k < 10; ++k) {
         if (!src[k]) return fail((ctx->err = "zkb_plonk_setup: null selector / sigma column", ZKB_ERR_INVALID));
         uint64_t *d;
-        int rc = dev_alloc_owned(ctx, pk, n * 32, &d);
+        rc = dev_alloc_owned(ctx, pk, n * 32, &d);
         if (rc) return fail(rc);
         rc = poly_from_evals_host(ctx, src[k], log_n, d, n, &pk->poly[k]);
         if (rc) return fail(rc);
     }
     for (int k = 0; k < 3; ++k) {
-        int rc = dev_alloc_owned(ctx, pk, n * 32, &pk->sigma_evals[k]);
+        rc = dev_alloc_owned(ctx, pk, n * 32, &pk->sigma_evals[k]);
         if (rc) return fail(rc);
         if (cudaMemcpyAsync(pk->sigma_evals[k], sigma[k], n * 32, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
             return fail((ctx->err = "zkb_plonk_setup: H2D copy failed", ZKB_ERR_CUDA));
@@ -558,56 +633,152 @@ int zkb_plonk_setup(zkb_ctx *ctx, unsigned log_n, const uint64_t *const selector
         const Fe q = fe_from(selectors[5] + 4 * i);
         if (!host::is_zero(q)) { pk->lookup_rows.push_back((uint32_t)i); pk->lookup_q.push_back(q); }
     }
-    {
-        uint64_t *rows_dev, *vals_dev;
-        const size_t n_rows = pk->lookup_rows.size();
-        int rc = dev_alloc_owned(ctx, pk, n_rows * 4 + 32, &rows_dev);
-        if (rc) return fail(rc);
-        rc = dev_alloc_owned(ctx, pk, n_rows * 32 + 32, &vals_dev);
-        if (rc) return fail(rc);
-        pk->d_lookup_rows = (uint32_t *)rows_dev;
-        pk->d_lookup_vals = vals_dev;
-        if (n_rows && cudaMemcpy(pk->d_lookup_rows, pk->lookup_rows.data(), n_rows * 4, cudaMemcpyHostToDevice) != cudaSuccess)
-            return fail((ctx->err = "zkb_plonk_setup: H2D copy failed", ZKB_ERR_CUDA));
-    }
-    // verifier key commitments in VerifierKey order (setup.rs:104-121)
-    const int vk_order[10] = {P_QM, P_QL, P_QR, P_QO, P_QC, P_S1, P_S2, P_S3, P_QLK, P_QT};
-    const DPoly *cp[10];
-    for (int k = 0; k < 10; ++k) cp[k] = &pk->poly[vk_order[k]];
-    int rc = commit_many(ctx, cp, 10, pk->vk);
+    rc = key_finish(ctx, pk, false);
     if (rc) return fail(rc);
-    // extended key: 10 coset tables on 4n + l_1 (keys/mod.rs:96-119); x_coset / zh_coset live inside the quotient kernel
-    for (int k = 0; k < 11; ++k) {
-        rc = dev_alloc_owned(ctx, pk, n4 * 32, &pk->epk[k]);
-        if (rc) return fail(rc);
-        if (k < 10) {
-            const DPoly &p = pk->poly[k];
-            if (cudaMemsetAsync(pk->epk[k], 0, n4 * 32, ctx->stream) != cudaSuccess ||
-                cudaMemcpyAsync(pk->epk[k], p.d, p.len * 32, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
-                return fail((ctx->err = "zkb_plonk_setup: device copy failed", ZKB_ERR_CUDA));
-            rc = zkb_ntt_dev(ctx, pk->epk[k], p.len, log_n + 2, 0, 1);
-        } else {
-            rc = zkb_l1_coset_dev(ctx, log_n, pk->epk[k]);
-        }
-        if (rc) return fail(rc);
-    }
-    // scratch arena for one proof: 9 witness cosets + the quotient (4n each) and ~30 n-sized buffers
-    pk->arena_bytes = (10 * n4 + 34 * (n + 16)) * 32 + 64 * 9 * 512;
-    if (cudaMalloc((void **)&pk->arena, pk->arena_bytes) != cudaSuccess)
-        return fail((ctx->err = "zkb_plonk_setup: cannot allocate the prover arena", ZKB_ERR_OOM));
-    if (cudaMallocHost((void **)&pk->stage, 4 * n * sizeof(Fe)) != cudaSuccess)
-        return fail((ctx->err = "zkb_plonk_setup: cannot allocate pinned staging", ZKB_ERR_OOM));
-    if (cudaMallocHost((void **)&pk->wire_stage, 3 * n * sizeof(Fe)) != cudaSuccess)
-        return fail((ctx->err = "zkb_plonk_setup: cannot allocate pinned staging", ZKB_ERR_OOM));
-    memset(pk->stage, 0, 4 * n * sizeof(Fe));                              // kept zero outside the regions a proof writes
-    pk->dirty_h[0][1] = pk->dirty_h[1][1] = n;
-    if (cudaStreamCreateWithFlags(&pk->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&pk->lookup_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&pk->lookup_uploaded, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&pk->wire_uploaded, cudaEventDisableTiming) != cudaSuccess)
-        return fail((ctx->err = "zkb_plonk_setup: cannot create the copy stream", ZKB_ERR_CUDA));
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail((ctx->err = "zkb_plonk_setup: stream error", ZKB_ERR_CUDA));
     *out = pk;
+    return ZKB_OK;
+}
+
+// The same key from what the reference's `compile` wrote: the ten ProverKey polynomials in coefficient form (pk file
+// order: q_m q_l q_r q_o q_c sigma1 sigma2 sigma3 q_lookup q_table) and, optionally, the VerifierKey commitments.  The
+// evaluation tables the prover needs (sigma1..3 and q_lookup over the domain, keys/mod.rs:121-145) come back by forward
+// NTTs, exactly (the transforms are bijections), so a key built this way proves byte-identically to one built by
+// zkb_plonk_setup from the composer's columns.
+int zkb_plonk_pk_from_polys(zkb_ctx *ctx, unsigned log_n, const uint64_t *const polys[10], const size_t lens[10], size_t table_size,
+                            const size_t *pi_positions, size_t n_pi, const uint64_t *vk_xy, const int *vk_inf, zkb_plonk_pk **out) {
+    if (!ctx || !out) return ZKB_ERR_INVALID;
+    *out = nullptr;
+    if (!polys || !lens || (!pi_positions && n_pi)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_pk_from_polys: null argument");
+    zkb_plonk_pk *pk = nullptr;
+    int rc = key_begin(ctx, log_n, table_size, pi_positions, n_pi, &pk);
+    if (rc) return rc;
+    const size_t n = pk->n;
+    auto fail = [&](int rc) { zkb_plonk_pk_destroy(ctx, pk); return rc; };
+    const int file_to_key[10] = {P_QM, P_QL, P_QR, P_QO, P_QC, P_S1, P_S2, P_S3, P_QLK, P_QT};
+    for (int f = 0; f < 10; ++f) {
+        const int k = file_to_key[f];
+        if (lens[f] > n || (!polys[f] && lens[f]))
+            return fail((ctx->err = "zkb_plonk_pk_from_polys: a key polynomial has more than n coefficients", ZKB_ERR_INVALID));
+        uint64_t *d;
+        rc = dev_alloc_owned(ctx, pk, n * 32, &d);
+        if (rc) return fail(rc);
+        if (cudaMemsetAsync(d, 0, n * 32, ctx->stream) != cudaSuccess ||
+            (lens[f] && cudaMemcpyAsync(d, polys[f], lens[f] * 32, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess))
+            return fail((ctx->err = "zkb_plonk_pk_from_polys: H2D copy failed", ZKB_ERR_CUDA));
+        pk->poly[k].d = d;
+        pk->poly[k].cap = n;
+        size_t len = lens[f];                                              // DensePolynomial invariant: no trailing zeros
+        while (len && !(polys[f][4 * (len - 1)] | polys[f][4 * (len - 1) + 1] | polys[f][4 * (len - 1) + 2] | polys[f][4 * (len - 1) + 3])) --len;
+        pk->poly[k].len = len;
+    }
+    // evaluation tables: sigma1..3 for z1 (keys/permutation.rs:74-92), q_lookup for f = q_lookup * c (prove.rs:157-161)
+    for (int k = 0; k < 4; ++k) {
+        uint64_t *d;
+        rc = dev_alloc_owned(ctx, pk, n * 32, &d);
+        if (rc) return fail(rc);
+        const DPoly &p = pk->poly[k < 3 ? P_S1 + k : P_QLK];
+        if (cudaMemcpyAsync(d, p.d, n * 32, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+            return fail((ctx->err = "zkb_plonk_pk_from_polys: device copy failed", ZKB_ERR_CUDA));
+        rc = zkb_ntt_dev(ctx, d, p.len, log_n, 0, 0);
+        if (rc) return fail(rc);
+        if (k < 3) { pk->sigma_evals[k] = d; continue; }
+        std::vector<Fe> q(n);
+        if (cudaMemcpyAsync(q.data(), d, n * 32, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            return fail((ctx->err = "zkb_plonk_pk_from_polys: D2H copy failed", ZKB_ERR_CUDA));
+        for (size_t i = 0; i < n; ++i)
+            if (!host::is_zero(q[i])) { pk->lookup_rows.push_back((uint32_t)i); pk->lookup_q.push_back(q[i]); }
+    }
+    if (vk_xy) {
+        for (int k = 0; k < 10; ++k) {
+            pk->vk[k].x = fe_from(vk_xy + 8 * k);
+            pk->vk[k].y = fe_from(vk_xy + 8 * k + 4);
+            pk->vk[k].inf = (vk_inf && vk_inf[k]) || (host::is_zero(pk->vk[k].x) && host::is_zero(pk->vk[k].y));
+        }
+    }
+    rc = key_finish(ctx, pk, vk_xy != nullptr);
+    if (rc) return fail(rc);
+    *out = pk;
+    return ZKB_OK;
+}
+
+// ProverKey + VerifierKey files of the reference CLI (bin/src/main.rs:274-281 reads them before every proof).
+// Public-input rows are recovered from vk.pi_roots (= omega^row, setup.rs:123).
+int zkb_plonk_load_keys(zkb_ctx *ctx, const char *pk_path, const char *vk_path, size_t table_size, zkb_plonk_pk **out) {
+    if (!ctx || !out) return ZKB_ERR_INVALID;
+    *out = nullptr;
+    size_t n = 0, n_roots = 0;
+    uint64_t vk_xy[80];
+    int vk_inf[10];
+    if (zkb_vk_file_read(vk_path, &n, nullptr, 0, &n_roots, vk_xy, vk_inf) != ZKB_OK)
+        ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_load_keys: not a VerifierKey file (ark-serialize unchecked, KZG10 / Bn254)");
+    if (n < 8 || (n & (n - 1)) || n > ((size_t)1 << 26)) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_plonk_load_keys: vk.n is not a supported domain size");
+    unsigned log_n = 0;
+    while (((size_t)1 << log_n) < n) ++log_n;
+    std::vector<Fe> roots(n_roots ? n_roots : 1);
+    if (zkb_vk_file_read(vk_path, &n, (uint64_t *)roots.data(), n_roots, &n_roots, vk_xy, vk_inf) != ZKB_OK)
+        ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_load_keys: cannot re-read the VerifierKey file");
+    std::vector<size_t> pos(n_roots);
+    {
+        std::unordered_map<Fe, size_t, KeyHash, KeyEq> want;
+        for (size_t i = 0; i < n_roots; ++i) want.emplace(roots[i], i);
+        if (want.size() != n_roots) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_load_keys: repeated public-input root");
+        const Fe w = host::fr_root_of_unity(log_n);
+        Fe x = FR_ONE();
+        size_t found = 0;
+        for (size_t i = 0; i < n && found < n_roots; ++i) {
+            auto it = want.find(x);
+            if (it != want.end()) { pos[it->second] = i; ++found; }
+            x = host::mul(x, w, host::FR);
+        }
+        if (found != n_roots) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_load_keys: a public-input root is not in the domain of size vk.n");
+        for (size_t i = 1; i < n_roots; ++i)
+            if (pos[i] <= pos[i - 1]) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_load_keys: public-input roots are not in row order");
+    }
+    size_t lens[10];
+    if (zkb_pk_file_info(pk_path, lens) != ZKB_OK)
+        ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_load_keys: not a ProverKey file (ark-serialize unchecked, labels of setup.rs:93-102)");
+    std::vector<std::vector<uint64_t>> store(10);
+    uint64_t *ptrs[10];
+    for (int k = 0; k < 10; ++k) {
+        if (lens[k] > n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_load_keys: a ProverKey polynomial has more than vk.n coefficients");
+        store[k].resize(4 * (lens[k] ? lens[k] : 1));
+        ptrs[k] = store[k].data();
+    }
+    if (zkb_pk_file_read(pk_path, ptrs, lens, lens) != ZKB_OK)
+        ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_load_keys: a ProverKey coefficient is not a canonical Fr element");
+    return zkb_plonk_pk_from_polys(ctx, log_n, ptrs, lens, table_size, pos.data(), n_roots, vk_xy, vk_inf, out);
+}
+
+// What `compile` writes (main.rs:106-112), from a key built here: pk and vk files the reference's CLI can read.
+int zkb_plonk_save_keys(zkb_ctx *ctx, const zkb_plonk_pk *pk, const char *pk_path, const char *vk_path) {
+    if (!ctx || !pk) return ZKB_ERR_INVALID;
+    if (pk_path) {
+        const int file_to_key[10] = {P_QM, P_QL, P_QR, P_QO, P_QC, P_S1, P_S2, P_S3, P_QLK, P_QT};
+        std::vector<std::vector<uint64_t>> store(10);
+        const uint64_t *ptrs[10];
+        size_t lens[10];
+        for (int f = 0; f < 10; ++f) {
+            const DPoly &p = pk->poly[file_to_key[f]];
+            store[f].resize(4 * (p.len ? p.len : 1));
+            lens[f] = p.len;
+            ptrs[f] = store[f].data();
+            if (p.len && cudaMemcpyAsync(store[f].data(), p.d, p.len * 32, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+                ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_save_keys: D2H copy failed");
+        }
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_save_keys: stream error");
+        if (zkb_pk_file_write(pk_path, ptrs, lens) != ZKB_OK) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_save_keys: cannot write the ProverKey file");
+    }
+    if (vk_path) {
+        const Fe w = host::fr_root_of_unity(pk->log_n);
+        std::vector<Fe> roots(pk->pi_pos.size() ? pk->pi_pos.size() : 1);
+        for (size_t i = 0; i < pk->pi_pos.size(); ++i) roots[i] = host::pow_u64(w, pk->pi_pos[i], host::FR);
+        uint64_t xy[80];
+        int inf[10];
+        zkb_plonk_vk_commitments(pk, xy, inf);
+        if (zkb_vk_file_write(vk_path, pk->n, (const uint64_t *)roots.data(), pk->pi_pos.size(), xy, inf) != ZKB_OK)
+            ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_save_keys: cannot write the VerifierKey file");
+    }
     return ZKB_OK;
 }
 

@@ -23,6 +23,10 @@ class GpuKZG10:
         """powers_of_g: (n, 8) uint64 host array or CUDA tensor of affine G1 points (Montgomery x||y)."""
         self.ctx.srs_load(powers_of_g)
 
+    def load_committer_key_file(self, path, max_points=0):
+        """deserialize_from_file::<CommitterKey>(ck_path) (bin/src/parser.rs:5-14): ark-serialize unchecked bytes."""
+        self.ctx.srs_load_ck_file(path, max_points)
+
     def supported_degree(self):
         return self.ctx.srs_size() - 1
 

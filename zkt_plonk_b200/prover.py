@@ -558,10 +558,33 @@ class NativeProver:
     """The same setup / prove behind the two C-ABI calls zkb_plonk_setup / zkb_plonk_prove (csrc/prover.cu): what a
     Rust FFI crate would call with the composer's vectors.  The committer key must be resident in `ctx`."""
 
-    def __init__(self, ctx, circuit):
+    def __init__(self, ctx, circuit, key_files=None, key_polys=None):
+        """key_files = (pk_path, vk_path): load the reference CLI's ProverKey / VerifierKey files (zkb_plonk_load_keys)
+        instead of running setup on the circuit's selector columns (zkb_plonk_setup).  key_polys = {name: (len, 4)
+        Montgomery coefficients}: the ProverKey's polynomials already in memory (zkb_plonk_pk_from_polys; the verifier
+        key's commitments are recomputed)."""
         import ctypes
         self.ctx, self.circuit = ctx, circuit
         lib = ctx._lib
+        h = ctypes.c_void_p()
+        if key_polys is not None:
+            from .keyfile import PK_ORDER
+            bufs = [np.ascontiguousarray(key_polys[name], dtype=np.uint64).reshape(-1, 4) for name in PK_ORDER]
+            keep = [b if b.shape[0] else np.zeros((1, 4), dtype=np.uint64) for b in bufs]
+            ptrs = (ctypes.c_void_p * 10)(*[b.ctypes.data for b in keep])
+            lens = (ctypes.c_size_t * 10)(*[b.shape[0] for b in bufs])
+            pos = list(circuit.pi.keys())
+            PP = (ctypes.c_size_t * max(len(pos), 1))(*pos)
+            ctx._check(lib.zkb_plonk_pk_from_polys(ctx._h, circuit.log_n, ptrs, lens, circuit.table_size, PP, len(pos), None, None,
+                                                   ctypes.byref(h)))
+            self._pk = h
+            return
+        if key_files is not None:
+            import os
+            ctx._check(lib.zkb_plonk_load_keys(ctx._h, os.fsencode(key_files[0]), os.fsencode(key_files[1]), circuit.table_size,
+                                               ctypes.byref(h)))
+            self._pk = h
+            return
         sel = [np.ascontiguousarray(circuit.selectors[k], dtype=np.uint64) for k in ("q_m", "q_l", "q_r", "q_o", "q_c", "q_lookup")]
         sig = [np.ascontiguousarray(x, dtype=np.uint64) for x in circuit.sigma]
         self._keep = sel + sig
@@ -569,9 +592,14 @@ class NativeProver:
         G = (ctypes.c_void_p * 3)(*[x.ctypes.data for x in sig])
         pos = list(circuit.pi.keys())
         PP = (ctypes.c_size_t * max(len(pos), 1))(*pos)
-        h = ctypes.c_void_p()
         ctx._check(lib.zkb_plonk_setup(ctx._h, circuit.log_n, S, G, circuit.table_size, PP, len(pos), ctypes.byref(h)))
         self._pk = h
+
+    def save_keys(self, pk_path, vk_path):
+        """Write the ProverKey / VerifierKey files `compile` writes (bin/src/main.rs:106-112)."""
+        import os
+        enc = lambda p: None if p is None else os.fsencode(p)
+        self.ctx._check(self.ctx._lib.zkb_plonk_save_keys(self.ctx._h, self._pk, enc(pk_path), enc(vk_path)))
 
     def set_transcript(self, name):
         """"merlin" (default) or "ethereum": which TranscriptProtocol later proofs use (zkb_plonk_pk_set_transcript)."""
