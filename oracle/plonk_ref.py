@@ -4,15 +4,15 @@
 integers, so that tests can run proof_system::prove (plonk-core/src/proof_system/prove.rs:59-470) entirely on the
 CPU and compare the proof bytes with the CUDA path.  `verify` restates Proof::verify
 (plonk-core/src/proof_system/proof.rs:285-503), including compute_r0 (:163-217) and
-compute_linearization_commitment (:220-282).  PC::check needs a BN254 pairing, which does not exist in this
-repository; because the synthetic SRS's trapdoor tau is known, the pairing equation
-e(W, tau*H) = e(C - v*G + z*W, H) is checked in G1 as  tau*W == C - v*G + z*W  (SonicKZG10::check's
-accumulate_elems / check_elems with no degree bounds and no hiding).  PARITY UNPINNED against the Rust binary: see
-zkb_oracle.c's header.
+compute_linearization_commitment (:220-282).  PC::check (SonicKZG10::check's accumulate_elems / check_elems with no
+degree bounds and no hiding) is available in two forms: with `cvk = (H, beta H)` it is the reference's own product of
+pairings e(C - v*G + z*W, H) * e(-W, beta*H) == 1 on the restated BN254 pairing (oracle/pairing.py); without it,
+because the synthetic SRS's trapdoor tau is known, the same equation is checked in G1 as  tau*W == C - v*G + z*W.
+PARITY UNPINNED against the Rust binary: see zkb_oracle.c's header.
 """
 import numpy as np
 
-from oracle import cref, pyref
+from oracle import cref, pairing, pyref
 from zkt_plonk_b200 import field
 from zkt_plonk_b200.prover import (P, Poly, Proof, fr_to_limbs, ints_to_mont_array, limbs_to_fr, mont_array_to_ints,
                                     point_to_ints)
@@ -143,19 +143,30 @@ def _lin_comb_points(points, scalars):
     return acc
 
 
-def _kzg_check(commits, point, values, w, eta, tau):
-    """SonicKZG10::check with the trapdoor in place of the pairing: tau * W == sum eta^i C_i - (sum eta^i v_i) G + z W."""
+def make_cvk(tau):
+    """The G2 half of sonic_pc::VerifierKey for a synthetic SRS: (h, beta_h) = (H, tau * H), H the alt_bn128 G2 generator
+    (KZG10::setup draws h at random; any h gives the same accept / reject decisions)."""
+    return (pairing.G2_GEN, pairing.g2_mul(tau % P, pairing.G2_GEN))
+
+
+def _kzg_check(commits, point, values, w, eta, tau, cvk=None):
+    """SonicKZG10::check for one query point: A = sum eta^i C_i - (sum eta^i v_i) G + z W, then
+    e(A, h) * e(-W, beta_h) == 1 (cvk given) or, with the trapdoor in place of the pairing, tau * W == A."""
     chal = [pow(eta, i, P) for i in range(len(commits))]
     c = _lin_comb_points(commits, chal)
     v = sum(e * x for e, x in zip(chal, values)) % P
     rhs = pyref.g1_add(pyref.g1_add(c, pyref.g1_neg(pyref.g1_mul(v, pyref.G1_GEN))), pyref.g1_mul(point, w) if w else None)
+    if cvk is not None:
+        return pairing.pairing_product_is_one([(rhs, cvk[0]), (pyref.g1_neg(w) if w else None, cvk[1])])
     lhs = pyref.g1_mul(tau, w) if w else None
     return lhs == rhs
 
 
-def verify(vk, proof, pub_inputs, tau, transcript="merlin"):
+def verify(vk, proof, pub_inputs, tau=None, transcript="merlin", cvk=None):
     """Proof::verify (proof.rs:285-503).  Returns 0 if accepted, else the failing step (1 or 2).
-    transcript: "merlin" (transcript.rs:49-109) or "ethereum" (gadgets/src/transcript.rs:8-90)."""
+    transcript: "merlin" (transcript.rs:49-109) or "ethereum" (gadgets/src/transcript.rs:8-90).
+    cvk = make_cvk(tau): PC::check by pairings, as the reference does; otherwise tau itself is needed."""
+    assert tau is not None or cvk is not None
     n = vk.n
     log_n = n.bit_length() - 1
     assert len(pub_inputs) == len(vk.pi_roots), "invalid length of public inputs"
@@ -205,12 +216,12 @@ def verify(vk, proof, pub_inputs, tau, transcript="merlin"):
         tr.append_scalar(k + "_eval", E[k])
     eta = tr.challenge_scalar("eta")
     ok1 = _kzg_check([r_commit, C["a"], C["b"], C["c"], V["sigma1"], V["sigma2"], V["q_lookup"], C["t"], C["h2"]], xi,
-                     [r0, E["a"], E["b"], E["c"], E["sigma1"], E["sigma2"], E["q_lookup"], E["t"], E["h2"]], proof.aw, eta, tau)
+                     [r0, E["a"], E["b"], E["c"], E["sigma1"], E["sigma2"], E["q_lookup"], E["t"], E["h2"]], proof.aw, eta, tau, cvk)
     if not ok1:
         return 1
     w_n = field.root_of_unity(log_n)
     ok2 = _kzg_check([C["z1"], C["z2"], C["t"], C["h1"]], xi * w_n % P,
-                     [E["z1_next"], E["z2_next"], E["t_next"], E["h1_next"]], proof.saw, eta, tau)
+                     [E["z1_next"], E["z2_next"], E["t_next"], E["h1_next"]], proof.saw, eta, tau, cvk)
     return 0 if ok2 else 2
 
 

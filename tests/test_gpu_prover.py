@@ -48,6 +48,7 @@ def test_gpu_proof_is_byte_identical_and_verifies(ctx, log_n, fixed_base):
     oproof = prover.prove(obe, opk, ovk, circ, blinders)
     assert gproof.to_bytes() == oproof.to_bytes()
     assert plonk_ref.verify(gvk, gproof, list(circ.pi.values()), TAU) == 0
+    assert plonk_ref.verify(gvk, gproof, list(circ.pi.values()), cvk=plonk_ref.make_cvk(TAU)) == 0     # PC::check by pairings
     ctx.srs_precompute(-1)
 
 

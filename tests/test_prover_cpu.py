@@ -78,6 +78,10 @@ def test_prove_verify_roundtrip_on_oracle_backend(log_n):
     assert len(raw) == 11 * 32 + 2 * 33 + 12 * 32
     pub = list(circ.pi.values())
     assert plonk_ref.verify(vk, proof, pub, TAU) == 0
+    # the reference's own PC::check: a product of two pairings per opening, no trapdoor involved
+    cvk = plonk_ref.make_cvk(TAU)
+    assert plonk_ref.verify(vk, proof, pub, cvk=cvk) == 0
+    assert plonk_ref.verify(vk, proof, pub, cvk=plonk_ref.make_cvk(TAU + 1)) == 1
     # same inputs, same bytes; different blinders, different proof that still verifies
     assert prover.prove(be, pk, vk, circ, blinders).to_bytes() == raw
     other = prover.prove(be, pk, vk, circ, [rnd.randrange(P) for _ in range(19)])
@@ -85,11 +89,14 @@ def test_prove_verify_roundtrip_on_oracle_backend(log_n):
     # tampering: an evaluation, a public input, a commitment
     bad = prover.Proof(dict(proof.commits), proof.aw, proof.saw, dict(proof.evals))
     bad.evals["a"] = (bad.evals["a"] + 1) % P
-    assert plonk_ref.verify(vk, bad, pub, TAU) != 0
+    assert plonk_ref.verify(vk, bad, pub, TAU) != 0 and plonk_ref.verify(vk, bad, pub, cvk=cvk) != 0
     assert plonk_ref.verify(vk, proof, [(pub[0] + 1) % P] + pub[1:], TAU) != 0
     bad = prover.Proof(dict(proof.commits), proof.aw, proof.saw, dict(proof.evals))
     bad.commits["z1"] = proof.commits["z2"]
-    assert plonk_ref.verify(vk, bad, pub, TAU) != 0
+    assert plonk_ref.verify(vk, bad, pub, TAU) != 0 and plonk_ref.verify(vk, bad, pub, cvk=cvk) != 0
+    bad = prover.Proof(dict(proof.commits), proof.aw, proof.saw, dict(proof.evals))
+    bad.evals["h1_next"] = (bad.evals["h1_next"] + 1) % P                  # only the second opening sees this one
+    assert plonk_ref.verify(vk, bad, pub, cvk=cvk) != 0
 
 
 def test_prove_verify_with_the_ethereum_transcript():
