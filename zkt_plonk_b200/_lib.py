@@ -8,7 +8,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkb200.so")
+# ZKB200_LIB selects another build of the same sources (e.g. the experimental libzkb200_sqr.so); never a fallback.
+LIB_PATH = os.environ.get("ZKB200_LIB") or os.path.join(_HERE, "libzkb200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "zkb200.h")
 
 ZKB_OK, ZKB_ERR_INVALID, ZKB_ERR_DOMAIN, ZKB_ERR_CUDA, ZKB_ERR_NO_SRS, ZKB_ERR_OOM = 0, -1, -2, -3, -4, -5

@@ -44,7 +44,7 @@ __device__ __noinline__ g1x_t g1x_double_affine(const g1a_t &p) {
     fe_t xx = fsqr<Q>(p.x);
     fe_t m = fadd<Q>(fdbl<Q>(xx), xx);
     r.x = fsub<Q>(fsub<Q>(fsqr<Q>(m), s), s);
-    r.y = fsub<Q>(fmul<Q>(m, fsub<Q>(s, r.x)), fmul<Q>(w, p.y));
+    r.y = fmsub2<Q>(m, fsub<Q>(s, r.x), w, p.y);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -61,7 +61,7 @@ __device__ __noinline__ g1x_t g1x_double(const g1x_t &p) {
     fe_t xx = fsqr<Q>(p.x);
     fe_t m = fadd<Q>(fdbl<Q>(xx), xx);
     r.x = fsub<Q>(fsub<Q>(fsqr<Q>(m), s), s);
-    r.y = fsub<Q>(fmul<Q>(m, fsub<Q>(s, r.x)), fmul<Q>(w, p.y));
+    r.y = fmsub2<Q>(m, fsub<Q>(s, r.x), w, p.y);
     r.zz = fmul<Q>(v, p.zz);
     r.zzz = fmul<Q>(w, p.zzz);
     return r;
@@ -84,7 +84,7 @@ __device__ __forceinline__ void g1x_add_mixed(g1x_t &acc, const g1a_t &q) {
     fe_t ppp = fmul<Q>(p, pp);
     fe_t qq = fmul<Q>(acc.x, pp);
     fe_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(fsqr<Q>(r), ppp), qq), qq);
-    fe_t y3 = fsub<Q>(fmul<Q>(r, fsub<Q>(qq, x3)), fmul<Q>(acc.y, ppp));
+    fe_t y3 = fmsub2<Q>(r, fsub<Q>(qq, x3), acc.y, ppp);
     acc.x = x3;
     acc.y = y3;
     acc.zz = fmul<Q>(acc.zz, pp);
@@ -110,7 +110,7 @@ __device__ __forceinline__ void g1x_add(g1x_t &acc, const g1x_t &q) {
     fe_t ppp = fmul<Q>(p, pp);
     fe_t qq = fmul<Q>(u1, pp);
     fe_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(fsqr<Q>(r), ppp), qq), qq);
-    fe_t y3 = fsub<Q>(fmul<Q>(r, fsub<Q>(qq, x3)), fmul<Q>(s1, ppp));
+    fe_t y3 = fmsub2<Q>(r, fsub<Q>(qq, x3), s1, ppp);
     acc.x = x3;
     acc.y = y3;
     acc.zz = fmul<Q>(fmul<Q>(acc.zz, q.zz), pp);

@@ -249,8 +249,197 @@ __device__ __forceinline__ fe_t fmul(const fe_t &a, const fe_t &b) {
     return r;
 }
 
+// ------------------------------------------------------------------ dedicated squaring
+// Triangular rows: with d = 2a (a < 2^254, so d fits 8 limbs), row i adds
+//     a_i * [ a_i, d_{i+1} & ~1, d_{i+2}, ..., d_7 ]   at relative limbs i .. 7
+// (d_{i+1} & ~1 = a_{i+1} << 1: the bit that 2a carries in from a_i belongs to a row already done), i.e. every
+// off-diagonal product once, doubled, plus the diagonal: 36 wide products instead of 64 in the a*a half; the
+// word-serial reduction (64 + 8) is unchanged.  Same even / odd accumulator layout as fmul, so each row is again
+// one carry chain per accumulator; a chain that starts above pair 0 first ripples the incoming carry through the
+// limbs below it (ALU pipe, which the product leaves idle).  tools/sqr/model.py replays these chains limb by limb
+// and asserts that every dropped carry is zero.
+//
+// K0 = first pair of the chain.  Operands as in row_mad_cin / row_mad_cout; unused multiplicands are ignored.
+template <int K0>
+__device__ __forceinline__ void tri_mad_cin(uint32_t &lo, uint32_t x, uint32_t (&acc)[8],
+                                            uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t b) {
+    if (K0 == 0) {
+        row_mad_cin(lo, x, acc, m0, m1, m2, m3, b);
+    } else if (K0 == 1) {
+        asm("add.cc.u32 %8, %8, %9;\n\t"
+            "addc.cc.u32 %0, %0, 0;\n\t"            "addc.cc.u32 %1, %1, 0;\n\t"
+            "madc.lo.cc.u32 %2, %11, %14, %2;\n\t" "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+            "madc.lo.cc.u32 %4, %12, %14, %4;\n\t" "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+            "madc.lo.cc.u32 %6, %13, %14, %6;\n\t" "madc.hi.u32 %7, %13, %14, %7;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+              "+r"(lo)
+            : "r"(x), "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+    } else if (K0 == 2) {
+        asm("add.cc.u32 %8, %8, %9;\n\t"
+            "addc.cc.u32 %0, %0, 0;\n\t"            "addc.cc.u32 %1, %1, 0;\n\t"
+            "addc.cc.u32 %2, %2, 0;\n\t"            "addc.cc.u32 %3, %3, 0;\n\t"
+            "madc.lo.cc.u32 %4, %12, %14, %4;\n\t" "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+            "madc.lo.cc.u32 %6, %13, %14, %6;\n\t" "madc.hi.u32 %7, %13, %14, %7;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+              "+r"(lo)
+            : "r"(x), "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+    } else {
+        asm("add.cc.u32 %8, %8, %9;\n\t"
+            "addc.cc.u32 %0, %0, 0;\n\t"            "addc.cc.u32 %1, %1, 0;\n\t"
+            "addc.cc.u32 %2, %2, 0;\n\t"            "addc.cc.u32 %3, %3, 0;\n\t"
+            "addc.cc.u32 %4, %4, 0;\n\t"            "addc.cc.u32 %5, %5, 0;\n\t"
+            "madc.lo.cc.u32 %6, %13, %14, %6;\n\t" "madc.hi.u32 %7, %13, %14, %7;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+              "+r"(lo)
+            : "r"(x), "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+    }
+}
+
+template <int K0>
+__device__ __forceinline__ void tri_mad_cout(uint32_t (&acc)[8], uint32_t &top,
+                                             uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t b) {
+    if (K0 == 0) {
+        row_mad_cout(acc, top, m0, m1, m2, m3, b);
+    } else if (K0 == 1) {
+        asm("mad.lo.cc.u32 %2, %10, %13, %2;\n\t"   "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"  "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"  "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32 %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+              "+r"(top)
+            : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+    } else if (K0 == 2) {
+        asm("mad.lo.cc.u32 %4, %11, %13, %4;\n\t"   "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"  "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32 %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+              "+r"(top)
+            : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+    } else if (K0 == 3) {
+        asm("mad.lo.cc.u32 %6, %12, %13, %6;\n\t"   "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32 %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+              "+r"(top)
+            : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+    }                                                  // K0 == 4: no even limb left in this row
+}
+
+// Montgomery reduction row + one-limb shift shared by fmul's and fsqr's rows.
 template <class P>
-__device__ __forceinline__ fe_t fsqr(const fe_t &a) { return fmul<P>(a, a); }
+__device__ __forceinline__ void mont_row_reduce(uint32_t (&E)[8], uint32_t (&O)[8], uint32_t &x) {
+    uint32_t m = E[0] * P::INV;
+    row_mad(O, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+    row_mad_cout(E, O[7], P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+    x = E[1];
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = O[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) O[k] = E[k + 2];
+    O[6] = 0; O[7] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) E[k] = t[k];
+}
+
+template <class P, int I>
+__device__ __forceinline__ void sqr_row(uint32_t (&E)[8], uint32_t (&O)[8], uint32_t &x, const uint32_t (&a)[8], const uint32_t (&d)[8]) {
+    // v[j] for j >= I: a_I, d_{I+1} & ~1, d_{I+2} ...; entries below I are never read by the chains
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < I ? 0u : (j == I ? a[I] : (j == I + 1 ? (d[j] & ~1u) : d[j]));
+    tri_mad_cin<I / 2>(E[0], x, O, v[1], v[3], v[5], v[7], a[I]);
+    tri_mad_cout<(I + 1) / 2>(E, O[7], v[0], v[2], v[4], v[6], a[I]);
+    mont_row_reduce<P>(E, O, x);
+}
+
+template <class P>
+__device__ __forceinline__ fe_t fsqr_tri(const fe_t &a) {
+    uint32_t d[8], E[8], O[8], x = 0;
+    d[0] = a.v[0] << 1;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) d[j] = __funnelshift_l(a.v[j - 1], a.v[j], 1);
+    row_mul(E, a.v[0], d[2], d[4], d[6], a.v[0]);
+    row_mul(O, d[1] & ~1u, d[3], d[5], d[7], a.v[0]);
+    mont_row_reduce<P>(E, O, x);
+    sqr_row<P, 1>(E, O, x, a.v, d);
+    sqr_row<P, 2>(E, O, x, a.v, d);
+    sqr_row<P, 3>(E, O, x, a.v, d);
+    sqr_row<P, 4>(E, O, x, a.v, d);
+    sqr_row<P, 5>(E, O, x, a.v, d);
+    sqr_row<P, 6>(E, O, x, a.v, d);
+    sqr_row<P, 7>(E, O, x, a.v, d);
+    fe_t r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"  "addc.cc.u32 %1, %9, %17;\n\t"  "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t" "addc.cc.u32 %4, %12, %20;\n\t" "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t" "addc.u32 %7, %15, %23;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+          "r"(x), "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+    reduce_once<P>(r.v);
+    return r;
+}
+
+// Every fsqr is the triangular squaring (bucket accumulation: 2 of the 10 products of an XYZZ mixed addition;
+// inversions: 254 of ~380 products).  Measured on B200 (profiles/r01f): bit-exact, bucket accumulation 2.7 % faster.
+// -DZKB_DEDICATED_SQR=0 restores the plain product for A/B measurements.
+#ifndef ZKB_DEDICATED_SQR
+#define ZKB_DEDICATED_SQR 1
+#endif
+template <class P>
+__device__ __forceinline__ fe_t fsqr(const fe_t &a) {
+#if ZKB_DEDICATED_SQR
+    return fsqr_tri<P>(a);
+#else
+    return fmul<P>(a, a);
+#endif
+}
+
+// (a*b + c*d) * R^-1 mod p with ONE word-serial reduction: the rows of both products are added before each
+// reduction row (200 instead of 272 multiply-adds).  Intermediate T < a + c + p < 3p < 2^256; the final value is
+// below p/4 + p/4 + p, so one conditional subtraction still normalises it (tools/sqr/model.py replays the chains).
+template <class P>
+__device__ __forceinline__ fe_t fmadd2(const fe_t &a, const fe_t &b, const fe_t &c, const fe_t &d) {
+    uint32_t E[8], O[8], x = 0;
+    row_mul(E, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+    row_mul(O, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+    row_mad(O, c.v[1], c.v[3], c.v[5], c.v[7], d.v[0]);
+    row_mad_cout(E, O[7], c.v[0], c.v[2], c.v[4], c.v[6], d.v[0]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i) {
+            row_mad_cin(E[0], x, O, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+            row_mad_cout(E, O[7], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+            row_mad(O, c.v[1], c.v[3], c.v[5], c.v[7], d.v[i]);
+            row_mad_cout(E, O[7], c.v[0], c.v[2], c.v[4], c.v[6], d.v[i]);
+        }
+        mont_row_reduce<P>(E, O, x);
+    }
+    fe_t r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"  "addc.cc.u32 %1, %9, %17;\n\t"  "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t" "addc.cc.u32 %4, %12, %20;\n\t" "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t" "addc.u32 %7, %15, %23;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+          "r"(x), "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+    reduce_once<P>(r.v);
+    return r;
+}
+
+// a*b - c*d: the second product enters as (p - c)*d.  Used for Y3 = R (Q - X3) - Y1 PPP of every XYZZ addition and
+// doubling (ec.cuh): 9 reductions instead of 10 per mixed addition.  Measured on B200 (profiles/r01g): bit-exact, bucket
+// accumulation 7.4 % faster (ptxas also settles on 128 registers: 4 CTAs per SM instead of 3).
+// -DZKB_FUSED_MADD2=0 restores the two separate products for A/B measurements.
+#ifndef ZKB_FUSED_MADD2
+#define ZKB_FUSED_MADD2 1
+#endif
+template <class P>
+__device__ __forceinline__ fe_t fmsub2(const fe_t &a, const fe_t &b, const fe_t &c, const fe_t &d) {
+#if ZKB_FUSED_MADD2
+    return fmadd2<P>(a, b, fneg<P>(c), d);
+#else
+    return fsub<P>(fmul<P>(a, b), fmul<P>(c, d));
+#endif
+}
 
 // a * small constant k (k <= 16) by an addition chain -- used for K1 = 7, K2 = 13, 3*X^2 ...
 template <class P>
