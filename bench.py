@@ -339,9 +339,11 @@ def run_main(args):
     ms_per_step = total_ms / args.steps
     value = world * n * args.steps / (total_ms * 1e-3)
     peaks, peak_src = measured_peaks()
-    # roofline of the dominant kernel: one mixed addition per non-zero digit (n * W, minus a 2^-c fraction),
-    # 10 Fq products each (XYZZ madd-2008-s: 8M + 2S), 136 32x32->64 MACs per product, and an IMAD.WIDE MAC
-    # occupies the fma pipe for two 32-bit IMAD issue slots (measured: zkb_bench_int mode 1 vs 0).
+    # roofline of the dominant kernel: one mixed addition per non-zero digit (n * W, minus a 2^-c fraction) of
+    # XYZZ madd-2008-s (8M + 2S).  32x32->64 multiply-adds of the algorithm as implemented: 136 per Montgomery product
+    # (8x8 + 8x8 + 8), 108 per squaring (36 + 64 + 8: off-diagonal products once), 200 for Y3 = R(Q - X3) - Y1*PPP (two
+    # products, ONE reduction) -> 6 * 136 + 2 * 108 + 200 = 1232 per addition (1360 before those two changes).  An
+    # IMAD.WIDE MAC occupies the fma pipe for two 32-bit IMAD issue slots (measured: zkb_bench_int mode 1 vs 0).
     # same MSM without the fixed-base tables (arbitrary-bases path: per-window buckets + host Horner fold)
     plain_ms = None
     if not args.no_precompute:
@@ -360,7 +362,8 @@ def run_main(args):
             ts.append(e0.elapsed_time(e1))
         plain_ms = statistics.mean(ts)
     adds = n * tm["windows"]
-    int_ops = adds * 10 * 136 * 2
+    macs_per_add = 6 * 136 + 2 * 108 + 200
+    int_ops = adds * macs_per_add * 2
     acc_s = statistics.mean(acc_ms) * 1e-3
     roofline = {"bound": "int32-imad (tensor cores unused: multi-precision integer work)", "kernel": "msm_accumulate_kernel",
                 "achieved": int_ops / acc_s / 1e12, "peak": int_peak / 1e12, "unit": "T int32 IMAD/s",
@@ -368,7 +371,7 @@ def run_main(args):
                 "traffic": ncu_traffic("msm_accumulate_kernel", f"2^{log_n}" + ("" if not args.no_precompute else "_plain")),
                 "peak_source": "measured live by zkb_bench_int (no integer peak in MEASURED_PEAKS.json)",
                 "kernel_ms": acc_s * 1e3, "kernel_share_of_step": acc_s * 1e3 / ms_per_step,
-                "algorithmic_ops_per_launch": int_ops, "window_bits": tm["c"], "windows": tm["windows"]}
+                "algorithmic_ops_per_launch": int_ops, "macs_per_mixed_addition": macs_per_add, "window_bits": tm["c"], "windows": tm["windows"]}
 
     # ---- extra: the NTT half of the metric (Fr NTT elems/s), one GPU, 2^22 (= 4n for a 2^20-gate circuit)
     extra = dict(prove_extra)

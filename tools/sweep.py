@@ -150,7 +150,7 @@ def sweep_msm():
             line = {"config": "msm", "log_n": ln, "n_gpus": world, "bases": mode, "ms": mean, "ms_min": best,
                     "points_per_s": n / (mean * 1e-3), "window_bits": tm["c"], "windows": tm["windows"],
                     "phases_ms_rank0": {k_: tm[k_] for k_ in ("sort_ms", "accumulate_ms", "heavy_ms", "reduce_ms", "total_ms")},
-                    "accumulate_imad_frac": adds * 10 * 136 * 2 / (tm["accumulate_ms"] * 1e-3) / INT_PEAK,
+                    "accumulate_imad_frac": adds * (6 * 136 + 2 * 108 + 200) * 2 / (tm["accumulate_ms"] * 1e-3) / INT_PEAK,
                     "group_adds_c_independent": n * 254 / ln}
             if mode == "tables":
                 line["table_build_s"] = t_build
