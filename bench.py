@@ -200,7 +200,7 @@ def run_reference(args):
                                    "not the arkworks binary"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ main arm
@@ -438,7 +438,7 @@ def run_main(args):
                       "reduce": tm["reduce_ms"], "device_total": tm["total_ms"]},
         "extra": extra,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -513,7 +513,26 @@ def run_prove_extra(device, log_n, dist, rank, world):
                     "(tests/test_gpu_sharded.py, tools/check_multigpu_prove.py)"}
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # Libraries loaded below write to fd 1 on their own (NCCL prints its version banner there when the box sets
+    # NCCL_DEBUG=VERSION): keep the original stdout for the JSON line only, send everything else to stderr.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
