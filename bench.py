@@ -64,6 +64,22 @@ def uniform_scalars(n, seed):
     return a
 
 
+def witness_like_scalars(n, seed):
+    """20 % zeros, 20 % ones, 20 % below 2^16, 40 % uniform -- the shape of selector, table and
+    evaluation-form polynomials (skewed bucket loads: giant buckets for 0 / 1, many empty ones)."""
+    sc = uniform_scalars(n, seed)
+    rng = np.random.default_rng(seed + 1)
+    kind = rng.random(n)
+    sc[kind < 0.2] = 0
+    ones = (kind >= 0.2) & (kind < 0.4)
+    sc[ones] = 0
+    sc[ones, 0] = 1
+    small = (kind >= 0.4) & (kind < 0.6)
+    sc[small] = 0
+    sc[small, 0] = rng.integers(0, 1 << 16, size=int(small.sum()), dtype=np.uint64)
+    return sc
+
+
 class ClockSampler:
     """SM clock and throttle reasons of one GPU sampled every ~5 ms through NVML (pynvml) on a thread while the timed
     region runs; falls back to `nvidia-smi -lms 100` (B200_PROFILING.md clocks line) when NVML is not importable.
@@ -317,6 +333,29 @@ def run_main(args):
         e2e_t = float(t.item())
     clocks = sampler.stop()
 
+    # ---- extra: the same MSM on witness-like (skewed) scalars, device-timed like `value`
+    skewed = None
+    if world == 1:
+        try:
+            d_sk = torch.from_numpy(witness_like_scalars(n, 555).view(np.int64)).to(dev)
+            for _ in range(3):
+                ctx.msm(d_sk)
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ctx.msm(d_sk)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            skewed = {"ms_per_step": statistics.mean(ts), "points_per_s": n / (statistics.mean(ts) * 1e-3),
+                      "scalars": "20 % zero, 20 % one, 20 % below 2^16, 40 % uniform in [0, r)"}
+            del d_sk
+        except Exception as e:                                    # never lose the headline line over an extra
+            skewed = {"error": repr(e)}
+
     # ---- extra: the prover path end to end (the "withdraw prove ms" part of the metric).  N = 1: synthetic circuit of
     # the withdraw circuit's size n = 2^18 and of BASELINE.json's 2^20 gates; N > 1: the 2^20-gate
     # proof with every commitment sharded by point range over the N GPUs (SPMD, csrc/comm.cu).  All ranks take part.
@@ -377,7 +416,7 @@ def run_main(args):
     extra = dict(prove_extra)
     extra.update({"msm_fixed_base_tables": {"enabled": not args.no_precompute, "build_seconds_once_per_srs": t_pre,
                                        "table_bytes": 0 if args.no_precompute else n * 64 * tm["windows"]},
-             "msm_plain_bases_ms_per_step": plain_ms})
+             "msm_plain_bases_ms_per_step": plain_ms, "msm_witness_like_scalars": skewed})
     try:
         ln = 22 if log_n >= 20 else log_n + 2
         x = torch.from_numpy(uniform_scalars(1 << ln, 5).view(np.int64)).to(dev)

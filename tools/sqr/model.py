@@ -88,6 +88,24 @@ def fmul2(a, b, c2, d, p):
     return finish(E, O, x, p)
 
 
+def fmaddn(pairs, p):
+    """sum of up to four products with one reduction (ff.cuh fmadd3 / fmadd4): intermediate T < 4p + p < 2^256 (p < 0.19 * 2^256),
+    final T < 4 * p/4 * 0.76 + p < 2p."""
+    inv = (-pow(p, -1, 1 << 32)) & M32
+    E, O, x = [0] * 8, [0] * 8, 0
+    ls = [(limbs(a), limbs(b)) for a, b in pairs]
+    for i in range(8):
+        t = E[0] + x
+        E[0], c = t & M32, t >> 32
+        for k, (al, bl) in enumerate(ls):
+            assert chain_mad(O, 0, [al[1], al[3], al[5], al[7]], bl[i], c if k == 0 else 0) == 0
+            c2 = chain_mad(E, 0, [al[0], al[2], al[4], al[6]], bl[i])
+            O[7] += c2
+            assert O[7] <= M32
+        E, O, x = reduce_and_shift(E, O, p, inv)
+    return finish(E, O, x, p)
+
+
 def carry_ripple(acc, upto, c):
     """addc.cc chain through acc[0..upto) with incoming carry c; returns the carry that reaches acc[upto]."""
     for k in range(upto):
@@ -140,6 +158,12 @@ def main():
             c2 = rnd.choice(vals[:14]) if rnd.random() < 0.2 else rnd.randrange(p)
             d = rnd.choice(vals[:14]) if rnd.random() < 0.2 else rnd.randrange(p)
             assert fmul2(a, b, c2, d, p) == (a * b + c2 * d) * rinv % p
+            for npairs in (3, 4):
+                prs = [(rnd.choice(vals[:14]) if rnd.random() < 0.3 else rnd.randrange(p),
+                        rnd.choice(vals[:14]) if rnd.random() < 0.3 else rnd.randrange(p)) for _ in range(npairs)]
+                assert fmaddn(prs, p) == sum(u * v for u, v in prs) * rinv % p
+        assert fmaddn([(p - 1, p - 1)] * 4, p) == 4 * (p - 1) * (p - 1) * rinv % p
+        assert fmaddn([(p - 1, p - 1)] * 3 + [(0, 0)], p) == 3 * (p - 1) * (p - 1) * rinv % p
         for a in edge:                                       # all four operands at their extremes
             for b in edge:
                 assert fmul2(a, b, p - 1, p - 1, p) == (a * b + (p - 1) * (p - 1)) * rinv % p

@@ -425,6 +425,43 @@ __device__ __forceinline__ fe_t fmadd2(const fe_t &a, const fe_t &b, const fe_t 
     return r;
 }
 
+// sum_{k<N} a[k]*b[k] * R^-1 mod p for N <= 4 with one reduction (p < 0.19 * 2^256: intermediate T < 4p + p < 2^256,
+// final T < 4 * 0.19 p + p < 2p; tools/sqr/model.py fmaddn asserts the dropped carries for N = 3, 4).
+template <class P, int N>
+__device__ __forceinline__ fe_t fmaddn(const fe_t (&a)[N], const fe_t (&b)[N]) {
+    static_assert(N >= 1 && N <= 4, "at most four products share a reduction");
+    uint32_t E[8], O[8], x = 0;
+    row_mul(E, a[0].v[0], a[0].v[2], a[0].v[4], a[0].v[6], b[0].v[0]);
+    row_mul(O, a[0].v[1], a[0].v[3], a[0].v[5], a[0].v[7], b[0].v[0]);
+#pragma unroll
+    for (int k = 1; k < N; ++k) {
+        row_mad(O, a[k].v[1], a[k].v[3], a[k].v[5], a[k].v[7], b[k].v[0]);
+        row_mad_cout(E, O[7], a[k].v[0], a[k].v[2], a[k].v[4], a[k].v[6], b[k].v[0]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i) {
+            row_mad_cin(E[0], x, O, a[0].v[1], a[0].v[3], a[0].v[5], a[0].v[7], b[0].v[i]);
+            row_mad_cout(E, O[7], a[0].v[0], a[0].v[2], a[0].v[4], a[0].v[6], b[0].v[i]);
+#pragma unroll
+            for (int k = 1; k < N; ++k) {
+                row_mad(O, a[k].v[1], a[k].v[3], a[k].v[5], a[k].v[7], b[k].v[i]);
+                row_mad_cout(E, O[7], a[k].v[0], a[k].v[2], a[k].v[4], a[k].v[6], b[k].v[i]);
+            }
+        }
+        mont_row_reduce<P>(E, O, x);
+    }
+    fe_t r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"  "addc.cc.u32 %1, %9, %17;\n\t"  "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t" "addc.cc.u32 %4, %12, %20;\n\t" "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t" "addc.u32 %7, %15, %23;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+          "r"(x), "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+    reduce_once<P>(r.v);
+    return r;
+}
+
 // a*b - c*d: the second product enters as (p - c)*d.  Used for Y3 = R (Q - X3) - Y1 PPP of every XYZZ addition and
 // doubling (ec.cuh): 9 reductions instead of 10 per mixed addition.  Measured on B200 (profiles/r01g): bit-exact, bucket
 // accumulation 7.4 % faster (ptxas also settles on 128 registers: 4 CTAs per SM instead of 3).

@@ -256,9 +256,73 @@ struct QuotArgs {
     uint32_t xtab_s, n4;
     uint32_t i_lo, i_hi;                                                               // elements [i_lo, i_hi) of the coset (a slice when several GPUs share the round)
     fe_t alpha, alpha2, alpha3, alpha4, alpha5, beta, gamma, delta, eps, opd, eopd, gen, k1, k2;
+    fe_t a3opd;                                                                        // alpha^3 (1 + delta)
     fe_t zh_inv[4];                                                                    // 1 / zh on the coset, by i mod 4
 };
 
+// ZKB_QUOT_FUSED: the same values with fewer multiplier slots -- sums of products share ONE Montgomery reduction
+// (fmaddn), the two L1 terms share a chain, K1 = 7 / K2 = 13 are addition chains on the ALU pipe, alpha^3 (1 + delta) and
+// the coset generator come pre-multiplied from the host (the x table's high half is scaled by g).  Every value is the
+// canonical residue of the same field expression, so the output is bit-identical to the plain kernel below.
+// Measured on B200 (profiles/r01j): 2.71 -> 2.06 ms at n = 2^20 (4 Mi elements), same SHA-256 of the output, polynomial
+// and prover suites bit-exact.  -DZKB_QUOT_FUSED=0 restores the plain kernel for A/B measurements.
+#ifndef ZKB_QUOT_FUSED
+#define ZKB_QUOT_FUSED 1
+#endif
+#if ZKB_QUOT_FUSED
+__global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotArgs p, uint4 *out) {
+    uint32_t i = p.i_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.i_hi) return;
+    uint32_t j = i + 4 < p.n4 ? i + 4 : i + 4 - p.n4;           // "next": x * w_n  (quotient_poly.rs:53-94)
+    const size_t I = 2 * (size_t)i, J = 2 * (size_t)j;
+    fe_t a = fload_ro(p.a + I), b = fload_ro(p.b + I), c = fload_ro(p.c + I);
+    // ---- arithmetic gate (keys/arithmetic.rs:67-81): (a b) q_m + a q_l + b q_r + c q_o under one reduction
+    fe_t acc;
+    {
+        const fe_t u[4] = {fmul<F>(a, b), a, b, c};
+        const fe_t v[4] = {fload_ro(p.qm + I), fload_ro(p.ql + I), fload_ro(p.qr + I), fload_ro(p.qo + I)};
+        acc = fmaddn<F, 4>(u, v);
+    }
+    acc = fadd<F>(acc, fload_ro(p.qc + I));
+    acc = fadd<F>(acc, fload_ro(p.pi + I));
+    const fe_t l1 = fload_ro(p.l1 + I), z2 = fload_ro(p.z2 + I);
+    // ---- permutation (keys/permutation.rs:97-137) + both L1 terms: alpha^2 L1 (z1 - 1) + alpha^4 L1 (z2 - 1)
+    {
+        fe_t bx = fmul<F>(p.beta, pow2lvl(p.xtab, p.xtab_s, i));          // beta * g * w_4n^i (g sits in the table)
+        fe_t ag = fadd<F>(a, p.gamma), bg = fadd<F>(b, p.gamma), cg = fadd<F>(c, p.gamma);
+        fe_t z1 = fload_ro(p.z1 + I), z1n = fload_ro(p.z1 + J);
+        fe_t t0 = fmul<F>(p.alpha, z1);
+        t0 = fmul<F>(t0, fadd<F>(bx, ag));
+        t0 = fmul<F>(t0, fadd<F>(fmul_small<F>(bx, 7), bg));
+        fe_t f0 = fadd<F>(fmul_small<F>(bx, 13), cg);
+        fe_t t1 = fmul<F>(p.alpha, z1n);
+        t1 = fmul<F>(t1, fadd<F>(fmul<F>(p.beta, fload_ro(p.s1 + I)), ag));
+        t1 = fmul<F>(t1, fadd<F>(fmul<F>(p.beta, fload_ro(p.s2 + I)), bg));
+        fe_t f1 = fadd<F>(fmul<F>(p.beta, fload_ro(p.s3 + I)), cg);
+        fe_t inner = fmadd2<F>(fsub<F>(z1, fone<F>()), p.alpha2, fsub<F>(z2, fone<F>()), p.alpha4);
+        const fe_t u[3] = {t0, fneg<F>(t1), inner};
+        const fe_t v[3] = {f0, f1, l1};
+        acc = fadd<F>(acc, fmaddn<F, 3>(u, v));
+    }
+    // ---- lookup (keys/lookup.rs:81-122)
+    {
+        fe_t t = fload_ro(p.t + I), tn = fload_ro(p.t + J), h1 = fload_ro(p.h1 + I), h1n = fload_ro(p.h1 + J);
+        fe_t h2 = fload_ro(p.h2 + I), z2n = fload_ro(p.z2 + J);
+        fe_t u0 = fadd<F>(fmul<F>(fload_ro(p.qlk + I), c), p.eps);
+        fe_t v0 = fadd<F>(fadd<F>(fmul<F>(p.delta, tn), p.eopd), t);
+        fe_t t0 = fmul<F>(fmul<F>(p.a3opd, z2), u0);
+        fe_t u1 = fadd<F>(fadd<F>(fmul<F>(p.delta, h2), p.eopd), h1);
+        fe_t v1 = fadd<F>(fadd<F>(fmul<F>(p.delta, h1n), p.eopd), h2);
+        fe_t t1 = fmul<F>(fmul<F>(p.alpha3, z2n), u1);
+        fe_t t3 = fmul<F>(p.alpha5, fload_ro(p.qt + I));
+        const fe_t u[3] = {t0, fneg<F>(t1), t3};
+        const fe_t v[3] = {v0, v1, t};
+        acc = fadd<F>(acc, fmaddn<F, 3>(u, v));
+    }
+    // ---- divide by the vanishing polynomial: zh takes 4 values on the 4n coset (quotient_poly.rs:220-224)
+    fstore(out + I, fmul<F>(acc, p.zh_inv[i & 3]));
+}
+#else
 __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotArgs p, uint4 *out) {
     uint32_t i = p.i_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.i_hi) return;
@@ -307,6 +371,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ Q
     // ---- divide by the vanishing polynomial: zh takes 4 values on the 4n coset (quotient_poly.rs:220-224)
     fstore(out + I, fmul<F>(acc, p.zh_inv[i & 3]));
 }
+#endif  // ZKB_QUOT_FUSED
 
 // ============================================================================================ polynomial utilities
 constexpr int EV_K = 16;                       // coefficients per thread in poly_eval
@@ -535,6 +600,7 @@ int zkb_quotient_evals_range_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t ch
     p.alpha = dev_fe(al); p.alpha2 = dev_fe(al2); p.alpha3 = dev_fe(al3); p.alpha4 = dev_fe(al4); p.alpha5 = dev_fe(al5);
     p.beta = dev_fe(be); p.gamma = dev_fe(ga); p.delta = dev_fe(de); p.eps = dev_fe(ep_); p.opd = dev_fe(opd); p.eopd = dev_fe(eopd);
     p.gen = dev_fe(g); p.k1 = dev_fe(from_u64(7, FR)); p.k2 = dev_fe(from_u64(13, FR));
+    p.a3opd = dev_fe(mul(al3, opd, FR));
     // zh(x_i) = g^n * (w_4n^n)^(i mod 4) - 1 : four values (keys/mod.rs:114-116 evaluates x^n - 1 on the coset)
     Fe gn = pow_u64(g, (uint64_t)n, FR), w4 = pow_u64(fr_root_of_unity(log_n + 2), (uint64_t)n, FR), cur = gn;
     for (int k = 0; k < 4; ++k) {
@@ -542,7 +608,11 @@ int zkb_quotient_evals_range_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t ch
         cur = mul(cur, w4, FR);
     }
     const void *tab;
+#if ZKB_QUOT_FUSED
+    int rc = zkb_pow2lvl_cached(ctx, (9ull << 32) | ((log_n + 2) << 1), log_n + 2, fr_root_of_unity(log_n + 2), g, &tab, &p.xtab_s);   // g * w^e
+#else
     int rc = zkb_pow2lvl_cached(ctx, (2ull << 32) | ((log_n + 2) << 1), log_n + 2, fr_root_of_unity(log_n + 2), one(FR), &tab, &p.xtab_s);
+#endif
     if (rc) return rc;
     p.xtab = (const uint4 *)tab;
     if (hi > lo) quotient_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, ctx->stream>>>(p, (uint4 *)out_dev);
