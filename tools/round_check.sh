@@ -12,4 +12,4 @@ timeout 90 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag
 echo "smoke rc=$?" | tee -a gpurun_out/${tag}_smoke.log
 timeout 200 python bench.py > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench.err
 echo "bench rc=$?"
-tail -3 gpurun_out/${tag}_new_tests.log gpurun_out/${tag}_gpu_tests.log gpurun_out/${tag}_smoke.log
+tail -n 3 gpurun_out/${tag}_new_tests.log gpurun_out/${tag}_gpu_tests.log gpurun_out/${tag}_smoke.log
