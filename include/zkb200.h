@@ -196,6 +196,25 @@ ZKB_API int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t
                     const uint64_t *table, size_t table_len, const uint64_t *pi_values, const uint64_t *blinders,
                     uint8_t proof_out[802], float timings_ms[8]);
 
+/* ---- verifier: host code, no GPU needed ---------------------------------------------------------------- */
+/* Proof::verify (plonk-core/src/proof_system/proof.rs:285-503) for BN254 / KZG10: transcript replay, compute_r0 (:163-217),
+ * the 13-point linearisation commitment (:220-282) and PC::check twice (:441-502), each the product of two pairings
+ * e(sum eta^i C_i - (sum eta^i v_i) G + z W, h) * e(-W, beta_h) == 1 that SonicKZG10::check evaluates.
+ * n, pi_roots (Montgomery Fr), vk_xy / vk_inf: the VerifierKey (zkb_vk_file_read / zkb_plonk_vk_commitments layout);
+ * pub_inputs: one Montgomery Fr per root; proof: the 802 bytes of Proof's CanonicalSerialize; g2_h, g2_beta_h: the G2
+ * half of sonic_pc::VerifierKey, each x.c0 x.c1 y.c0 y.c1 (4 limbs each, Montgomery Fq: arkworks' in-memory G2Affine);
+ * transcript_kind as zkb_plonk_pk_set_transcript.
+ * Returns 0 = accepted, 1 / 2 = Error::ProofVerificationError { step }, negative = malformed input (a point off its
+ * curve, a non-canonical integer ...). */
+ZKB_API int zkb_plonk_verify(size_t n, const uint64_t *pi_roots_mont, size_t n_pi, const uint64_t vk_xy[80], const int vk_inf[10],
+                     const uint64_t *pub_inputs_mont, const uint8_t proof[802], const uint64_t g2_h[16], const uint64_t g2_beta_h[16],
+                     int transcript_kind);
+/* e(P, Q) on BN254 (optimal ate; ark-ec 0.3 PairingEngine::pairing): the 12 coefficients of the result in the basis
+ * 1, w, .., w^11 of Fq12 = Fq[w] / (w^12 - 18 w^6 + 82), canonical integers (4 limbs each).  For tests against
+ * oracle/pairing.py; zkb_pairing_product_is_one is what the verifier uses (PairingEngine::product_of_pairings == 1). */
+ZKB_API int zkb_pairing(const uint64_t g1_xy[8], const uint64_t g2_xy[16], uint64_t out_canonical[48]);
+ZKB_API int zkb_pairing_product_is_one(const uint64_t *g1_xy, const uint64_t *g2_xy, size_t count, int *is_one);
+
 /* ---- the reference CLI's key files ---------------------------------------------------------------------- */
 /* `compile` writes ck / cvk / pk / epk / vk with ark-serialize 0.3 serialize_unchecked (bin/src/parser.rs:16-29,
  * main.rs:96-113); `prove-withdraw` reads them back before every proof (parser.rs:5-14, main.rs:274-281).  Byte

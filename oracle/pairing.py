@@ -232,3 +232,72 @@ def pairing_product_is_one(pairs):
     for p1, q2 in pairs:
         f = f12_mul(f, miller_loop(q2, p1))
     return final_exponentiation(f) == F12_ONE
+
+
+# ---- the same Miller loop with the G2 arithmetic kept on the twist (Fq2) and sparse lines: the shape of the C++ verifier
+# (csrc/verify.cu), which tests compare against the generic loop above value for value.
+def f2_conj(a):
+    return (a[0], (-a[1]) % Q)
+
+
+def f2_pow(a, e):
+    acc = (1, 0)
+    while e:
+        if e & 1:
+            acc = f2_mul(acc, a)
+        a = f2_mul(a, a)
+        e >>= 1
+    return acc
+
+
+XI = (9, 1)
+FROB_X = f2_pow(XI, (Q - 1) // 3)                 # (w^2)^(q-1): x-coordinate factor of the q-power Frobenius on the twist
+FROB_Y = f2_pow(XI, (Q - 1) // 2)                 # (w^3)^(q-1)
+FROB2_X = f2_pow(XI, (Q * Q - 1) // 3)            # q^2-power: an element of Fq (a cube root of unity); the y factor is -1
+
+
+def embed(a):
+    """Fq2 -> Fq12 coefficients (two of them): a0 + a1 i = (a0 - 9 a1) + a1 w^6."""
+    return ((a[0] - 9 * a[1]) % Q, a[1])
+
+
+def sparse_line(lam, xr, yr, p1):
+    """Line through the untwisted (xr, yr) with slope embed(lam) w, evaluated at p1 = (xp, yp) in E(Fq):
+    -yp + xp embed(lam) w + embed(yr - lam xr) w^3  ->  coefficients at w^0, w^1, w^7, w^3, w^9."""
+    out = [0] * 12
+    l0, l1 = embed(lam)
+    c0, c1 = embed(f2_sub(yr, f2_mul(lam, xr)))
+    out[0] = (-p1[1]) % Q
+    out[1], out[7] = l0 * p1[0] % Q, l1 * p1[0] % Q
+    out[3], out[9] = c0, c1
+    return out
+
+
+def miller_loop_twist(q2, p1):
+    if q2 is None or p1 is None:
+        return F12_ONE
+    xq, yq = q2
+    xr, yr = q2
+    f = F12_ONE
+
+    def add_step(f, xr, yr, x2, y2, square):
+        if square:
+            lam = f2_mul(f2_mul((3, 0), f2_mul(xr, xr)), f2_inv(f2_add(yr, yr)))
+            x2, y2 = xr, yr
+        else:
+            lam = f2_mul(f2_sub(y2, yr), f2_inv(f2_sub(x2, xr)))
+        line = sparse_line(lam, xr, yr, p1)
+        f = f12_mul(f12_mul(f, f), line) if square else f12_mul(f, line)
+        x3 = f2_sub(f2_sub(f2_mul(lam, lam), xr), x2)
+        y3 = f2_sub(f2_mul(lam, f2_sub(xr, x3)), yr)
+        return f, x3, y3
+
+    for i in range(ATE_LOOP_COUNT.bit_length() - 2, -1, -1):
+        f, xr, yr = add_step(f, xr, yr, None, None, True)
+        if (ATE_LOOP_COUNT >> i) & 1:
+            f, xr, yr = add_step(f, xr, yr, xq, yq, False)
+    x1, y1 = f2_mul(f2_conj(xq), FROB_X), f2_mul(f2_conj(yq), FROB_Y)           # pi(Q)
+    x2, y2 = f2_mul(xq, FROB2_X), yq                                            # -pi^2(Q): y * (-1) negated again
+    f, xr, yr = add_step(f, xr, yr, x1, y1, False)
+    lam = f2_mul(f2_sub(y2, yr), f2_inv(f2_sub(x2, xr)))
+    return f12_mul(f, sparse_line(lam, xr, yr, p1))

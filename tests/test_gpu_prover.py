@@ -97,6 +97,8 @@ def test_native_cpp_driver_matches_python_and_oracle(ctx, log_n, fixed_base):
     proof = prover.proof_from_bytes(raw)
     assert proof.to_bytes() == raw
     assert plonk_ref.verify(native.vk(), proof, list(circ.pi.values()), TAU) == 0
+    from zkt_plonk_b200 import verifier                                   # zkb_plonk_verify: PC::check by pairings, host side
+    assert verifier.verify(native.vk(), raw, list(circ.pi.values()), plonk_ref.make_cvk(TAU)) == 0
     assert tm["total_ms"] > 0
     native.close()
     ctx.srs_precompute(-1)

@@ -10,3 +10,4 @@ from .context import Context, sum_partials  # noqa: F401
 from .domain import GpuEvaluationDomain  # noqa: F401
 from .kzg import GpuKZG10, PCError  # noqa: F401
 from . import keyfile, prover_ops  # noqa: F401,E402
+# `prover` (round schedule) and `verifier` (zkb_plonk_verify) are imported on demand: they pull in the transcript code

@@ -94,6 +94,9 @@ def load():
                                     ctypes.POINTER(i), ctypes.POINTER(vp)]),
         "zkb_plonk_load_keys": (i, [vp, ctypes.c_char_p, ctypes.c_char_p, sz, ctypes.POINTER(vp)]),
         "zkb_plonk_save_keys": (i, [vp, vp, ctypes.c_char_p, ctypes.c_char_p]),
+        "zkb_plonk_verify": (i, [sz, vp, sz, vp, ctypes.POINTER(i), vp, vp, vp, vp, i]),
+        "zkb_pairing": (i, [vp, vp, vp]),
+        "zkb_pairing_product_is_one": (i, [vp, vp, sz, ctypes.POINTER(i)]),
         "zkb_launch_count": (ctypes.c_uint64, [vp]),
         "zkb_msm_last_timing": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),
         "zkb_bench_int": (i, [vp, i, ctypes.POINTER(ctypes.c_double)]),

@@ -1,0 +1,454 @@
+// verify.cu -- Proof::verify of zkt-plonk on the host.  No GPU work: the verifier is a 13-point linear
+// combination, two KZG checks and a handful of field operations (milliseconds in the reference as well).
+//
+//   zkb_plonk_verify   plonk-core/src/proof_system/proof.rs:285-503 (compute_r0 :163-217, compute_linearization_commitment
+//                      :220-282 with keys/{arithmetic,permutation,lookup}.rs::compute_linearization_commitment), then
+//                      PC::check twice (:441-502) = SonicKZG10::check without degree bounds or hiding:
+//                      e(sum eta^i C_i - (sum eta^i v_i) G + z W, h) * e(-W, beta_h) == 1
+//   zkb_pairing        e(P, Q) on BN254 (ark-ec 0.3 / ark-bn254 0.3 are crates.io dependencies, un-vendored): optimal ate,
+//                      restated in its simplest exact form -- Fq12 = Fq[w] / (w^12 - 18 w^6 + 82), G2 arithmetic on the
+//                      twist in affine Fq2 coordinates, sparse line functions, the two Frobenius-twisted additions, final
+//                      exponentiation as one power (q^12 - 1) / r.  A product-of-pairings check has the same outcome under
+//                      any correct pairing, so arkworks' internal conventions cannot change accept / reject.
+// tests/test_verify.py compares zkb_pairing with the independent Python restatement (oracle/pairing.py) coefficient by
+// coefficient and zkb_plonk_verify with oracle/plonk_ref.py on accepted and tampered proofs.
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/zkb200.h"
+#include "host_plonk.h"
+
+namespace {
+
+using host::FQ;
+using host::FR;
+
+// ================================================================================================ constants
+const uint64_t FINAL_EXP[44] = {
+    0x86964b64ca86f120ULL, 0x40a4efb7e54523a4ULL, 0x837fa97896e84abbULL, 0x361102b6b9b2b918ULL,
+    0xc0de81def35692daULL, 0xbe04c7e8a6c3c760ULL, 0xd766f9c9d570bb7fULL, 0xc230974d83561841ULL,
+    0x5bba1668c3be69a3ULL, 0x7f3811c410526294ULL, 0x29baee7ddadda71cULL, 0xbf813b8d145da900ULL,
+    0x641bbadf423f9a2cULL, 0xa80bb4ea44eacc5eULL, 0xcd65664814fde37cULL, 0x4a0364b9580291d2ULL,
+    0xee93dfb10826f0ddULL, 0x6b42db8dc5514724ULL, 0xbb10cf430b0f3785ULL, 0x40494e406f804216ULL,
+    0x55cfe107acf3aafbULL, 0x2088ec80e0ebae87ULL, 0x846a3ed011a337a0ULL, 0x48a45a4a1e3a5195ULL,
+    0xe5664568dfc50e16ULL, 0xab6a41294c0cc4ebULL, 0x82d0d602d268c7daULL, 0x6668449aed3cc48aULL,
+    0x5062cd0fb2015dfcULL, 0x7f2940a8b1ddb3d1ULL, 0x77f5b63a2a226448ULL, 0xfef0781361e443aeULL,
+    0xf977870e88d5c6c8ULL, 0x790364a61f676baaULL, 0x5887e72eceaddea3ULL, 0x1377e563a09a1b70ULL,
+    0x0c54efee1bd8c3b2ULL, 0x3ec3d15ad524d8f7ULL, 0xdaf15466b2383a5dULL, 0xe1e30a73bb94fec0ULL,
+    0x6a1c71015f3f7be2ULL, 0x842d43bf6369b1ffULL, 0x20fddadf107d20bcULL, 0x0000002f4b6dc970ULL};
+const uint64_t SQRT_EXP[4] = {0x4f082305b61f3f52ULL, 0x65e05aa45a1c72a3ULL, 0x6e14116da0605617ULL, 0x0c19139cb84c680aULL};   // (q + 1) / 4
+const uint64_t FROB_X_C0[4] = {0x99e39557176f553dULL, 0xb78cc310c2c3330cULL, 0x4c0bec3cf559b143ULL, 0x2fb347984f7911f7ULL};
+const uint64_t FROB_X_C1[4] = {0x1665d51c640fcba2ULL, 0x32ae2a1d0b7c9dceULL, 0x4ba4cc8bd75a0794ULL, 0x16c9e55061ebae20ULL};
+const uint64_t FROB_Y_C0[4] = {0xdc54014671a0135aULL, 0xdbaae0eda9c95998ULL, 0xdc5ec698b6e2f9b9ULL, 0x063cf305489af5dcULL};
+const uint64_t FROB_Y_C1[4] = {0x82d37f632623b0e3ULL, 0x21807dc98fa25bd2ULL, 0x0704b5a7ec796f2bULL, 0x07c03cbcac41049aULL};
+const uint64_t FROB2_X_C0[4] = {0xe4bd44e5607cfd48ULL, 0xc28f069fbb966e3dULL, 0x5e6dd9e7e0acccb0ULL, 0x30644e72e131a029ULL};
+const uint64_t ATE_LOOP_LOW = 0x9d797039be763ba8ULL;      // 6x + 2 = 2^64 + this (x = 4965661367192848881): top bit implicit
+
+inline Fe q_from_canon(const uint64_t c[4]) { Fe f, r2; memcpy(f.l, c, 32); memcpy(r2.l, FQ.r2, 32); return host::mul(f, r2, FQ); }
+inline Fe q_small(uint64_t v) { return host::from_u64(v, FQ); }
+inline Fe qadd(const Fe &a, const Fe &b) { return host::add(a, b, FQ); }
+inline Fe qsub(const Fe &a, const Fe &b) { return host::sub(a, b, FQ); }
+inline Fe qmul(const Fe &a, const Fe &b) { return host::mul(a, b, FQ); }
+inline Fe qneg(const Fe &a) { Fe z = {{0, 0, 0, 0}}; return host::sub(z, a, FQ); }
+inline Fe qzero() { Fe z = {{0, 0, 0, 0}}; return z; }
+
+// ================================================================================================ Fq2 = Fq[i] / (i^2 + 1)
+struct F2 { Fe c0, c1; };
+inline F2 f2_add(const F2 &a, const F2 &b) { return {qadd(a.c0, b.c0), qadd(a.c1, b.c1)}; }
+inline F2 f2_sub(const F2 &a, const F2 &b) { return {qsub(a.c0, b.c0), qsub(a.c1, b.c1)}; }
+inline F2 f2_mul(const F2 &a, const F2 &b) {
+    return {qsub(qmul(a.c0, b.c0), qmul(a.c1, b.c1)), qadd(qmul(a.c0, b.c1), qmul(a.c1, b.c0))};
+}
+inline F2 f2_conj(const F2 &a) { return {a.c0, qneg(a.c1)}; }
+inline F2 f2_inv(const F2 &a) {
+    Fe d = host::inv(qadd(qmul(a.c0, a.c0), qmul(a.c1, a.c1)), FQ);
+    return {qmul(a.c0, d), qneg(qmul(a.c1, d))};
+}
+inline bool f2_is_zero(const F2 &a) { return host::is_zero(a.c0) && host::is_zero(a.c1); }
+inline bool f2_eq(const F2 &a, const F2 &b) { return feq(a.c0, b.c0) && feq(a.c1, b.c1); }
+
+struct G2 { F2 x, y; bool inf; };
+
+// y^2 = x^3 + 3 / (9 + i)
+bool g2_on_curve(const G2 &p) {
+    if (p.inf) return true;
+    F2 xi = {q_small(9), q_small(1)}, three = {q_small(3), qzero()};
+    F2 b2 = f2_mul(three, f2_inv(xi));
+    return f2_eq(f2_sub(f2_mul(p.y, p.y), f2_mul(f2_mul(p.x, p.x), p.x)), b2);
+}
+
+// ================================================================================================ Fq12 = Fq[w] / (w^12 - 18 w^6 + 82)
+struct F12 { Fe c[12]; };
+F12 f12_one() { F12 r; for (int i = 0; i < 12; ++i) r.c[i] = qzero(); r.c[0] = host::one(FQ); return r; }
+bool f12_eq(const F12 &a, const F12 &b) { for (int i = 0; i < 12; ++i) if (!feq(a.c[i], b.c[i])) return false; return true; }
+
+F12 f12_mul(const F12 &a, const F12 &b) {
+    Fe t[23];
+    for (int k = 0; k < 23; ++k) t[k] = qzero();
+    for (int i = 0; i < 12; ++i) {
+        if (host::is_zero(a.c[i])) continue;
+        for (int j = 0; j < 12; ++j) t[i + j] = qadd(t[i + j], qmul(a.c[i], b.c[j]));
+    }
+    const Fe k18 = q_small(18), k82 = q_small(82);
+    for (int k = 22; k >= 12; --k) {                       // w^12 = 18 w^6 - 82
+        if (host::is_zero(t[k])) continue;
+        t[k - 6] = qadd(t[k - 6], qmul(k18, t[k]));
+        t[k - 12] = qsub(t[k - 12], qmul(k82, t[k]));
+    }
+    F12 r;
+    for (int k = 0; k < 12; ++k) r.c[k] = t[k];
+    return r;
+}
+
+F12 f12_pow(const F12 &a, const uint64_t *e, int limbs) {
+    F12 acc = f12_one();
+    bool started = false;
+    for (int i = 64 * limbs - 1; i >= 0; --i) {
+        if (started) acc = f12_mul(acc, acc);
+        if ((e[i >> 6] >> (i & 63)) & 1) { acc = started ? f12_mul(acc, a) : a; started = true; }
+    }
+    return acc;
+}
+
+// Fq2 -> two Fq12 coefficients: a0 + a1 i = (a0 - 9 a1) + a1 w^6
+inline void embed(const F2 &a, Fe *lo, Fe *hi) {
+    *lo = qsub(a.c0, qmul(q_small(9), a.c1));
+    *hi = a.c1;
+}
+
+// line through the untwisted (xr, yr) with slope embed(lam) w, at P = (xp, yp) in E(Fq):
+//   -yp + xp embed(lam) w + embed(yr - lam xr) w^3      (coefficients at w^0, w^1, w^7, w^3, w^9)
+F12 sparse_line(const F2 &lam, const F2 &xr, const F2 &yr, const Fe &xp, const Fe &yp) {
+    F12 l;
+    for (int i = 0; i < 12; ++i) l.c[i] = qzero();
+    Fe l0, l1, c0, c1;
+    embed(lam, &l0, &l1);
+    embed(f2_sub(yr, f2_mul(lam, xr)), &c0, &c1);
+    l.c[0] = qneg(yp);
+    l.c[1] = qmul(l0, xp);
+    l.c[7] = qmul(l1, xp);
+    l.c[3] = c0;
+    l.c[9] = c1;
+    return l;
+}
+
+struct Miller {
+    F12 f;
+    F2 xr, yr;
+    Fe xp, yp;
+    // one step: tangent at R (square == true) or chord through R and (x2, y2); f <- f^2 * line or f * line; R <- 2R or R + Q
+    void step(bool square, F2 x2, F2 y2) {
+        F2 lam;
+        if (square) {
+            F2 three = {q_small(3), qzero()};
+            lam = f2_mul(f2_mul(three, f2_mul(xr, xr)), f2_inv(f2_add(yr, yr)));
+            x2 = xr;
+            y2 = yr;
+        } else {
+            lam = f2_mul(f2_sub(y2, yr), f2_inv(f2_sub(x2, xr)));
+        }
+        F12 line = sparse_line(lam, xr, yr, xp, yp);
+        f = square ? f12_mul(f12_mul(f, f), line) : f12_mul(f, line);
+        F2 x3 = f2_sub(f2_sub(f2_mul(lam, lam), xr), x2);
+        F2 y3 = f2_sub(f2_mul(lam, f2_sub(xr, x3)), yr);
+        xr = x3;
+        yr = y3;
+    }
+};
+
+// Miller loop of the optimal ate pairing; the identity on either side gives 1.  (P, Q of prime order r: the chord / tangent
+// denominators cannot vanish inside the loop.)
+F12 miller_loop(const G2 &q, const Fe &xp, const Fe &yp, bool p_inf) {
+    if (q.inf || p_inf) return f12_one();
+    Miller m;
+    m.f = f12_one();
+    m.xr = q.x; m.yr = q.y; m.xp = xp; m.yp = yp;
+    for (int i = 63; i >= 0; --i) {
+        m.step(true, q.x, q.y);
+        if ((ATE_LOOP_LOW >> i) & 1) m.step(false, q.x, q.y);
+    }
+    const F2 frob_x = {q_from_canon(FROB_X_C0), q_from_canon(FROB_X_C1)}, frob_y = {q_from_canon(FROB_Y_C0), q_from_canon(FROB_Y_C1)};
+    const F2 frob2_x = {q_from_canon(FROB2_X_C0), qzero()};
+    F2 x1 = f2_mul(f2_conj(q.x), frob_x), y1 = f2_mul(f2_conj(q.y), frob_y);      // pi(Q)
+    F2 x2 = f2_mul(q.x, frob2_x), y2 = q.y;                                        // -pi^2(Q)
+    m.step(false, x1, y1);
+    F2 lam = f2_mul(f2_sub(y2, m.yr), f2_inv(f2_sub(x2, m.xr)));
+    return f12_mul(m.f, sparse_line(lam, m.xr, m.yr, xp, yp));
+}
+
+F12 final_exponentiation(const F12 &f) { return f12_pow(f, FINAL_EXP, 44); }
+
+// ================================================================================================ G1 on the host (XYZZ)
+struct X1 { Fe x, y, zz, zzz; };
+inline bool x1_inf(const X1 &p) { return host::is_zero(p.zz); }
+inline X1 x1_zero() { X1 p; memset(&p, 0, sizeof p); return p; }
+inline X1 x1_from(const Pt &a) {
+    if (a.inf) return x1_zero();
+    return {a.x, a.y, host::one(FQ), host::one(FQ)};
+}
+X1 x1_dbl(const X1 &p) {
+    if (x1_inf(p)) return p;
+    Fe u = qadd(p.y, p.y), v = qmul(u, u), w = qmul(u, v), s = qmul(p.x, v);
+    Fe xx = qmul(p.x, p.x), m = qadd(qadd(xx, xx), xx);
+    X1 r;
+    r.x = qsub(qsub(qmul(m, m), s), s);
+    r.y = qsub(qmul(m, qsub(s, r.x)), qmul(w, p.y));
+    r.zz = qmul(v, p.zz);
+    r.zzz = qmul(w, p.zzz);
+    return r;
+}
+X1 x1_add(const X1 &a, const X1 &b) {
+    if (x1_inf(a)) return b;
+    if (x1_inf(b)) return a;
+    Fe u1 = qmul(a.x, b.zz), u2 = qmul(b.x, a.zz), s1 = qmul(a.y, b.zzz), s2 = qmul(b.y, a.zzz);
+    Fe p = qsub(u2, u1), r = qsub(s2, s1);
+    if (host::is_zero(p)) return host::is_zero(r) ? x1_dbl(a) : x1_zero();
+    Fe pp = qmul(p, p), ppp = qmul(p, pp), q = qmul(u1, pp);
+    X1 o;
+    o.x = qsub(qsub(qsub(qmul(r, r), ppp), q), q);
+    o.y = qsub(qmul(r, qsub(q, o.x)), qmul(s1, ppp));
+    o.zz = qmul(qmul(a.zz, b.zz), pp);
+    o.zzz = qmul(qmul(a.zzz, b.zzz), ppp);
+    return o;
+}
+// scalar (Montgomery Fr) * point
+X1 x1_mul(const Fe &k_mont, const Pt &p) {
+    Fe one = {{1, 0, 0, 0}};
+    Fe k = host::mul(k_mont, one, FR);                    // canonical
+    X1 base = x1_from(p), acc = x1_zero();
+    for (int i = 255; i >= 0; --i) {
+        acc = x1_dbl(acc);
+        if ((k.l[i >> 6] >> (i & 63)) & 1) acc = x1_add(acc, base);
+    }
+    return acc;
+}
+Pt x1_affine(const X1 &p) {
+    Pt r;
+    r.inf = x1_inf(p);
+    if (r.inf) { r.x = qzero(); r.y = qzero(); return r; }
+    Fe zi = host::inv(p.zzz, FQ);
+    Fe zzi = qmul(zi, p.zz);
+    zzi = qmul(zzi, zzi);
+    r.x = qmul(p.x, zzi);
+    r.y = qmul(p.y, zi);
+    return r;
+}
+Pt pt_neg(const Pt &p) { Pt r = p; if (!p.inf) r.y = qneg(p.y); return r; }
+bool g1_on_curve(const Pt &p) {
+    if (p.inf) return true;
+    return feq(qmul(p.y, p.y), qadd(qmul(qmul(p.x, p.x), p.x), q_small(3)));
+}
+
+// GroupAffine::deserialize (compressed, ark-ec 0.3): x little endian, bit 6 of the last byte = infinity, bit 7 = (y > -y)
+bool g1_decompress(const uint8_t in[32], Pt *out) {
+    Fe x;
+    memcpy(x.l, in, 32);
+    const bool inf = (x.l[3] >> 62) & 1, positive = (x.l[3] >> 63) & 1;
+    x.l[3] &= ~(3ULL << 62);
+    if (inf) { out->inf = true; out->x = qzero(); out->y = qzero(); return true; }
+    if (host::ge(x.l, FQ.p)) return false;
+    Fe r2;
+    memcpy(r2.l, FQ.r2, 32);
+    Fe xm = host::mul(x, r2, FQ);
+    Fe rhs = qadd(qmul(qmul(xm, xm), xm), q_small(3));
+    Fe y = host::pow(rhs, SQRT_EXP, FQ);                  // q = 3 mod 4
+    if (!feq(qmul(y, y), rhs)) return false;               // x is not on the curve
+    Fe one = {{1, 0, 0, 0}};
+    Fe yc = host::mul(y, one, FQ), nyc;
+    host::sub_raw(nyc.l, FQ.p, yc.l);
+    if (host::is_zero(yc)) memset(nyc.l, 0, 32);
+    bool gt = false;
+    for (int i = 3; i >= 0; --i) if (yc.l[i] != nyc.l[i]) { gt = yc.l[i] > nyc.l[i]; break; }
+    out->inf = false;
+    out->x = xm;
+    out->y = gt == positive ? y : qneg(y);
+    return true;
+}
+
+G2 g2_from(const uint64_t v[16]) {
+    G2 p;
+    p.x = {fe_from(v), fe_from(v + 4)};
+    p.y = {fe_from(v + 8), fe_from(v + 12)};
+    p.inf = f2_is_zero(p.x) && f2_is_zero(p.y);
+    return p;
+}
+bool fq_canonical_mont(const Fe &m) { return !host::ge(m.l, FQ.p); }
+
+bool pairing_product_is_one(const Pt *g1, const G2 *g2, size_t k) {
+    F12 f = f12_one();
+    for (size_t i = 0; i < k; ++i) f = f12_mul(f, miller_loop(g2[i], g1[i].x, g1[i].y, g1[i].inf));
+    return f12_eq(final_exponentiation(f), f12_one());
+}
+
+// util.rs:185-195 compute_lagrange_evaluation(n, point, zh_eval, tau) = zh * point / (n (tau - point))
+Fe lagrange(uint64_t n, const Fe &point, const Fe &zh, const Fe &tau) {
+    Fe den = fmul(host::from_u64(n, FR), fsub(tau, point));
+    return fmul(fmul(zh, point), host::inv(den, FR));
+}
+
+// SonicKZG10::check for one query point (no degree bounds, no hiding)
+bool kzg_check(const Pt *commits, const Fe *values, size_t k, const Fe &point, const Pt &w, const Fe &eta, const G2 &h, const G2 &beta_h) {
+    X1 c = x1_zero();
+    Fe chal = FR_ONE(), v = {{0, 0, 0, 0}};
+    for (size_t i = 0; i < k; ++i) {
+        c = x1_add(c, x1_mul(chal, commits[i]));
+        v = fadd(v, fmul(chal, values[i]));
+        chal = fmul(chal, eta);
+    }
+    Pt gen;
+    gen.inf = false; gen.x = q_small(1); gen.y = q_small(2);
+    X1 a = x1_add(x1_add(c, x1_mul(fneg(v), gen)), x1_mul(point, w));
+    Pt g1s[2] = {x1_affine(a), pt_neg(w)};
+    G2 g2s[2] = {h, beta_h};
+    return pairing_product_is_one(g1s, g2s, 2);
+}
+
+}  // namespace
+
+extern "C" {
+
+int zkb_pairing(const uint64_t g1_xy[8], const uint64_t g2_xy[16], uint64_t out_canonical[48]) {
+    if (!g1_xy || !g2_xy || !out_canonical) return ZKB_ERR_INVALID;
+    Pt p;
+    p.x = fe_from(g1_xy); p.y = fe_from(g1_xy + 4);
+    p.inf = host::is_zero(p.x) && host::is_zero(p.y);
+    G2 q = g2_from(g2_xy);
+    if (!fq_canonical_mont(p.x) || !fq_canonical_mont(p.y) || !g1_on_curve(p) || !g2_on_curve(q)) return ZKB_ERR_INVALID;
+    F12 e = final_exponentiation(miller_loop(q, p.x, p.y, p.inf));
+    Fe one = {{1, 0, 0, 0}};
+    for (int i = 0; i < 12; ++i) {
+        Fe c = host::mul(e.c[i], one, FQ);
+        memcpy(out_canonical + 4 * i, c.l, 32);
+    }
+    return ZKB_OK;
+}
+
+int zkb_pairing_product_is_one(const uint64_t *g1_xy, const uint64_t *g2_xy, size_t count, int *is_one) {
+    if ((!g1_xy || !g2_xy) && count) return ZKB_ERR_INVALID;
+    if (!is_one) return ZKB_ERR_INVALID;
+    std::vector<Pt> ps(count);
+    std::vector<G2> qs(count);
+    for (size_t i = 0; i < count; ++i) {
+        ps[i].x = fe_from(g1_xy + 8 * i); ps[i].y = fe_from(g1_xy + 8 * i + 4);
+        ps[i].inf = host::is_zero(ps[i].x) && host::is_zero(ps[i].y);
+        qs[i] = g2_from(g2_xy + 16 * i);
+        if (!g1_on_curve(ps[i]) || !g2_on_curve(qs[i])) return ZKB_ERR_INVALID;
+    }
+    *is_one = pairing_product_is_one(ps.data(), qs.data(), count) ? 1 : 0;
+    return ZKB_OK;
+}
+
+int zkb_plonk_verify(size_t n, const uint64_t *pi_roots_mont, size_t n_pi, const uint64_t vk_xy[80], const int vk_inf[10],
+                     const uint64_t *pub_inputs_mont, const uint8_t proof[802], const uint64_t g2_h[16], const uint64_t g2_beta_h[16],
+                     int transcript_kind) {
+    if (!vk_xy || !proof || !g2_h || !g2_beta_h || ((!pi_roots_mont || !pub_inputs_mont) && n_pi)) return ZKB_ERR_INVALID;
+    if (n < 2 || (n & (n - 1)) || n > ((size_t)1 << 28) || (transcript_kind != 0 && transcript_kind != 1)) return ZKB_ERR_INVALID;
+    unsigned log_n = 0;
+    while (((size_t)1 << log_n) < n) ++log_n;
+    // ---- inputs
+    Pt V[10];                                             // q_m q_l q_r q_o q_c sigma1 sigma2 sigma3 q_lookup q_table
+    for (int k = 0; k < 10; ++k) {
+        V[k].x = fe_from(vk_xy + 8 * k); V[k].y = fe_from(vk_xy + 8 * k + 4);
+        V[k].inf = (vk_inf && vk_inf[k]) || (host::is_zero(V[k].x) && host::is_zero(V[k].y));
+        if (!V[k].inf && (!fq_canonical_mont(V[k].x) || !fq_canonical_mont(V[k].y) || !g1_on_curve(V[k]))) return ZKB_ERR_INVALID;
+    }
+    const G2 h = g2_from(g2_h), beta_h = g2_from(g2_beta_h);
+    if (!g2_on_curve(h) || !g2_on_curve(beta_h)) return ZKB_ERR_INVALID;
+    Pt C[11], aw, saw;                                    // a b c t h1 h2 z1 z2 q_lo q_mid q_hi  (proof.rs:112-154)
+    for (int k = 0; k < 11; ++k) if (!g1_decompress(proof + 32 * k, &C[k])) return ZKB_ERR_INVALID;
+    if (!g1_decompress(proof + 352, &aw) || !g1_decompress(proof + 385, &saw) || proof[384] != 0 || proof[417] != 0) return ZKB_ERR_INVALID;
+    Fe E[12];                                             // a b c sigma1 sigma2 z1_next q_lookup t t_next z2_next h1_next h2
+    {
+        Fe r2;
+        memcpy(r2.l, FR.r2, 32);
+        for (int k = 0; k < 12; ++k) {
+            Fe c;
+            memcpy(c.l, proof + 418 + 32 * k, 32);
+            if (host::ge(c.l, FR.p)) return ZKB_ERR_INVALID;
+            E[k] = host::mul(c, r2, FR);
+        }
+    }
+    enum { E_A, E_B, E_C, E_S1, E_S2, E_Z1N, E_QLK, E_T, E_TN, E_Z2N, E_H1N, E_H2 };
+    enum { C_A, C_B, C_C, C_T, C_H1, C_H2, C_Z1, C_Z2, C_QLO, C_QMID, C_QHI };
+    enum { V_QM, V_QL, V_QR, V_QO, V_QC, V_S1, V_S2, V_S3, V_QLK, V_QT };
+    const Fe *pi = (const Fe *)pub_inputs_mont, *roots = (const Fe *)pi_roots_mont;
+    // ---- transcript (keys/mod.rs:260-275, proof.rs:300-430)
+    Transcript tr("ZKT Plonk", transcript_kind);
+    tr.append_u64("circuit_size", (uint64_t)n);
+    {
+        const char *labels[10] = {"q_m_commit", "q_l_commit", "q_r_commit", "q_o_commit", "q_c_commit", "sigma1_commit",
+                                  "sigma2_commit", "sigma3_commit", "q_lookup_commit", "q_table_commit"};
+        for (int k = 0; k < 10; ++k) tr.append_commitment(labels[k], V[k]);
+    }
+    tr.append_scalars("pi", pi, n_pi);
+    tr.append_commitment("a_commit", C[C_A]);
+    tr.append_commitment("b_commit", C[C_B]);
+    tr.append_commitment("c_commit", C[C_C]);
+    tr.append_commitment("t_commit", C[C_T]);
+    tr.append_commitment("h1_commit", C[C_H1]);
+    tr.append_commitment("h2_commit", C[C_H2]);
+    const Fe beta = tr.challenge_scalar("beta"), gamma = tr.challenge_scalar("gamma");
+    const Fe delta = tr.challenge_scalar("delta"), epsilon = tr.challenge_scalar("epsilon");
+    tr.append_commitment("z1_commit", C[C_Z1]);
+    tr.append_commitment("z2_commit", C[C_Z2]);
+    const Fe alpha = tr.challenge_scalar("alpha");
+    tr.append_commitment("q_lo_commit", C[C_QLO]);
+    tr.append_commitment("q_mid_commit", C[C_QMID]);
+    tr.append_commitment("q_hi_commit", C[C_QHI]);
+    const Fe xi = tr.challenge_scalar("xi");
+    // ---- scalars
+    const Fe one = FR_ONE();
+    const Fe zh = fsub(host::pow_u64(xi, (uint64_t)n, FR), one);
+    const Fe l1 = lagrange(n, one, zh, xi);
+    const Fe al2 = fmul(alpha, alpha), al3 = fmul(al2, alpha), al4 = fmul(al2, al2), al5 = fmul(al4, alpha);
+    const Fe opd = fadd(one, delta), eopd = fmul(epsilon, opd);
+    // compute_r0 (proof.rs:163-217)
+    Fe part1 = {{0, 0, 0, 0}};
+    for (size_t k = 0; k < n_pi; ++k) part1 = fsub(part1, fmul(lagrange(n, roots[k], zh, xi), pi[k]));
+    Fe part2 = fmul(fmul(fmul(fmul(alpha, E[E_Z1N]), fadd(fadd(E[E_A], fmul(beta, E[E_S1])), gamma)),
+                         fadd(fadd(E[E_B], fmul(beta, E[E_S2])), gamma)), fadd(E[E_C], gamma));
+    Fe part3 = fmul(l1, al2);
+    Fe part4 = fmul(fmul(fmul(al3, E[E_Z2N]), fadd(eopd, fmul(delta, E[E_H2]))), fadd(fadd(eopd, E[E_H2]), fmul(delta, E[E_H1N])));
+    Fe part5 = fmul(l1, al4);
+    const Fe r0 = fadd(fadd(fadd(fadd(part1, part2), part3), part4), part5);
+    // compute_linearization_commitment (proof.rs:220-282)
+    const Fe bz = fmul(beta, xi), k1 = host::from_u64(7, FR), k2 = host::from_u64(13, FR);
+    Fe sc[13];
+    const Pt *pts[13] = {&V[V_QM], &V[V_QL], &V[V_QR], &V[V_QO], &V[V_QC], &C[C_Z1], &V[V_S3], &C[C_Z2], &C[C_H1], &V[V_QT],
+                         &C[C_QLO], &C[C_QMID], &C[C_QHI]};
+    sc[0] = fmul(E[E_A], E[E_B]); sc[1] = E[E_A]; sc[2] = E[E_B]; sc[3] = E[E_C]; sc[4] = one;
+    sc[5] = fadd(fmul(fmul(fmul(alpha, fadd(fadd(bz, E[E_A]), gamma)), fadd(fadd(fmul(bz, k1), E[E_B]), gamma)),
+                      fadd(fadd(fmul(bz, k2), E[E_C]), gamma)), fmul(l1, al2));
+    sc[6] = fneg(fmul(fmul(fmul(fmul(alpha, beta), E[E_Z1N]), fadd(fadd(fmul(beta, E[E_S1]), E[E_A]), gamma)),
+                      fadd(fadd(fmul(beta, E[E_S2]), E[E_B]), gamma)));
+    sc[7] = fadd(fmul(fmul(fmul(al3, opd), fadd(epsilon, fmul(E[E_QLK], E[E_C]))), fadd(fadd(eopd, E[E_T]), fmul(delta, E[E_TN]))),
+                 fmul(al4, l1));
+    sc[8] = fneg(fmul(fmul(al3, E[E_Z2N]), fadd(fadd(eopd, E[E_H2]), fmul(delta, E[E_H1N]))));
+    sc[9] = fmul(al5, E[E_T]);
+    const Fe xn2 = fmul(fmul(fadd(zh, one), xi), xi);     // xi^(n + 2)
+    sc[10] = fneg(zh); sc[11] = fneg(fmul(zh, xn2)); sc[12] = fneg(fmul(fmul(zh, xn2), xn2));
+    X1 rc = x1_zero();
+    for (int k = 0; k < 13; ++k) rc = x1_add(rc, x1_mul(sc[k], *pts[k]));
+    const Pt r_commit = x1_affine(rc);
+    {
+        const char *labels[12] = {"a_eval", "b_eval", "c_eval", "sigma1_eval", "sigma2_eval", "z1_next_eval", "q_lookup_eval", "t_eval",
+                                  "t_next_eval", "z2_next_eval", "h1_next_eval", "h2_eval"};
+        for (int k = 0; k < 12; ++k) tr.append_scalar(labels[k], E[k]);
+    }
+    const Fe eta = tr.challenge_scalar("eta");
+    // ---- the two openings (proof.rs:441-502)
+    {
+        const Pt cs[9] = {r_commit, C[C_A], C[C_B], C[C_C], V[V_S1], V[V_S2], V[V_QLK], C[C_T], C[C_H2]};
+        const Fe vs[9] = {r0, E[E_A], E[E_B], E[E_C], E[E_S1], E[E_S2], E[E_QLK], E[E_T], E[E_H2]};
+        if (!kzg_check(cs, vs, 9, xi, aw, eta, h, beta_h)) return 1;
+    }
+    {
+        const Pt cs[4] = {C[C_Z1], C[C_Z2], C[C_T], C[C_H1]};
+        const Fe vs[4] = {E[E_Z1N], E[E_Z2N], E[E_TN], E[E_H1N]};
+        if (!kzg_check(cs, vs, 4, fmul(xi, host::fr_root_of_unity(log_n)), saw, eta, h, beta_h)) return 2;
+    }
+    return 0;
+}
+
+}  // extern "C"
