@@ -227,6 +227,9 @@ ZKB_API int zkb_ck_file_info(const char *path, size_t *n_powers, size_t *max_deg
 ZKB_API int zkb_ck_file_read(const char *path, size_t first, size_t count, uint64_t *xy_mont_out);
 ZKB_API int zkb_ck_file_write(const char *path, const uint64_t *xy_mont, size_t n_powers, const uint64_t *gamma_xy_mont, size_t n_gamma,
                       size_t max_degree);
+/* cvk = sonic_pc::VerifierKey<Bn254>: only its first four fields are read -- g, gamma_g (G1; either may be NULL) and
+ * h, beta_h (G2: x.c0 x.c1 y.c0 y.c1, Montgomery), which is what zkb_plonk_verify takes. */
+ZKB_API int zkb_cvk_file_read(const char *path, uint64_t g_xy[8], uint64_t gamma_g_xy[8], uint64_t h_xy[16], uint64_t beta_h_xy[16]);
 /* deserialize_from_file::<CommitterKey>(ck_path) + keeping powers_of_g resident: the first min(max_points, all) powers
  * become the context's SRS (max_points = 0: all). */
 ZKB_API int zkb_srs_load_ck_file(zkb_ctx *ctx, const char *path, size_t max_points);

@@ -63,6 +63,23 @@ def committer_key(powers, gamma_powers, max_degree):
     return vec(list(powers), g1) + vec(list(gamma_powers), g1) + b"\x00\x00\x00" + u64(max_degree)
 
 
+def g2(pt):
+    """G2Affine, uncompressed: x.c0 x.c1 y.c0 y.c1, flags in the last byte."""
+    if pt is None:
+        b = bytearray(fe(0) + fe(0) + fe(1) + fe(0))
+        b[127] |= 1 << 6
+        return bytes(b)
+    (x0, x1), (y0, y1) = pt
+    return fe(x0) + fe(x1) + fe(y0) + fe(y1)
+
+
+def sonic_verifier_key(g, gamma_g, h, beta_h, supported_degree, max_degree, n_ell=3):
+    """cvk as sonic_pc::VerifierKey derives it; the two G2Prepared fields (Vec of Fq2 triples + infinity flag) are filled
+    with placeholder coefficients: no reader in this repository looks past beta_h."""
+    prepared = vec([((1, 2), (3, 4), (5, 6))] * n_ell, lambda t: b"".join(fe(c) for pair in t for c in pair)) + b"\x00"
+    return g1(g) + g1(gamma_g) + g2(h) + g2(beta_h) + prepared + prepared + option(None, u64) + u64(supported_degree) + u64(max_degree)
+
+
 # ---- readers (for files written by the product)
 class _Rd:
     def __init__(self, data):

@@ -19,4 +19,4 @@ mod prover;
 pub use ctx::{Ctx, Error};
 pub use domain::GpuDomain;
 pub use kzg::GpuKZG10;
-pub use prover::{prove_native, NativeKey, Transcript};
+pub use prover::{prove_native, verify_native, NativeKey, Transcript};

@@ -103,3 +103,40 @@ pub fn prove_native(
     })?;
     Ok(out)
 }
+
+/// `Proof::verify` (plonk-core/src/proof_system/proof.rs:285-503) on the host: transcript replay, r0, the 13-point
+/// linearisation commitment, and `PC::check` twice as products of pairings.  `vk_xy`: the ten VerifierKey commitments in
+/// seed_transcript order (x || y Montgomery limbs, identity = zeros); `h`, `beta_h`: the G2 half of the commitment
+/// scheme's verifier key as x.c0 x.c1 y.c0 y.c1 Montgomery limbs (`G2Affine`'s in-memory order).
+/// Ok(()) = accepted, Err(step) mirrors `Error::ProofVerificationError { step }`; malformed input is step 0.
+pub fn verify_native(
+    n: usize,
+    pi_roots: &[Fr],
+    vk_xy: &[u64; 80],
+    pub_inputs: &[Fr],
+    proof: &[u8; 802],
+    h: &[u64; 16],
+    beta_h: &[u64; 16],
+    transcript: Transcript,
+) -> Result<(), u32> {
+    assert_eq!(pi_roots.len(), pub_inputs.len());
+    let rc = unsafe {
+        sys::zkb_plonk_verify(
+            n,
+            pi_roots.as_ptr() as *const u64,
+            pi_roots.len(),
+            vk_xy.as_ptr(),
+            core::ptr::null(),
+            pub_inputs.as_ptr() as *const u64,
+            proof.as_ptr(),
+            h.as_ptr(),
+            beta_h.as_ptr(),
+            transcript as i32,
+        )
+    };
+    match rc {
+        0 => Ok(()),
+        1 | 2 => Err(rc as u32),
+        _ => Err(0),
+    }
+}

@@ -139,3 +139,23 @@ def test_malformed_files_are_refused(tmp_path, keys):
     path.write_bytes(arkser.vec(pts, arkser.g1) + arkser.vec(pts, arkser.g1) + b"\x01" + arkser.vec(pts, arkser.g1) + b"\x00\x00" + arkser.u64(1))
     with pytest.raises(_lib.ZkbError):
         keyfile.ck_info(path)
+
+
+def test_cvk_file_head_feeds_the_verifier(tmp_path, keys):
+    """The G2 half of the commitment verifier key, read from a cvk-shaped file, verifies a proof made on the same SRS."""
+    from oracle import pairing as pr
+    from zkt_plonk_b200 import verifier
+    circ, pk, vk, polys = keys
+    h, beta_h = plonk_ref.make_cvk(TAU)
+    gamma_g = pyref.g1_mul(77, pyref.G1_GEN)
+    path = tmp_path / "cvk"
+    path.write_bytes(arkser.sonic_verifier_key(pyref.G1_GEN, gamma_g, h, beta_h, 4 * circ.n, 1 << 20))
+    g_arr, gg_arr, h_arr, bh_arr = keyfile.cvk_read(path)
+    assert _array_to_pts(np.stack([g_arr, gg_arr])) == [pyref.G1_GEN, gamma_g]
+    assert np.array_equal(h_arr, verifier.g2_array(h)) and np.array_equal(bh_arr, verifier.g2_array(beta_h))
+    be = plonk_ref.OracleBackend(plonk_ref.make_srs_host(circ.n + 8, TAU))
+    raw = prover.prove(be, pk, vk, circ, list(range(3, 22))).to_bytes()
+    assert verifier.verify(vk, raw, list(circ.pi.values()), (h, beta_h)) == 0
+    path.write_bytes(path.read_bytes()[:300])
+    with pytest.raises(_lib.ZkbError):
+        keyfile.cvk_read(path)

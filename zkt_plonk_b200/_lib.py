@@ -84,6 +84,7 @@ def load():
         "zkb_ck_file_info": (i, [ctypes.c_char_p, ctypes.POINTER(sz), ctypes.POINTER(sz)]),
         "zkb_ck_file_read": (i, [ctypes.c_char_p, sz, sz, vp]),
         "zkb_ck_file_write": (i, [ctypes.c_char_p, vp, sz, vp, sz, sz]),
+        "zkb_cvk_file_read": (i, [ctypes.c_char_p, vp, vp, vp, vp]),
         "zkb_srs_load_ck_file": (i, [vp, ctypes.c_char_p, sz]),
         "zkb_pk_file_info": (i, [ctypes.c_char_p, ctypes.POINTER(sz)]),
         "zkb_pk_file_read": (i, [ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz)]),

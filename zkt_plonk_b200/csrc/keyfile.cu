@@ -21,6 +21,10 @@
 //         degree_bound: Option<usize>, hiding_bound: Option<usize> } with the labels of setup.rs:93-102
 //   vk  = VerifierKey { n: usize, pi_roots: Vec<Fr>, arith { q_m q_l q_r q_o q_c }, perm { sigma1 sigma2 sigma3 },
 //         lookup { q_lookup q_table } } of kzg10::Commitment(G1Affine)   (keys/mod.rs:180-203)
+//   cvk = sonic_pc::VerifierKey<Bn254> { g: G1Affine, gamma_g: G1Affine, h: G2Affine, beta_h: G2Affine, prepared_h,
+//         prepared_beta_h: G2Prepared, degree_bounds_and_neg_powers_of_h: Option<..>, supported_degree, max_degree }
+//         [ark-poly-commit 0.3: recalled].  Only the first four fields are read (384 bytes: the verifier needs h and
+//         beta_h, and derives its own line coefficients); G2Affine = x.c0 x.c1 y.c0 y.c1, flags in the last byte of y.c1.
 // The in-memory side of every function is this library's usual form (Montgomery limbs, identity = (0, 0)).
 // The epk file (13 coset tables, 1.7 GiB at n = 2^20) is never read: the key loader rebuilds those tables in HBM
 // with 10 coset NTTs, which is faster than reading them from disk.
@@ -185,6 +189,31 @@ int zkb_srs_load_ck_file(zkb_ctx *ctx, const char *path, size_t max_points) {
     rc = zkb_ck_file_read(path, 0, n, xy.data());
     if (rc) ZKB_FAIL(ctx, rc, "zkb_srs_load_ck_file: a coordinate is not a canonical Fq element");
     return zkb_srs_load_g1(ctx, xy.data(), n);
+}
+
+// ---- cvk: g, gamma_g (G1) and h, beta_h (G2) from the head of the file
+int zkb_cvk_file_read(const char *path, uint64_t g_xy[8], uint64_t gamma_g_xy[8], uint64_t h_xy[16], uint64_t beta_h_xy[16]) {
+    if (!h_xy || !beta_h_xy) return ZKB_ERR_INVALID;
+    File F(path, "rb");
+    if (!F.f) return ZKB_ERR_INVALID;
+    uint8_t b[384];
+    if (!F.rd(b, 384)) return ZKB_ERR_INVALID;
+    uint64_t tmp[8];
+    if (!point_from_file(b, g_xy ? g_xy : tmp) || !point_from_file(b + 64, gamma_g_xy ? gamma_g_xy : tmp)) return ZKB_ERR_INVALID;
+    uint64_t *dst[2] = {h_xy, beta_h_xy};
+    for (int k = 0; k < 2; ++k) {
+        const uint8_t *src = b + 128 + 128 * k;
+        Fe c[4];
+        memcpy(c, src, 128);
+        const bool inf = (c[3].l[3] >> 62) & 1;
+        c[3].l[3] &= ~(3ULL << 62);
+        for (int j = 0; j < 4; ++j) {
+            if (host::ge(c[j].l, host::FQ.p)) return ZKB_ERR_INVALID;
+            c[j] = to_mont(c[j], host::FQ);
+        }
+        if (inf) memset(dst[k], 0, 128); else memcpy(dst[k], c, 128);
+    }
+    return ZKB_OK;
 }
 
 // ---- pk

@@ -91,3 +91,11 @@ def vk_write(path, n, pi_roots, commits_xy, is_inf=None):
     xy = np.ascontiguousarray(commits_xy, dtype=np.uint64).reshape(10, 8)
     inf = (ctypes.c_int * 10)(*[int(bool(x)) for x in (is_inf or [0] * 10)])
     _check(_lib.lib().zkb_vk_file_write(_path(path), n, _vp(keep), roots.shape[0], _vp(xy), inf), f"{path}: cannot write")
+
+
+def cvk_read(path):
+    """(g, gamma_g, h, beta_h) of a sonic_pc::VerifierKey file: (8,), (8,), (16,), (16,) uint64 Montgomery arrays."""
+    g, gg = np.zeros(8, dtype=np.uint64), np.zeros(8, dtype=np.uint64)
+    h, bh = np.zeros(16, dtype=np.uint64), np.zeros(16, dtype=np.uint64)
+    _check(_lib.lib().zkb_cvk_file_read(_path(path), _vp(g), _vp(gg), _vp(h), _vp(bh)), f"{path}: not a sonic_pc::VerifierKey file")
+    return g, gg, h, bh
