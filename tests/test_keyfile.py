@@ -159,3 +159,41 @@ def test_cvk_file_head_feeds_the_verifier(tmp_path, keys):
     path.write_bytes(path.read_bytes()[:300])
     with pytest.raises(_lib.ZkbError):
         keyfile.cvk_read(path)
+
+
+def test_readers_survive_mutated_files(tmp_path, keys):
+    """Byte flips, truncations and length-field inflation of valid files: every reader returns an error or a parse --
+    it never crashes, hangs or allocates by an attacker-chosen length (lengths are bounded before any allocation)."""
+    circ, pk, vk, polys = keys
+    rnd = random.Random(99)
+    pts = [pyref.g1_mul(k + 1, pyref.G1_GEN) for k in range(6)]
+    h, beta_h = plonk_ref.make_cvk(TAU)
+    files = {
+        "pk": (arkser.prover_key(polys), keyfile.pk_read),
+        "vk": (arkser.verifier_key(vk.n, vk.pi_roots, vk.commits), keyfile.vk_read),
+        "ck": (arkser.committer_key(pts, pts[:2], 5), keyfile.ck_read),
+        "cvk": (arkser.sonic_verifier_key(pts[0], pts[1], h, beta_h, 64, 64), keyfile.cvk_read),
+    }
+    path = tmp_path / "mut"
+    outcomes = {"ok": 0, "refused": 0}
+    for name, (good, reader) in files.items():
+        for trial in range(120):
+            data = bytearray(good)
+            kind = trial % 4
+            if kind == 0:                                               # flip a few bytes
+                for _ in range(rnd.randrange(1, 4)):
+                    data[rnd.randrange(len(data))] ^= 1 << rnd.randrange(8)
+            elif kind == 1:                                             # truncate
+                data = data[: rnd.randrange(len(data))]
+            elif kind == 2:                                             # huge length field somewhere plausible
+                off = rnd.choice([0, 8, 11, 19]) if len(data) > 27 else 0
+                data[off: off + 8] = (rnd.choice([1 << 40, (1 << 64) - 1, 1 << 31])).to_bytes(8, "little")
+            else:                                                       # garbage tail
+                data += bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 40)))
+            path.write_bytes(bytes(data))
+            try:
+                reader(path)
+                outcomes["ok"] += 1
+            except _lib.ZkbError:
+                outcomes["refused"] += 1
+    assert outcomes["refused"] > 100 and outcomes["ok"] + outcomes["refused"] == 480
