@@ -301,3 +301,28 @@ def miller_loop_twist(q2, p1):
     f, xr, yr = add_step(f, xr, yr, x1, y1, False)
     lam = f2_mul(f2_sub(y2, yr), f2_inv(f2_sub(x2, xr)))
     return f12_mul(f, sparse_line(lam, xr, yr, p1))
+
+
+# ---- final exponentiation split as (q^6 - 1) (q^2 + 1) ((q^4 - q^2 + 1) / r): the shape of csrc/verify.cu
+ZETA = f2_pow(XI, (Q * Q - 1) // 6)               # w^(q^2) = ZETA * w; a sixth root of unity, it lies in Fq
+HARD_EXP = (Q ** 4 - Q ** 2 + 1) // R
+
+
+def f12_conj(a):
+    """q^6-power Frobenius: w -> -w."""
+    return [(-c) % Q if k & 1 else c for k, c in enumerate(a)]
+
+
+def f12_frob2(a):
+    """q^2-power Frobenius: coefficients are in Fq, w^k -> ZETA^k w^k."""
+    out, z = [], 1
+    for c in a:
+        out.append(c * z % Q)
+        z = z * ZETA[0] % Q
+    return out
+
+
+def final_exponentiation_split(f):
+    t = f12_mul(f12_conj(f), f12_inv(f))
+    t = f12_mul(f12_frob2(t), t)
+    return f12_pow(t, HARD_EXP)
