@@ -139,6 +139,36 @@ def quotient_evals(log_n, ch, wit, epk):
     return out
 
 
+def poly_eval(coeffs, z_limbs):
+    """DensePolynomial::evaluate: coeffs (n, 4) Montgomery, z (4,) Montgomery -> (4,) Montgomery."""
+    c = np.ascontiguousarray(coeffs, dtype=np.uint64)
+    z = np.ascontiguousarray(z_limbs, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().zko_poly_eval(_p(c), ctypes.c_size_t(c.shape[0]), _p(z), _p(out))
+    return out
+
+
+def poly_lincomb(polys, scalars, out_len):
+    """sum_j scalars[j] * polys[j] (zero-extended) -> (out_len, 4); polys: list of (len_j, 4), scalars (k, 4), Montgomery."""
+    keep = [np.ascontiguousarray(p, dtype=np.uint64).reshape(-1, 4) for p in polys]
+    ptrs = (ctypes.c_void_p * len(keep))(*[p.ctypes.data if p.shape[0] else None for p in keep])
+    lens = (ctypes.c_size_t * len(keep))(*[p.shape[0] for p in keep])
+    sc = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((out_len, 4), dtype=np.uint64)
+    lib().zko_poly_lincomb(ctypes.c_size_t(len(keep)), ptrs, lens, _p(sc), _p(out), ctypes.c_size_t(out_len))
+    return out
+
+
+def poly_divide_linear(coeffs, z_limbs):
+    """((p(X) - p(z)) / (X - z) as (n - 1, 4), p(z) as (4,)), Montgomery."""
+    c = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+    z = np.ascontiguousarray(z_limbs, dtype=np.uint64)
+    quot = np.zeros((max(c.shape[0] - 1, 1), 4), dtype=np.uint64)
+    ev = np.zeros(4, dtype=np.uint64)
+    lib().zko_poly_divide_linear(_p(c), ctypes.c_size_t(c.shape[0]), _p(z), _p(quot), _p(ev))
+    return quot[: max(c.shape[0] - 1, 0)], ev
+
+
 def num_threads():
     return lib().zko_num_threads()
 

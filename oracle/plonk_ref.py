@@ -101,33 +101,54 @@ class OracleBackend:
         return cref.ntt(ev, log_n + 2, True, True)
 
     def evaluate(self, poly, z):
-        acc = 0
-        for cf in reversed(mont_array_to_ints(poly.data[: poly.len])):
-            acc = (acc * z + cf) % P
-        return acc
+        return limbs_to_fr(cref.poly_eval(poly.data[: poly.len], fr_to_limbs(z))) if poly.len else 0
 
     def lincomb(self, polys, scalars, cap=None):
         m = max(p.len for p in polys)
-        acc = [0] * m
-        for p, s in zip(polys, scalars):
-            for k, cf in enumerate(mont_array_to_ints(p.data[: p.len])):
-                acc[k] = (acc[k] + s * cf) % P
+        sc = np.stack([fr_to_limbs(x % P) for x in scalars])
         buf = np.zeros((cap or m, 4), dtype=np.uint64)
-        buf[:m] = ints_to_mont_array(acc)
+        buf[:m] = cref.poly_lincomb([p.data[: p.len] for p in polys], sc, m)
         return Poly(buf, m)
 
     def divide_linear(self, poly, z):
-        cf = mont_array_to_ints(poly.data[: poly.len])
+        m = poly.len
+        buf = np.zeros((max(m - 1, 1), 4), dtype=np.uint64)
+        if m == 0:
+            return Poly(buf, 0), 0
+        quot, ev = cref.poly_divide_linear(poly.data[:m], fr_to_limbs(z))
+        if m > 1:
+            buf[: m - 1] = quot
+        return Poly(buf, m - 1), limbs_to_fr(ev)
+
+
+class PythonIntPolyOps:
+    """The three polynomial helpers above in plain Python integers (the definitions): tests check the C versions against
+    these on random polynomials."""
+
+    @staticmethod
+    def evaluate(coeffs, z):
+        acc = 0
+        for cf in reversed(coeffs):
+            acc = (acc * z + cf) % P
+        return acc
+
+    @staticmethod
+    def lincomb(polys, scalars):
+        m = max(len(p) for p in polys)
+        acc = [0] * m
+        for p, s in zip(polys, scalars):
+            for k, cf in enumerate(p):
+                acc[k] = (acc[k] + s * cf) % P
+        return acc
+
+    @staticmethod
+    def divide_linear(cf, z):
         m = len(cf)
         w, carry = [0] * max(m - 1, 0), 0
         for k in range(m - 1, 0, -1):
             carry = (cf[k] + z * carry) % P
             w[k - 1] = carry
-        ev = ((cf[0] if m else 0) + z * carry) % P
-        buf = np.zeros((max(m - 1, 1), 4), dtype=np.uint64)
-        if m > 1:
-            buf[: m - 1] = ints_to_mont_array(w)
-        return Poly(buf, max(m - 1, 0)), ev
+        return w, ((cf[0] if m else 0) + z * carry) % P
 
 
 # ------------------------------------------------------------------------------------------------ verifier

@@ -27,6 +27,11 @@
  *   zko_quotient_evals         plonk-core/src/proof_system/quotient_poly.rs:98-224 with
  *                              keys/arithmetic.rs:67-81, keys/permutation.rs:97-137, keys/lookup.rs:81-122
  *   zko_epk_free_tables        keys/mod.rs:109-119 (x_coset, zh_coset, l_1_coset)
+ *   zko_poly_eval              ark-poly 0.3 DensePolynomial::evaluate (Horner), as used by
+ *                              linearization_poly.rs:55-75
+ *   zko_poly_lincomb           the axpy chains of linearization_poly.rs:77-111 and SonicKZG10::open's
+ *                              combination with powers of the opening challenge
+ *   zko_poly_divide_linear     ark-poly-commit 0.3 kzg10::compute_witness_polynomial: (p(X) - p(z)) / (X - z)
  */
 #include <stdint.h>
 #include <stddef.h>
@@ -543,6 +548,53 @@ API void zko_quotient_evals(unsigned log_n, const u64 *ch, const u64 *const *wit
         fp_inv(&zi, &zh[i], &FR);
         fp_mul(&out[i], &sum, &zi, &FR);
     }
+}
+
+/* out = sum_k coeffs[k] z^k (Montgomery in and out) */
+API void zko_poly_eval(const u64 *coeffs_, size_t n, const u64 *z_, u64 *out_) {
+    const fe *c = (const fe *)coeffs_;
+    fe z, acc;
+    memcpy(z.l, z_, 32);
+    memset(&acc, 0, sizeof acc);
+    for (size_t k = n; k-- > 0;) {
+        fp_mul(&acc, &acc, &z, &FR);
+        fp_add(&acc, &acc, &c[k], &FR);
+    }
+    memcpy(out_, acc.l, 32);
+}
+
+/* out[i] = sum_j scalars[j] * polys[j][i] for i < out_len (polynomial j has lens[j] coefficients) */
+API void zko_poly_lincomb(size_t k, const u64 *const *polys, const size_t *lens, const u64 *scalars_, u64 *out_, size_t out_len) {
+    fe *out = (fe *)out_;
+    const fe *sc = (const fe *)scalars_;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)out_len; ++i) {
+        fe acc, t;
+        memset(&acc, 0, sizeof acc);
+        for (size_t j = 0; j < k; ++j) {
+            if ((size_t)i >= lens[j]) continue;
+            fp_mul(&t, &sc[j], &((const fe *)polys[j])[i], &FR);
+            fp_add(&acc, &acc, &t, &FR);
+        }
+        out[i] = acc;
+    }
+}
+
+/* quot (n - 1 coefficients) = (p(X) - p(z)) / (X - z) by synthetic division from the top; eval = p(z) */
+API void zko_poly_divide_linear(const u64 *coeffs_, size_t n, const u64 *z_, u64 *quot_, u64 *eval_) {
+    const fe *c = (const fe *)coeffs_;
+    fe *q = (fe *)quot_;
+    fe z, carry, t;
+    memcpy(z.l, z_, 32);
+    memset(&carry, 0, sizeof carry);
+    for (size_t k = n; k-- > 1;) {
+        fp_mul(&t, &z, &carry, &FR);
+        fp_add(&carry, &c[k], &t, &FR);
+        q[k - 1] = carry;
+    }
+    fp_mul(&t, &z, &carry, &FR);
+    if (n) fp_add(&t, &t, &c[0], &FR);
+    memcpy(eval_, t.l, 32);
 }
 
 API int zko_num_threads(void) {

@@ -166,3 +166,32 @@ def test_quotient_and_free_tables_vs_python():
     got = cref.quotient_evals(log_n, m([ch[k] for k in ("alpha", "beta", "gamma", "delta", "epsilon")]),
                               {k: m(v) for k, v in wit.items()}, {k: m(v) for k, v in epk.items()})
     assert cref.limbs_to_ints(canon(cref.FR, got)) == pyref.quotient_coset_evals(log_n, ch, wit, epk)
+
+
+def test_c_polynomial_helpers_match_python_integers():
+    """zko_poly_eval / zko_poly_lincomb / zko_poly_divide_linear against the definitions in Python integers."""
+    import random
+    from oracle import plonk_ref
+    from zkt_plonk_b200.prover import P, Poly, ints_to_mont_array, mont_array_to_ints
+    rnd = random.Random(5)
+    be = plonk_ref.OracleBackend(np.zeros((1, 8), dtype=np.uint64))
+    ref = plonk_ref.PythonIntPolyOps
+    for n in (1, 2, 7, 64, 257):
+        cf = [rnd.randrange(P) for _ in range(n)]
+        z = rnd.randrange(P)
+        poly = Poly(ints_to_mont_array(cf), n)
+        assert be.evaluate(poly, z) == ref.evaluate(cf, z)
+        quot, ev = be.divide_linear(poly, z)
+        w, e = ref.divide_linear(cf, z)
+        assert ev == e and quot.len == n - 1 and mont_array_to_ints(quot.data[: quot.len]) == w
+        # (X - z) * quot + p(z) == p
+        if n == 1:
+            assert e == cf[0]
+            continue
+        back = [(-(z * w[0]) + e) % P] + [(w[k - 1] - z * w[k]) % P for k in range(1, n - 1)] + [w[-1]]
+        assert back == cf
+    polys = [[rnd.randrange(P) for _ in range(m)] for m in (5, 9, 1, 9)]
+    scalars = [rnd.randrange(P) for _ in polys]
+    got = be.lincomb([Poly(ints_to_mont_array(p), len(p)) for p in polys], scalars, cap=12)
+    assert got.len == 9 and mont_array_to_ints(got.data[:9]) == ref.lincomb(polys, scalars) and not got.data[9:].any()
+    assert be.evaluate(Poly(np.zeros((1, 4), dtype=np.uint64), 0), 5) == 0
