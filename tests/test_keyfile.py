@@ -156,6 +156,7 @@ def test_cvk_file_head_feeds_the_verifier(tmp_path, keys):
     be = plonk_ref.OracleBackend(plonk_ref.make_srs_host(circ.n + 8, TAU))
     raw = prover.prove(be, pk, vk, circ, list(range(3, 22))).to_bytes()
     assert verifier.verify(vk, raw, list(circ.pi.values()), (h, beta_h)) == 0
+    assert verifier.verify(vk, raw, list(circ.pi.values()), (h_arr, bh_arr)) == 0          # straight from the file
     path.write_bytes(path.read_bytes()[:300])
     with pytest.raises(_lib.ZkbError):
         keyfile.cvk_read(path)

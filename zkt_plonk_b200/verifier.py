@@ -26,6 +26,8 @@ def g1_array(pt):
 
 def g2_array(pt):
     """((x0, x1), (y0, y1)) canonical ints -> (16,) uint64: x.c0 x.c1 y.c0 y.c1 in Montgomery form (arkworks' G2Affine)."""
+    if isinstance(pt, np.ndarray):                       # already in the ABI's form (e.g. from keyfile.cvk_read)
+        return np.ascontiguousarray(pt, dtype=np.uint64).reshape(16)
     out = np.zeros(16, dtype=np.uint64)
     if pt is not None:
         (x0, x1), (y0, y1) = pt
@@ -40,7 +42,7 @@ def _vp(a):
 
 def verify(vk, proof_bytes, pub_inputs, cvk_g2, transcript="merlin"):
     """vk: prover.VerifierKey; proof_bytes: the 802 serialised bytes; pub_inputs: canonical ints, one per vk.pi_roots entry;
-    cvk_g2 = (h, beta_h) as Fq2 coordinate tuples.  Returns 0 (accepted), 1 or 2 (failing step); raises on malformed input."""
+    cvk_g2 = (h, beta_h) as Fq2 coordinate tuples of canonical ints or as the (16,) arrays keyfile.cvk_read returns.  Returns 0 (accepted), 1 or 2 (failing step); raises on malformed input."""
     assert len(proof_bytes) == 802 and len(pub_inputs) == len(vk.pi_roots), "invalid length of public inputs"
     xy = np.stack([g1_array(vk.commits[name]) for name in VerifierKey.ORDER])
     inf = (ctypes.c_int * 10)(*[int(vk.commits[name] is None) for name in VerifierKey.ORDER])
