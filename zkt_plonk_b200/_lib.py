@@ -98,6 +98,7 @@ def load():
         "zkb_plonk_verify": (i, [sz, vp, sz, vp, ctypes.POINTER(i), vp, vp, vp, vp, i]),
         "zkb_pairing": (i, [vp, vp, vp]),
         "zkb_pairing_product_is_one": (i, [vp, vp, sz, ctypes.POINTER(i)]),
+        "zkb_probe_batch_affine": (i, [vp, vp, u, i, u, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u)]),
         "zkb_launch_count": (ctypes.c_uint64, [vp]),
         "zkb_msm_last_timing": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),
         "zkb_bench_int": (i, [vp, i, ctypes.POINTER(ctypes.c_double)]),

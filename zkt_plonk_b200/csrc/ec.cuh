@@ -35,7 +35,7 @@ __device__ __forceinline__ g1x_t g1x_from_affine(const g1a_t &p) {
 }
 
 // 2 * (affine p), p finite  (mdbl-2008-s-1)
-__device__ __noinline__ g1x_t g1x_double_affine(const g1a_t &p) {
+static __device__ __noinline__ g1x_t g1x_double_affine(const g1a_t &p) {
     g1x_t r;
     fe_t u = fdbl<Q>(p.y);
     fe_t v = fsqr<Q>(u);
@@ -51,7 +51,7 @@ __device__ __noinline__ g1x_t g1x_double_affine(const g1a_t &p) {
 }
 
 // 2 * p  (dbl-2008-s-1)
-__device__ __noinline__ g1x_t g1x_double(const g1x_t &p) {
+static __device__ __noinline__ g1x_t g1x_double(const g1x_t &p) {
     if (g1x_is_inf(p)) return p;
     g1x_t r;
     fe_t u = fdbl<Q>(p.y);
@@ -142,7 +142,7 @@ __device__ __forceinline__ void g1x_store(void *p, const g1x_t &a) {
 }
 
 // XYZZ -> affine on the device (one field inversion; used off the critical path and in tests)
-__device__ __noinline__ g1a_t g1x_to_affine(const g1x_t &p) {
+static __device__ __noinline__ g1a_t g1x_to_affine(const g1x_t &p) {
     g1a_t r;
     if (g1x_is_inf(p)) { r.x = fzero<Q>(); r.y = fzero<Q>(); return r; }
     fe_t zi = finv<Q>(p.zzz);                    // 1/ZZZ
