@@ -311,7 +311,8 @@ ZKB_API int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec);
 /* EXPERIMENT (csrc/probe_batch_affine.cu): bucket-accumulation inner loop as XYZZ mixed additions (what the
  * product runs) against batch-affine additions with one shared inversion per CTA and step (binary extended Euclid on the
  * ALU pipe), on the same points.  table_dev: 2^log_table distinct affine points in HBM; m: accumulators per thread of the
- * batch-affine kernel (4 or 8); steps: additions per accumulator.  out[0] / out[1]: additions per second of the two loops;
+ * batch-affine kernel (4 or 8: accumulators in shared memory; -4, -8, -16: in global memory / L2); steps: additions per
+ * accumulator.  out[0] / out[1]: additions per second of the two loops;
  * *mismatches: accumulators whose results differ (must be 0). */
 ZKB_API int zkb_probe_batch_affine(zkb_ctx *ctx, const uint64_t *table_dev, unsigned log_table, int m, unsigned steps, double out[2],
                            unsigned *mismatches);

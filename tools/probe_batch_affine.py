@@ -19,7 +19,7 @@ k = torch.from_numpy(uniform_scalars(n, 11).view(np.int64)).cuda()
 table = torch.empty((n, 8), dtype=torch.int64, device="cuda")
 ctx.g1_fixed_base_mul_dev(G, k, n, table)
 torch.cuda.synchronize()
-for m in (4, 8):
+for m in (4, 8, -4, -8, -16):        # negative: accumulators in global memory (L2) instead of shared memory
     out = (ctypes.c_double * 2)()
     mis = ctypes.c_uint(0)
     ctx._check(ctx._lib.zkb_probe_batch_affine(ctx._h, ctypes.c_void_p(table.data_ptr()), args.log_table, m, args.steps, out, ctypes.byref(mis)))

@@ -120,28 +120,32 @@ __global__ void __launch_bounds__(PB_THREADS) pb_to_affine_kernel(const g1x_t *i
 }
 
 // ---- mode 1: batch-affine with one inversion per CTA and step
-// shared memory: accumulators [M][128] (x, y), prefixes [M][128], tree [2 * 128]
-template <int M>
+// shared memory: prefixes [M][128], tree [2 * 128] and, unless GACC, the accumulators [M][128] (x, y).  GACC keeps the
+// accumulators in global memory (`out` itself: L2-resident, as the bucket array of the real kernel would be), which
+// leaves room for more resident CTAs to hide the inversion of the others.
+template <int M, bool GACC>
 __global__ void __launch_bounds__(PB_THREADS) pb_affine_kernel(const g1a_t *__restrict__ table, uint32_t tmask, uint32_t steps, g1a_t *out) {
     extern __shared__ uint4 pb_sm[];
-    fe_t *ax = reinterpret_cast<fe_t *>(pb_sm);                  // [M * 128]
-    fe_t *ay = ax + M * PB_THREADS;
-    fe_t *pre = ay + M * PB_THREADS;                             // prefix products of the thread's differences
+    fe_t *pre = reinterpret_cast<fe_t *>(pb_sm);                 // prefix products of the thread's differences [M * 128]
     fe_t *tree = pre + M * PB_THREADS;                           // node k = node 2k * node 2k+1; leaves at 128 + t
+    fe_t *sax = tree + 2 * PB_THREADS;                           // shared-memory accumulators (unused with GACC)
+    fe_t *say = sax + M * PB_THREADS;
     const uint32_t t = threadIdx.x;
     // accumulator ids are laid out so that mode 0's thread `id` and this kernel's slot (block, i, t) coincide
     auto gid = [&](int i) { return (blockIdx.x * M + i) * PB_THREADS + t; };
+    auto px = [&](int i) -> fe_t * { return GACC ? &out[gid(i)].x : &sax[i * PB_THREADS + t]; };
+    auto py = [&](int i) -> fe_t * { return GACC ? &out[gid(i)].y : &say[i * PB_THREADS + t]; };
     for (int i = 0; i < M; ++i) {
         g1a_t p = g1a_load(table + pb_start(gid(i), tmask));
-        fstore(&ax[i * PB_THREADS + t], p.x);
-        fstore(&ay[i * PB_THREADS + t], p.y);
+        fstore(px(i), p.x);
+        fstore(py(i), p.y);
     }
     for (uint32_t s = 0; s < steps; ++s) {
         // 1. differences and their running product
         fe_t run;
         for (int i = 0; i < M; ++i) {
             fe_t x2 = fload_ro(&table[pb_index(gid(i), s, tmask)].x);
-            fe_t d = fsub<Q>(x2, fload(&ax[i * PB_THREADS + t]));
+            fe_t d = fsub<Q>(x2, fload(px(i)));
             run = i ? fmul<Q>(run, d) : d;
             fstore(&pre[i * PB_THREADS + t], run);
         }
@@ -168,22 +172,23 @@ __global__ void __launch_bounds__(PB_THREADS) pb_affine_kernel(const g1a_t *__re
         fe_t inv_run = fload(&tree[PB_THREADS + t]);
         for (int i = M - 1; i >= 0; --i) {
             g1a_t p2 = g1a_load(table + pb_index(gid(i), s, tmask));
-            fe_t x1 = fload(&ax[i * PB_THREADS + t]), y1 = fload(&ay[i * PB_THREADS + t]);
+            fe_t x1 = fload(px(i)), y1 = fload(py(i));
             fe_t d = fsub<Q>(p2.x, x1);
             fe_t inv_d = i ? fmul<Q>(inv_run, fload(&pre[(i - 1) * PB_THREADS + t])) : inv_run;
             if (i) inv_run = fmul<Q>(inv_run, d);
             fe_t lam = fmul<Q>(fsub<Q>(p2.y, y1), inv_d);
             fe_t x3 = fsub<Q>(fsub<Q>(fsqr<Q>(lam), x1), p2.x);
             fe_t y3 = fsub<Q>(fmul<Q>(lam, fsub<Q>(x1, x3)), y1);
-            fstore(&ax[i * PB_THREADS + t], x3);
-            fstore(&ay[i * PB_THREADS + t], y3);
+            fstore(px(i), x3);
+            fstore(py(i), y3);
         }
         __syncthreads();                                          // tree and prefixes are rewritten by the next step
     }
-    for (int i = 0; i < M; ++i) {
-        fstore(&out[gid(i)].x, fload(&ax[i * PB_THREADS + t]));
-        fstore(&out[gid(i)].y, fload(&ay[i * PB_THREADS + t]));
-    }
+    if (!GACC)
+        for (int i = 0; i < M; ++i) {
+            fstore(&out[gid(i)].x, fload(px(i)));
+            fstore(&out[gid(i)].y, fload(py(i)));
+        }
 }
 
 __global__ void pb_compare_kernel(const g1a_t *a, const g1a_t *b, uint32_t n, uint32_t *mismatches) {
@@ -193,17 +198,17 @@ __global__ void pb_compare_kernel(const g1a_t *a, const g1a_t *b, uint32_t n, ui
     if (!feq(ax, bx) || !feq(ay, by)) atomicAdd(mismatches, 1u);
 }
 
-template <int M>
+template <int M, bool GACC>
 int run_affine(zkb_ctx *ctx, const g1a_t *table, uint32_t tmask, uint32_t steps, uint32_t blocks, g1a_t *out, float *ms) {
-    const size_t smem = ((size_t)3 * M * PB_THREADS + 2 * PB_THREADS) * sizeof(fe_t);
-    ZKB_CUDA(ctx, cudaFuncSetAttribute(pb_affine_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = ((size_t)(GACC ? 1 : 3) * M * PB_THREADS + 2 * PB_THREADS) * sizeof(fe_t);
+    ZKB_CUDA(ctx, cudaFuncSetAttribute(pb_affine_kernel<M, GACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;
     ZKB_CUDA(ctx, cudaEventCreate(&e0));
     ZKB_CUDA(ctx, cudaEventCreate(&e1));
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         ZKB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-        pb_affine_kernel<M><<<blocks, PB_THREADS, smem, ctx->stream>>>(table, tmask, steps, out);
+        pb_affine_kernel<M, GACC><<<blocks, PB_THREADS, smem, ctx->stream>>>(table, tmask, steps, out);
         ZKB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
         ZKB_CUDA(ctx, cudaEventSynchronize(e1));
         ZKB_CUDA(ctx, cudaGetLastError());
@@ -222,12 +227,16 @@ int run_affine(zkb_ctx *ctx, const g1a_t *table, uint32_t tmask, uint32_t steps,
 extern "C" {
 
 // table_dev: 2^log_table distinct affine points in HBM (e.g. from zkb_g1_fixed_base_mul_dev); m = accumulators per thread
-// of the batch-affine kernel (4 or 8); steps = additions per accumulator.  out[0] = XYZZ additions / s, out[1] = batch-affine
+// of the batch-affine kernel (4, 8 or 16; negative: the same with the accumulators in global memory instead of shared
+// memory); steps = additions per accumulator.  out[0] = XYZZ additions / s, out[1] = batch-affine
 // additions / s, *mismatches = accumulators whose two results differ (must be 0).
 int zkb_probe_batch_affine(zkb_ctx *ctx, const uint64_t *table_dev, unsigned log_table, int m, unsigned steps, double out[2],
                            unsigned *mismatches) {
     if (!ctx || !table_dev || !out || !mismatches) return ZKB_ERR_INVALID;
-    if ((m != 4 && m != 8) || log_table < 4 || log_table > 24 || steps == 0) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_probe_batch_affine: m in {4, 8}, 4 <= log_table <= 24");
+    const bool gacc = m < 0;
+    if (gacc) m = -m;
+    if ((m != 4 && m != 8 && m != 16) || (m == 16 && !gacc) || log_table < 4 || log_table > 24 || steps == 0)
+        ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_probe_batch_affine: |m| in {4, 8, 16} (16 only with global accumulators), 4 <= log_table <= 24");
     const uint32_t tmask = (1u << log_table) - 1;
     const uint32_t blocks = (uint32_t)ctx->sm_count * 8;          // batch-affine CTAs; the XYZZ kernel runs blocks * m CTAs
     const uint32_t n_acc = blocks * (uint32_t)m * PB_THREADS;
@@ -256,7 +265,9 @@ int zkb_probe_batch_affine(zkb_ctx *ctx, const uint64_t *table_dev, unsigned log
     out[0] = (double)n_acc * steps / (best * 1e-3);
     pb_to_affine_kernel<<<blocks * m, PB_THREADS, 0, ctx->stream>>>(raw_x, n_acc, res_x);
     float ms = 0;
-    rc = m == 4 ? run_affine<4>(ctx, table, tmask, steps, blocks, res_a, &ms) : run_affine<8>(ctx, table, tmask, steps, blocks, res_a, &ms);
+    if (!gacc) rc = m == 4 ? run_affine<4, false>(ctx, table, tmask, steps, blocks, res_a, &ms) : run_affine<8, false>(ctx, table, tmask, steps, blocks, res_a, &ms);
+    else rc = m == 4 ? run_affine<4, true>(ctx, table, tmask, steps, blocks, res_a, &ms)
+            : m == 8 ? run_affine<8, true>(ctx, table, tmask, steps, blocks, res_a, &ms) : run_affine<16, true>(ctx, table, tmask, steps, blocks, res_a, &ms);
     if (rc) return rc;
     out[1] = (double)n_acc * steps / (ms * 1e-3);
     ZKB_CUDA(ctx, cudaMemsetAsync(d_mis, 0, 4, ctx->stream));
