@@ -11,6 +11,9 @@
 //   zkb::compute_z2_poly          plonk-core/src/lookup/mod.rs:25-85
 //   zkb::quotient_compute         plonk-core/src/proof_system/quotient_poly.rs:20-227
 //   zkb::extend_prover_key        plonk-core/src/proof_system/keys/mod.rs:78-146
+//   zkb::PlonkKey                 proof_system::setup / prove behind zkb_plonk_setup, zkb_plonk_load_keys, zkb_plonk_prove
+//                                 (setup.rs:42-166, prove.rs:59-470; key files of bin/src/parser.rs:5-29)
+//   zkb::verify                   Proof::verify (proof_system/proof.rs:285-503), host side
 //
 // Errors: the reference returns Error::InvalidEvalDomainSize / PC errors or panics on broken invariants; here every
 // failure is a zkb::Error exception carrying the zkb_status code and the library's message (nothing crosses the C
@@ -23,6 +26,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "zkb200.h"
@@ -282,6 +286,108 @@ inline DensePolynomial quotient_compute(const GpuDomain &domain, const ExtendedP
     out.download(q.data(), q.size() * 32);
     truncate(q);
     return q;
+}
+
+// ---------------------------------------------------------------------------------------------------- whole prover / verifier
+enum class Transcript : int { Merlin = 0, Ethereum = 1 };      // the T: TranscriptProtocol parameter (plonk.rs:39-46)
+
+struct VerifierKeyData {                                       // keys/mod.rs:180-203, in this boundary's forms
+    size_t n = 0;
+    std::vector<Fr> pi_roots;
+    std::array<G1Affine, 10> commitments{};                    // q_m q_l q_r q_o q_c sigma1 sigma2 sigma3 q_lookup q_table
+};
+
+struct G2Affine {                                              // x.c0 x.c1 y.c0 y.c1, Montgomery Fq (arkworks' in-memory order)
+    uint64_t w[16];
+};
+
+// A proving key resident in HBM (ProverKey + ExtendedProverKey + VerifierKey commitments); the committer key must already
+// be resident in the context (GpuKZG10::trim / zkb_srs_load_ck_file).
+class PlonkKey {
+  public:
+    // proof_system::setup with extend = true, from the composer's padded columns (n = 2^log_n elements each)
+    static PlonkKey setup(const Context &ctx, unsigned log_n, const std::array<const std::vector<Fr> *, 6> &selectors /* q_m q_l q_r q_o q_c q_lookup */,
+                          const std::array<const std::vector<Fr> *, 3> &sigma_evals, size_t table_size, const std::vector<size_t> &pi_positions) {
+        const size_t n = size_t(1) << log_n;
+        const uint64_t *s[6], *g[3];
+        for (int k = 0; k < 6; ++k) {
+            if (selectors[k]->size() != n) throw Error(ZKB_ERR_INVALID, "PlonkKey::setup: selector column must hold n elements");
+            s[k] = selectors[k]->data()->l;
+        }
+        for (int k = 0; k < 3; ++k) {
+            if (sigma_evals[k]->size() != n) throw Error(ZKB_ERR_INVALID, "PlonkKey::setup: sigma column must hold n elements");
+            g[k] = sigma_evals[k]->data()->l;
+        }
+        zkb_plonk_pk *pk = nullptr;
+        ctx.check(zkb_plonk_setup(ctx.raw(), log_n, s, g, table_size, pi_positions.data(), pi_positions.size(), &pk));
+        return PlonkKey(ctx, pk);
+    }
+    // deserialize_from_file::<ProverKey> + ::<VerifierKey> (bin/src/main.rs:274-281)
+    static PlonkKey load(const Context &ctx, const std::string &pk_path, const std::string &vk_path, size_t table_size) {
+        zkb_plonk_pk *pk = nullptr;
+        ctx.check(zkb_plonk_load_keys(ctx.raw(), pk_path.c_str(), vk_path.c_str(), table_size, &pk));
+        return PlonkKey(ctx, pk);
+    }
+    void save(const std::string &pk_path, const std::string &vk_path) const {
+        ctx_.check(zkb_plonk_save_keys(ctx_.raw(), pk_.get(), pk_path.c_str(), vk_path.c_str()));
+    }
+    void set_transcript(Transcript t) { ctx_.check(zkb_plonk_pk_set_transcript(pk_.get(), static_cast<int>(t))); }
+    std::array<G1Affine, 10> vk_commitments() const {
+        std::array<G1Affine, 10> out{};
+        ctx_.check(zkb_plonk_vk_commitments(pk_.get(), reinterpret_cast<uint64_t *>(out.data()), nullptr));
+        return out;
+    }
+    // proof_system::prove: padded wires, the lookup table's entries, one value per public-input row, the 19 blinders in
+    // the reference's draw order.  Returns Proof's 802 serialised bytes.
+    std::array<uint8_t, 802> prove(const std::vector<Fr> &a, const std::vector<Fr> &b, const std::vector<Fr> &c, const std::vector<Fr> &table,
+                                   const std::vector<Fr> &pi_values, const std::array<Fr, 19> &blinders) const {
+        std::array<uint8_t, 802> out{};
+        const Fr zero{{0, 0, 0, 0}};
+        ctx_.check(zkb_plonk_prove(ctx_.raw(), pk_.get(), a.data()->l, b.data()->l, c.data()->l, table.empty() ? zero.l : table.data()->l,
+                                   table.size(), pi_values.empty() ? zero.l : pi_values.data()->l, blinders.data()->l, out.data(), nullptr));
+        return out;
+    }
+
+  private:
+    PlonkKey(const Context &ctx, zkb_plonk_pk *pk) : ctx_(ctx) {
+        zkb_ctx *raw = ctx.raw();
+        pk_ = std::shared_ptr<zkb_plonk_pk>(pk, [raw](zkb_plonk_pk *p) { zkb_plonk_pk_destroy(raw, p); });
+    }
+    Context ctx_;                                               // keeps the context alive as long as the key
+    std::shared_ptr<zkb_plonk_pk> pk_;
+};
+
+// Proof::verify: 0 = accepted, 1 / 2 = Error::ProofVerificationError { step }; throws on malformed input.  Host code, no GPU.
+inline int verify(const VerifierKeyData &vk, const std::vector<Fr> &pub_inputs, const std::array<uint8_t, 802> &proof, const G2Affine &h,
+                  const G2Affine &beta_h, Transcript t = Transcript::Merlin) {
+    if (pub_inputs.size() != vk.pi_roots.size()) throw Error(ZKB_ERR_INVALID, "invalid length of public inputs");
+    const Fr zero{{0, 0, 0, 0}};
+    int rc = zkb_plonk_verify(vk.n, vk.pi_roots.empty() ? zero.l : vk.pi_roots.data()->l, vk.pi_roots.size(),
+                              reinterpret_cast<const uint64_t *>(vk.commitments.data()), nullptr, pub_inputs.empty() ? zero.l : pub_inputs.data()->l,
+                              proof.data(), h.w, beta_h.w, static_cast<int>(t));
+    if (rc < 0) throw Error(rc, "zkb_plonk_verify: malformed verifier key, proof or G2 elements");
+    return rc;
+}
+
+// deserialize_from_file::<VerifierKey> (vk) and the G2 half of the commitment verifier key (cvk)
+inline VerifierKeyData read_vk_file(const std::string &path) {
+    VerifierKeyData vk;
+    size_t n_roots = 0;
+    int inf[10];
+    if (zkb_vk_file_read(path.c_str(), &vk.n, nullptr, 0, &n_roots, reinterpret_cast<uint64_t *>(vk.commitments.data()), inf) != ZKB_OK)
+        throw Error(ZKB_ERR_INVALID, path + ": not a VerifierKey file");
+    vk.pi_roots.resize(n_roots);
+    Fr dummy;
+    if (zkb_vk_file_read(path.c_str(), &vk.n, n_roots ? vk.pi_roots.data()->l : dummy.l, n_roots, &n_roots,
+                         reinterpret_cast<uint64_t *>(vk.commitments.data()), inf) != ZKB_OK)
+        throw Error(ZKB_ERR_INVALID, path + ": cannot re-read the VerifierKey file");
+    return vk;
+}
+inline std::pair<G2Affine, G2Affine> read_cvk_file(const std::string &path) {
+    std::pair<G2Affine, G2Affine> out{};
+    if (zkb_cvk_file_read(path.c_str(), nullptr, nullptr, out.first.w, out.second.w) != ZKB_OK)
+        throw Error(ZKB_ERR_INVALID, path + ": not a sonic_pc::VerifierKey file");
+    return out;
 }
 
 }  // namespace zkb

@@ -95,3 +95,23 @@ def test_verifier_refuses_malformed_input(proved):
         verifier.verify(vk, bytes(bad), pub, cvk)
     with pytest.raises(_lib.ZkbError):
         verifier.verify(vk, bytes(raw), pub, (((1, 2), (3, 4)), cvk[1]))              # h not on the twist
+
+
+def test_cpp_mirror_reads_key_files_and_verifies(tmp_path, proved):
+    """include/zkb200.hpp's host-only half (zkb::read_vk_file, zkb::read_cvk_file, zkb::verify) in a C++ program
+    (tests/cpp/test_mirror_host.cpp): files written by the Python restatement, a proof from the oracle backend."""
+    import os
+    import subprocess
+    from oracle import arkser
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "tests", "cpp"), "-s", "test_mirror_host"])
+    circ, vk, proofs = proved
+    h, beta_h = plonk_ref.make_cvk(TAU)
+    (tmp_path / "vk").write_bytes(arkser.verifier_key(vk.n, vk.pi_roots, vk.commits))
+    (tmp_path / "cvk").write_bytes(arkser.sonic_verifier_key(pyref.G1_GEN, pyref.G1_GEN, h, beta_h, 4 * circ.n, 4 * circ.n))
+    (tmp_path / "proof").write_bytes(proofs["merlin"])
+    (tmp_path / "pub").write_bytes(prover.ints_to_mont_array(list(circ.pi.values())).tobytes())
+    out = subprocess.run([os.path.join(root, "tests", "cpp", "test_mirror_host")] + [str(tmp_path / f) for f in ("vk", "cvk", "proof", "pub")],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert f"n={vk.n} roots={len(vk.pi_roots)} verify=0" in out.stdout
