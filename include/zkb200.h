@@ -126,6 +126,10 @@ ZKB_API int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], c
                               uint64_t *out_points_dev);
 /* Force the window size c (0 = automatic cost model).  For tests and tuning. */
 ZKB_API int zkb_msm_set_window(zkb_ctx *ctx, int c);
+/* Bucket-accumulation kernel: 0 = XYZZ mixed additions (default, the measured path); 1 = EXPERIMENTAL batched affine
+ * additions with one shared inversion per CTA and step (csrc/msm_affine.cu).  Same results either way.
+ * ZKB_MSM_MODE=1 in the environment selects mode 1 for contexts created afterwards. */
+ZKB_API int zkb_msm_set_mode(zkb_ctx *ctx, int mode);
 
 /* ---- grand products, quotient, polynomial utilities (all device-resident, enqueue on the context's stream) -------------- */
 /* compute_z1_poly before its final iFFT (plonk-core/src/permutation/mod.rs:181-254): out[0] = 1,

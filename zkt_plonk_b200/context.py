@@ -97,6 +97,10 @@ class Context:
         import os
         self._check(self._lib.zkb_srs_load_ck_file(self._h, os.fsencode(path), int(max_points)))
 
+    def set_msm_mode(self, mode):
+        """0: XYZZ bucket accumulation (default); 1: EXPERIMENTAL batched affine additions (csrc/msm_affine.cu)."""
+        self._check(self._lib.zkb_msm_set_mode(self._h, int(mode)))
+
     def srs_precompute(self, c=0):
         """Build (c >= 0) or drop (c < 0) the fixed-base window tables of the resident SRS."""
         self._check(self._lib.zkb_srs_precompute(self._h, int(c)))

@@ -1,4 +1,6 @@
 // api.cu -- extern "C" boundary of libzkb200.so (include/zkb200.h): context, memory, host-pointer wrappers.
+#include <stdlib.h>
+
 #include "ctx.h"
 #include "ff.cuh"
 #include "ff52.cuh"
@@ -154,6 +156,8 @@ int zkb_ctx_create(int device, zkb_ctx **out) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    const char *mode = getenv("ZKB_MSM_MODE");                  // "1": experimental batch-affine bucket accumulation (msm_affine.cu)
+    if (mode && mode[0] == '1' && mode[1] == 0) ctx->msm_mode = 1;
     *out = ctx;
     return ZKB_OK;
 }

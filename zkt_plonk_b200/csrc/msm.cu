@@ -685,9 +685,15 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     if (rc) return rc;
     msm_task_scatter_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, ws.ntasks, nb, pl.seg, ws.size_cursor, ws.task_order);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[1], s));
-    msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, ws.sorted, ws.counts, ws.starts, ws.ntasks,
-                                                                             ws.task_base, ws.task_order, ws.misc, pl.seg, ws.task_out,
-                                                                             ws.bucket_val);
+    if (ctx->msm_mode == 1) {                                   // EXPERIMENTAL: batched affine additions (msm_affine.cu)
+        rc = zkb_launch_accumulate_affine(ctx, s, max_tasks, d_points, ws.sorted, ws.counts, ws.starts, ws.ntasks, ws.task_base,
+                                          ws.task_order, ws.misc, pl.seg, ws.task_out, ws.bucket_val);
+        if (rc) return rc;
+    } else {
+        msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, ws.sorted, ws.counts, ws.starts, ws.ntasks,
+                                                                                 ws.task_base, ws.task_order, ws.misc, pl.seg, ws.task_out,
+                                                                                 ws.bucket_val);
+    }
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[2], s));
     msm_combine_heavy_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out,
                                                                ws.bucket_val);
@@ -847,6 +853,13 @@ int zkb_srs_precompute(zkb_ctx *ctx, int c) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cudaFree(fb->rows.p); delete fb; ctx->err = cudaGetErrorString(e); return ZKB_ERR_CUDA; }
     st->fixed_base = fb;
+    return ZKB_OK;
+}
+
+int zkb_msm_set_mode(zkb_ctx *ctx, int mode) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (mode != 0 && mode != 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_set_mode: 0 = XYZZ accumulation, 1 = experimental batch-affine accumulation");
+    ctx->msm_mode = mode;
     return ZKB_OK;
 }
 
