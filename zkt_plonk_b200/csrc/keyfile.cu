@@ -31,6 +31,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -185,7 +186,12 @@ int zkb_srs_load_ck_file(zkb_ctx *ctx, const char *path, size_t max_points) {
     if (rc) ZKB_FAIL(ctx, rc, "zkb_srs_load_ck_file: not a sonic_pc::CommitterKey file written without degree bounds");
     if (max_points && max_points < n) n = max_points;
     if (n == 0) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_load_ck_file: the key holds no powers");
-    std::vector<uint64_t> xy(8 * n);
+    std::vector<uint64_t> xy;
+    try {
+        xy.resize(8 * n);                                          // nothing may throw across the C boundary
+    } catch (const std::bad_alloc &) {
+        ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_srs_load_ck_file: not enough host memory for the committer key");
+    }
     rc = zkb_ck_file_read(path, 0, n, xy.data());
     if (rc) ZKB_FAIL(ctx, rc, "zkb_srs_load_ck_file: a coordinate is not a canonical Fq element");
     return zkb_srs_load_g1(ctx, xy.data(), n);

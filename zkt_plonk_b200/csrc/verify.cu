@@ -409,6 +409,7 @@ int zkb_pairing(const uint64_t g1_xy[8], const uint64_t g2_xy[16], uint64_t out_
 int zkb_pairing_product_is_one(const uint64_t *g1_xy, const uint64_t *g2_xy, size_t count, int *is_one) {
     if ((!g1_xy || !g2_xy) && count) return ZKB_ERR_INVALID;
     if (!is_one) return ZKB_ERR_INVALID;
+    if (count > (1u << 20)) return ZKB_ERR_INVALID;               // a pairing product has a handful of factors
     std::vector<Pt> ps(count);
     std::vector<G2> qs(count);
     for (size_t i = 0; i < count; ++i) {
