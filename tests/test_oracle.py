@@ -195,3 +195,20 @@ def test_c_polynomial_helpers_match_python_integers():
     got = be.lincomb([Poly(ints_to_mont_array(p), len(p)) for p in polys], scalars, cap=12)
     assert got.len == 9 and mont_array_to_ints(got.data[:9]) == ref.lincomb(polys, scalars) and not got.data[9:].any()
     assert be.evaluate(Poly(np.zeros((1, 4), dtype=np.uint64), 0), 5) == 0
+
+
+def test_permutation_coset_constants_like_the_reference():
+    """permutation/constants.rs:33-50 (test_constants) on BN254: K1 = 7 and K2 = 13 generate valid, distinct cosets of the
+    largest radix-2 subgroup (size 2^28): K1^(2^28) != 1, K2^(2^28) != 1 and (K1 / K2)^(2^28) != 1; also the domain generator
+    the NTTs use is the one arkworks derives (g = 5, omega = 5^((r - 1) / 2^28))."""
+    r = pyref.R_MOD
+    n = 1 << 28
+    assert (r - 1) % n == 0 and (r - 1) % (2 * n) != 0                      # two-adicity of Fr is exactly 28
+    assert pyref.K1 == 7 and pyref.K2 == 13
+    assert pow(pyref.K1, n, r) != 1 and pow(pyref.K2, n, r) != 1
+    assert pow(pyref.K1 * pow(pyref.K2, -1, r) % r, n, r) != 1
+    w = pow(5, (r - 1) // n, r)
+    assert w == 19103219067921713944291392827692070036145651957329286315305642004821462161904     # SURVEY.md section 8
+    assert pow(w, n, r) == 1 and pow(w, n // 2, r) == r - 1
+    from zkt_plonk_b200 import field
+    assert field.root_of_unity(28) == w and field.root_of_unity(10) == pow(w, 1 << 18, r)
