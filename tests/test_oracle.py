@@ -212,3 +212,26 @@ def test_permutation_coset_constants_like_the_reference():
     assert pow(w, n, r) == 1 and pow(w, n // 2, r) == r - 1
     from zkt_plonk_b200 import field
     assert field.root_of_unity(28) == w and field.root_of_unity(10) == pow(w, 1 << 18, r)
+
+
+def test_z2_identity_with_the_reference_tests_vectors():
+    """lookup/mod.rs:101-164 (test_compute_z2_poly): t = {0,0,1,2,3,4,5,6}, f = {3,6,0,5,4,3,2,0}, (h1, h2) = combine_split;
+    for every domain element  (1+d)(e+f)(d t(wx) + e(1+d) + t) z2(x) == (d h2 + e(1+d) + h1)(d h1(wx) + e(1+d) + h2) z2(wx)
+    and z2(1) = 1.  On the domain the polynomial evaluations are the vectors themselves (next row = index + 1 mod n)."""
+    from zkt_plonk_b200 import prover
+    p = pyref.R_MOD
+    rnd = random.Random(31)
+    t, f = [0, 0, 1, 2, 3, 4, 5, 6], [3, 6, 0, 5, 4, 3, 2, 0]
+    h1, h2 = prover.combine_split(t, f)
+    assert len(h1) == len(h2) == 8 and sorted(h1 + h2) == sorted(t + f)
+    delta, eps = rnd.randrange(p), rnd.randrange(p)
+    z2 = cref.limbs_to_ints(cref.from_mont(cref.FR, cref.z2_evals(
+        3, cref.to_mont(cref.FR, cref.ints_to_limbs([delta]))[0], cref.to_mont(cref.FR, cref.ints_to_limbs([eps]))[0],
+        *[cref.to_mont(cref.FR, cref.ints_to_limbs(v)) for v in (f, t, h1, h2)])))
+    assert z2 == pyref.z2_evals(3, delta, eps, f, t, h1, h2) and z2[0] == 1
+    opd, eopd = (1 + delta) % p, eps * (1 + delta) % p
+    for i in range(8):
+        j = (i + 1) % 8
+        part_1 = opd * (eps + f[i]) % p * (delta * t[j] + eopd + t[i]) % p * z2[i] % p
+        part_2 = (delta * h2[i] + eopd + h1[i]) % p * (delta * h1[j] + eopd + h2[i]) % p * z2[j] % p
+        assert part_1 == part_2, i
