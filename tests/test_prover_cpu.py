@@ -28,14 +28,16 @@ def test_challenge_scalar_is_31_bytes_le():
     assert v == int.from_bytes(b.challenge_bytes(b"beta", 31), "little") and v < 1 << 248
 
 
-def test_combine_split_matches_reference_unit_test_shape():
-    """multiset.rs:272-329: halves alternate, every element of f must be in t."""
-    t, f = [0, 1, 2, 3, 4, 5, 6, 7], [3, 6, 0, 5, 4, 3, 2, 0, 0, 1, 2]
-    h1, h2 = prover.combine_split(t, f)
-    assert sorted(h1 + h2) == sorted(t + f) and abs(len(h1) - len(h2)) <= 1
-    assert h1 == [0, 0, 1, 2, 3, 3, 4, 5, 6, 7] or len(h1) + len(h2) == 19
+def test_combine_split_reference_golden_vector():
+    """multiset.rs:271-329 (test_combine_split): the reference's own expected halves for t = {0..6},
+    f = {3,6,0,5,4,3,2,0,0,1,2} -- both host implementations (Python lists, numpy limb rows)."""
+    t, f = [0, 1, 2, 3, 4, 5, 6], [3, 6, 0, 5, 4, 3, 2, 0, 0, 1, 2]
+    evens, odds = [0, 0, 1, 2, 2, 3, 4, 5, 6], [0, 0, 1, 2, 3, 3, 4, 5, 6]
+    assert prover.combine_split(t, f) == (evens, odds)
+    a1, a2 = prover.combine_split_arrays(prover.ints_to_mont_array(t), prover.ints_to_mont_array(f))
+    assert prover.mont_array_to_ints(a1) == evens and prover.mont_array_to_ints(a2) == odds
     with pytest.raises(ValueError):
-        prover.combine_split([1, 2], [3])
+        prover.combine_split([1, 2], [3])                      # ElementNotIndexedInTable (multiset.rs:121)
 
 
 def test_vectorised_host_plumbing_matches_the_reference_shaped_one():
