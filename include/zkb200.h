@@ -92,11 +92,18 @@ ZKB_API size_t zkb_srs_size(zkb_ctx *ctx);
  * key like PC::trim).  Later MSMs against the SRS feed one shared bucket set and need no window fold.
  * c > 0: that window size; c == 0: cost model (20 at n = 2^20); c < 0: drop the tables.  Loading a new SRS drops them. */
 ZKB_API int zkb_srs_precompute(zkb_ctx *ctx, int c);
-/* sum_{i<n} scalars[i] * SRS[offset + i]  ->  affine (x, y) Montgomery; *is_inf = 1 and (0,0) for the identity. */
+/* sum_{i<n} scalars[i] * SRS[offset + i]  ->  affine (x, y) Montgomery; *is_inf = 1 and (0,0) for the identity.
+ * Precondition (not checked): every scalar is a canonical integer < r, what Fr::into_repr hands VariableBaseMSM (a value
+ * >= 2^255 would lose its top digit's carry).  The single-MSM entry points return ZKB_ERR_INVALID while a zkb_commit_push
+ * batch is open on the context (they would reuse its staging buffer and result slot). */
 ZKB_API int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);
 ZKB_API int zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);
 /* Same, but returns the un-normalised XYZZ partial sum (X, Y, ZZ, ZZZ: 16 limbs) of one point-range shard. */
 ZKB_API int zkb_msm_g1_dev_partial(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xyzz[16]);
+/* Point-range sharded MSM over the ranks of the context's communicator (zkb_comm_init): every rank
+ * passes the scalars of ITS resident SRS range, the partial sums are exchanged over NCCL inside the call and every rank
+ * returns the same affine point.  Collective: all ranks must call it.  Without a communicator it is zkb_msm_g1_dev. */
+ZKB_API int zkb_msm_g1_sharded_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);
 /* Combine `count` shard results (after the NCCL all-gather of 128 B per rank) into the affine commitment. */
 ZKB_API int zkb_g1_sum_partials(const uint64_t *xyzz, size_t count, uint64_t out_xy[8], int *is_inf);
 /* Arbitrary bases: drop-in for VariableBaseMSM::multi_scalar_mul(bases, scalars) and
@@ -218,6 +225,9 @@ ZKB_API int zkb_plonk_verify(size_t n, const uint64_t *pi_roots_mont, size_t n_p
  * oracle/pairing.py; zkb_pairing_product_is_one is what the verifier uses (PairingEngine::product_of_pairings == 1). */
 ZKB_API int zkb_pairing(const uint64_t g1_xy[8], const uint64_t g2_xy[16], uint64_t out_canonical[48]);
 ZKB_API int zkb_pairing_product_is_one(const uint64_t *g1_xy, const uint64_t *g2_xy, size_t count, int *is_one);
+/* out = k * Q on G2 (k canonical, Q and out as x.c0 x.c1 y.c0 y.c1 Montgomery limbs; identity = zeros).  Host code, setup
+ * time only: ark-poly-commit 0.3 kzg10::setup's beta_h = beta * h, needed to verify against a synthetic SRS (bench.py). */
+ZKB_API int zkb_g2_mul(const uint64_t g2_xy[16], const uint64_t scalar_canonical[4], uint64_t out_xy[16]);
 
 /* ---- the reference CLI's key files ---------------------------------------------------------------------- */
 /* `compile` writes ck / cvk / pk / epk / vk with ark-serialize 0.3 serialize_unchecked (bin/src/parser.rs:16-29,

@@ -61,9 +61,8 @@ class OracleBackend:
     def add_blinders(self, poly, blinders):
         for i, b in enumerate(blinders):
             poly.data[poly.len + i] = fr_to_limbs(b)
-        for i, b in enumerate(blinders):
-            if i < poly.len:
-                poly.data[i] = fr_to_limbs((limbs_to_fr(poly.data[i]) - b) % P)
+        for i, b in enumerate(blinders):        # prove.rs:472-483: extend first, then coeffs[i] -= b_i for EVERY i < k
+            poly.data[i] = fr_to_limbs((limbs_to_fr(poly.data[i]) - b) % P)
         poly.len += len(blinders)
 
     def commit(self, poly):

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: minutes of host CPU work beside the GPU (north-star sizes against the CPU prover)")
 
 
 @pytest.fixture(scope="session")

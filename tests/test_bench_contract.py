@@ -36,3 +36,23 @@ def test_synthetic_scalars_are_canonical():
         assert a.dtype == np.uint64 and a.shape == (1 << 12, 4) and max(vals) < R
     w = [sum(int(x) << (64 * k) for k, x in enumerate(row)) for row in bench.witness_like_scalars(1 << 12, 3)]
     assert 0.1 < sum(v == 0 for v in w) / len(w) < 0.3 and 0.1 < sum(v == 1 for v in w) / len(w) < 0.3
+
+
+def test_closed_form_check_agrees_with_the_oracle_msm():
+    """bench.py checks every MSM against (sum s_i k_i mod r) * G for bases P_i = k_i * G.  Pin that closed form (and the
+    limb <-> integer helpers it rests on) against the oracle's VariableBaseMSM on the same points."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import cref
+    n = 300
+    k = bench.uniform_scalars(n, 7)
+    s = bench.uniform_scalars(n, 8)
+    G = cref.to_mont(cref.FQ, cref.ints_to_limbs([1, 2])).reshape(8)
+    P = cref.g1_mul(G, k)
+    got, inf = cref.msm_g1(P, s)
+    d = bench.dot_mod_r(bench.limbs_to_ints(s), bench.limbs_to_ints(k))
+    assert d == sum(a * b for a, b in zip(bench.limbs_to_ints(s), bench.limbs_to_ints(k))) % R
+    exp = cref.g1_mul(G, bench.int_to_limbs(d))
+    assert not inf and np.array_equal(exp.reshape(8), got)
+    assert bench.bench_config(20, 2) == {"workload": "kzg_commit_g1_msm_2^20", "points_per_gpu": 1 << 20, "total_points": 2 << 20,
+                                         "scalars": "uniform in [0,r), canonical", "curve": "BN254"}

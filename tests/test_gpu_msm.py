@@ -208,6 +208,11 @@ def test_commit_push_finish_matches_batch(ctx):
         junk = torch.zeros(1 << 16, dtype=torch.int64, device="cuda") + k   # unrelated work between pushes
     with pytest.raises(ZkbError):
         ctx.commit_batch_dev(devs[:1], lens[:1])                # a push batch is open
+    sc = cref.from_mont(cref.FR, polys[0])
+    for call in (lambda: ctx.msm(to_dev(sc)), lambda: ctx.msm(sc), lambda: ctx.commit_dev(devs[0], 0, lens[0]),
+                 lambda: ctx.msm_bases(h_pts[:16], sc[:16]), lambda: ctx.msm_partial(to_dev(sc), 0, n)):
+        with pytest.raises(ZkbError):                           # single MSMs would reuse the batch's staging and result slot
+            call()
     got = ctx.commit_finish(len(polys) + 1)
     empty = got.pop(2)
     assert empty[1] and not empty[0].any()

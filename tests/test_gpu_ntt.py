@@ -111,6 +111,23 @@ def test_batch_and_domain_mirror(ctx):
     assert np.array_equal(buf, xs[2])
 
 
+@pytest.mark.parametrize("log_n,inverse,length", [(18, False, None), (20, False, (1 << 18) + 3), (20, True, None), (22, False, (1 << 20) + 3)])
+def test_batch_of_nine_against_oracle(ctx, log_n, inverse, length):
+    """zkb_ntt_batch_dev at the prover's sizes: nine transforms in one launch per pass (round 4: nine zero-padded coset NTTs
+    of 4n points from polynomials of <= n + 3 coefficients, quotient_poly.rs:52-96; rounds 1-3: batches of size-n iNTTs),
+    each compared with the oracle's transform of the same (zero-padded) input."""
+    n = 1 << log_n
+    xs = [rand_fr_mont(n, 300 + 10 * log_n + k) for k in range(9)]
+    ds = [to_dev(x) for x in xs]
+    ctx.ntt_batch_dev(ds, log_n, inverse, True, length=length)
+    for x, d in zip(xs, ds):
+        ref_in = x
+        if length is not None:
+            ref_in = np.zeros_like(x)
+            ref_in[:length] = x[:length]
+        assert np.array_equal(to_host(d), cref.ntt(ref_in, log_n, inverse, True))
+
+
 def test_error_codes(ctx):
     import zkt_plonk_b200 as z
     with pytest.raises(z.ZkbError) as e:

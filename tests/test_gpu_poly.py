@@ -91,7 +91,7 @@ def test_grand_product_zero_denominator_is_reported(ctx):
         prover_ops.compute_z1_poly(dom, beta, gamma, *[to_dev(c) for c in cols])
 
 
-@pytest.mark.parametrize("log_n", [3, 8, 12])
+@pytest.mark.parametrize("log_n", [3, 8, 12, 16])
 def test_quotient_kernel_vs_oracle(ctx, log_n):
     import torch
     n4 = 4 << log_n
@@ -200,6 +200,40 @@ def test_add_blinders_keeps_domain_evaluations(ctx):
     for k in range(n):
         x = pow(w, k, pyref.R_MOD)
         assert sum(c * pow(x, j, pyref.R_MOD) for j, c in enumerate(gi)) % pyref.R_MOD == ei[k]
+
+
+def _add_blinders_like_rust(coeffs, blinders, p):
+    """prove.rs:472-483 word for word on Python lists: extend_from_slice, then zip(coeffs, blinders) sub_assign."""
+    out = list(coeffs) + list(blinders)
+    for i, b in enumerate(blinders):
+        out[i] = (out[i] - b) % p
+    return out
+
+
+@pytest.mark.parametrize("length", [0, 1, 2, 3, 5])
+def test_add_blinders_shorter_than_k(ctx, length):
+    """len < k: the subtraction reaches the blinders that were just appended (len = 0 gives the zero polynomial)."""
+    import torch
+    from zkt_plonk_b200 import prover_ops
+    p = pyref.R_MOD
+    coeffs = rand_fr_mont(max(length, 1), 70 + length)[:length]
+    blinders = rand_fr_mont(3, 80 + length)
+    buf = torch.zeros((length + 3 + 2, 4), dtype=torch.int64, device="cuda")
+    if length:
+        buf[:length] = to_dev(coeffs)
+    assert prover_ops.add_blinders_to_poly(ctx, buf, length, blinders) == length + 3
+    exp = _add_blinders_like_rust(ints(coeffs) if length else [], ints(blinders), p)
+    assert ints(to_host(buf))[: length + 3] == exp
+    if length == 0:
+        assert exp == [0, 0, 0]
+    # the oracle backend restates the same rule
+    from oracle import plonk_ref
+    from zkt_plonk_b200.prover import Poly
+    data = np.zeros((length + 5, 4), dtype=np.uint64)
+    data[:length] = coeffs
+    po = Poly(data, length)
+    plonk_ref.OracleBackend(np.zeros((1, 8), dtype=np.uint64)).add_blinders(po, ints(blinders))
+    assert po.len == length + 3 and ints(po.data)[: length + 3] == exp
 
 
 def test_kzg_open_mirror(ctx):

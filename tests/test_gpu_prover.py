@@ -52,6 +52,28 @@ def test_gpu_proof_is_byte_identical_and_verifies(ctx, log_n, fixed_base):
     ctx.srs_precompute(-1)
 
 
+def test_degenerate_circuits_in_the_native_driver(ctx):
+    """Same shapes as tests/test_prover_cpu.py::test_degenerate_circuits_behave_like_the_reference.  "no_lookup": h1 and h2
+    are zero polynomials before blinding (add_blinders_to_poly with len = 0 < k) and z2 has one coefficient; the native
+    driver must emit the bytes the oracle-backend schedule emits.  "const_wire": the quotient is not a polynomial of
+    3n + 6 coefficients; zkb_plonk_prove must return an error (the reference fails in PC::commit), not overrun a buffer."""
+    circ = synthetic.make_edge_circuit(5, "no_lookup", seed=3)
+    d_srs, h_srs = gpu_srs(ctx, circ.n + 8)
+    ctx.srs_load(d_srs)
+    blinders = list(range(5, 24))
+    native = prover.NativeProver(ctx, circ)
+    raw = native.prove_bytes(blinders)
+    native.close()
+    obe = plonk_ref.OracleBackend(h_srs)
+    opk, ovk = prover.setup(obe, circ)
+    assert raw == prover.prove(obe, opk, ovk, circ, blinders).to_bytes()
+    circ = synthetic.make_edge_circuit(5, "const_wire", seed=3)
+    native = prover.NativeProver(ctx, circ)
+    with pytest.raises(Exception, match="quotient longer"):
+        native.prove_bytes(blinders)
+    native.close()
+
+
 def test_gpu_proof_2_14_verifies(ctx):
     """Larger circuit: too slow for the Python-int oracle prover, so acceptance by the verifier is the check."""
     import zkt_plonk_b200 as z

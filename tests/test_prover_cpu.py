@@ -101,6 +101,47 @@ def test_prove_verify_roundtrip_on_oracle_backend(log_n):
     assert plonk_ref.verify(vk, bad, pub, cvk=cvk) != 0
 
 
+@pytest.mark.parametrize("length", [0, 1, 2, 3, 6])
+def test_oracle_add_blinders_follows_the_reference_for_short_polynomials(length):
+    """prove.rs:472-483: extend by the k blinders FIRST, then coeffs[i] -= b_i for every i < k -- also when len < k."""
+    rnd = random.Random(length)
+    coeffs = [rnd.randrange(P) for _ in range(length)]
+    bl = [rnd.randrange(P) for _ in range(3)]
+    rust = coeffs + bl
+    for i, b in enumerate(bl):
+        rust[i] = (rust[i] - b) % P
+    data = np.zeros((length + 4, 4), dtype=np.uint64)
+    if length:
+        data[:length] = prover.ints_to_mont_array(coeffs)
+    po = prover.Poly(data, length)
+    plonk_ref.OracleBackend(np.zeros((1, 8), dtype=np.uint64)).add_blinders(po, bl)
+    assert po.len == length + 3 and prover.mont_array_to_ints(po.data[: po.len]) == rust
+    if length == 0:
+        assert rust == [0, 0, 0]
+
+
+def test_degenerate_circuits_behave_like_the_reference():
+    """A polynomial shorter than n is blinded at its CURRENT length (prove.rs:472-483), which is not + b(X)(X^n - 1), so
+    the blinded polynomial no longer agrees with its evaluations on the domain and the division by Z_H is not exact.
+    "no_lookup" (empty table, no lookup rows: h1 = h2 = 0 -> [b-b, ..] = 0, but z2 = 1 -> [1-b0, b0-b1, b1-b2, b2]): the
+    remainder has low degree, the quotient still fits 3n + 6 coefficients, and the reference emits a proof that its own
+    verifier rejects -- the restated prover must emit the same bytes, not fail.  "const_wire" (a = 5 on every row): the
+    interpolated quotient fills all 4n coefficients, q_hi exceeds the committer key and the reference fails in PC::commit;
+    the restated prover reports it instead of writing past its buffers."""
+    circ = synthetic.make_edge_circuit(4, "no_lookup", seed=2)
+    assert synthetic.check_gates(circ)
+    be = plonk_ref.OracleBackend(plonk_ref.make_srs_host(circ.n + 8, TAU))
+    pk, vk = prover.setup(be, circ)
+    proof = prover.prove(be, pk, vk, circ, list(range(3, 22)))
+    assert proof.commits["h1"] is None and proof.commits["h2"] is None and proof.commits["t"] is None   # zero polynomials
+    assert plonk_ref.verify(vk, proof, list(circ.pi.values()), TAU) != 0
+    circ = synthetic.make_edge_circuit(4, "const_wire", seed=2)
+    assert synthetic.check_gates(circ)
+    pk, vk = prover.setup(be, circ)
+    with pytest.raises(ValueError, match="quotient longer"):
+        prover.prove(be, pk, vk, circ, list(range(3, 22)))
+
+
 def test_prove_verify_with_the_ethereum_transcript():
     """`T = EthereumTranscript` (bin feature "ethereum-transcript"): same schedule, other challenges; a proof made with
     one transcript is rejected under the other."""

@@ -3,6 +3,7 @@ restatements (oracle/pairing.py, oracle/plonk_ref.py) -- the pairing coefficient
 proofs (both transcripts), on every kind of tampering the reference's checks catch, and on malformed inputs."""
 import random
 
+import numpy as np
 import pytest
 
 from oracle import pairing as pr
@@ -95,6 +96,29 @@ def test_verifier_refuses_malformed_input(proved):
         verifier.verify(vk, bytes(bad), pub, cvk)
     with pytest.raises(_lib.ZkbError):
         verifier.verify(vk, bytes(raw), pub, (((1, 2), (3, 4)), cvk[1]))              # h not on the twist
+    # ark-ec 0.3 SWFlags::from_u8: infinity + positive-y both set is not a flag; the x field must be canonical even under
+    # the infinity flag -- the accepted byte set must equal arkworks' (no malleated encodings of the same point)
+    bad = bytearray(raw)
+    bad[31] |= 0xC0
+    with pytest.raises(_lib.ZkbError):
+        verifier.verify(vk, bytes(bad), pub, cvk)
+    bad = bytearray(raw)
+    bad[0:32] = b"\xff" * 31 + b"\x7f"                                                # infinity flag, x field >= q
+    with pytest.raises(_lib.ZkbError):
+        verifier.verify(vk, bytes(bad), pub, cvk)
+
+
+def test_g2_mul_against_the_oracle():
+    """zkb_g2_mul (setup-time beta_h = beta * h of a synthetic SRS; bench.py verifies its timed proofs with it) against the
+    Python restatement of G2 arithmetic, incl. k = 0, 1, r - 1, r."""
+    from oracle import pairing
+    for k in (0, 1, 2, 12345678901234567890123, P - 1, P, TAU):
+        got = verifier.g2_mul(k)
+        exp = pairing.g2_mul(k % P, pairing.G2_GEN) if k % P else None
+        assert np.array_equal(got, verifier.g2_array(exp)), k
+    h, bh = verifier.make_cvk(TAU)
+    eh, ebh = plonk_ref.make_cvk(TAU)
+    assert np.array_equal(h, verifier.g2_array(eh)) and np.array_equal(bh, verifier.g2_array(ebh))
 
 
 def test_cpp_mirror_reads_key_files_and_verifies(tmp_path, proved):

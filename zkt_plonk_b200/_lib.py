@@ -56,6 +56,7 @@ def load():
         "zkb_msm_g1": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
         "zkb_msm_g1_dev": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
         "zkb_msm_g1_dev_partial": (i, [vp, vp, sz, sz, vp]),
+        "zkb_msm_g1_sharded_dev": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
         "zkb_g1_sum_partials": (i, [vp, sz, vp, ctypes.POINTER(i)]),
         "zkb_msm_g1_bases": (i, [vp, vp, vp, sz, vp, ctypes.POINTER(i)]),
         "zkb_commit_batch_dev": (i, [vp, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, vp, ctypes.POINTER(i)]),
@@ -99,6 +100,7 @@ def load():
         "zkb_plonk_verify": (i, [sz, vp, sz, vp, ctypes.POINTER(i), vp, vp, vp, vp, i]),
         "zkb_pairing": (i, [vp, vp, vp]),
         "zkb_pairing_product_is_one": (i, [vp, vp, sz, ctypes.POINTER(i)]),
+        "zkb_g2_mul": (i, [vp, vp, vp]),
         "zkb_probe_batch_affine": (i, [vp, vp, u, i, u, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u)]),
         "zkb_launch_count": (ctypes.c_uint64, [vp]),
         "zkb_msm_last_timing": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),

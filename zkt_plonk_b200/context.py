@@ -126,6 +126,15 @@ class Context:
         self._check(self._lib.zkb_msm_g1_dev_partial(self._h, _dev_ptr(scalars_dev), offset, n, _host_ptr(out)))
         return out
 
+    def msm_sharded(self, scalars_dev, offset=0, n=None):
+        """Collective (every rank of the context's communicator): this rank's scalars against its resident SRS range; the
+        partial sums are exchanged inside the library (NCCL) and every rank returns the same ((8,) affine, is_inf)."""
+        n = scalars_dev.numel() // 4 if n is None else n
+        out = np.zeros(8, dtype=np.uint64)
+        inf = ctypes.c_int(0)
+        self._check(self._lib.zkb_msm_g1_sharded_dev(self._h, _dev_ptr(scalars_dev), offset, n, _host_ptr(out), ctypes.byref(inf)))
+        return out, bool(inf.value)
+
     def msm_bases(self, points, scalars):
         n = min(points.shape[0], scalars.shape[0])
         out = np.zeros(8, dtype=np.uint64)

@@ -73,6 +73,7 @@ bool point_from_file(const uint8_t *src, uint64_t *xy) {
     memcpy(x.l, src, 32);
     memcpy(y.l, src + 32, 32);
     const bool inf = (y.l[3] >> 62) & 1;
+    if (inf && ((y.l[3] >> 63) & 1)) return false;                // SWFlags::from_u8: both flag bits set is no valid flag
     y.l[3] &= ~(3ULL << 62);
     if (host::ge(x.l, host::FQ.p) || host::ge(y.l, host::FQ.p)) return false;
     if (inf) { memset(xy, 0, 64); return true; }

@@ -875,6 +875,7 @@ int zkb_msm_g1_dev_partial(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t off
     if (!ctx || !out_xyzz) return ZKB_ERR_INVALID;
     if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_msm: offset + n exceeds the loaded SRS");
     if (!scalars_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: null scalars");
+    if (!state(ctx)->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "a zkb_commit_push batch is open (its scalars and results live in the buffers this call would reuse): call zkb_commit_finish first");
     MsmPlan pl;
     const FixedBase *fb = (const FixedBase *)state(ctx)->fixed_base;
     if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;      // forced window: plain path
@@ -899,6 +900,21 @@ int zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, siz
     return ZKB_OK;
 }
 
+// Point-range sharded MSM: every rank of the communicator calls this with the scalars of ITS resident range
+// (scalars_dev[i] pairs with resident point offset + i); the ranks' partial sums are exchanged over NCCL (csrc/comm.cu) and
+// every rank returns the same affine point.  world == 1: the same as zkb_msm_g1_dev.
+int zkb_msm_g1_sharded_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+    if (!ctx || !out_xy) return ZKB_ERR_INVALID;
+    if (ctx->world == 1) return zkb_msm_g1_dev(ctx, scalars_dev, offset, n, out_xy, is_inf);
+    uint64_t mine[16];
+    int rc = zkb_msm_g1_dev_partial(ctx, scalars_dev, offset, n, mine);
+    if (rc) return rc;
+    std::vector<uint64_t> all((size_t)ctx->world * 16);
+    rc = zkb_comm_allgather(ctx, mine, 128, all.data());
+    if (rc) return rc;
+    return zkb_g1_sum_partials(all.data(), (size_t)ctx->world, out_xy, is_inf);
+}
+
 // Host scalars.  From 2^18 points on the MSM runs as two point-range halves through the two pipelined workspaces: the
 // second half of the scalars crosses PCIe (copy stream) while the first half is sorted and accumulated, and the first
 // half's window reduction overlaps the second half's accumulation; the two partial sums are added on the host.
@@ -906,10 +922,11 @@ int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
     if (!scalars_host && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1: null scalars");
     if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_msm: offset + n exceeds the loaded SRS");
+    if (!state(ctx)->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "a zkb_commit_push batch is open (its scalars and results live in the buffers this call would reuse): call zkb_commit_finish first");
     int rc = zkb_reserve(ctx, ctx->stage, n * 32 + 32);
     if (rc) return rc;
     MsmState *st = state(ctx);
-    if (n < ((size_t)1 << 18) || !st->pipe_partial.empty()) {
+    if (n < ((size_t)1 << 18)) {
         ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
         return zkb_msm_g1_dev(ctx, (const uint64_t *)ctx->stage.p, offset, n, out_xy, is_inf);
     }
@@ -948,6 +965,7 @@ int zkb_msm_g1_bases(zkb_ctx *ctx, const uint64_t *points_host, const uint64_t *
                      uint64_t out_xy[8], int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
     if ((!points_host || !scalars_host) && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1_bases: null input");
+    if (!state(ctx)->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "a zkb_commit_push batch is open (its scalars and results live in the buffers this call would reuse): call zkb_commit_finish first");
     int rc = zkb_reserve(ctx, ctx->stage, n * 96 + 96);
     if (rc) return rc;
     char *d_pts = (char *)ctx->stage.p, *d_sc = d_pts + n * 64;
@@ -983,6 +1001,7 @@ int zkb_commit_dev(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset,
     if (!coeffs_mont_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_dev: null coefficients");
     if (ctx->world > 1 || ctx->srs_global_n != ctx->srs_n) return zkb_commit_batch_dev(ctx, &coeffs_mont_dev, &offset, &n, 1, out_xy, is_inf);
     if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_commit_dev: offset + n exceeds the loaded SRS");
+    if (!state(ctx)->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "a zkb_commit_push batch is open (its scalars and results live in the buffers this call would reuse): call zkb_commit_finish first");
     int rc = zkb_reserve(ctx, ctx->stage, n * 32 + 32);
     if (rc) return rc;
     if (n) fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)coeffs_mont_dev, (uint4 *)ctx->stage.p, (uint32_t)n);

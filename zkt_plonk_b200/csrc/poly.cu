@@ -465,13 +465,15 @@ __global__ void __launch_bounds__(256) shift_down_kernel(const uint4 *in, size_t
     fstore(quot + 2 * (j - 1), fload_ro(in + 2 * j));
 }
 
-// add_blinders_to_poly (prove.rs:472-483) for a polynomial whose buffer has room for len + k coefficients:
-// coeffs[len + i] = b_i, coeffs[i] -= b_i
+// add_blinders_to_poly (prove.rs:472-483) for a polynomial whose buffer has room for len + k coefficients.  The reference
+// FIRST extends the coefficient vector by the k blinders and THEN subtracts b_i from coeffs[i] for every i < k, so for
+// len < k the subtraction reaches blinders that were just appended (len = 0: [b0-b0, b1-b1, b2-b2] = the zero polynomial;
+// len = 1: [c0-b0, b0-b1, b1-b2, b2]).  One CTA: the barrier orders the two steps.
 __global__ void add_blinders_kernel(uint4 *coeffs, size_t len, const __grid_constant__ LcArgs b) {
     uint32_t i = threadIdx.x;
-    if (i >= b.k) return;
-    fstore(coeffs + 2 * (len + i), b.s[i]);
-    if (i < len) fstore(coeffs + 2 * (size_t)i, fsub<F>(fload(coeffs + 2 * (size_t)i), b.s[i]));
+    if (i < b.k) fstore(coeffs + 2 * (len + i), b.s[i]);
+    __syncthreads();
+    if (i < b.k) fstore(coeffs + 2 * (size_t)i, fsub<F>(fload(coeffs + 2 * (size_t)i), b.s[i]));
 }
 
 __global__ void fr_fill_kernel(uint4 *out, size_t n, fe_t v) {

@@ -830,6 +830,11 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     size_t q_len = 0;
     TRY(zkb_poly_effective_len_dev(ctx, q_buf, n4, &q_len));
     if (q_len < 2 * (n + 2)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "quotient shorter than 2(n+2): the reference's slice would panic (prove.rs:287-292)");
+    // a satisfied circuit whose blinded polynomials all had n coefficients gives deg q <= 3n + 5.  Anything longer means the
+    // division by Z_H was not exact: an unsatisfied witness, or a polynomial shorter than n before add_blinders_to_poly
+    // (prove.rs:472-483 appends at the CURRENT length, which only equals + b(X)(X^n - 1) at full length -- e.g. z2 = 1 for a
+    // circuit without any lookup).  The reference then fails in PC::commit (q_hi exceeds the committer key's degree).
+    if (q_len - 2 * (n + 2) > cap) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "quotient longer than 3n + 6 coefficients: the division by Z_H was not exact (prove.rs:287-292; PC::commit would fail upstream)");
     DPoly q_part[3];
     {
         const size_t lo[3] = {0, n + 2, 2 * (n + 2)}, hi[3] = {n + 2, 2 * (n + 2), q_len};

@@ -326,8 +326,9 @@ bool g1_decompress(const uint8_t in[32], Pt *out) {
     memcpy(x.l, in, 32);
     const bool inf = (x.l[3] >> 62) & 1, positive = (x.l[3] >> 63) & 1;
     x.l[3] &= ~(3ULL << 62);
+    if (inf && positive) return false;                     // SWFlags::from_u8: both flag bits set is no valid flag
+    if (host::ge(x.l, FQ.p)) return false;                 // the x field must be canonical, also under the infinity flag
     if (inf) { out->inf = true; out->x = qzero(); out->y = qzero(); return true; }
-    if (host::ge(x.l, FQ.p)) return false;
     Fe r2;
     memcpy(r2.l, FQ.r2, 32);
     Fe xm = host::mul(x, r2, FQ);
@@ -387,6 +388,43 @@ bool kzg_check(const Pt *commits, const Fe *values, size_t k, const Fe &point, c
 }  // namespace
 
 extern "C" {
+
+// k * Q on the twist E'(Fq2): y^2 = x^3 + 3 / (9 + i), affine double-and-add (one Fq2 inversion per step; setup-time only).
+// KZG10::setup's beta_h = beta * h for a synthetic SRS whose trapdoor is known (ark-poly-commit 0.3 kzg10::setup).
+int zkb_g2_mul(const uint64_t g2_xy[16], const uint64_t scalar_canonical[4], uint64_t out_xy[16]) {
+    if (!g2_xy || !scalar_canonical || !out_xy) return ZKB_ERR_INVALID;
+    const G2 q = g2_from(g2_xy);
+    if (!g2_on_curve(q)) return ZKB_ERR_INVALID;
+    G2 acc;
+    acc.inf = true;
+    acc.x = {qzero(), qzero()};
+    acc.y = acc.x;
+    auto add = [](const G2 &a, const G2 &b) -> G2 {
+        if (a.inf) return b;
+        if (b.inf) return a;
+        F2 lam;
+        if (f2_eq(a.x, b.x)) {
+            if (!f2_eq(a.y, b.y) || f2_is_zero(a.y)) { G2 z; z.inf = true; z.x = {qzero(), qzero()}; z.y = z.x; return z; }
+            const F2 three = {q_small(3), qzero()};
+            lam = f2_mul(f2_mul(three, f2_mul(a.x, a.x)), f2_inv(f2_add(a.y, a.y)));
+        } else {
+            lam = f2_mul(f2_sub(b.y, a.y), f2_inv(f2_sub(b.x, a.x)));
+        }
+        G2 r;
+        r.inf = false;
+        r.x = f2_sub(f2_sub(f2_mul(lam, lam), a.x), b.x);
+        r.y = f2_sub(f2_mul(lam, f2_sub(a.x, r.x)), a.y);
+        return r;
+    };
+    for (int bit = 255; bit >= 0; --bit) {
+        acc = add(acc, acc);
+        if ((scalar_canonical[bit >> 6] >> (bit & 63)) & 1) acc = add(acc, q);
+    }
+    if (acc.inf) { memset(out_xy, 0, 128); return ZKB_OK; }
+    memcpy(out_xy, acc.x.c0.l, 32); memcpy(out_xy + 4, acc.x.c1.l, 32);
+    memcpy(out_xy + 8, acc.y.c0.l, 32); memcpy(out_xy + 12, acc.y.c1.l, 32);
+    return ZKB_OK;
+}
 
 int zkb_pairing(const uint64_t g1_xy[8], const uint64_t g2_xy[16], uint64_t out_canonical[48]) {
     if (!g1_xy || !g2_xy || !out_canonical) return ZKB_ERR_INVALID;

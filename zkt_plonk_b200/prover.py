@@ -489,6 +489,9 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     q_buf = be.quotient(log_n, pk.epk, (alpha, beta, gamma, delta, epsilon), polys)
     q_len = be.effective_len(q_buf, 4 * n)
     assert q_len >= 2 * (n + 2), "quotient shorter than 2(n+2): the reference's slice would panic"
+    if q_len - 2 * (n + 2) > n + 8:                           # same guard and reason as csrc/prover.cu
+        raise ValueError("quotient longer than 3n + 6 coefficients: the division by Z_H was not exact "
+                         "(prove.rs:287-292; PC::commit would fail upstream)")
     parts = []
     for lo, hi in ((0, n + 2), (n + 2, 2 * (n + 2)), (2 * (n + 2), q_len)):
         buf = be.slice_copy(q_buf, lo, hi, n + 8)

@@ -23,7 +23,7 @@ def make_circuit(log_n, seed=0, table_size=None, n_public=4, lookup_frac=0.01, f
     table = list(dict.fromkeys(table))                       # IndexSet: distinct, insertion ordered
     used = max(8, int(n * fill))                              # rows >= used are padding (all selectors 0, Variable::Zero)
     kind = rng.random(used)
-    n_lookup = max(1, int(used * lookup_frac))
+    n_lookup = max(1, int(used * lookup_frac)) if lookup_frac > 0 else 0
     a, b, c = [0] * n, [0] * n, [0] * n
     var_a, var_b, var_c = [0] * n, [0] * n, [0] * n           # variable ids; 0 = Variable::Zero
     q_m, q_l, q_r, q_o, q_c, q_lk = ([0] * n for _ in range(6))
@@ -64,13 +64,21 @@ def make_circuit(log_n, seed=0, table_size=None, n_public=4, lookup_frac=0.01, f
         var_a[i], var_b[i], var_c[i] = va, vb, vc
         a[i], b[i], c[i] = x, y, values[vc]
 
-    # ---- permutation: positions of the same variable form one cycle
+    return _finish(log_n, (var_a, var_b, var_c), (a, b, c), (q_m, q_l, q_r, q_o, q_c, q_lk), table, table_size, pi)
+
+
+def _finish(log_n, var_ids, wires, sels, table, table_size, pi):
+    """sigma evaluations from the variable ids (positions of the same variable form one cycle) + Montgomery arrays."""
+    n = 1 << log_n
+    var_a, var_b, var_c = var_ids
+    a, b, c = wires
+    q_m, q_l, q_r, q_o, q_c, q_lk = sels
     w = field.root_of_unity(log_n)
     roots = [1] * n
     for i in range(1, n):
         roots[i] = roots[i - 1] * w % P
     ks = (1, field.K1, field.K2)
-    var_of = np.array(var_a + var_b + var_c, dtype=np.int64)  # position p = wire * n + row
+    var_of = np.array(list(var_a) + list(var_b) + list(var_c), dtype=np.int64)  # position p = wire * n + row
     order = np.argsort(var_of, kind="stable")
     sorted_vars = var_of[order]
     nxt = np.empty(3 * n, dtype=np.int64)
@@ -87,6 +95,57 @@ def make_circuit(log_n, seed=0, table_size=None, n_public=4, lookup_frac=0.01, f
                  "q_o": ints_to_mont_array(q_o), "q_c": ints_to_mont_array(q_c), "q_lookup": ints_to_mont_array(q_lk)}
     return Circuit(log_n, selectors, sigma, table, table_size, ints_to_mont_array(a), ints_to_mont_array(b),
                    ints_to_mont_array(c), pi)
+
+
+def make_edge_circuit(log_n, kind, seed=0, table_size=4):
+    """Degenerate shapes the reference handles and a prover must too (add_blinders_to_poly with len < k, prove.rs:472-483):
+    "no_lookup"  -- empty lookup table and no lookup rows: t = f = h1 = h2 = 0, so h1 and h2 are ZERO polynomials (len 0)
+                    before their 3 blinders are appended;
+    "const_wire" -- wire a holds the same value on every row of the domain (no padding rows): a(X) has ONE coefficient
+                    before its 2 blinders; also no lookups."""
+    n = 1 << log_n
+    rng = np.random.default_rng(seed)
+    vals = [0]
+
+    def new_var(v):
+        vals.append(v % P)
+        return len(vals) - 1
+
+    q_m, q_l, q_r, q_o, q_c, q_lk = ([0] * n for _ in range(6))
+    var_a, var_b, var_c = [0] * n, [0] * n, [0] * n
+    a, b, c = [0] * n, [0] * n, [0] * n
+    pi = {}
+    if kind == "no_lookup":
+        used = max(8, n - n // 4)
+        for i in range(used):
+            va = new_var(int(rng.integers(1, 1 << 62))) if i < 4 or i % 3 else var_c[i - 1]
+            vb = new_var(int(rng.integers(1, 1 << 62)))
+            x, y = vals[va], vals[vb]
+            if i < 2:
+                q_l[i] = 1
+                pi[i] = (-x) % P
+                vc = 0
+            elif i % 2:
+                q_m[i], q_o[i] = 1, P - 1
+                vc = new_var(x * y)
+            else:
+                q_l[i], q_r[i], q_o[i] = 1, 1, P - 1
+                vc = new_var(x + y)
+            var_a[i], var_b[i], var_c[i] = va, vb, vc
+            a[i], b[i], c[i] = x, y, vals[vc]
+        table = []
+    elif kind == "const_wire":
+        five = new_var(5)
+        for i in range(n):                                      # every row: 5 * b - c = 0, a is the same variable everywhere
+            vb = new_var(int(rng.integers(1, 1 << 62)))
+            vc = new_var(5 * vals[vb])
+            q_m[i], q_o[i] = 1, P - 1
+            var_a[i], var_b[i], var_c[i] = five, vb, vc
+            a[i], b[i], c[i] = 5, vals[vb], vals[vc]
+        table = []
+    else:
+        raise ValueError(kind)
+    return _finish(log_n, (var_a, var_b, var_c), (a, b, c), (q_m, q_l, q_r, q_o, q_c, q_lk), table, table_size, pi)
 
 
 def check_gates(circ):

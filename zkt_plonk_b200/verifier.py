@@ -40,6 +40,30 @@ def _vp(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+# alt_bn128 G2 generator (EIP-197), ((x.c0, x.c1), (y.c0, y.c1))
+G2_GEN = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+           11559732032986387107991004021392285783925812861821192530917403151452391805634),
+          (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+           4082367875863433681332203403145435568316851327593401208105741076214120093531))
+
+
+def g2_mul(k, pt=G2_GEN):
+    """k * pt on G2 through the C ABI (zkb_g2_mul); returns the (16,) Montgomery array the verifier takes."""
+    k = int(k)
+    sc = np.array([(k >> (64 * j)) & (2**64 - 1) for j in range(4)], dtype=np.uint64)
+    out = np.zeros(16, dtype=np.uint64)
+    rc = _lib.lib().zkb_g2_mul(_vp(g2_array(pt)), _vp(sc), _vp(out))
+    if rc != 0:
+        raise _lib.ZkbError(rc, "zkb_g2_mul: point not on the twist")
+    return out
+
+
+def make_cvk(tau):
+    """(h, beta_h) = (H, tau * H) for a synthetic SRS with known trapdoor (kzg10::setup draws h at random; any h gives the
+    same accept / reject decisions).  Product code: bench.py verifies every timed proof with it."""
+    return g2_array(G2_GEN), g2_mul(tau)
+
+
 def verify(vk, proof_bytes, pub_inputs, cvk_g2, transcript="merlin"):
     """vk: prover.VerifierKey; proof_bytes: the 802 serialised bytes; pub_inputs: canonical ints, one per vk.pi_roots entry;
     cvk_g2 = (h, beta_h) as Fq2 coordinate tuples of canonical ints or as the (16,) arrays keyfile.cvk_read returns.  Returns 0 (accepted), 1 or 2 (failing step); raises on malformed input."""
