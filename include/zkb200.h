@@ -133,9 +133,11 @@ ZKB_API int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], c
                               uint64_t *out_points_dev);
 /* Force the window size c (0 = automatic cost model).  For tests and tuning. */
 ZKB_API int zkb_msm_set_window(zkb_ctx *ctx, int c);
-/* Bucket-accumulation kernel: 0 = XYZZ mixed additions (default, the measured path); 1 = EXPERIMENTAL batched affine
- * additions with one shared inversion per CTA and step (csrc/msm_affine.cu).  Same results either way.
- * ZKB_MSM_MODE=1 in the environment selects mode 1 for contexts created afterwards. */
+/* Batched-affine pair rounds in front of the XYZZ bucket accumulation (csrc/msm_pairs.cuh): each round adds
+ * entries 2k and 2k + 1 of every bucket in affine coordinates (5M + 1S per addition, one inversion per thread and batch of
+ * 32..128 pairs, prefix products in HBM), halving the work left for the 8M + 2S XYZZ additions.  mode: 0 = none, 1..6 =
+ * that many rounds, -1 = chosen per MSM from the mean bucket load.  Same results for every mode (affine sums are canonical).
+ * ZKB_MSM_MODE=<mode> in the environment sets the mode of contexts created afterwards. */
 ZKB_API int zkb_msm_set_mode(zkb_ctx *ctx, int mode);
 
 /* ---- grand products, quotient, polynomial utilities (all device-resident, enqueue on the context's stream) -------------- */
@@ -291,8 +293,7 @@ ZKB_API int zkb_comm_allgather_host(zkb_ctx *ctx, const void *send_host, size_t 
 ZKB_API int zkb_srs_set_range(zkb_ctx *ctx, size_t global_lo, size_t global_n);
 
 /* ---- test hooks (parity of the device field library against the oracle) ----------------------------------------- */
-/* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a), 7 = a * b * 2^-260 through the
- * experimental FP64-pipe product (csrc/ff52.cuh).  Host pointers. */
+/* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a).  Host pointers. */
 ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n);
 
 /* Host only (no GPU): the round driver's MultiSet::combine_split (multiset.rs:103-146) specialised to t = table entries
@@ -314,22 +315,14 @@ ZKB_API uint64_t zkb_launch_count(zkb_ctx *ctx);
  * out_ms[0] digits + counting sort + task ordering, [1] bucket accumulation (the integer-bound kernel),
  * [2] oversized-bucket combine, [3] window reduction, [4] total.  info[0] = n * windows, info[1] = c, info[2] = windows. */
 ZKB_API int zkb_msm_last_timing(zkb_ctx *ctx, float out_ms[5], uint64_t info[3]);
+/* The part of out_ms[0] above spent in the batched-affine pair rounds of the last MSM, and how many rounds ran. */
+ZKB_API int zkb_msm_last_pair_rounds(zkb_ctx *ctx, float *pairs_ms, int *rounds);
 
 /* ---- measurement: integer-pipe peak (not in MEASURED_PEAKS.json; SURVEY.md 8d asks for it) ------------------------- */
 /* mode 0: 32-bit IMAD/s, mode 1: IMAD.WIDE.U32/s (the instruction the Montgomery product is made of),
- * mode 2: Fq Montgomery products/s in a dependency-chained loop, mode 3: FP64 FMA/s, mode 4: Fq products/s of the FP64-pipe
- * product (ff52.cuh), mode 5: both products in alternating warps, modes 6-8: pipe-sharing probes (IMAD + DFMA, IMAD + ALU,
- * DFMA + ALU in one thread; result = groups/s).  All 148 SMs, best of 3 timed launches. */
+ * mode 2: Fq Montgomery products/s in a dependency-chained loop, mode 3: FP64 FMA/s, modes 6-8: pipe-sharing probes
+ * (IMAD + DFMA, IMAD + ALU, DFMA + ALU in one thread; result = groups/s).  All 148 SMs, best of 3 timed launches. */
 ZKB_API int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec);
-
-/* EXPERIMENT (csrc/probe_batch_affine.cu): bucket-accumulation inner loop as XYZZ mixed additions (what the
- * product runs) against batch-affine additions with one shared inversion per CTA and step (binary extended Euclid on the
- * ALU pipe), on the same points.  table_dev: 2^log_table distinct affine points in HBM; m: accumulators per thread of the
- * batch-affine kernel (4 or 8: accumulators in shared memory; -4, -8, -16: in global memory / L2); steps: additions per
- * accumulator.  out[0] / out[1]: additions per second of the two loops;
- * *mismatches: accumulators whose results differ (must be 0). */
-ZKB_API int zkb_probe_batch_affine(zkb_ctx *ctx, const uint64_t *table_dev, unsigned log_table, int m, unsigned steps, double out[2],
-                           unsigned *mismatches);
 
 #ifdef __cplusplus
 }

@@ -243,3 +243,76 @@ def test_host_scalar_msm_two_halves(ctx, tables):
     exp, einf = cref.msm_g1(h_pts[off:], s)
     assert inf == einf and np.array_equal(got, exp)
     ctx.srs_precompute(-1)
+
+
+@pytest.mark.parametrize("rounds", [1, 3, 6])
+def test_pair_rounds_vs_oracle(ctx, rounds):
+    """zkb_msm_set_mode(rounds): batched-affine pair rounds (csrc/msm_pairs.cuh) in front of the XYZZ accumulation give the
+    same affine point as the oracle -- edge cases that make SPECIAL pairs (a repeated base with equal digits: P + P; P and
+    -P in one bucket; the point at infinity among the bases; all-ones scalars: one giant bucket reduced over every round),
+    plain bases and fixed-base tables, uniform and witness-like scalars, windows small enough that buckets hold many entries."""
+    ctx.set_msm_mode(rounds)
+    try:
+        n = 2048
+        _, P = gpu_points(ctx, n, 7)
+        s = cref.rand_fe(cref.FR, n, 8)
+        rm1 = cref.ints_to_limbs([0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000000])[0]
+        s[0] = 0
+        s[1] = [1, 0, 0, 0]
+        s[3] = rm1
+        P[10] = P[11]
+        s[10] = s[11]                # equal digits on equal points: doubling inside a pair
+        P[12] = P[13]
+        s[12] = [5, 0, 0, 0]
+        s[13] = cref.ints_to_limbs([0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001 - 5])[0]   # -5: P and -P cancel
+        P[20] = 0                    # point at infinity in the bases
+        exp, einf = cref.msm_g1(P, s)
+        for c in (0, 4, 7, 11):
+            ctx.set_msm_window(c)
+            got, inf = ctx.msm_bases(P, s)
+            assert inf == einf and np.array_equal(got, exp), c
+        ctx.set_msm_window(0)
+        ones = np.zeros((n, 4), dtype=np.uint64)
+        ones[:, 0] = 1
+        got, inf = ctx.msm_bases(P, ones)
+        assert np.array_equal(got, cref.msm_g1(P, ones)[0])
+        got, inf = ctx.msm_bases(P[:64], np.zeros((64, 4), dtype=np.uint64))
+        assert inf and not got.any()
+        # resident SRS, fixed-base tables, 2^16 points: uniform and witness-like scalars, an offset into the key
+        n = 1 << 16
+        dP, P = gpu_points(ctx, n + 3, 170 + rounds)
+        ctx.srs_load(dP)
+        for tables in (False, True):
+            if tables:
+                ctx.srs_precompute(0)
+            for sc in (cref.rand_fe(cref.FR, n, 171), skewed_scalars(n, 172)):
+                got, inf = ctx.msm(to_dev(sc), offset=3)
+                exp, einf = cref.msm_g1(P[3:], sc)
+                assert inf == einf and np.array_equal(got, exp), (tables,)
+                tm = ctx.msm_last_timing()
+                assert tm["pair_rounds"] == rounds
+        ctx.srs_precompute(-1)
+    finally:
+        ctx.set_msm_mode(0)
+        ctx.set_msm_window(0)
+
+
+def test_pair_rounds_2_20_against_the_xyzz_path(ctx):
+    """North-star size: the 2^20-point fixed-base MSM with 3 pair rounds and in automatic mode equals the XYZZ-only result
+    (which test_msm_2_20_vs_oracle pins to the oracle) on uniform and witness-like scalars."""
+    n = 1 << 20
+    dP, _ = gpu_points(ctx, n, 333)
+    ctx.srs_load(dP)
+    ctx.srs_precompute(0)
+    try:
+        for sc in (cref.rand_fe(cref.FR, n, 334), skewed_scalars(n, 335)):
+            d = to_dev(sc)
+            ctx.set_msm_mode(0)
+            want = ctx.msm(d)
+            for mode in (3, -1):
+                ctx.set_msm_mode(mode)
+                got = ctx.msm(d)
+                assert got[1] == want[1] and np.array_equal(got[0], want[0]), mode
+    finally:
+        ctx.set_msm_mode(0)
+        ctx.srs_precompute(-1)

@@ -101,9 +101,9 @@ def load():
         "zkb_pairing": (i, [vp, vp, vp]),
         "zkb_pairing_product_is_one": (i, [vp, vp, sz, ctypes.POINTER(i)]),
         "zkb_g2_mul": (i, [vp, vp, vp]),
-        "zkb_probe_batch_affine": (i, [vp, vp, u, i, u, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u)]),
         "zkb_launch_count": (ctypes.c_uint64, [vp]),
         "zkb_msm_last_timing": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),
+        "zkb_msm_last_pair_rounds": (i, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i)]),
         "zkb_bench_int": (i, [vp, i, ctypes.POINTER(ctypes.c_double)]),
         "zkb_comm_unique_id": (i, [vp]),
         "zkb_comm_init": (i, [vp, vp, i, i]),

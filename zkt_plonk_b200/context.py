@@ -98,7 +98,8 @@ class Context:
         self._check(self._lib.zkb_srs_load_ck_file(self._h, os.fsencode(path), int(max_points)))
 
     def set_msm_mode(self, mode):
-        """0: XYZZ bucket accumulation (default); 1: EXPERIMENTAL batched affine additions (csrc/msm_affine.cu)."""
+        """Batched-affine pair rounds in front of the XYZZ bucket accumulation (csrc/msm_pairs.cuh): 0 = none, 1..6 = that
+        many rounds, -1 = chosen per MSM.  Results are identical for every mode."""
         self._check(self._lib.zkb_msm_set_mode(self._h, int(mode)))
 
     def srs_precompute(self, c=0):
@@ -281,7 +282,10 @@ class Context:
         ms = (ctypes.c_float * 5)()
         info = (ctypes.c_uint64 * 3)()
         self._check(self._lib.zkb_msm_last_timing(self._h, ms, info))
-        return {"sort_ms": ms[0], "accumulate_ms": ms[1], "heavy_ms": ms[2], "reduce_ms": ms[3], "total_ms": ms[4],
+        pm, pr = ctypes.c_float(0), ctypes.c_int(0)
+        self._check(self._lib.zkb_msm_last_pair_rounds(self._h, ctypes.byref(pm), ctypes.byref(pr)))
+        return {"sort_ms": ms[0] - pm.value, "pair_rounds_ms": pm.value, "pair_rounds": int(pr.value), "accumulate_ms": ms[1],
+                "heavy_ms": ms[2], "reduce_ms": ms[3], "total_ms": ms[4],
                 "entries": int(info[0]), "c": int(info[1]), "windows": int(info[2])}
 
     def bench_int(self, mode):

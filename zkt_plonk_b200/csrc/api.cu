@@ -1,10 +1,9 @@
 // api.cu -- extern "C" boundary of libzkb200.so (include/zkb200.h): context, memory, host-pointer wrappers.
 #include <stdlib.h>
+#include <string.h>
 
 #include "ctx.h"
 #include "ff.cuh"
-#include "ff52.cuh"
-#include "ff_kara.cuh"
 
 using namespace zkb;
 
@@ -22,8 +21,6 @@ __global__ void fp_binop_kernel(int op, uint4 *out, const uint4 *a, const uint4 
         case 3: r = fsqr<P>(x); break;
         case 4: r = finv<P>(x); break;
         case 5: r = fto_mont<P>(x); break;
-        case 8: r = fmul_kara<P>(x, y); break;                                            // must equal op 0
-        case 7: r = fe_from_fe52(fmul52<P>(fe52_from_fe(x), fe52_from_fe(y))); break;   // a * b * 2^-260 on the FP64 pipe
         default: r = ffrom_mont<P>(x); break;
     }
     fstore(out + 2 * i, r);
@@ -91,36 +88,6 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, uint32_t i
 #pragma unroll
         for (int k = 0; k < 4; ++k) r ^= a[k] ^ c[k] ^ (uint32_t)__double2ll_rn(d[k]);
         out[t] = r;
-    } else if (mode == 4 || (mode == 5 && ((threadIdx.x >> 5) & 1))) {   // Montgomery products on the FP64 pipe (ff52.cuh)
-        fe52_t x[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) x[k].v[j] = ((uint64_t)(t * 2654435761u + k * 40503u + j) * 0x9E3779B97F4A7C15ULL) & (MASK52 >> 8);
-        }
-        for (uint32_t i = 0; i < iters; ++i) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) x[k] = fmul52<FqP>(x[k], x[(k + 1) & 3]);
-        }
-        uint64_t r = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r ^= x[k].v[0] ^ x[k].v[4];
-        out[t] = (uint32_t)(r ^ (r >> 32));
-    } else if (mode == 9) {                                       // Karatsuba product chain (ff_kara.cuh)
-        fe_t x[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[k].v[j] = (t * 2654435761u + k * 40503u + j) & 0x0fffffffu;
-        }
-        for (uint32_t i = 0; i < iters; ++i) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) x[k] = fmul_kara<FqP>(x[k], x[(k + 1) & 3]);
-        }
-        uint32_t r = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r ^= x[k].v[0] ^ x[k].v[7];
-        out[t] = r;
     } else {
         fe_t x[4];
 #pragma unroll
@@ -156,8 +123,9 @@ int zkb_ctx_create(int device, zkb_ctx **out) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    const char *mode = getenv("ZKB_MSM_MODE");                  // "1": experimental batch-affine bucket accumulation (msm_affine.cu)
-    if (mode && mode[0] == '1' && mode[1] == 0) ctx->msm_mode = 1;
+    const char *mode = getenv("ZKB_MSM_MODE");                  // pair rounds (msm_pairs.cuh): "0".."6", or "-1" / "auto"
+    if (mode && mode[0] >= '0' && mode[0] <= '6' && mode[1] == 0) ctx->msm_mode = mode[0] - '0';
+    else if (mode && (!strcmp(mode, "-1") || !strcmp(mode, "auto"))) ctx->msm_mode = -1;
     *out = ctx;
     return ZKB_OK;
 }
@@ -276,8 +244,8 @@ int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint
 
 // ---------------------------------------------------------------------------------------------- microbenchmark
 int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec) {
-    if (!ctx || !ops_per_sec || mode < 0 || mode > 9) return ZKB_ERR_INVALID;
-    const uint32_t blocks = ctx->sm_count * 8, threads = 256, iters = (mode == 2 || mode == 4 || mode == 5 || mode == 9) ? 512 : 4096;
+    if (!ctx || !ops_per_sec || mode < 0 || mode > 8 || mode == 4 || mode == 5) return ZKB_ERR_INVALID;
+    const uint32_t blocks = ctx->sm_count * 8, threads = 256, iters = mode == 2 ? 512 : 4096;
     int rc = zkb_reserve(ctx, ctx->stage, (size_t)blocks * threads * 4);
     if (rc) return rc;
     cudaEvent_t e0, e1;
@@ -295,7 +263,7 @@ int zkb_bench_int(zkb_ctx *ctx, int mode, double *ops_per_sec) {
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    double per_thread = (double)iters * ((mode == 2 || mode == 4 || mode == 5 || mode == 9) ? 4 : mode >= 6 ? 4 : 8);   // modes 6-8: per pair
+    double per_thread = (double)iters * (mode == 2 ? 4 : mode >= 6 ? 4 : 8);   // modes 6-8: per pair
     *ops_per_sec = per_thread * blocks * threads / (best * 1e-3);
     return ZKB_OK;
 }

@@ -35,7 +35,8 @@ struct zkb_ctx {
     size_t srs_n = 0;
     void *msm_state = nullptr;   // opaque (owned by msm.cu)
     int msm_force_c = 0;         // 0 = cost model picks the window size
-    int msm_mode = 0;            // 0 = XYZZ bucket accumulation (default); 1 = EXPERIMENTAL batch-affine kernel (msm_affine.cu)
+    int msm_mode = 0;            // batched-affine pair rounds in front of the XYZZ accumulation (msm_pairs.cuh): 0 = none,
+                                 // 1..6 = that many, -1 = chosen per MSM from the mean bucket load
 
     // ---- multi-GPU (comm.cu): one process per GPU, commitments sharded by point range
     void *comm = nullptr;        // ncclComm_t (NCCL is dlopen'ed: the library has no link-time dependency on it)
@@ -104,10 +105,6 @@ int zkb_comm_allgather(zkb_ctx *ctx, const void *send_host, size_t bytes, void *
 // the same in place on the device, enqueued on `stream` (no synchronisation)
 int zkb_comm_allgather_dev(zkb_ctx *ctx, void *buf_dev, size_t bytes_per_rank, cudaStream_t stream);
 // two-level power tables base^e = lo[e & (2^s - 1)] * hi[e >> s], e < 2^lm (Montgomery Fr); hi is pre-scaled by hi_scale
-// msm_affine.cu: the experimental batch-affine bucket accumulation, launched by msm.cu when ctx->msm_mode == 1
-int zkb_launch_accumulate_affine(zkb_ctx *ctx, cudaStream_t s, uint64_t max_tasks, const void *points, const uint32_t *sorted,
-                                 const uint32_t *counts, const uint32_t *starts, const uint32_t *ntasks, const uint32_t *task_base,
-                                 const void *task_order, const uint32_t *misc, uint32_t seg, void *task_out, void *bucket_val);
 int zkb_pow2lvl_cached(zkb_ctx *ctx, uint64_t key, unsigned lm, const zkb::host::Fe &base, const zkb::host::Fe &hi_scale,
                        const void **out, uint32_t *s_out);
 int zkb_pow2lvl_build(zkb_ctx *ctx, void *out, unsigned lm, const zkb::host::Fe &base, const zkb::host::Fe &hi_scale,

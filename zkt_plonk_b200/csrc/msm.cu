@@ -31,6 +31,7 @@
 #include "ctx.h"
 #include "ec.cuh"
 #include "host_ff.h"
+#include "msm_pairs.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -58,6 +59,7 @@ struct MsmPlan {
     uint64_t red_buf_elems[2];           // ping-pong buffers of the recursion (levels alternate)
     uint32_t seg;                        // max points per accumulation task
     uint32_t id_base, id_stride;         // fixed-base: entry id = id_base + w * id_stride + i
+    pairs::Plan pp;                      // pair rounds in front of the XYZZ accumulation (pp.rounds == 0: none)
 };
 
 struct MsmWs {                           // carved out of ctx->msm_ws
@@ -70,6 +72,7 @@ struct MsmWs {                           // carved out of ctx->msm_ws
     g1x_t *task_out;                     // partial sums of the tasks of multi-task buckets
     g1x_t *bucket_val;                   // dense: one XYZZ value per bucket (zero = empty)
     g1x_t *red_buf[2];                   // level outputs, [stream][group][t]
+    pairs::Ws pw;                        // batched-affine pair rounds (msm_pairs.cuh); unused when the plan has no rounds
 };
 
 struct MsmSlot {                         // one MSM in flight: its own workspace, result buffer and completion event
@@ -85,6 +88,8 @@ struct MsmState {
     cudaStream_t copy_stream = nullptr;  // uploads of host scalars, overlapped with the MSM of the previous part
     cudaEvent_t part_uploaded[2] = {nullptr, nullptr};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase boundaries of the last MSM
+    cudaEvent_t ev_pairs[2] = {nullptr, nullptr};                        // around the pair rounds of the last MSM
+    uint32_t last_rounds = 0;
     bool ev_valid = false;
     uint64_t last_entries = 0;           // n * W upper bound of bucket insertions of the last MSM
     uint32_t last_c = 0, last_W = 0;
@@ -270,7 +275,8 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + 32));
 }
 
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__restrict__ points, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__restrict__ points, const g1a_t *__restrict__ pool,
+                                                             const uint32_t *__restrict__ sorted,
                                                              const uint32_t *__restrict__ counts, const uint32_t *__restrict__ starts,
                                                              const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_base,
                                                              const uint2 *__restrict__ task_order, const uint32_t *__restrict__ misc,
@@ -286,16 +292,17 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__rest
     // Three-deep gather pipeline: L2 prefetch PF points ahead (no registers held; the fixed-base tables are far
     // larger than L2, so every gather is an HBM access), register load one point ahead, add the current point.
     constexpr uint32_t PF = 6;
-    for (uint32_t k = 1; k < PF && k < cnt; ++k) prefetch_l2(points + (idx[k] & ~SIGN_BIT));
+    // an entry is a point of the base / table array or (bit 30, after pair rounds) a sum in the pool of intermediate results
+    for (uint32_t k = 1; k < PF && k < cnt; ++k) prefetch_l2(pairs::ref_ptr(points, pool, idx[k]));
     uint32_t v = idx[0];
-    g1a_t p = g1a_load(points + (v & ~SIGN_BIT));
+    g1a_t p = g1a_load(pairs::ref_ptr(points, pool, v));
     for (uint32_t k = 0; k < cnt; ++k) {
         uint32_t vn = 0;
         g1a_t pn;
-        if (k + PF < cnt) prefetch_l2(points + (idx[k + PF] & ~SIGN_BIT));
+        if (k + PF < cnt) prefetch_l2(pairs::ref_ptr(points, pool, idx[k + PF]));
         if (k + 1 < cnt) {                                   // issue the next gather before the addition
             vn = idx[k + 1];
-            pn = g1a_load(points + (vn & ~SIGN_BIT));
+            pn = g1a_load(pairs::ref_ptr(points, pool, vn));
         }
         if (v & SIGN_BIT) p.y = fneg<FqP>(p.y);
         g1x_add_mixed(acc, p);
@@ -558,7 +565,20 @@ uint32_t pick_window(size_t n, bool shared_buckets, int sm_count) {
     return best_c;
 }
 
-MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset, int sm_count) {
+// pair rounds for an MSM of `entries` bucket insertions over nb buckets.  mode >= 0: that many rounds; mode < 0: automatic --
+// a round pays while buckets still hold several entries (it halves them at 788 instead of 1232 multiply-adds per addition,
+// for ~6 small launches), so: floor(log2(mean load)) - 1 rounds, none for small MSMs (latency-bound) or when the
+// references / the pool would not fit their 30 index bits or a sane share of HBM.
+uint32_t pick_pair_rounds(int mode, uint64_t entries, uint64_t nb, uint64_t max_id) {
+    if (mode == 0 || entries < 2 || max_id >= pairs::POOL || entries >= pairs::POOL || entries > (1ull << 28)) return 0;
+    if (mode > 0) return (uint32_t)std::min(mode, pairs::MAX_ROUNDS);
+    if (entries < (1ull << 19)) return 0;
+    const double mean = (double)entries / (double)std::max<uint64_t>(1, std::min(nb, entries));
+    int r = (int)std::floor(std::log2(std::max(mean, 1.0))) - 1;
+    return (uint32_t)std::max(0, std::min(r, 4));
+}
+
+MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset, int sm_count, int pair_mode = 0) {
     MsmPlan pl;
     if (fb) {
         pl.c = fb->c; pl.W = fb->W; pl.G = 1; pl.wide = fb->wide;
@@ -594,6 +614,9 @@ MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset, int
     uint32_t seg = 256;
     while (seg < 4.0 * mean && seg < SEG_MAX) seg <<= 1;
     pl.seg = seg;
+    const uint64_t max_id = fb ? (uint64_t)pl.id_base + (uint64_t)(pl.W - 1) * pl.id_stride + n : n;
+    pl.pp = pairs::make_plan(pick_pair_rounds(pair_mode, (uint64_t)n * pl.W, pl.nbuckets, max_id), (uint64_t)n * pl.W, pl.nbuckets,
+                             (uint64_t)sm_count * 4 * pairs::THREADS);
     return pl;
 }
 
@@ -611,6 +634,19 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
            o_hist = take((SEG_MAX + 1) * 4), o_hcur = take((SEG_MAX + 1) * 4), o_misc = take(64), o_heavy = take(nb * 4),
            o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)), o_bval = take(nb * sizeof(g1x_t)),
            o_red0 = take(pl.red_buf_elems[0] * sizeof(g1x_t)), o_red1 = take(pl.red_buf_elems[1] * sizeof(g1x_t));
+    size_t o_pr[2] = {0, 0}, o_pc[2] = {0, 0}, o_ps[2] = {0, 0}, o_pk = 0, o_pscan = 0, o_prefs = 0, o_ppre = 0, o_pool = 0;
+    if (pl.pp.rounds) {
+        for (int k = 0; k < 2; ++k) {
+            o_pr[k] = take(pl.pp.e_ub[1] * 4 + 4);
+            o_pc[k] = take(nb * 4);
+            o_ps[k] = take(nb * 4);
+        }
+        o_pk = take((nb + 1) * 8);
+        o_pscan = take(((nb + 1) / pairs::SCAN_TILE64 + 2) * 8);
+        o_prefs = take(pl.pp.scratch_elems * sizeof(uint2));
+        o_ppre = take(pl.pp.scratch_elems * sizeof(fe_t));
+        o_pool = take((pl.pp.pool_base[pl.pp.rounds] + 1) * sizeof(g1a_t));
+    }
     int rc = zkb_reserve(ctx, buf, off);
     if (rc) return rc;
     char *p = (char *)buf.p;
@@ -620,6 +656,13 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
     ws.misc = (uint32_t *)(p + o_misc); ws.heavy_list = (uint32_t *)(p + o_heavy); ws.task_order = (uint2 *)(p + o_order);
     ws.task_out = (g1x_t *)(p + o_out); ws.bucket_val = (g1x_t *)(p + o_bval);
     ws.red_buf[0] = (g1x_t *)(p + o_red0); ws.red_buf[1] = (g1x_t *)(p + o_red1);
+    if (pl.pp.rounds) {
+        for (int k = 0; k < 2; ++k) {
+            ws.pw.refs[k] = (uint32_t *)(p + o_pr[k]); ws.pw.counts[k] = (uint32_t *)(p + o_pc[k]); ws.pw.starts[k] = (uint32_t *)(p + o_ps[k]);
+        }
+        ws.pw.pk = (unsigned long long *)(p + o_pk); ws.pw.scan_tmp = (unsigned long long *)(p + o_pscan);
+        ws.pw.pairrefs = (uint2 *)(p + o_prefs); ws.pw.prefix = (fe_t *)(p + o_ppre); ws.pw.pool = (g1a_t *)(p + o_pool);
+    }
     *max_tasks_out = max_tasks;
     *max_heavy_tasks_out = max_heavy_tasks;
     return ZKB_OK;
@@ -638,7 +681,7 @@ MsmState *state(zkb_ctx *ctx) {
 int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, size_t n, int force_c, const FixedBase *fb,
                 size_t offset, MsmPlan *plan_out, int slot_id = 0, bool pipelined = false) {
     if (n >= (1ull << 31)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n must be < 2^31");
-    MsmPlan pl = make_plan(n, force_c, fb, offset, ctx->sm_count);
+    MsmPlan pl = make_plan(n, force_c, fb, offset, ctx->sm_count, ctx->msm_mode);
     if ((uint64_t)n * pl.W >= (1ull << 32)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n * windows must be < 2^32");
     MsmWs ws;
     uint64_t max_tasks, max_heavy;
@@ -664,7 +707,10 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     cudaStream_t s = ctx->stream;
     const uint32_t nb = (uint32_t)pl.nbuckets, n32 = (uint32_t)n;
     const uint32_t gstride = pl.G == 1 ? 0 : pl.B;
-    if (!st->ev[0]) for (int k = 0; k < 5; ++k) ZKB_CUDA(ctx, cudaEventCreate(&st->ev[k]));
+    if (!st->ev[0]) {
+        for (int k = 0; k < 5; ++k) ZKB_CUDA(ctx, cudaEventCreate(&st->ev[k]));
+        for (int k = 0; k < 2; ++k) ZKB_CUDA(ctx, cudaEventCreate(&st->ev_pairs[k]));
+    }
     st->last_entries = (uint64_t)n * pl.W; st->last_c = pl.c; st->last_W = pl.W;
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[0], s));
 
@@ -678,6 +724,32 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     ZKB_CUDA(ctx, cudaMemcpyAsync(ws.cursor, ws.starts, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
     if (n32) msm_scatter_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, pl.id_base, pl.id_stride,
                                                                   ws.cursor, ws.sorted);
+    // ---- batched-affine pair rounds (msm_pairs.cuh): each halves every bucket; the XYZZ accumulation below then works on
+    // what is left, through the references / counts / starts of the last round
+    const g1a_t *pool = nullptr;
+    ZKB_CUDA(ctx, cudaEventRecord(st->ev_pairs[0], s));
+    if (pl.pp.rounds && n32) {
+        const uint32_t *refs = ws.sorted, *cnts = ws.counts, *sts = ws.starts;
+        const uint32_t nscan = nb + 1, ntiles = (nscan + pairs::SCAN_TILE64 - 1) / pairs::SCAN_TILE64;
+        for (uint32_t r = 0; r < pl.pp.rounds; ++r) {
+            uint32_t *nrefs = ws.pw.refs[r & 1], *ncnts = ws.pw.counts[r & 1], *nsts = ws.pw.starts[r & 1];
+            pairs::pack_kernel<<<(nscan + 255) / 256, 256, 0, s>>>(cnts, nb, ws.pw.pk);
+            pairs::scan64_reduce_kernel<<<ntiles, 256, 0, s>>>(ws.pw.pk, nscan, ws.pw.scan_tmp);
+            pairs::scan64_sums_kernel<<<1, 256, 0, s>>>(ws.pw.scan_tmp, ntiles);
+            pairs::scan64_apply_kernel<<<ntiles, 256, 0, s>>>(ws.pw.pk, nscan, ws.pw.scan_tmp);
+            pairs::finish_kernel<<<(nb + 255) / 256, 256, 0, s>>>(cnts, sts, refs, (const uint2 *)ws.pw.pk, nb, ncnts, nsts, nrefs);
+            pairs::pair_add_kernel<<<pl.pp.grid[r], pairs::THREADS, 0, s>>>(d_points, ws.pw.pool, refs, sts, (const uint2 *)ws.pw.pk, nb,
+                                                                         pl.pp.m[r], (uint32_t)pl.pp.pool_base[r], nrefs, ws.pw.pairrefs,
+                                                                         ws.pw.prefix);
+            refs = nrefs; cnts = ncnts; sts = nsts;
+        }
+        ZKB_CUDA(ctx, cudaGetLastError());
+        ws.sorted = const_cast<uint32_t *>(refs); ws.counts = const_cast<uint32_t *>(cnts); ws.starts = const_cast<uint32_t *>(sts);
+        pool = ws.pw.pool;
+        ctx->launches += 6 * pl.pp.rounds;
+    }
+    ZKB_CUDA(ctx, cudaEventRecord(st->ev_pairs[1], s));
+    st->last_rounds = n32 ? pl.pp.rounds : 0;
     msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, nb, pl.seg, ws.ntasks, ws.size_hist, ws.misc, ws.heavy_list);
     rc = exclusive_scan(ctx, ws.ntasks, ws.task_base, nb, ws.scan_tmp, ws.misc + 1);
     if (rc) return rc;
@@ -685,15 +757,9 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     if (rc) return rc;
     msm_task_scatter_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, ws.ntasks, nb, pl.seg, ws.size_cursor, ws.task_order);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[1], s));
-    if (ctx->msm_mode == 1) {                                   // EXPERIMENTAL: batched affine additions (msm_affine.cu)
-        rc = zkb_launch_accumulate_affine(ctx, s, max_tasks, d_points, ws.sorted, ws.counts, ws.starts, ws.ntasks, ws.task_base,
-                                          ws.task_order, ws.misc, pl.seg, ws.task_out, ws.bucket_val);
-        if (rc) return rc;
-    } else {
-        msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, ws.sorted, ws.counts, ws.starts, ws.ntasks,
-                                                                                 ws.task_base, ws.task_order, ws.misc, pl.seg, ws.task_out,
-                                                                                 ws.bucket_val);
-    }
+    msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, pool, ws.sorted, ws.counts, ws.starts, ws.ntasks,
+                                                                             ws.task_base, ws.task_order, ws.misc, pl.seg, ws.task_out,
+                                                                             ws.bucket_val);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[2], s));
     msm_combine_heavy_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out,
                                                                ws.bucket_val);
@@ -770,6 +836,7 @@ void zkb_msm_release(zkb_ctx *ctx) {
     if (st->copy_stream) cudaStreamDestroy(st->copy_stream);
     for (cudaEvent_t e : st->part_uploaded) if (e) cudaEventDestroy(e);
     for (int k = 0; k < 5; ++k) if (st->ev[k]) cudaEventDestroy(st->ev[k]);
+    for (int k = 0; k < 2; ++k) if (st->ev_pairs[k]) cudaEventDestroy(st->ev_pairs[k]);
     if (st->fixed_base) {
         FixedBase *fb = (FixedBase *)st->fixed_base;
         if (fb->rows.p) cudaFree(fb->rows.p);
@@ -858,7 +925,7 @@ int zkb_srs_precompute(zkb_ctx *ctx, int c) {
 
 int zkb_msm_set_mode(zkb_ctx *ctx, int mode) {
     if (!ctx) return ZKB_ERR_INVALID;
-    if (mode != 0 && mode != 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_set_mode: 0 = XYZZ accumulation, 1 = experimental batch-affine accumulation");
+    if (mode < -1 || mode > pairs::MAX_ROUNDS) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_set_mode: -1 = automatic, 0 = XYZZ accumulation only, 1..6 = that many batched-affine pair rounds first");
     ctx->msm_mode = mode;
     return ZKB_OK;
 }
@@ -1032,6 +1099,17 @@ int zkb_msm_last_timing(zkb_ctx *ctx, float out_ms[5], uint64_t info[3]) {
     for (int k = 0; k < 4; ++k) ZKB_CUDA(ctx, cudaEventElapsedTime(&out_ms[k], st->ev[k], st->ev[k + 1]));
     ZKB_CUDA(ctx, cudaEventElapsedTime(&out_ms[4], st->ev[0], st->ev[4]));
     if (info) { info[0] = st->last_entries; info[1] = st->last_c; info[2] = st->last_W; }
+    return ZKB_OK;
+}
+
+// the share of phase 0 above that the batched-affine pair rounds took, in ms, and how many rounds ran
+int zkb_msm_last_pair_rounds(zkb_ctx *ctx, float *pairs_ms, int *rounds) {
+    if (!ctx || !pairs_ms || !rounds) return ZKB_ERR_INVALID;
+    MsmState *st = state(ctx);
+    if (!st->ev_valid) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_last_pair_rounds: no MSM has run on this context");
+    ZKB_CUDA(ctx, cudaEventSynchronize(st->ev_pairs[1]));
+    ZKB_CUDA(ctx, cudaEventElapsedTime(pairs_ms, st->ev_pairs[0], st->ev_pairs[1]));
+    *rounds = (int)st->last_rounds;
     return ZKB_OK;
 }
 
