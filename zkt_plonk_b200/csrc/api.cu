@@ -126,6 +126,8 @@ int zkb_ctx_create(int device, zkb_ctx **out) {
     const char *mode = getenv("ZKB_MSM_MODE");                  // pair rounds (msm_pairs.cuh): "0".."6", or "-1" / "auto"
     if (mode && mode[0] >= '0' && mode[0] <= '6' && mode[1] == 0) ctx->msm_mode = mode[0] - '0';
     else if (mode && (!strcmp(mode, "-1") || !strcmp(mode, "auto"))) ctx->msm_mode = -1;
+    const char *fg = getenv("ZKB_L2_FETCH");                    // experiment: L2 fetch granularity hint (32 / 64 / 128 bytes)
+    if (fg && (atoi(fg) == 32 || atoi(fg) == 64 || atoi(fg) == 128)) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
     *out = ctx;
     return ZKB_OK;
 }

@@ -38,6 +38,10 @@ constexpr uint32_t PF = 4;               // L2 prefetch distance, in pairs
 __device__ __forceinline__ const g1a_t *ref_ptr(const g1a_t *points, const g1a_t *pool, uint32_t ref) {
     return ((ref & POOL) ? pool : points) + (ref & ID_MASK);
 }
+// `prefetch.global.L2` pulls the whole 128-byte line: exact for a pair of adjacent pool entries (rounds >= 1), but for 64-byte
+// table points gathered at random (round 0) it doubles the DRAM traffic (measured: 6.4 GB read per 6.7 M pairs).  The sized
+// alternative, cp.async.bulk.prefetch.L2, takes a warp-uniform address: ptxas serialises it over the 32 lanes (a waterfall
+// loop of ~7 instructions per lane), which costs more than it saves.
 __device__ __forceinline__ void prefetch_x(const g1a_t *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_xy(const g1a_t *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -145,16 +149,16 @@ __global__ void __launch_bounds__(THREADS, 4) pair_add_kernel(const g1a_t *__res
                                                               const uint2 *__restrict__ sc, uint32_t nb, uint32_t m, uint32_t out_base,
                                                               uint32_t *__restrict__ nrefs, uint2 *__restrict__ pairrefs,
                                                               fe_t *__restrict__ prefix) {
-    const uint32_t T = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t T = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     const uint32_t total = sc[nb].x;
+    if ((unsigned long long)(t - lane) * m >= total) return;      // the whole warp is past the end (warp-uniform)
     const unsigned long long j0l = (unsigned long long)t * m;
-    if (j0l >= total) return;
-    const uint32_t j0 = (uint32_t)j0l, cnt = min(m, total - j0);
+    const uint32_t j0 = j0l < total ? (uint32_t)j0l : total, cnt = min(m, total - j0);   // cnt == 0: only helps with the inversion
     uint2 *my_refs = pairrefs + t;                               // element i at my_refs[i * T]
     fe_t *my_pre = prefix + t;
 
     // ---- phase 1a: which entries form my pairs (metadata only)
-    {
+    if (cnt) {
         uint32_t lo = 0, hi = nb;                                // largest b with sc[b].x <= j0
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 4) pair_add_kernel(const g1a_t *__res
     // ---- phase 1b: running product of the denominators
     const fe_t one = fone<Q>();
     fe_t run = one;
-    {
+    if (cnt) {
         for (uint32_t u = 0; u < PF && u < cnt; ++u) {
             const uint2 pr = my_refs[(size_t)u * T];
             prefetch_x(ref_ptr(points, pool, pr.x));
@@ -218,8 +222,39 @@ __global__ void __launch_bounds__(THREADS, 4) pair_add_kernel(const g1a_t *__res
         }
     }
 
-    // ---- ONE inversion for the whole batch (ALU pipe)
-    fe_t inv = finv_euclid<Q>(run);
+    // ---- ONE inversion per WARP and batch: the 32 lane totals are multiplied up by two shuffle scans (prefix and suffix
+    // products, 5 steps each), lane 0 inverts the warp total (binary extended Euclid, ALU pipe: the other warps of the SM
+    // keep the multiplier busy), and 1 / T_l = (1 / T_0..31) * T_0..l-1 * T_l+1..31.  A lock-step inversion in all 32 lanes
+    // would cost the same issue slots per lane and diverge in its data-dependent loops (measured: 0.5 ms per round).
+    fe_t inv;
+    {
+        fe_t pfx = run, sfx = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            fe_t up, dn;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                up.v[k] = __shfl_up_sync(0xffffffffu, pfx.v[k], d);
+                dn.v[k] = __shfl_down_sync(0xffffffffu, sfx.v[k], d);
+            }
+            if (lane >= (uint32_t)d) pfx = fmul<Q>(pfx, up);
+            if (lane + d < 32) sfx = fmul<Q>(sfx, dn);
+        }
+        fe_t tot;                                                // T_0 * ... * T_31 sits in lane 31's prefix
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot.v[k] = __shfl_sync(0xffffffffu, pfx.v[k], 31);
+        if (lane == 0) tot = finv_euclid<Q>(tot);
+        fe_t before, after;                                      // exclusive prefix / suffix products of my lane
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            tot.v[k] = __shfl_sync(0xffffffffu, tot.v[k], 0);
+            before.v[k] = __shfl_up_sync(0xffffffffu, pfx.v[k], 1);
+            after.v[k] = __shfl_down_sync(0xffffffffu, sfx.v[k], 1);
+        }
+        inv = tot;
+        if (lane > 0) inv = fmul<Q>(inv, before);
+        if (lane < 31) inv = fmul<Q>(inv, after);
+    }
 
     // ---- phase 2: the additions, last pair first
     for (uint32_t u = 0; u < PF && u < cnt; ++u) {
