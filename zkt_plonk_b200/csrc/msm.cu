@@ -66,8 +66,12 @@ struct MsmWs {                           // carved out of ctx->msm_ws
     uint32_t *counts, *starts, *cursor, *ntasks, *task_base, *sorted;
     uint32_t *scan_tmp;                  // block sums for the scans
     uint32_t *size_hist, *size_cursor;   // SEG + 1 bins
-    uint32_t *misc;                      // [0] = heavy bucket count, [1] = total tasks
-    uint32_t *heavy_list;
+    uint32_t *misc;                      // [0] heavy buckets, [1] total tasks, [2] chunk items, [3] chunk_out slots, [4] multi-chunk buckets
+    uint32_t *heavy_list;                // buckets cut into more than one task
+    uint32_t *heavy_slot;                // per heavy bucket: first slot in chunk_out, or ~0 when it has a single chunk
+    uint32_t *multi_list;                // heavy-list indices of the buckets with more than one chunk
+    uint2 *chunk_items;                  // (heavy-list index, chunk): one warp folds up to HEAVY_CHUNK task results
+    g1x_t *chunk_out;                    // chunk sums of multi-chunk buckets
     uint2 *task_order;
     g1x_t *task_out;                     // partial sums of the tasks of multi-task buckets
     g1x_t *bucket_val;                   // dense: one XYZZ value per bucket (zero = empty)
@@ -105,7 +109,7 @@ struct MsmState {
 // Window w covers bits [start_w, start_w + width_w): the first `wide` windows are c bits wide, the rest c - 1
 // (wide = W: uniform c-bit windows).  Balanced widths keep every window's digit spread over the whole bucket range.
 template <class F>
-__device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], uint32_t c, uint32_t W, uint32_t wide, F f) {
+__device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], uint32_t c, uint32_t W, uint32_t wide, F f, uint32_t w0 = 0) {
     uint32_t carry = 0, bit = 0;
     for (uint32_t w = 0; w < W; ++w) {
         const uint32_t width = w < wide ? c : c - 1;
@@ -117,12 +121,23 @@ __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], uint32_t 
         raw += carry;
         if (raw > half) {
             carry = 1;                            // digit = raw - 2^c <= 0
-            if (raw != full) f(w, full - raw - 1, true);
+            if (raw != full && w >= w0) f(w, full - raw - 1, true);
         } else {
             carry = 0;
-            if (raw) f(w, raw - 1, false);
+            if (raw && w >= w0) f(w, raw - 1, false);
         }
     }
+}
+
+// digit of window 0 alone (no incoming carry): returns false when it is zero
+__device__ __forceinline__ bool first_digit(const uint32_t (&s)[8], uint32_t c, uint32_t wide, uint32_t *bucket, bool *neg) {
+    const uint32_t width = wide > 0 ? c : c - 1;
+    const uint32_t half = 1u << (width - 1), full = 1u << width;
+    const uint32_t raw = s[0] & (full - 1);                       // width <= 24 bits: inside the first limb
+    if (raw > half) { *bucket = full - raw - 1; *neg = true; return true; }   // raw < full always (no carry in)
+    *bucket = raw - 1;
+    *neg = false;
+    return raw != 0;
 }
 
 __device__ __forceinline__ void load_scalar(const uint4 *p, size_t i, uint32_t (&s)[8]) {
@@ -130,26 +145,48 @@ __device__ __forceinline__ void load_scalar(const uint4 *p, size_t i, uint32_t (
     s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
 }
 
+// Window 0 is where skewed scalars collide: every scalar equal to one (and every small one) has its only digit there, so
+// a witness-like vector sends 20 % of its entries to ONE counter.  Lanes of a warp that hit the same bucket are found
+// with match.any and served by one atomic (the leader adds the group's size and hands out ranks); the other windows'
+// digits are spread and go one atomic each.
+__device__ __forceinline__ uint32_t warp_aggregated_add(uint32_t *counters, uint32_t bucket, bool has, uint32_t *rank) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t peers = __match_any_sync(0xffffffffu, has ? bucket : 0xffffffffu);     // lanes without a digit group together
+    const uint32_t leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (has && lane == leader) base = atomicAdd(&counters[bucket], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    *rank = __popc(peers & ((1u << lane) - 1));
+    return base;
+}
+
 // gstride = B when every window has its own bucket group, 0 when all windows share one (fixed-base tables)
 __global__ void msm_count_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, uint32_t gstride, uint32_t *counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t s[8];
-    load_scalar(scalars, i, s);
-    for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t b, bool) { atomicAdd(&counts[w * gstride + b], 1u); });
+    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (i < n) load_scalar(scalars, i, s);                        // lanes past the end keep s = 0: no digits
+    uint32_t b0 = 0, rank;
+    bool neg0 = false;
+    const bool has0 = first_digit(s, c, wide, &b0, &neg0);
+    warp_aggregated_add(counts, b0, has0, &rank);
+    for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t b, bool) { atomicAdd(&counts[w * gstride + b], 1u); }, 1);
 }
 
 // entry id = id_base + w * id_stride + i  (id_stride = 0: plain bases; = SRS size: fixed-base table rows)
 __global__ void msm_scatter_kernel(const uint4 *scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, uint32_t gstride,
                                    uint32_t id_base, uint32_t id_stride, uint32_t *cursor, uint32_t *sorted) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t s[8];
-    load_scalar(scalars, i, s);
+    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (i < n) load_scalar(scalars, i, s);
+    uint32_t b0 = 0, rank;
+    bool neg0 = false;
+    const bool has0 = first_digit(s, c, wide, &b0, &neg0);
+    const uint32_t base0 = warp_aggregated_add(cursor, b0, has0, &rank);
+    if (has0) sorted[base0 + rank] = (id_base + i) | (neg0 ? SIGN_BIT : 0u);
     for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t b, bool neg) {
         uint32_t slot = atomicAdd(&cursor[w * gstride + b], 1u);
         sorted[slot] = (id_base + w * id_stride + i) | (neg ? SIGN_BIT : 0u);
-    });
+    }, 1);
 }
 
 // ------------------------------------------------------------------ exclusive scan of uint32 (three phases)
@@ -228,8 +265,10 @@ int exclusive_scan(zkb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, 
 }
 
 // ------------------------------------------------------------------ tasks
+constexpr uint32_t HEAVY_CHUNK = 64;     // task results folded by one warp (two per lane, then a shuffle tree)
+
 __global__ void msm_ntasks_kernel(const uint32_t *counts, uint32_t nb, uint32_t SEG, uint32_t *ntasks, uint32_t *size_hist,
-                                  uint32_t *misc, uint32_t *heavy_list) {
+                                  uint32_t *misc, uint32_t *heavy_list, uint32_t *heavy_slot, uint32_t *multi_list, uint2 *chunk_items) {
     __shared__ uint32_t h[SEG_MAX + 1];
     for (uint32_t k = threadIdx.x; k <= SEG; k += blockDim.x) h[k] = 0;
     __syncthreads();
@@ -242,7 +281,18 @@ __global__ void msm_ntasks_kernel(const uint32_t *counts, uint32_t nb, uint32_t 
             uint32_t full = cnt / SEG, rem = cnt - full * SEG;
             if (full) atomicAdd(&h[0], full);               // bin = SEG - size (descending size order)
             if (rem) atomicAdd(&h[SEG - rem], 1u);
-            if (nt > 1) heavy_list[atomicAdd(&misc[0], 1u)] = b;
+            if (nt > 1) {                                   // oversized bucket: its task results are folded in chunks of HEAVY_CHUNK
+                const uint32_t h = atomicAdd(&misc[0], 1u), chunks = (nt + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+                heavy_list[h] = b;
+                const uint32_t c0 = atomicAdd(&misc[2], chunks);
+                for (uint32_t k = 0; k < chunks; ++k) chunk_items[c0 + k] = make_uint2(h, k);
+                if (chunks > 1) {
+                    heavy_slot[h] = atomicAdd(&misc[3], chunks);
+                    multi_list[atomicAdd(&misc[4], 1u)] = h;
+                } else {
+                    heavy_slot[h] = 0xffffffffu;
+                }
+            }
         }
     }
     __syncthreads();
@@ -325,54 +375,50 @@ __device__ __forceinline__ g1x_t shfl_down_g1x(const g1x_t &p, int d) {
     return r;
 }
 
-constexpr uint32_t HEAVY_CTA_MIN = 64;   // buckets with more tasks than this are folded by a whole CTA
+// Oversized buckets (skewed scalars: ones / small values pile up on a few digits), two stages of one warp per work item.
+// Stage 1: a warp folds one chunk of <= HEAVY_CHUNK task results of a bucket (two per lane, then a shuffle tree: 7 additions
+// deep) into the bucket's value (single chunk) or into a chunk sum.  Stage 2: a warp folds the chunk sums of a multi-chunk
+// bucket (lanes stride over them).  A 200k-entry bucket cut into 64-entry tasks is 3300 tasks -> 52 chunks -> one value, each
+// stage ~30 us, instead of one CTA walking all task results.
+__device__ __forceinline__ void warp_fold_store(g1x_t acc, uint32_t lane, uint32_t live, g1x_t *dst) {
+    for (int d = 16; d >= 1; d >>= 1) {
+        if ((uint32_t)d >= live) continue;                         // uniform across the warp
+        g1x_t o = shfl_down_g1x(acc, d);
+        if (lane < (uint32_t)d) g1x_add(acc, o);
+    }
+    __syncwarp();
+    if (lane == 0) g1x_store(dst, acc);
+}
 
-// buckets with 2..HEAVY_CTA_MIN tasks: one warp each, lanes stride over the task results, shuffle tree at the end
-__global__ void __launch_bounds__(128) msm_combine_heavy_kernel(const uint32_t *misc, const uint32_t *heavy_list,
-                                                                const uint32_t *ntasks, const uint32_t *task_base,
-                                                                const g1x_t *task_out, g1x_t *bucket_val) {
-    uint32_t lane = threadIdx.x & 31;
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    uint32_t nheavy = misc[0];
-    for (uint32_t h = warp; h < nheavy; h += nwarps) {
-        uint32_t b = heavy_list[h], nt = ntasks[b];
-        if (nt > HEAVY_CTA_MIN) continue;
-        const g1x_t *base = task_out + task_base[b];
+__global__ void __launch_bounds__(128) msm_combine_chunks_kernel(const uint32_t *misc, const uint32_t *heavy_list, const uint32_t *heavy_slot,
+                                                                 const uint2 *chunk_items, const uint32_t *ntasks, const uint32_t *task_base,
+                                                                 const g1x_t *task_out, g1x_t *chunk_out, g1x_t *bucket_val) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nitems = misc[2];
+    for (uint32_t it = warp; it < nitems; it += nwarps) {
+        const uint2 item = chunk_items[it];
+        const uint32_t b = heavy_list[item.x], nt = ntasks[b], lo = item.y * HEAVY_CHUNK, len = min(HEAVY_CHUNK, nt - lo);
+        const g1x_t *base = task_out + task_base[b] + lo;
         g1x_t acc = g1x_inf();
-        for (uint32_t k = lane; k < nt; k += 32) g1x_add(acc, g1x_load(base + k));
-        for (int d = 16; d >= 1; d >>= 1) {
-            if ((uint32_t)d >= nt) continue;                     // uniform across the warp
-            g1x_t o = shfl_down_g1x(acc, d);
-            if (lane < (uint32_t)d) g1x_add(acc, o);
-        }
-        __syncwarp();
-        if (lane == 0) g1x_store(bucket_val + b, acc);
+        for (uint32_t k = lane; k < len; k += 32) g1x_add(acc, g1x_load(base + k));
+        const uint32_t slot = heavy_slot[item.x];
+        warp_fold_store(acc, lane, min(len, 32u), slot == 0xffffffffu ? bucket_val + b : chunk_out + slot + item.y);
     }
 }
 
-// giant buckets (skewed scalars: zeros / ones / small values pile up on a few digits): one CTA each
-__global__ void __launch_bounds__(128) msm_combine_giant_kernel(const uint32_t *misc, const uint32_t *heavy_list,
-                                                                const uint32_t *ntasks, const uint32_t *task_base,
-                                                                const g1x_t *task_out, g1x_t *bucket_val) {
-    __shared__ g1x_t sm[128];
-    uint32_t nheavy = misc[0];
-    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
-        uint32_t b = heavy_list[h], nt = ntasks[b];
-        if (nt <= HEAVY_CTA_MIN) continue;                       // uniform across the CTA
-        const g1x_t *base = task_out + task_base[b];
+__global__ void __launch_bounds__(128) msm_combine_final_kernel(const uint32_t *misc, const uint32_t *heavy_list, const uint32_t *heavy_slot,
+                                                                const uint32_t *multi_list, const uint32_t *ntasks, const g1x_t *chunk_out,
+                                                                g1x_t *bucket_val) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nmulti = misc[4];
+    for (uint32_t it = warp; it < nmulti; it += nwarps) {
+        const uint32_t h = multi_list[it], b = heavy_list[h], chunks = (ntasks[b] + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+        const g1x_t *base = chunk_out + heavy_slot[h];
         g1x_t acc = g1x_inf();
-        for (uint32_t k = threadIdx.x; k < nt; k += 128) g1x_add(acc, g1x_load(base + k));
-        sm[threadIdx.x] = acc;
-        for (uint32_t stride = 64; stride >= 1; stride >>= 1) {
-            __syncthreads();
-            if (threadIdx.x < stride) {
-                g1x_t a = sm[threadIdx.x];
-                g1x_add(a, sm[threadIdx.x + stride]);
-                sm[threadIdx.x] = a;
-            }
-        }
-        if (threadIdx.x == 0) g1x_store(bucket_val + b, sm[0]);
-        __syncthreads();
+        for (uint32_t k = lane; k < chunks; k += 32) g1x_add(acc, g1x_load(base + k));
+        warp_fold_store(acc, lane, min(chunks, 32u), bucket_val + b);
     }
 }
 
@@ -607,12 +653,13 @@ MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset, int
         pl.red_buf_elems[l & 1] = std::max(pl.red_buf_elems[l & 1], out_elems);
         ++pl.red_levels;
     }
-    // task length: at least 256 and four times the mean bucket load (rounded up to a power of two, capped), so
-    // that ordinary buckets -- including the denser ones of narrow / top windows -- stay a single task while an
-    // oversized bucket (skewed scalars) is cut into pieces a few times the typical thread's work
+    // task length: at least 64 and 2.5 times the mean bucket load (rounded up to a power of two, capped), so that
+    // ordinary buckets stay a single task while an oversized bucket (skewed scalars) is cut into pieces of a few times the
+    // typical thread's work: the accumulation ends when its longest task does, and a lone warp needs ~4 us per addition
+    // (256-entry tasks kept the witness-like 2^20 MSM at 1.38 ms of accumulation for 43 % of the insertions)
     double mean = (double)n * pl.W / (double)pl.nbuckets;
-    uint32_t seg = 256;
-    while (seg < 4.0 * mean && seg < SEG_MAX) seg <<= 1;
+    uint32_t seg = 64;
+    while (seg < 2.5 * mean && seg < SEG_MAX) seg <<= 1;
     pl.seg = seg;
     const uint64_t max_id = fb ? (uint64_t)pl.id_base + (uint64_t)(pl.W - 1) * pl.id_stride + n : n;
     pl.pp = pairs::make_plan(pick_pair_rounds(pair_mode, (uint64_t)n * pl.W, pl.nbuckets, max_id), (uint64_t)n * pl.W, pl.nbuckets,
@@ -632,6 +679,8 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
     size_t o_counts = take(nb * 4), o_starts = take(nb * 4), o_cursor = take(nb * 4), o_ntasks = take(nb * 4),
            o_tbase = take(nb * 4), o_sorted = take(entries * 4 + 4), o_scan = take((nb / SCAN_TILE + 2) * 4),
            o_hist = take((SEG_MAX + 1) * 4), o_hcur = take((SEG_MAX + 1) * 4), o_misc = take(64), o_heavy = take(nb * 4),
+           o_hslot = take(nb * 4), o_multi = take(nb * 4), o_citems = take((nb + max_tasks / HEAVY_CHUNK + 2) * 8),
+           o_cout = take((max_tasks / (HEAVY_CHUNK / 2) + 4) * sizeof(g1x_t)),
            o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)), o_bval = take(nb * sizeof(g1x_t)),
            o_red0 = take(pl.red_buf_elems[0] * sizeof(g1x_t)), o_red1 = take(pl.red_buf_elems[1] * sizeof(g1x_t));
     size_t o_pr[2] = {0, 0}, o_pc[2] = {0, 0}, o_ps[2] = {0, 0}, o_pk = 0, o_pscan = 0, o_prefs = 0, o_ppre = 0, o_pool = 0;
@@ -654,6 +703,8 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
     ws.ntasks = (uint32_t *)(p + o_ntasks); ws.task_base = (uint32_t *)(p + o_tbase); ws.sorted = (uint32_t *)(p + o_sorted);
     ws.scan_tmp = (uint32_t *)(p + o_scan); ws.size_hist = (uint32_t *)(p + o_hist); ws.size_cursor = (uint32_t *)(p + o_hcur);
     ws.misc = (uint32_t *)(p + o_misc); ws.heavy_list = (uint32_t *)(p + o_heavy); ws.task_order = (uint2 *)(p + o_order);
+    ws.heavy_slot = (uint32_t *)(p + o_hslot); ws.multi_list = (uint32_t *)(p + o_multi); ws.chunk_items = (uint2 *)(p + o_citems);
+    ws.chunk_out = (g1x_t *)(p + o_cout);
     ws.task_out = (g1x_t *)(p + o_out); ws.bucket_val = (g1x_t *)(p + o_bval);
     ws.red_buf[0] = (g1x_t *)(p + o_red0); ws.red_buf[1] = (g1x_t *)(p + o_red1);
     if (pl.pp.rounds) {
@@ -750,7 +801,8 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     }
     ZKB_CUDA(ctx, cudaEventRecord(st->ev_pairs[1], s));
     st->last_rounds = n32 ? pl.pp.rounds : 0;
-    msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, nb, pl.seg, ws.ntasks, ws.size_hist, ws.misc, ws.heavy_list);
+    msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, nb, pl.seg, ws.ntasks, ws.size_hist, ws.misc, ws.heavy_list, ws.heavy_slot,
+                                                       ws.multi_list, ws.chunk_items);
     rc = exclusive_scan(ctx, ws.ntasks, ws.task_base, nb, ws.scan_tmp, ws.misc + 1);
     if (rc) return rc;
     rc = exclusive_scan(ctx, ws.size_hist, ws.size_cursor, pl.seg + 1, ws.scan_tmp, nullptr);
@@ -761,9 +813,9 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
                                                                              ws.task_base, ws.task_order, ws.misc, pl.seg, ws.task_out,
                                                                              ws.bucket_val);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[2], s));
-    msm_combine_heavy_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out,
-                                                               ws.bucket_val);
-    msm_combine_giant_kernel<<<ctx->sm_count, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.ntasks, ws.task_base, ws.task_out,
+    msm_combine_chunks_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.heavy_slot, ws.chunk_items, ws.ntasks, ws.task_base,
+                                                                ws.task_out, ws.chunk_out, ws.bucket_val);
+    msm_combine_final_kernel<<<ctx->sm_count, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.heavy_slot, ws.multi_list, ws.ntasks, ws.chunk_out,
                                                           ws.bucket_val);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[3], s));
     cudaStream_t ts = s;

@@ -14,6 +14,8 @@
 // In a tile the transform is decimation-in-frequency with one __syncthreads per stage; elements sit in
 // shared memory as two 16-byte planes (low / high half) so that a quarter-warp always covers all 32 banks.
 // Coset scaling and the n^-1 factor are fused into the first load / last store.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "ctx.h"
@@ -171,6 +173,126 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const __grid_constant__ P
             emit_output(a, out, c, r, base, k, x[p]);
         }
     }
+}
+
+
+// ------------------------------------------------------------------ compile-time tile size: radix-4 steps, 3 CTAs per SM
+// Same pass as ntt_pass_kernel (same PassArgs, same tables, bit-identical results) restructured around what limited it
+// (ncu, round 1: 2 CTAs of 256 threads per SM at 108 registers, 8 barriers per tile, twiddle loads stalling each product):
+//   * LT is a template parameter, every loop is unrolled, so ptxas hoists the twiddle and shared-memory loads of a step above
+//     its products;
+//   * two butterfly stages per barrier (a radix-4 step on elements j, j + H/2, j + H, j + 3H/2: four products, three
+//     twiddles w^j, w^(j + H/2), w^(2j)), the first stage of an odd-sized tile is done on the fly while loading (its
+//     partners j and j + T/2 are loaded by the same thread), the last two stages run in registers on 4 consecutive
+//     elements and go straight to global memory: 5 barriers instead of 8 for T = 2048;
+//   * at most 4 elements live per thread (32 data registers), so the kernel fits 80 registers: 3 CTAs of 256 threads
+//     (6 warps per scheduler instead of 4) to cover the fixed-latency carry chains and the load / store phases.
+template <int LT>
+__global__ void __launch_bounds__((1 << LT) / 8, 768 / ((1 << LT) / 8)) ntt_pass_kernel_r4(const __grid_constant__ PassArgs a) {
+    constexpr uint32_t T = 1u << LT, NT = T / 8;
+    constexpr bool ODD = (LT & 1) != 0;                            // odd tile bits: stage LT-1 is fused into the load
+    extern __shared__ uint4 sm[];
+    uint4 *const mine = a.data[blockIdx.y], *const scr = a.scr + blockIdx.y * a.scr_stride;
+    const uint4 *const in = (a.mode & M_FIRST) ? mine : scr;
+    uint4 *const out = (a.mode & M_LAST) ? mine : scr;
+    uint4 *s_lo = sm, *s_hi = sm + T + (T >> 3) + 1;
+    const uint32_t tid = threadIdx.x;
+    const unsigned long long tile = blockIdx.x;
+    const unsigned long long c = tile & ((1ull << a.log_s) - 1);
+    const unsigned long long r = tile >> a.log_s;
+    const unsigned long long base = (r << (LT + a.log_s)) + c;
+
+    auto load_elem = [&](uint32_t j) -> fe_t {
+        const unsigned long long idx = base + ((unsigned long long)j << a.log_s);
+        if (idx >= a.len) return fzero<FrP>();
+        fe_t v = fload(in + 2 * idx);
+        if (a.mode & M_IN_COSET) v = fmul<FrP>(v, a.cs_direct ? fload_ro(a.cs_direct + 2 * idx) : pow2lvl(a.cs2, a.cs_s, idx));
+        return v;
+    };
+
+    // ---- load (zero padding + coset scaling fused); odd LT: butterfly with the partner T/2 away before the store
+    if (ODD) {
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            const uint32_t j = tid + NT * q;                       // j < T/2
+            fe_t u = load_elem(j), v = load_elem(j + T / 2);
+            fe_t d = fsub<FrP>(u, v);
+            u = fadd<FrP>(u, v);
+            d = fmul<FrP>(d, fload_ro(a.tile_tw + 2 * (size_t)j));
+            sm_store(s_lo, s_hi, j, u);
+            sm_store(s_lo, s_hi, j + T / 2, d);
+        }
+    } else {
+#pragma unroll
+        for (uint32_t q = 0; q < 8; ++q) sm_store(s_lo, s_hi, tid + NT * q, load_elem(tid + NT * q));
+    }
+
+    // ---- radix-4 steps through shared memory: stages (lh, lh - 1), lh = LT-1-ODD, LT-3-ODD, ..., 3
+    constexpr int LH0 = LT - 1 - (ODD ? 1 : 0);
+#pragma unroll
+    for (int lh = LH0; lh >= 3; lh -= 2) {
+        __syncthreads();
+        const uint32_t H = 1u << lh, s1 = 1u << (LT - 1 - lh);     // twiddle stride of stage lh; stage lh - 1 uses 2 * s1
+#pragma unroll
+        for (uint32_t q = 0; q < 2; ++q) {
+            const uint32_t g = tid + NT * q;                       // group of 4, g < T/4
+            const uint32_t j = g & (H / 2 - 1), blk = g >> (lh - 1);
+            const uint32_t e0 = (blk << (lh + 1)) + j;
+            fe_t x0 = sm_load(s_lo, s_hi, e0), x1 = sm_load(s_lo, s_hi, e0 + H / 2);
+            fe_t x2 = sm_load(s_lo, s_hi, e0 + H), x3 = sm_load(s_lo, s_hi, e0 + H + H / 2);
+            // stage lh: (x0, x2) with w^(j s1), (x1, x3) with w^((j + H/2) s1)
+            fe_t d = fsub<FrP>(x0, x2);
+            x0 = fadd<FrP>(x0, x2);
+            x2 = fmul<FrP>(d, fload_ro(a.tile_tw + 2 * (size_t)(j * s1)));
+            d = fsub<FrP>(x1, x3);
+            x1 = fadd<FrP>(x1, x3);
+            x3 = fmul<FrP>(d, fload_ro(a.tile_tw + 2 * (size_t)((j + H / 2) * s1)));
+            // stage lh - 1: (x0, x1) and (x2, x3), both with w^(2 j s1)
+            const fe_t w2 = fload_ro(a.tile_tw + 2 * (size_t)(2 * j * s1));
+            d = fsub<FrP>(x0, x1);
+            x0 = fadd<FrP>(x0, x1);
+            x1 = fmul<FrP>(d, w2);
+            d = fsub<FrP>(x2, x3);
+            x2 = fadd<FrP>(x2, x3);
+            x3 = fmul<FrP>(d, w2);
+            sm_store(s_lo, s_hi, e0, x0);
+            sm_store(s_lo, s_hi, e0 + H / 2, x1);
+            sm_store(s_lo, s_hi, e0 + H, x2);
+            sm_store(s_lo, s_hi, e0 + H + H / 2, x3);
+        }
+    }
+    __syncthreads();
+
+    // ---- last two stages (h = 2, 1) on 4 consecutive elements in registers: one product (w_4), then the outputs
+    const fe_t w4 = fload_ro(a.tile_tw + 2 * (size_t)(T >> 2));
+#pragma unroll
+    for (uint32_t q = 0; q < 2; ++q) {
+        const uint32_t g = tid + NT * q;
+        fe_t x0 = sm_load(s_lo, s_hi, 4 * g), x1 = sm_load(s_lo, s_hi, 4 * g + 1);
+        fe_t x2 = sm_load(s_lo, s_hi, 4 * g + 2), x3 = sm_load(s_lo, s_hi, 4 * g + 3);
+        bfly(x0, x2);
+        bfly(x1, x3);
+        x3 = fmul<FrP>(x3, w4);
+        bfly(x0, x1);
+        bfly(x2, x3);
+        emit_output(a, out, c, r, base, __brev(4 * g) >> (32 - LT), x0);
+        emit_output(a, out, c, r, base, __brev(4 * g + 1) >> (32 - LT), x1);
+        emit_output(a, out, c, r, base, __brev(4 * g + 2) >> (32 - LT), x2);
+        emit_output(a, out, c, r, base, __brev(4 * g + 3) >> (32 - LT), x3);
+    }
+}
+
+template <int LT>
+int launch_r4(zkb_ctx *ctx, const PassArgs &a, size_t tiles, size_t count) {
+    constexpr size_t T = (size_t)1 << LT;
+    const size_t smem = 2 * (T + T / 8 + 1) * 16;
+    static bool configured = false;
+    if (!configured) {
+        ZKB_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel_r4<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        configured = true;
+    }
+    ntt_pass_kernel_r4<LT><<<dim3((unsigned)tiles, (unsigned)count), (unsigned)(T / 8), smem, ctx->stream>>>(a);
+    return ZKB_OK;
 }
 
 // out[j] = scale * base^(j << shift)
@@ -389,7 +511,14 @@ int zkb_ntt_run_batch(zkb_ctx *ctx, uint64_t *const *d_ptrs, size_t count, size_
         unsigned threads = (unsigned)(T / 8 < 32 ? 32 : (T / 8 > 256 ? 256 : T / 8));
         size_t tiles = n >> t;
         size_t smem = 2 * (T + T / 8 + 1) * 16;
-        ntt_pass_kernel<<<dim3((unsigned)tiles, (unsigned)count), threads, smem, ctx->stream>>>(a);
+        static const bool use_r4 = !getenv("ZKB_NTT_V1");          // ZKB_NTT_V1=1: the round-1 kernel (A/B measurements)
+        rc = ZKB_OK;
+        if (use_r4 && t == 11) rc = launch_r4<11>(ctx, a, tiles, count);
+        else if (use_r4 && t == 10) rc = launch_r4<10>(ctx, a, tiles, count);
+        else if (use_r4 && t == 9) rc = launch_r4<9>(ctx, a, tiles, count);
+        else if (use_r4 && t == 8) rc = launch_r4<8>(ctx, a, tiles, count);
+        else ntt_pass_kernel<<<dim3((unsigned)tiles, (unsigned)count), threads, smem, ctx->stream>>>(a);
+        if (rc) return rc;
         ctx->launches += 1;
         ZKB_CUDA(ctx, cudaGetLastError());
     }
