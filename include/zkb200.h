@@ -79,6 +79,11 @@ ZKB_API int zkb_ntt_batch_dev(zkb_ctx *ctx, uint64_t *const *ptrs_host, size_t c
  * transforms of 2^12..2^26 elements) save one field product per element per use.  enable = 0 falls back to the
  * two-level tables (a few KB) when HBM is needed for something else.  Default: enabled. */
 ZKB_API int zkb_ntt_set_direct_tables(zkb_ctx *ctx, int enable);
+/* Pass kernel: 0 (default) = the radix-4 kernel (compile-time tile size, two stages per barrier, 3 CTAs per SM) on
+ * 2048-element tiles, where it measured faster, the generic kernel elsewhere; 1 = the generic kernel everywhere; 2 = the
+ * radix-4 kernel on every tile of 256..2048 elements.  Same results for every choice.  ZKB_NTT_KERNEL=<kind> in the
+ * environment sets it for contexts created afterwards. */
+ZKB_API int zkb_ntt_set_kernel(zkb_ctx *ctx, int kind);
 
 /* ---- MSM: replaces VariableBaseMSM::multi_scalar_mul / kzg10::commit's inner product ------------------------------ */
 /* Reference: ark-ec 0.3 msm::VariableBaseMSM::multi_scalar_mul, called from plonk-core/src/commitment.rs:42 and via

@@ -39,6 +39,31 @@ def test_large_against_oracle(ctx, log_n):
     assert np.array_equal(to_host(d), x)
 
 
+@pytest.mark.parametrize("kind", [1, 2])
+def test_both_pass_kernels_give_the_same_results(ctx, kind):
+    """zkb_ntt_set_kernel: the generic pass kernel everywhere (1) and the radix-4 kernel on every tile of 256..2048 elements
+    (2; the default uses it on 2048-element tiles only) against the oracle: 2^16 = 8+8, 2^17 = 9+8, 2^19 = 10+9, 2^21 = 11+10,
+    2^22 = 11+11 bits, all four modes, and a zero-padded batch."""
+    ctx.ntt_set_kernel(kind)
+    try:
+        for log_n in (16, 17, 19, 21, 22):
+            x = rand_fr_mont(1 << log_n, 2000 + log_n)
+            for inv, cos in (MODES if log_n <= 19 else [(False, True), (True, True)]):
+                d = to_dev(x)
+                ctx.ntt_dev(d, log_n, inv, cos)
+                assert np.array_equal(to_host(d), cref.ntt(x, log_n, inv, cos)), (log_n, inv, cos)
+        log_n, length = 18, (1 << 16) + 3
+        xs = [rand_fr_mont(1 << log_n, 2100 + k) for k in range(3)]
+        ds = [to_dev(x) for x in xs]
+        ctx.ntt_batch_dev(ds, log_n, False, True, length=length)
+        for x, d in zip(xs, ds):
+            ref_in = np.zeros_like(x)
+            ref_in[:length] = x[:length]
+            assert np.array_equal(to_host(d), cref.ntt(ref_in, log_n, False, True))
+    finally:
+        ctx.ntt_set_kernel(0)
+
+
 def test_two_level_tables_give_the_same_results(ctx):
     """zkb_ntt_set_direct_tables(0): the small two-level twiddle path (used above 2^26 or when HBM is scarce)."""
     log_n = 14

@@ -1,5 +1,5 @@
 """NTT timing on one GPU as JSON lines: coset forward / inverse, zero-padded coset (the quotient round's shape) and the batch of
-nine, per size.  ZKB_NTT_V1=1 in the environment selects the round-1 pass kernel (A/B against the radix-4 kernel).
+nine, per size.  ZKB_NTT_KERNEL=0/1/2 in the environment selects the pass kernel (zkb_ntt_set_kernel).
 
   python tools/ntt_ab.py [--sizes 16 18 20 22 24]"""
 import argparse, json, os, sys
@@ -26,7 +26,7 @@ def timeit(fn, reps=7, warm=3):
     return min(ts), float(np.median(ts))
 
 
-variant = "v1" if os.environ.get("ZKB_NTT_V1") else "r4"
+variant = {"0": "default", "1": "generic", "2": "radix4_all"}[os.environ.get("ZKB_NTT_KERNEL", "0")]
 for log_n in args.sizes:
     n = 1 << log_n
     d = torch.randint(0, 2**62, (n, 4), dtype=torch.int64, device="cuda"); d[:, 3] &= (1 << 60) - 1

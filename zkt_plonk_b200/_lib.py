@@ -49,6 +49,7 @@ def load():
         "zkb_ntt_dev": (i, [vp, vp, sz, u, i, i]),
         "zkb_ntt_batch_dev": (i, [vp, ctypes.POINTER(vp), sz, sz, u, i, i]),
         "zkb_ntt_set_direct_tables": (i, [vp, i]),
+        "zkb_ntt_set_kernel": (i, [vp, i]),
         "zkb_srs_load_g1": (i, [vp, vp, sz]),
         "zkb_srs_load_g1_dev": (i, [vp, vp, sz]),
         "zkb_srs_size": (sz, [vp]),

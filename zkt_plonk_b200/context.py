@@ -81,6 +81,10 @@ class Context:
                                                 int(inverse), int(coset)))
         return tensors
 
+    def ntt_set_kernel(self, kind):
+        """0: radix-4 pass kernel on 2048-element tiles (default), 1: generic kernel everywhere, 2: radix-4 wherever it exists."""
+        self._check(self._lib.zkb_ntt_set_kernel(self._h, int(kind)))
+
     def ntt_set_direct_tables(self, enable):
         self._check(self._lib.zkb_ntt_set_direct_tables(self._h, int(bool(enable))))
 

@@ -126,6 +126,8 @@ int zkb_ctx_create(int device, zkb_ctx **out) {
     const char *mode = getenv("ZKB_MSM_MODE");                  // pair rounds (msm_pairs.cuh): "0".."6", or "-1" / "auto"
     if (mode && mode[0] >= '0' && mode[0] <= '6' && mode[1] == 0) ctx->msm_mode = mode[0] - '0';
     else if (mode && (!strcmp(mode, "-1") || !strcmp(mode, "auto"))) ctx->msm_mode = -1;
+    const char *nk = getenv("ZKB_NTT_KERNEL");                  // "0" / "1" / "2": see zkb_ntt_set_kernel
+    if (nk && nk[0] >= '0' && nk[0] <= '2' && nk[1] == 0) ctx->ntt_kernel = nk[0] - '0';
     const char *fg = getenv("ZKB_L2_FETCH");                    // experiment: L2 fetch granularity hint (32 / 64 / 128 bytes)
     if (fg && (atoi(fg) == 32 || atoi(fg) == 64 || atoi(fg) == 128)) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
     *out = ctx;
@@ -193,6 +195,12 @@ int zkb_d2h(zkb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
 }
 
 // ---------------------------------------------------------------------------------------------- NTT
+int zkb_ntt_set_kernel(zkb_ctx *ctx, int kind) {
+    if (!ctx || kind < 0 || kind > 2) return ZKB_ERR_INVALID;
+    ctx->ntt_kernel = kind;
+    return ZKB_OK;
+}
+
 int zkb_ntt_set_direct_tables(zkb_ctx *ctx, int enable) {
     if (!ctx) return ZKB_ERR_INVALID;
     ctx->ntt_no_direct = !enable;

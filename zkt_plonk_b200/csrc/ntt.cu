@@ -511,12 +511,14 @@ int zkb_ntt_run_batch(zkb_ctx *ctx, uint64_t *const *d_ptrs, size_t count, size_
         unsigned threads = (unsigned)(T / 8 < 32 ? 32 : (T / 8 > 256 ? 256 : T / 8));
         size_t tiles = n >> t;
         size_t smem = 2 * (T + T / 8 + 1) * 16;
-        static const bool use_r4 = !getenv("ZKB_NTT_V1");          // ZKB_NTT_V1=1: the round-1 kernel (A/B measurements)
+        // measured (profiles/r02d_ntt_*.jsonl): the radix-4 kernel wins on 2048-element tiles (2^22: 0.94 vs 1.05 ms, nine at
+        // once 7.1 vs 8.4 ms) and loses on smaller ones, where its 216 KB of shared memory per SM leave the tile twiddles no L1
+        const bool r4_all = ctx->ntt_kernel == 2;
         rc = ZKB_OK;
-        if (use_r4 && t == 11) rc = launch_r4<11>(ctx, a, tiles, count);
-        else if (use_r4 && t == 10) rc = launch_r4<10>(ctx, a, tiles, count);
-        else if (use_r4 && t == 9) rc = launch_r4<9>(ctx, a, tiles, count);
-        else if (use_r4 && t == 8) rc = launch_r4<8>(ctx, a, tiles, count);
+        if (t == 11 && ctx->ntt_kernel != 1) rc = launch_r4<11>(ctx, a, tiles, count);
+        else if (r4_all && t == 10) rc = launch_r4<10>(ctx, a, tiles, count);
+        else if (r4_all && t == 9) rc = launch_r4<9>(ctx, a, tiles, count);
+        else if (r4_all && t == 8) rc = launch_r4<8>(ctx, a, tiles, count);
         else ntt_pass_kernel<<<dim3((unsigned)tiles, (unsigned)count), threads, smem, ctx->stream>>>(a);
         if (rc) return rc;
         ctx->launches += 1;
