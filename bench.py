@@ -97,6 +97,34 @@ def dot_mod_r(s_ints, k_ints):
     return acc % R_MOD
 
 
+def _limbs13(a):
+    """(n, 4) uint64 -> (20, n) float64 of 13-bit limbs (exact)."""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    cols = [np.ascontiguousarray(a[:, w]) for w in range(4)]
+    out = np.empty((20, a.shape[0]), dtype=np.float64)
+    for j in range(20):
+        w, off = divmod(13 * j, 64)
+        v = cols[w] >> np.uint64(off)
+        if off > 51 and w + 1 < 4:
+            v |= cols[w + 1] << np.uint64(64 - off)
+        v &= np.uint64(0x1FFF)
+        out[j] = v
+    return out
+
+
+def dot_mod_r_fast(s_limbs, k_limbs, chunk=1 << 20):
+    """The same dot product for millions of terms: both vectors in 13-bit limbs, one float64 GEMM per chunk of 2^20 terms
+    (every entry of the 20 x 20 limb-product matrix stays below 2^46, exact in a double), recombined with Python integers."""
+    n = s_limbs.shape[0]
+    acc = [[0] * 20 for _ in range(20)]
+    for lo in range(0, n, chunk):
+        m = _limbs13(s_limbs[lo:lo + chunk]) @ _limbs13(k_limbs[lo:lo + chunk]).T
+        for a in range(20):
+            for b in range(20):
+                acc[a][b] += int(m[a, b])
+    return sum(acc[a][b] << (13 * (a + b)) for a in range(20) for b in range(20)) % R_MOD
+
+
 def int_to_limbs(v):
     return np.array([[(v >> (64 * j)) & (2**64 - 1) for j in range(4)]], dtype=np.uint64)
 
@@ -297,7 +325,7 @@ def run_main(args):
     # so sum_i s_i P_i = (sum_i s_i k_i mod r) * G -- one host big-integer dot product per rank and set (summed over the
     # ranks through the library's own all-gather) and ONE fixed-base multiplication.  Checked at every N, for every step.
     k_ints = limbs_to_ints(k_host)
-    dots = [dot_mod_r(limbs_to_ints(h.numpy().view(np.uint64)), k_ints) for h in host_sets]
+    dots = [dot_mod_r_fast(h.numpy().view(np.uint64), k_host) for h in host_sets]
     if world > 1:
         alld = ctx.comm_allgather(np.concatenate([int_to_limbs(d) for d in dots]))          # (world, NSETS, 4)
         dots = [sum(limbs_to_ints(alld[:, j, :])) % R_MOD for j in range(NSETS)]
@@ -390,6 +418,17 @@ def run_main(args):
         checked["mismatches"] = int(t.item())
     bit_exact = checked["mismatches"] == 0 and checked["steps"] > 0
 
+    # ---- extra: fixed-size MSMs cut by point range over the N ranks (BASELINE.json configs[4]: strong scaling; the driver's
+    # efficiency for a size is ms(N = 1) / (N * ms(N))).  Every rank holds total / N points (its 2^20 bench points, tiled when it
+    # needs more: timing does not depend on the point values) and total / N fresh uniform scalars; results are checked against
+    # the same closed form as the headline.  All ranks take part.
+    sweep = {}
+    if not args.no_sweep:
+        try:
+            sweep = run_fixed_size_sweep(z, torch, dist, local_rank, rank, world, P, k_host, G, flush, args.sweep_logs)
+        except Exception as e:                                    # never lose the headline line over an extra
+            sweep = {"error": repr(e)}
+
     # ---- extra: the same MSM on witness-like (skewed) scalars, device-timed like `value`
     skewed = None
     if world == 1:
@@ -425,7 +464,7 @@ def run_main(args):
         sizes = [args.prove_log_n] if args.prove_log_n else ([18, 20] if world == 1 else [20])
         for ln in sizes:
             try:
-                prove_extra[f"prove_2^{ln}"] = run_prove_extra(local_rank, ln, dist, rank, world)
+                prove_extra.update(run_prove_extra(local_rank, ln, dist, rank, world))
             except Exception as e:
                 prove_extra[f"prove_2^{ln}_error"] = repr(e)
 
@@ -475,6 +514,7 @@ def run_main(args):
 
     # ---- extra: the NTT half of the metric (Fr NTT elems/s), one GPU, 2^22 (= 4n for a 2^20-gate circuit)
     extra = dict(prove_extra)
+    extra["msm_fixed_size_sweep"] = sweep
     extra.update({"msm_fixed_base_tables": {"enabled": not args.no_precompute, "build_seconds_once_per_srs": t_pre,
                                        "table_bytes": 0 if args.no_precompute else n * 64 * tm["windows"]},
              "msm_plain_bases_ms_per_step": plain_ms, "msm_witness_like_scalars": skewed})
@@ -603,18 +643,90 @@ def run_main(args):
         raise SystemExit("bench.py: MSM result differs from the closed-form answer (see \"check\" in the JSON line)")
 
 
+def run_fixed_size_sweep(z, torch, dist, device, rank, world, P, k_host, G, flush, total_logs):
+    dev = torch.device(f"cuda:{device}")
+    n = P.shape[0]
+    out = {}
+    ctx = z.Context(device)
+    ctx.set_stream(torch.cuda.current_stream())
+    if world > 1:
+        ctx.comm_init()
+    for tl in total_logs:
+        m = (1 << tl) // world
+        if m * world != 1 << tl or m < 1:
+            continue
+        tiles = (m + n - 1) // n
+        Pm = P if m == n else (P[:m].contiguous() if m < n else P.repeat(tiles, 1)[:m].contiguous())
+        ctx.srs_load(Pm)
+        ctx.srs_precompute(0)
+        del Pm
+        s_host = uniform_scalars(m, 9000 + tl + 1000 * rank)
+        k_big = k_host[:m] if m <= n else np.tile(k_host, (tiles, 1))[:m]
+        d = int_to_limbs(dot_mod_r_fast(s_host, k_big))
+        del k_big
+        if world > 1:
+            d = int_to_limbs(sum(limbs_to_ints(ctx.comm_allgather(d).reshape(world, 4))) % R_MOD)
+        exp = torch.empty((1, 8), dtype=torch.int64, device=dev)
+        ctx.g1_fixed_base_mul_dev(G, torch.from_numpy(d.view(np.int64)).to(dev), 1, exp)
+        s_dev = torch.from_numpy(s_host.view(np.int64)).to(dev)
+        torch.cuda.synchronize()
+        want = exp.cpu().numpy().view(np.uint64).reshape(8)
+        ok, ts = True, []
+        for it in range(5):
+            flush.zero_()
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            got, inf = ctx.msm_sharded(s_dev, 0, m)
+            e1.record()
+            torch.cuda.synchronize()
+            ok = ok and (not inf) and np.array_equal(got, want)
+            if it >= 2:
+                ts.append(e0.elapsed_time(e1))
+        ms = sum(ts) / len(ts)
+        if dist:
+            t = torch.tensor([ms, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, ok = float(t[0].item()), t[1].item() == 0.0
+        out[f"2^{tl}"] = {"total_points": 1 << tl, "points_per_gpu": m, "ms": ms, "points_per_s": (1 << tl) / (ms * 1e-3), "bit_exact": bool(ok),
+                          "window_bits": ctx.msm_last_timing()["c"]}
+        del s_dev
+    ctx.close()
+    out["note"] = ("one MSM of the stated total size, cut by point range over the ranks (zkb_msm_g1_sharded_dev), scalars resident, "
+                   "mean of 3 device-timed runs after 2 warm-ups, max over ranks, L2 flushed; checked against the closed form")
+    return out
+
+
 def run_prove_extra(device, log_n, dist, rank, world):
     """Full prove through zkb_plonk_setup / zkb_plonk_prove on a synthetic circuit of 2^log_n gates.  world > 1: SPMD --
-    every rank runs the rounds on the same witness, each commitment MSM is sharded by point range (this rank holds
-    SRS[lo, hi) and its fixed-base tables) and the 128-byte partial sums are all-gathered over NCCL."""
+    every rank runs the rounds on the same witness.  Two layouts of the committer key are measured:
+    "replicated" -- every rank holds the whole key and the library splits each round's batch of commitments among the ranks
+    (one group of ranks per commitment where its cost model says so, else every commitment cut over all ranks);
+    "point_range" -- every rank holds one contiguous range of the key and computes that range of EVERY commitment.
+    The first is reported as prove_2^k, the second as prove_2^k_point_range."""
+    from zkt_plonk_b200 import synthetic
+    circ = synthetic.make_circuit(log_n, seed=1)
+    out = {f"prove_2^{log_n}": _prove_once(device, log_n, circ, dist, rank, world, "replicated" if world > 1 else "single")}
+    if world > 1:
+        try:
+            out[f"prove_2^{log_n}_point_range"] = _prove_once(device, log_n, circ, dist, rank, world, "point_range")
+            a, b = out[f"prove_2^{log_n}"], out[f"prove_2^{log_n}_point_range"]
+            out[f"prove_2^{log_n}"]["same_bytes_as_point_range_layout"] = a["proof_sha256"] == b["proof_sha256"]
+        except Exception as e:
+            out[f"prove_2^{log_n}_point_range_error"] = repr(e)
+    return out
+
+
+def _prove_once(device, log_n, circ, dist, rank, world, layout):
     import torch
     import zkt_plonk_b200 as z
-    from zkt_plonk_b200 import prover, synthetic
-    from zkt_plonk_b200.parallel import attach_sharded_srs
+    from zkt_plonk_b200 import prover
+    from zkt_plonk_b200.parallel import attach_replicated_srs, attach_sharded_srs
     P = prover.P
     tau = 0x2B7E151628AED2A6ABF7158809CF4F3C762E7160F38B4DA56A784D9045190CFE % P
     n = 1 << log_n
-    circ = synthetic.make_circuit(log_n, seed=1)
     ctx = z.Context(device)
     ctx.set_stream(torch.cuda.current_stream())
     one_two = np.zeros((2, 4), dtype=np.uint64)
@@ -634,8 +746,10 @@ def run_prove_extra(device, log_n, dist, rank, world):
         ctx.g1_fixed_base_mul_dev(G, torch.from_numpy(k.view(np.int64)).to(out.device), hi - lo, out)
         return out
 
-    if world > 1:
+    if world > 1 and layout == "point_range":
         attach_sharded_srs(ctx, srs_range, n + 8)
+    elif world > 1:
+        attach_replicated_srs(ctx, srs_range, n + 8)
     else:
         ctx.srs_load(srs_range(0, n + 8))
         ctx.srs_precompute(0)
@@ -679,7 +793,7 @@ def run_prove_extra(device, log_n, dist, rank, world):
     native.close()
     ctx.close()
     return {"workload": f"plonk_plookup_prove_n=2^{log_n}" + (" (withdraw-circuit size)" if log_n == 18 else "") +
-                        f", {world} GPU, fixed-base SRS tables" + (", commitments sharded by point range (SPMD)" if world > 1 else ""),
+                        f", {world} GPU, fixed-base SRS tables" + (f", SPMD, committer key layout: {layout}" if world > 1 else ""),
             "api": "zkb_plonk_prove (C ABI): host wires/table/blinders in, 802 proof bytes out",
             "prove_ms": wall, "prove_ms_with_round_syncs": best["total_ms"], "device_rounds_ms": best["device_rounds_ms"],
             "host_lookup_plumbing_ms": best["host_lookup_plumbing_ms"], "h2d_wires_ms": best["h2d_wires_ms"],
@@ -720,6 +834,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precompute", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--sweep-logs", dest="sweep_logs", type=int, nargs="*", default=[20, 22, 24],
+                    help="total sizes (log2) of the fixed-size MSM sweep in extra.msm_fixed_size_sweep")
     ap.add_argument("--prove-log-n", dest="prove_log_n", type=int, default=0,
                     help="size of the full-prove extra (default: 2^18 and 2^20 on one GPU, 2^20 sharded on several)")
     args = ap.parse_args()

@@ -132,6 +132,9 @@ ZKB_API int zkb_commit_batch_dev(zkb_ctx *ctx, const uint64_t *const *coeffs_mon
  * commitment to wire a).  The coefficient buffers must stay untouched until zkb_commit_finish returns. */
 ZKB_API int zkb_commit_push(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset, size_t len);
 ZKB_API int zkb_commit_finish(zkb_ctx *ctx, uint64_t *out_xy, int *is_inf);
+/* Close the open batch WITHOUT the exchange between ranks: this rank's XYZZ partial sum of every pushed commitment (16
+ * limbs each, the identity where the rank had no share).  zkb_g1_sum_partials over the ranks gives the commitment. */
+ZKB_API int zkb_commit_finish_partials(zkb_ctx *ctx, uint64_t *out_xyzz);
 /* out_points_dev[i] = scalars_dev[i] * base: builds [tau^i]G-style SRS / synthetic points directly in HBM
  * (what PC::setup's FixedBaseMSM does once per SRS, plonk.rs:195). */
 ZKB_API int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], const uint64_t *scalars_dev, size_t n,
@@ -296,6 +299,15 @@ ZKB_API int zkb_comm_allgather_host(zkb_ctx *ctx, const void *send_host, size_t 
  * powers.  zkb_commit_dev / zkb_commit_batch_dev / zkb_plonk_setup / zkb_plonk_prove then take GLOBAL offsets and
  * lengths; zkb_msm_g1* keep addressing the resident range.  zkb_srs_size reports global_n. */
 ZKB_API int zkb_srs_set_range(zkb_ctx *ctx, size_t global_lo, size_t global_n);
+/* The other layout: every rank of the communicator holds the WHOLE committer key (load it on every rank, then call this
+ * before zkb_srs_precompute).  Commitments still take global offsets and lengths; per batch the library either cuts every
+ * commitment over all ranks or gives each commitment of the batch its own group of ranks (the 3 / 3 /
+ * 2 / 3 independent commitments of prove.rs:134,179,250,307), by a cost model fitted to measurements (fanout = -1), or as
+ * forced (0 = shard, 1 = fan out).  Results are identical for every layout. */
+ZKB_API int zkb_srs_set_replicated(zkb_ctx *ctx, int fanout);
+/* How many commitments the next zkb_commit_push batch will hold (zkb_commit_batch_dev knows; an incremental batch does
+ * not): needed to fan a batch out over a replicated key.  Without it every pushed commitment is cut over all ranks. */
+ZKB_API int zkb_commit_expect(zkb_ctx *ctx, size_t count);
 
 /* ---- test hooks (parity of the device field library against the oracle) ----------------------------------------- */
 /* field: 0 = Fr, 1 = Fq;  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a), 5 to_mont(a), 6 from_mont(a).  Host pointers. */
@@ -307,6 +319,13 @@ ZKB_API int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, co
  * zeroed buffers and {0, n, 0, n}).  Returns ZKB_ERR_INVALID for ElementNotIndexedInTable. */
 ZKB_API int zkb_test_combine_split(const uint64_t *table, size_t table_len, size_t n, const uint64_t *f, const uint32_t *rows,
                            size_t n_rows, uint64_t *h1, uint64_t *h2, size_t dirty[4], size_t out_lens[2]);
+
+/* Test hook: set rank / world of a context without creating a communicator (single-GPU tests of the multi-GPU layouts:
+ * zkb_commit_push + zkb_commit_finish_partials only). */
+ZKB_API int zkb_test_set_rank_world(zkb_ctx *ctx, int rank, int world);
+/* Host only (no GPU): [lo, hi) of commitment k (of a batch of E, `len` coefficients at SRS offset `offset`) that `rank` of
+ * `world` computes over a replicated key (zkb_srs_set_replicated); fanout as there.  lo == hi: nothing. */
+ZKB_API int zkb_test_replicated_share(int world, int rank, int fanout, size_t E, size_t k, size_t offset, size_t len, size_t out_lo_hi[2]);
 
 /* Host only (no GPU): run a scripted transcript and return its challenges (32 B canonical little-endian each).
  * ops[i]: 0 append_u64(args[9i]), 1 append_scalar(args[9i..9i+4), Montgomery Fr), 2 append_commitment(x = args[9i..],

@@ -52,6 +52,10 @@ def test_closed_form_check_agrees_with_the_oracle_msm():
     got, inf = cref.msm_g1(P, s)
     d = bench.dot_mod_r(bench.limbs_to_ints(s), bench.limbs_to_ints(k))
     assert d == sum(a * b for a, b in zip(bench.limbs_to_ints(s), bench.limbs_to_ints(k))) % R
+    assert bench.dot_mod_r_fast(s, k) == d and bench.dot_mod_r_fast(s, k, chunk=64) == d          # GEMM on 13-bit limbs
+    big_s, big_k = bench.uniform_scalars(50000, 9), bench.uniform_scalars(50000, 10)
+    big_s[:3] = np.uint64(0xFFFFFFFFFFFFFFFF)                                                      # all-ones limbs (not canonical: fine here)
+    assert bench.dot_mod_r_fast(big_s, big_k) == bench.dot_mod_r(bench.limbs_to_ints(big_s), bench.limbs_to_ints(big_k))
     exp = cref.g1_mul(G, bench.int_to_limbs(d))
     assert not inf and np.array_equal(exp.reshape(8), got)
     assert bench.bench_config(20, 2) == {"workload": "kzg_commit_g1_msm_2^20", "points_per_gpu": 1 << 20, "total_points": 2 << 20,

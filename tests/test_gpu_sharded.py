@@ -55,6 +55,45 @@ def test_range_commitments_add_up(ctx, n, world, tables):
         assert inf == einf and np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("world,fanout", [(2, 1), (3, 1), (8, 1), (8, 0), (5, -1)])
+def test_replicated_key_shares_add_up(ctx, world, fanout):
+    """zkb_srs_set_replicated: every "rank" holds the whole key and computes its share of each commitment of a batch --
+    one group of ranks per commitment (fan-out) or every commitment cut over all ranks.  Run on one GPU with contexts that
+    are told their rank (test hook), closing each batch without the exchange: the ranks' partial sums must add up to the
+    commitments of the plain single-context batch, for batches of 3, 2 and 1 commitments with unequal lengths."""
+    import torch
+    import zkt_plonk_b200 as z
+    n = 3001
+    d_pts, h_pts = gpu_points(ctx, n, 14)
+    polys = [rand_fr_mont(n, 31), rand_fr_mont(n - 37, 32), rand_fr_mont(n - 2, 33)]
+    polys[1][:50] = 0
+    devs = [to_dev(p) for p in polys]
+    lens = [p.shape[0] for p in polys]
+    ctx.srs_load(d_pts)
+    want = ctx.commit_batch_dev(devs, lens)
+    parts = {}
+    for r in range(world):
+        c = z.Context(0)
+        c.set_stream(torch.cuda.current_stream())
+        c.srs_load(d_pts)
+        c._check(c._lib.zkb_test_set_rank_world(c._h, r, world))
+        c.srs_set_replicated(fanout)
+        c.srs_precompute(0)
+        for batch in ((0, 1, 2), (0, 1), (2,)):
+            c.commit_expect(len(batch))
+            for k in batch:
+                c.commit_push(devs[k], lens[k], 0)
+            parts[(r, batch)] = c.commit_finish_partials(len(batch))
+        c.close()
+    for batch in ((0, 1, 2), (0, 1), (2,)):
+        busy = [sum(bool(parts[(r, batch)][j].any()) for j in range(len(batch))) for r in range(world)]
+        if fanout == 1 and world >= len(batch) > 1:
+            assert max(busy) == 1                                   # fan-out: every rank works on ONE commitment of the batch
+        for j, k in enumerate(batch):
+            got, inf = sum_partials(np.stack([parts[(r, batch)][j] for r in range(world)]))
+            assert inf == want[k][1] and np.array_equal(got, want[k][0]), (batch, k)
+
+
 def test_range_must_fit_the_key(ctx):
     from zkt_plonk_b200._lib import ZkbError
     d_pts, _ = gpu_points(ctx, 64, 12)

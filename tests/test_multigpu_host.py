@@ -61,6 +61,39 @@ def test_shard_bounds():
     assert b[0] == 0 and b[-1] == (1 << 20) + 3 and all(0 <= y - x - (1 << 17) <= 1 for x, y in zip(b, b[1:]))
 
 
+def test_replicated_key_shares_partition_every_commitment():
+    """zkb_srs_set_replicated (csrc/msm.cu replicated_share, host arithmetic): for every world size, batch size and layout the
+    shares of the ranks tile [offset, offset + len) exactly once per commitment; with fan-out every rank serves exactly one
+    commitment of the batch and the groups differ in size by at most one rank."""
+    import ctypes
+    from zkt_plonk_b200 import _lib
+    fn = _lib.lib().zkb_test_replicated_share
+    out = (ctypes.c_size_t * 2)()
+    for world in (1, 2, 3, 4, 8):
+        for E in (1, 2, 3, 10):
+            for fanout in (0, 1, -1):
+                for offset, length in ((0, (1 << 20) + 3), (5, 1000), (0, 3), (7, 0)):
+                    served = [0] * world
+                    for k in range(E):
+                        pieces = []
+                        for r in range(world):
+                            assert fn(world, r, fanout, E, k, offset, length, out) == 0
+                            if out[1] > out[0]:
+                                pieces.append((out[0], out[1]))
+                                served[r] += 1
+                        pieces.sort()
+                        pos = offset
+                        for lo, hi in pieces:
+                            assert lo == pos
+                            pos = hi
+                        assert pos == offset + length
+                        if fanout == 1 and 2 <= E <= world and length >= world:
+                            assert world // E <= len(pieces) <= world // E + 1
+                    if fanout == 1 and 2 <= E <= world and length >= world:
+                        assert max(served) == 1
+    assert fn(2, 2, 0, 1, 0, 0, 10, out) != 0                        # rank out of range
+
+
 def test_sharded_msm_world2_gloo():
     ctxmp = mp.get_context("spawn")
     q = ctxmp.Queue()

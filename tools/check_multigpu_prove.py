@@ -45,25 +45,42 @@ def srs_range(c, lo, hi):
     return out
 
 
-lo, hi = attach_sharded_srs(ctx, lambda a, b: srs_range(ctx, a, b), n + 8)
-assert ctx.srs_size() == n + 8
-native = prover.NativeProver(ctx, circ)
+from zkt_plonk_b200.parallel import attach_replicated_srs
 blinders = list(range(500, 519))
-raw = native.prove_bytes(blinders)
-times = []
-for _ in range(args.reps):
-    dist.barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    raw2 = native.prove_bytes(blinders)
-    times.append((time.perf_counter() - t0) * 1e3)
-    assert raw2 == raw
-digest = np.frombuffer(hashlib.sha256(raw).digest(), dtype=np.uint8)
-alld = ctx.comm_allgather(digest)
-assert all(np.array_equal(alld[r], digest) for r in range(world)), "ranks disagree on the proof bytes"
-_, rounds = native.prove_bytes(blinders, timings=True)
-tmax = torch.tensor([min(times)], device="cuda"); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+layouts = {}
+raw = None
+for layout in ("point_range", "replicated_fanout", "replicated_shard", "replicated_auto"):
+    c = ctx if layout == "point_range" else z.Context(local)
+    c.set_stream(torch.cuda.current_stream())
+    if layout == "point_range":
+        lo, hi = attach_sharded_srs(c, lambda a, b: srs_range(c, a, b), n + 8)
+    else:
+        attach_replicated_srs(c, lambda a, b: srs_range(c, a, b), n + 8, fanout={"replicated_fanout": 1, "replicated_shard": 0, "replicated_auto": -1}[layout])
+        lo, hi = 0, n + 8
+    assert c.srs_size() == n + 8
+    nat = prover.NativeProver(c, circ)
+    r0 = nat.prove_bytes(blinders)
+    times = []
+    for _ in range(args.reps):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r1 = nat.prove_bytes(blinders)
+        times.append((time.perf_counter() - t0) * 1e3)
+        assert r1 == r0
+    digest = np.frombuffer(hashlib.sha256(r0).digest(), dtype=np.uint8)
+    alld = c.comm_allgather(digest)
+    assert all(np.array_equal(alld[r], digest) for r in range(world)), f"{layout}: ranks disagree on the proof bytes"
+    assert raw is None or raw == r0, f"{layout}: proof differs from the point-range layout's"
+    raw = r0
+    tmax = torch.tensor([min(times)], device="cuda"); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    layouts[layout] = float(tmax.item())
+    if layout == "point_range":
+        native, rounds_src = nat, nat
+        _, rounds = nat.prove_bytes(blinders, timings=True)
+    else:
+        nat.close(); c.close()
 if rank == 0:
-    res = {"world": world, "log_n": args.log_n, "range": [lo, hi], "prove_ms_sharded": float(tmax.item()), "ranks_agree": True,
+    res = {"world": world, "log_n": args.log_n, "range": [lo, hi], "prove_ms_by_layout": layouts, "ranks_agree": True, "layouts_byte_identical": True,
            "rounds_ms_rank0_with_syncs": {k: round(v, 3) for k, v in rounds.items()}}
     ref_ctx = z.Context(local); ref_ctx.set_stream(torch.cuda.current_stream())
     ref_ctx.srs_load(srs_range(ref_ctx, 0, n + 8)); ref_ctx.srs_precompute(0)

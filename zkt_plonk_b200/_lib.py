@@ -113,6 +113,11 @@ def load():
         "zkb_comm_world": (i, [vp]),
         "zkb_comm_allgather_host": (i, [vp, vp, sz, vp]),
         "zkb_srs_set_range": (i, [vp, sz, sz]),
+        "zkb_srs_set_replicated": (i, [vp, i]),
+        "zkb_commit_expect": (i, [vp, sz]),
+        "zkb_commit_finish_partials": (i, [vp, vp]),
+        "zkb_test_set_rank_world": (i, [vp, i, i]),
+        "zkb_test_replicated_share": (i, [i, i, i, sz, sz, sz, sz, ctypes.POINTER(sz)]),
     }
     for name, (res, args) in sig.items():
         if not hasattr(lib, name):

@@ -205,6 +205,15 @@ class Context:
         """The resident SRS is [global_lo, global_lo + resident) of a key of global_n powers (commitments shard)."""
         self._check(self._lib.zkb_srs_set_range(self._h, int(global_lo), int(global_n)))
 
+    def srs_set_replicated(self, fanout=-1):
+        """Every rank holds the whole committer key; the library splits each batch of commitments among the ranks (fanout:
+        -1 cost model, 0 always shard every commitment over all ranks, 1 always one group of ranks per commitment)."""
+        self._check(self._lib.zkb_srs_set_replicated(self._h, int(fanout)))
+
+    def commit_expect(self, count):
+        """Size of the next commit_push batch (lets a replicated key fan the batch out over the ranks)."""
+        self._check(self._lib.zkb_commit_expect(self._h, int(count)))
+
     def commit_push(self, coeffs_dev, length, offset=0):
         """Enqueue the MSM of one more HBM-resident polynomial of the open batch (returns at once)."""
         self._check(self._lib.zkb_commit_push(self._h, _dev_ptr(coeffs_dev), offset, length))
@@ -215,6 +224,12 @@ class Context:
         inf = (ctypes.c_int * max(count, 1))()
         self._check(self._lib.zkb_commit_finish(self._h, _host_ptr(out), inf))
         return [(out[j].copy(), bool(inf[j])) for j in range(count)]
+
+    def commit_finish_partials(self, count):
+        """Close the open batch without the exchange between ranks: (count, 16) XYZZ partial sums of this rank."""
+        out = np.zeros((max(count, 1), 16), dtype=np.uint64)
+        self._check(self._lib.zkb_commit_finish_partials(self._h, _host_ptr(out)))
+        return out[:count]
 
     def set_msm_window(self, c):
         self._check(self._lib.zkb_msm_set_window(self._h, int(c)))

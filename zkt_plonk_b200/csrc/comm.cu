@@ -208,6 +208,20 @@ int zkb_srs_set_range(zkb_ctx *ctx, size_t global_lo, size_t global_n) {
     if (global_lo + ctx->srs_n > global_n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_set_range: the resident range exceeds the key");
     ctx->srs_lo = global_lo;
     ctx->srs_global_n = global_n;
+    ctx->srs_replicated = false;
+    return ZKB_OK;
+}
+
+// The other multi-GPU layout: EVERY rank holds the whole committer key (2^20 + 8 points are 64 MiB, with window tables
+// under 1 GiB of 180), and the library decides per batch of commitments who computes what: one group of ranks per
+// commitment ("fan-out": prove.rs:134,179,250,307 commit to 3 / 3 / 2 / 3 independent polynomials) or every commitment cut
+// over all ranks -- see fanout_wins in msm.cu.  fanout: -1 = cost model, 0 = always shard, 1 = always fan out.
+int zkb_srs_set_replicated(zkb_ctx *ctx, int fanout) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (fanout < -1 || fanout > 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_set_replicated: fanout is -1 (cost model), 0 or 1");
+    if (ctx->srs_lo != 0 || ctx->srs_global_n != ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_set_replicated: this context holds a range of the key (zkb_srs_set_range)");
+    ctx->srs_replicated = true;
+    ctx->fanout = fanout;
     return ZKB_OK;
 }
 

@@ -45,6 +45,9 @@ struct zkb_ctx {
     int rank = 0, world = 1;
     size_t srs_lo = 0;           // global index of the first resident SRS point
     size_t srs_global_n = 0;     // size of the whole committer key (== srs_n unless this context holds one range of it)
+    bool srs_replicated = false; // every rank holds the WHOLE key: the library splits each batch of commitments among the ranks
+    int fanout = -1;             // replicated key, batches of several commitments: 1 = one group of ranks per commitment,
+                                 // 0 = every commitment sharded over all ranks, -1 = cost model (msm.cu fanout_wins)
     DevBuf comm_buf;             // device staging of the all-gather
     void *comm_pinned = nullptr; // pinned host staging of the all-gather
     size_t comm_pinned_bytes = 0;

@@ -101,6 +101,7 @@ struct MsmState {
     // open batch of pipelined commitments (zkb_commit_push / zkb_commit_finish)
     std::vector<std::array<uint64_t, 16>> pipe_partial;   // folded XYZZ partial sum of every pushed commitment
     std::vector<char> pipe_pending;      // 1: enqueued, result still in its slot's pinned buffer
+    size_t pipe_expected = 1;            // commitments the open batch will hold (zkb_commit_expect): decides the multi-GPU layout
     MsmPlan pipe_plan[2];
 };
 
@@ -905,6 +906,7 @@ void zkb_commit_abort(zkb_ctx *ctx) {
         if (st->pipe_pending[k]) cudaEventSynchronize(st->slot[k & 1].tail_done);
     st->pipe_partial.clear();
     st->pipe_pending.clear();
+    st->pipe_expected = 1;
 }
 
 extern "C" {
@@ -921,6 +923,7 @@ int zkb_srs_load_g1(zkb_ctx *ctx, const uint64_t *xy_mont_host, size_t n) {
     ctx->srs_n = n;
     ctx->srs_lo = 0;
     ctx->srs_global_n = n;
+    ctx->srs_replicated = false;
     zkb_srs_precompute(ctx, -1);
     return ZKB_OK;
 }
@@ -935,6 +938,7 @@ int zkb_srs_load_g1_dev(zkb_ctx *ctx, const uint64_t *xy_mont_dev, size_t n) {
     ctx->srs_n = n;
     ctx->srs_lo = 0;
     ctx->srs_global_n = n;
+    ctx->srs_replicated = false;
     zkb_srs_precompute(ctx, -1);
     return ZKB_OK;
 }
@@ -958,7 +962,10 @@ int zkb_srs_precompute(zkb_ctx *ctx, int c) {
     const size_t n = ctx->srs_n;
     if (n == 0) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_srs_precompute: no SRS loaded");
     FixedBase *fb = new FixedBase();
-    fb->c = c > 0 ? (uint32_t)c : pick_window(n, true, ctx->sm_count);
+    // replicated key on several GPUs: an MSM covers a share of the key (1/world of it when every commitment is sharded, about
+    // 3/world in a fanned-out round of three), so the window is chosen for that size, not for the whole key
+    const size_t n_typical = (ctx->srs_replicated && ctx->world > 1) ? std::max<size_t>(n * 2 / (size_t)ctx->world, 1024) : n;
+    fb->c = c > 0 ? (uint32_t)c : pick_window(n_typical, true, ctx->sm_count);
     fb->W = balanced_windows(fb->c, &fb->wide);
     if (fb->wide == 0 && fb->c > 3) { fb->c -= 1; fb->wide = fb->W; }   // every window narrow: that is just c - 1 (half the buckets)
     fb->n = n;
@@ -1183,6 +1190,60 @@ static int commit_collect(zkb_ctx *ctx, MsmState *st, size_t k) {          // fo
     return ZKB_OK;
 }
 
+// ---- replicated committer key (zkb_srs_set_replicated): which part of commitment k of a batch of E this rank computes.
+// "Shard": every commitment is cut into `world` point ranges -- every rank runs E small MSMs and pays E times the fixed cost
+// of one (sort, bucket reduction over 2^(c-1) buckets, latency-bound tail: ~0.45 ms whatever the size).  "Fan-out": the
+// ranks are split into E groups, group j computes commitment j alone (sharded by point range inside the group) -- every
+// rank runs ONE larger MSM.  Fan-out wins while the saved fixed costs outweigh the coarser balance (groups of unequal
+// size): E (F + P len / world)  vs  F + P len / (smallest group), F and P from measurements on B200 (profiles/r02*).
+static bool fanout_wins(const zkb_ctx *ctx, size_t E, size_t len) {
+    const size_t world = (size_t)ctx->world;
+    if (E < 2 || world < E) return false;
+    if (ctx->fanout >= 0) return ctx->fanout != 0;
+    const double F = 0.45, P = 2.1e-6;                          // ms per MSM; ms per point (0.14 ns x ~15 windows)
+    const double shard = (double)E * (F + P * (double)len / (double)world);
+    const double fan = F + P * (double)len / (double)(world / E);
+    return fan < shard;
+}
+
+static void replicated_share(const zkb_ctx *ctx, size_t E, size_t k, size_t offset, size_t len, size_t *lo, size_t *hi) {
+    size_t parts = (size_t)ctx->world, idx = (size_t)ctx->rank;
+    if (k < E && fanout_wins(ctx, E, len)) {
+        const size_t base = parts / E, rem = parts % E;          // commitment j gets base + (j < rem) consecutive ranks
+        size_t start = 0, mine = E, gsize = 0;
+        for (size_t j = 0; j < E; ++j) {
+            const size_t sz = base + (j < rem ? 1 : 0);
+            if (idx >= start && idx < start + sz) { mine = j; gsize = sz; break; }
+            start += sz;
+        }
+        if (mine != k) { *lo = *hi = offset; return; }           // another group's commitment
+        parts = gsize;
+        idx -= start;
+    }
+    const size_t q = len / parts, r = len % parts;                // balanced contiguous ranges
+    *lo = offset + idx * q + std::min(idx, r);
+    *hi = *lo + q + (idx < r ? 1 : 0);
+}
+
+// host-only test hook: the share of commitment k (of a batch of E, length len at `offset`) that `rank` of `world` computes
+int zkb_test_replicated_share(int world, int rank, int fanout, size_t E, size_t k, size_t offset, size_t len, size_t out_lo_hi[2]) {
+    if (world < 1 || rank < 0 || rank >= world || !out_lo_hi) return ZKB_ERR_INVALID;
+    zkb_ctx fake;
+    fake.world = world;
+    fake.rank = rank;
+    fake.fanout = fanout;
+    replicated_share(&fake, E, k, offset, len, &out_lo_hi[0], &out_lo_hi[1]);
+    return ZKB_OK;
+}
+
+int zkb_commit_expect(zkb_ctx *ctx, size_t count) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    MsmState *st = state(ctx);
+    if (!st->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_expect: a zkb_commit_push batch is already open");
+    st->pipe_expected = count ? count : 1;
+    return ZKB_OK;
+}
+
 int zkb_commit_push(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset, size_t len) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!coeffs_mont_dev && len) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_push: null coefficients");
@@ -1192,7 +1253,8 @@ int zkb_commit_push(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset
     if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;
     const size_t k = st->pipe_partial.size();
     const int slot = (int)(k & 1);
-    const size_t g_lo = std::max(offset, ctx->srs_lo), g_hi = std::min(offset + len, ctx->srs_lo + ctx->srs_n);
+    size_t g_lo = std::max(offset, ctx->srs_lo), g_hi = std::min(offset + len, ctx->srs_lo + ctx->srs_n);
+    if (ctx->world > 1 && ctx->srs_replicated) replicated_share(ctx, st->pipe_expected, k, offset, len, &g_lo, &g_hi);
     const size_t n = g_hi > g_lo ? g_hi - g_lo : 0;
     int rc = ZKB_OK;
     if (k >= 2) {                                                          // slot reuse: MSM k-2 must be folded first
@@ -1222,6 +1284,31 @@ int zkb_commit_push(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset
     return ZKB_OK;
 }
 
+// the open batch's results as THIS rank's un-normalised XYZZ partial sums (16 limbs each), without any exchange: for callers
+// that combine the ranks themselves, and for the single-GPU tests of the multi-GPU layouts
+int zkb_commit_finish_partials(zkb_ctx *ctx, uint64_t *out_xyzz /* count x 16 */) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    MsmState *st = state(ctx);
+    const size_t count = st->pipe_partial.size();
+    if (!out_xyzz && count) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_finish_partials: null output");
+    int rc = ZKB_OK;
+    for (size_t k = 0; k < count && !rc; ++k) rc = commit_collect(ctx, st, k);
+    for (size_t k = 0; k < count && !rc; ++k) memcpy(out_xyzz + 16 * k, st->pipe_partial[k].data(), 128);
+    st->pipe_partial.clear();
+    st->pipe_pending.clear();
+    st->pipe_expected = 1;
+    return rc;
+}
+
+// test hook: make this context believe it is `rank` of `world` without a communicator (only zkb_commit_push /
+// zkb_commit_finish_partials are meaningful then)
+int zkb_test_set_rank_world(zkb_ctx *ctx, int rank, int world) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return ZKB_ERR_INVALID;
+    ctx->rank = rank;
+    ctx->world = world;
+    return ZKB_OK;
+}
+
 int zkb_commit_finish(zkb_ctx *ctx, uint64_t *out_xy /* count x 8 */, int *is_inf /* count or NULL */) {
     if (!ctx) return ZKB_ERR_INVALID;
     MsmState *st = state(ctx);
@@ -1232,6 +1319,7 @@ int zkb_commit_finish(zkb_ctx *ctx, uint64_t *out_xy /* count x 8 */, int *is_in
     std::vector<std::array<uint64_t, 16>> part;
     part.swap(st->pipe_partial);
     st->pipe_pending.clear();
+    st->pipe_expected = 1;
     if (rc) return rc;
     if (ctx->world > 1 && count) {
         std::vector<std::array<uint64_t, 16>> all((size_t)ctx->world * count);
@@ -1265,6 +1353,7 @@ int zkb_commit_batch_dev(zkb_ctx *ctx, const uint64_t *const *coeffs_mont_dev, c
     MsmState *st = state(ctx);
     if (!st->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_batch_dev: a zkb_commit_push batch is still open");
     int rc = ZKB_OK;
+    st->pipe_expected = count ? count : 1;
     for (size_t k = 0; k < count && !rc; ++k) rc = zkb_commit_push(ctx, coeffs_mont_dev[k], offsets ? offsets[k] : 0, lens[k]);
     if (rc) {                                                              // drain and drop the partial batch
         std::vector<uint64_t> scratch(8 * st->pipe_partial.size() + 8);

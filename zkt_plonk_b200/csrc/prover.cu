@@ -699,6 +699,7 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
         // memory bandwidth, so a rank uploads only its 1/world slice and the slices are all-gathered over NVLink.
         const bool split = ctx->world > 1 && ctx->comm && n % (size_t)ctx->world == 0;
         const size_t chunk = split ? n / (size_t)ctx->world : n, first = split ? (size_t)ctx->rank * chunk : 0;
+        TRY(zkb_commit_expect(ctx, 3));                                  // a, b, c: one batch (prove.rs:133-135), pushed as the wires arrive
         for (int k = 0; k < 3; ++k) {
             const uint64_t *src = wires[k].host + 4 * first;
             if (chunk * 32 >= ((size_t)16 << 20)) {                      // measured: pays off from ~16 MiB (2.6 vs 3.2 ms at 32 MiB)

@@ -44,6 +44,20 @@ def attach_sharded_srs(ctx, load_range, global_n, group=None, precompute=True):
     return b[rank], b[rank + 1]
 
 
+def attach_replicated_srs(ctx, load_range, global_n, group=None, fanout=-1, precompute=True):
+    """The other SPMD layout (csrc/comm.cu zkb_srs_set_replicated): every rank loads the WHOLE committer key
+    (`load_range(0, global_n)`); per batch of commitments the library either cuts every commitment over all ranks or gives
+    each commitment its own group of ranks (fan-out of the 3 / 3 / 2 / 3 independent commitments of a round).  fanout: -1
+    cost model, 0 always shard, 1 always fan out.  zkb_commit_batch_dev / zkb_plonk_setup / zkb_plonk_prove run unchanged
+    on every rank and return identical results."""
+    rank, world = ctx.comm_init(group)
+    ctx.srs_load(load_range(0, global_n))
+    ctx.srs_set_replicated(fanout)
+    if precompute:
+        ctx.srs_precompute(0)
+    return rank, world
+
+
 class ShardedMSM:
     """`partial_fn(scalars_shard) -> (16,) uint64 XYZZ` computes this rank's partial sum; by default it is the
     CUDA bucket method on the context's resident SRS range."""
