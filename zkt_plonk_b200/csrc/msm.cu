@@ -477,6 +477,56 @@ __global__ void __launch_bounds__(RED_THREADS, WIDE ? RED_CTAS_PER_SM : 1) msm_w
     g1x_store(out + ((size_t)(n_plain + 1) * G + g) * M_out + t, acc);
 }
 
+// ---- the binary (2-to-1) levels with FOUR lanes per addition (g1x_add_coop4): a level is one dependent addition per output,
+// so its latency is the addition's latency.  One body, two launch shapes: a grid over (outputs, streams, groups) while a
+// level still has thousands of additions, and ONE CTA that walks all remaining levels with a barrier between them once a
+// level fits it (the last ~8 levels of a 2^19-bucket reduction: no launch gaps).
+constexpr uint32_t TAIL_THREADS = 1024, TAIL_GROUPS = TAIL_THREADS / 4;
+
+__device__ __forceinline__ void wsum_binary_coop(const g1x_t *__restrict__ in, g1x_t *__restrict__ out, uint32_t M_in, uint32_t M_out,
+                                                 uint32_t n_plain, uint32_t G, uint32_t strm, uint32_t g, uint32_t t, uint32_t sub) {
+    const g1x_t *src = in + ((size_t)strm * G + g) * M_in + (size_t)2 * t;
+    g1x_t *dst = out + ((size_t)strm * G + g) * M_out + t;
+    g1x_t *dst_a = out + ((size_t)(n_plain + 1) * G + g) * M_out + t;     // the new plain stream A (from stream 0 only)
+    g1x_t x0 = g1x_load(src);
+    if (2 * t + 1 < M_in) {
+        const g1x_t x1 = g1x_load(src + 1);
+        if (strm == 0) g1x_store_coop4(dst_a, x1, sub);
+        x0 = g1x_add_coop4(x0, x1, sub);
+    } else if (strm == 0) {
+        g1x_store_coop4(dst_a, g1x_inf(), sub);
+    }
+    g1x_store_coop4(dst, x0, sub);
+}
+
+__global__ void __launch_bounds__(RED_THREADS) msm_wsum_binary_coop_kernel(const g1x_t *__restrict__ in, uint32_t M_in, uint32_t M_out,
+                                                                            uint32_t n_plain, g1x_t *__restrict__ out) {
+    const uint32_t t = (blockIdx.x * RED_THREADS + threadIdx.x) >> 2, sub = threadIdx.x & 3;
+    if (t >= M_out) return;                                        // whole groups of four leave together
+    wsum_binary_coop(in, out, M_in, M_out, n_plain, gridDim.z, blockIdx.y, blockIdx.z, t, sub);
+}
+
+struct TailArgs {
+    uint32_t l0, levels, G;                                        // levels [l0, levels) are done here
+    uint32_t m[RED_MAX_LEVELS + 1];                                // input length of every level
+};
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) msm_wsum_tail_kernel(const __grid_constant__ TailArgs a, const g1x_t *first_in,
+                                                                        g1x_t *buf0, g1x_t *buf1) {
+    const uint32_t grp = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    const g1x_t *in = first_in;
+    for (uint32_t l = a.l0; l < a.levels; ++l) {
+        g1x_t *out = (l & 1) ? buf1 : buf0;
+        const uint32_t M_in = a.m[l], M_out = a.m[l + 1], per = M_out * a.G, total = (l + 1) * per;
+        for (uint32_t w = grp; w < total; w += TAIL_GROUPS) {
+            const uint32_t strm = w / per, rem = w - strm * per, g = rem / M_out, t = rem - g * M_out;
+            wsum_binary_coop(in, out, M_in, M_out, l, a.G, strm, g, t, sub);
+        }
+        __syncthreads();                                           // this CTA wrote `out`; the next level reads it
+        in = out;
+    }
+}
+
 // Fixed-base table: rows[w][i] = 2^(c*w) * P_i (affine), w < W.  One thread per point walks the windows.
 __global__ void __launch_bounds__(128) msm_precompute_kernel(const g1a_t *__restrict__ points, uint32_t n, uint32_t c, uint32_t W,
                                                              uint32_t wide, g1a_t *__restrict__ rows) {
@@ -826,18 +876,35 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
         ZKB_CUDA(ctx, cudaStreamWaitEvent(ts, sl.acc_done, 0));
     }
     const g1x_t *level_in = ws.bucket_val;
+    uint32_t tail_fused_from = pl.red_levels;
     for (uint32_t l = 0; l < pl.red_levels; ++l) {
         const uint32_t m_in = pl.red_m[l], m_out = pl.red_m[l + 1];
         dim3 grid((m_out + RED_THREADS - 1) / RED_THREADS, l + 1, pl.G);
         g1x_t *level_out = ws.red_buf[l & 1];
-        if (pl.red_r[l] != 2) msm_wsum_level_kernel<true><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, pl.red_r[l], l, level_out);
-        else msm_wsum_level_kernel<false><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, 2, l, level_out);
+        if (pl.red_r[l] != 2) {
+            msm_wsum_level_kernel<true><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, pl.red_r[l], l, level_out);
+        } else if (!ctx->msm_coop_tail) {
+            msm_wsum_level_kernel<false><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, 2, l, level_out);
+        } else if ((uint64_t)(l + 1) * pl.G * m_out <= 2 * TAIL_GROUPS) {
+            // this level and every later one (all binary, each smaller than the one before) in ONE CTA
+            TailArgs ta;
+            ta.l0 = l; ta.levels = pl.red_levels; ta.G = pl.G;
+            for (uint32_t k = 0; k <= pl.red_levels; ++k) ta.m[k] = pl.red_m[k];
+            msm_wsum_tail_kernel<<<1, TAIL_THREADS, 0, ts>>>(ta, level_in, ws.red_buf[0], ws.red_buf[1]);
+            level_in = ws.red_buf[(pl.red_levels - 1) & 1];
+            tail_fused_from = l;
+            break;
+        } else {
+            dim3 cgrid((4 * m_out + RED_THREADS - 1) / RED_THREADS, l + 1, pl.G);
+            msm_wsum_binary_coop_kernel<<<cgrid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, l, level_out);
+        }
         level_in = level_out;
     }
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], ts));
     ZKB_CUDA(ctx, cudaGetLastError());
     st->ev_valid = true;
-    ctx->launches += 16 + pl.red_levels; // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduction levels
+    // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduction levels (the fused tail is one)
+    ctx->launches += 16 + tail_fused_from + (tail_fused_from < pl.red_levels ? 1 : 0);
     // the last level's output is [stream][group][1]: stream 0 = plain total, stream 1 + k = total of A_k
     ZKB_CUDA(ctx, cudaMemcpyAsync(sl.pinned, pl.red_levels ? (const void *)level_in : (const void *)ws.bucket_val, out_bytes,
                                   cudaMemcpyDeviceToHost, ts));
@@ -1274,7 +1341,9 @@ int zkb_commit_push(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset
         if (rc) return rc;
     }
     uint4 *scal = (uint4 *)((char *)ctx->stage.p + (size_t)slot * stride);
-    if (k >= 2) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->slot[slot].tail_done, 0));
+    // slot reuse: the scalars of the slot's previous MSM must have been consumed (the events exist once the slot has run an MSM:
+    // with a fanned-out batch a rank skips the commitments of the other groups)
+    if (k >= 2 && st->slot[slot].tail_done) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->slot[slot].tail_done, 0));
     fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)(coeffs_mont_dev + 4 * (g_lo - offset)), scal, (uint32_t)n);
     const size_t off = g_lo - ctx->srs_lo;
     rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, scal, n, 0, fb, off, &st->pipe_plan[slot], slot, true)
