@@ -9,14 +9,18 @@
 //!                        bytes of `Proof`'s `CanonicalSerialize` (drop-in for the body of `ZKTPlonk::prove`,
 //!                        plonk-core/src/plonk.rs:94-111);
 //!   * [`GpuDomain`]      the `D` parameter (plonk-core/src/plonk.rs:39-46, util.rs:27-140);
-//!   * [`GpuKZG10`]       helpers for the `PC` parameter: commit / multi_scalar_mul on the resident committer key
-//!                        (commitment.rs:10-46).
+//!   * [`GpuKZG10Pc`]     the `PC` parameter as a type: `impl PolynomialCommitment<Fr, DensePolynomial<Fr>>` +
+//!                        `impl HomomorphicCommitment<Fr>` over SonicKZG10's associated types (commitment.rs:9-46); setup /
+//!                        trim / check delegate, commit / open / multi_scalar_mul run on the GPU ([`GpuKZG10`] helpers).
+//!                        rust/patches/instance.rs.patch swaps it (and `GpuDomain`) into bin/src/instance.rs:67-84.
 mod ctx;
 mod domain;
 mod kzg;
+mod pc;
 mod prover;
 
 pub use ctx::{Ctx, Error};
 pub use domain::GpuDomain;
 pub use kzg::GpuKZG10;
+pub use pc::GpuKZG10Pc;
 pub use prover::{prove_native, verify_native, NativeKey, Transcript};
