@@ -90,7 +90,7 @@ struct MsmState {
     MsmSlot slot[2];                     // slot 0: single MSMs; slots 0/1 alternate in pipelined batches
     cudaStream_t tail_stream = nullptr;  // high-priority stream for the latency-bound tail of a pipelined MSM
     cudaStream_t copy_stream = nullptr;  // uploads of host scalars, overlapped with the MSM of the previous part
-    cudaEvent_t part_uploaded[2] = {nullptr, nullptr};
+    cudaEvent_t part_uploaded[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase boundaries of the last MSM
     cudaEvent_t ev_pairs[2] = {nullptr, nullptr};                        // around the pair rounds of the last MSM
     uint32_t last_rounds = 0;
@@ -377,49 +377,44 @@ __device__ __forceinline__ g1x_t shfl_down_g1x(const g1x_t &p, int d) {
 }
 
 // Oversized buckets (skewed scalars: ones / small values pile up on a few digits), two stages of one warp per work item.
-// Stage 1: a warp folds one chunk of <= HEAVY_CHUNK task results of a bucket (two per lane, then a shuffle tree: 7 additions
-// deep) into the bucket's value (single chunk) or into a chunk sum.  Stage 2: a warp folds the chunk sums of a multi-chunk
-// bucket (lanes stride over them).  A 200k-entry bucket cut into 64-entry tasks is 3300 tasks -> 52 chunks -> one value, each
+// Stage 1: a warp folds one chunk of <= HEAVY_CHUNK task results of a bucket into the bucket's value (single chunk) or into a
+// chunk sum.  Stage 2: a warp folds the chunk sums of a multi-chunk bucket.  A 200k-entry bucket cut into 64-entry tasks is 3300 tasks -> 52 chunks -> one value, each
 // stage ~30 us, instead of one CTA walking all task results.
-__device__ __forceinline__ void warp_fold_store(g1x_t acc, uint32_t lane, uint32_t live, g1x_t *dst) {
-    for (int d = 16; d >= 1; d >>= 1) {
-        if ((uint32_t)d >= live) continue;                         // uniform across the warp
-        g1x_t o = shfl_down_g1x(acc, d);
-        if (lane < (uint32_t)d) g1x_add(acc, o);
+// `len` points at base[0 .. len) folded by one warp working as 8 groups of 4 lanes (g1x_add_coop4: four lanes per addition,
+// ~1/3 of a lone thread's latency): group q adds base[q], base[q + 8], ... in turn, then the eight group sums are folded in a
+// three-level tree.  All 32 lanes of the warp must call it.
+__device__ __forceinline__ void warp_fold_store_coop(const g1x_t *base, uint32_t len, g1x_t *dst) {
+    const uint32_t lane = threadIdx.x & 31, q = lane >> 2, sub = lane & 3;
+    g1x_t acc = g1x_inf();
+    for (uint32_t k = q; k < len; k += 8) acc = g1x_add_coop4(acc, g1x_load(base + k), sub);
+    for (int d = 4; d >= 1; d >>= 1) {
+        const g1x_t o = shfl_down_g1x(acc, 4 * d);                  // every lane takes part in the exchange
+        if (q < (uint32_t)d && q + d < len) acc = g1x_add_coop4(acc, o, sub);
     }
-    __syncwarp();
-    if (lane == 0) g1x_store(dst, acc);
+    if (q == 0) g1x_store_coop4(dst, acc, sub);
 }
 
 __global__ void __launch_bounds__(128) msm_combine_chunks_kernel(const uint32_t *misc, const uint32_t *heavy_list, const uint32_t *heavy_slot,
                                                                  const uint2 *chunk_items, const uint32_t *ntasks, const uint32_t *task_base,
                                                                  const g1x_t *task_out, g1x_t *chunk_out, g1x_t *bucket_val) {
-    const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nitems = misc[2];
     for (uint32_t it = warp; it < nitems; it += nwarps) {
         const uint2 item = chunk_items[it];
         const uint32_t b = heavy_list[item.x], nt = ntasks[b], lo = item.y * HEAVY_CHUNK, len = min(HEAVY_CHUNK, nt - lo);
-        const g1x_t *base = task_out + task_base[b] + lo;
-        g1x_t acc = g1x_inf();
-        for (uint32_t k = lane; k < len; k += 32) g1x_add(acc, g1x_load(base + k));
         const uint32_t slot = heavy_slot[item.x];
-        warp_fold_store(acc, lane, min(len, 32u), slot == 0xffffffffu ? bucket_val + b : chunk_out + slot + item.y);
+        warp_fold_store_coop(task_out + task_base[b] + lo, len, slot == 0xffffffffu ? bucket_val + b : chunk_out + slot + item.y);
     }
 }
 
 __global__ void __launch_bounds__(128) msm_combine_final_kernel(const uint32_t *misc, const uint32_t *heavy_list, const uint32_t *heavy_slot,
                                                                 const uint32_t *multi_list, const uint32_t *ntasks, const g1x_t *chunk_out,
                                                                 g1x_t *bucket_val) {
-    const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nmulti = misc[4];
     for (uint32_t it = warp; it < nmulti; it += nwarps) {
         const uint32_t h = multi_list[it], b = heavy_list[h], chunks = (ntasks[b] + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
-        const g1x_t *base = chunk_out + heavy_slot[h];
-        g1x_t acc = g1x_inf();
-        for (uint32_t k = lane; k < chunks; k += 32) g1x_add(acc, g1x_load(base + k));
-        warp_fold_store(acc, lane, min(chunks, 32u), bucket_val + b);
+        warp_fold_store_coop(chunk_out + heavy_slot[h], chunks, bucket_val + b);
     }
 }
 
@@ -475,56 +470,6 @@ __global__ void __launch_bounds__(RED_THREADS, WIDE ? RED_CTAS_PER_SM : 1) msm_w
     g1x_add(run, cur);                                            // + X[0]: the plain sum
     g1x_store(dst, run);
     g1x_store(out + ((size_t)(n_plain + 1) * G + g) * M_out + t, acc);
-}
-
-// ---- the binary (2-to-1) levels with FOUR lanes per addition (g1x_add_coop4): a level is one dependent addition per output,
-// so its latency is the addition's latency.  One body, two launch shapes: a grid over (outputs, streams, groups) while a
-// level still has thousands of additions, and ONE CTA that walks all remaining levels with a barrier between them once a
-// level fits it (the last ~8 levels of a 2^19-bucket reduction: no launch gaps).
-constexpr uint32_t TAIL_THREADS = 1024, TAIL_GROUPS = TAIL_THREADS / 4;
-
-__device__ __forceinline__ void wsum_binary_coop(const g1x_t *__restrict__ in, g1x_t *__restrict__ out, uint32_t M_in, uint32_t M_out,
-                                                 uint32_t n_plain, uint32_t G, uint32_t strm, uint32_t g, uint32_t t, uint32_t sub) {
-    const g1x_t *src = in + ((size_t)strm * G + g) * M_in + (size_t)2 * t;
-    g1x_t *dst = out + ((size_t)strm * G + g) * M_out + t;
-    g1x_t *dst_a = out + ((size_t)(n_plain + 1) * G + g) * M_out + t;     // the new plain stream A (from stream 0 only)
-    g1x_t x0 = g1x_load(src);
-    if (2 * t + 1 < M_in) {
-        const g1x_t x1 = g1x_load(src + 1);
-        if (strm == 0) g1x_store_coop4(dst_a, x1, sub);
-        x0 = g1x_add_coop4(x0, x1, sub);
-    } else if (strm == 0) {
-        g1x_store_coop4(dst_a, g1x_inf(), sub);
-    }
-    g1x_store_coop4(dst, x0, sub);
-}
-
-__global__ void __launch_bounds__(RED_THREADS) msm_wsum_binary_coop_kernel(const g1x_t *__restrict__ in, uint32_t M_in, uint32_t M_out,
-                                                                            uint32_t n_plain, g1x_t *__restrict__ out) {
-    const uint32_t t = (blockIdx.x * RED_THREADS + threadIdx.x) >> 2, sub = threadIdx.x & 3;
-    if (t >= M_out) return;                                        // whole groups of four leave together
-    wsum_binary_coop(in, out, M_in, M_out, n_plain, gridDim.z, blockIdx.y, blockIdx.z, t, sub);
-}
-
-struct TailArgs {
-    uint32_t l0, levels, G;                                        // levels [l0, levels) are done here
-    uint32_t m[RED_MAX_LEVELS + 1];                                // input length of every level
-};
-
-__global__ void __launch_bounds__(TAIL_THREADS, 1) msm_wsum_tail_kernel(const __grid_constant__ TailArgs a, const g1x_t *first_in,
-                                                                        g1x_t *buf0, g1x_t *buf1) {
-    const uint32_t grp = threadIdx.x >> 2, sub = threadIdx.x & 3;
-    const g1x_t *in = first_in;
-    for (uint32_t l = a.l0; l < a.levels; ++l) {
-        g1x_t *out = (l & 1) ? buf1 : buf0;
-        const uint32_t M_in = a.m[l], M_out = a.m[l + 1], per = M_out * a.G, total = (l + 1) * per;
-        for (uint32_t w = grp; w < total; w += TAIL_GROUPS) {
-            const uint32_t strm = w / per, rem = w - strm * per, g = rem / M_out, t = rem - g * M_out;
-            wsum_binary_coop(in, out, M_in, M_out, l, a.G, strm, g, t, sub);
-        }
-        __syncthreads();                                           // this CTA wrote `out`; the next level reads it
-        in = out;
-    }
 }
 
 // Fixed-base table: rows[w][i] = 2^(c*w) * P_i (affine), w < W.  One thread per point walks the windows.
@@ -876,35 +821,21 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
         ZKB_CUDA(ctx, cudaStreamWaitEvent(ts, sl.acc_done, 0));
     }
     const g1x_t *level_in = ws.bucket_val;
-    uint32_t tail_fused_from = pl.red_levels;
     for (uint32_t l = 0; l < pl.red_levels; ++l) {
         const uint32_t m_in = pl.red_m[l], m_out = pl.red_m[l + 1];
         dim3 grid((m_out + RED_THREADS - 1) / RED_THREADS, l + 1, pl.G);
         g1x_t *level_out = ws.red_buf[l & 1];
-        if (pl.red_r[l] != 2) {
-            msm_wsum_level_kernel<true><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, pl.red_r[l], l, level_out);
-        } else if (!ctx->msm_coop_tail) {
-            msm_wsum_level_kernel<false><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, 2, l, level_out);
-        } else if ((uint64_t)(l + 1) * pl.G * m_out <= 2 * TAIL_GROUPS) {
-            // this level and every later one (all binary, each smaller than the one before) in ONE CTA
-            TailArgs ta;
-            ta.l0 = l; ta.levels = pl.red_levels; ta.G = pl.G;
-            for (uint32_t k = 0; k <= pl.red_levels; ++k) ta.m[k] = pl.red_m[k];
-            msm_wsum_tail_kernel<<<1, TAIL_THREADS, 0, ts>>>(ta, level_in, ws.red_buf[0], ws.red_buf[1]);
-            level_in = ws.red_buf[(pl.red_levels - 1) & 1];
-            tail_fused_from = l;
-            break;
-        } else {
-            dim3 cgrid((4 * m_out + RED_THREADS - 1) / RED_THREADS, l + 1, pl.G);
-            msm_wsum_binary_coop_kernel<<<cgrid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, l, level_out);
-        }
+        // (measured and dropped, profiles/r02f_msm_coop.jsonl: binary levels with four lanes per addition and the last levels
+        // fused into one CTA -- 0.50 instead of 0.43 ms at 2^19 buckets: a level costs its launch gap, not its addition, and
+        // the wide early levels are throughput-bound, where four lanes per addition do 2.5x the work)
+        if (pl.red_r[l] != 2) msm_wsum_level_kernel<true><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, pl.red_r[l], l, level_out);
+        else msm_wsum_level_kernel<false><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, 2, l, level_out);
         level_in = level_out;
     }
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], ts));
     ZKB_CUDA(ctx, cudaGetLastError());
     st->ev_valid = true;
-    // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduction levels (the fused tail is one)
-    ctx->launches += 16 + tail_fused_from + (tail_fused_from < pl.red_levels ? 1 : 0);
+    ctx->launches += 16 + pl.red_levels; // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduction levels
     // the last level's output is [stream][group][1]: stream 0 = plain total, stream 1 + k = total of A_k
     ZKB_CUDA(ctx, cudaMemcpyAsync(sl.pinned, pl.red_levels ? (const void *)level_in : (const void *)ws.bucket_val, out_bytes,
                                   cudaMemcpyDeviceToHost, ts));
@@ -1108,9 +1039,9 @@ int zkb_msm_g1_sharded_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t off
     return zkb_g1_sum_partials(all.data(), (size_t)ctx->world, out_xy, is_inf);
 }
 
-// Host scalars.  From 2^18 points on the MSM runs as two point-range halves through the two pipelined workspaces: the
-// second half of the scalars crosses PCIe (copy stream) while the first half is sorted and accumulated, and the first
-// half's window reduction overlaps the second half's accumulation; the two partial sums are added on the host.
+// Host scalars.  From 2^18 points on the MSM runs as two or three point ranges through the two pipelined workspaces: the
+// next range of the scalars crosses PCIe (copy stream) while the previous one is sorted and accumulated, and a range's
+// window reduction overlaps the next range's accumulation; the partial sums are added on the host.
 int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
     if (!scalars_host && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1: null scalars");
@@ -1132,22 +1063,35 @@ int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t
     // the staging buffer may still be read by work enqueued earlier on the main stream: the copies wait for it
     ZKB_CUDA(ctx, cudaEventRecord(st->part_uploaded[0], ctx->stream));
     ZKB_CUDA(ctx, cudaStreamWaitEvent(st->copy_stream, st->part_uploaded[0], 0));
-    const size_t part_n[2] = {n / 2, n - n / 2}, part_lo[2] = {0, n / 2};
+    // 2^19 points and more: three point ranges of 20 / 40 / 40 %.  The GPU idles until the first range has crossed PCIe, so
+    // that one is small; every further range costs one more sort and reduction (the reductions run on the tail stream under
+    // the next range's accumulation), so there are only three.  Two workspaces alternate: range 2 reuses range 0's after its
+    // result has been folded on the host.
+    const int parts = n >= ((size_t)1 << 19) ? 3 : 2;
+    size_t part_lo[4] = {0, 0, 0, n};
+    if (parts == 3) { part_lo[1] = n / 5; part_lo[2] = n / 5 + (n - n / 5) / 2; }
+    else { part_lo[1] = n / 2; part_lo[2] = n; }
     MsmPlan plans[2];
-    for (int k = 0; k < 2; ++k) {
-        char *dst = (char *)ctx->stage.p + part_lo[k] * 32;
-        ZKB_CUDA(ctx, cudaMemcpyAsync(dst, scalars_host + 4 * part_lo[k], part_n[k] * 32, cudaMemcpyHostToDevice, st->copy_stream));
+    hec::Pt total = hec::inf();
+    for (int k = 0; k < parts; ++k) {
+        const int slot = k & 1;
+        const size_t lo = part_lo[k], cnt = part_lo[k + 1] - lo;
+        if (k >= 2) {                                             // the slot's previous range: fold its result, free its workspace
+            ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[slot].tail_done));
+            total = hec::add(total, msm_fold(plans[slot], st->slot[slot].pinned));
+        }
+        char *dst = (char *)ctx->stage.p + lo * 32;
+        ZKB_CUDA(ctx, cudaMemcpyAsync(dst, scalars_host + 4 * lo, cnt * 32, cudaMemcpyHostToDevice, st->copy_stream));
         ZKB_CUDA(ctx, cudaEventRecord(st->part_uploaded[k], st->copy_stream));
         ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->part_uploaded[k], 0));
-        const size_t off = offset + part_lo[k];
-        rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, (const uint4 *)dst, part_n[k], 0, fb, off, &plans[k], k, true)
-                : msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + off, (const uint4 *)dst, part_n[k], ctx->msm_force_c, nullptr, 0, &plans[k], k, true);
+        const size_t off = offset + lo;
+        rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, (const uint4 *)dst, cnt, 0, fb, off, &plans[slot], slot, true)
+                : msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + off, (const uint4 *)dst, cnt, ctx->msm_force_c, nullptr, 0, &plans[slot], slot, true);
         if (rc) return rc;
     }
-    hec::Pt total = hec::inf();
-    for (int k = 0; k < 2; ++k) {
-        ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[k].tail_done));
-        total = hec::add(total, msm_fold(plans[k], st->slot[k].pinned));
+    for (int k = parts >= 2 ? parts - 2 : 0; k < parts; ++k) {
+        ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[k & 1].tail_done));
+        total = hec::add(total, msm_fold(plans[k & 1], st->slot[k & 1].pinned));
     }
     hec::to_affine(total, out_xy, is_inf);
     return ZKB_OK;
