@@ -117,55 +117,6 @@ __device__ __forceinline__ void g1x_add(g1x_t &acc, const g1x_t &q) {
     acc.zzz = fmul<Q>(fmul<Q>(acc.zzz, q.zzz), ppp);
 }
 
-// acc + q by FOUR cooperating lanes (consecutive, aligned to 4; sub = lane & 3; all four hold both operands and all four
-// return the sum).  The 14 products of add-2008-s are independent in groups of four, so the four lanes run them as 4 rounds
-// of one product each with the results exchanged by shuffles: ~2.7k cycles instead of ~7.7k for a lone thread.  For the
-// latency-bound ends of the bucket method (binary tail of the window reduction, oversized-bucket combine), where a level is
-// one dependent addition and nothing else can hide it.  Same field values as g1x_add (canonical residues), so the same point.
-__device__ __forceinline__ fe_t fe_from_lane(const fe_t &v, int src, uint32_t mask) {
-    fe_t r;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r.v[k] = __shfl_sync(mask, v.v[k], src, 4);
-    return r;
-}
-__device__ __forceinline__ fe_t fe_pick(uint32_t sub, const fe_t &a0, const fe_t &a1, const fe_t &a2, const fe_t &a3) {
-    fe_t r;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r.v[k] = sub == 0 ? a0.v[k] : sub == 1 ? a1.v[k] : sub == 2 ? a2.v[k] : a3.v[k];
-    return r;
-}
-static __device__ __noinline__ g1x_t g1x_add_coop4(const g1x_t &a, const g1x_t &b, uint32_t sub) {
-    if (g1x_is_inf(b)) return a;                               // every branch is uniform inside the group of four
-    if (g1x_is_inf(a)) return b;
-    const uint32_t mask = 0xFu << ((threadIdx.x & 31u) & ~3u);
-    // round 1: U1 = X1 ZZ2, U2 = X2 ZZ1, S1 = Y1 ZZZ2, S2 = Y2 ZZZ1
-    fe_t m = fmul<Q>(fe_pick(sub, a.x, b.x, a.y, b.y), fe_pick(sub, b.zz, a.zz, b.zzz, a.zzz));
-    const fe_t u1 = fe_from_lane(m, 0, mask), u2 = fe_from_lane(m, 1, mask), s1 = fe_from_lane(m, 2, mask), s2 = fe_from_lane(m, 3, mask);
-    const fe_t p = fsub<Q>(u2, u1), r = fsub<Q>(s2, s1);
-    if (fis_zero<Q>(p)) {
-        if (fis_zero<Q>(r)) return g1x_double(a);
-        return g1x_inf();
-    }
-    // round 2: PP = P^2, RR = R^2, ZZ1 ZZ2, ZZZ1 ZZZ2
-    m = fmul<Q>(fe_pick(sub, p, r, a.zz, a.zzz), fe_pick(sub, p, r, b.zz, b.zzz));
-    const fe_t pp = fe_from_lane(m, 0, mask), rr = fe_from_lane(m, 1, mask), zz12 = fe_from_lane(m, 2, mask), zzz12 = fe_from_lane(m, 3, mask);
-    // round 3: PPP = P PP, Q = U1 PP, ZZ3 = ZZ1 ZZ2 PP  (lane 3 repeats lane 2's product)
-    m = fmul<Q>(fe_pick(sub, p, u1, zz12, zz12), pp);
-    const fe_t ppp = fe_from_lane(m, 0, mask), q = fe_from_lane(m, 1, mask), zz3 = fe_from_lane(m, 2, mask);
-    g1x_t o;
-    o.x = fsub<Q>(fsub<Q>(fsub<Q>(rr, ppp), q), q);
-    // round 4: R (Q - X3), S1 PPP, ZZZ3 = ZZZ1 ZZZ2 PPP
-    m = fmul<Q>(fe_pick(sub, r, s1, zzz12, zzz12), fe_pick(sub, fsub<Q>(q, o.x), ppp, ppp, ppp));
-    o.y = fsub<Q>(fe_from_lane(m, 0, mask), fe_from_lane(m, 1, mask));
-    o.zz = zz3;
-    o.zzz = fe_from_lane(m, 2, mask);
-    return o;
-}
-// coordinate `sub` (0: x, 1: y, 2: zz, 3: zzz) of a point stored by lane `sub` of a group: one coalesced 128-byte store
-__device__ __forceinline__ void g1x_store_coop4(void *p, const g1x_t &a, uint32_t sub) {
-    fstore(reinterpret_cast<char *>(p) + 32 * sub, fe_pick(sub, a.x, a.y, a.zz, a.zzz));
-}
-
 __device__ __forceinline__ g1a_t g1a_neg(const g1a_t &p) {
     g1a_t r;
     r.x = p.x;

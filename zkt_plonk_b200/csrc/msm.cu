@@ -33,6 +33,8 @@
 #include "host_ff.h"
 #include "msm_pairs.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cmath>
 #include <array>
@@ -380,18 +382,21 @@ __device__ __forceinline__ g1x_t shfl_down_g1x(const g1x_t &p, int d) {
 // Stage 1: a warp folds one chunk of <= HEAVY_CHUNK task results of a bucket into the bucket's value (single chunk) or into a
 // chunk sum.  Stage 2: a warp folds the chunk sums of a multi-chunk bucket.  A 200k-entry bucket cut into 64-entry tasks is 3300 tasks -> 52 chunks -> one value, each
 // stage ~30 us, instead of one CTA walking all task results.
-// `len` points at base[0 .. len) folded by one warp working as 8 groups of 4 lanes (g1x_add_coop4: four lanes per addition,
-// ~1/3 of a lone thread's latency): group q adds base[q], base[q + 8], ... in turn, then the eight group sums are folded in a
-// three-level tree.  All 32 lanes of the warp must call it.
-__device__ __forceinline__ void warp_fold_store_coop(const g1x_t *base, uint32_t len, g1x_t *dst) {
-    const uint32_t lane = threadIdx.x & 31, q = lane >> 2, sub = lane & 3;
+// `len` points at base[0 .. len) folded by one warp: lanes stride over them, then a shuffle tree.  (Four cooperating lanes
+// per addition -- the 14 products of an XYZZ addition as 4 rounds of one product per lane -- were measured here and in the
+// binary tail of the window reduction and dropped: a lone warp is bound by its instruction issue latency, and the exchange
+// by shuffles costs what the shorter product chain saves; profiles/r02f, r02g.)
+__device__ __forceinline__ void warp_fold_store(const g1x_t *base, uint32_t len, g1x_t *dst) {
+    const uint32_t lane = threadIdx.x & 31;
     g1x_t acc = g1x_inf();
-    for (uint32_t k = q; k < len; k += 8) acc = g1x_add_coop4(acc, g1x_load(base + k), sub);
-    for (int d = 4; d >= 1; d >>= 1) {
-        const g1x_t o = shfl_down_g1x(acc, 4 * d);                  // every lane takes part in the exchange
-        if (q < (uint32_t)d && q + d < len) acc = g1x_add_coop4(acc, o, sub);
+    for (uint32_t k = lane; k < len; k += 32) g1x_add(acc, g1x_load(base + k));
+    for (int d = 16; d >= 1; d >>= 1) {
+        if ((uint32_t)d >= len) continue;                          // uniform across the warp
+        g1x_t o = shfl_down_g1x(acc, d);
+        if (lane < (uint32_t)d) g1x_add(acc, o);
     }
-    if (q == 0) g1x_store_coop4(dst, acc, sub);
+    __syncwarp();
+    if (lane == 0) g1x_store(dst, acc);
 }
 
 __global__ void __launch_bounds__(128) msm_combine_chunks_kernel(const uint32_t *misc, const uint32_t *heavy_list, const uint32_t *heavy_slot,
@@ -403,7 +408,7 @@ __global__ void __launch_bounds__(128) msm_combine_chunks_kernel(const uint32_t 
         const uint2 item = chunk_items[it];
         const uint32_t b = heavy_list[item.x], nt = ntasks[b], lo = item.y * HEAVY_CHUNK, len = min(HEAVY_CHUNK, nt - lo);
         const uint32_t slot = heavy_slot[item.x];
-        warp_fold_store_coop(task_out + task_base[b] + lo, len, slot == 0xffffffffu ? bucket_val + b : chunk_out + slot + item.y);
+        warp_fold_store(task_out + task_base[b] + lo, len, slot == 0xffffffffu ? bucket_val + b : chunk_out + slot + item.y);
     }
 }
 
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(128) msm_combine_final_kernel(const uint32_t *
     const uint32_t nmulti = misc[4];
     for (uint32_t it = warp; it < nmulti; it += nwarps) {
         const uint32_t h = multi_list[it], b = heavy_list[h], chunks = (ntasks[b] + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
-        warp_fold_store_coop(chunk_out + heavy_slot[h], chunks, bucket_val + b);
+        warp_fold_store(chunk_out + heavy_slot[h], chunks, bucket_val + b);
     }
 }
 
@@ -1063,14 +1068,13 @@ int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t
     // the staging buffer may still be read by work enqueued earlier on the main stream: the copies wait for it
     ZKB_CUDA(ctx, cudaEventRecord(st->part_uploaded[0], ctx->stream));
     ZKB_CUDA(ctx, cudaStreamWaitEvent(st->copy_stream, st->part_uploaded[0], 0));
-    // 2^19 points and more: three point ranges of 20 / 40 / 40 %.  The GPU idles until the first range has crossed PCIe, so
-    // that one is small; every further range costs one more sort and reduction (the reductions run on the tail stream under
-    // the next range's accumulation), so there are only three.  Two workspaces alternate: range 2 reuses range 0's after its
-    // result has been folded on the host.
-    const int parts = n >= ((size_t)1 << 19) ? 3 : 2;
-    size_t part_lo[4] = {0, 0, 0, n};
-    if (parts == 3) { part_lo[1] = n / 5; part_lo[2] = n / 5 + (n - n / 5) / 2; }
-    else { part_lo[1] = n / 2; part_lo[2] = n; }
+    // Two point ranges.  The GPU idles until the first range has crossed PCIe, so that one is the smaller; every range costs
+    // a sort and a window reduction of its own (the first one's reduction runs on the tail stream under the second one's
+    // accumulation).  Measured at 2^20 (profiles/r02g, r02h): three ranges of 20 / 40 / 40 % are SLOWER than two halves (3.71
+    // vs 3.41 ms: the call is bound by GPU work, not by the transfer).
+    static const int first_pct = [] { const char *e = getenv("ZKB_MSM_SPLIT"); int v = e ? atoi(e) : 0; return v >= 10 && v <= 90 ? v : 40; }();
+    const int parts = 2;
+    size_t part_lo[4] = {0, n * (size_t)first_pct / 100, n, n};
     MsmPlan plans[2];
     hec::Pt total = hec::inf();
     for (int k = 0; k < parts; ++k) {
