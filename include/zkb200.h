@@ -212,7 +212,10 @@ ZKB_API int zkb_plonk_vk_commitments(const zkb_plonk_pk *pk, uint64_t out_xy[80]
  * pi_values: one value per pi_position; blinders: the 19 elements the reference draws with F::rand, in draw order
  * a(2) b(2) c(2) h1(3) h2(2) z1(3) z2(3) b0 b1; proof_out: the 802 bytes of Proof's CanonicalSerialize.
  * timings_ms (optional, 8 floats; non-NULL drains the stream at every boundary): wire upload, round 1, host lookup
- * plumbing, round 2, round 3, round 4, round 5, total. */
+ * plumbing, round 2, round 3, round 4, round 5, total.
+ * NOT re-entrant per key: although `pk` is const in the signature (it is never changed as a KEY), a proof uses the key's
+ * HBM arena, pinned staging and dirty-range bookkeeping as scratch, so one key serves one zkb_plonk_prove at a time (one
+ * proving thread per context, as prove() is !Send upstream: prove.rs:62); concurrent proofs need one key object each. */
 ZKB_API int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, const uint64_t *b, const uint64_t *c,
                     const uint64_t *table, size_t table_len, const uint64_t *pi_values, const uint64_t *blinders,
                     uint8_t proof_out[802], float timings_ms[8]);

@@ -29,7 +29,7 @@ def test_against_oracle_all_modes(ctx, log_n):
         assert np.array_equal(got, cref.ntt(x, log_n, inv, cos)), (log_n, inv, cos)
 
 
-@pytest.mark.parametrize("log_n", [22, 23])
+@pytest.mark.parametrize("log_n", [22, 23, 24])
 def test_large_against_oracle(ctx, log_n):
     x = rand_fr_mont(1 << log_n, 77)
     d = to_dev(x)

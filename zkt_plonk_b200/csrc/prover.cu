@@ -699,7 +699,10 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
         // memory bandwidth, so a rank uploads only its 1/world slice and the slices are all-gathered over NVLink.
         const bool split = ctx->world > 1 && ctx->comm && n % (size_t)ctx->world == 0;
         const size_t chunk = split ? n / (size_t)ctx->world : n, first = split ? (size_t)ctx->rank * chunk : 0;
-        TRY(zkb_commit_expect(ctx, 3));                                  // a, b, c: one batch (prove.rs:133-135), pushed as the wires arrive
+        // a, b, c are one batch upstream (prove.rs:133-135), but here they are pushed as the wires cross PCIe: every push is
+        // cut over ALL ranks (no zkb_commit_expect).  Fanning this batch out -- one group of ranks per wire -- serialises it
+        // behind the uploads: the last group starts its (larger) MSM only when the last wire has arrived (measured on 8 B200:
+        // round 1 4.6 instead of 3.5 ms at n = 2^20, profiles/r02i_bench_n8.json).
         for (int k = 0; k < 3; ++k) {
             const uint64_t *src = wires[k].host + 4 * first;
             if (chunk * 32 >= ((size_t)16 << 20)) {                      // measured: pays off from ~16 MiB (2.6 vs 3.2 ms at 32 MiB)
