@@ -328,12 +328,13 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + 32));
 }
 
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__restrict__ points, const g1a_t *__restrict__ pool,
+__global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const g1a_t *__restrict__ points, const g1a_t *__restrict__ pool,
                                                              const uint32_t *__restrict__ sorted,
                                                              const uint32_t *__restrict__ counts, const uint32_t *__restrict__ starts,
                                                              const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_base,
                                                              const uint2 *__restrict__ task_order, const uint32_t *__restrict__ misc,
-                                                             uint32_t SEG, g1x_t *__restrict__ task_out, g1x_t *__restrict__ bucket_val) {
+                                                             uint32_t SEG, g1x_t *__restrict__ task_out, g1x_t *__restrict__ bucket_val,
+                                                             uint32_t PF) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= misc[1]) return;
     uint2 task = task_order[t];
@@ -342,9 +343,12 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1a_t *__rest
     const uint32_t *idx = sorted + starts[b] + s * SEG;
 
     g1x_t acc = g1x_inf();
-    // Three-deep gather pipeline: L2 prefetch PF points ahead (no registers held; the fixed-base tables are far
-    // larger than L2, so every gather is an HBM access), register load one point ahead, add the current point.
-    constexpr uint32_t PF = 6;
+    // Gather pipeline: register load one point ahead, add the current point.  One addition of a warp takes ~10 us with four
+    // warps per scheduler, ten times an HBM access, so the load issued one iteration ahead always arrives in time; the
+    // optional L2 prefetch PF points ahead (round 1's default, PF = 6) buys nothing and `prefetch.global.L2` pulls whole
+    // 128-byte lines for 64-byte points: measured 1.894 ms without it against 1.905 with it at 2^20
+    // (profiles/r02k_msm_prefetch_distance.log), and half the DRAM traffic.
+    // (PF = L2 prefetch distance in points, 0 = none: a kernel argument so that its effect on time and DRAM traffic can be measured)
     // an entry is a point of the base / table array or (bit 30, after pair rounds) a sum in the pool of intermediate results
     for (uint32_t k = 1; k < PF && k < cnt; ++k) prefetch_l2(pairs::ref_ptr(points, pool, idx[k]));
     uint32_t v = idx[0];
@@ -812,7 +816,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[1], s));
     msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, pool, ws.sorted, ws.counts, ws.starts, ws.ntasks,
                                                                              ws.task_base, ws.task_order, ws.misc, pl.seg, ws.task_out,
-                                                                             ws.bucket_val);
+                                                                             ws.bucket_val, (uint32_t)ctx->msm_prefetch);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[2], s));
     msm_combine_chunks_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.heavy_slot, ws.chunk_items, ws.ntasks, ws.task_base,
                                                                 ws.task_out, ws.chunk_out, ws.bucket_val);
