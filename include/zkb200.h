@@ -219,6 +219,15 @@ ZKB_API int zkb_plonk_vk_commitments(const zkb_plonk_pk *pk, uint64_t out_xy[80]
 ZKB_API int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, const uint64_t *b, const uint64_t *c,
                     const uint64_t *table, size_t table_len, const uint64_t *pi_values, const uint64_t *blinders,
                     uint8_t proof_out[802], float timings_ms[8]);
+/* ProvingComposer::wire_evals (prove.rs:49-55) on the device.  zkb_plonk_pk_set_wiring gives the key the
+ * circuit's wire maps (w_l, w_r, w_o of the padded composer: n variable indices each, 0 = Variable::Zero); zkb_plonk_prove_vars
+ * then takes the variable assignment (n_vars Montgomery elements, var_values[0] = 0 for Variable::Zero) instead of the three
+ * wire vectors: the assignment crosses PCIe once (typically well under 3n elements) and the wires are gathered in HBM.  Same
+ * 802 bytes as zkb_plonk_prove on a = value_of_var(w_l[i]) etc. */
+ZKB_API int zkb_plonk_pk_set_wiring(zkb_ctx *ctx, zkb_plonk_pk *pk, const uint32_t *w_l, const uint32_t *w_r, const uint32_t *w_o);
+ZKB_API int zkb_plonk_prove_vars(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *var_values, size_t n_vars, const uint64_t *table,
+                         size_t table_len, const uint64_t *pi_values, const uint64_t *blinders, uint8_t proof_out[802],
+                         float timings_ms[8]);
 
 /* ---- verifier: host code, no GPU needed ---------------------------------------------------------------- */
 /* Proof::verify (plonk-core/src/proof_system/proof.rs:285-503) for BN254 / KZG10: transcript replay, compute_r0 (:163-217),

@@ -74,6 +74,44 @@ def test_degenerate_circuits_in_the_native_driver(ctx):
     native.close()
 
 
+@pytest.mark.parametrize("log_n", [6, 12])
+def test_wires_gathered_on_the_device_give_the_same_proof(ctx, log_n):
+    """zkb_plonk_pk_set_wiring + zkb_plonk_prove_vars (ProvingComposer::wire_evals on the device, prove.rs:49-55; SURVEY.md
+    8f-1): the key keeps w_l / w_r / w_o, the proof uploads the variable assignment only.  Same 802 bytes as the call that
+    takes the three wire vectors; bad inputs are refused."""
+    import ctypes
+    from zkt_plonk_b200._lib import ZkbError
+    circ = synthetic.make_circuit(log_n, seed=80 + log_n, table_size=min(64, (1 << log_n) // 4))
+    assert circ.var_values.shape[0] < 3 * circ.n
+    for k, w in enumerate((circ.a, circ.b, circ.c)):
+        assert np.array_equal(circ.var_values[circ.wiring[k]], w)
+    d_srs, _ = gpu_srs(ctx, circ.n + 8)
+    ctx.srs_load(d_srs)
+    native = prover.NativeProver(ctx, circ)
+    blinders = list(range(300, 319))
+    want = native.prove_bytes(blinders)
+    with pytest.raises(ZkbError):
+        native.prove_bytes(blinders, from_vars=True)              # no wiring yet
+    native.set_wiring()
+    assert native.prove_bytes(blinders, from_vars=True) == want
+    assert native.prove_bytes(blinders, from_vars=True) == want   # and again (the assignment buffer is reused)
+    assert native.prove_bytes(blinders) == want                   # the wire-vector entry still works on the same key
+    good = circ.var_values
+    try:
+        circ.var_values = good[: good.shape[0] - 1]               # the wiring refers to a variable beyond n_vars
+        with pytest.raises(ZkbError):
+            native.prove_bytes(blinders, from_vars=True)
+        bad = good.copy()
+        bad[0, 0] = 1                                              # Variable::Zero must be zero
+        circ.var_values = bad
+        with pytest.raises(ZkbError):
+            native.prove_bytes(blinders, from_vars=True)
+    finally:
+        circ.var_values = good
+    assert native.prove_bytes(blinders, from_vars=True) == want
+    native.close()
+
+
 def test_gpu_proof_2_14_verifies(ctx):
     """Larger circuit: too slow for the Python-int oracle prover, so acceptance by the verifier is the check."""
     import zkt_plonk_b200 as z

@@ -84,6 +84,8 @@ def load():
         "zkb_test_transcript": (i, [i, vp, sz, vp, vp]),
         "zkb_plonk_vk_commitments": (i, [vp, vp, ctypes.POINTER(i)]),
         "zkb_plonk_prove": (i, [vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, ctypes.POINTER(ctypes.c_float)]),
+        "zkb_plonk_pk_set_wiring": (i, [vp, vp, vp, vp, vp]),
+        "zkb_plonk_prove_vars": (i, [vp, vp, vp, sz, vp, sz, vp, vp, vp, ctypes.POINTER(ctypes.c_float)]),
         "zkb_ck_file_info": (i, [ctypes.c_char_p, ctypes.POINTER(sz), ctypes.POINTER(sz)]),
         "zkb_ck_file_read": (i, [ctypes.c_char_p, sz, sz, vp]),
         "zkb_ck_file_write": (i, [ctypes.c_char_p, vp, sz, vp, sz, sz]),

@@ -130,8 +130,6 @@ int zkb_ctx_create(int device, zkb_ctx **out) {
     if (pf && atoi(pf) >= 0 && atoi(pf) <= 16) ctx->msm_prefetch = atoi(pf);
     const char *nk = getenv("ZKB_NTT_KERNEL");                  // "0" / "1" / "2": see zkb_ntt_set_kernel
     if (nk && nk[0] >= '0' && nk[0] <= '2' && nk[1] == 0) ctx->ntt_kernel = nk[0] - '0';
-    const char *fg = getenv("ZKB_L2_FETCH");                    // experiment: L2 fetch granularity hint (32 / 64 / 128 bytes)
-    if (fg && (atoi(fg) == 32 || atoi(fg) == 64 || atoi(fg) == 128)) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
     *out = ctx;
     return ZKB_OK;
 }

@@ -137,6 +137,12 @@ struct zkb_plonk_pk {
     char *arena = nullptr;                       // per-proof scratch: reset at the start of every prove
     size_t arena_bytes = 0, arena_off = 0;
     int transcript_kind = 0;                     // 0 MerlinTranscript (default binary), 1 EthereumTranscript
+    // ProvingComposer::wire_evals on the device (zkb_plonk_pk_set_wiring): the circuit's wire maps, 0 = Variable::Zero
+    uint32_t *d_wiring[3] = {nullptr, nullptr, nullptr};   // w_l, w_r, w_o: n variable indices each, in HBM
+    std::vector<uint32_t> lookup_wo;             // w_o on the lookup rows (the host side of round 2 needs c there)
+    size_t n_vars_max = 0;                       // 1 + the largest variable index the wiring refers to
+    uint64_t *d_vars = nullptr;                  // the assignment of the current proof in HBM (grown on demand)
+    size_t d_vars_cap = 0;
 };
 
 namespace {
@@ -195,6 +201,15 @@ __global__ void scatter_fe_kernel(uint4 *dst, const unsigned long long *pos, con
     if (k >= count) return;
     dst[2 * pos[k]] = vals[2 * k];
     dst[2 * pos[k] + 1] = vals[2 * k + 1];
+}
+
+// ProvingComposer::wire_evals (prove.rs:49-55): wire[i] = value_of_var(w[i]); vars[0] is Variable::Zero's value (zero)
+__global__ void __launch_bounds__(256) gather_wire_kernel(uint4 *__restrict__ wire, const uint32_t *__restrict__ w, const uint4 *__restrict__ vars, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t v = w[i];
+    wire[2 * i] = __ldg(vars + 2 * v);
+    wire[2 * i + 1] = __ldg(vars + 2 * v + 1);
 }
 
 __global__ void scatter_fe_rows_kernel(uint4 *dst, const uint32_t *rows, const uint4 *vals, size_t count) {
@@ -288,6 +303,7 @@ void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
     if (pk->arena) cudaFree(pk->arena);
     if (pk->stage) cudaFreeHost(pk->stage);
     if (pk->wire_stage) cudaFreeHost(pk->wire_stage);
+    if (pk->d_vars) cudaFree(pk->d_vars);
     if (pk->copy_stream) cudaStreamDestroy(pk->copy_stream);
     if (pk->lookup_stream) cudaStreamDestroy(pk->lookup_stream);
     if (pk->lookup_uploaded) cudaEventDestroy(pk->lookup_uploaded);
@@ -567,12 +583,22 @@ int zkb_plonk_vk_commitments(const zkb_plonk_pk *pk, uint64_t out_xy[80], int is
     return ZKB_OK;
 }
 
-int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, const uint64_t *b, const uint64_t *c,
-                    const uint64_t *table, size_t table_len, const uint64_t *pi_values, const uint64_t *blinders,
-                    uint8_t proof_out[802], float timings_ms[8]) {
+}  // extern "C"
+
+// Both entry points: the wires come either as three host vectors (a, b, c) or, after zkb_plonk_pk_set_wiring, as the
+// variable assignment `vars` (n_vars elements) from which the device gathers them.
+static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, const uint64_t *b, const uint64_t *c,
+                      const uint64_t *vars, size_t n_vars, const uint64_t *table, size_t table_len, const uint64_t *pi_values,
+                      const uint64_t *blinders, uint8_t proof_out[802], float timings_ms[8]) {
     if (!ctx || !pk) return ZKB_ERR_INVALID;
-    if (!a || !b || !c || (!table && table_len) || (!pi_values && !pk->pi_pos.empty()) || !blinders || !proof_out)
+    if ((!vars && (!a || !b || !c)) || (!table && table_len) || (!pi_values && !pk->pi_pos.empty()) || !blinders || !proof_out)
         ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: null argument");
+    if (vars) {
+        if (!pk->d_wiring[0]) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove_vars: the key has no wiring (zkb_plonk_pk_set_wiring)");
+        if (n_vars < pk->n_vars_max) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove_vars: the wiring refers to variables beyond n_vars");
+        const uint64_t *z = vars;
+        if (z[0] | z[1] | z[2] | z[3]) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove_vars: vars[0] is Variable::Zero and must be zero");
+    }
     if (table_len > pk->table_size) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: table size exceeds max size (lookup/table.rs:57)");
     const unsigned log_n = pk->log_n;
     const size_t n = pk->n, n4 = 4 * n, cap = n + 8, n_pi = pk->pi_pos.size();
@@ -613,12 +639,12 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
         if (table_len) memcpy(t_vals, table, table_len * 32);           // LookupTable::into_multiset: entries then zeros
         mpk->dirty_t = table_len;
         const Fe one = FR_ONE();
-        const Fe *cv = (const Fe *)c;
+        const Fe *cv = (const Fe *)c, *vv = (const Fe *)vars;
         const size_t n_rows = pk->lookup_rows.size();
         for (size_t r = 0; r < n_rows; ++r) {                           // f is zero outside the lookup gates: kept as a compact list
-            const size_t i = pk->lookup_rows[r];
+            const Fe &ci = vv ? vv[pk->lookup_wo[r]] : cv[pk->lookup_rows[r]];   // c on that row: given, or value_of_var(w_o[row])
             const Fe &q = pk->lookup_q[r];
-            f_vals[r] = feq(q, one) ? cv[i] : fmul(q, cv[i]);
+            f_vals[r] = feq(q, one) ? ci : fmul(q, ci);
         }
         size_t n_h1 = 0, n_h2 = 0;
         if (!combine_split_sparse((const Fe *)table, table_len, n, f_vals, n_rows, h1_vals, h2_vals, mpk->dirty_h, &n_h1, &n_h2)) {
@@ -703,7 +729,33 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
         // cut over ALL ranks (no zkb_commit_expect).  Fanning this batch out -- one group of ranks per wire -- serialises it
         // behind the uploads: the last group starts its (larger) MSM only when the last wire has arrived (measured on 8 B200:
         // round 1 4.6 instead of 3.5 ms at n = 2^20, profiles/r02i_bench_n8.json).
-        for (int k = 0; k < 3; ++k) {
+        if (vars) {
+            // the assignment crosses PCIe once (n_vars elements instead of 3n), every rank its 1/world slice, then the three
+            // wires are gathered in HBM (ProvingComposer::wire_evals, prove.rs:49-55)
+            zkb_plonk_pk *mpk = const_cast<zkb_plonk_pk *>(pk);
+            const size_t world = split ? (size_t)ctx->world : 1, vpad = (n_vars + world - 1) / world * world;
+            if (mpk->d_vars_cap < vpad) {
+                if (mpk->d_vars) { ZKB_CUDA(ctx, cudaStreamSynchronize(pk->copy_stream)); cudaFree(mpk->d_vars); mpk->d_vars = nullptr; }
+                ZKB_CUDA(ctx, cudaMalloc((void **)&mpk->d_vars, vpad * 32));
+                mpk->d_vars_cap = vpad;
+            }
+            const size_t vchunk = vpad / world, vfirst = split ? (size_t)ctx->rank * vchunk : 0;
+            const size_t vcount = vfirst < n_vars ? std::min(vchunk, n_vars - vfirst) : 0;
+            if (vcount) ZKB_CUDA(ctx, cudaMemcpyAsync(mpk->d_vars + 4 * vfirst, vars + 4 * vfirst, vcount * 32, cudaMemcpyHostToDevice, pk->copy_stream));
+            if (split) TRY(zkb_comm_allgather_dev(ctx, mpk->d_vars, vchunk * 32, pk->copy_stream));
+            for (int k = 0; k < 3; ++k)
+                gather_wire_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pk->copy_stream>>>((uint4 *)wires[k].dev, pk->d_wiring[k],
+                                                                                           (const uint4 *)mpk->d_vars, n);
+            ZKB_CUDA(ctx, cudaGetLastError());
+            ZKB_CUDA(ctx, cudaEventRecord(pk->wire_uploaded, pk->copy_stream));
+            ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->wire_uploaded, 0));
+            tick(0);
+            for (int k = 0; k < 3; ++k) {
+                TRY(blinded_from_dev_evals(wires[k].dev, 2, wires[k].poly));
+                TRY(zkb_commit_push(ctx, wires[k].poly->d, 0, wires[k].poly->len));
+            }
+        }
+        for (int k = 0; k < 3 && !vars; ++k) {
             const uint64_t *src = wires[k].host + 4 * first;
             if (chunk * 32 >= ((size_t)16 << 20)) {                      // measured: pays off from ~16 MiB (2.6 vs 3.2 ms at 32 MiB)
                 Fe *pinned = pk->wire_stage + (size_t)k * n + first;
@@ -959,6 +1011,47 @@ int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, con
     for (int k = 0; k < 12; ++k, o += 32) fe_bytes(ev[k], host::FR, o);
     if (timings_ms) timings_ms[7] = (float)(now_ms() - t_start);
     return ZKB_OK;
+}
+
+extern "C" {
+
+int zkb_plonk_prove(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, const uint64_t *b, const uint64_t *c,
+                    const uint64_t *table, size_t table_len, const uint64_t *pi_values, const uint64_t *blinders,
+                    uint8_t proof_out[802], float timings_ms[8]) {
+    if (ctx && (!a || !b || !c)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: null argument");
+    return prove_impl(ctx, pk, a, b, c, nullptr, 0, table, table_len, pi_values, blinders, proof_out, timings_ms);
+}
+
+// ProvingComposer::wire_evals (prove.rs:49-55) moved to the device: the key keeps the circuit's wire maps,
+// a proof uploads the variable assignment once and the three wires are gathered in HBM.
+int zkb_plonk_pk_set_wiring(zkb_ctx *ctx, zkb_plonk_pk *pk, const uint32_t *w_l, const uint32_t *w_r, const uint32_t *w_o) {
+    if (!ctx || !pk) return ZKB_ERR_INVALID;
+    if (!w_l || !w_r || !w_o) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_pk_set_wiring: null wire map");
+    const size_t n = pk->n;
+    const uint32_t *w[3] = {w_l, w_r, w_o};
+    uint32_t vmax = 0;
+    for (int k = 0; k < 3; ++k)
+        for (size_t i = 0; i < n; ++i) vmax = std::max(vmax, w[k][i]);
+    for (int k = 0; k < 3; ++k) {
+        if (!pk->d_wiring[k]) {
+            uint64_t *d;
+            TRY(dev_alloc_owned(ctx, pk, n * 4, &d));
+            pk->d_wiring[k] = (uint32_t *)d;
+        }
+        ZKB_CUDA(ctx, cudaMemcpyAsync(pk->d_wiring[k], w[k], n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pk->lookup_wo.resize(pk->lookup_rows.size());
+    for (size_t r = 0; r < pk->lookup_rows.size(); ++r) pk->lookup_wo[r] = w_o[pk->lookup_rows[r]];
+    pk->n_vars_max = (size_t)vmax + 1;
+    return ZKB_OK;
+}
+
+int zkb_plonk_prove_vars(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *var_values, size_t n_vars, const uint64_t *table,
+                         size_t table_len, const uint64_t *pi_values, const uint64_t *blinders, uint8_t proof_out[802],
+                         float timings_ms[8]) {
+    if (ctx && (!var_values || !n_vars)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove_vars: null assignment");
+    return prove_impl(ctx, pk, nullptr, nullptr, nullptr, var_values, n_vars, table, table_len, pi_values, blinders, proof_out, timings_ms);
 }
 
 }  // extern "C"

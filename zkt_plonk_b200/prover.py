@@ -86,10 +86,13 @@ class Circuit:
     selectors: dict q_m,q_l,q_r,q_o,q_c,q_lookup -> (n,4) Montgomery; sigma: (sigma1,sigma2,sigma3) evals (n,4);
     table: list of canonical ints (<= table_size entries); witness a,b,c: (n,4) Montgomery; pi: {row: int}."""
 
-    def __init__(self, log_n, selectors, sigma, table, table_size, a, b, c, pi):
+    def __init__(self, log_n, selectors, sigma, table, table_size, a, b, c, pi, wiring=None, var_values=None):
         self.log_n, self.n = log_n, 1 << log_n
         self.selectors, self.sigma, self.table, self.table_size = selectors, sigma, table, table_size
         self.a, self.b, self.c, self.pi = a, b, c, dict(sorted(pi.items()))
+        # optional: the composer's wire maps w_l / w_r / w_o ((3, n) uint32 variable indices, 0 = Variable::Zero) and the
+        # variable assignment ((n_vars, 4) Montgomery, row 0 zero): a = var_values[wiring[0]] etc. (prove.rs:49-55)
+        self.wiring, self.var_values = wiring, var_values
 
 
 class ProverKey:
@@ -617,9 +620,20 @@ class NativeProver:
         w = field.root_of_unity(self.circuit.log_n)
         return VerifierKey(self.circuit.n, [pow(w, p, P) for p in self.circuit.pi.keys()], commits)
 
-    def prove_bytes(self, blinders, timings=False):
+    def set_wiring(self, wiring=None):
+        """zkb_plonk_pk_set_wiring: the key keeps the circuit's wire maps; prove_bytes(..., from_vars=True) then uploads the
+        variable assignment instead of the three wire vectors (ProvingComposer::wire_evals on the device)."""
+        import ctypes
+        w = np.ascontiguousarray(self.circuit.wiring if wiring is None else wiring, dtype=np.uint32)
+        assert w.shape == (3, self.circuit.n)
+        vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+        self.ctx._check(self.ctx._lib.zkb_plonk_pk_set_wiring(self.ctx._h, self._pk, vp(w[0]), vp(w[1]), vp(w[2])))
+
+    def prove_bytes(self, blinders, timings=False, from_vars=False):
         import ctypes
         c = self.circuit
+        if from_vars:
+            return self._prove_vars(blinders, timings)
         a, b, cc = (np.ascontiguousarray(x, dtype=np.uint64) for x in (c.a, c.b, c.c))
         table = ints_to_mont_array(c.table) if c.table else np.zeros((1, 4), dtype=np.uint64)
         pi = ints_to_mont_array(list(c.pi.values())) if c.pi else np.zeros((1, 4), dtype=np.uint64)
@@ -629,6 +643,25 @@ class NativeProver:
         vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
         self.ctx._check(self.ctx._lib.zkb_plonk_prove(self.ctx._h, self._pk, vp(a), vp(b), vp(cc), vp(table), len(c.table), vp(pi),
                                                       vp(bl), vp(out), tm))
+        raw = out.tobytes()
+        if timings:
+            names = ("h2d_wires_ms", "round1_wires_ms", "host_lookup_plumbing_ms", "round2_lookup_ms", "round3_grand_products_ms",
+                     "round4_quotient_ms", "round5_linearisation_openings_ms", "total_ms")
+            return raw, dict(zip(names, [float(x) for x in tm]))
+        return raw
+
+    def _prove_vars(self, blinders, timings):
+        import ctypes
+        c = self.circuit
+        vals = np.ascontiguousarray(c.var_values, dtype=np.uint64)
+        table = ints_to_mont_array(c.table) if c.table else np.zeros((1, 4), dtype=np.uint64)
+        pi = ints_to_mont_array(list(c.pi.values())) if c.pi else np.zeros((1, 4), dtype=np.uint64)
+        bl = ints_to_mont_array(blinders)
+        out = np.zeros(802, dtype=np.uint8)
+        tm = (ctypes.c_float * 8)() if timings else None
+        vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+        self.ctx._check(self.ctx._lib.zkb_plonk_prove_vars(self.ctx._h, self._pk, vp(vals), vals.shape[0], vp(table), len(c.table),
+                                                           vp(pi), vp(bl), vp(out), tm))
         raw = out.tobytes()
         if timings:
             names = ("h2d_wires_ms", "round1_wires_ms", "host_lookup_plumbing_ms", "round2_lookup_ms", "round3_grand_products_ms",

@@ -64,10 +64,10 @@ def make_circuit(log_n, seed=0, table_size=None, n_public=4, lookup_frac=0.01, f
         var_a[i], var_b[i], var_c[i] = va, vb, vc
         a[i], b[i], c[i] = x, y, values[vc]
 
-    return _finish(log_n, (var_a, var_b, var_c), (a, b, c), (q_m, q_l, q_r, q_o, q_c, q_lk), table, table_size, pi)
+    return _finish(log_n, (var_a, var_b, var_c), (a, b, c), (q_m, q_l, q_r, q_o, q_c, q_lk), table, table_size, pi, values)
 
 
-def _finish(log_n, var_ids, wires, sels, table, table_size, pi):
+def _finish(log_n, var_ids, wires, sels, table, table_size, pi, values=None):
     """sigma evaluations from the variable ids (positions of the same variable form one cycle) + Montgomery arrays."""
     n = 1 << log_n
     var_a, var_b, var_c = var_ids
@@ -93,8 +93,10 @@ def _finish(log_n, var_ids, wires, sels, table, table_size, pi):
 
     selectors = {"q_m": ints_to_mont_array(q_m), "q_l": ints_to_mont_array(q_l), "q_r": ints_to_mont_array(q_r),
                  "q_o": ints_to_mont_array(q_o), "q_c": ints_to_mont_array(q_c), "q_lookup": ints_to_mont_array(q_lk)}
+    wiring = np.array([list(var_a), list(var_b), list(var_c)], dtype=np.uint32)
+    var_values = ints_to_mont_array(values) if values is not None else None
     return Circuit(log_n, selectors, sigma, table, table_size, ints_to_mont_array(a), ints_to_mont_array(b),
-                   ints_to_mont_array(c), pi)
+                   ints_to_mont_array(c), pi, wiring=wiring, var_values=var_values)
 
 
 def make_edge_circuit(log_n, kind, seed=0, table_size=4):
@@ -145,7 +147,7 @@ def make_edge_circuit(log_n, kind, seed=0, table_size=4):
         table = []
     else:
         raise ValueError(kind)
-    return _finish(log_n, (var_a, var_b, var_c), (a, b, c), (q_m, q_l, q_r, q_o, q_c, q_lk), table, table_size, pi)
+    return _finish(log_n, (var_a, var_b, var_c), (a, b, c), (q_m, q_l, q_r, q_o, q_c, q_lk), table, table_size, pi, vals)
 
 
 def check_gates(circ):
