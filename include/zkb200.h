@@ -109,6 +109,8 @@ ZKB_API int zkb_msm_g1_dev_partial(zkb_ctx *ctx, const uint64_t *scalars_dev, si
  * passes the scalars of ITS resident SRS range, the partial sums are exchanged over NCCL inside the call and every rank
  * returns the same affine point.  Collective: all ranks must call it.  Without a communicator it is zkb_msm_g1_dev. */
 ZKB_API int zkb_msm_g1_sharded_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);
+/* The same with HOST scalars: the upload of this rank's scalars overlaps their accumulation (the two-range path of zkb_msm_g1). */
+ZKB_API int zkb_msm_g1_sharded(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf);
 /* Combine `count` shard results (after the NCCL all-gather of 128 B per rank) into the affine commitment. */
 ZKB_API int zkb_g1_sum_partials(const uint64_t *xyzz, size_t count, uint64_t out_xy[8], int *is_inf);
 /* Arbitrary bases: drop-in for VariableBaseMSM::multi_scalar_mul(bases, scalars) and

@@ -58,6 +58,7 @@ def load():
         "zkb_msm_g1_dev": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
         "zkb_msm_g1_dev_partial": (i, [vp, vp, sz, sz, vp]),
         "zkb_msm_g1_sharded_dev": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
+        "zkb_msm_g1_sharded": (i, [vp, vp, sz, sz, vp, ctypes.POINTER(i)]),
         "zkb_g1_sum_partials": (i, [vp, sz, vp, ctypes.POINTER(i)]),
         "zkb_msm_g1_bases": (i, [vp, vp, vp, sz, vp, ctypes.POINTER(i)]),
         "zkb_commit_batch_dev": (i, [vp, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, vp, ctypes.POINTER(i)]),

@@ -134,9 +134,13 @@ class Context:
     def msm_sharded(self, scalars_dev, offset=0, n=None):
         """Collective (every rank of the context's communicator): this rank's scalars against its resident SRS range; the
         partial sums are exchanged inside the library (NCCL) and every rank returns the same ((8,) affine, is_inf)."""
-        n = scalars_dev.numel() // 4 if n is None else n
         out = np.zeros(8, dtype=np.uint64)
         inf = ctypes.c_int(0)
+        if isinstance(scalars_dev, np.ndarray):                    # host scalars: upload overlapped with the accumulation
+            n = scalars_dev.shape[0] if n is None else n
+            self._check(self._lib.zkb_msm_g1_sharded(self._h, _host_ptr(scalars_dev), offset, n, _host_ptr(out), ctypes.byref(inf)))
+            return out, bool(inf.value)
+        n = scalars_dev.numel() // 4 if n is None else n
         self._check(self._lib.zkb_msm_g1_sharded_dev(self._h, _dev_ptr(scalars_dev), offset, n, _host_ptr(out), ctypes.byref(inf)))
         return out, bool(inf.value)
 

@@ -1051,8 +1051,7 @@ int zkb_msm_g1_sharded_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t off
 // Host scalars.  From 2^18 points on the MSM runs as two or three point ranges through the two pipelined workspaces: the
 // next range of the scalars crosses PCIe (copy stream) while the previous one is sorted and accumulated, and a range's
 // window reduction overlaps the next range's accumulation; the partial sums are added on the host.
-int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
-    if (!ctx || !out_xy) return ZKB_ERR_INVALID;
+static int msm_host_partial(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xyzz[16]) {
     if (!scalars_host && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1: null scalars");
     if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_msm: offset + n exceeds the loaded SRS");
     if (!state(ctx)->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "a zkb_commit_push batch is open (its scalars and results live in the buffers this call would reuse): call zkb_commit_finish first");
@@ -1061,7 +1060,7 @@ int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t
     MsmState *st = state(ctx);
     if (n < ((size_t)1 << 18)) {
         ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-        return zkb_msm_g1_dev(ctx, (const uint64_t *)ctx->stage.p, offset, n, out_xy, is_inf);
+        return zkb_msm_g1_dev_partial(ctx, (const uint64_t *)ctx->stage.p, offset, n, out_xyzz);
     }
     if (!st->copy_stream) {
         ZKB_CUDA(ctx, cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
@@ -1101,8 +1100,30 @@ int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t
         ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[k & 1].tail_done));
         total = hec::add(total, msm_fold(plans[k & 1], st->slot[k & 1].pinned));
     }
-    hec::to_affine(total, out_xy, is_inf);
+    memcpy(out_xyzz, &total, 128);
     return ZKB_OK;
+}
+
+int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+    if (!ctx || !out_xy) return ZKB_ERR_INVALID;
+    uint64_t xyzz[16];
+    int rc = msm_host_partial(ctx, scalars_host, offset, n, xyzz);
+    if (rc) return rc;
+    return zkb_g1_sum_partials(xyzz, 1, out_xy, is_inf);
+}
+
+// zkb_msm_g1_sharded_dev with HOST scalars: every rank uploads the scalars of its resident range through the pipelined
+// two-range path above (upload under accumulation), then the partial sums are exchanged
+int zkb_msm_g1_sharded(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+    if (!ctx || !out_xy) return ZKB_ERR_INVALID;
+    uint64_t mine[16];
+    int rc = msm_host_partial(ctx, scalars_host, offset, n, mine);
+    if (rc) return rc;
+    if (ctx->world == 1) return zkb_g1_sum_partials(mine, 1, out_xy, is_inf);
+    std::vector<uint64_t> all((size_t)ctx->world * 16);
+    rc = zkb_comm_allgather(ctx, mine, 128, all.data());
+    if (rc) return rc;
+    return zkb_g1_sum_partials(all.data(), (size_t)ctx->world, out_xy, is_inf);
 }
 
 // arbitrary bases (drop-in for VariableBaseMSM::multi_scalar_mul / HomomorphicCommitment::multi_scalar_mul)
