@@ -191,103 +191,113 @@ __global__ void __launch_bounds__(THREADS, 4) pair_add_kernel(const g1a_t *__res
         }
     }
 
-    // ---- phase 1b: running product of the denominators
+    // Odd warps cut their pairs into two batches (one third, two thirds), even warps run one: every batch ends phase 1 with an
+    // inversion that keeps its warp off the multiplier for tens of microseconds, and warps that started together would all
+    // invert together (measured: 12 % of a round's stall samples).  Staggered, one half of an SM's warps multiplies while the
+    // other inverts.
     const fe_t one = fone<Q>();
-    fe_t run = one;
-    if (cnt) {
-        for (uint32_t u = 0; u < PF && u < cnt; ++u) {
-            const uint2 pr = my_refs[(size_t)u * T];
-            prefetch_x(ref_ptr(points, pool, pr.x));
-            prefetch_x(ref_ptr(points, pool, pr.y));
-        }
-        uint2 pr = my_refs[0];
-        fe_t x1 = fload(&ref_ptr(points, pool, pr.x)->x), x2 = fload(&ref_ptr(points, pool, pr.y)->x);
-        for (uint32_t i = 0; i < cnt; ++i) {
-            fe_t nx1 = x1, nx2 = x2;
-            if (i + PF < cnt) {
-                const uint2 pf = my_refs[(size_t)(i + PF) * T];
-                prefetch_x(ref_ptr(points, pool, pf.x));
-                prefetch_x(ref_ptr(points, pool, pf.y));
-            }
-            if (i + 1 < cnt) {                                   // next pair's x coordinates in flight during the product
-                const uint2 nr = my_refs[(size_t)(i + 1) * T];
-                nx1 = fload(&ref_ptr(points, pool, nr.x)->x);
-                nx2 = fload(&ref_ptr(points, pool, nr.y)->x);
-            }
-            const fe_t d = fsub<Q>(x2, x1);
-            if (!special_pair(x1, x2, d)) run = fmul<Q>(run, d);
-            fstore(&my_pre[(size_t)i * T], run);
-            x1 = nx1;
-            x2 = nx2;
-        }
-    }
+    const uint32_t nbatch = ((threadIdx.x >> 5) & 1) ? 2 : 1;
+    for (uint32_t bt = 0; bt < nbatch; ++bt) {
+        const uint32_t lo = nbatch == 1 ? 0 : (bt == 0 ? 0 : cnt / 3), hi = nbatch == 1 ? cnt : (bt == 0 ? cnt / 3 : cnt);
+        const uint32_t len = hi - lo;
 
-    // ---- ONE inversion per WARP and batch: the 32 lane totals are multiplied up by two shuffle scans (prefix and suffix
-    // products, 5 steps each), lane 0 inverts the warp total (binary extended Euclid, ALU pipe: the other warps of the SM
-    // keep the multiplier busy), and 1 / T_l = (1 / T_0..31) * T_0..l-1 * T_l+1..31.  A lock-step inversion in all 32 lanes
-    // would cost the same issue slots per lane and diverge in its data-dependent loops (measured: 0.5 ms per round).
-    fe_t inv;
-    {
-        fe_t pfx = run, sfx = run;
+        // ---- phase 1b: running product of the denominators of pairs [lo, hi).  Loads run two pairs ahead in registers (x
+        // coordinates only) and the references three ahead; no L2 prefetch instruction (it pulls 128-byte lines).
+        fe_t run = one;
+        if (len) {
+            uint2 r1 = my_refs[(size_t)lo * T], r2 = len > 1 ? my_refs[(size_t)(lo + 1) * T] : r1, r3 = len > 2 ? my_refs[(size_t)(lo + 2) * T] : r1;
+            fe_t xa1 = fload_ro(&ref_ptr(points, pool, r1.x)->x), xa2 = fload_ro(&ref_ptr(points, pool, r1.y)->x);
+            fe_t xb1 = fload_ro(&ref_ptr(points, pool, r2.x)->x), xb2 = fload_ro(&ref_ptr(points, pool, r2.y)->x);
+            for (uint32_t i = lo; i < hi; ++i) {
+                const uint2 r4 = i + 3 < hi ? my_refs[(size_t)(i + 3) * T] : r3;
+                fe_t xc1 = xb1, xc2 = xb2;
+                if (i + 2 < hi) {
+                    xc1 = fload_ro(&ref_ptr(points, pool, r3.x)->x);
+                    xc2 = fload_ro(&ref_ptr(points, pool, r3.y)->x);
+                }
+                const fe_t d = fsub<Q>(xa2, xa1);
+                if (!special_pair(xa1, xa2, d)) run = fmul<Q>(run, d);
+                fstore(&my_pre[(size_t)i * T], run);
+                xa1 = xb1; xa2 = xb2; xb1 = xc1; xb2 = xc2;
+                r3 = r4;
+            }
+        }
+
+        // ---- ONE inversion per WARP and batch: the 32 lane totals are multiplied up by two shuffle scans (prefix and suffix
+        // products, 5 steps each), lane 0 inverts the warp total (binary extended Euclid, ALU pipe: the other warps of the SM
+        // keep the multiplier busy), and 1 / T_l = (1 / T_0..31) * T_0..l-1 * T_l+1..31.  A lock-step inversion in all 32
+        // lanes would cost the same issue slots per lane and diverge in its data-dependent loops (measured: 0.5 ms per round).
+        fe_t inv;
+        {
+            fe_t pfx = run, sfx = run;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            fe_t up, dn;
+            for (int d = 1; d < 32; d <<= 1) {
+                fe_t up, dn;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    up.v[k] = __shfl_up_sync(0xffffffffu, pfx.v[k], d);
+                    dn.v[k] = __shfl_down_sync(0xffffffffu, sfx.v[k], d);
+                }
+                if (lane >= (uint32_t)d) pfx = fmul<Q>(pfx, up);
+                if (lane + d < 32) sfx = fmul<Q>(sfx, dn);
+            }
+            fe_t tot;                                            // T_0 * ... * T_31 sits in lane 31's prefix
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tot.v[k] = __shfl_sync(0xffffffffu, pfx.v[k], 31);
+            if (lane == 0) tot = finv_euclid<Q>(tot);
+            fe_t before, after;                                  // exclusive prefix / suffix products of my lane
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                up.v[k] = __shfl_up_sync(0xffffffffu, pfx.v[k], d);
-                dn.v[k] = __shfl_down_sync(0xffffffffu, sfx.v[k], d);
+                tot.v[k] = __shfl_sync(0xffffffffu, tot.v[k], 0);
+                before.v[k] = __shfl_up_sync(0xffffffffu, pfx.v[k], 1);
+                after.v[k] = __shfl_down_sync(0xffffffffu, sfx.v[k], 1);
             }
-            if (lane >= (uint32_t)d) pfx = fmul<Q>(pfx, up);
-            if (lane + d < 32) sfx = fmul<Q>(sfx, dn);
+            inv = tot;
+            if (lane > 0) inv = fmul<Q>(inv, before);
+            if (lane < 31) inv = fmul<Q>(inv, after);
         }
-        fe_t tot;                                                // T_0 * ... * T_31 sits in lane 31's prefix
-#pragma unroll
-        for (int k = 0; k < 8; ++k) tot.v[k] = __shfl_sync(0xffffffffu, pfx.v[k], 31);
-        if (lane == 0) tot = finv_euclid<Q>(tot);
-        fe_t before, after;                                      // exclusive prefix / suffix products of my lane
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            tot.v[k] = __shfl_sync(0xffffffffu, tot.v[k], 0);
-            before.v[k] = __shfl_up_sync(0xffffffffu, pfx.v[k], 1);
-            after.v[k] = __shfl_down_sync(0xffffffffu, sfx.v[k], 1);
-        }
-        inv = tot;
-        if (lane > 0) inv = fmul<Q>(inv, before);
-        if (lane < 31) inv = fmul<Q>(inv, after);
-    }
 
-    // ---- phase 2: the additions, last pair first
-    for (uint32_t u = 0; u < PF && u < cnt; ++u) {
-        const uint2 pr = my_refs[(size_t)(cnt - 1 - u) * T];
-        prefetch_xy(ref_ptr(points, pool, pr.x));
-        prefetch_xy(ref_ptr(points, pool, pr.y));
-    }
-    for (uint32_t i = cnt; i-- > 0;) {
-        if (i >= PF) {
-            const uint2 pf = my_refs[(size_t)(i - PF) * T];
-            prefetch_xy(ref_ptr(points, pool, pf.x));
-            prefetch_xy(ref_ptr(points, pool, pf.y));
-            if (i > PF) prefetch_32(&my_pre[(size_t)(i - PF - 1) * T]);
+        // ---- phase 2: the additions of pairs [lo, hi), last pair first.  The next pair's points and prefix product are
+        // loaded (into registers) in the middle of the current addition, once lambda is known and Py, Qy are dead.
+        if (len) {
+            uint2 pr = my_refs[(size_t)(hi - 1) * T];
+            g1a_t p = g1a_load(ref_ptr(points, pool, pr.x)), q = g1a_load(ref_ptr(points, pool, pr.y));
+            fe_t pre = hi - 1 > lo ? fload(&my_pre[(size_t)(hi - 2) * T]) : one;
+            uint2 npr = hi - 1 > lo ? my_refs[(size_t)(hi - 2) * T] : pr;
+            for (uint32_t i = hi; i-- > lo;) {
+                // (pool sums were written by earlier rounds = earlier launches, table points never change: read-only path)
+                if (pr.x & SIGN) p.y = fneg<Q>(p.y);
+                if (pr.y & SIGN) q.y = fneg<Q>(q.y);
+                const fe_t d = fsub<Q>(q.x, p.x);
+                const bool more = i > lo;
+                const uint2 nnpr = i > lo + 1 ? my_refs[(size_t)(i - 2) * T] : npr;
+                g1a_t r, np = p, nq = q;
+                fe_t npre = one;
+                if (special_pair(p.x, q.x, d)) {
+                    r = add_slow(p, q);
+                    if (more) {
+                        np = g1a_load(ref_ptr(points, pool, npr.x));
+                        nq = g1a_load(ref_ptr(points, pool, npr.y));
+                        if (i > lo + 1) npre = fload(&my_pre[(size_t)(i - 2) * T]);
+                    }
+                } else {
+                    const fe_t inv_d = fmul<Q>(inv, pre);
+                    inv = fmul<Q>(inv, d);
+                    const fe_t lam = fmul<Q>(fsub<Q>(q.y, p.y), inv_d);
+                    const fe_t px = p.x, py = p.y, qx = q.x;
+                    if (more) {                                  // the next pair is in flight during the two products below
+                        np = g1a_load(ref_ptr(points, pool, npr.x));
+                        nq = g1a_load(ref_ptr(points, pool, npr.y));
+                        if (i > lo + 1) npre = fload(&my_pre[(size_t)(i - 2) * T]);
+                    }
+                    r.x = fsub<Q>(fsub<Q>(fsqr<Q>(lam), px), qx);
+                    r.y = fsub<Q>(fmul<Q>(lam, fsub<Q>(px, r.x)), py);
+                }
+                fstore(&pool[out_base + j0 + i].x, r.x);
+                fstore(&pool[out_base + j0 + i].y, r.y);
+                p = np; q = nq; pre = npre; pr = npr; npr = nnpr;
+            }
         }
-        const uint2 pr = my_refs[(size_t)i * T];
-        g1a_t p = g1a_load(ref_ptr(points, pool, pr.x)), q = g1a_load(ref_ptr(points, pool, pr.y));
-        // (pool results were written by earlier rounds = earlier launches, table points never change: the read-only path is safe)
-        if (pr.x & SIGN) p.y = fneg<Q>(p.y);
-        if (pr.y & SIGN) q.y = fneg<Q>(q.y);
-        const fe_t d = fsub<Q>(q.x, p.x);
-        g1a_t r;
-        if (special_pair(p.x, q.x, d)) {
-            r = add_slow(p, q);
-        } else {
-            const fe_t pre = i ? fload(&my_pre[(size_t)(i - 1) * T]) : one;
-            const fe_t inv_d = fmul<Q>(inv, pre);
-            inv = fmul<Q>(inv, d);
-            const fe_t lam = fmul<Q>(fsub<Q>(q.y, p.y), inv_d);
-            r.x = fsub<Q>(fsub<Q>(fsqr<Q>(lam), p.x), q.x);
-            r.y = fsub<Q>(fmul<Q>(lam, fsub<Q>(p.x, r.x)), p.y);
-        }
-        fstore(&pool[out_base + j0 + i].x, r.x);
-        fstore(&pool[out_base + j0 + i].y, r.y);
     }
 }
 
