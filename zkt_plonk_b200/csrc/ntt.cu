@@ -512,7 +512,9 @@ int zkb_ntt_run_batch(zkb_ctx *ctx, uint64_t *const *d_ptrs, size_t count, size_
         size_t tiles = n >> t;
         size_t smem = 2 * (T + T / 8 + 1) * 16;
         // measured (profiles/r02d_ntt_*.jsonl): the radix-4 kernel wins on 2048-element tiles (2^22: 0.94 vs 1.05 ms, nine at
-        // once 7.1 vs 8.4 ms) and loses on smaller ones, where its 216 KB of shared memory per SM leave the tile twiddles no L1
+        // once 7.1 vs 8.4 ms) and loses on smaller ones (2^20: 0.30 vs 0.26 ms) -- also when it is built for the generic
+        // kernel's occupancy (128 registers, 512 threads per SM, 84 KB of L1 left: profiles/r02o_ntt_kernel3.jsonl), so it is
+        // not the L1 that its 216 KB of shared memory per SM take away
         const bool r4_all = ctx->ntt_kernel == 2;
         rc = ZKB_OK;
         if (t == 11 && ctx->ntt_kernel != 1) rc = launch_r4<11>(ctx, a, tiles, count);
