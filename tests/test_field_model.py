@@ -31,12 +31,3 @@ def test_carry_chains_of_the_device_field_routines():
             assert m.fmaddn([(p - 1, p - 1)] * n, p) == n * (p - 1) ** 2 * rinv % p
             prs = [(rnd.choice(vals), rnd.choice(vals)) for _ in range(n)]
             assert m.fmaddn(prs, p) == sum(u * v for u, v in prs) * rinv % p
-
-
-def test_batch_affine_control_flow_model():
-    """tools/sqr/model_batch_affine.py: the lock-step / batch-inversion bookkeeping of csrc/msm_affine.cu (experimental,
-    off by default) against plain affine sums, including doublings and cancellations inside a batch."""
-    spec = importlib.util.spec_from_file_location("ba_model", os.path.join(ROOT, "tools", "sqr", "model_batch_affine.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    mod.main()

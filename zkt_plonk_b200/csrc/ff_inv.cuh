@@ -4,7 +4,7 @@
 // finv<P> (ff.cuh) is Fermat: ~380 dependent Montgomery products, all on the multiplier pipe, ~93 us as one chain.  A batch
 // inversion needs ONE inverse per CTA and step, computed by one thread while the others wait or work on something else, so
 // what matters is its latency and that it stays off the multiplier pipe: binary extended Euclid (HAC 14.61), ~530 shift /
-// subtract steps on 8 x 32-bit limbs.  Bit-exact against the XYZZ path in zkb_probe_batch_affine (profiles/r01n).
+// subtract steps on 8 x 32-bit limbs.  Bit-exact: every pair-round MSM test (tests/test_gpu_msm.py) goes through it.
 #pragma once
 #include "ff.cuh"
 
