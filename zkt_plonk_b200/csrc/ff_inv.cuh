@@ -1,9 +1,9 @@
-// ff_inv.cuh -- modular inversion on the ALU pipe (EXPERIMENTAL: used by the batch-affine probe and by the optional
-// batch-affine bucket accumulation, not by the default product path).
+// ff_inv.cuh -- modular inversion on the ALU pipe, for the batched-affine pair rounds (msm_pairs.cuh: an opt-in mode of the
+// bucket accumulation, not the default product path).
 //
 // finv<P> (ff.cuh) is Fermat: ~380 dependent Montgomery products, all on the multiplier pipe, ~93 us as one chain.  A batch
-// inversion needs ONE inverse per CTA and step, computed by one thread while the others wait or work on something else, so
-// what matters is its latency and that it stays off the multiplier pipe: binary extended Euclid (HAC 14.61), ~530 shift /
+// inversion needs ONE inverse per warp and batch, computed by one lane while the SM's other warps keep multiplying, so what
+// matters is its latency and that it stays off the multiplier pipe: binary extended Euclid (HAC 14.61), ~530 shift /
 // subtract steps on 8 x 32-bit limbs.  Bit-exact: every pair-round MSM test (tests/test_gpu_msm.py) goes through it.
 #pragma once
 #include "ff.cuh"
