@@ -1,0 +1,151 @@
+//! `GpuIpaPc`: the reference's other commitment scheme, `IPA<G, D> = InnerProductArgPC<G, D, DensePolynomial<_>>`
+//! (plonk-core/src/commitment.rs:49-86; exercised by plonk-core/src/test.rs:73-84), over BN254 G1 with Blake2s, as a `PC` type.
+//!
+//! What moves to the GPU is what IPA shares with KZG10 on this path -- the MSMs over a fixed key:
+//!   * `commit`: `comm = sum_i coeff_i * ck.comm_key[i]` (ipa_pc `cm_commit` without hiding: `rng = None`, no hiding bounds, as
+//!     plonk-core always calls it) -> the same resident-key MSM as KZG10 (`zkb_srs_load_g1` on `comm_key`, `zkb_msm_g1`);
+//!   * `HomomorphicCommitment::multi_scalar_mul` (commitment.rs:60-86) -> `zkb_msm_g1_bases`.
+//! `setup` / `trim` / `open` / `check` delegate to ark-poly-commit: `open` is a log(n)-round folding protocol whose per-round
+//! MSMs over halves of the key are NOT accelerated here (they would be `zkb_msm_g1_bases` calls plus a point-folding kernel);
+//! this is the seam, not a full IPA prover.  Associated types are InnerProductArgPC's own, so proofs keep their bytes.
+//!
+//! NOT COMPILED HERE (no rustc / cargo in the build image); signatures are ark-poly-commit 0.3.0's as recalled.
+use crate::ctx::CTX;
+use crate::kzg::{pack_points, unpack_point};
+use ark_bn254::{Fr, G1Affine};
+use ark_ff::{PrimeField, Zero};
+use ark_poly::univariate::DensePolynomial;
+use ark_poly_commit::{ipa_pc, LabeledCommitment, LabeledPolynomial, PCRandomness, PolynomialCommitment};
+use ark_std::rand::RngCore;
+use blake2::Blake2s;
+use core::ffi::c_int;
+use plonk_core::commitment::{HomomorphicCommitment, IPA};
+use std::cell::Cell;
+use zkb200_sys as sys;
+
+type Poly = DensePolynomial<Fr>;
+type Inner = IPA<G1Affine, Blake2s>;
+
+pub struct GpuIpaPc;
+
+thread_local! {
+    static RESIDENT: Cell<(usize, usize)> = Cell::new((0, 0));      // (address, length) of the comm_key resident on the GPU
+}
+
+fn ensure_resident(key: &[G1Affine]) {
+    let id = (key.as_ptr() as usize, key.len());
+    RESIDENT.with(|r| {
+        if r.get() != id {
+            CTX.with(|ctx| {
+                let xy = pack_points(key);
+                ctx.check(unsafe { sys::zkb_srs_load_g1(ctx.raw(), xy.as_ptr(), key.len()) })?;
+                ctx.check(unsafe { sys::zkb_srs_precompute(ctx.raw(), 0) })
+            })
+            .expect("zkb200: comm_key upload failed");
+            r.set(id);
+        }
+    });
+}
+
+impl PolynomialCommitment<Fr, Poly> for GpuIpaPc {
+    type UniversalParams = <Inner as PolynomialCommitment<Fr, Poly>>::UniversalParams;
+    type CommitterKey = <Inner as PolynomialCommitment<Fr, Poly>>::CommitterKey;
+    type VerifierKey = <Inner as PolynomialCommitment<Fr, Poly>>::VerifierKey;
+    type PreparedVerifierKey = <Inner as PolynomialCommitment<Fr, Poly>>::PreparedVerifierKey;
+    type Commitment = <Inner as PolynomialCommitment<Fr, Poly>>::Commitment;
+    type PreparedCommitment = <Inner as PolynomialCommitment<Fr, Poly>>::PreparedCommitment;
+    type Randomness = <Inner as PolynomialCommitment<Fr, Poly>>::Randomness;
+    type Proof = <Inner as PolynomialCommitment<Fr, Poly>>::Proof;
+    type BatchProof = <Inner as PolynomialCommitment<Fr, Poly>>::BatchProof;
+    type Error = <Inner as PolynomialCommitment<Fr, Poly>>::Error;
+
+    fn setup<R: RngCore>(max_degree: usize, num_vars: Option<usize>, rng: &mut R) -> Result<Self::UniversalParams, Self::Error> {
+        Inner::setup(max_degree, num_vars, rng)
+    }
+
+    fn trim(
+        pp: &Self::UniversalParams,
+        supported_degree: usize,
+        supported_hiding_bound: usize,
+        enforced_degree_bounds: Option<&[usize]>,
+    ) -> Result<(Self::CommitterKey, Self::VerifierKey), Self::Error> {
+        Inner::trim(pp, supported_degree, supported_hiding_bound, enforced_degree_bounds)
+    }
+
+    fn commit<'a>(
+        ck: &Self::CommitterKey,
+        polynomials: impl IntoIterator<Item = &'a LabeledPolynomial<Fr, Poly>>,
+        rng: Option<&mut dyn RngCore>,
+    ) -> Result<(Vec<LabeledCommitment<Self::Commitment>>, Vec<Self::Randomness>), Self::Error>
+    where
+        Poly: 'a,
+    {
+        let polys: Vec<_> = polynomials.into_iter().collect();
+        if rng.is_some() || polys.iter().any(|p| p.degree_bound().is_some() || p.hiding_bound().is_some()) {
+            return Inner::commit(ck, polys, rng);                  // hiding / shifted commitments: never asked for by plonk-core
+        }
+        ensure_resident(&ck.comm_key);
+        let mut comms = Vec::with_capacity(polys.len());
+        let mut rands = Vec::with_capacity(polys.len());
+        for p in polys {
+            let coeffs = &p.polynomial().coeffs;
+            let bigints: Vec<_> = coeffs.iter().map(|c| c.into_repr()).collect();
+            let (mut xy, mut inf) = ([0u64; 8], 0 as c_int);
+            CTX.with(|ctx| {
+                ctx.check(unsafe { sys::zkb_msm_g1(ctx.raw(), bigints.as_ptr() as *const u64, 0, bigints.len(), xy.as_mut_ptr(), &mut inf) })
+            })
+            .expect("zkb200: zkb_msm_g1 failed");
+            let comm = ipa_pc::Commitment { comm: unpack_point(&xy, inf), shifted_comm: None };
+            comms.push(LabeledCommitment::new(p.label().to_string(), comm, None));
+            rands.push(Self::Randomness::empty());
+        }
+        Ok((comms, rands))
+    }
+
+    fn open_individual_opening_challenges<'a>(
+        ck: &Self::CommitterKey,
+        labeled_polynomials: impl IntoIterator<Item = &'a LabeledPolynomial<Fr, Poly>>,
+        commitments: impl IntoIterator<Item = &'a LabeledCommitment<Self::Commitment>>,
+        point: &'a Fr,
+        opening_challenges: &dyn Fn(u64) -> Fr,
+        rands: impl IntoIterator<Item = &'a Self::Randomness>,
+        rng: Option<&mut dyn RngCore>,
+    ) -> Result<Self::Proof, Self::Error>
+    where
+        Poly: 'a,
+        Self::Randomness: 'a,
+        Self::Commitment: 'a,
+    {
+        Inner::open_individual_opening_challenges(ck, labeled_polynomials, commitments, point, opening_challenges, rands, rng)
+    }
+
+    fn check_individual_opening_challenges<'a>(
+        vk: &Self::VerifierKey,
+        commitments: impl IntoIterator<Item = &'a LabeledCommitment<Self::Commitment>>,
+        point: &'a Fr,
+        values: impl IntoIterator<Item = Fr>,
+        proof: &Self::Proof,
+        opening_challenges: &dyn Fn(u64) -> Fr,
+        rng: Option<&mut dyn RngCore>,
+    ) -> Result<bool, Self::Error>
+    where
+        Self::Commitment: 'a,
+    {
+        Inner::check_individual_opening_challenges(vk, commitments, point, values, proof, opening_challenges, rng)
+    }
+}
+
+impl HomomorphicCommitment<Fr> for GpuIpaPc {
+    fn multi_scalar_mul(commitments: &[Self::Commitment], scalars: &[Fr]) -> Self::Commitment {
+        let n = commitments.len().min(scalars.len());
+        let pts = pack_points(&commitments[..n].iter().map(|c| c.comm).collect::<Vec<_>>());
+        let reprs: Vec<_> = scalars[..n].iter().map(|s| s.into_repr()).collect();
+        let (mut xy, mut inf) = ([0u64; 8], 0 as c_int);
+        CTX.with(|ctx| {
+            ctx.check(unsafe { sys::zkb_msm_g1_bases(ctx.raw(), pts.as_ptr(), reprs.as_ptr() as *const u64, n, xy.as_mut_ptr(), &mut inf) })
+        })
+        .expect("zkb200: zkb_msm_g1_bases failed");
+        let _ = Fr::zero();
+        ipa_pc::Commitment { comm: unpack_point(&xy, inf), shifted_comm: None }
+    }
+}

@@ -17,7 +17,7 @@ use zkb200_sys as sys;
 pub struct GpuKZG10;
 
 /// `G1Affine` is `repr(Rust)` (x, y, infinity): repack into the ABI's x || y Montgomery limbs, identity = (0, 0).
-fn pack_points(points: &[G1Affine]) -> Vec<u64> {
+pub(crate) fn pack_points(points: &[G1Affine]) -> Vec<u64> {
     let mut out = vec![0u64; 8 * points.len()];
     for (i, p) in points.iter().enumerate() {
         if p.infinity {
@@ -29,7 +29,7 @@ fn pack_points(points: &[G1Affine]) -> Vec<u64> {
     out
 }
 
-fn unpack_point(xy: &[u64; 8], is_inf: c_int) -> G1Affine {
+pub(crate) fn unpack_point(xy: &[u64; 8], is_inf: c_int) -> G1Affine {
     if is_inf != 0 {
         return G1Affine::zero();
     }

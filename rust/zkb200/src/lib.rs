@@ -13,14 +13,18 @@
 //!                        `impl HomomorphicCommitment<Fr>` over SonicKZG10's associated types (commitment.rs:9-46); setup /
 //!                        trim / check delegate, commit / open / multi_scalar_mul run on the GPU ([`GpuKZG10`] helpers).
 //!                        rust/patches/instance.rs.patch swaps it (and `GpuDomain`) into bin/src/instance.rs:67-84.
+//!   * [`GpuIpaPc`]       the same seam for the reference's other scheme, `IPA<G1Affine, Blake2s>` (commitment.rs:49-86):
+//!                        `commit` and `multi_scalar_mul` on the GPU, `open` / `check` delegated to ark-poly-commit.
 mod ctx;
 mod domain;
+mod ipa;
 mod kzg;
 mod pc;
 mod prover;
 
 pub use ctx::{Ctx, Error};
 pub use domain::GpuDomain;
+pub use ipa::GpuIpaPc;
 pub use kzg::GpuKZG10;
 pub use pc::GpuKZG10Pc;
 pub use prover::{prove_native, verify_native, NativeKey, Transcript};
