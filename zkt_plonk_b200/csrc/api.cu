@@ -126,8 +126,6 @@ int zkb_ctx_create(int device, zkb_ctx **out) {
     const char *mode = getenv("ZKB_MSM_MODE");                  // pair rounds (msm_pairs.cuh): "0".."6", or "-1" / "auto"
     if (mode && mode[0] >= '0' && mode[0] <= '6' && mode[1] == 0) ctx->msm_mode = mode[0] - '0';
     else if (mode && (!strcmp(mode, "-1") || !strcmp(mode, "auto"))) ctx->msm_mode = -1;
-    const char *so = getenv("ZKB_MSM_SORT");                    // "0": the global-atomic counting sort everywhere (A/B measurements)
-    if (so && so[0] == '0' && so[1] == 0) ctx->msm_sort = 0;
     const char *pf = getenv("ZKB_MSM_PF");                      // L2 prefetch distance of the accumulation's gathers (0..16)
     if (pf && atoi(pf) >= 0 && atoi(pf) <= 16) ctx->msm_prefetch = atoi(pf);
     const char *nk = getenv("ZKB_NTT_KERNEL");                  // "0" / "1" / "2": see zkb_ntt_set_kernel

@@ -37,7 +37,6 @@ struct zkb_ctx {
     size_t srs_n = 0;
     void *msm_state = nullptr;   // opaque (owned by msm.cu)
     int msm_force_c = 0;         // 0 = cost model picks the window size
-    int msm_sort = 1;            // 1: two-pass partitioned sort for large MSMs (shared-memory atomics), 0: global-atomic counting sort
     int msm_prefetch = 0;        // L2 prefetch distance (points) of the bucket accumulation's gathers; 0 = none (measured best)
     int msm_mode = 0;            // batched-affine pair rounds in front of the XYZZ accumulation (msm_pairs.cuh): 0 = none,
                                  // 1..6 = that many, -1 = chosen per MSM from the mean bucket load

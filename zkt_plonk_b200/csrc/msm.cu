@@ -62,17 +62,12 @@ struct MsmPlan {
     uint32_t seg;                        // max points per accumulation task
     uint32_t id_base, id_stride;         // fixed-base: entry id = id_base + w * id_stride + i
     pairs::Plan pp;                      // pair rounds in front of the XYZZ accumulation (pp.rounds == 0: none)
-    bool part_sort;                      // two-pass partitioned sort (large MSMs) instead of the global-atomic counting sort
-    uint32_t part_n, part_ctas, part_per_cta;   // partitions, CTAs of pass A, scalars per CTA
 };
 
 struct MsmWs {                           // carved out of ctx->msm_ws
     uint32_t *counts, *starts, *cursor, *ntasks, *task_base, *sorted;
     uint32_t *scan_tmp;                  // block sums for the scans
     uint32_t *size_hist, *size_cursor;   // SEG + 1 bins
-    uint32_t *part_hist;                 // partitioned sort: [partition][CTA] entry counts, scanned in place (+ the total)
-    uint2 *records;                      // partitioned sort: (entry, bucket) records grouped by partition
-    uint32_t *part_scan_tmp;
     uint32_t *misc;                      // [0] heavy buckets, [1] total tasks, [2] chunk items, [3] chunk_out slots, [4] multi-chunk buckets
     uint32_t *heavy_list;                // buckets cut into more than one task
     uint32_t *heavy_slot;                // per heavy bucket: first slot in chunk_out, or ~0 when it has a single chunk
@@ -270,119 +265,6 @@ int exclusive_scan(zkb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, 
     scan_apply_kernel<<<ntiles, 256, 0, ctx->stream>>>(in, n, tmp, out);
     ZKB_CUDA(ctx, cudaGetLastError());
     return ZKB_OK;
-}
-
-// ------------------------------------------------------------------ partitioned counting sort (large MSMs)
-// The sort above pays one global atomic per entry twice (count, scatter): 27 M L2 atomics and 13.6 M scattered 4-byte writes
-// at 2^20 points.  Here the bucket range is cut into partitions of PART_BUCKETS buckets and the entries are sorted in two
-// passes whose atomics are all in shared memory:
-//   pass A  a CTA takes a run of scalars, histograms its entries per PARTITION in shared memory (part_count), a scan over
-//           [partition][CTA] gives every (partition, CTA) its slice of the record array, and the CTA writes 8-byte records
-//           (bucket | entry) into its slices (part_scatter);
-//   pass B  one CTA per partition counts its records per bucket in shared memory, scans the 2048 counters, writes counts[]
-//           and starts[] of its buckets, and places the entries (part_place): all traffic of a partition stays inside its own
-//           slices of `records` and `sorted`.
-// Lanes of a warp that hit the same bucket in pass B are served by one shared-memory atomic (match.any): a pile of equal
-// digits (every scalar equal to one) would otherwise serialise on one counter.
-constexpr uint32_t PART_BUCKETS_LOG = 11, PART_BUCKETS = 1u << PART_BUCKETS_LOG;
-constexpr uint32_t PART_MAX = 1024;          // partitions (shared-memory histogram of pass A)
-constexpr uint32_t PART_A_THREADS = 256, PART_B_THREADS = 512;
-
-__global__ void __launch_bounds__(PART_A_THREADS) part_count_kernel(const uint4 *scalars, uint32_t n, uint32_t per_cta, uint32_t c, uint32_t W,
-                                                                   uint32_t wide, uint32_t gstride, uint32_t nparts, uint32_t *part_hist) {
-    __shared__ uint32_t h[PART_MAX];
-    for (uint32_t k = threadIdx.x; k < nparts; k += PART_A_THREADS) h[k] = 0;
-    __syncthreads();
-    const uint32_t lo = blockIdx.x * per_cta, hi = min(n, lo + per_cta);
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += PART_A_THREADS) {
-        uint32_t s[8];
-        load_scalar(scalars, i, s);
-        for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t b, bool) { atomicAdd(&h[(w * gstride + b) >> PART_BUCKETS_LOG], 1u); });
-    }
-    __syncthreads();
-    for (uint32_t k = threadIdx.x; k < nparts; k += PART_A_THREADS) part_hist[(size_t)k * gridDim.x + blockIdx.x] = h[k];
-}
-
-__global__ void __launch_bounds__(PART_A_THREADS) part_scatter_kernel(const uint4 *scalars, uint32_t n, uint32_t per_cta, uint32_t c, uint32_t W,
-                                                                     uint32_t wide, uint32_t gstride, uint32_t id_base, uint32_t id_stride,
-                                                                     uint32_t nparts, const uint32_t *part_off, uint2 *records) {
-    __shared__ uint32_t cur[PART_MAX];
-    for (uint32_t k = threadIdx.x; k < nparts; k += PART_A_THREADS) cur[k] = part_off[(size_t)k * gridDim.x + blockIdx.x];
-    __syncthreads();
-    const uint32_t lo = blockIdx.x * per_cta, hi = min(n, lo + per_cta);
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += PART_A_THREADS) {
-        uint32_t s[8];
-        load_scalar(scalars, i, s);
-        for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t b, bool neg) {
-            const uint32_t gb = w * gstride + b;
-            const uint32_t slot = atomicAdd(&cur[gb >> PART_BUCKETS_LOG], 1u);
-            records[slot] = make_uint2((id_base + w * id_stride + i) | (neg ? SIGN_BIT : 0u), gb);
-        });
-    }
-}
-
-// one CTA per partition p: records [part_off[p * ncta], part_off[(p + 1) * ncta]) (the scan has one extra element: the total)
-__global__ void __launch_bounds__(PART_B_THREADS) part_place_kernel(const uint2 *__restrict__ records, const uint32_t *__restrict__ part_off,
-                                                                   uint32_t ncta, uint32_t nb, uint32_t *__restrict__ counts,
-                                                                   uint32_t *__restrict__ starts, uint32_t *__restrict__ sorted) {
-    __shared__ uint32_t cnt[PART_BUCKETS], sm_scan[16];
-    const uint32_t p = blockIdx.x, b0 = p << PART_BUCKETS_LOG, lane = threadIdx.x & 31;
-    const uint32_t rlo = part_off[(size_t)p * ncta], rhi = part_off[(size_t)(p + 1) * ncta];
-    for (uint32_t k = threadIdx.x; k < PART_BUCKETS; k += PART_B_THREADS) cnt[k] = 0;
-    __syncthreads();
-    // whole warps walk the records together (match.any needs every lane of the mask)
-    const uint32_t span = ((rhi - rlo + 31) / 32) * 32;
-    for (uint32_t k = threadIdx.x; k < span; k += PART_B_THREADS) {
-        const bool live = rlo + k < rhi;
-        const uint32_t lb = live ? records[rlo + k].y - b0 : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, lb);
-        if (live && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&cnt[lb], (uint32_t)__popc(peers));
-    }
-    __syncthreads();
-    // exclusive scan of the 2048 counters: 4 per thread, then across the 512 threads
-    uint32_t v[4], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { v[k] = cnt[4 * threadIdx.x + k]; sum += v[k]; }
-    uint32_t x = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-        if (lane >= (uint32_t)d) x += y;
-    }
-    if (lane == 31) sm_scan[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t t = threadIdx.x < PART_B_THREADS / 32 ? sm_scan[threadIdx.x] : 0;
-#pragma unroll
-        for (int d = 1; d < 16; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, t, d);
-            if (lane >= (uint32_t)d) t += y;
-        }
-        if (threadIdx.x < PART_B_THREADS / 32) sm_scan[threadIdx.x] = t;      // inclusive totals of the warps
-    }
-    __syncthreads();
-    uint32_t ex = x - sum + ((threadIdx.x >> 5) ? sm_scan[(threadIdx.x >> 5) - 1] : 0);
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t b = b0 + 4 * threadIdx.x + k;
-        if (b < nb) { counts[b] = v[k]; starts[b] = rlo + ex; }
-        cnt[4 * threadIdx.x + k] = rlo + ex;                                   // becomes the bucket's cursor
-        ex += v[k];
-    }
-    __syncthreads();
-    for (uint32_t k = threadIdx.x; k < span; k += PART_B_THREADS) {
-        const bool live = rlo + k < rhi;
-        uint2 rec = make_uint2(0, 0);
-        if (live) rec = records[rlo + k];
-        const uint32_t lb = live ? rec.y - b0 : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, lb);
-        const uint32_t leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (live && lane == leader) base = atomicAdd(&cnt[lb], (uint32_t)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (live) sorted[base + __popc(peers & ((1u << lane) - 1))] = rec.x;
-    }
 }
 
 // ------------------------------------------------------------------ tasks
@@ -747,7 +629,7 @@ uint32_t pick_pair_rounds(int mode, uint64_t entries, uint64_t nb, uint64_t max_
     return (uint32_t)std::max(0, std::min(r, 4));
 }
 
-MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset, int sm_count, int pair_mode = 0, int sort_mode = 1) {
+MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset, int sm_count, int pair_mode = 0) {
     MsmPlan pl;
     if (fb) {
         pl.c = fb->c; pl.W = fb->W; pl.G = 1; pl.wide = fb->wide;
@@ -784,12 +666,6 @@ MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset, int
     uint32_t seg = 64;
     while (seg < 2.5 * mean && seg < SEG_MAX) seg <<= 1;
     pl.seg = seg;
-    // partitioned sort from 2^17 entries on (below that the MSM is launch-bound and the plain sort has fewer launches)
-    pl.part_n = (uint32_t)((pl.nbuckets + PART_BUCKETS - 1) / PART_BUCKETS);
-    pl.part_sort = sort_mode != 0 && (uint64_t)n * pl.W >= (1ull << 17) && pl.part_n >= 2 && pl.part_n <= PART_MAX;
-    pl.part_ctas = (uint32_t)std::min<uint64_t>((n + 1023) / 1024, (uint64_t)sm_count * 8);
-    if (pl.part_ctas == 0) pl.part_ctas = 1;
-    pl.part_per_cta = (uint32_t)((n + pl.part_ctas - 1) / pl.part_ctas);
     const uint64_t max_id = fb ? (uint64_t)pl.id_base + (uint64_t)(pl.W - 1) * pl.id_stride + n : n;
     pl.pp = pairs::make_plan(pick_pair_rounds(pair_mode, (uint64_t)n * pl.W, pl.nbuckets, max_id), (uint64_t)n * pl.W, pl.nbuckets,
                              (uint64_t)sm_count * 4 * pairs::THREADS);
@@ -812,12 +688,6 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
            o_cout = take((max_tasks / (HEAVY_CHUNK / 2) + 4) * sizeof(g1x_t)),
            o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)), o_bval = take(nb * sizeof(g1x_t)),
            o_red0 = take(pl.red_buf_elems[0] * sizeof(g1x_t)), o_red1 = take(pl.red_buf_elems[1] * sizeof(g1x_t));
-    size_t o_phist = 0, o_pscan2 = 0, o_recs = 0;
-    if (pl.part_sort) {
-        o_phist = take(((size_t)pl.part_n * pl.part_ctas + 1) * 4);
-        o_pscan2 = take((((size_t)pl.part_n * pl.part_ctas + 1) / SCAN_TILE + 2) * 4);
-        o_recs = take(entries * 8 + 8);
-    }
     size_t o_pr[2] = {0, 0}, o_pc[2] = {0, 0}, o_ps[2] = {0, 0}, o_pk = 0, o_pscan = 0, o_prefs = 0, o_ppre = 0, o_pool = 0;
     if (pl.pp.rounds) {
         for (int k = 0; k < 2; ++k) {
@@ -842,7 +712,6 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
     ws.chunk_out = (g1x_t *)(p + o_cout);
     ws.task_out = (g1x_t *)(p + o_out); ws.bucket_val = (g1x_t *)(p + o_bval);
     ws.red_buf[0] = (g1x_t *)(p + o_red0); ws.red_buf[1] = (g1x_t *)(p + o_red1);
-    ws.part_hist = (uint32_t *)(p + o_phist); ws.part_scan_tmp = (uint32_t *)(p + o_pscan2); ws.records = (uint2 *)(p + o_recs);
     if (pl.pp.rounds) {
         for (int k = 0; k < 2; ++k) {
             ws.pw.refs[k] = (uint32_t *)(p + o_pr[k]); ws.pw.counts[k] = (uint32_t *)(p + o_pc[k]); ws.pw.starts[k] = (uint32_t *)(p + o_ps[k]);
@@ -868,7 +737,7 @@ MsmState *state(zkb_ctx *ctx) {
 int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, size_t n, int force_c, const FixedBase *fb,
                 size_t offset, MsmPlan *plan_out, int slot_id = 0, bool pipelined = false) {
     if (n >= (1ull << 31)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n must be < 2^31");
-    MsmPlan pl = make_plan(n, force_c, fb, offset, ctx->sm_count, ctx->msm_mode, ctx->msm_sort);
+    MsmPlan pl = make_plan(n, force_c, fb, offset, ctx->sm_count, ctx->msm_mode);
     if ((uint64_t)n * pl.W >= (1ull << 32)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n * windows must be < 2^32");
     MsmWs ws;
     uint64_t max_tasks, max_heavy;
@@ -901,28 +770,16 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     st->last_entries = (uint64_t)n * pl.W; st->last_c = pl.c; st->last_W = pl.W;
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[0], s));
 
+    ZKB_CUDA(ctx, cudaMemsetAsync(ws.counts, 0, (size_t)nb * 4, s));
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.size_hist, 0, (SEG_MAX + 1) * 4, s));
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.misc, 0, 64, s));
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.bucket_val, 0, (size_t)nb * sizeof(g1x_t), s));
-    if (pl.part_sort && n32) {
-        const uint32_t nh = pl.part_n * pl.part_ctas + 1;            // + 1: the scan leaves the total after the last slice
-        ZKB_CUDA(ctx, cudaMemsetAsync(ws.part_hist + (nh - 1), 0, 4, s));
-        part_count_kernel<<<pl.part_ctas, PART_A_THREADS, 0, s>>>(d_scalars, n32, pl.part_per_cta, pl.c, pl.W, pl.wide, gstride, pl.part_n,
-                                                                  ws.part_hist);
-        rc = exclusive_scan(ctx, ws.part_hist, ws.part_hist, nh, ws.part_scan_tmp, nullptr);
-        if (rc) return rc;
-        part_scatter_kernel<<<pl.part_ctas, PART_A_THREADS, 0, s>>>(d_scalars, n32, pl.part_per_cta, pl.c, pl.W, pl.wide, gstride, pl.id_base,
-                                                                    pl.id_stride, pl.part_n, ws.part_hist, ws.records);
-        part_place_kernel<<<pl.part_n, PART_B_THREADS, 0, s>>>(ws.records, ws.part_hist, pl.part_ctas, nb, ws.counts, ws.starts, ws.sorted);
-    } else {
-        ZKB_CUDA(ctx, cudaMemsetAsync(ws.counts, 0, (size_t)nb * 4, s));
-        if (n32) msm_count_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, ws.counts);
-        rc = exclusive_scan(ctx, ws.counts, ws.starts, nb, ws.scan_tmp, nullptr);
-        if (rc) return rc;
-        ZKB_CUDA(ctx, cudaMemcpyAsync(ws.cursor, ws.starts, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
-        if (n32) msm_scatter_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, pl.id_base, pl.id_stride,
-                                                                      ws.cursor, ws.sorted);
-    }
+    if (n32) msm_count_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, ws.counts);
+    rc = exclusive_scan(ctx, ws.counts, ws.starts, nb, ws.scan_tmp, nullptr);
+    if (rc) return rc;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ws.cursor, ws.starts, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
+    if (n32) msm_scatter_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, pl.id_base, pl.id_stride,
+                                                                  ws.cursor, ws.sorted);
     // ---- batched-affine pair rounds (msm_pairs.cuh): each halves every bucket; the XYZZ accumulation below then works on
     // what is left, through the references / counts / starts of the last round
     const g1a_t *pool = nullptr;
@@ -987,7 +844,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], ts));
     ZKB_CUDA(ctx, cudaGetLastError());
     st->ev_valid = true;
-    ctx->launches += 16 + pl.red_levels + (pl.part_sort ? 1 : 0); // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduction levels
+    ctx->launches += 16 + pl.red_levels; // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduction levels
     // the last level's output is [stream][group][1]: stream 0 = plain total, stream 1 + k = total of A_k
     ZKB_CUDA(ctx, cudaMemcpyAsync(sl.pinned, pl.red_levels ? (const void *)level_in : (const void *)ws.bucket_val, out_bytes,
                                   cudaMemcpyDeviceToHost, ts));
