@@ -175,6 +175,10 @@ ZKB_API int zkb_quotient_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t 
 ZKB_API int zkb_l1_coset_dev(zkb_ctx *ctx, unsigned log_n, uint64_t *out_dev);
 /* DensePolynomial::evaluate (linearization_poly.rs:55-75): out = sum_k coeffs[k] z^k; z, out on the host. Synchronous. */
 ZKB_API int zkb_poly_eval_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, size_t n, const uint64_t z[4], uint64_t out[4]);
+/* The same for k <= 16 polynomials in one launch pair and one host round trip (the 12 openings of prove.rs:320-345 share two
+ * points): points_host and out_host hold k x 4 words; polynomial j is evaluated at points_host[j]. Synchronous. */
+ZKB_API int zkb_poly_eval_many_dev(zkb_ctx *ctx, size_t k, const uint64_t *const *polys_dev, const size_t *lens,
+                           const uint64_t *points_host, uint64_t *out_host);
 /* out[i] = sum_{j<k} scalars[j] * polys[j][i], i < out_len (k <= 16; shorter polynomials are zero-extended):
  * the axpy chains of linearization_poly.rs:77-111 and SonicKZG10::open's eta-combination. */
 ZKB_API int zkb_poly_lincomb_dev(zkb_ctx *ctx, size_t k, const uint64_t *const *polys_dev, const size_t *lens,

@@ -179,6 +179,30 @@ def test_poly_eval_lincomb_divide(ctx, n):
     assert ints(to_host(out)) == [(si[0] * x + si[1] * y) % p for x, y in zip(ci, oi)]
 
 
+def test_poly_eval_many_matches_single_evaluations(ctx):
+    """the batched evaluation of round 5 (12 openings at two points): every result equals the single-polynomial call and
+    Horner on integers; polynomials of different lengths (one empty, one a single coefficient), three distinct points."""
+    p = pyref.R_MOD
+    lens = [100003, 4096, 1, 0, 70001, 17, 4096, 100003, 2, 33333, 65536, 5]
+    rng = random.Random(99)
+    pts_i = [rng.randrange(p) for _ in range(3)]
+    which = [0, 0, 1, 2, 1, 0, 2, 1, 0, 0, 1, 2]
+    polys, ci = [], []
+    for k, n in enumerate(lens):
+        c = rand_fr_mont(max(n, 1), 3100 + k)
+        polys.append(to_dev(c))
+        ci.append(ints(c)[:n])
+    pts = np.stack([fr_mont_int(pts_i[w]) for w in which])
+    got = ctx.poly_eval_many_dev(polys, lens, pts)
+    for k, n in enumerate(lens):
+        acc = 0
+        for c in reversed(ci[k]):
+            acc = (acc * pts_i[which[k]] + c) % p
+        assert ints(got[k].reshape(1, 4))[0] == acc, k
+        if n:
+            assert np.array_equal(got[k], ctx.poly_eval_dev(polys[k], n, pts[k])), k
+
+
 def test_add_blinders_keeps_domain_evaluations(ctx):
     """prove.rs:498-544: blinding changes the polynomial but not its evaluations over the domain."""
     import torch

@@ -75,6 +75,7 @@ def load():
         "zkb_quotient_evals_dev": (i, [vp, u, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), vp]),
         "zkb_l1_coset_dev": (i, [vp, u, vp]),
         "zkb_poly_eval_dev": (i, [vp, vp, sz, vp, vp]),
+        "zkb_poly_eval_many_dev": (i, [vp, sz, vp, vp, vp, vp]),
         "zkb_poly_lincomb_dev": (i, [vp, sz, ctypes.POINTER(vp), ctypes.POINTER(sz), vp, vp, sz]),
         "zkb_poly_divide_linear_dev": (i, [vp, vp, sz, vp, vp, vp]),
         "zkb_poly_add_blinders_dev": (i, [vp, vp, sz, vp, sz]),

@@ -274,6 +274,16 @@ class Context:
         self._check(self._lib.zkb_poly_eval_dev(self._h, _dev_ptr(coeffs), n, _host_ptr(z), _host_ptr(out)))
         return out
 
+    def poly_eval_many_dev(self, polys, lens, points):
+        """polys[j] (device, lens[j] coefficients) evaluated at points[j] (k x 4 words, Montgomery form); returns k x 4 words."""
+        k = len(polys)
+        P = (ctypes.c_void_p * k)(*[_dev_ptr(t).value for t in polys])
+        L = (ctypes.c_size_t * k)(*lens)
+        pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(k, 4)
+        out = np.zeros((k, 4), dtype=np.uint64)
+        self._check(self._lib.zkb_poly_eval_many_dev(self._h, k, P, L, _host_ptr(pts), _host_ptr(out)))
+        return out
+
     def poly_lincomb_dev(self, polys, lens, scalars, out, out_len):
         k = len(polys)
         P = (ctypes.c_void_p * k)(*[_dev_ptr(t).value for t in polys])

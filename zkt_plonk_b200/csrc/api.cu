@@ -141,7 +141,7 @@ void zkb_ctx_destroy(zkb_ctx *ctx) {
     for (auto &kv : ctx->tables) cudaFree(kv.second.p);
     DevBuf *bufs[] = {&ctx->ntt_scratch, &ctx->stage, &ctx->ptr_stage, &ctx->srs, &ctx->poly_ws};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
-    if (ctx->gp_flag) cudaFree(ctx->gp_flag);
+    if (ctx->len_slot) cudaFree(ctx->len_slot);
     zkb_msm_release(ctx);
     zkb_comm_release(ctx);
     delete ctx;

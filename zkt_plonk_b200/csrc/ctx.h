@@ -55,7 +55,8 @@ struct zkb_ctx {
 
     // ---- elementwise / scan kernels (poly.cu)
     DevBuf poly_ws;
-    uint32_t *gp_flag = nullptr; // device flag: a grand product met a zero denominator
+    int gp_failed = 0;           // the last grand product met a zero denominator
+    unsigned long long *len_slot = nullptr;   // device word of zkb_poly_effective_len_dev
 };
 
 #define ZKB_CUDA(ctx, call)                                                                   \

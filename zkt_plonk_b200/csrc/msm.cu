@@ -834,9 +834,10 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
         const uint32_t m_in = pl.red_m[l], m_out = pl.red_m[l + 1];
         dim3 grid((m_out + RED_THREADS - 1) / RED_THREADS, l + 1, pl.G);
         g1x_t *level_out = ws.red_buf[l & 1];
-        // (measured and dropped, profiles/r02f_msm_coop.jsonl: binary levels with four lanes per addition and the last levels
-        // fused into one CTA -- 0.50 instead of 0.43 ms at 2^19 buckets: a level costs its launch gap, not its addition, and
-        // the wide early levels are throughput-bound, where four lanes per addition do 2.5x the work)
+        // (measured and dropped: profiles/r02f_msm_coop.jsonl -- binary levels with four lanes per addition, 0.50 instead of
+        // 0.43 ms at 2^19 buckets; profiles/r02v_msm_tail.jsonl -- the last ten levels as ONE launch of masked tree sums over the
+        // 1024 partial sums per stream, 0.429 vs 0.429 ms: a level costs the ~9 us of its one dependent XYZZ addition in a
+        // lone warp, not its launch)
         if (pl.red_r[l] != 2) msm_wsum_level_kernel<true><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, pl.red_r[l], l, level_out);
         else msm_wsum_level_kernel<false><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, 2, l, level_out);
         level_in = level_out;

@@ -195,52 +195,49 @@ __global__ void __launch_bounds__(256) z2_terms_kernel(Z2Args p, uint4 *num, uin
     fstore(den + 2 * (size_t)i, fmul<F>(d0, d1));
 }
 
-// slot <- slot^-1 (one thread; the only inversion of a grand product).  flag[0] = 1 if the input was zero.
-__global__ void fr_invert_one_kernel(uint4 *slot, uint32_t *flag) {
-    fe_t v = fload(slot);
-    if (fis_zero<F>(v)) { flag[0] = 1; return; }     // the reference panics here (inverse().unwrap())
-    fstore(slot, finv<F>(v));
-}
-
 // z[0] = 1; z[i+1] = prefix_num[i] * suffix_den[i+1] * total_den^-1
-__global__ void __launch_bounds__(256) grand_product_combine_kernel(const uint4 *pnum, const uint4 *sden, const uint4 *tinv,
+__global__ void __launch_bounds__(256) grand_product_combine_kernel(const uint4 *pnum, const uint4 *sden, const fe_t tinv,
                                                                     uint32_t n, uint4 *z) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (i == 0) { fstore(z, fone<F>()); return; }
     fe_t v = fmul<F>(fload_ro(pnum + 2 * (size_t)(i - 1)), fload_ro(sden + 2 * (size_t)i));
-    fstore(z + 2 * (size_t)i, fmul<F>(v, fload_ro(tinv)));
+    fstore(z + 2 * (size_t)i, fmul<F>(v, tinv));
 }
 
-struct GpWs { uint4 *num, *den, *tiles_a, *tiles_b; uint32_t *flag; };
+struct GpWs { uint4 *num, *den, *tiles_a, *tiles_b; };
 
 int gp_workspace(zkb_ctx *ctx, size_t n, GpWs &w) {
     size_t ntiles = (n + SC_TILE - 1) / SC_TILE + 2;
     size_t bytes = 2 * n * 32 + 2 * ntiles * 32;
     int rc = zkb_reserve(ctx, ctx->poly_ws, bytes);
     if (rc) return rc;
-    if (!ctx->gp_flag) ZKB_CUDA(ctx, cudaMalloc((void **)&ctx->gp_flag, 256));
     char *p = (char *)ctx->poly_ws.p;
     w.num = (uint4 *)p; p += n * 32;
     w.den = (uint4 *)p; p += n * 32;
     w.tiles_a = (uint4 *)p; p += ntiles * 32;
     w.tiles_b = (uint4 *)p;
-    w.flag = ctx->gp_flag;
     return ZKB_OK;
 }
 
-// shared tail of z1 / z2 once num and den are materialised
+fe_t dev_fe(const host::Fe &f);
+
+// shared tail of z1 / z2 once num and den are materialised.  The one inversion of a grand product (of the total of the
+// denominators) is done on the HOST: a lone GPU thread needs 151 us for the Fermat chain (profiles/r02t_trace_2^18.jsonl),
+// the 32-byte round trip and the host's chain ~35 us, and the zero-denominator check comes with it.
 int grand_product_finish(zkb_ctx *ctx, const GpWs &w, size_t n, uint4 *out) {
     uint32_t ntiles = (uint32_t)((n + SC_TILE - 1) / SC_TILE);
-    ZKB_CUDA(ctx, cudaMemsetAsync(w.flag, 0, 4, ctx->stream));
     int rc = fr_scan<0, 0>(ctx, w.num, w.num, n, w.tiles_a);         // inclusive prefix products of num
     if (rc) return rc;
     rc = fr_scan<0, 1>(ctx, w.den, w.den, n, w.tiles_b);             // inclusive suffix products of den
     if (rc) return rc;
-    fr_invert_one_kernel<<<1, 1, 0, ctx->stream>>>(w.tiles_b + 2 * (size_t)ntiles, w.flag);
-    grand_product_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(w.num, w.den, w.tiles_b + 2 * (size_t)ntiles,
-                                                                                      (uint32_t)n, out);
-    ctx->launches += 2;
+    host::Fe total;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(total.l, w.tiles_b + 2 * (size_t)ntiles, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->gp_failed = (total.l[0] | total.l[1] | total.l[2] | total.l[3]) == 0;   // the reference panics here (inverse().unwrap())
+    const host::Fe tinv = ctx->gp_failed ? total : host::inv(total, host::FR);
+    grand_product_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(w.num, w.den, dev_fe(tinv), (uint32_t)n, out);
+    ctx->launches += 1;
     ZKB_CUDA(ctx, cudaGetLastError());
     return ZKB_OK;
 }
@@ -434,6 +431,71 @@ struct LcArgs {
     uint32_t k;
 };
 
+// Several polynomials at once (the 12 openings of round 5 share two points): blockIdx.y selects the polynomial, its point
+// and its table; partial sums of polynomial k start at a.first[k].
+struct EvArgs {
+    const uint4 *p[LC_MAX];
+    unsigned long long len[LC_MAX];
+    fe_t z[LC_MAX];
+    uint32_t tab[LC_MAX];      // offset (in field elements) of the point's two-level table
+    uint32_t first[LC_MAX + 1];
+    uint32_t s;
+};
+
+__global__ void __launch_bounds__(256) poly_eval_many_partial_kernel(const __grid_constant__ EvArgs a, const uint4 *tabs, uint4 *partial) {
+    __shared__ fe_t sm[8];
+    const uint32_t k = blockIdx.y;
+    const size_t n = a.len[k];
+    if ((size_t)blockIdx.x * 256 * EV_K >= n) return;                  // uniform over the CTA
+    const uint4 *coeffs = a.p[k];
+    const fe_t z = a.z[k];
+    size_t base = ((size_t)blockIdx.x * 256 + threadIdx.x) * EV_K;
+    fe_t acc = fzero<F>();
+    if (base < n) {
+        int cnt = (int)(n - base < (size_t)EV_K ? n - base : (size_t)EV_K);
+        for (int c = cnt - 1; c >= 0; --c) acc = fadd<F>(fmul<F>(acc, z), fload_ro(coeffs + 2 * (base + c)));   // Horner
+        acc = fmul<F>(acc, pow2lvl(tabs + 2 * (size_t)a.tab[k], a.s, base));
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        fe_t o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = __shfl_down_sync(0xffffffffu, acc.v[i], d);
+        acc = fadd<F>(acc, o);
+    }
+    if (lane == 0) sm[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fe_t t = sm[0];
+        for (int w = 1; w < 8; ++w) t = fadd<F>(t, sm[w]);
+        fstore(partial + 2 * ((size_t)a.first[k] + blockIdx.x), t);
+    }
+}
+
+// out[k] = sum of partial[first[k] .. first[k+1])
+__global__ void __launch_bounds__(256) fr_sum_many_kernel(const __grid_constant__ EvArgs a, const uint4 *partial, uint4 *out) {
+    __shared__ fe_t sm[8];
+    const uint32_t k = blockIdx.x, lo = a.first[k], hi = a.first[k + 1];
+    fe_t acc = fzero<F>();
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) acc = fadd<F>(acc, fload(partial + 2 * (size_t)i));
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        fe_t o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = __shfl_down_sync(0xffffffffu, acc.v[i], d);
+        acc = fadd<F>(acc, o);
+    }
+    if (lane == 0) sm[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fe_t t = sm[0];
+        for (int w = 1; w < 8; ++w) t = fadd<F>(t, sm[w]);
+        fstore(out + 2 * (size_t)k, t);
+    }
+}
+
 // out[i] = sum_k s_k * p_k[i]  (coefficients past a polynomial's length are zero)
 __global__ void __launch_bounds__(256) poly_lincomb_kernel(const __grid_constant__ LcArgs a, uint4 *out, size_t out_len) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -561,14 +623,7 @@ int zkb_z2_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t delta[4], cons
 }
 
 // 1 if the last grand product on this context met a zero denominator (the reference would have panicked)
-int zkb_grand_product_failed(zkb_ctx *ctx) {
-    if (!ctx) return 0;
-    uint32_t flag = 0;
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
-    if (!ctx->gp_flag) return 0;
-    if (cudaMemcpy(&flag, ctx->gp_flag, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return (int)flag;
-}
+int zkb_grand_product_failed(zkb_ctx *ctx) { return ctx ? ctx->gp_failed : 0; }
 
 int zkb_quotient_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t challenges[20], const uint64_t *const wit[9],
                            const uint64_t *const epk[11], uint64_t *out_dev) {
@@ -662,6 +717,56 @@ int zkb_poly_eval_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, size_t n, const 
     return ZKB_OK;
 }
 
+// k evaluations with one launch pair and ONE host round trip: round 5 evaluates 12 polynomials at xi or xi * w, and a round
+// trip per evaluation (two table kernels, the partial sums, the total, a 32-byte download, a synchronise) cost 65 us each
+// on a B200 (profiles/r02t_trace_2^18.jsonl) against 14 us of arithmetic.  Equal points share a table.
+int zkb_poly_eval_many_dev(zkb_ctx *ctx, size_t k, const uint64_t *const *polys_dev, const size_t *lens, const uint64_t *points_host,
+                           uint64_t *out_host) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (k == 0 || k > (size_t)LC_MAX) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_poly_eval_many_dev: 1 <= k <= 16");
+    if (!polys_dev || !lens || !points_host || !out_host) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_poly_eval_many_dev: null argument");
+    EvArgs a;
+    size_t max_len = 0;
+    uint32_t max_blocks = 0, total_blocks = 0;
+    for (size_t i = 0; i < k; ++i) {
+        if (!polys_dev[i] && lens[i]) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_poly_eval_many_dev: null polynomial");
+        a.p[i] = (const uint4 *)polys_dev[i];
+        a.len[i] = lens[i];
+        memcpy(a.z[i].v, points_host + 4 * i, 32);
+        const uint32_t nb = (uint32_t)((lens[i] + 256 * EV_K - 1) / (256 * EV_K));
+        a.first[i] = total_blocks;
+        total_blocks += nb;
+        max_blocks = nb > max_blocks ? nb : max_blocks;
+        max_len = lens[i] > max_len ? lens[i] : max_len;
+    }
+    a.first[k] = total_blocks;
+    if (max_len == 0) { memset(out_host, 0, k * 32); return ZKB_OK; }
+    unsigned lm = ceil_log2_sz(max_len);
+    if (lm < 1) lm = 1;
+    const size_t tab_elems = ((size_t)1 << ((lm + 1) / 2)) + ((size_t)1 << (lm - (lm + 1) / 2));
+    size_t distinct[LC_MAX], n_distinct = 0;                            // index of the first polynomial with that point
+    for (size_t i = 0; i < k; ++i) {
+        size_t d = 0;
+        while (d < n_distinct && memcmp(points_host + 4 * distinct[d], points_host + 4 * i, 32)) ++d;
+        if (d == n_distinct) distinct[n_distinct++] = i;
+        a.tab[i] = (uint32_t)(d * tab_elems);
+    }
+    int rc = zkb_reserve(ctx, ctx->poly_ws, (n_distinct * tab_elems + total_blocks + k + 2) * 32);
+    if (rc) return rc;
+    uint4 *tab = (uint4 *)ctx->poly_ws.p, *partial = tab + 2 * n_distinct * tab_elems, *res = partial + 2 * (size_t)total_blocks;
+    for (size_t d = 0; d < n_distinct; ++d) {
+        rc = zkb_pow2lvl_build(ctx, tab + 2 * d * tab_elems, lm, host_fe(points_host + 4 * distinct[d]), host::one(host::FR), &a.s);
+        if (rc) return rc;
+    }
+    poly_eval_many_partial_kernel<<<dim3(max_blocks, (unsigned)k), 256, 0, ctx->stream>>>(a, tab, partial);
+    fr_sum_many_kernel<<<(unsigned)k, 256, 0, ctx->stream>>>(a, partial, res);
+    ctx->launches += 2 + 2 * n_distinct;
+    ZKB_CUDA(ctx, cudaGetLastError());
+    ZKB_CUDA(ctx, cudaMemcpyAsync(out_host, res, k * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKB_OK;
+}
+
 int zkb_poly_lincomb_dev(zkb_ctx *ctx, size_t k, const uint64_t *const *polys_dev, const size_t *lens,
                          const uint64_t *scalars_host, uint64_t *out_dev, size_t out_len) {
     if (!ctx) return ZKB_ERR_INVALID;
@@ -739,8 +844,8 @@ int zkb_poly_effective_len_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, size_t 
     if (!out_len || (!coeffs_dev && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_poly_effective_len_dev: null argument");
     *out_len = 0;
     if (n == 0) return ZKB_OK;
-    if (!ctx->gp_flag) ZKB_CUDA(ctx, cudaMalloc((void **)&ctx->gp_flag, 256));
-    unsigned long long *slot = (unsigned long long *)(ctx->gp_flag + 8);
+    if (!ctx->len_slot) ZKB_CUDA(ctx, cudaMalloc((void **)&ctx->len_slot, 256));
+    unsigned long long *slot = ctx->len_slot;
     ZKB_CUDA(ctx, cudaMemsetAsync(slot, 0, 8, ctx->stream));
     effective_len_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)coeffs_dev, n, slot);
     ctx->launches += 1;

@@ -133,7 +133,7 @@ struct zkb_plonk_pk {
     cudaStream_t copy_stream = nullptr;          // wire uploads (+ their all-gather on several GPUs), issued by the proving thread
     cudaStream_t lookup_stream = nullptr;        // uploads of the lookup multisets, issued by the worker thread: a stream of
                                                  // their own, so that 4n pinned elements never queue in front of a wire
-    cudaEvent_t lookup_uploaded = nullptr, wire_uploaded = nullptr;
+    cudaEvent_t lookup_uploaded = nullptr, wire_uploaded = nullptr, wire_ev[3] = {nullptr, nullptr, nullptr};
     char *arena = nullptr;                       // per-proof scratch: reset at the start of every prove
     size_t arena_bytes = 0, arena_off = 0;
     int transcript_kind = 0;                     // 0 MerlinTranscript (default binary), 1 EthereumTranscript
@@ -231,23 +231,34 @@ int commit_finish_pts(zkb_ctx *ctx, size_t count, Pt *out) {
     return ZKB_OK;
 }
 
-// The caller's vectors are pageable: cudaMemcpyAsync stages them through the driver at ~10 GB/s with the host blocked.
-// For large wires a few threads copy them into pinned memory instead (the DMA that follows is asynchronous).
-void parallel_copy(void *dst, const void *src, size_t bytes) {
-    size_t nt = bytes >> 21;                                               // one thread per 2 MiB, at most 8
-    unsigned hw = std::thread::hardware_concurrency();
-    const size_t cap = hw >= 16 ? 8 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
-    nt = nt > cap ? cap : nt;
-    if (nt <= 1) { memcpy(dst, src, bytes); return; }
-    const size_t part = (bytes / nt + 4095) & ~(size_t)4095;
+// The caller's vectors are pageable: cudaMemcpyAsync would stage them through the driver at ~12 GB/s with the host blocked
+// (0.67 ms per 8 MiB wire on the B200 box, profiles/r02t_trace_2^18.jsonl).  Instead a few threads copy 1 MiB pieces into pinned
+// memory and each piece is handed to the DMA engine as soon as it is staged, so staging and PCIe overlap.
+// Returns false if a CUDA call failed.  Runs on the uploader thread of a proof.
+bool staged_upload(int device, uint64_t *dst_dev, const void *src_host, void *pinned, size_t bytes, cudaStream_t stream) {
+    const size_t piece = (size_t)1 << 20, pieces = (bytes + piece - 1) / piece;
+    // threads: one per 8 MiB, 2..4.  More starve the DMA engine of host memory bandwidth (8 threads: 18.8 instead of 17.6 ms
+    // per 2^18-gate proof), a single one cannot feed it at 32 MiB per wire (55.8 instead of 51.5 ms at 2^20;
+    // profiles/r02v_ab_prove*.jsonl)
+    const unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = std::min<size_t>(4, std::max<size_t>(2, bytes >> 23));
+    if (hw < 4) nt = 1;
+    if (const char *e = getenv("ZKB_STAGE_THREADS")) nt = (size_t)std::max(1, atoi(e));   // for A/B measurements
+    nt = pieces < nt ? pieces : nt;
+    std::atomic<bool> ok{true};
+    auto run = [&](size_t t) {
+        if (cudaSetDevice(device) != cudaSuccess) { ok.store(false); return; }
+        for (size_t i = t; i < pieces; i += nt) {
+            const size_t lo = i * piece, len = lo + piece < bytes ? piece : bytes - lo;
+            memcpy((char *)pinned + lo, (const char *)src_host + lo, len);
+            if (cudaMemcpyAsync((char *)dst_dev + lo, (char *)pinned + lo, len, cudaMemcpyHostToDevice, stream) != cudaSuccess) ok.store(false);
+        }
+    };
     std::vector<std::thread> pool;
-    for (size_t k = 1; k < nt; ++k) {
-        const size_t lo = k * part, hi = lo + part < bytes ? lo + part : bytes;
-        if (lo >= bytes) break;
-        pool.emplace_back([=]() { memcpy((char *)dst + lo, (const char *)src + lo, hi - lo); });
-    }
-    memcpy(dst, src, part < bytes ? part : bytes);
+    for (size_t t = 1; t < nt; ++t) pool.emplace_back(run, t);
+    run(0);
     for (auto &t : pool) t.join();
+    return ok.load();
 }
 
 double now_ms() {
@@ -308,6 +319,7 @@ void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
     if (pk->lookup_stream) cudaStreamDestroy(pk->lookup_stream);
     if (pk->lookup_uploaded) cudaEventDestroy(pk->lookup_uploaded);
     if (pk->wire_uploaded) cudaEventDestroy(pk->wire_uploaded);
+    for (cudaEvent_t e : pk->wire_ev) if (e) cudaEventDestroy(e);
     delete pk;
 }
 
@@ -381,7 +393,10 @@ int key_finish(zkb_ctx *ctx, zkb_plonk_pk *pk, bool have_vk) {
     if (cudaStreamCreateWithFlags(&pk->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&pk->lookup_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&pk->lookup_uploaded, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&pk->wire_uploaded, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&pk->wire_uploaded, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pk->wire_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pk->wire_ev[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pk->wire_ev[2], cudaEventDisableTiming) != cudaSuccess)
         ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_setup: cannot create the copy stream");
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_setup: stream error");
     return ZKB_OK;
@@ -718,82 +733,145 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
         }
         return ZKB_OK;
     };
-    DPoly pa, pb, pc;
-    {
-        struct { const uint64_t *host; uint64_t *dev; DPoly *poly; } wires[3] = {{a, ev_a, &pa}, {b, ev_b, &pb}, {c, ev_c, &pc}};
-        // Several GPUs (SPMD): every rank needs the whole wire for its NTTs, but the ranks of one box share the host's
-        // memory bandwidth, so a rank uploads only its 1/world slice and the slices are all-gathered over NVLink.
-        const bool split = ctx->world > 1 && ctx->comm && n % (size_t)ctx->world == 0;
-        const size_t chunk = split ? n / (size_t)ctx->world : n, first = split ? (size_t)ctx->rank * chunk : 0;
-        // a, b, c are one batch upstream (prove.rs:133-135), but here they are pushed as the wires cross PCIe: every push is
-        // cut over ALL ranks (no zkb_commit_expect).  Fanning this batch out -- one group of ranks per wire -- serialises it
-        // behind the uploads: the last group starts its (larger) MSM only when the last wire has arrived (measured on 8 B200:
-        // round 1 4.6 instead of 3.5 ms at n = 2^20, profiles/r02i_bench_n8.json).
-        if (vars) {
-            // the assignment crosses PCIe once (n_vars elements instead of 3n), every rank its 1/world slice, then the three
-            // wires are gathered in HBM (ProvingComposer::wire_evals, prove.rs:49-55)
-            zkb_plonk_pk *mpk = const_cast<zkb_plonk_pk *>(pk);
-            const size_t world = split ? (size_t)ctx->world : 1, vpad = (n_vars + world - 1) / world * world;
-            if (mpk->d_vars_cap < vpad) {
-                if (mpk->d_vars) { ZKB_CUDA(ctx, cudaStreamSynchronize(pk->copy_stream)); cudaFree(mpk->d_vars); mpk->d_vars = nullptr; }
-                ZKB_CUDA(ctx, cudaMalloc((void **)&mpk->d_vars, vpad * 32));
-                mpk->d_vars_cap = vpad;
-            }
-            const size_t vchunk = vpad / world, vfirst = split ? (size_t)ctx->rank * vchunk : 0;
-            const size_t vcount = vfirst < n_vars ? std::min(vchunk, n_vars - vfirst) : 0;
-            if (vcount) ZKB_CUDA(ctx, cudaMemcpyAsync(mpk->d_vars + 4 * vfirst, vars + 4 * vfirst, vcount * 32, cudaMemcpyHostToDevice, pk->copy_stream));
-            if (split) TRY(zkb_comm_allgather_dev(ctx, mpk->d_vars, vchunk * 32, pk->copy_stream));
-            for (int k = 0; k < 3; ++k)
-                gather_wire_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pk->copy_stream>>>((uint4 *)wires[k].dev, pk->d_wiring[k],
-                                                                                           (const uint4 *)mpk->d_vars, n);
-            ZKB_CUDA(ctx, cudaGetLastError());
-            ZKB_CUDA(ctx, cudaEventRecord(pk->wire_uploaded, pk->copy_stream));
-            ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->wire_uploaded, 0));
-            tick(0);
-            for (int k = 0; k < 3; ++k) {
-                TRY(blinded_from_dev_evals(wires[k].dev, 2, wires[k].poly));
-                TRY(zkb_commit_push(ctx, wires[k].poly->d, 0, wires[k].poly->len));
-            }
+    DPoly pa, pb, pc, pt, ph1, ph2, ppi;
+    struct { const uint64_t *host; uint64_t *dev; DPoly *poly; } wires[3] = {{a, ev_a, &pa}, {b, ev_b, &pb}, {c, ev_c, &pc}};
+    // Several GPUs (SPMD): every rank needs the whole wire for its NTTs, but the ranks of one box share the host's
+    // memory bandwidth, so a rank uploads only its 1/world slice and the slices are all-gathered over NVLink.
+    const bool split = ctx->world > 1 && ctx->comm && n % (size_t)ctx->world == 0;
+    const size_t chunk = split ? n / (size_t)ctx->world : n, first = split ? (size_t)ctx->rank * chunk : 0;
+    // the variable assignment instead of the wires: it crosses PCIe once (n_vars elements instead of 3n), every rank its
+    // 1/world slice, then the three wires are gathered in HBM (ProvingComposer::wire_evals, prove.rs:49-55)
+    size_t vchunk = 0, vfirst = 0, vcount = 0;
+    if (vars) {
+        zkb_plonk_pk *mpk = const_cast<zkb_plonk_pk *>(pk);
+        const size_t world = split ? (size_t)ctx->world : 1, vpad = (n_vars + world - 1) / world * world;
+        if (mpk->d_vars_cap < vpad) {
+            if (mpk->d_vars) { ZKB_CUDA(ctx, cudaStreamSynchronize(pk->copy_stream)); cudaFree(mpk->d_vars); mpk->d_vars = nullptr; }
+            ZKB_CUDA(ctx, cudaMalloc((void **)&mpk->d_vars, vpad * 32));
+            mpk->d_vars_cap = vpad;
         }
-        for (int k = 0; k < 3 && !vars; ++k) {
-            const uint64_t *src = wires[k].host + 4 * first;
-            if (chunk * 32 >= ((size_t)16 << 20)) {                      // measured: pays off from ~16 MiB (2.6 vs 3.2 ms at 32 MiB)
-                Fe *pinned = pk->wire_stage + (size_t)k * n + first;
-                parallel_copy(pinned, src, chunk * 32);
-                src = (const uint64_t *)pinned;
-            }
-            ZKB_CUDA(ctx, cudaMemcpyAsync(wires[k].dev + 4 * first, src, chunk * 32, cudaMemcpyHostToDevice, pk->copy_stream));
-            if (split) TRY(zkb_comm_allgather_dev(ctx, wires[k].dev, chunk * 32, pk->copy_stream));
-            ZKB_CUDA(ctx, cudaEventRecord(pk->wire_uploaded, pk->copy_stream));
-            ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->wire_uploaded, 0));
-            if (k == 0) tick(0);
-            TRY(blinded_from_dev_evals(wires[k].dev, 2, wires[k].poly));
-            TRY(zkb_commit_push(ctx, wires[k].poly->d, 0, wires[k].poly->len));
-        }
+        vchunk = vpad / world;
+        vfirst = split ? (size_t)ctx->rank * vchunk : 0;
+        vcount = vfirst < n_vars ? std::min(vchunk, n_vars - vfirst) : 0;
     }
-    Pt c_a[3];
-    TRY(commit_finish_pts(ctx, 3, c_a));
-    tr.append_commitment("a_commit", c_a[0]);
-    tr.append_commitment("b_commit", c_a[1]);
-    tr.append_commitment("c_commit", c_a[2]);
+    // All uploads are issued up front by one thread (staging through pinned memory, DMA and -- on several GPUs -- the
+    // all-gather on the copy stream), so wire b crosses PCIe while the proving thread is still enqueueing the commitment to
+    // wire a: issued from the proving thread between the commitments, the copies left the GPU idle for 0.35 ms per wire at
+    // n = 2^18 (profiles/r02t_trace_2^18.jsonl).  up_recorded = number of wires whose event has been recorded.
+    std::atomic<int> up_recorded{0}, up_failed{0};
+    std::thread uploader([&]() {
+        bool ok = cudaSetDevice(ctx->device) == cudaSuccess;
+        cudaStream_t cs = pk->copy_stream;
+        if (vars) {
+            uint64_t *dst = pk->d_vars + 4 * vfirst;
+            const uint64_t *src = vars + 4 * vfirst;
+            if (ok && vcount) {
+                if (vcount <= 3 * n) ok = staged_upload(ctx->device, dst, src, pk->wire_stage, vcount * 32, cs);
+                else ok = cudaMemcpyAsync(dst, src, vcount * 32, cudaMemcpyHostToDevice, cs) == cudaSuccess;
+            }
+            if (ok && split) ok = zkb_comm_allgather_dev(ctx, pk->d_vars, vchunk * 32, cs) == ZKB_OK;
+            for (int k = 0; k < 3 && ok; ++k)
+                gather_wire_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>((uint4 *)wires[k].dev, pk->d_wiring[k], (const uint4 *)pk->d_vars, n);
+            ok = ok && cudaGetLastError() == cudaSuccess && cudaEventRecord(pk->wire_ev[2], cs) == cudaSuccess;
+            if (!ok) up_failed.store(1);
+            up_recorded.store(3, std::memory_order_release);
+            return;
+        }
+        for (int k = 0; k < 3; ++k) {
+            ok = ok && staged_upload(ctx->device, wires[k].dev + 4 * first, wires[k].host + 4 * first, pk->wire_stage + (size_t)k * n + first,
+                                     chunk * 32, cs);
+            if (ok && split) ok = zkb_comm_allgather_dev(ctx, wires[k].dev, chunk * 32, cs) == ZKB_OK;
+            ok = ok && cudaEventRecord(pk->wire_ev[k], cs) == cudaSuccess;
+            if (!ok) up_failed.store(1);
+            up_recorded.store(k + 1, std::memory_order_release);
+        }
+    });
+    Joiner uploader_joiner{uploader};
+    // a, b, c are one batch upstream (prove.rs:133-135), but here they are pushed as the wires cross PCIe: every push is
+    // cut over ALL ranks (no zkb_commit_expect).  Fanning this batch out -- one group of ranks per wire -- serialises it
+    // behind the uploads: the last group starts its (larger) MSM only when the last wire has arrived (measured on 8 B200:
+    // round 1 4.6 instead of 3.5 ms at n = 2^20, profiles/r02i_bench_n8.json).
+    for (int k = 0; k < 3; ++k) {
+        while (up_recorded.load(std::memory_order_acquire) <= k) std::this_thread::yield();
+        if (up_failed.load()) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_prove: upload of the wires failed");
+        ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->wire_ev[vars ? 2 : k], 0));
+        if (k == 0) tick(0);
+        TRY(blinded_from_dev_evals(wires[k].dev, 2, wires[k].poly));
+        TRY(zkb_commit_push(ctx, wires[k].poly->d, 0, wires[k].poly->len));
+    }
+    uploader.join();
     tick(1);
 
-    // ---- round 2: lookup multisets on the host (prove.rs:145-167)
+    // ---- round 2: lookup multisets on the host (prove.rs:145-167).  t, h1, h2 depend on the witness and the table only, and
+    // their commitments enter the transcript before any challenge is drawn (prove.rs:183-199), so they join the batch of
+    // a, b, c: six pipelined commitments, one exposed reduction tail and one exchange between the ranks instead of two.
     lookup_worker.join();                                               // started before round 1 (see above)
     if (lookup_status.load() == 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "ElementNotIndexedInTable (lookup/multiset.rs:121)");
     if (lookup_status.load() == 2) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: combine_split halves are not n long");
     if (lookup_status.load() == 3) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_prove: upload of the lookup multisets failed");
     ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->lookup_uploaded, 0));
     tick(2);
-    DPoly pt, ph1, ph2;
     {
         const uint64_t *evs[3] = {ev_t, ev_h1, ev_h2};
         const int kb[3] = {0, 3, 2};
         DPoly *outs[3] = {&pt, &ph1, &ph2};
         TRY(blinded_from_dev_evals_many(evs, kb, outs, 3));
+        for (int k = 0; k < 3; ++k) TRY(zkb_commit_push(ctx, outs[k]->d, 0, outs[k]->len));
     }
-    Pt c_t[3];
-    { const DPoly *ps[3] = {&pt, &ph1, &ph2}; TRY(commit_many(ctx, ps, 3, c_t)); }
+    // ---- round 4's challenge-independent part, enqueued behind the six commitments: the public-input polynomial and the
+    // coset NTTs of a, b, c, pi, t, h1, h2 run on the main stream while the reductions of the last commitments finish on the
+    // tail stream and the host folds and exchanges the results (the GPU was idle there)
+    std::vector<unsigned long long> pi_pos_host(pk->pi_pos.begin(), pk->pi_pos.end());
+    {
+        for (size_t k = 0; k < n_pi; ++k)
+            if (pk->pi_pos[k] >= n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: public input position out of range");
+        uint64_t *d, *d_vals = nullptr, *d_pos = nullptr;                  // PublicInputs::as_evals (pi.rs:75-82), built in HBM
+        TAKE(d, n);
+        ZKB_CUDA(ctx, cudaMemsetAsync(d, 0, n * 32, s));
+        if (n_pi) {
+            TAKE(d_vals, n_pi); TAKE(d_pos, (n_pi + 3) / 4);
+            ZKB_CUDA(ctx, cudaMemcpyAsync(d_vals, pi_values, n_pi * 32, cudaMemcpyHostToDevice, s));
+            ZKB_CUDA(ctx, cudaMemcpyAsync(d_pos, pi_pos_host.data(), n_pi * 8, cudaMemcpyHostToDevice, s));
+            scatter_fe_kernel<<<(unsigned)((n_pi + 127) / 128), 128, 0, s>>>((uint4 *)d, (const unsigned long long *)d_pos, (const uint4 *)d_vals, n_pi);
+            ZKB_CUDA(ctx, cudaGetLastError());
+        }
+        TRY(zkb_ntt_dev(ctx, d, n, log_n, 1, 0));
+        ppi.d = d; ppi.cap = n;
+        TRY(zkb_poly_effective_len_dev(ctx, d, n, &ppi.len));
+    }
+    // Several GPUs (SPMD): the nine coset NTTs are independent, so rank k % world transforms polynomial k, every
+    // rank receives the slice (+ 4 halo elements for the "next row" reads) its part of the quotient needs, evaluates
+    // that part, and the quotient slices are all-gathered before the (replicated) coset iNTT.
+    const size_t world = (size_t)ctx->world;
+    const bool fan = world > 1 && ctx->comm && n4 % world == 0 && n4 / world >= 4;
+    DPoly pz1, pz2;
+    const DPoly *wit_p[9] = {&pz1, &pz2, &pa, &pb, &pc, &ppi, &pt, &ph1, &ph2};
+    uint64_t *wit_w[9];
+    for (int k = 0; k < 9; ++k) TAKE(wit_w[k], n4);
+    auto coset_ntts = [&](int k_lo, int k_hi) -> int {                  // polynomials wit_p[k_lo .. k_hi) -> wit_w, this rank's share
+        uint64_t *own[9];
+        size_t n_own = 0, max_len = 0;
+        for (int k = k_lo; k < k_hi; ++k) {
+            if (fan && (size_t)k % world != (size_t)ctx->rank) continue;
+            uint64_t *d = wit_w[k];
+            ZKB_CUDA(ctx, cudaMemsetAsync(d, 0, n4 * 32, s));
+            ZKB_CUDA(ctx, cudaMemcpyAsync(d, wit_p[k]->d, wit_p[k]->len * 32, cudaMemcpyDeviceToDevice, s));
+            own[n_own++] = d;
+            max_len = wit_p[k]->len > max_len ? wit_p[k]->len : max_len;
+        }
+        if (!n_own) return ZKB_OK;
+        return zkb_ntt_batch_dev(ctx, own, n_own, max_len, log_n + 2, 0, 1);   // the buffers are zero beyond their own lengths
+    };
+    TRY(coset_ntts(2, 9));
+    Pt c_a[3], c_t[3];
+    {
+        Pt six[6];
+        TRY(commit_finish_pts(ctx, 6, six));
+        for (int k = 0; k < 3; ++k) { c_a[k] = six[k]; c_t[k] = six[3 + k]; }
+    }
+    tr.append_commitment("a_commit", c_a[0]);
+    tr.append_commitment("b_commit", c_a[1]);
+    tr.append_commitment("c_commit", c_a[2]);
     tr.append_commitment("t_commit", c_t[0]);
     tr.append_commitment("h1_commit", c_t[1]);
     tr.append_commitment("h2_commit", c_t[2]);
@@ -804,7 +882,6 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
     tick(3);
 
     // ---- round 3: grand products (prove.rs:209-251)
-    DPoly pz1, pz2;
     {
         uint64_t *z1e, *z2e;
         TAKE(z1e, n); TAKE(z2e, n);
@@ -817,67 +894,33 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
         DPoly *outs[2] = {&pz1, &pz2};
         TRY(blinded_from_dev_evals_many(evs, kb, outs, 2));
     }
+    // the coset NTTs of z1 and z2 need the polynomials, not alpha: enqueued behind the two commitments, they run while the
+    // last reduction finishes on the tail stream and the host folds the results
     Pt c_z[2];
-    { const DPoly *ps[2] = {&pz1, &pz2}; TRY(commit_many(ctx, ps, 2, c_z)); }
+    TRY(zkb_commit_expect(ctx, 2));
+    TRY(zkb_commit_push(ctx, pz1.d, 0, pz1.len));
+    TRY(zkb_commit_push(ctx, pz2.d, 0, pz2.len));
+    TRY(coset_ntts(0, 2));
+    TRY(commit_finish_pts(ctx, 2, c_z));
     tr.append_commitment("z1_commit", c_z[0]);
     tr.append_commitment("z2_commit", c_z[1]);
     tick(4);
 
-    // ---- round 4: quotient (prove.rs:258-308, quotient_poly.rs:20-227)
-    DPoly ppi;
-    {
-        for (size_t k = 0; k < n_pi; ++k)
-            if (pk->pi_pos[k] >= n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: public input position out of range");
-        uint64_t *d, *d_vals = nullptr, *d_pos = nullptr;                  // PublicInputs::as_evals (pi.rs:75-82), built in HBM
-        TAKE(d, n);
-        ZKB_CUDA(ctx, cudaMemsetAsync(d, 0, n * 32, s));
-        if (n_pi) {
-            std::vector<unsigned long long> pos(pk->pi_pos.begin(), pk->pi_pos.end());
-            TAKE(d_vals, n_pi); TAKE(d_pos, (n_pi + 3) / 4);
-            ZKB_CUDA(ctx, cudaMemcpyAsync(d_vals, pi_values, n_pi * 32, cudaMemcpyHostToDevice, s));
-            ZKB_CUDA(ctx, cudaMemcpyAsync(d_pos, pos.data(), n_pi * 8, cudaMemcpyHostToDevice, s));
-            ZKB_CUDA(ctx, cudaStreamSynchronize(s));                     // `pos` is a host temporary
-            scatter_fe_kernel<<<(unsigned)((n_pi + 127) / 128), 128, 0, s>>>((uint4 *)d, (const unsigned long long *)d_pos, (const uint4 *)d_vals, n_pi);
-            ZKB_CUDA(ctx, cudaGetLastError());
-        }
-        TRY(zkb_ntt_dev(ctx, d, n, log_n, 1, 0));
-        ppi.d = d; ppi.cap = n;
-        TRY(zkb_poly_effective_len_dev(ctx, d, n, &ppi.len));
-    }
+    // ---- round 4: quotient (prove.rs:258-308, quotient_poly.rs:20-227); its nine coset NTTs ran above
     const Fe alpha = tr.challenge_scalar("alpha");
     uint64_t *q_buf;
     {
-        const DPoly *wit_p[9] = {&pz1, &pz2, &pa, &pb, &pc, &ppi, &pt, &ph1, &ph2};
-        uint64_t *wit_w[9];
         const uint64_t *wit[9];
-        // Several GPUs (SPMD): the nine coset NTTs are independent, so rank k % world transforms polynomial k, every
-        // rank receives the slice (+ 4 halo elements for the "next row" reads) its part of the quotient needs, evaluates
-        // that part, and the quotient slices are all-gathered before the (replicated) coset iNTT.
-        const size_t world = (size_t)ctx->world;
-        const bool fan = world > 1 && ctx->comm && n4 % world == 0 && n4 / world >= 4;
-        uint64_t *own[9];
-        size_t n_own = 0, max_len = 0;
-        for (int k = 0; k < 9; ++k) {
-            uint64_t *d;
-            TAKE(d, n4);
-            wit_w[k] = d;
-            wit[k] = d;
-            if (fan && (size_t)k % world != (size_t)ctx->rank) continue;
-            ZKB_CUDA(ctx, cudaMemsetAsync(d, 0, n4 * 32, s));
-            ZKB_CUDA(ctx, cudaMemcpyAsync(d, wit_p[k]->d, wit_p[k]->len * 32, cudaMemcpyDeviceToDevice, s));
-            own[n_own++] = d;
-            max_len = wit_p[k]->len > max_len ? wit_p[k]->len : max_len;
-        }
-        TRY(zkb_ntt_batch_dev(ctx, own, n_own, max_len, log_n + 2, 0, 1));   // the buffers are zero beyond their own lengths
+        for (int k = 0; k < 9; ++k) wit[k] = wit_w[k];
         uint64_t ch[20];
         const Fe *cs[5] = {&alpha, &beta, &gamma, &delta, &epsilon};
         for (int k = 0; k < 5; ++k) memcpy(ch + 4 * k, cs[k]->l, 32);
         TAKE(q_buf, n4);
         if (fan) {
-            const size_t chunk = n4 / world, lo = (size_t)ctx->rank * chunk;
+            const size_t chunk4 = n4 / world, lo = (size_t)ctx->rank * chunk4;
             TRY(zkb_comm_spread_slices(ctx, wit_w, 9, n4, 4, s));
-            TRY(zkb_quotient_evals_range_dev(ctx, log_n, ch, wit, (const uint64_t *const *)pk->epk, q_buf, lo, lo + chunk));
-            TRY(zkb_comm_allgather_dev(ctx, q_buf, chunk * 32, s));
+            TRY(zkb_quotient_evals_range_dev(ctx, log_n, ch, wit, (const uint64_t *const *)pk->epk, q_buf, lo, lo + chunk4));
+            TRY(zkb_comm_allgather_dev(ctx, q_buf, chunk4 * 32, s));
         } else {
             TRY(zkb_quotient_evals_dev(ctx, log_n, ch, wit, (const uint64_t *const *)pk->epk, q_buf));
         }
@@ -939,7 +982,11 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
         struct { const DPoly *p; const Fe *at; } q[12] = {
             {&pa, &xi}, {&pb, &xi}, {&pc, &xi}, {&pk->poly[P_S1], &xi}, {&pk->poly[P_S2], &xi}, {&pz1, &shifted},
             {&pk->poly[P_QLK], &xi}, {&pt, &xi}, {&pt, &shifted}, {&pz2, &shifted}, {&ph1, &shifted}, {&ph2, &xi}};
-        for (int k = 0; k < 12; ++k) TRY(zkb_poly_eval_dev(ctx, q[k].p->d, q[k].p->len, q[k].at->l, ev[k].l));
+        const uint64_t *ptrs[12];
+        size_t lens[12];
+        Fe at[12];
+        for (int k = 0; k < 12; ++k) { ptrs[k] = q[k].p->d; lens[k] = q[k].p->len; at[k] = *q[k].at; }
+        TRY(zkb_poly_eval_many_dev(ctx, 12, ptrs, lens, (const uint64_t *)at, (uint64_t *)ev));
     }
     const Fe &ea = ev[0], &eb = ev[1], &ec = ev[2], &es1 = ev[3], &es2 = ev[4], &ez1n = ev[5], &eql = ev[6], &et = ev[7],
              &etn = ev[8], &ez2n = ev[9], &eh1n = ev[10], &eh2 = ev[11];
