@@ -822,7 +822,10 @@ def _prove_once(device, log_n, circ, dist, rank, world, layout):
             "from_variable_assignment": from_vars,
             "verify_rc": verify_rc, "verify_ms_host": verify_ms, "proof_sha256": digest.hex(), "ranks_agree": ranks_agree,
             "note": "prove_ms: wall clock around the call, max over ranks; the per-round breakdown drains the stream at every "
-                    "boundary.  verify_rc: zkb_plonk_verify (pairing check) on the bytes of the last timed proof, 0 = accepted, on "
+                    "boundary, and the boundaries follow the driver's schedule, not the paper's rounds: round1 = wires uploaded, "
+                    "transformed and their three commitments enqueued; round2 = t, h1, h2 transformed and enqueued, the public-input "
+                    "polynomial, seven of round 4's nine coset NTTs, then all six commitments folded; round3 = grand products, "
+                    "their commitments and the two remaining coset NTTs; round4 = quotient evaluation onwards.  verify_rc: zkb_plonk_verify (pairing check) on the bytes of the last timed proof, 0 = accepted, on "
                     "every rank; ranks_agree: SHA-256 of the proof all-gathered and compared (N > 1).  Byte identity with the "
                     "oracle-backend prover: tests/test_gpu_prover.py (2^5..2^10, and 2^18 / 2^20 marked slow)"}
 

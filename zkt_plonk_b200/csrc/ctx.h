@@ -49,6 +49,7 @@ struct zkb_ctx {
     bool srs_replicated = false; // every rank holds the WHOLE key: the library splits each batch of commitments among the ranks
     int fanout = -1;             // replicated key, batches of several commitments: 1 = one group of ranks per commitment,
                                  // 0 = every commitment sharded over all ranks, -1 = cost model (msm.cu fanout_wins)
+    cudaStream_t comm_stream = nullptr;   // host-to-host exchanges (zkb_comm_allgather) run here, not behind the context's stream
     DevBuf comm_buf;             // device staging of the all-gather
     void *comm_pinned = nullptr; // pinned host staging of the all-gather
     size_t comm_pinned_bytes = 0;
