@@ -481,6 +481,83 @@ __global__ void __launch_bounds__(RED_THREADS, WIDE ? RED_CTAS_PER_SM : 1) msm_w
     g1x_store(out + ((size_t)(n_plain + 1) * G + g) * M_out + t, acc);
 }
 
+// A binary level with FOUR lanes per addition.  A level's additions are independent but each is one dependent chain of 14
+// field products -- ~9 us in a warp of its own -- and from the fifth level on a level is a single CTA or less, so the
+// sixteen levels cost their additions' LATENCY (0.18 of the 0.43 ms of a 2^19-bucket reduction).  The products of an
+// XYZZ addition form four rounds of at most four independent ones; lane l of a group computes one product per round, the
+// results move by shuffles (9 field elements per addition), and lane l stores coordinate l of the sum:
+//   round 1   u1 = X1 ZZ2      u2 = X2 ZZ1     s1 = Y1 ZZZ2     s2 = Y2 ZZZ1        p = u2 - u1, r = s2 - s1
+//   round 2   pp = p^2         zz = ZZ1 ZZ2    rr = r^2         zzz = ZZZ1 ZZZ2
+//   round 3   ppp = p pp       q = u1 pp       ZZ3 = zz pp      --                   X3 = rr - ppp - 2 q
+//   round 4   --               r (q - X3)      s1 ppp           ZZZ3 = zzz ppp       Y3 = r (q - X3) - s1 ppp
+// 16 lane-products instead of 14, a quarter of the depth.  Infinity and p == 0 (doubling / cancellation) are uniform over a
+// group and take the one-lane formulas.  Same sums as msm_wsum_level_kernel<false> (canonical field elements either way).
+__device__ __forceinline__ fe_t shfl_fe(unsigned mask, const fe_t &a, int src) {
+    fe_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_sync(mask, a.v[i], src);
+    return r;
+}
+__device__ __forceinline__ fe_t shfl_xor_fe(unsigned mask, const fe_t &a, int m) {
+    fe_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_xor_sync(mask, a.v[i], m);
+    return r;
+}
+__device__ __forceinline__ fe_t sel_fe(bool c, const fe_t &a, const fe_t &b) {
+    fe_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = c ? a.v[i] : b.v[i];
+    return r;
+}
+
+__global__ void __launch_bounds__(RED_THREADS) msm_wsum_level_coop_kernel(const g1x_t *__restrict__ in, uint32_t M_in, uint32_t M_out,
+                                                                         uint32_t n_plain, g1x_t *__restrict__ out) {
+    const uint32_t t = (blockIdx.x * RED_THREADS + threadIdx.x) >> 2, l = threadIdx.x & 3, base = (threadIdx.x & 31) & ~3u;
+    const uint32_t strm = blockIdx.y, g = blockIdx.z, G = gridDim.z;
+    const unsigned m0 = __ballot_sync(0xffffffffu, t < M_out);    // whole groups leave; the masks name the lanes that stay
+    if (t >= M_out) return;
+    const g1x_t *src = in + ((size_t)strm * G + g) * M_in + (size_t)2 * t;
+    const char *p0 = reinterpret_cast<const char *>(src), *p1 = p0 + sizeof(g1x_t);
+    char *dst = reinterpret_cast<char *>(out + ((size_t)strm * G + g) * M_out + t);
+    const bool pair = M_in - 2 * t > 1;
+    if (strm == 0)                                                // the new A stream: X[2t + 1], one coordinate per lane
+        fstore(reinterpret_cast<char *>(out + ((size_t)(n_plain + 1) * G + g) * M_out + t) + 32 * l, pair ? fload(p1 + 32 * l) : fzero<Q>());
+    // coordinates: 0 x, 1 y, 2 zz, 3 zzz.  lane 0: X1, ZZ2; lane 1: X2, ZZ1; lane 2: Y1, ZZZ2; lane 3: Y2, ZZZ1
+    const fe_t a = pair || !(l & 1) ? fload(((l & 1) ? p1 : p0) + 32 * (l >> 1)) : fzero<Q>();
+    const fe_t b = pair ? fload(((l & 1) ? p0 : p1) + 64 + 32 * (l >> 1)) : fzero<Q>();
+    // infinity on either side (ZZ == 0; a missing partner counts as infinity): the sum is the other point
+    const bool inf2 = __shfl_sync(m0, (int)fis_zero<Q>(b), base) != 0;          // ZZ2 sits on lane 0
+    const bool inf1 = __shfl_sync(m0, (int)fis_zero<Q>(b), base + 1) != 0;      // ZZ1 on lane 1
+    const unsigned m1 = __ballot_sync(m0, !(inf1 || inf2));
+    if (inf1 || inf2) {
+        fstore(dst + 32 * l, inf2 ? fload(p0 + 32 * l) : fload(p1 + 32 * l));
+        return;
+    }
+    fe_t prod = fmul<Q>(a, b);                                                   // u1 | u2 | s1 | s2
+    const fe_t other = shfl_xor_fe(m1, prod, 1);
+    const fe_t lo = sel_fe(l & 1, other, prod);                                  // u1 (lanes 0, 1), s1 (lanes 2, 3)
+    const fe_t d = fsub<Q>(sel_fe(l & 1, prod, other), lo);                      // p  (lanes 0, 1), r  (lanes 2, 3)
+    const bool pz = __shfl_sync(m1, (int)fis_zero<Q>(d), base) != 0;
+    const unsigned m2 = __ballot_sync(m1, !pz);
+    if (pz) {                                                                    // same x: every lane runs the complete formulas
+        g1x_t x0 = g1x_load(p0);
+        g1x_add(x0, g1x_load(p1));
+        fstore(dst + 32 * l, l == 0 ? x0.x : l == 1 ? x0.y : l == 2 ? x0.zz : x0.zzz);
+        return;
+    }
+    const fe_t bp = shfl_xor_fe(m2, b, 1);                                       // lane 1: ZZ2, lane 3: ZZZ2
+    const fe_t prod2 = fmul<Q>(sel_fe(l & 1, b, d), sel_fe(l & 1, bp, d));       // pp | zz | rr | zzz
+    const fe_t pp = shfl_fe(m2, prod2, base), zz = shfl_fe(m2, prod2, base + 1);
+    const fe_t prod3 = fmul<Q>(l == 0 ? d : l == 1 ? lo : l == 2 ? zz : pp, pp); // ppp | q | ZZ3 | (unused)
+    const fe_t ppp = shfl_fe(m2, prod3, base), q = shfl_fe(m2, prod3, base + 1), rr = shfl_fe(m2, prod2, base + 2);
+    const fe_t r = shfl_fe(m2, d, base + 2);
+    const fe_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(rr, ppp), q), q);
+    const fe_t prod4 = fmul<Q>(l == 1 ? r : l == 2 ? lo : l == 3 ? prod2 : ppp, l == 1 ? fsub<Q>(q, x3) : ppp);   // -- | r (q - X3) | s1 ppp | ZZZ3
+    const fe_t t1 = shfl_fe(m2, prod4, base + 2);
+    fstore(dst + 32 * l, l == 0 ? x3 : l == 1 ? fsub<Q>(prod4, t1) : l == 2 ? prod3 : prod4);
+}
+
 // Fixed-base table: rows[w][i] = 2^(c*w) * P_i (affine), w < W.  One thread per point walks the windows.
 __global__ void __launch_bounds__(128) msm_precompute_kernel(const g1a_t *__restrict__ points, uint32_t n, uint32_t c, uint32_t W,
                                                              uint32_t wide, g1a_t *__restrict__ rows) {
@@ -839,6 +916,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
         // 1024 partial sums per stream, 0.429 vs 0.429 ms: a level costs the ~9 us of its one dependent XYZZ addition in a
         // lone warp, not its launch)
         if (pl.red_r[l] != 2) msm_wsum_level_kernel<true><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, pl.red_r[l], l, level_out);
+        else if (ctx->msm_coop) msm_wsum_level_coop_kernel<<<dim3((4 * m_out + RED_THREADS - 1) / RED_THREADS, l + 1, pl.G), RED_THREADS, 0, ts>>>(level_in, m_in, m_out, l, level_out);
         else msm_wsum_level_kernel<false><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, 2, l, level_out);
         level_in = level_out;
     }
