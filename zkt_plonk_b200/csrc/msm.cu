@@ -67,7 +67,8 @@ struct MsmPlan {
 struct MsmWs {                           // carved out of ctx->msm_ws
     uint32_t *counts, *starts, *cursor, *ntasks, *task_base, *sorted;
     uint32_t *scan_tmp;                  // block sums for the scans
-    uint32_t *size_hist, *size_cursor;   // SEG + 1 bins
+    uint32_t *size_hist, *size_cursor;   // SEG + 1 bins (the cursors are the histogram after its in-place scan)
+    size_t zero_bytes;                   // counts, size_hist and misc are adjacent: bytes cleared per MSM, from counts on
     uint32_t *misc;                      // [0] heavy buckets, [1] total tasks, [2] chunk items, [3] chunk_out slots, [4] multi-chunk buckets
     uint32_t *heavy_list;                // buckets cut into more than one task
     uint32_t *heavy_slot;                // per heavy bucket: first slot in chunk_out, or ~0 when it has a single chunk
@@ -247,7 +248,8 @@ __global__ void __launch_bounds__(256) scan_sums_kernel(uint32_t *tile_sums, uin
     if (threadIdx.x == 0 && total_out) *total_out = running;
 }
 
-__global__ void __launch_bounds__(256) scan_apply_kernel(const uint32_t *in, uint32_t n, const uint32_t *tile_sums, uint32_t *out) {
+// out2 (may be null): a second copy of the result (the sort's write cursors start as a copy of the bucket offsets)
+__global__ void __launch_bounds__(256) scan_apply_kernel(const uint32_t *in, uint32_t n, const uint32_t *tile_sums, uint32_t *out, uint32_t *out2) {
     __shared__ uint32_t sm[16];
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 8, v[8], s = 0;
 #pragma unroll
@@ -255,14 +257,17 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const uint32_t *in, uin
     uint32_t total;
     uint32_t ex = block_exclusive_scan_256(s, sm, &total) + tile_sums[blockIdx.x];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+    for (int k = 0; k < 8; ++k) {
+        if (base + k < n) { out[base + k] = ex; if (out2) out2[base + k] = ex; }
+        ex += v[k];
+    }
 }
 
-int exclusive_scan(zkb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tmp, uint32_t *total_out) {
+int exclusive_scan(zkb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tmp, uint32_t *total_out, uint32_t *out2 = nullptr) {
     uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     scan_reduce_kernel<<<ntiles, 256, 0, ctx->stream>>>(in, n, tmp);
     scan_sums_kernel<<<1, 256, 0, ctx->stream>>>(tmp, ntiles, total_out);
-    scan_apply_kernel<<<ntiles, 256, 0, ctx->stream>>>(in, n, tmp, out);
+    scan_apply_kernel<<<ntiles, 256, 0, ctx->stream>>>(in, n, tmp, out, out2);
     ZKB_CUDA(ctx, cudaGetLastError());
     return ZKB_OK;
 }
@@ -758,9 +763,10 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
     const uint64_t max_heavy_tasks = 2 * (entries / pl.seg) + 2;   // tasks of buckets with more than seg points
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_counts = take(nb * 4), o_starts = take(nb * 4), o_cursor = take(nb * 4), o_ntasks = take(nb * 4),
-           o_tbase = take(nb * 4), o_sorted = take(entries * 4 + 4), o_scan = take((nb / SCAN_TILE + 2) * 4),
-           o_hist = take((SEG_MAX + 1) * 4), o_hcur = take((SEG_MAX + 1) * 4), o_misc = take(64), o_heavy = take(nb * 4),
+    // counts, the size histogram and the counters are adjacent: one memset clears the three
+    size_t o_counts = take(nb * 4), o_hist = take((SEG_MAX + 1) * 4), o_misc = take(64), o_zero_end = off,
+           o_starts = take(nb * 4), o_cursor = take(nb * 4), o_ntasks = take(nb * 4),
+           o_tbase = take(nb * 4), o_sorted = take(entries * 4 + 4), o_scan = take((nb / SCAN_TILE + 2) * 4), o_heavy = take(nb * 4),
            o_hslot = take(nb * 4), o_multi = take(nb * 4), o_citems = take((nb + max_tasks / HEAVY_CHUNK + 2) * 8),
            o_cout = take((max_tasks / (HEAVY_CHUNK / 2) + 4) * sizeof(g1x_t)),
            o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)), o_bval = take(nb * sizeof(g1x_t)),
@@ -783,7 +789,8 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
     char *p = (char *)buf.p;
     ws.counts = (uint32_t *)(p + o_counts); ws.starts = (uint32_t *)(p + o_starts); ws.cursor = (uint32_t *)(p + o_cursor);
     ws.ntasks = (uint32_t *)(p + o_ntasks); ws.task_base = (uint32_t *)(p + o_tbase); ws.sorted = (uint32_t *)(p + o_sorted);
-    ws.scan_tmp = (uint32_t *)(p + o_scan); ws.size_hist = (uint32_t *)(p + o_hist); ws.size_cursor = (uint32_t *)(p + o_hcur);
+    ws.scan_tmp = (uint32_t *)(p + o_scan); ws.size_hist = (uint32_t *)(p + o_hist); ws.size_cursor = ws.size_hist;
+    ws.zero_bytes = o_zero_end - o_counts;
     ws.misc = (uint32_t *)(p + o_misc); ws.heavy_list = (uint32_t *)(p + o_heavy); ws.task_order = (uint2 *)(p + o_order);
     ws.heavy_slot = (uint32_t *)(p + o_hslot); ws.multi_list = (uint32_t *)(p + o_multi); ws.chunk_items = (uint2 *)(p + o_citems);
     ws.chunk_out = (g1x_t *)(p + o_cout);
@@ -847,14 +854,11 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     st->last_entries = (uint64_t)n * pl.W; st->last_c = pl.c; st->last_W = pl.W;
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[0], s));
 
-    ZKB_CUDA(ctx, cudaMemsetAsync(ws.counts, 0, (size_t)nb * 4, s));
-    ZKB_CUDA(ctx, cudaMemsetAsync(ws.size_hist, 0, (SEG_MAX + 1) * 4, s));
-    ZKB_CUDA(ctx, cudaMemsetAsync(ws.misc, 0, 64, s));
+    ZKB_CUDA(ctx, cudaMemsetAsync(ws.counts, 0, ws.zero_bytes, s));           // counts, size_hist, misc
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.bucket_val, 0, (size_t)nb * sizeof(g1x_t), s));
     if (n32) msm_count_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, ws.counts);
-    rc = exclusive_scan(ctx, ws.counts, ws.starts, nb, ws.scan_tmp, nullptr);
+    rc = exclusive_scan(ctx, ws.counts, ws.starts, nb, ws.scan_tmp, nullptr, ws.cursor);
     if (rc) return rc;
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ws.cursor, ws.starts, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
     if (n32) msm_scatter_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, pl.id_base, pl.id_stride,
                                                                   ws.cursor, ws.sorted);
     // ---- batched-affine pair rounds (msm_pairs.cuh): each halves every bucket; the XYZZ accumulation below then works on
@@ -887,8 +891,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
                                                        ws.multi_list, ws.chunk_items);
     rc = exclusive_scan(ctx, ws.ntasks, ws.task_base, nb, ws.scan_tmp, ws.misc + 1);
     if (rc) return rc;
-    rc = exclusive_scan(ctx, ws.size_hist, ws.size_cursor, pl.seg + 1, ws.scan_tmp, nullptr);
-    if (rc) return rc;
+    scan_sums_kernel<<<1, 256, 0, s>>>(ws.size_hist, pl.seg + 1, nullptr);   // <= SEG_MAX + 1 bins: one CTA, in place (size_cursor == size_hist)
     msm_task_scatter_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, ws.ntasks, nb, pl.seg, ws.size_cursor, ws.task_order);
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[1], s));
     msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, pool, ws.sorted, ws.counts, ws.starts, ws.ntasks,
@@ -911,10 +914,12 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
         const uint32_t m_in = pl.red_m[l], m_out = pl.red_m[l + 1];
         dim3 grid((m_out + RED_THREADS - 1) / RED_THREADS, l + 1, pl.G);
         g1x_t *level_out = ws.red_buf[l & 1];
-        // (measured and dropped: profiles/r02f_msm_coop.jsonl -- binary levels with four lanes per addition, 0.50 instead of
-        // 0.43 ms at 2^19 buckets; profiles/r02v_msm_tail.jsonl -- the last ten levels as ONE launch of masked tree sums over the
-        // 1024 partial sums per stream, 0.429 vs 0.429 ms: a level costs the ~9 us of its one dependent XYZZ addition in a
-        // lone warp, not its launch)
+        // binary levels: four lanes per addition (msm_wsum_level_coop_kernel; 0.423 -> 0.386 ms at 2^19 buckets,
+        // profiles/r02z_msm_coop.jsonl).  A first version of that idea (every lane loading both points, fourteen products laid
+        // out over the lanes without regard to their dependencies, the last levels fused into one CTA) had measured 0.50 ms
+        // (profiles/r02f_msm_coop.jsonl).  Also measured and dropped: the last ten levels as ONE launch of masked tree sums over
+        // the 1024 partial sums per stream, 0.429 vs 0.429 ms (profiles/r02v_msm_tail.jsonl): a level costs its one dependent
+        // XYZZ addition, not its launch
         if (pl.red_r[l] != 2) msm_wsum_level_kernel<true><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, pl.red_r[l], l, level_out);
         else if (ctx->msm_coop) msm_wsum_level_coop_kernel<<<dim3((4 * m_out + RED_THREADS - 1) / RED_THREADS, l + 1, pl.G), RED_THREADS, 0, ts>>>(level_in, m_in, m_out, l, level_out);
         else msm_wsum_level_kernel<false><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, 2, l, level_out);
@@ -923,7 +928,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], ts));
     ZKB_CUDA(ctx, cudaGetLastError());
     st->ev_valid = true;
-    ctx->launches += 16 + pl.red_levels; // 3 scans x 3 kernels + count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduction levels
+    ctx->launches += 14 + pl.red_levels; // 2 scans x 3 kernels + the bin scan, count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduction levels
     // the last level's output is [stream][group][1]: stream 0 = plain total, stream 1 + k = total of A_k
     ZKB_CUDA(ctx, cudaMemcpyAsync(sl.pinned, pl.red_levels ? (const void *)level_in : (const void *)ws.bucket_val, out_bytes,
                                   cudaMemcpyDeviceToHost, ts));
