@@ -12,6 +12,8 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -237,11 +239,11 @@ int commit_finish_pts(zkb_ctx *ctx, size_t count, Pt *out) {
 // Returns false if a CUDA call failed.  Runs on the uploader thread of a proof.
 bool staged_upload(int device, uint64_t *dst_dev, const void *src_host, void *pinned, size_t bytes, cudaStream_t stream) {
     const size_t piece = (size_t)1 << 20, pieces = (bytes + piece - 1) / piece;
-    // threads: one per 8 MiB, 2..4.  More starve the DMA engine of host memory bandwidth (8 threads: 18.8 instead of 17.6 ms
-    // per 2^18-gate proof), a single one cannot feed it at 32 MiB per wire (55.8 instead of 51.5 ms at 2^20;
-    // profiles/r02v_ab_prove*.jsonl)
+    // threads: one per 8 MiB, 1..4.  More starve the DMA engine of host memory bandwidth (8 threads: 18.8 instead of 17.6 ms
+    // per 2^18-gate proof, one or two: 17.6), a single one cannot feed it at 32 MiB per wire (55.8 instead of 51.5 ms at
+    // 2^20; profiles/r02v_ab_prove*.jsonl); the 1/world slices of a multi-GPU proof take one thread per rank
     const unsigned hw = std::thread::hardware_concurrency();
-    size_t nt = std::min<size_t>(4, std::max<size_t>(2, bytes >> 23));
+    size_t nt = std::min<size_t>(4, std::max<size_t>(1, bytes >> 23));
     if (hw < 4) nt = 1;
     if (const char *e = getenv("ZKB_STAGE_THREADS")) nt = (size_t)std::max(1, atoi(e));   // for A/B measurements
     nt = pieces < nt ? pieces : nt;
@@ -759,6 +761,12 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
     // wire a: issued from the proving thread between the commitments, the copies left the GPU idle for 0.35 ms per wire at
     // n = 2^18 (profiles/r02t_trace_2^18.jsonl).  up_recorded = number of wires whose event has been recorded.
     std::atomic<int> up_recorded{0}, up_failed{0};
+    std::mutex up_mutex;
+    std::condition_variable up_cv;                                      // the proving thread sleeps until a wire's event exists:
+    auto up_publish = [&](int wires_recorded) {                         // several ranks share one host, a spinning thread per rank starves the stagers
+        { std::lock_guard<std::mutex> lock(up_mutex); up_recorded.store(wires_recorded, std::memory_order_release); }
+        up_cv.notify_all();
+    };
     std::thread uploader([&]() {
         bool ok = cudaSetDevice(ctx->device) == cudaSuccess;
         cudaStream_t cs = pk->copy_stream;
@@ -774,7 +782,7 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
                 gather_wire_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>((uint4 *)wires[k].dev, pk->d_wiring[k], (const uint4 *)pk->d_vars, n);
             ok = ok && cudaGetLastError() == cudaSuccess && cudaEventRecord(pk->wire_ev[2], cs) == cudaSuccess;
             if (!ok) up_failed.store(1);
-            up_recorded.store(3, std::memory_order_release);
+            up_publish(3);
             return;
         }
         for (int k = 0; k < 3; ++k) {
@@ -783,7 +791,7 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
             if (ok && split) ok = zkb_comm_allgather_dev(ctx, wires[k].dev, chunk * 32, cs) == ZKB_OK;
             ok = ok && cudaEventRecord(pk->wire_ev[k], cs) == cudaSuccess;
             if (!ok) up_failed.store(1);
-            up_recorded.store(k + 1, std::memory_order_release);
+            up_publish(k + 1);
         }
     });
     Joiner uploader_joiner{uploader};
@@ -792,7 +800,10 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
     // behind the uploads: the last group starts its (larger) MSM only when the last wire has arrived (measured on 8 B200:
     // round 1 4.6 instead of 3.5 ms at n = 2^20, profiles/r02i_bench_n8.json).
     for (int k = 0; k < 3; ++k) {
-        while (up_recorded.load(std::memory_order_acquire) <= k) std::this_thread::yield();
+        {
+            std::unique_lock<std::mutex> lock(up_mutex);
+            up_cv.wait(lock, [&]() { return up_recorded.load(std::memory_order_acquire) > k; });
+        }
         if (up_failed.load()) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_prove: upload of the wires failed");
         ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->wire_ev[vars ? 2 : k], 0));
         if (k == 0) tick(0);
