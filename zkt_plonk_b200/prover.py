@@ -635,8 +635,7 @@ class NativeProver:
         if from_vars:
             return self._prove_vars(blinders, timings)
         a, b, cc = (np.ascontiguousarray(x, dtype=np.uint64) for x in (c.a, c.b, c.c))
-        table = ints_to_mont_array(c.table) if c.table else np.zeros((1, 4), dtype=np.uint64)
-        pi = ints_to_mont_array(list(c.pi.values())) if c.pi else np.zeros((1, 4), dtype=np.uint64)
+        table, pi = self._table_pi()
         bl = ints_to_mont_array(blinders)
         out = np.zeros(802, dtype=np.uint8)
         tm = (ctypes.c_float * 8)() if timings else None
@@ -650,12 +649,23 @@ class NativeProver:
             return raw, dict(zip(names, [float(x) for x in tm]))
         return raw
 
+    def _table_pi(self):
+        """The lookup table and the public inputs as Montgomery limbs (what the C ABI takes).  The circuit holds them as Python
+        integers; converting 1024 table entries costs ~1.8 ms of interpreter time, so it is done once per prover, not per proof
+        (a caller on the reference's side hands its field elements over as they are).  Assign a new list to change the table."""
+        c = self.circuit
+        key = (id(c.table), len(c.table), tuple(c.pi.items()) if c.pi else ())    # another list object = another table
+        if getattr(self, "_tp_key", None) != key:
+            table = ints_to_mont_array(c.table) if c.table else np.zeros((1, 4), dtype=np.uint64)
+            pi = ints_to_mont_array(list(c.pi.values())) if c.pi else np.zeros((1, 4), dtype=np.uint64)
+            self._tp_key, self._tp = key, (table, pi)
+        return self._tp
+
     def _prove_vars(self, blinders, timings):
         import ctypes
         c = self.circuit
         vals = np.ascontiguousarray(c.var_values, dtype=np.uint64)
-        table = ints_to_mont_array(c.table) if c.table else np.zeros((1, 4), dtype=np.uint64)
-        pi = ints_to_mont_array(list(c.pi.values())) if c.pi else np.zeros((1, 4), dtype=np.uint64)
+        table, pi = self._table_pi()
         bl = ints_to_mont_array(blinders)
         out = np.zeros(802, dtype=np.uint8)
         tm = (ctypes.c_float * 8)() if timings else None
