@@ -130,6 +130,8 @@ int zkb_ctx_create(int device, zkb_ctx **out) {
     if (pf && atoi(pf) >= 0 && atoi(pf) <= 16) ctx->msm_prefetch = atoi(pf);
     const char *co = getenv("ZKB_MSM_COOP");                    // "0": one thread per addition in the binary reduction levels (A/B)
     if (co && (co[0] == '0' || co[0] == '1') && co[1] == 0) ctx->msm_coop = co[0] - '0';
+    const char *nf = getenv("ZKB_NTT_FOLD");                    // "0": do not fold the coset factor into the inter-pass table (A/B)
+    if (nf && nf[0] == '0' && nf[1] == 0) ctx->ntt_no_fold = true;
     const char *nk = getenv("ZKB_NTT_KERNEL");                  // "0" / "1" / "2": see zkb_ntt_set_kernel
     if (nk && nk[0] >= '0' && nk[0] <= '2' && nk[1] == 0) ctx->ntt_kernel = nk[0] - '0';
     *out = ctx;

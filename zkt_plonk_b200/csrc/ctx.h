@@ -27,6 +27,7 @@ struct zkb_ctx {
     std::map<uint64_t, DevBuf> tables;
     DevBuf ntt_scratch;          // ping-pong buffer for multi-pass transforms
     bool ntt_no_direct = false;  // true: never build the fully expanded twiddle / coset tables (saves N x 32 B each)
+    bool ntt_no_fold = false;    // true: forward coset transforms stream the expanded coset table instead of folding g^c (A/B)
     int ntt_kernel = 0;          // 0: radix-4 pass kernel where it measured faster (2048-element tiles), 1: the generic kernel
                                  // everywhere, 2: the radix-4 kernel for every tile of 256..2048 elements
     DevBuf stage;                // staging buffer for host-pointer entry points

@@ -39,6 +39,7 @@ struct PassArgs {
     const uint4 *cs2;       // two-level table of coset powers (g^e or g^-e / n): lo[2^cs_s] then hi
     const uint4 *tw_direct; // optional: w_M^(c*k) at [c * T + k]  (one product instead of two per element)
     const uint4 *cs_direct; // optional: coset power of every index e at [e]
+    const uint4 *cs_tile;   // optional (first pass of a forward coset transform): (g^S)^j, j < T -- see the fold below
     unsigned long long len; // elements >= len read as zero (first pass only)
     uint32_t t, log_s, log_n;
     uint32_t tw_s, cs_s;
@@ -72,6 +73,15 @@ __device__ __forceinline__ fe_t pow2lvl(const uint4 *tab, uint32_t s, unsigned l
     fe_t a = fload_ro(tab + 2 * (size_t)lo);
     fe_t b = fload_ro(tab + 2 * ((size_t)(1u << s) + hi));
     return fmul<FrP>(a, b);
+}
+
+// Factor of input element idx = c + j * S of the first pass of a forward coset transform.  g^idx = g^c * (g^S)^j, and the
+// tile's transform is linear, so g^c can leave through the OUTPUT side: with cs_tile set the load multiplies by (g^S)^j (T
+// entries: they stay in L1 / L2) and the inter-pass table of this pass carries w_M^(c k) * g^c.  Same number of products,
+// one expanded table (N x 32 B) less to stream per transform.
+__device__ __forceinline__ fe_t coset_in_factor(const PassArgs &a, unsigned long long idx, uint32_t j) {
+    if (a.cs_tile) return fload_ro(a.cs_tile + 2 * (size_t)j);
+    return a.cs_direct ? fload_ro(a.cs_direct + 2 * idx) : pow2lvl(a.cs2, a.cs_s, idx);
 }
 
 // inter-pass twiddle / output scaling and the store of output k of this tile (shared by both store paths)
@@ -117,7 +127,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const __grid_constant__ P
         fe_t v;
         if (idx < a.len) {
             v = fload(in + 2 * idx);
-            if (a.mode & M_IN_COSET) v = fmul<FrP>(v, a.cs_direct ? fload_ro(a.cs_direct + 2 * idx) : pow2lvl(a.cs2, a.cs_s, idx));
+            if (a.mode & M_IN_COSET) v = fmul<FrP>(v, coset_in_factor(a, idx, j));
         } else {
             v = fzero<FrP>();
         }
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__((1 << LT) / 8, 768 / ((1 << LT) / 8)) ntt_pass
         const unsigned long long idx = base + ((unsigned long long)j << a.log_s);
         if (idx >= a.len) return fzero<FrP>();
         fe_t v = fload(in + 2 * idx);
-        if (a.mode & M_IN_COSET) v = fmul<FrP>(v, a.cs_direct ? fload_ro(a.cs_direct + 2 * idx) : pow2lvl(a.cs2, a.cs_s, idx));
+        if (a.mode & M_IN_COSET) v = fmul<FrP>(v, coset_in_factor(a, idx, j));
         return v;
     };
 
@@ -315,6 +325,15 @@ __global__ void expand_twiddle_kernel(uint4 *out, const uint4 *tw2, uint32_t tw_
     if (i >= count) return;
     unsigned long long c = i >> t, k = i & ((1ull << t) - 1);
     fstore(out + 2 * i, pow2lvl(tw2, tw_s, c * k));
+}
+
+// the same with the tile's coset factor folded in: out[c * T + k] = w_M^(c*k) * g^c
+__global__ void expand_twiddle_coset_kernel(uint4 *out, const uint4 *tw2, uint32_t tw_s, const uint4 *cs2, uint32_t cs_s, uint32_t t,
+                                            unsigned long long count) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned long long c = i >> t, k = i & ((1ull << t) - 1);
+    fstore(out + 2 * i, fmul<FrP>(pow2lvl(tw2, tw_s, c * k), pow2lvl(cs2, cs_s, c)));
 }
 
 // out[e] = base^e (pre-scaled) for e < count, expanded from the two-level table
@@ -464,8 +483,10 @@ int zkb_ntt_run_batch(zkb_ctx *ctx, uint64_t *const *d_ptrs, size_t count, size_
         if (rc) return rc;
     }
     const bool direct = log_n >= 12 && log_n <= DIRECT_MAX_LOG && !ctx->ntt_no_direct;
+    // forward coset transforms of two or more passes fold the coset factor (coset_in_factor): no expanded coset table then
+    const bool fold_coset = direct && coset && !inverse && m >= 2 && !ctx->ntt_no_fold;
     const uint4 *cs_direct = nullptr;
-    if (coset && direct) {
+    if (coset && direct && !fold_coset) {
         uint64_t key = (5ull << 32) | (log_n << 1) | (unsigned)inverse;
         int rc = get_direct_table(ctx, key, n, cs2, cs_s, -1, &cs_direct);
         if (rc) return rc;
@@ -494,7 +515,32 @@ int zkb_ntt_run_batch(zkb_ctx *ctx, uint64_t *const *d_ptrs, size_t count, size_
             uint64_t key = (2ull << 32) | (lm << 1) | (unsigned)inverse;
             rc = get_2lvl_table(ctx, key, lm, w, host::one(host::FR), &a.tw2, &a.tw_s);
             if (rc) return rc;
-            if (direct) {
+            if (direct && first && coset && !inverse && fold_coset) {
+                // forward coset transform, first pass: (g^S)^j at the load, g^c in the inter-pass table (coset_in_factor)
+                uint64_t ckey = (6ull << 32) | ((uint64_t)t << 16) | (log_n << 1);
+                auto it = ctx->tables.find(ckey);
+                if (it == ctx->tables.end()) {
+                    DevBuf b;
+                    rc = zkb_reserve(ctx, b, ((size_t)1 << t) * 32);
+                    if (rc) return rc;
+                    rc = build_pow_table(ctx, (uint4 *)b.p, host::from_u64(5, host::FR), host::one(host::FR), 1u << t, log_s);
+                    if (rc) return rc;
+                    it = ctx->tables.emplace(ckey, b).first;
+                }
+                a.cs_tile = (const uint4 *)it->second.p;
+                uint64_t dkey = (7ull << 32) | ((uint64_t)t << 16) | (lm << 1);
+                it = ctx->tables.find(dkey);
+                if (it == ctx->tables.end()) {
+                    DevBuf b;
+                    rc = zkb_reserve(ctx, b, ((size_t)1 << lm) * 32);
+                    if (rc) return rc;
+                    const unsigned long long cnt = 1ull << lm;
+                    expand_twiddle_coset_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>((uint4 *)b.p, a.tw2, a.tw_s, cs2, cs_s, t, cnt);
+                    ZKB_CUDA(ctx, cudaGetLastError());
+                    it = ctx->tables.emplace(dkey, b).first;
+                }
+                a.tw_direct = (const uint4 *)it->second.p;
+            } else if (direct) {
                 uint64_t dkey = (4ull << 32) | ((uint64_t)t << 16) | (lm << 1) | (unsigned)inverse;
                 rc = get_direct_table(ctx, dkey, 1ull << lm, a.tw2, a.tw_s, (int)t, &a.tw_direct);
                 if (rc) return rc;
