@@ -6,10 +6,19 @@
  * plonk-core/src/proof_system/prove.rs:59-74).  Each entry point below names the reference interface it
  * replaces; INTEGRATION.md shows the Rust `extern "C"` crate that binds them behind `D` and `PC`.
  *
+ * Curves.  The reference is generic over the pairing engine (its own full test runs on Bls12_381 and Bls12_377,
+ * plonk-core/src/plonk.rs:226-254; the CLI fixes Bn254, bin/src/instance.rs:7-10) and Rust monomorphises per curve.  This library
+ * is compiled once per curve with identical entry points: libzkb200.so (BN254: everything below), libzkb200_bls12_381.so and
+ * libzkb200_bls12_377.so (context, memory, field hooks, NTT, MSM / commitments, polynomial kernels, multi-GPU; the protocol
+ * driver, key files and pairing verifier return ZKB_ERR_UNSUPPORTED there).  zkb_curve_info tells a caller which one it loaded
+ * and the element widths: array sizes written below as [8] / [16] / [80] are the BN254 ones (fq_words = 4); on the BLS12 curves
+ * an affine point is 12 words and an XYZZ partial sum 24 (fq_words = 6).  Scalars are 4 words on every curve.
+ *
  * Conventions (identical to arkworks 0.3 in-memory forms, so no conversion at the boundary):
- *   - Fr / Fq element  = 4 x uint64_t little-endian limbs, MONTGOMERY form (R = 2^256).
+ *   - Fr element       = 4 x uint64_t little-endian limbs, MONTGOMERY form (R = 2^256).
+ *   - Fq element       = fq_words x uint64_t little-endian limbs, MONTGOMERY form (R = 2^256 on BN254, 2^384 on BLS12-381 / 377).
  *   - MSM scalars      = 4 x uint64_t little-endian limbs, CANONICAL form (what `into_repr()` yields).
- *   - G1 affine point  = x || y (8 x uint64_t, Montgomery Fq); the point at infinity is (0, 0).
+ *   - G1 affine point  = x || y (2 x fq_words uint64_t, Montgomery Fq); the point at infinity is (0, 0).
  *   - NTT data is in natural order on input and output.
  *   - Every function returns 0 on success and a negative zkb_status otherwise; nothing throws or aborts.
  *     zkb_last_error(ctx) gives a human-readable reason.  Pointers are caller-owned and not retained.
@@ -39,10 +48,11 @@ typedef struct zkb_ctx zkb_ctx;
 typedef enum {
     ZKB_OK = 0,
     ZKB_ERR_INVALID = -1,    /* bad argument (null pointer, size not allowed ...) */
-    ZKB_ERR_DOMAIN = -2,     /* log_n > TWO_ADICITY (28): Error::InvalidEvalDomainSize, prove.rs:77-81 */
+    ZKB_ERR_DOMAIN = -2,     /* log_n > TWO_ADICITY (28 on BN254): Error::InvalidEvalDomainSize, prove.rs:77-81 */
     ZKB_ERR_CUDA = -3,       /* a CUDA runtime call failed */
     ZKB_ERR_NO_SRS = -4,     /* MSM asked for more points than the loaded SRS holds (kzg10 TooManyCoefficients) */
-    ZKB_ERR_OOM = -5
+    ZKB_ERR_OOM = -5,
+    ZKB_ERR_UNSUPPORTED = -6 /* entry point not compiled into this curve's build of the library (zkb_curve_info) */
 } zkb_status;
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
@@ -55,6 +65,12 @@ ZKB_API int zkb_ctx_set_stream(zkb_ctx *ctx, void *cuda_stream);
 ZKB_API int zkb_ctx_sync(zkb_ctx *ctx);
 ZKB_API const char *zkb_last_error(zkb_ctx *ctx);
 ZKB_API const char *zkb_version(void);
+/* Which curve this shared object was compiled for (the `E: PairingEngine` of the reference's generics): curve_id 0 = BN254,
+ * 1 = BLS12-381, 2 = BLS12-377; 64-bit words of a scalar and of a base-field element; bit length of r; has_prover = 1 when
+ * zkb_plonk_* / key files / zkb_plonk_verify are compiled in.  Any pointer may be NULL.  Needs no context and no GPU. */
+ZKB_API int zkb_curve_info(int *curve_id, int *fr_words, int *fq_words, int *fr_bits, int *has_prover);
+/* The curve's G1 generator (ark-* 0.3 G1_GENERATOR_X / _Y), affine, Montgomery form: 2 x fq_words words. */
+ZKB_API int zkb_g1_generator(uint64_t *out_xy);
 
 /* ---- device memory (for HBM-resident pipelines) -------------------------------------------------------------- */
 ZKB_API int zkb_dev_alloc(zkb_ctx *ctx, size_t bytes, void **dptr);
@@ -66,7 +82,7 @@ ZKB_API int zkb_d2h(zkb_ctx *ctx, void *dst_host, const void *src_dev, size_t by
 /* Reference: ark-poly 0.3 Radix2EvaluationDomain via plonk-core/src/util.rs:63-140 (poly_from_evals :63-86,
  * poly_from_coset_evals :90-100, evals_from_poly_ref :104-113, coset_evals_from_poly(_ref) :117-140).
  * data holds 2^log_n elements of which the first `len` are input (the rest are treated as zero, as
- * fft_in_place's resize does); inverse: multiplies by n^-1; coset: generator g = 5 (forward: scale coefficient i
+ * fft_in_place's resize does); inverse: multiplies by n^-1; coset: generator g = Fr::multiplicative_generator() (5 on BN254, 7 on BLS12-381, 22 on BLS12-377; forward: scale coefficient i
  * by g^i first; inverse: scale output i by g^-i). */
 ZKB_API int zkb_ntt(zkb_ctx *ctx, uint64_t *data_host, size_t len, unsigned log_n, int inverse, int coset);
 ZKB_API int zkb_ntt_dev(zkb_ctx *ctx, uint64_t *data_dev, size_t len, unsigned log_n, int inverse, int coset);

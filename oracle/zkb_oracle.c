@@ -44,7 +44,10 @@
 typedef unsigned __int128 u128;
 typedef uint64_t u64;
 
-typedef struct { u64 l[4]; } fe;           /* one field element, LE limbs */
+typedef struct { u64 l[4]; } fe;           /* one scalar-field element, LE limbs (Fr has 4 limbs on every curve) */
+#include "zko_curve_params.h"
+#define NQ ZKO_FQ_L
+typedef struct { u64 l[NQ]; } fq;          /* one base-field element: 4 limbs on BN254, 6 on BLS12-381 / BLS12-377 */
 
 typedef struct {
     u64 p[4];     /* modulus */
@@ -52,182 +55,162 @@ typedef struct {
     u64 r2[4];    /* R^2 mod p */
     u64 inv;      /* -p^-1 mod 2^64 */
 } fparams;
+typedef struct { u64 p[NQ], r[NQ], r2[NQ], inv; } fqparams;
 
-static const fparams FR = {
-    {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
-    {0xac96341c4ffffffbULL, 0x36fc76959f60cd29ULL, 0x666ea36f7879462eULL, 0x0e0a77c19a07df2fULL},
-    {0x1bb8e645ae216da7ULL, 0x53fe3ab1e35c59e3ULL, 0x8c49833d53bb8085ULL, 0x0216d0b17f4e44a5ULL},
-    0xc2e1f593efffffffULL};
+static const fparams FR = ZKO_FR_INIT;
+static const fqparams FQ = ZKO_FQ_INIT;
 
-static const fparams FQ = {
-    {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
-    {0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL},
-    {0xf32cfc5b538afa89ULL, 0xb5e71911d44501fbULL, 0x47ab1eff0a417ff6ULL, 0x06d89f71cab8351fULL},
-    0x87d20782e4866389ULL};
-
-/* ------------------------------------------------------------------ field arithmetic */
-static inline int fe_is_zero(const fe *a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0; }
-static inline int fe_eq(const fe *a, const fe *b) {
-    return a->l[0] == b->l[0] && a->l[1] == b->l[1] && a->l[2] == b->l[2] && a->l[3] == b->l[3];
-}
-static inline int geq(const u64 *a, const u64 *b) {
-    for (int i = 3; i >= 0; --i) { if (a[i] != b[i]) return a[i] > b[i]; }
-    return 1;
-}
-static inline void sub_nored(u64 *o, const u64 *a, const u64 *b) {
-    u128 br = 0;
-    for (int i = 0; i < 4; ++i) { u128 t = (u128)a[i] - b[i] - (u64)br; o[i] = (u64)t; br = (t >> 64) & 1; }
-}
-static inline void fp_add(fe *o, const fe *a, const fe *b, const fparams *P) {
-    u128 c = 0; u64 t[4];
-    for (int i = 0; i < 4; ++i) { c += (u128)a->l[i] + b->l[i]; t[i] = (u64)c; c >>= 64; }
-    if (geq(t, P->p)) sub_nored(o->l, t, P->p); else memcpy(o->l, t, 32);   /* p < 2^254: no carry out */
-}
-static inline void fp_sub(fe *o, const fe *a, const fe *b, const fparams *P) {
-    u64 t[4]; u128 br = 0;
-    for (int i = 0; i < 4; ++i) { u128 d = (u128)a->l[i] - b->l[i] - (u64)br; t[i] = (u64)d; br = (d >> 64) & 1; }
-    if (br) { u128 c = 0; for (int i = 0; i < 4; ++i) { c += (u128)t[i] + P->p[i]; t[i] = (u64)c; c >>= 64; } }
-    memcpy(o->l, t, 32);
-}
-static inline void fp_neg(fe *o, const fe *a, const fparams *P) {
-    if (fe_is_zero(a)) { *o = *a; return; }
-    sub_nored(o->l, P->p, a->l);
-}
-static inline void fp_dbl(fe *o, const fe *a, const fparams *P) { fp_add(o, a, a, P); }
-
-/* CIOS Montgomery multiplication, 4 limbs */
-static inline void fp_mul(fe *o, const fe *a, const fe *b, const fparams *P) {
-    u64 t[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < 4; ++i) {
-        u128 c = 0;
-        for (int j = 0; j < 4; ++j) { c += (u128)a->l[j] * b->l[i] + t[j]; t[j] = (u64)c; c >>= 64; }
-        c += t[4]; t[4] = (u64)c; t[5] = (u64)(c >> 64);
-        u64 m = t[0] * P->inv;
-        c = (u128)m * P->p[0] + t[0]; c >>= 64;
-        for (int j = 1; j < 4; ++j) { c += (u128)m * P->p[j] + t[j]; t[j - 1] = (u64)c; c >>= 64; }
-        c += t[4]; t[3] = (u64)c; t[4] = t[5] + (u64)(c >> 64);
-    }
-    if (t[4] || geq(t, P->p)) sub_nored(o->l, t, P->p); else memcpy(o->l, t, 32);
-}
-static inline void fp_sqr(fe *o, const fe *a, const fparams *P) { fp_mul(o, a, a, P); }
-static inline void fp_to_mont(fe *o, const fe *a, const fparams *P) { fe r2; memcpy(r2.l, P->r2, 32); fp_mul(o, a, &r2, P); }
-static inline void fp_from_mont(fe *o, const fe *a, const fparams *P) { fe one = {{1, 0, 0, 0}}; fp_mul(o, a, &one, P); }
-static inline void fp_one(fe *o, const fparams *P) { memcpy(o->l, P->r, 32); }
-static inline void fp_from_u64(fe *o, u64 v, const fparams *P) { fe t = {{v, 0, 0, 0}}; fp_to_mont(o, &t, P); }
-
-static void fp_pow(fe *o, const fe *a, const u64 e[4], const fparams *P) {
-    fe acc; fp_one(&acc, P);
-    for (int i = 255; i >= 0; --i) {
-        fp_sqr(&acc, &acc, P);
-        if ((e[i >> 6] >> (i & 63)) & 1) fp_mul(&acc, &acc, a, P);
-    }
-    *o = acc;
-}
-/* a^(p-2); a must be non-zero (the reference unwraps inverse(), permutation/mod.rs:242) */
-static void fp_inv(fe *o, const fe *a, const fparams *P) {
-    u64 e[4]; u64 two[4] = {2, 0, 0, 0};
-    sub_nored(e, P->p, two);
-    fp_pow(o, a, e, P);
-}
+/* ------------------------------------------------------------------ field arithmetic: fp_* over Fr's 4 limbs, fq_* over Fq's NQ */
+#define NL 4
+#define FE fe
+#define FPARAMS fparams
+#define FN(name) fp_##name
+#include "zko_field.inc"
+#undef NL
+#undef FE
+#undef FPARAMS
+#undef FN
+#define NL NQ
+#define FE fq
+#define FPARAMS fqparams
+#define FN(name) fq_##name
+#include "zko_field.inc"
+#undef NL
+#undef FE
+#undef FPARAMS
+#undef FN
+static inline int fe_is_zero(const fe *a) { return fp_is_zero(a); }
+static inline int fe_eq(const fe *a, const fe *b) { return fp_eq(a, b); }
+static inline int geq(const u64 *a, const u64 *b) { return fp_geq(a, b); }
+static inline void sub_nored(u64 *o, const u64 *a, const u64 *b) { fp_sub_nored(o, a, b); }
 
 /* ------------------------------------------------------------------ G1 Jacobian (Z == 0 is infinity) */
-typedef struct { fe x, y, z; } g1j;
-typedef struct { fe x, y; } g1a;            /* (0,0) encodes infinity at the C boundary */
+static const fq FQ_ZERO = {{0}};
+typedef struct { fq x, y, z; } g1j;
+typedef struct { fq x, y; } g1a;            /* (0,0) encodes infinity at the C boundary */
 
-static inline int g1a_is_inf(const g1a *p) { return fe_is_zero(&p->x) && fe_is_zero(&p->y); }
-static inline void g1j_set_inf(g1j *p) { memset(p, 0, sizeof *p); fp_one(&p->x, &FQ); fp_one(&p->y, &FQ); }
-static inline int g1j_is_inf(const g1j *p) { return fe_is_zero(&p->z); }
+static inline int g1a_is_inf(const g1a *p) { return fq_is_zero(&p->x) && fq_is_zero(&p->y); }
+static inline void g1j_set_inf(g1j *p) { memset(p, 0, sizeof *p); fq_one(&p->x, &FQ); fq_one(&p->y, &FQ); }
+static inline int g1j_is_inf(const g1j *p) { return fq_is_zero(&p->z); }
 
 static void g1j_double(g1j *r, const g1j *p) {           /* dbl-2009-l */
     if (g1j_is_inf(p)) { *r = *p; return; }
-    fe a, b, c, d, e, f, t;
-    fp_sqr(&a, &p->x, &FQ); fp_sqr(&b, &p->y, &FQ); fp_sqr(&c, &b, &FQ);
-    fp_add(&d, &p->x, &b, &FQ); fp_sqr(&d, &d, &FQ); fp_sub(&d, &d, &a, &FQ); fp_sub(&d, &d, &c, &FQ); fp_dbl(&d, &d, &FQ);
-    fp_dbl(&e, &a, &FQ); fp_add(&e, &e, &a, &FQ);
-    fp_sqr(&f, &e, &FQ);
-    fe z3; fp_mul(&z3, &p->y, &p->z, &FQ); fp_dbl(&z3, &z3, &FQ);
-    fe x3; fp_dbl(&t, &d, &FQ); fp_sub(&x3, &f, &t, &FQ);
-    fe y3; fp_sub(&t, &d, &x3, &FQ); fp_mul(&y3, &e, &t, &FQ);
-    fp_dbl(&c, &c, &FQ); fp_dbl(&c, &c, &FQ); fp_dbl(&c, &c, &FQ); fp_sub(&y3, &y3, &c, &FQ);
+    fq a, b, c, d, e, f, t;
+    fq_sqr(&a, &p->x, &FQ); fq_sqr(&b, &p->y, &FQ); fq_sqr(&c, &b, &FQ);
+    fq_add(&d, &p->x, &b, &FQ); fq_sqr(&d, &d, &FQ); fq_sub(&d, &d, &a, &FQ); fq_sub(&d, &d, &c, &FQ); fq_dbl(&d, &d, &FQ);
+    fq_dbl(&e, &a, &FQ); fq_add(&e, &e, &a, &FQ);
+    fq_sqr(&f, &e, &FQ);
+    fq z3; fq_mul(&z3, &p->y, &p->z, &FQ); fq_dbl(&z3, &z3, &FQ);
+    fq x3; fq_dbl(&t, &d, &FQ); fq_sub(&x3, &f, &t, &FQ);
+    fq y3; fq_sub(&t, &d, &x3, &FQ); fq_mul(&y3, &e, &t, &FQ);
+    fq_dbl(&c, &c, &FQ); fq_dbl(&c, &c, &FQ); fq_dbl(&c, &c, &FQ); fq_sub(&y3, &y3, &c, &FQ);
     r->x = x3; r->y = y3; r->z = z3;
 }
 
 static void g1j_add_mixed(g1j *r, const g1j *p, const g1a *q) {   /* madd-2007-bl */
     if (g1a_is_inf(q)) { *r = *p; return; }
-    if (g1j_is_inf(p)) { r->x = q->x; r->y = q->y; fp_one(&r->z, &FQ); return; }
-    fe z1z1, u2, s2, h, hh, i, j, rr, v, t;
-    fp_sqr(&z1z1, &p->z, &FQ);
-    fp_mul(&u2, &q->x, &z1z1, &FQ);
-    fp_mul(&s2, &q->y, &p->z, &FQ); fp_mul(&s2, &s2, &z1z1, &FQ);
-    if (fe_eq(&u2, &p->x) && fe_eq(&s2, &p->y)) { g1j_double(r, p); return; }
-    fp_sub(&h, &u2, &p->x, &FQ);
-    fp_sqr(&hh, &h, &FQ);
-    fp_dbl(&i, &hh, &FQ); fp_dbl(&i, &i, &FQ);
-    fp_mul(&j, &h, &i, &FQ);
-    fp_sub(&rr, &s2, &p->y, &FQ); fp_dbl(&rr, &rr, &FQ);
-    fp_mul(&v, &p->x, &i, &FQ);
-    fe x3, y3, z3;
-    fp_sqr(&x3, &rr, &FQ); fp_sub(&x3, &x3, &j, &FQ); fp_sub(&x3, &x3, &v, &FQ); fp_sub(&x3, &x3, &v, &FQ);
-    fp_sub(&t, &v, &x3, &FQ); fp_mul(&y3, &rr, &t, &FQ);
-    fp_mul(&t, &p->y, &j, &FQ); fp_dbl(&t, &t, &FQ); fp_sub(&y3, &y3, &t, &FQ);
-    fp_add(&z3, &p->z, &h, &FQ); fp_sqr(&z3, &z3, &FQ); fp_sub(&z3, &z3, &z1z1, &FQ); fp_sub(&z3, &z3, &hh, &FQ);
+    if (g1j_is_inf(p)) { r->x = q->x; r->y = q->y; fq_one(&r->z, &FQ); return; }
+    fq z1z1, u2, s2, h, hh, i, j, rr, v, t;
+    fq_sqr(&z1z1, &p->z, &FQ);
+    fq_mul(&u2, &q->x, &z1z1, &FQ);
+    fq_mul(&s2, &q->y, &p->z, &FQ); fq_mul(&s2, &s2, &z1z1, &FQ);
+    if (fq_eq(&u2, &p->x) && fq_eq(&s2, &p->y)) { g1j_double(r, p); return; }
+    fq_sub(&h, &u2, &p->x, &FQ);
+    fq_sqr(&hh, &h, &FQ);
+    fq_dbl(&i, &hh, &FQ); fq_dbl(&i, &i, &FQ);
+    fq_mul(&j, &h, &i, &FQ);
+    fq_sub(&rr, &s2, &p->y, &FQ); fq_dbl(&rr, &rr, &FQ);
+    fq_mul(&v, &p->x, &i, &FQ);
+    fq x3, y3, z3;
+    fq_sqr(&x3, &rr, &FQ); fq_sub(&x3, &x3, &j, &FQ); fq_sub(&x3, &x3, &v, &FQ); fq_sub(&x3, &x3, &v, &FQ);
+    fq_sub(&t, &v, &x3, &FQ); fq_mul(&y3, &rr, &t, &FQ);
+    fq_mul(&t, &p->y, &j, &FQ); fq_dbl(&t, &t, &FQ); fq_sub(&y3, &y3, &t, &FQ);
+    fq_add(&z3, &p->z, &h, &FQ); fq_sqr(&z3, &z3, &FQ); fq_sub(&z3, &z3, &z1z1, &FQ); fq_sub(&z3, &z3, &hh, &FQ);
     r->x = x3; r->y = y3; r->z = z3;
 }
 
 static void g1j_add(g1j *r, const g1j *p, const g1j *q) {         /* add-2007-bl */
     if (g1j_is_inf(p)) { *r = *q; return; }
     if (g1j_is_inf(q)) { *r = *p; return; }
-    fe z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t;
-    fp_sqr(&z1z1, &p->z, &FQ); fp_sqr(&z2z2, &q->z, &FQ);
-    fp_mul(&u1, &p->x, &z2z2, &FQ); fp_mul(&u2, &q->x, &z1z1, &FQ);
-    fp_mul(&s1, &p->y, &q->z, &FQ); fp_mul(&s1, &s1, &z2z2, &FQ);
-    fp_mul(&s2, &q->y, &p->z, &FQ); fp_mul(&s2, &s2, &z1z1, &FQ);
-    if (fe_eq(&u1, &u2) && fe_eq(&s1, &s2)) { g1j_double(r, p); return; }
-    fp_sub(&h, &u2, &u1, &FQ);
-    fp_dbl(&i, &h, &FQ); fp_sqr(&i, &i, &FQ);
-    fp_mul(&j, &h, &i, &FQ);
-    fp_sub(&rr, &s2, &s1, &FQ); fp_dbl(&rr, &rr, &FQ);
-    fp_mul(&v, &u1, &i, &FQ);
-    fe x3, y3, z3;
-    fp_sqr(&x3, &rr, &FQ); fp_sub(&x3, &x3, &j, &FQ); fp_sub(&x3, &x3, &v, &FQ); fp_sub(&x3, &x3, &v, &FQ);
-    fp_sub(&t, &v, &x3, &FQ); fp_mul(&y3, &rr, &t, &FQ);
-    fp_mul(&t, &s1, &j, &FQ); fp_dbl(&t, &t, &FQ); fp_sub(&y3, &y3, &t, &FQ);
-    fp_add(&z3, &p->z, &q->z, &FQ); fp_sqr(&z3, &z3, &FQ); fp_sub(&z3, &z3, &z1z1, &FQ); fp_sub(&z3, &z3, &z2z2, &FQ);
-    fp_mul(&z3, &z3, &h, &FQ);
+    fq z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t;
+    fq_sqr(&z1z1, &p->z, &FQ); fq_sqr(&z2z2, &q->z, &FQ);
+    fq_mul(&u1, &p->x, &z2z2, &FQ); fq_mul(&u2, &q->x, &z1z1, &FQ);
+    fq_mul(&s1, &p->y, &q->z, &FQ); fq_mul(&s1, &s1, &z2z2, &FQ);
+    fq_mul(&s2, &q->y, &p->z, &FQ); fq_mul(&s2, &s2, &z1z1, &FQ);
+    if (fq_eq(&u1, &u2) && fq_eq(&s1, &s2)) { g1j_double(r, p); return; }
+    fq_sub(&h, &u2, &u1, &FQ);
+    fq_dbl(&i, &h, &FQ); fq_sqr(&i, &i, &FQ);
+    fq_mul(&j, &h, &i, &FQ);
+    fq_sub(&rr, &s2, &s1, &FQ); fq_dbl(&rr, &rr, &FQ);
+    fq_mul(&v, &u1, &i, &FQ);
+    fq x3, y3, z3;
+    fq_sqr(&x3, &rr, &FQ); fq_sub(&x3, &x3, &j, &FQ); fq_sub(&x3, &x3, &v, &FQ); fq_sub(&x3, &x3, &v, &FQ);
+    fq_sub(&t, &v, &x3, &FQ); fq_mul(&y3, &rr, &t, &FQ);
+    fq_mul(&t, &s1, &j, &FQ); fq_dbl(&t, &t, &FQ); fq_sub(&y3, &y3, &t, &FQ);
+    fq_add(&z3, &p->z, &q->z, &FQ); fq_sqr(&z3, &z3, &FQ); fq_sub(&z3, &z3, &z1z1, &FQ); fq_sub(&z3, &z3, &z2z2, &FQ);
+    fq_mul(&z3, &z3, &h, &FQ);
     r->x = x3; r->y = y3; r->z = z3;
 }
 
 static void g1j_to_affine(g1a *r, const g1j *p) {
     if (g1j_is_inf(p)) { memset(r, 0, sizeof *r); return; }
-    fe zi, zi2, zi3;
-    fp_inv(&zi, &p->z, &FQ); fp_sqr(&zi2, &zi, &FQ); fp_mul(&zi3, &zi2, &zi, &FQ);
-    fp_mul(&r->x, &p->x, &zi2, &FQ); fp_mul(&r->y, &p->y, &zi3, &FQ);
+    fq zi, zi2, zi3;
+    fq_inv(&zi, &p->z, &FQ); fq_sqr(&zi2, &zi, &FQ); fq_mul(&zi3, &zi2, &zi, &FQ);
+    fq_mul(&r->x, &p->x, &zi2, &FQ); fq_mul(&r->y, &p->y, &zi3, &FQ);
 }
 
 /* ------------------------------------------------------------------ exported helpers */
 #define API __attribute__((visibility("default")))
 
+/* which curve this oracle library was compiled for, and its base-field width */
+API void zko_curve_info(int *curve_id, int *fq_words, int *fr_bits) {
+    if (curve_id) *curve_id = ZKO_CURVE;
+    if (fq_words) *fq_words = NQ;
+    if (fr_bits) *fr_bits = ZKO_FR_BITS;
+}
+/* field 0: Fr (4 words per element), field 1: Fq (NQ words per element) */
 API void zko_to_mont(int field, u64 *out, const u64 *in, size_t n) {
-    const fparams *P = field ? &FQ : &FR;
-    for (size_t i = 0; i < n; ++i) fp_to_mont((fe *)(out + 4 * i), (const fe *)(in + 4 * i), P);
+    for (size_t i = 0; i < n; ++i) {
+        if (field) fq_to_mont((fq *)(out + NQ * i), (const fq *)(in + NQ * i), &FQ);
+        else fp_to_mont((fe *)(out + 4 * i), (const fe *)(in + 4 * i), &FR);
+    }
 }
 API void zko_from_mont(int field, u64 *out, const u64 *in, size_t n) {
-    const fparams *P = field ? &FQ : &FR;
-    for (size_t i = 0; i < n; ++i) fp_from_mont((fe *)(out + 4 * i), (const fe *)(in + 4 * i), P);
-}
-/* Map arbitrary 256-bit words into [0,p): clear the two top bits, subtract p once if needed. */
-API void zko_normalize(int field, u64 *data, size_t n) {
-    const fparams *P = field ? &FQ : &FR;
     for (size_t i = 0; i < n; ++i) {
-        u64 *d = data + 4 * i;
-        d[3] &= 0x3fffffffffffffffULL;
-        if (geq(d, P->p)) sub_nored(d, d, P->p);
+        if (field) fq_from_mont((fq *)(out + NQ * i), (const fq *)(in + NQ * i), &FQ);
+        else fp_from_mont((fe *)(out + 4 * i), (const fe *)(in + 4 * i), &FR);
+    }
+}
+/* Map arbitrary words into [0,p): clear the bits above the modulus' bit length (two on BN254), subtract p once if needed. */
+static unsigned top_bits(const u64 *p, int nl) { unsigned b = 64; while (b && !((p[nl - 1] >> (b - 1)) & 1)) --b; return b; }
+API void zko_normalize(int field, u64 *data, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        if (field) {
+            u64 *d = data + NQ * i; unsigned tb = top_bits(FQ.p, NQ);
+            if (tb < 64) d[NQ - 1] &= (((u64)1 << tb) - 1);
+            if (fq_geq(d, FQ.p)) fq_sub_nored(d, d, FQ.p);
+        } else {
+            u64 *d = data + 4 * i; unsigned tb = top_bits(FR.p, 4);
+            if (tb < 64) d[3] &= (((u64)1 << tb) - 1);
+            if (geq(d, FR.p)) sub_nored(d, d, FR.p);
+        }
     }
 }
 /* op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 inv(a) (a != 0) -- all Montgomery in, Montgomery out */
 API void zko_fp_binop(int field, int op, u64 *out, const u64 *a, const u64 *b, size_t n) {
-    const fparams *P = field ? &FQ : &FR;
     for (size_t i = 0; i < n; ++i) {
+        if (field) {
+            const fq *x = (const fq *)(a + NQ * i), *y = (const fq *)(b + NQ * i); fq *o = (fq *)(out + NQ * i);
+            switch (op) {
+                case 0: fq_mul(o, x, y, &FQ); break;
+                case 1: fq_add(o, x, y, &FQ); break;
+                case 2: fq_sub(o, x, y, &FQ); break;
+                case 3: fq_sqr(o, x, &FQ); break;
+                default: fq_inv(o, x, &FQ); break;
+            }
+            continue;
+        }
+        const fparams *P = &FR;
         const fe *x = (const fe *)(a + 4 * i), *y = (const fe *)(b + 4 * i); fe *o = (fe *)(out + 4 * i);
         switch (op) {
             case 0: fp_mul(o, x, y, P); break;
@@ -241,11 +224,12 @@ API void zko_fp_binop(int field, int op, u64 *out, const u64 *a, const u64 *b, s
 
 /* ------------------------------------------------------------------ NTT (ark-poly Radix2EvaluationDomain) */
 static void fr_root_of_unity(fe *w, unsigned log_n) {
-    /* TWO_ADIC_ROOT_OF_UNITY = 5^((r-1)/2^28), then squared (28 - log_n) times (Radix2EvaluationDomain::new) */
-    static const u64 T[4] = {0x9b9709143e1f593fULL, 0x181585d2833e8487ULL, 0x131a029b85045b68ULL, 0x000000030644e72eULL}; /* (r-1)>>28 */
-    fe g; fp_from_u64(&g, 5, &FR);
+    /* TWO_ADIC_ROOT_OF_UNITY = GENERATOR^((r-1)/2^TWO_ADICITY) (5^((r-1)/2^28) on BN254), then squared TWO_ADICITY - log_n times
+     * (Radix2EvaluationDomain::new) */
+    static const u64 T[4] = ZKO_FR_T_INIT;
+    fe g; fp_from_u64(&g, ZKO_FR_GENERATOR, &FR);
     fp_pow(w, &g, T, &FR);
-    for (unsigned i = log_n; i < 28; ++i) fp_sqr(w, w, &FR);
+    for (unsigned i = log_n; i < ZKO_FR_TWO_ADICITY; ++i) fp_sqr(w, w, &FR);
 }
 
 static inline size_t bitrev(size_t x, unsigned bits) {
@@ -257,7 +241,7 @@ static inline size_t bitrev(size_t x, unsigned bits) {
 /* in place, natural order in and out, data holds 2^log_n Montgomery Fr elements.
  * inverse: uses w^-1 and multiplies by n^-1; coset: g = 5 powers before (forward) / g^-1 powers after (inverse). */
 API int zko_ntt(u64 *data, unsigned log_n, int inverse, int coset, int threads) {
-    if (log_n > 28) return -1;
+    if (log_n > ZKO_FR_TWO_ADICITY || log_n > 40) return -1;
     size_t n = (size_t)1 << log_n;
     fe *x = (fe *)data;
 #ifdef _OPENMP
@@ -266,7 +250,7 @@ API int zko_ntt(u64 *data, unsigned log_n, int inverse, int coset, int threads) 
     fe w; fr_root_of_unity(&w, log_n);
     if (inverse) fp_inv(&w, &w, &FR);
     if (coset && !inverse) {                   /* distribute_powers(coeffs, g) */
-        fe g, cur; fp_from_u64(&g, 5, &FR); fp_one(&cur, &FR);
+        fe g, cur; fp_from_u64(&g, ZKO_FR_GENERATOR, &FR); fp_one(&cur, &FR);
         for (size_t i = 0; i < n; ++i) { fp_mul(&x[i], &x[i], &cur, &FR); fp_mul(&cur, &cur, &g, &FR); }
     }
     if (n > 1) {
@@ -297,7 +281,7 @@ API int zko_ntt(u64 *data, unsigned log_n, int inverse, int coset, int threads) 
     if (inverse) {
         fe ninv; fp_from_u64(&ninv, (u64)n, &FR); fp_inv(&ninv, &ninv, &FR);
         if (coset) {                           /* ifft's size_inv, then distribute_powers(evals, g^-1) */
-            fe gi, cur = ninv; fp_from_u64(&gi, 5, &FR); fp_inv(&gi, &gi, &FR);
+            fe gi, cur = ninv; fp_from_u64(&gi, ZKO_FR_GENERATOR, &FR); fp_inv(&gi, &gi, &FR);
             for (size_t i = 0; i < n; ++i) { fp_mul(&x[i], &x[i], &cur, &FR); fp_mul(&cur, &cur, &gi, &FR); }
         } else {
 #pragma omp parallel for schedule(static) if (n >= 4096)
@@ -319,13 +303,13 @@ static inline u64 scalar_window(const u64 s[4], unsigned start, unsigned c) {
 }
 
 /* points: n x (x,y) Montgomery Fq, (0,0) = infinity; scalars: n x canonical 256-bit integers (into_repr) */
-API int zko_msm_g1(const u64 *points, const u64 *scalars, size_t n, u64 out_xy[8], int *is_inf, int threads) {
+API int zko_msm_g1(const u64 *points, const u64 *scalars, size_t n, u64 *out_xy /* 2 NQ words */, int *is_inf, int threads) {
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
 #endif
     const g1a *bases = (const g1a *)points;
     unsigned c = n < 32 ? 3 : (ceil_log2(n) * 69 / 100) + 2;      /* ln_without_floats(size) + 2 */
-    const unsigned num_bits = 254;                                   /* Fr MODULUS_BITS */
+    const unsigned num_bits = ZKO_FR_BITS;                                   /* Fr MODULUS_BITS */
     unsigned nwin = (num_bits + c - 1) / c;
     g1j *wsum = (g1j *)malloc(nwin * sizeof(g1j));
     const u64 one[4] = {1, 0, 0, 0};
@@ -333,9 +317,9 @@ API int zko_msm_g1(const u64 *points, const u64 *scalars, size_t n, u64 out_xy[8
 #pragma omp parallel for schedule(dynamic, 1)
     for (unsigned w = 0; w < nwin; ++w) {
         unsigned w_start = w * c;
-        g1j res; g1j_set_inf(&res); res.z = (fe){{0, 0, 0, 0}};
+        g1j res; g1j_set_inf(&res); res.z = FQ_ZERO;
         g1j *buckets = (g1j *)malloc(nb * sizeof(g1j));
-        for (size_t b = 0; b < nb; ++b) { buckets[b].z = (fe){{0, 0, 0, 0}}; }
+        for (size_t b = 0; b < nb; ++b) { buckets[b].z = FQ_ZERO; }
         for (size_t i = 0; i < n; ++i) {
             const u64 *s = scalars + 4 * i;
             if ((s[0] | s[1] | s[2] | s[3]) == 0) continue;       /* filter(|s| !s.is_zero()) */
@@ -346,7 +330,7 @@ API int zko_msm_g1(const u64 *points, const u64 *scalars, size_t n, u64 out_xy[8
                 if (d) g1j_add_mixed(&buckets[d - 1], &buckets[d - 1], &bases[i]);
             }
         }
-        g1j running; running.z = (fe){{0, 0, 0, 0}};
+        g1j running; running.z = FQ_ZERO;
         for (size_t b = nb; b-- > 0;) {
             g1j_add(&running, &running, &buckets[b]);
             g1j_add(&res, &res, &running);
@@ -354,7 +338,7 @@ API int zko_msm_g1(const u64 *points, const u64 *scalars, size_t n, u64 out_xy[8
         free(buckets);
         wsum[w] = res;
     }
-    g1j total; total.z = (fe){{0, 0, 0, 0}};
+    g1j total; total.z = FQ_ZERO;
     for (unsigned w = nwin; w-- > 1;) {
         g1j_add(&total, &total, &wsum[w]);
         for (unsigned k = 0; k < c; ++k) g1j_double(&total, &total);
@@ -362,59 +346,59 @@ API int zko_msm_g1(const u64 *points, const u64 *scalars, size_t n, u64 out_xy[8
     g1j_add(&total, &total, &wsum[0]);
     free(wsum);
     g1a aff; g1j_to_affine(&aff, &total);
-    memcpy(out_xy, &aff, 64);
+    memcpy(out_xy, &aff, sizeof aff);
     if (is_inf) *is_inf = g1j_is_inf(&total);
     return 0;
 }
 
 /* out[i] = scalars[i] * base, affine; scalars canonical.  Plain double-and-add (definition). */
-API void zko_g1_mul(const u64 base_xy[8], const u64 *scalars, size_t n, u64 *out_xy) {
+API void zko_g1_mul(const u64 *base_xy, const u64 *scalars, size_t n, u64 *out_xy) {
     const g1a *B = (const g1a *)base_xy;
 #pragma omp parallel for schedule(dynamic, 16)
     for (size_t i = 0; i < n; ++i) {
         const u64 *s = scalars + 4 * i;
-        g1j acc; acc.z = (fe){{0, 0, 0, 0}};
+        g1j acc; acc.z = FQ_ZERO;
         for (int b = 255; b >= 0; --b) {
             g1j_double(&acc, &acc);
             if ((s[b >> 6] >> (b & 63)) & 1) g1j_add_mixed(&acc, &acc, B);
         }
-        g1j_to_affine((g1a *)(out_xy + 8 * i), &acc);
+        g1j_to_affine((g1a *)(out_xy + 2 * NQ * i), &acc);
     }
 }
 
 /* out = sum_i points[i] (affine in, affine out) */
-API void zko_g1_sum(const u64 *points, size_t n, u64 out_xy[8]) {
-    g1j acc; acc.z = (fe){{0, 0, 0, 0}};
-    for (size_t i = 0; i < n; ++i) g1j_add_mixed(&acc, &acc, (const g1a *)(points + 8 * i));
+API void zko_g1_sum(const u64 *points, size_t n, u64 *out_xy /* 2 NQ words */) {
+    g1j acc; acc.z = FQ_ZERO;
+    for (size_t i = 0; i < n; ++i) g1j_add_mixed(&acc, &acc, (const g1a *)(points + 2 * NQ * i));
     g1j_to_affine((g1a *)out_xy, &acc);
 }
 
 /* out[i] = start + i * step (affine), i < n: cheap synthetic base points for CPU-only timing runs. */
-API void zko_g1_walk(const u64 start_xy[8], const u64 step_xy[8], size_t n, u64 *out_xy) {
+API void zko_g1_walk(const u64 *start_xy, const u64 *step_xy, size_t n, u64 *out_xy) {
     const g1a *S = (const g1a *)start_xy, *D = (const g1a *)step_xy;
     const size_t CH = 4096;
     size_t nch = (n + CH - 1) / CH;
 #pragma omp parallel for schedule(dynamic, 1)
     for (size_t c = 0; c < nch; ++c) {
         /* chunk start = start + (c*CH) * step by double-and-add */
-        g1j acc; acc.z = (fe){{0, 0, 0, 0}};
+        g1j acc; acc.z = FQ_ZERO;
         size_t k = c * CH;
         for (int b = 63; b >= 0; --b) { g1j_double(&acc, &acc); if ((k >> b) & 1) g1j_add_mixed(&acc, &acc, D); }
         g1j_add_mixed(&acc, &acc, S);
         size_t hi = (c + 1) * CH < n ? (c + 1) * CH : n;
         for (size_t i = c * CH; i < hi; ++i) {
-            g1j_to_affine((g1a *)(out_xy + 8 * i), &acc);
+            g1j_to_affine((g1a *)(out_xy + 2 * NQ * i), &acc);
             g1j_add_mixed(&acc, &acc, D);
         }
     }
 }
 
-API int zko_g1_on_curve(const u64 xy[8]) {
+API int zko_g1_on_curve(const u64 *xy) {
     const g1a *p = (const g1a *)xy;
     if (g1a_is_inf(p)) return 1;
-    fe l, r, three; fp_sqr(&l, &p->y, &FQ);
-    fp_sqr(&r, &p->x, &FQ); fp_mul(&r, &r, &p->x, &FQ); fp_from_u64(&three, 3, &FQ); fp_add(&r, &r, &three, &FQ);
-    return fe_eq(&l, &r);
+    fq l, r, three; fq_sqr(&l, &p->y, &FQ);
+    fq_sqr(&r, &p->x, &FQ); fq_mul(&r, &r, &p->x, &FQ); fq_from_u64(&three, ZKO_G1_B, &FQ); fq_add(&r, &r, &three, &FQ);
+    return fq_eq(&l, &r);
 }
 
 /* ------------------------------------------------------------------ grand products */
@@ -480,7 +464,7 @@ API void zko_z2_evals(unsigned log_n, const u64 *delta_, const u64 *eps_, const 
 API void zko_epk_free_tables(unsigned log_n, u64 *x_, u64 *zh_, u64 *l1_) {
     size_t n = (size_t)1 << log_n, n4 = 4 * n;
     fe *xs = (fe *)x_, *zh = (fe *)zh_, *l1 = (fe *)l1_;
-    fe w, g, one, ninv; fr_root_of_unity(&w, log_n + 2); fp_from_u64(&g, 5, &FR); fp_one(&one, &FR);
+    fe w, g, one, ninv; fr_root_of_unity(&w, log_n + 2); fp_from_u64(&g, ZKO_FR_GENERATOR, &FR); fp_one(&one, &FR);
     fp_from_u64(&ninv, (u64)n, &FR); fp_inv(&ninv, &ninv, &FR);
     xs[0] = g;
     for (size_t i = 1; i < n4; ++i) fp_mul(&xs[i], &xs[i - 1], &w, &FR);

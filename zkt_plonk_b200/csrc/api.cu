@@ -13,7 +13,8 @@ template <class P>
 __global__ void fp_binop_kernel(int op, uint4 *out, const uint4 *a, const uint4 *b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fe_t x = fload(a + 2 * i), y = fload(b + 2 * i), r;
+    constexpr int Q4 = P::N / 4;                                  // 16-byte pieces per element
+    fel_t<P::N> x = floadn<P::N>(a + Q4 * i), y = floadn<P::N>(b + Q4 * i), r;
     switch (op) {
         case 0: r = fmul<P>(x, y); break;
         case 1: r = fadd<P>(x, y); break;
@@ -23,7 +24,7 @@ __global__ void fp_binop_kernel(int op, uint4 *out, const uint4 *a, const uint4 
         case 5: r = fto_mont<P>(x); break;
         default: r = ffrom_mont<P>(x); break;
     }
-    fstore(out + 2 * i, r);
+    fstore(out + Q4 * i, r);
 }
 
 
@@ -89,11 +90,11 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, uint32_t i
         for (int k = 0; k < 4; ++k) r ^= a[k] ^ c[k] ^ (uint32_t)__double2ll_rn(d[k]);
         out[t] = r;
     } else {
-        fe_t x[4];
+        fq_t x[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[k].v[j] = (t * 2654435761u + k * 40503u + j) & 0x0fffffffu;
+            for (int j = 0; j < FqP::N; ++j) x[k].v[j] = (t * 2654435761u + k * 40503u + j) & 0x00ffffffu;
         }
         for (uint32_t i = 0; i < iters; ++i) {
 #pragma unroll
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, uint32_t i
         }
         uint32_t r = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) r ^= x[k].v[0] ^ x[k].v[7];
+        for (int k = 0; k < 4; ++k) r ^= x[k].v[0] ^ x[k].v[FqP::N - 1];
         out[t] = r;
     }
 }
@@ -110,7 +111,26 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, uint32_t i
 
 extern "C" {
 
-const char *zkb_version(void) { return "zkb200 0.1 (sm_100a)"; }
+const char *zkb_version(void) { return "zkb200 0.1 (sm_100a, " ZKB_CURVE_NAME ")"; }
+
+// The curve this library was compiled for (one shared object per curve, same entry points): 0 BN254, 1 BLS12-381, 2 BLS12-377;
+// 64-bit words of a scalar (always 4) and of a base-field element (4 or 6: an affine point is twice, an XYZZ partial sum four
+// times that); bit length of the scalar field's modulus; 1 when the prover driver / key files / verifier are compiled in.
+int zkb_curve_info(int *curve_id, int *fr_words, int *fq_words, int *fr_bits, int *has_prover) {
+    if (curve_id) *curve_id = ZKB_CURVE;
+    if (fr_words) *fr_words = host::FR_L;
+    if (fq_words) *fq_words = host::FQ_L;
+    if (fr_bits) *fr_bits = FrP::BITS;
+    if (has_prover) *has_prover = ZKB_CURVE == ZKB_CURVE_BN254 ? 1 : 0;
+    return ZKB_OK;
+}
+// the G1 generator of the curve: affine, Montgomery form, 2 x fq_words words
+int zkb_g1_generator(uint64_t *out_xy) {
+    if (!out_xy) return ZKB_ERR_INVALID;
+    memcpy(out_xy, host::G1_GEN_X, 8 * host::FQ_L);
+    memcpy(out_xy + host::FQ_L, host::G1_GEN_Y, 8 * host::FQ_L);
+    return ZKB_OK;
+}
 
 int zkb_ctx_create(int device, zkb_ctx **out) {
     if (!out) return ZKB_ERR_INVALID;
@@ -226,7 +246,7 @@ int zkb_ntt_batch_dev(zkb_ctx *ctx, uint64_t *const *ptrs_host, size_t count, si
 int zkb_ntt(zkb_ctx *ctx, uint64_t *data_host, size_t len, unsigned log_n, int inverse, int coset) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!data_host) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: null data pointer");
-    if (log_n > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ntt: log_n exceeds Fr TWO_ADICITY (28)");
+    if (log_n > host::FR_TWO_ADICITY || log_n > 31) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ntt: log_n exceeds Fr TWO_ADICITY (28 on BN254) or 31");
     size_t n = (size_t)1 << log_n;
     if (len > n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: len > 2^log_n");
     int rc = zkb_reserve(ctx, ctx->stage, n * 32);
@@ -242,16 +262,17 @@ int zkb_ntt(zkb_ctx *ctx, uint64_t *data_host, size_t len, unsigned log_n, int i
 // ---------------------------------------------------------------------------------------------- test hooks
 int zkb_test_fp_binop(zkb_ctx *ctx, int field, int op, uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n) {
     if (!ctx || !out || !a || !b) return ZKB_ERR_INVALID;
-    int rc = zkb_reserve(ctx, ctx->stage, 3 * n * 32);
+    const size_t eb = field == 0 ? 8 * host::FR_L : 8 * host::FQ_L;   // bytes per element
+    int rc = zkb_reserve(ctx, ctx->stage, 3 * n * eb);
     if (rc) return rc;
-    uint4 *da = (uint4 *)ctx->stage.p, *db = da + 2 * n, *dout = db + 2 * n;
-    ZKB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    uint4 *da = (uint4 *)ctx->stage.p, *db = da + n * eb / 16, *dout = db + n * eb / 16;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(da, a, n * eb, cudaMemcpyHostToDevice, ctx->stream));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(db, b, n * eb, cudaMemcpyHostToDevice, ctx->stream));
     unsigned blocks = (unsigned)((n + 127) / 128);
     if (field == 0) fp_binop_kernel<FrP><<<blocks, 128, 0, ctx->stream>>>(op, dout, da, db, n);
     else fp_binop_kernel<FqP><<<blocks, 128, 0, ctx->stream>>>(op, dout, da, db, n);
     ZKB_CUDA(ctx, cudaGetLastError());
-    ZKB_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(out, dout, n * eb, cudaMemcpyDeviceToHost, ctx->stream));
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ZKB_OK;
 }

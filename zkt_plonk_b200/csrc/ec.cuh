@@ -1,4 +1,5 @@
-// ec.cuh -- BN254 G1 (y^2 = x^3 + 3) group law on the device.
+// ec.cuh -- G1 group law on the device for the curve of this build (y^2 = x^3 + b: BN254, BLS12-381, BLS12-377; the
+// formulas below use a = 0 and never b).
 //
 // Replaces ark-ec 0.3 `short_weierstrass_jacobian::{GroupAffine, GroupProjective}` for the bucket
 // method.  Accumulators use extended Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2):
@@ -12,8 +13,9 @@
 
 namespace zkb {
 
-struct g1a_t { fe_t x, y; };                 // affine, Montgomery Fq
-struct g1x_t { fe_t x, y, zz, zzz; };        // XYZZ
+struct g1a_t { fq_t x, y; };                 // affine, Montgomery Fq (64 bytes on BN254, 96 on the BLS12 curves)
+struct g1x_t { fq_t x, y, zz, zzz; };        // XYZZ
+constexpr int FQ_BYTES = 4 * FqP::N;         // bytes of one base-field element
 
 #ifdef __CUDACC__
 typedef FqP Q;
@@ -37,12 +39,12 @@ __device__ __forceinline__ g1x_t g1x_from_affine(const g1a_t &p) {
 // 2 * (affine p), p finite  (mdbl-2008-s-1)
 static __device__ __noinline__ g1x_t g1x_double_affine(const g1a_t &p) {
     g1x_t r;
-    fe_t u = fdbl<Q>(p.y);
-    fe_t v = fsqr<Q>(u);
-    fe_t w = fmul<Q>(u, v);
-    fe_t s = fmul<Q>(p.x, v);
-    fe_t xx = fsqr<Q>(p.x);
-    fe_t m = fadd<Q>(fdbl<Q>(xx), xx);
+    fq_t u = fdbl<Q>(p.y);
+    fq_t v = fsqr<Q>(u);
+    fq_t w = fmul<Q>(u, v);
+    fq_t s = fmul<Q>(p.x, v);
+    fq_t xx = fsqr<Q>(p.x);
+    fq_t m = fadd<Q>(fdbl<Q>(xx), xx);
     r.x = fsub<Q>(fsub<Q>(fsqr<Q>(m), s), s);
     r.y = fmsub2<Q>(m, fsub<Q>(s, r.x), w, p.y);
     r.zz = v;
@@ -54,12 +56,12 @@ static __device__ __noinline__ g1x_t g1x_double_affine(const g1a_t &p) {
 static __device__ __noinline__ g1x_t g1x_double(const g1x_t &p) {
     if (g1x_is_inf(p)) return p;
     g1x_t r;
-    fe_t u = fdbl<Q>(p.y);
-    fe_t v = fsqr<Q>(u);
-    fe_t w = fmul<Q>(u, v);
-    fe_t s = fmul<Q>(p.x, v);
-    fe_t xx = fsqr<Q>(p.x);
-    fe_t m = fadd<Q>(fdbl<Q>(xx), xx);
+    fq_t u = fdbl<Q>(p.y);
+    fq_t v = fsqr<Q>(u);
+    fq_t w = fmul<Q>(u, v);
+    fq_t s = fmul<Q>(p.x, v);
+    fq_t xx = fsqr<Q>(p.x);
+    fq_t m = fadd<Q>(fdbl<Q>(xx), xx);
     r.x = fsub<Q>(fsub<Q>(fsqr<Q>(m), s), s);
     r.y = fmsub2<Q>(m, fsub<Q>(s, r.x), w, p.y);
     r.zz = fmul<Q>(v, p.zz);
@@ -71,20 +73,20 @@ static __device__ __noinline__ g1x_t g1x_double(const g1x_t &p) {
 __device__ __forceinline__ void g1x_add_mixed(g1x_t &acc, const g1a_t &q) {
     if (g1a_is_inf(q)) return;
     if (g1x_is_inf(acc)) { acc.x = q.x; acc.y = q.y; acc.zz = fone<Q>(); acc.zzz = fone<Q>(); return; }
-    fe_t u2 = fmul<Q>(q.x, acc.zz);
-    fe_t s2 = fmul<Q>(q.y, acc.zzz);
-    fe_t p = fsub<Q>(u2, acc.x);
-    fe_t r = fsub<Q>(s2, acc.y);
+    fq_t u2 = fmul<Q>(q.x, acc.zz);
+    fq_t s2 = fmul<Q>(q.y, acc.zzz);
+    fq_t p = fsub<Q>(u2, acc.x);
+    fq_t r = fsub<Q>(s2, acc.y);
     if (fis_zero<Q>(p)) {                         // same x: doubling or cancellation (rare)
         if (fis_zero<Q>(r)) acc = g1x_double_affine(q);
         else acc = g1x_inf();
         return;
     }
-    fe_t pp = fsqr<Q>(p);
-    fe_t ppp = fmul<Q>(p, pp);
-    fe_t qq = fmul<Q>(acc.x, pp);
-    fe_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(fsqr<Q>(r), ppp), qq), qq);
-    fe_t y3 = fmsub2<Q>(r, fsub<Q>(qq, x3), acc.y, ppp);
+    fq_t pp = fsqr<Q>(p);
+    fq_t ppp = fmul<Q>(p, pp);
+    fq_t qq = fmul<Q>(acc.x, pp);
+    fq_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(fsqr<Q>(r), ppp), qq), qq);
+    fq_t y3 = fmsub2<Q>(r, fsub<Q>(qq, x3), acc.y, ppp);
     acc.x = x3;
     acc.y = y3;
     acc.zz = fmul<Q>(acc.zz, pp);
@@ -95,22 +97,22 @@ __device__ __forceinline__ void g1x_add_mixed(g1x_t &acc, const g1a_t &q) {
 __device__ __forceinline__ void g1x_add(g1x_t &acc, const g1x_t &q) {
     if (g1x_is_inf(q)) return;
     if (g1x_is_inf(acc)) { acc = q; return; }
-    fe_t u1 = fmul<Q>(acc.x, q.zz);
-    fe_t u2 = fmul<Q>(q.x, acc.zz);
-    fe_t s1 = fmul<Q>(acc.y, q.zzz);
-    fe_t s2 = fmul<Q>(q.y, acc.zzz);
-    fe_t p = fsub<Q>(u2, u1);
-    fe_t r = fsub<Q>(s2, s1);
+    fq_t u1 = fmul<Q>(acc.x, q.zz);
+    fq_t u2 = fmul<Q>(q.x, acc.zz);
+    fq_t s1 = fmul<Q>(acc.y, q.zzz);
+    fq_t s2 = fmul<Q>(q.y, acc.zzz);
+    fq_t p = fsub<Q>(u2, u1);
+    fq_t r = fsub<Q>(s2, s1);
     if (fis_zero<Q>(p)) {
         if (fis_zero<Q>(r)) acc = g1x_double(acc);
         else acc = g1x_inf();
         return;
     }
-    fe_t pp = fsqr<Q>(p);
-    fe_t ppp = fmul<Q>(p, pp);
-    fe_t qq = fmul<Q>(u1, pp);
-    fe_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(fsqr<Q>(r), ppp), qq), qq);
-    fe_t y3 = fmsub2<Q>(r, fsub<Q>(qq, x3), s1, ppp);
+    fq_t pp = fsqr<Q>(p);
+    fq_t ppp = fmul<Q>(p, pp);
+    fq_t qq = fmul<Q>(u1, pp);
+    fq_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(fsqr<Q>(r), ppp), qq), qq);
+    fq_t y3 = fmsub2<Q>(r, fsub<Q>(qq, x3), s1, ppp);
     acc.x = x3;
     acc.y = y3;
     acc.zz = fmul<Q>(fmul<Q>(acc.zz, q.zz), pp);
@@ -126,27 +128,27 @@ __device__ __forceinline__ g1a_t g1a_neg(const g1a_t &p) {
 
 __device__ __forceinline__ g1a_t g1a_load(const void *p) {
     g1a_t r;
-    r.x = fload_ro(p);
-    r.y = fload_ro(reinterpret_cast<const char *>(p) + 32);
+    r.x = floadn_ro<FqP::N>(p);
+    r.y = floadn_ro<FqP::N>(reinterpret_cast<const char *>(p) + FQ_BYTES);
     return r;
 }
 __device__ __forceinline__ g1x_t g1x_load(const void *p) {
     const char *c = reinterpret_cast<const char *>(p);
     g1x_t r;
-    r.x = fload(c); r.y = fload(c + 32); r.zz = fload(c + 64); r.zzz = fload(c + 96);
+    r.x = floadn<FqP::N>(c); r.y = floadn<FqP::N>(c + FQ_BYTES); r.zz = floadn<FqP::N>(c + 2 * FQ_BYTES); r.zzz = floadn<FqP::N>(c + 3 * FQ_BYTES);
     return r;
 }
 __device__ __forceinline__ void g1x_store(void *p, const g1x_t &a) {
     char *c = reinterpret_cast<char *>(p);
-    fstore(c, a.x); fstore(c + 32, a.y); fstore(c + 64, a.zz); fstore(c + 96, a.zzz);
+    fstore(c, a.x); fstore(c + FQ_BYTES, a.y); fstore(c + 2 * FQ_BYTES, a.zz); fstore(c + 3 * FQ_BYTES, a.zzz);
 }
 
 // XYZZ -> affine on the device (one field inversion; used off the critical path and in tests)
 static __device__ __noinline__ g1a_t g1x_to_affine(const g1x_t &p) {
     g1a_t r;
     if (g1x_is_inf(p)) { r.x = fzero<Q>(); r.y = fzero<Q>(); return r; }
-    fe_t zi = finv<Q>(p.zzz);                    // 1/ZZZ
-    fe_t zz_i = fmul<Q>(zi, p.zz);               // ZZ/ZZZ = 1/Z
+    fq_t zi = finv<Q>(p.zzz);                    // 1/ZZZ
+    fq_t zz_i = fmul<Q>(zi, p.zz);               // ZZ/ZZZ = 1/Z
     zz_i = fsqr<Q>(zz_i);                        // 1/ZZ
     r.x = fmul<Q>(p.x, zz_i);
     r.y = fmul<Q>(p.y, zi);

@@ -47,8 +47,14 @@ namespace {
 constexpr uint32_t SEG_MAX = 1024;       // upper bound of the per-MSM task length `seg` (points per accumulation task)
 constexpr uint32_t RED_THREADS = 128;    // threads per CTA in the window reduction
 constexpr uint32_t RED_MAX_LEVELS = 26;  // levels of the weighted-sum recursion
-constexpr uint32_t RED_CTAS_PER_SM = 3;  // resident CTAs of the wide level (<= 170 registers per thread)
+constexpr uint32_t RED_CTAS_PER_SM = FqP::N == 8 ? 3 : 2;   // resident CTAs of the wide level (<= 170 registers per thread; 255 with 12-limb coordinates)
+constexpr uint32_t ACC_CTAS_PER_SM = FqP::N == 8 ? 4 : 2;   // bucket accumulation: 128 registers per thread (255 with 12-limb coordinates)
 constexpr uint32_t SIGN_BIT = 0x80000000u;
+// widths at the C boundary, in 64-bit words: an affine point (x, y) and an un-normalised XYZZ partial sum (8 / 16 on BN254,
+// 12 / 24 on the BLS12 curves: zkb_curve_info reports them)
+constexpr int AFF_W = 2 * host::FQ_L, XYZZ_W = 4 * host::FQ_L;
+constexpr size_t AFF_BYTES = 8 * AFF_W, XYZZ_BYTES = 8 * XYZZ_W;
+constexpr uint32_t SCALAR_BITS = FrP::BITS;   // 254 (BN254), 255 (BLS12-381), 253 (BLS12-377)
 
 struct MsmPlan {
     uint32_t c, W, B;                    // window bits, windows, buckets per group (2^(c-1))
@@ -102,7 +108,7 @@ struct MsmState {
     uint32_t last_c = 0, last_W = 0;
     void *fixed_base = nullptr;          // FixedBase* (fixed-base window tables of the resident SRS)
     // open batch of pipelined commitments (zkb_commit_push / zkb_commit_finish)
-    std::vector<std::array<uint64_t, 16>> pipe_partial;   // folded XYZZ partial sum of every pushed commitment
+    std::vector<std::array<uint64_t, XYZZ_W>> pipe_partial;   // folded XYZZ partial sum of every pushed commitment
     std::vector<char> pipe_pending;      // 1: enqueued, result still in its slot's pinned buffer
     size_t pipe_expected = 1;            // commitments the open batch will hold (zkb_commit_expect): decides the multi-GPU layout
     MsmPlan pipe_plan[2];
@@ -333,7 +339,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + 32));
 }
 
-__global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const g1a_t *__restrict__ points, const g1a_t *__restrict__ pool,
+__global__ void __launch_bounds__(128, ACC_CTAS_PER_SM) msm_accumulate_kernel(const g1a_t *__restrict__ points, const g1a_t *__restrict__ pool,
                                                              const uint32_t *__restrict__ sorted,
                                                              const uint32_t *__restrict__ counts, const uint32_t *__restrict__ starts,
                                                              const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_base,
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const g1a_t *__r
 __device__ __forceinline__ g1x_t shfl_down_g1x(const g1x_t &p, int d) {
     g1x_t r;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < FqP::N; ++i) {
         r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], d);
         r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], d);
         r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], d);
@@ -497,22 +503,22 @@ __global__ void __launch_bounds__(RED_THREADS, WIDE ? RED_CTAS_PER_SM : 1) msm_w
 //   round 4   --               r (q - X3)      s1 ppp           ZZZ3 = zzz ppp       Y3 = r (q - X3) - s1 ppp
 // 16 lane-products instead of 14, a quarter of the depth.  Infinity and p == 0 (doubling / cancellation) are uniform over a
 // group and take the one-lane formulas.  Same sums as msm_wsum_level_kernel<false> (canonical field elements either way).
-__device__ __forceinline__ fe_t shfl_fe(unsigned mask, const fe_t &a, int src) {
-    fe_t r;
+__device__ __forceinline__ fq_t shfl_fe(unsigned mask, const fq_t &a, int src) {
+    fq_t r;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_sync(mask, a.v[i], src);
+    for (int i = 0; i < FqP::N; ++i) r.v[i] = __shfl_sync(mask, a.v[i], src);
     return r;
 }
-__device__ __forceinline__ fe_t shfl_xor_fe(unsigned mask, const fe_t &a, int m) {
-    fe_t r;
+__device__ __forceinline__ fq_t shfl_xor_fe(unsigned mask, const fq_t &a, int m) {
+    fq_t r;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_xor_sync(mask, a.v[i], m);
+    for (int i = 0; i < FqP::N; ++i) r.v[i] = __shfl_xor_sync(mask, a.v[i], m);
     return r;
 }
-__device__ __forceinline__ fe_t sel_fe(bool c, const fe_t &a, const fe_t &b) {
-    fe_t r;
+__device__ __forceinline__ fq_t sel_fe(bool c, const fq_t &a, const fq_t &b) {
+    fq_t r;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r.v[i] = c ? a.v[i] : b.v[i];
+    for (int i = 0; i < FqP::N; ++i) r.v[i] = c ? a.v[i] : b.v[i];
     return r;
 }
 
@@ -527,40 +533,40 @@ __global__ void __launch_bounds__(RED_THREADS) msm_wsum_level_coop_kernel(const 
     char *dst = reinterpret_cast<char *>(out + ((size_t)strm * G + g) * M_out + t);
     const bool pair = M_in - 2 * t > 1;
     if (strm == 0)                                                // the new A stream: X[2t + 1], one coordinate per lane
-        fstore(reinterpret_cast<char *>(out + ((size_t)(n_plain + 1) * G + g) * M_out + t) + 32 * l, pair ? fload(p1 + 32 * l) : fzero<Q>());
+        fstore(reinterpret_cast<char *>(out + ((size_t)(n_plain + 1) * G + g) * M_out + t) + FQ_BYTES * l, pair ? floadn<FqP::N>(p1 + FQ_BYTES * l) : fzero<Q>());
     // coordinates: 0 x, 1 y, 2 zz, 3 zzz.  lane 0: X1, ZZ2; lane 1: X2, ZZ1; lane 2: Y1, ZZZ2; lane 3: Y2, ZZZ1
-    const fe_t a = pair || !(l & 1) ? fload(((l & 1) ? p1 : p0) + 32 * (l >> 1)) : fzero<Q>();
-    const fe_t b = pair ? fload(((l & 1) ? p0 : p1) + 64 + 32 * (l >> 1)) : fzero<Q>();
+    const fq_t a = pair || !(l & 1) ? floadn<FqP::N>(((l & 1) ? p1 : p0) + FQ_BYTES * (l >> 1)) : fzero<Q>();
+    const fq_t b = pair ? floadn<FqP::N>(((l & 1) ? p0 : p1) + 2 * FQ_BYTES + FQ_BYTES * (l >> 1)) : fzero<Q>();
     // infinity on either side (ZZ == 0; a missing partner counts as infinity): the sum is the other point
     const bool inf2 = __shfl_sync(m0, (int)fis_zero<Q>(b), base) != 0;          // ZZ2 sits on lane 0
     const bool inf1 = __shfl_sync(m0, (int)fis_zero<Q>(b), base + 1) != 0;      // ZZ1 on lane 1
     const unsigned m1 = __ballot_sync(m0, !(inf1 || inf2));
     if (inf1 || inf2) {
-        fstore(dst + 32 * l, inf2 ? fload(p0 + 32 * l) : fload(p1 + 32 * l));
+        fstore(dst + FQ_BYTES * l, inf2 ? floadn<FqP::N>(p0 + FQ_BYTES * l) : floadn<FqP::N>(p1 + FQ_BYTES * l));
         return;
     }
-    fe_t prod = fmul<Q>(a, b);                                                   // u1 | u2 | s1 | s2
-    const fe_t other = shfl_xor_fe(m1, prod, 1);
-    const fe_t lo = sel_fe(l & 1, other, prod);                                  // u1 (lanes 0, 1), s1 (lanes 2, 3)
-    const fe_t d = fsub<Q>(sel_fe(l & 1, prod, other), lo);                      // p  (lanes 0, 1), r  (lanes 2, 3)
+    fq_t prod = fmul<Q>(a, b);                                                   // u1 | u2 | s1 | s2
+    const fq_t other = shfl_xor_fe(m1, prod, 1);
+    const fq_t lo = sel_fe(l & 1, other, prod);                                  // u1 (lanes 0, 1), s1 (lanes 2, 3)
+    const fq_t d = fsub<Q>(sel_fe(l & 1, prod, other), lo);                      // p  (lanes 0, 1), r  (lanes 2, 3)
     const bool pz = __shfl_sync(m1, (int)fis_zero<Q>(d), base) != 0;
     const unsigned m2 = __ballot_sync(m1, !pz);
     if (pz) {                                                                    // same x: every lane runs the complete formulas
         g1x_t x0 = g1x_load(p0);
         g1x_add(x0, g1x_load(p1));
-        fstore(dst + 32 * l, l == 0 ? x0.x : l == 1 ? x0.y : l == 2 ? x0.zz : x0.zzz);
+        fstore(dst + FQ_BYTES * l, l == 0 ? x0.x : l == 1 ? x0.y : l == 2 ? x0.zz : x0.zzz);
         return;
     }
-    const fe_t bp = shfl_xor_fe(m2, b, 1);                                       // lane 1: ZZ2, lane 3: ZZZ2
-    const fe_t prod2 = fmul<Q>(sel_fe(l & 1, b, d), sel_fe(l & 1, bp, d));       // pp | zz | rr | zzz
-    const fe_t pp = shfl_fe(m2, prod2, base), zz = shfl_fe(m2, prod2, base + 1);
-    const fe_t prod3 = fmul<Q>(l == 0 ? d : l == 1 ? lo : l == 2 ? zz : pp, pp); // ppp | q | ZZ3 | (unused)
-    const fe_t ppp = shfl_fe(m2, prod3, base), q = shfl_fe(m2, prod3, base + 1), rr = shfl_fe(m2, prod2, base + 2);
-    const fe_t r = shfl_fe(m2, d, base + 2);
-    const fe_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(rr, ppp), q), q);
-    const fe_t prod4 = fmul<Q>(l == 1 ? r : l == 2 ? lo : l == 3 ? prod2 : ppp, l == 1 ? fsub<Q>(q, x3) : ppp);   // -- | r (q - X3) | s1 ppp | ZZZ3
-    const fe_t t1 = shfl_fe(m2, prod4, base + 2);
-    fstore(dst + 32 * l, l == 0 ? x3 : l == 1 ? fsub<Q>(prod4, t1) : l == 2 ? prod3 : prod4);
+    const fq_t bp = shfl_xor_fe(m2, b, 1);                                       // lane 1: ZZ2, lane 3: ZZZ2
+    const fq_t prod2 = fmul<Q>(sel_fe(l & 1, b, d), sel_fe(l & 1, bp, d));       // pp | zz | rr | zzz
+    const fq_t pp = shfl_fe(m2, prod2, base), zz = shfl_fe(m2, prod2, base + 1);
+    const fq_t prod3 = fmul<Q>(l == 0 ? d : l == 1 ? lo : l == 2 ? zz : pp, pp); // ppp | q | ZZ3 | (unused)
+    const fq_t ppp = shfl_fe(m2, prod3, base), q = shfl_fe(m2, prod3, base + 1), rr = shfl_fe(m2, prod2, base + 2);
+    const fq_t r = shfl_fe(m2, d, base + 2);
+    const fq_t x3 = fsub<Q>(fsub<Q>(fsub<Q>(rr, ppp), q), q);
+    const fq_t prod4 = fmul<Q>(l == 1 ? r : l == 2 ? lo : l == 3 ? prod2 : ppp, l == 1 ? fsub<Q>(q, x3) : ppp);   // -- | r (q - X3) | s1 ppp | ZZZ3
+    const fq_t t1 = shfl_fe(m2, prod4, base + 2);
+    fstore(dst + FQ_BYTES * l, l == 0 ? x3 : l == 1 ? fsub<Q>(prod4, t1) : l == 2 ? prod3 : prod4);
 }
 
 // Fixed-base table: rows[w][i] = 2^(c*w) * P_i (affine), w < W.  One thread per point walks the windows.
@@ -608,9 +614,10 @@ __global__ void fr_from_mont_kernel(const uint4 *in, uint4 *out, uint32_t n) {
 
 // ------------------------------------------------------------------ host-side group law (window fold + affine)
 namespace hec {
-using host::Fe;
+typedef host::Fq Fe;                     // base-field element (4 or 6 x u64)
 using host::FQ;
 struct Pt { Fe x, y, zz, zzz; };
+static_assert(sizeof(Pt) == XYZZ_BYTES && sizeof(g1x_t) == XYZZ_BYTES && sizeof(g1a_t) == AFF_BYTES, "point layouts");
 inline bool is_inf(const Pt &p) { return host::is_zero(p.zz); }
 inline Pt inf() { Pt p; memset(&p, 0, sizeof p); return p; }
 inline Pt dbl(const Pt &p) {
@@ -647,13 +654,13 @@ inline Pt mul_small(const Pt &p, uint32_t k) {                   // k * p, doubl
     }
     return acc;
 }
-inline void to_affine(const Pt &p, uint64_t out_xy[8], int *is_inf_out) {
-    if (is_inf(p)) { memset(out_xy, 0, 64); if (is_inf_out) *is_inf_out = 1; return; }
+inline void to_affine(const Pt &p, uint64_t *out_xy /* AFF_W words */, int *is_inf_out) {
+    if (is_inf(p)) { memset(out_xy, 0, AFF_BYTES); if (is_inf_out) *is_inf_out = 1; return; }
     Fe zi = host::inv(p.zzz, FQ);
     Fe zzi = host::sqr(host::mul(zi, p.zz, FQ), FQ);
     Fe x = host::mul(p.x, zzi, FQ), y = host::mul(p.y, zi, FQ);
-    memcpy(out_xy, x.l, 32);
-    memcpy(out_xy + 4, y.l, 32);
+    memcpy(out_xy, x.l, AFF_BYTES / 2);
+    memcpy(out_xy + AFF_W / 2, y.l, AFF_BYTES / 2);
     if (is_inf_out) *is_inf_out = 0;
 }
 }  // namespace hec
@@ -668,9 +675,9 @@ struct FixedBase {                       // fixed-base tables of the resident SR
 // Balanced fixed-base windows: W = ceil(255 / c) windows, the first *wide of width c and the rest c - 1, so that
 // no window is left with only a few bits (a 2-bit top window would pile n/4 points on each of 4 buckets).
 uint32_t balanced_windows(uint32_t c, uint32_t *wide) {
-    // widths must sum to >= 255: 254 scalar bits plus one spare bit, so that the top window's raw value plus the
-    // incoming carry never exceeds half of its range (no carry out of the top window)
-    const uint32_t BITS = 255;
+    // widths must sum to the scalar's bit length plus one spare bit (255 on BN254), so that the top window's raw value plus
+    // the incoming carry never exceeds half of its range (no carry out of the top window)
+    const uint32_t BITS = SCALAR_BITS + 1;
     uint32_t W = (BITS + c - 1) / c;                           // fewest c-bit windows that cover BITS
     uint32_t slack = W * c - BITS;                              // bits to give back by narrowing windows to c - 1
     *wide = W - (slack < W ? slack : W);
@@ -686,7 +693,7 @@ uint32_t pick_window(size_t n, bool shared_buckets, int sm_count) {
     double best = 1e300;
     const double wave = (double)sm_count * 3 * 128;
     for (uint32_t c = 6; c <= 22; ++c) {
-        uint32_t wide = 1, W = shared_buckets ? balanced_windows(c, &wide) : 254 / c + 1;
+        uint32_t wide = 1, W = shared_buckets ? balanced_windows(c, &wide) : SCALAR_BITS / c + 1;
         if (shared_buckets && wide == 0) continue;               // equivalent to c - 1 with uniform windows
         const double buckets = (shared_buckets ? 1.0 : (double)W) * (double)(1u << (c - 1));
         const double waves = buckets / wave;
@@ -703,7 +710,7 @@ uint32_t pick_window(size_t n, bool shared_buckets, int sm_count) {
 // for ~6 small launches), so: floor(log2(mean load)) - 1 rounds, none for small MSMs (latency-bound) or when the
 // references / the pool would not fit their 30 index bits or a sane share of HBM.
 uint32_t pick_pair_rounds(int mode, uint64_t entries, uint64_t nb, uint64_t max_id) {
-    if (mode == 0 || entries < 2 || max_id >= pairs::POOL || entries >= pairs::POOL || entries > (1ull << 28)) return 0;
+    if (!ZKB_HAVE_PAIR_ROUNDS || mode == 0 || entries < 2 || max_id >= pairs::POOL || entries >= pairs::POOL || entries > (1ull << 28)) return 0;
     if (mode > 0) return (uint32_t)std::min(mode, pairs::MAX_ROUNDS);
     if (entries < (1ull << 19)) return 0;
     const double mean = (double)entries / (double)std::max<uint64_t>(1, std::min(nb, entries));
@@ -718,7 +725,7 @@ MsmPlan make_plan(size_t n, int force_c, const FixedBase *fb, size_t offset, int
         pl.id_base = (uint32_t)offset; pl.id_stride = (uint32_t)fb->n;
     } else {
         pl.c = force_c > 0 ? (uint32_t)force_c : pick_window(n, false, sm_count);
-        pl.W = 254 / pl.c + 1; pl.G = pl.W; pl.wide = pl.W;
+        pl.W = SCALAR_BITS / pl.c + 1; pl.G = pl.W; pl.wide = pl.W;
         pl.id_base = 0; pl.id_stride = 0;
     }
     pl.B = 1u << (pl.c - 1);
@@ -772,6 +779,7 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
            o_order = take(max_tasks * 8), o_out = take(max_tasks * sizeof(g1x_t)), o_bval = take(nb * sizeof(g1x_t)),
            o_red0 = take(pl.red_buf_elems[0] * sizeof(g1x_t)), o_red1 = take(pl.red_buf_elems[1] * sizeof(g1x_t));
     size_t o_pr[2] = {0, 0}, o_pc[2] = {0, 0}, o_ps[2] = {0, 0}, o_pk = 0, o_pscan = 0, o_prefs = 0, o_ppre = 0, o_pool = 0;
+#if ZKB_HAVE_PAIR_ROUNDS
     if (pl.pp.rounds) {
         for (int k = 0; k < 2; ++k) {
             o_pr[k] = take(pl.pp.e_ub[1] * 4 + 4);
@@ -781,9 +789,10 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
         o_pk = take((nb + 1) * 8);
         o_pscan = take(((nb + 1) / pairs::SCAN_TILE64 + 2) * 8);
         o_prefs = take(pl.pp.scratch_elems * sizeof(uint2));
-        o_ppre = take(pl.pp.scratch_elems * sizeof(fe_t));
+        o_ppre = take(pl.pp.scratch_elems * sizeof(fq_t));
         o_pool = take((pl.pp.pool_base[pl.pp.rounds] + 1) * sizeof(g1a_t));
     }
+#endif
     int rc = zkb_reserve(ctx, buf, off);
     if (rc) return rc;
     char *p = (char *)buf.p;
@@ -801,7 +810,7 @@ int carve_ws(zkb_ctx *ctx, DevBuf &buf, const MsmPlan &pl, size_t n, MsmWs &ws, 
             ws.pw.refs[k] = (uint32_t *)(p + o_pr[k]); ws.pw.counts[k] = (uint32_t *)(p + o_pc[k]); ws.pw.starts[k] = (uint32_t *)(p + o_ps[k]);
         }
         ws.pw.pk = (unsigned long long *)(p + o_pk); ws.pw.scan_tmp = (unsigned long long *)(p + o_pscan);
-        ws.pw.pairrefs = (uint2 *)(p + o_prefs); ws.pw.prefix = (fe_t *)(p + o_ppre); ws.pw.pool = (g1a_t *)(p + o_pool);
+        ws.pw.pairrefs = (uint2 *)(p + o_prefs); ws.pw.prefix = (fq_t *)(p + o_ppre); ws.pw.pool = (g1a_t *)(p + o_pool);
     }
     *max_tasks_out = max_tasks;
     *max_heavy_tasks_out = max_heavy_tasks;
@@ -865,6 +874,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     // what is left, through the references / counts / starts of the last round
     const g1a_t *pool = nullptr;
     ZKB_CUDA(ctx, cudaEventRecord(st->ev_pairs[0], s));
+#if ZKB_HAVE_PAIR_ROUNDS
     if (pl.pp.rounds && n32) {
         const uint32_t *refs = ws.sorted, *cnts = ws.counts, *sts = ws.starts;
         const uint32_t nscan = nb + 1, ntiles = (nscan + pairs::SCAN_TILE64 - 1) / pairs::SCAN_TILE64;
@@ -885,6 +895,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
         pool = ws.pw.pool;
         ctx->launches += 6 * pl.pp.rounds;
     }
+#endif
     ZKB_CUDA(ctx, cudaEventRecord(st->ev_pairs[1], s));
     st->last_rounds = n32 ? pl.pp.rounds : 0;
     msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, nb, pl.seg, ws.ntasks, ws.size_hist, ws.misc, ws.heavy_list, ws.heavy_slot,
@@ -1007,9 +1018,9 @@ int zkb_srs_precompute(zkb_ctx *ctx, int c);
 int zkb_srs_load_g1(zkb_ctx *ctx, const uint64_t *xy_mont_host, size_t n) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!xy_mont_host && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_load_g1: null points");
-    int rc = zkb_reserve(ctx, ctx->srs, n * 64 + 64);
+    int rc = zkb_reserve(ctx, ctx->srs, n * AFF_BYTES + AFF_BYTES);
     if (rc) return rc;
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->srs.p, xy_mont_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->srs.p, xy_mont_host, n * AFF_BYTES, cudaMemcpyHostToDevice, ctx->stream));
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->srs_n = n;
     ctx->srs_lo = 0;
@@ -1022,9 +1033,9 @@ int zkb_srs_load_g1(zkb_ctx *ctx, const uint64_t *xy_mont_host, size_t n) {
 int zkb_srs_load_g1_dev(zkb_ctx *ctx, const uint64_t *xy_mont_dev, size_t n) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!xy_mont_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_load_g1_dev: null points");
-    int rc = zkb_reserve(ctx, ctx->srs, n * 64 + 64);
+    int rc = zkb_reserve(ctx, ctx->srs, n * AFF_BYTES + AFF_BYTES);
     if (rc) return rc;
-    ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->srs.p, xy_mont_dev, n * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->srs.p, xy_mont_dev, n * AFF_BYTES, cudaMemcpyDeviceToDevice, ctx->stream));
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->srs_n = n;
     ctx->srs_lo = 0;
@@ -1088,7 +1099,7 @@ int zkb_msm_set_window(zkb_ctx *ctx, int c) {
 }
 
 // scalars on the device, bases = resident SRS[offset .. offset + n); result as an XYZZ partial sum (16 limbs)
-int zkb_msm_g1_dev_partial(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xyzz[16]) {
+int zkb_msm_g1_dev_partial(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t *out_xyzz /* XYZZ_W words */) {
     if (!ctx || !out_xyzz) return ZKB_ERR_INVALID;
     if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_msm: offset + n exceeds the loaded SRS");
     if (!scalars_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: null scalars");
@@ -1102,17 +1113,17 @@ int zkb_msm_g1_dev_partial(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t off
     hec::Pt total;
     rc = msm_finish(ctx, pl, &total);
     if (rc) return rc;
-    memcpy(out_xyzz, &total, 128);
+    memcpy(out_xyzz, &total, XYZZ_BYTES);
     return ZKB_OK;
 }
 
-int zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+int zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t *out_xy /* AFF_W words */, int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
-    uint64_t xyzz[16];
+    uint64_t xyzz[XYZZ_W];
     int rc = zkb_msm_g1_dev_partial(ctx, scalars_dev, offset, n, xyzz);
     if (rc) return rc;
     hec::Pt p;
-    memcpy(&p, xyzz, 128);
+    memcpy(&p, xyzz, XYZZ_BYTES);
     hec::to_affine(p, out_xy, is_inf);
     return ZKB_OK;
 }
@@ -1120,14 +1131,14 @@ int zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, siz
 // Point-range sharded MSM: every rank of the communicator calls this with the scalars of ITS resident range
 // (scalars_dev[i] pairs with resident point offset + i); the ranks' partial sums are exchanged over NCCL (csrc/comm.cu) and
 // every rank returns the same affine point.  world == 1: the same as zkb_msm_g1_dev.
-int zkb_msm_g1_sharded_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+int zkb_msm_g1_sharded_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t offset, size_t n, uint64_t *out_xy /* AFF_W words */, int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
     if (ctx->world == 1) return zkb_msm_g1_dev(ctx, scalars_dev, offset, n, out_xy, is_inf);
-    uint64_t mine[16];
+    uint64_t mine[XYZZ_W];
     int rc = zkb_msm_g1_dev_partial(ctx, scalars_dev, offset, n, mine);
     if (rc) return rc;
-    std::vector<uint64_t> all((size_t)ctx->world * 16);
-    rc = zkb_comm_allgather(ctx, mine, 128, all.data());
+    std::vector<uint64_t> all((size_t)ctx->world * XYZZ_W);
+    rc = zkb_comm_allgather(ctx, mine, XYZZ_BYTES, all.data());
     if (rc) return rc;
     return zkb_g1_sum_partials(all.data(), (size_t)ctx->world, out_xy, is_inf);
 }
@@ -1135,7 +1146,7 @@ int zkb_msm_g1_sharded_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t off
 // Host scalars.  From 2^18 points on the MSM runs as two or three point ranges through the two pipelined workspaces: the
 // next range of the scalars crosses PCIe (copy stream) while the previous one is sorted and accumulated, and a range's
 // window reduction overlaps the next range's accumulation; the partial sums are added on the host.
-static int msm_host_partial(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xyzz[16]) {
+static int msm_host_partial(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t *out_xyzz /* XYZZ_W words */) {
     if (!scalars_host && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1: null scalars");
     if (offset + n > ctx->srs_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_msm: offset + n exceeds the loaded SRS");
     if (!state(ctx)->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "a zkb_commit_push batch is open (its scalars and results live in the buffers this call would reuse): call zkb_commit_finish first");
@@ -1184,13 +1195,13 @@ static int msm_host_partial(zkb_ctx *ctx, const uint64_t *scalars_host, size_t o
         ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[k & 1].tail_done));
         total = hec::add(total, msm_fold(plans[k & 1], st->slot[k & 1].pinned));
     }
-    memcpy(out_xyzz, &total, 128);
+    memcpy(out_xyzz, &total, XYZZ_BYTES);
     return ZKB_OK;
 }
 
-int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t *out_xy /* AFF_W words */, int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
-    uint64_t xyzz[16];
+    uint64_t xyzz[XYZZ_W];
     int rc = msm_host_partial(ctx, scalars_host, offset, n, xyzz);
     if (rc) return rc;
     return zkb_g1_sum_partials(xyzz, 1, out_xy, is_inf);
@@ -1198,28 +1209,28 @@ int zkb_msm_g1(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t
 
 // zkb_msm_g1_sharded_dev with HOST scalars: every rank uploads the scalars of its resident range through the pipelined
 // two-range path above (upload under accumulation), then the partial sums are exchanged
-int zkb_msm_g1_sharded(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+int zkb_msm_g1_sharded(zkb_ctx *ctx, const uint64_t *scalars_host, size_t offset, size_t n, uint64_t *out_xy /* AFF_W words */, int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
-    uint64_t mine[16];
+    uint64_t mine[XYZZ_W];
     int rc = msm_host_partial(ctx, scalars_host, offset, n, mine);
     if (rc) return rc;
     if (ctx->world == 1) return zkb_g1_sum_partials(mine, 1, out_xy, is_inf);
-    std::vector<uint64_t> all((size_t)ctx->world * 16);
-    rc = zkb_comm_allgather(ctx, mine, 128, all.data());
+    std::vector<uint64_t> all((size_t)ctx->world * XYZZ_W);
+    rc = zkb_comm_allgather(ctx, mine, XYZZ_BYTES, all.data());
     if (rc) return rc;
     return zkb_g1_sum_partials(all.data(), (size_t)ctx->world, out_xy, is_inf);
 }
 
 // arbitrary bases (drop-in for VariableBaseMSM::multi_scalar_mul / HomomorphicCommitment::multi_scalar_mul)
 int zkb_msm_g1_bases(zkb_ctx *ctx, const uint64_t *points_host, const uint64_t *scalars_host, size_t n,
-                     uint64_t out_xy[8], int *is_inf) {
+                     uint64_t *out_xy /* AFF_W words */, int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
     if ((!points_host || !scalars_host) && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1_bases: null input");
     if (!state(ctx)->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "a zkb_commit_push batch is open (its scalars and results live in the buffers this call would reuse): call zkb_commit_finish first");
-    int rc = zkb_reserve(ctx, ctx->stage, n * 96 + 96);
+    int rc = zkb_reserve(ctx, ctx->stage, (n + 1) * (AFF_BYTES + 32));
     if (rc) return rc;
-    char *d_pts = (char *)ctx->stage.p, *d_sc = d_pts + n * 64;
-    ZKB_CUDA(ctx, cudaMemcpyAsync(d_pts, points_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    char *d_pts = (char *)ctx->stage.p, *d_sc = d_pts + n * AFF_BYTES;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_pts, points_host, n * AFF_BYTES, cudaMemcpyHostToDevice, ctx->stream));
     ZKB_CUDA(ctx, cudaMemcpyAsync(d_sc, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     MsmPlan pl;
     rc = msm_enqueue(ctx, (const g1a_t *)d_pts, (const uint4 *)d_sc, n, ctx->msm_force_c, nullptr, 0, &pl);
@@ -1232,12 +1243,12 @@ int zkb_msm_g1_bases(zkb_ctx *ctx, const uint64_t *points_host, const uint64_t *
 }
 
 // sum of `count` XYZZ partial results (multi-GPU combine after the all-gather), affine out
-int zkb_g1_sum_partials(const uint64_t *xyzz, size_t count, uint64_t out_xy[8], int *is_inf) {
+int zkb_g1_sum_partials(const uint64_t *xyzz, size_t count, uint64_t *out_xy /* AFF_W words */, int *is_inf) {
     if ((!xyzz && count) || !out_xy) return ZKB_ERR_INVALID;
     hec::Pt total = hec::inf();
     for (size_t i = 0; i < count; ++i) {
         hec::Pt p;
-        memcpy(&p, xyzz + 16 * i, 128);
+        memcpy(&p, xyzz + XYZZ_W * i, XYZZ_BYTES);
         total = hec::add(total, p);
     }
     hec::to_affine(total, out_xy, is_inf);
@@ -1246,7 +1257,7 @@ int zkb_g1_sum_partials(const uint64_t *xyzz, size_t count, uint64_t out_xy[8], 
 
 // kzg10::commit's inner product for one polynomial held in HBM in Montgomery form:
 // converts the coefficients to canonical integers (into_repr) and runs the MSM against SRS[offset..].
-int zkb_commit_dev(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset, size_t n, uint64_t out_xy[8], int *is_inf) {
+int zkb_commit_dev(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset, size_t n, uint64_t *out_xy /* AFF_W words */, int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
     if (!coeffs_mont_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_dev: null coefficients");
     if (ctx->world > 1 || ctx->srs_global_n != ctx->srs_n) return zkb_commit_batch_dev(ctx, &coeffs_mont_dev, &offset, &n, 1, out_xy, is_inf);
@@ -1260,11 +1271,11 @@ int zkb_commit_dev(zkb_ctx *ctx, const uint64_t *coeffs_mont_dev, size_t offset,
 }
 
 // out_points_dev[i] = scalars_dev[i] * base  (affine, Montgomery); scalars canonical.
-int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], const uint64_t *scalars_dev, size_t n, uint64_t *out_points_dev) {
+int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t *base_xy /* AFF_W words */, const uint64_t *scalars_dev, size_t n, uint64_t *out_points_dev) {
     if (!ctx || !base_xy) return ZKB_ERR_INVALID;
     if ((!scalars_dev || !out_points_dev) && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_g1_fixed_base_mul_dev: null buffer");
     g1a_t b;
-    memcpy(&b, base_xy, 64);
+    memcpy(&b, base_xy, AFF_BYTES);
     if (n) g1_fixed_base_mul_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(b, (const uint4 *)scalars_dev, (uint32_t)n, (g1a_t *)out_points_dev);
     ZKB_CUDA(ctx, cudaGetLastError());
     return ZKB_OK;
@@ -1309,7 +1320,7 @@ static int commit_collect(zkb_ctx *ctx, MsmState *st, size_t k) {          // fo
     const int slot = (int)(k & 1);
     ZKB_CUDA(ctx, cudaEventSynchronize(st->slot[slot].tail_done));
     hec::Pt p = msm_fold(st->pipe_plan[slot], st->slot[slot].pinned);
-    memcpy(st->pipe_partial[k].data(), &p, 128);
+    memcpy(st->pipe_partial[k].data(), &p, XYZZ_BYTES);
     st->pipe_pending[k] = 0;
     return ZKB_OK;
 }
@@ -1419,7 +1430,7 @@ int zkb_commit_finish_partials(zkb_ctx *ctx, uint64_t *out_xyzz /* count x 16 */
     if (!out_xyzz && count) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_finish_partials: null output");
     int rc = ZKB_OK;
     for (size_t k = 0; k < count && !rc; ++k) rc = commit_collect(ctx, st, k);
-    for (size_t k = 0; k < count && !rc; ++k) memcpy(out_xyzz + 16 * k, st->pipe_partial[k].data(), 128);
+    for (size_t k = 0; k < count && !rc; ++k) memcpy(out_xyzz + XYZZ_W * k, st->pipe_partial[k].data(), XYZZ_BYTES);
     st->pipe_partial.clear();
     st->pipe_pending.clear();
     st->pipe_expected = 1;
@@ -1442,30 +1453,30 @@ int zkb_commit_finish(zkb_ctx *ctx, uint64_t *out_xy /* count x 8 */, int *is_in
     if (!out_xy && count) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_commit_finish: null output");
     int rc = ZKB_OK;
     for (size_t k = 0; k < count && !rc; ++k) rc = commit_collect(ctx, st, k);
-    std::vector<std::array<uint64_t, 16>> part;
+    std::vector<std::array<uint64_t, XYZZ_W>> part;
     part.swap(st->pipe_partial);
     st->pipe_pending.clear();
     st->pipe_expected = 1;
     if (rc) return rc;
     if (ctx->world > 1 && count) {
-        std::vector<std::array<uint64_t, 16>> all((size_t)ctx->world * count);
-        rc = zkb_comm_allgather(ctx, part.data(), count * 128, all.data());
+        std::vector<std::array<uint64_t, XYZZ_W>> all((size_t)ctx->world * count);
+        rc = zkb_comm_allgather(ctx, part.data(), count * XYZZ_BYTES, all.data());
         if (rc) return rc;
         for (size_t k = 0; k < count; ++k) {
             hec::Pt total = hec::inf();
             for (int r = 0; r < ctx->world; ++r) {
                 hec::Pt p;
-                memcpy(&p, all[(size_t)r * count + k].data(), 128);
+                memcpy(&p, all[(size_t)r * count + k].data(), XYZZ_BYTES);
                 total = hec::add(total, p);
             }
-            hec::to_affine(total, out_xy + 8 * k, is_inf ? is_inf + k : nullptr);
+            hec::to_affine(total, out_xy + AFF_W * k, is_inf ? is_inf + k : nullptr);
         }
         return ZKB_OK;
     }
     for (size_t k = 0; k < count; ++k) {
         hec::Pt p;
-        memcpy(&p, part[k].data(), 128);
-        hec::to_affine(p, out_xy + 8 * k, is_inf ? is_inf + k : nullptr);
+        memcpy(&p, part[k].data(), XYZZ_BYTES);
+        hec::to_affine(p, out_xy + AFF_W * k, is_inf ? is_inf + k : nullptr);
     }
     return ZKB_OK;
 }
@@ -1482,7 +1493,7 @@ int zkb_commit_batch_dev(zkb_ctx *ctx, const uint64_t *const *coeffs_mont_dev, c
     st->pipe_expected = count ? count : 1;
     for (size_t k = 0; k < count && !rc; ++k) rc = zkb_commit_push(ctx, coeffs_mont_dev[k], offsets ? offsets[k] : 0, lens[k]);
     if (rc) {                                                              // drain and drop the partial batch
-        std::vector<uint64_t> scratch(8 * st->pipe_partial.size() + 8);
+        std::vector<uint64_t> scratch(AFF_W * st->pipe_partial.size() + AFF_W);
         std::string err = ctx->err;
         zkb_commit_finish(ctx, scratch.data(), nullptr);
         ctx->err = err;

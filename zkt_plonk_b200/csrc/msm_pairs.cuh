@@ -24,7 +24,9 @@
 // formulas; affine outputs are canonical, so the results are bit-identical to the XYZZ-only path.
 #pragma once
 #include "ec.cuh"
+#if ZKB_CURVE == ZKB_CURVE_BN254
 #include "ff_inv.cuh"
+#endif
 
 namespace zkb {
 namespace pairs {
@@ -49,6 +51,10 @@ __device__ __forceinline__ void prefetch_xy(const g1a_t *p) {
 }
 __device__ __forceinline__ void prefetch_32(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// The pair rounds (an opt-in mode, off by default) exist for the 8-limb base field only: ff_inv.cuh's Euclid and the register
+// budget of pair_add_kernel are written for BN254.  On the BLS12 builds a plan never has rounds (msm.cu pick_pair_rounds).
+#if ZKB_CURVE == ZKB_CURVE_BN254
+#define ZKB_HAVE_PAIR_ROUNDS 1
 // ------------------------------------------------------------------ per-round bookkeeping
 // pk[b] = pairs of bucket b | entries of bucket b after the round << 32, b < nb; pk[nb] = 0 (the scan's total lands there)
 __global__ void __launch_bounds__(256) pack_kernel(const uint32_t *__restrict__ counts, uint32_t nb, unsigned long long *__restrict__ pk) {
@@ -301,6 +307,10 @@ __global__ void __launch_bounds__(THREADS, 4) pair_add_kernel(const g1a_t *__res
     }
 }
 
+#else
+#define ZKB_HAVE_PAIR_ROUNDS 0
+#endif
+
 // ------------------------------------------------------------------ host side
 struct Plan {
     uint32_t rounds = 0;
@@ -339,7 +349,7 @@ struct Ws {
     uint32_t *refs[2], *counts[2], *starts[2];
     unsigned long long *pk, *scan_tmp;
     uint2 *pairrefs;
-    fe_t *prefix;
+    fq_t *prefix;
     g1a_t *pool;
 };
 

@@ -453,7 +453,7 @@ int zkb_ntt_run_batch(zkb_ctx *ctx, uint64_t *const *d_ptrs, size_t count, size_
         }
         return ZKB_OK;
     }
-    if (log_n > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ntt: log_n exceeds Fr TWO_ADICITY (28)");
+    if (log_n > host::FR_TWO_ADICITY || log_n > 31) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ntt: log_n exceeds Fr TWO_ADICITY (28 on BN254) or 31");
     const size_t n = (size_t)1 << log_n;
     if (len > n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ntt: len > 2^log_n");
     inverse = inverse ? 1 : 0;
@@ -476,7 +476,7 @@ int zkb_ntt_run_batch(zkb_ctx *ctx, uint64_t *const *d_ptrs, size_t count, size_
     uint32_t cs_s = 0;
     host::Fe ninv = host::inv(host::from_u64((uint64_t)n, host::FR), host::FR);
     if (coset) {
-        host::Fe g = host::from_u64(5, host::FR);
+        host::Fe g = host::from_u64(host::FR_GENERATOR, host::FR);
         uint64_t key = (3ull << 32) | (log_n << 1) | (unsigned)inverse;
         int rc = inverse ? get_2lvl_table(ctx, key, log_n, host::inv(g, host::FR), ninv, &cs2, &cs_s)
                          : get_2lvl_table(ctx, key, log_n, g, host::one(host::FR), &cs2, &cs_s);
@@ -523,7 +523,7 @@ int zkb_ntt_run_batch(zkb_ctx *ctx, uint64_t *const *d_ptrs, size_t count, size_
                     DevBuf b;
                     rc = zkb_reserve(ctx, b, ((size_t)1 << t) * 32);
                     if (rc) return rc;
-                    rc = build_pow_table(ctx, (uint4 *)b.p, host::from_u64(5, host::FR), host::one(host::FR), 1u << t, log_s);
+                    rc = build_pow_table(ctx, (uint4 *)b.p, host::from_u64(host::FR_GENERATOR, host::FR), host::one(host::FR), 1u << t, log_s);
                     if (rc) return rc;
                     it = ctx->tables.emplace(ckey, b).first;
                 }

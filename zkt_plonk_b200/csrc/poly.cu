@@ -578,7 +578,7 @@ int zkb_z1_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t beta[4], const
                      const uint64_t *sigma3, uint64_t *out_dev) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!beta || !gamma || !a || !b || !c || !sigma1 || !sigma2 || !sigma3 || !out_dev) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_z1_evals_dev: null argument");
-    if (log_n > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_z1_evals_dev: log_n exceeds Fr TWO_ADICITY (28)");
+    if (log_n > host::FR_TWO_ADICITY || log_n > 31) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_z1_evals_dev: log_n exceeds Fr TWO_ADICITY (28 on BN254) or 31");
     const size_t n = (size_t)1 << log_n;
     GpWs w;
     int rc = gp_workspace(ctx, n, w);
@@ -605,7 +605,7 @@ int zkb_z2_evals_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t delta[4], cons
                      const uint64_t *t, const uint64_t *h1, const uint64_t *h2, uint64_t *out_dev) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!delta || !epsilon || !f || !t || !h1 || !h2 || !out_dev) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_z2_evals_dev: null argument");
-    if (log_n > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_z2_evals_dev: log_n exceeds Fr TWO_ADICITY (28)");
+    if (log_n > host::FR_TWO_ADICITY || log_n > 31) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_z2_evals_dev: log_n exceeds Fr TWO_ADICITY (28 on BN254) or 31");
     const size_t n = (size_t)1 << log_n;
     GpWs w;
     int rc = gp_workspace(ctx, n, w);
@@ -636,7 +636,7 @@ int zkb_quotient_evals_range_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t ch
                                  const uint64_t *const epk[11], uint64_t *out_dev, size_t lo, size_t hi) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!challenges || !wit || !epk || !out_dev) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_quotient_evals_dev: null argument");
-    if (log_n + 2 > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_quotient_evals_dev: 4n exceeds 2^28 (InvalidEvalDomainSize)");
+    if (log_n + 2 > host::FR_TWO_ADICITY || log_n + 2 > 31) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_quotient_evals_dev: 4n exceeds 2^28 (InvalidEvalDomainSize)");
     if (log_n < 3) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_quotient_evals_dev: n >= 8 required (quotient_poly.rs:44 asserts n >= 5)");
     for (int k = 0; k < 9; ++k) if (!wit[k]) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_quotient_evals_dev: null witness table");
     for (int k = 0; k < 11; ++k) if (!epk[k]) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_quotient_evals_dev: null key table");
@@ -653,7 +653,7 @@ int zkb_quotient_evals_range_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t ch
     Fe al = host_fe(challenges), be = host_fe(challenges + 4), ga = host_fe(challenges + 8), de = host_fe(challenges + 12),
        ep_ = host_fe(challenges + 16);
     Fe al2 = sqr(al, FR), al3 = mul(al2, al, FR), al4 = mul(al3, al, FR), al5 = mul(al4, al, FR);
-    Fe opd = add(one(FR), de, FR), eopd = mul(ep_, opd, FR), g = from_u64(5, FR);
+    Fe opd = add(one(FR), de, FR), eopd = mul(ep_, opd, FR), g = from_u64(host::FR_GENERATOR, FR);
     p.alpha = dev_fe(al); p.alpha2 = dev_fe(al2); p.alpha3 = dev_fe(al3); p.alpha4 = dev_fe(al4); p.alpha5 = dev_fe(al5);
     p.beta = dev_fe(be); p.gamma = dev_fe(ga); p.delta = dev_fe(de); p.eps = dev_fe(ep_); p.opd = dev_fe(opd); p.eopd = dev_fe(eopd);
     p.gen = dev_fe(g); p.k1 = dev_fe(from_u64(7, FR)); p.k2 = dev_fe(from_u64(13, FR));
@@ -683,7 +683,7 @@ int zkb_quotient_evals_range_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t ch
 int zkb_l1_coset_dev(zkb_ctx *ctx, unsigned log_n, uint64_t *out_dev) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!out_dev) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_l1_coset_dev: null output");
-    if (log_n + 2 > 28) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_l1_coset_dev: 4n exceeds 2^28 (InvalidEvalDomainSize)");
+    if (log_n + 2 > host::FR_TWO_ADICITY || log_n + 2 > 31) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_l1_coset_dev: 4n exceeds 2^28 (InvalidEvalDomainSize)");
     const size_t n = (size_t)1 << log_n;
     // L_1 = ifft(e_0) has all n coefficients equal to 1/n; its coset FFT over 4n is the table (keys/mod.rs:117-119)
     host::Fe ninv = host::inv(host::from_u64((uint64_t)n, host::FR), host::FR);
