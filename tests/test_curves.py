@@ -1,0 +1,154 @@
+"""CPU-only: the BLS12-381 / BLS12-377 builds (the reference's test_full runs on both: plonk-core/src/plonk.rs:226-254).
+
+Pins the per-curve C oracle (oracle/zkb_oracle.c compiled with -DZKO_CURVE=1/2) against the mathematical definitions in
+Python big integers -- field operations, the O(n^2) DFT with the root arkworks derives, affine double-and-add -- and against
+published constants (ark-bls12-381 / ark-bls12-377 0.3 TWO_ADIC_ROOT_OF_UNITY, the standard G1 generators); checks the
+generated sources are current and that every build of the product library exports the whole C ABI.
+"""
+import ctypes
+import importlib.util
+import os
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import cref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location("gen_curves", os.path.join(ROOT, "tools", "gen_curves.py"))
+gen_curves = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(gen_curves)
+CURVES = {c["name"]: c for c in gen_curves.CURVES}
+BLS = ["bls12_381", "bls12_377"]
+
+
+def limbs(vals, nw):
+    a = np.zeros((len(vals), nw), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        for j in range(nw):
+            a[i, j] = (v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    return a
+
+
+def ints(a, nw):
+    a = np.ascontiguousarray(a).reshape(-1, nw)
+    return [sum(int(a[i, j]) << (64 * j) for j in range(nw)) for i in range(a.shape[0])]
+
+
+def test_generated_sources_are_current(tmp_path):
+    """curve_params.h, ff_wide.cuh, zko_curve_params.h and unsupported.cu are what their generators produce."""
+    csrc = os.path.join(ROOT, "zkt_plonk_b200", "csrc")
+    assert open(os.path.join(csrc, "curve_params.h")).read() == gen_curves.gen_params()
+    assert open(os.path.join(csrc, "ff_wide.cuh")).read() == gen_curves.gen_wide()
+    assert open(os.path.join(ROOT, "oracle", "zko_curve_params.h")).read() == gen_curves.gen_oracle_params()
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "tools", "gen_unsupported.py"), "--check"]) == 0
+
+
+@pytest.mark.parametrize("curve", BLS)
+def test_published_constants(curve):
+    c = CURVES[curve]
+    gen_curves.check(c)                       # generator on the curve and of order r, GENERATOR a non-residue, GENERATOR^T == root
+    r = c["r"]
+    assert pow(c["root"], 1 << c["s"], r) == 1 and pow(c["root"], 1 << (c["s"] - 1), r) == r - 1
+    assert {"bls12_381": (32, 7, 255, 381), "bls12_377": (47, 22, 253, 377)}[curve] == (c["s"], c["fr_gen"], r.bit_length(), c["q"].bit_length())
+    o = cref.oracle(curve)
+    assert (o.nq, o.fr_bits) == (6, r.bit_length())
+    one = ints(o.to_mont(cref.FQ, limbs([1], 6)), 6)[0]
+    assert one == (1 << 384) % c["q"]
+
+
+@pytest.mark.parametrize("curve", BLS)
+def test_field_ops_vs_python(curve):
+    o, c = cref.oracle(curve), CURVES[curve]
+    for field, p, nw in ((cref.FR, c["r"], 4), (cref.FQ, c["q"], 6)):
+        a, b = o.rand_fe(field, 200, 1), o.rand_fe(field, 200, 2)
+        a[0], b[0] = 0, 0
+        a[1] = limbs([p - 1], nw)[0]
+        b[1] = a[1]
+        a[2] = limbs([1], nw)[0]
+        ai, bi = ints(a, nw), ints(b, nw)
+        assert all(x < p for x in ai + bi)
+        am, bm = o.to_mont(field, a), o.to_mont(field, b)
+        assert ints(o.from_mont(field, am), nw) == ai
+        assert ints(o.from_mont(field, o.binop(field, 0, am, bm)), nw) == [x * y % p for x, y in zip(ai, bi)]
+        assert ints(o.from_mont(field, o.binop(field, 1, am, bm)), nw) == [(x + y) % p for x, y in zip(ai, bi)]
+        assert ints(o.from_mont(field, o.binop(field, 2, am, bm)), nw) == [(x - y) % p for x, y in zip(ai, bi)]
+        assert ints(o.from_mont(field, o.binop(field, 3, am)), nw) == [x * x % p for x in ai]
+        assert ints(o.from_mont(field, o.binop(field, 4, am[1:])), nw) == [pow(x, -1, p) for x in ai[1:]]
+
+
+@pytest.mark.parametrize("curve", BLS)
+@pytest.mark.parametrize("log_n", [0, 1, 3, 6])
+def test_ntt_vs_definition(curve, log_n):
+    """A_k = sum_j a_j w^(jk) with w = TWO_ADIC_ROOT^(2^(s - log_n)); coset: a_j scaled by g^j first (g = GENERATOR); inverses undo."""
+    o, c = cref.oracle(curve), CURVES[curve]
+    r, n = c["r"], 1 << log_n
+    w = pow(c["root"], 1 << (c["s"] - log_n), r)
+    g = c["fr_gen"]
+    x = o.rand_fe(cref.FR, n, 10 + log_n)
+    xi = ints(x, 4)
+    xm = o.to_mont(cref.FR, x)
+    fwd = [sum(xi[j] * pow(w, j * k, r) for j in range(n)) % r for k in range(n)]
+    cfwd = [sum(xi[j] * pow(g, j, r) * pow(w, j * k, r) for j in range(n)) % r for k in range(n)]
+    assert ints(o.from_mont(cref.FR, o.ntt(xm, log_n)), 4) == fwd
+    assert ints(o.from_mont(cref.FR, o.ntt(xm, log_n, coset=True)), 4) == cfwd
+    assert np.array_equal(o.ntt(o.ntt(xm, log_n), log_n, inverse=True), xm)
+    assert np.array_equal(o.ntt(o.ntt(xm, log_n, coset=True), log_n, inverse=True, coset=True), xm)
+
+
+@pytest.mark.parametrize("curve", BLS)
+def test_g1_and_msm_vs_affine_definition(curve):
+    o, c = cref.oracle(curve), CURVES[curve]
+    q, r = c["q"], c["r"]
+    G = c["gen"]
+    mq = lambda pts: o.to_mont(cref.FQ, limbs([v for P in pts for v in (P if P else (0, 0))], 6)).reshape(len(pts), 12)
+    gm = mq([G])[0].copy()
+    assert o.g1_on_curve(gm)
+    rnd = random.Random(5)
+    ks = [0, 1, 2, r - 1, r - 2] + [rnd.randrange(r) for _ in range(7)]
+    got = o.g1_mul(gm, limbs(ks, 4))
+    exp = [gen_curves.ec_mul(k, G, q) for k in ks]
+    assert np.array_equal(got, mq(exp))
+    # MSM over points k_i G with the edge scalars the reference meets (0, 1, r - 1), the point at infinity and a repeated base
+    n = 70
+    pk = [rnd.randrange(1, r) for _ in range(n)]
+    pts = o.g1_mul(gm, limbs(pk, 4))
+    pts[3] = 0
+    pk[3] = 0
+    pts[5] = pts[4]
+    pk[5] = pk[4]
+    sc = [rnd.randrange(r) for _ in range(n)]
+    sc[0], sc[1], sc[2], sc[7] = 0, 1, r - 1, 1
+    out, inf = o.msm_g1(pts, limbs(sc, 4))
+    exp_k = sum(s * k for s, k in zip(sc, pk)) % r
+    assert not inf and np.array_equal(out, mq([gen_curves.ec_mul(exp_k, G, q)])[0])
+    out, inf = o.msm_g1(pts[:2], limbs([r - 1, 0], 4))
+    assert np.array_equal(out, mq([gen_curves.ec_mul((r - 1) * pk[0] % r, G, q)])[0])
+    out, inf = o.msm_g1(pts[:4], limbs([0, 0, 0, 0], 4))
+    assert inf and not out.any()
+
+
+@pytest.mark.parametrize("curve", ["bn254"] + BLS)
+def test_every_build_exports_the_whole_abi(curve):
+    """No compute calls (no GPU here): each curve's shared object loads, exports every symbol include/zkb200.h declares and
+    reports its curve; the BN254-only entry points of the BLS12 builds answer ZKB_ERR_UNSUPPORTED instead of missing."""
+    from zkt_plonk_b200 import _lib
+    lib = _lib.lib(curve)
+    missing = [s for s in _lib.declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+    cid, frw, fqw, bits, has_prover = _lib.curve_info(curve)
+    assert (cid, frw) == (_lib.CURVE_IDS[curve], 4)
+    assert (fqw, bits, has_prover) == {"bn254": (4, 254, 1), "bls12_381": (6, 255, 0), "bls12_377": (6, 253, 0)}[curve]
+    gen = np.zeros(2 * fqw, dtype=np.uint64)
+    assert lib.zkb_g1_generator(ctypes.c_void_p(gen.ctypes.data)) == 0
+    o = cref.oracle(curve)
+    assert o.g1_on_curve(gen)
+    exp = CURVES[curve]["gen"]
+    assert ints(o.from_mont(cref.FQ, gen.reshape(2, fqw)), fqw) == list(exp)
+    if curve != "bn254":
+        n = ctypes.c_size_t(0)
+        assert lib.zkb_ck_file_info(b"/nonexistent", ctypes.byref(n), ctypes.byref(n)) == _lib.ZKB_ERR_UNSUPPORTED
+        assert lib.zkb_plonk_verify(0, None, 0, None, None, None, None, None, None, 0) == _lib.ZKB_ERR_UNSUPPORTED

@@ -1,4 +1,8 @@
-"""Loader for libzkb200.so (the C ABI of include/zkb200.h).
+"""Loader for libzkb200.so (the C ABI of include/zkb200.h) and its per-curve builds.
+
+One shared object per curve, same entry points (the reference's generics monomorphise per pairing engine, plonk.rs:226-254):
+`lib()` / `lib("bn254")` is libzkb200.so (everything), `lib("bls12_381")` and `lib("bls12_377")` hold the field, NTT, MSM /
+commitment and polynomial kernels; their protocol-driver entry points return ZKB_ERR_UNSUPPORTED.
 
 There is NO CPU fallback: if the shared library is missing the import fails loudly, and if no CUDA device
 is present `Context()` raises.  Nothing under oracle/ is ever imported from here.
@@ -12,7 +16,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ZKB200_LIB") or os.path.join(_HERE, "libzkb200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "zkb200.h")
 
-ZKB_OK, ZKB_ERR_INVALID, ZKB_ERR_DOMAIN, ZKB_ERR_CUDA, ZKB_ERR_NO_SRS, ZKB_ERR_OOM = 0, -1, -2, -3, -4, -5
+CURVE_LIBS = {"bn254": LIB_PATH, "bls12_381": os.path.join(_HERE, "libzkb200_bls12_381.so"),
+              "bls12_377": os.path.join(_HERE, "libzkb200_bls12_377.so")}
+CURVE_IDS = {"bn254": 0, "bls12_381": 1, "bls12_377": 2}
+
+ZKB_OK, ZKB_ERR_INVALID, ZKB_ERR_DOMAIN, ZKB_ERR_CUDA, ZKB_ERR_NO_SRS, ZKB_ERR_OOM, ZKB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 
 
 class ZkbError(RuntimeError):
@@ -27,12 +35,13 @@ def declared_symbols():
         return sorted(set(re.findall(r"^ZKB_API [\w \*]*?\b(zkb_\w+)\(", f.read(), flags=re.M)))
 
 
-def load():
-    if not os.path.exists(LIB_PATH):
+def load(curve="bn254"):
+    path = CURVE_LIBS[curve]
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  zkt_plonk_b200 has no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     vp, sz, u, i = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_int
     sig = {
         "zkb_ctx_create": (i, [i, ctypes.POINTER(vp)]),
@@ -41,6 +50,8 @@ def load():
         "zkb_ctx_sync": (i, [vp]),
         "zkb_last_error": (ctypes.c_char_p, [vp]),
         "zkb_version": (ctypes.c_char_p, []),
+        "zkb_curve_info": (i, [ctypes.POINTER(i)] * 5),
+        "zkb_g1_generator": (i, [vp]),
         "zkb_dev_alloc": (i, [vp, sz, ctypes.POINTER(vp)]),
         "zkb_dev_free": (i, [vp, vp]),
         "zkb_h2d": (i, [vp, vp, vp, sz]),
@@ -131,11 +142,19 @@ def load():
     return lib
 
 
-_LIB = None
+_LIBS = {}
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        _LIB = load()
-    return _LIB
+def lib(curve="bn254"):
+    if curve not in _LIBS:
+        _LIBS[curve] = load(curve)
+    return _LIBS[curve]
+
+
+def curve_info(curve="bn254"):
+    """(curve_id, fr_words, fq_words, fr_bits, has_prover) of a curve's library -- needs no GPU."""
+    v = [ctypes.c_int(0) for _ in range(5)]
+    rc = lib(curve).zkb_curve_info(*[ctypes.byref(x) for x in v])
+    if rc != 0:
+        raise ZkbError(rc, "zkb_curve_info failed")
+    return tuple(x.value for x in v)

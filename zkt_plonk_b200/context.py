@@ -23,8 +23,12 @@ def _dev_ptr(t):
 
 
 class Context:
-    def __init__(self, device=0, stream=None):
-        self._lib = _lib.lib()
+    def __init__(self, device=0, stream=None, curve="bn254"):
+        """curve: "bn254" (default; the whole library), "bls12_381" or "bls12_377" (field / NTT / MSM / polynomial kernels)."""
+        self._lib = _lib.lib(curve)
+        self.curve = curve
+        _, self.fr_words, self.fq_words, self.fr_bits, self.has_prover = _lib.curve_info(curve)
+        self.aff_words, self.xyzz_words = 2 * self.fq_words, 4 * self.fq_words      # an affine point / an XYZZ partial sum
         h = ctypes.c_void_p()
         rc = self._lib.zkb_ctx_create(int(device), ctypes.byref(h))
         if rc != 0:
@@ -94,7 +98,7 @@ class Context:
         if isinstance(points, np.ndarray):
             self._check(self._lib.zkb_srs_load_g1(self._h, _host_ptr(points), points.shape[0]))
         else:
-            self._check(self._lib.zkb_srs_load_g1_dev(self._h, _dev_ptr(points), points.numel() // 8))
+            self._check(self._lib.zkb_srs_load_g1_dev(self._h, _dev_ptr(points), points.numel() // self.aff_words))
 
     def srs_load_ck_file(self, path, max_points=0):
         """powers_of_g of the reference CLI's committer-key file (`ck`, bin/src/main.rs:274) become the resident SRS."""
@@ -115,7 +119,7 @@ class Context:
 
     def msm(self, scalars, offset=0, n=None):
         """scalars: canonical, host (n,4) uint64 array or CUDA tensor.  Returns ((8,) uint64 affine, is_inf)."""
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(self.aff_words, dtype=np.uint64)
         inf = ctypes.c_int(0)
         if isinstance(scalars, np.ndarray):
             n = scalars.shape[0] if n is None else n
@@ -127,14 +131,14 @@ class Context:
         return out, bool(inf.value)
 
     def msm_partial(self, scalars_dev, offset, n):
-        out = np.zeros(16, dtype=np.uint64)
+        out = np.zeros(self.xyzz_words, dtype=np.uint64)
         self._check(self._lib.zkb_msm_g1_dev_partial(self._h, _dev_ptr(scalars_dev), offset, n, _host_ptr(out)))
         return out
 
     def msm_sharded(self, scalars_dev, offset=0, n=None):
         """Collective (every rank of the context's communicator): this rank's scalars against its resident SRS range; the
         partial sums are exchanged inside the library (NCCL) and every rank returns the same ((8,) affine, is_inf)."""
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(self.aff_words, dtype=np.uint64)
         inf = ctypes.c_int(0)
         if isinstance(scalars_dev, np.ndarray):                    # host scalars: upload overlapped with the accumulation
             n = scalars_dev.shape[0] if n is None else n
@@ -146,14 +150,14 @@ class Context:
 
     def msm_bases(self, points, scalars):
         n = min(points.shape[0], scalars.shape[0])
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(self.aff_words, dtype=np.uint64)
         inf = ctypes.c_int(0)
         self._check(self._lib.zkb_msm_g1_bases(self._h, _host_ptr(points), _host_ptr(scalars), n, _host_ptr(out),
                                                ctypes.byref(inf)))
         return out, bool(inf.value)
 
     def commit_dev(self, coeffs_mont_dev, offset, n):
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(self.aff_words, dtype=np.uint64)
         inf = ctypes.c_int(0)
         self._check(self._lib.zkb_commit_dev(self._h, _dev_ptr(coeffs_mont_dev), offset, n, _host_ptr(out),
                                              ctypes.byref(inf)))
@@ -165,7 +169,7 @@ class Context:
         P = (ctypes.c_void_p * k)(*[_dev_ptr(t).value for t in coeffs_list])
         L = (ctypes.c_size_t * k)(*lens)
         O = (ctypes.c_size_t * k)(*(offsets if offsets is not None else [0] * k))
-        out = np.zeros((k, 8), dtype=np.uint64)
+        out = np.zeros((k, self.aff_words), dtype=np.uint64)
         inf = (ctypes.c_int * k)()
         self._check(self._lib.zkb_commit_batch_dev(self._h, P, O, L, k, _host_ptr(out), inf))
         return [(out[j].copy(), bool(inf[j])) for j in range(k)]
@@ -224,14 +228,14 @@ class Context:
 
     def commit_finish(self, count):
         """Wait for the open batch of `count` pushed polynomials; [((8,) affine, is_inf), ...] in push order."""
-        out = np.zeros((max(count, 1), 8), dtype=np.uint64)
+        out = np.zeros((max(count, 1), self.aff_words), dtype=np.uint64)
         inf = (ctypes.c_int * max(count, 1))()
         self._check(self._lib.zkb_commit_finish(self._h, _host_ptr(out), inf))
         return [(out[j].copy(), bool(inf[j])) for j in range(count)]
 
     def commit_finish_partials(self, count):
         """Close the open batch without the exchange between ranks: (count, 16) XYZZ partial sums of this rank."""
-        out = np.zeros((max(count, 1), 16), dtype=np.uint64)
+        out = np.zeros((max(count, 1), self.xyzz_words), dtype=np.uint64)
         self._check(self._lib.zkb_commit_finish_partials(self._h, _host_ptr(out)))
         return out[:count]
 
@@ -327,7 +331,13 @@ class Context:
         return v.value
 
     # -- test hook
+    def g1_generator(self):
+        out = np.zeros(self.aff_words, dtype=np.uint64)
+        self._check(self._lib.zkb_g1_generator(_host_ptr(out)))
+        return out
+
     def fp_binop(self, field, op, a, b=None):
+        """field 0: Fr ((n, 4) words), field 1: Fq ((n, fq_words) words)."""
         b = a if b is None else b
         out = np.empty_like(a)
         self._check(self._lib.zkb_test_fp_binop(self._h, field, op, _host_ptr(out), _host_ptr(a), _host_ptr(b),
@@ -335,12 +345,14 @@ class Context:
         return out
 
 
-def sum_partials(parts):
-    """parts: (k, 16) uint64 XYZZ shard results -> ((8,) affine, is_inf).  Host-only (<= 8 group additions)."""
-    parts = np.ascontiguousarray(parts, dtype=np.uint64).reshape(-1, 16)
-    out = np.zeros(8, dtype=np.uint64)
+def sum_partials(parts, curve="bn254"):
+    """parts: (k, 16) uint64 XYZZ shard results -> ((8,) affine, is_inf) (24 / 12 words on the BLS12 curves).  Host-only
+    (<= 8 group additions)."""
+    fq_words = _lib.curve_info(curve)[2]
+    parts = np.ascontiguousarray(parts, dtype=np.uint64).reshape(-1, 4 * fq_words)
+    out = np.zeros(2 * fq_words, dtype=np.uint64)
     inf = ctypes.c_int(0)
-    rc = _lib.lib().zkb_g1_sum_partials(_host_ptr(parts), parts.shape[0], _host_ptr(out), ctypes.byref(inf))
+    rc = _lib.lib(curve).zkb_g1_sum_partials(_host_ptr(parts), parts.shape[0], _host_ptr(out), ctypes.byref(inf))
     if rc != 0:
         raise ZkbError(rc, "zkb_g1_sum_partials failed")
     return out, bool(inf.value)
