@@ -112,7 +112,7 @@ def _limbs13(a):
     return out
 
 
-def dot_mod_r_fast(s_limbs, k_limbs, chunk=1 << 20):
+def dot_mod_r_fast(s_limbs, k_limbs, chunk=1 << 20, modulus=None):
     """The same dot product for millions of terms: both vectors in 13-bit limbs, one float64 GEMM per chunk of 2^20 terms
     (every entry of the 20 x 20 limb-product matrix stays below 2^46, exact in a double), recombined with Python integers."""
     n = s_limbs.shape[0]
@@ -122,7 +122,7 @@ def dot_mod_r_fast(s_limbs, k_limbs, chunk=1 << 20):
         for a in range(20):
             for b in range(20):
                 acc[a][b] += int(m[a, b])
-    return sum(acc[a][b] << (13 * (a + b)) for a in range(20) for b in range(20)) % R_MOD
+    return sum(acc[a][b] << (13 * (a + b)) for a in range(20) for b in range(20)) % (modulus or R_MOD)
 
 
 def int_to_limbs(v):
@@ -594,6 +594,8 @@ def run_main(args):
         del x, xs, epk, qout, wit, cols, zout
     except Exception as e:  # the extras must never sink the MSM line
         extra["ntt_error"] = repr(e)
+    if world == 1 and not args.no_curves:
+        extra["other_curves"] = run_curve_extras(z, torch, dev, flush, int_peak, min(log_n, 20))
 
     # ---- CPU baseline (rank 0, N = 1): the oracle's VariableBaseMSM restatement on the same points and scalars
     cpu = None
@@ -642,6 +644,99 @@ def run_main(args):
         dist.destroy_process_group()
     if not bit_exact:
         raise SystemExit("bench.py: MSM result differs from the closed-form answer (see \"check\" in the JSON line)")
+
+
+CURVE_R = {"bls12_381": 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001,
+           "bls12_377": 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001}
+
+
+def run_curve_extras(z, torch, dev, flush, int_peak, log_n):
+    """The same two kernels on the other curves the reference is tested on (plonk.rs:226-254): one resident-key G1 MSM of
+    2^log_n points and one coset NTT of 2^(log_n + 2) elements per curve, through that curve's build of the library
+    (libzkb200_bls12_381.so / libzkb200_bls12_377.so), device-timed like the headline; every MSM result is checked against the
+    closed form (sum s_i k_i mod r) * G.  Scalars: 252 random bits (below every r)."""
+    out = {}
+    n, ln = 1 << log_n, min(log_n + 2, 22)
+    for curve, r in CURVE_R.items():
+        try:
+            c = z.Context(dev.index or 0, curve=curve)
+            c.set_stream(torch.cuda.current_stream())
+            rng = np.random.default_rng(11)
+
+            def scalars(m):
+                a = rng.integers(0, 2**64, size=(m, 4), dtype=np.uint64)
+                a[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+                return a
+
+            G = c.g1_generator()
+            k_host = scalars(n)
+            P = torch.empty((n, c.aff_words), dtype=torch.int64, device=dev)
+            c.g1_fixed_base_mul_dev(G, torch.from_numpy(k_host.view(np.int64)).to(dev), n, P)
+            c.srs_load(P)
+            t0 = time.perf_counter()
+            c.srs_precompute(0)
+            torch.cuda.synchronize()
+            t_pre = time.perf_counter() - t0
+            s_host = scalars(n)
+            s_dev = torch.from_numpy(s_host.view(np.int64)).to(dev)
+            dot = dot_mod_r_fast(s_host, k_host, modulus=r)
+            exp = torch.empty((1, c.aff_words), dtype=torch.int64, device=dev)
+            c.g1_fixed_base_mul_dev(G, torch.from_numpy(int_to_limbs(dot).view(np.int64)).to(dev), 1, exp)
+            torch.cuda.synchronize()
+            exp = exp.cpu().numpy().view(np.uint64)[0]
+            ok, ts, acc = True, [], []
+            for it in range(3 + 5):
+                flush.zero_()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                got, inf = c.msm(s_dev)
+                e1.record()
+                torch.cuda.synchronize()
+                ok = ok and (not inf) and bool(np.array_equal(got, exp))
+                if it >= 3:
+                    ts.append(e0.elapsed_time(e1))
+                    acc.append(c.msm_last_timing()["accumulate_ms"])
+            tm = c.msm_last_timing()
+            ms = statistics.mean(ts)
+            # one mixed addition as implemented for 12 limbs: 10 products (no dedicated squaring, no shared reduction) of
+            # 2 * 12^2 + 12 = 300 multiply-adds each
+            macs_per_add = 10 * 300
+            int_ops = 2.0 * n * tm["windows"] * macs_per_add
+            acc_s = statistics.mean(acc) * 1e-3
+            N = 1 << ln
+            x = torch.from_numpy(scalars(N).view(np.int64)).to(dev)
+            for _ in range(3):
+                c.ntt_dev(x, ln, False, True)
+            tn = []
+            for _ in range(5):
+                flush.zero_()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                c.ntt_dev(x, ln, False, True)
+                e1.record()
+                torch.cuda.synchronize()
+                tn.append(e0.elapsed_time(e1))
+            t_ntt = statistics.mean(tn) * 1e-3
+            prods = (N // 2) * ln + N
+            out[curve] = {"msm": {"workload": f"kzg_commit_g1_msm_2^{log_n}", "ms_per_step": ms, "points_per_s": n / (ms * 1e-3),
+                                  "bit_exact_vs_closed_form": ok, "window_bits": tm["c"], "windows": tm["windows"],
+                                  "phases_ms": {"sort": tm["sort_ms"], "accumulate": tm["accumulate_ms"], "heavy": tm["heavy_ms"], "reduce": tm["reduce_ms"]},
+                                  "fixed_base_tables": {"build_seconds_once_per_srs": t_pre, "table_bytes": n * 8 * c.aff_words * tm["windows"]},
+                                  "roofline_int": {"kernel": "msm_accumulate_kernel", "achieved": int_ops / acc_s / 1e12, "peak": int_peak / 1e12,
+                                                   "unit": "T int32 IMAD/s", "frac": int_ops / acc_s / int_peak,
+                                                   "macs_per_mixed_addition": macs_per_add}},
+                           "ntt": {"workload": f"coset_fft_2^{ln}", "ms": t_ntt * 1e3, "elems_per_s": N / t_ntt,
+                                   "roofline_int": {"achieved": 2.0 * prods * 136 / t_ntt / 1e12, "peak": int_peak / 1e12,
+                                                    "unit": "T int32 IMAD/s", "frac": 2.0 * prods * 136 / t_ntt / int_peak}},
+                           "dtype": "Fr u32x8, Fq u32x12"}
+            del P, x, s_dev
+            c.close()
+            torch.cuda.empty_cache()
+        except Exception as e:  # the extras must never sink the headline
+            out[curve] = {"error": repr(e)}
+    return out
 
 
 def run_fixed_size_sweep(z, torch, dist, device, rank, world, P, k_host, G, flush, total_logs):
@@ -860,6 +955,7 @@ def main():
     ap.add_argument("--no-precompute", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-curves", dest="no_curves", action="store_true", help="skip the BLS12-381 / BLS12-377 MSM and NTT extras")
     ap.add_argument("--sweep-logs", dest="sweep_logs", type=int, nargs="*", default=[20, 22, 24],
                     help="total sizes (log2) of the fixed-size MSM sweep in extra.msm_fixed_size_sweep")
     ap.add_argument("--prove-log-n", dest="prove_log_n", type=int, default=0,

@@ -9,8 +9,9 @@ import zkt_plonk_b200 as z
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--sizes", type=int, nargs="+", default=[16, 18, 20, 22, 24])
+ap.add_argument("--curve", default="bn254", choices=["bn254", "bls12_381", "bls12_377"])
 args = ap.parse_args()
-ctx = z.Context(0); ctx.set_stream(torch.cuda.current_stream())
+ctx = z.Context(0, curve=args.curve); ctx.set_stream(torch.cuda.current_stream())
 FLUSH = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.int64, device="cuda")
 peak = ctx.bench_int(0)
 
@@ -34,7 +35,7 @@ for log_n in args.sizes:
     for name, inv, cos, ln in (("coset_fwd", False, True, n), ("coset_inv", True, True, n), ("plain_inv", True, False, n),
                                ("coset_fwd_zero_padded_n/4+3", False, True, n // 4 + 3)):
         best, med = timeit(lambda: ctx.ntt_dev(d, log_n, inv, cos, length=ln))
-        print(json.dumps({"kernel": variant, "log_n": log_n, "what": name, "ms_best": round(best, 4), "ms_median": round(med, 4),
+        print(json.dumps({"curve": args.curve, "kernel": variant, "log_n": log_n, "what": name, "ms_best": round(best, 4), "ms_median": round(med, 4),
                           "gelem_per_s": round(n / best / 1e6, 3), "imad_frac_algorithmic": round(2 * 136 * prods / (best * 1e-3) / peak, 4)}), flush=True)
     if log_n <= 22:
         ds = [d] + [torch.roll(d, k + 1, 0).contiguous() for k in range(8)]
