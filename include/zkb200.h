@@ -157,6 +157,12 @@ ZKB_API int zkb_commit_finish_partials(zkb_ctx *ctx, uint64_t *out_xyzz);
  * (what PC::setup's FixedBaseMSM does once per SRS, plonk.rs:195). */
 ZKB_API int zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_xy[8], const uint64_t *scalars_dev, size_t n,
                               uint64_t *out_points_dev);
+/* A large single MSM runs as point ranges through ONE set of buckets: the sort phase of range k + 1 (and, for host scalars, its
+ * upload) overlaps the bucket accumulation of range k, the bucket reduction is paid once.  dev_parts / host_parts: ranges for
+ * scalars in HBM / in host memory (1 = the whole MSM at once); min_log: smallest MSM (log2 points) cut this way.
+ * Defaults 1 / 4 / 19 (measured on B200, profiles/r02am: ranges pay for host scalars, 3.24 -> 3.04 ms at 2^20, not for scalars already in
+ * HBM).  Results are identical for every setting. */
+ZKB_API int zkb_msm_set_parts(zkb_ctx *ctx, int dev_parts, int host_parts, int min_log);
 /* Force the window size c (0 = automatic cost model).  For tests and tuning. */
 ZKB_API int zkb_msm_set_window(zkb_ctx *ctx, int c);
 /* Batched-affine pair rounds in front of the XYZZ bucket accumulation (csrc/msm_pairs.cuh): each round adds

@@ -148,6 +148,13 @@ def test_msm_resident_key(cv, log_n, tables):
             exp, _ = o.msm_g1(pts[5:5 + half], sc[:half])
             got, _ = ctx.msm(to_dev(sc[:half]), offset=5, n=half)
             assert np.array_equal(got, exp)
+            if log_n == 16:                                     # the same MSM as point ranges through shared buckets
+                ctx.set_msm_parts(3, 5, 10)
+                try:
+                    assert np.array_equal(ctx.msm(to_dev(sc[:half]), offset=5, n=half)[0], exp)
+                    assert np.array_equal(ctx.msm(np.ascontiguousarray(sc[:half]), offset=5)[0], exp)
+                finally:
+                    ctx.set_msm_parts(1, 4, 19)
     finally:
         ctx.srs_precompute(-1)
 

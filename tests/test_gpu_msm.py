@@ -245,6 +245,40 @@ def test_host_scalar_msm_two_halves(ctx, tables):
     ctx.srs_precompute(-1)
 
 
+@pytest.mark.parametrize("parts", [(2, 3), (3, 7), (7, 2)])
+@pytest.mark.parametrize("tables", [False, True])
+def test_msm_as_point_ranges_through_shared_buckets(ctx, parts, tables):
+    """zkb_msm_set_parts: one MSM cut into point ranges that accumulate into ONE bucket array (sort of range k + 1 and the
+    upload of host scalars under the accumulation of range k, one reduction): device and host scalars, uniform and witness-like
+    scalars (oversized buckets: the combine kernels add to the bucket's earlier sum too), an offset into the key, sizes that do
+    not divide by the number of ranges -- against the oracle and against the undivided MSM."""
+    n, off = (1 << 13) + 5, 3
+    d_pts, h_pts = gpu_points(ctx, n + off, 91)
+    ctx.srs_load(d_pts)
+    if tables:
+        ctx.srs_precompute(0)
+    try:
+        for seed, skew in ((1, False), (2, True)):
+            s = skewed_scalars(n, 92 + seed) if skew else cref.rand_fe(cref.FR, n, 92 + seed)
+            exp, einf = cref.msm_g1(h_pts[off:], s)
+            ctx.set_msm_parts(1, 1, 19)
+            whole, winf = ctx.msm(to_dev(s), offset=off, n=n)
+            ctx.set_msm_parts(parts[0], parts[1], 8)
+            for _ in range(2):                                     # twice: the second call reuses every buffer and event
+                got, inf = ctx.msm(to_dev(s), offset=off, n=n)
+                assert inf == einf == winf and np.array_equal(got, exp) and np.array_equal(got, whole), (parts, tables, skew, "dev")
+                got, inf = ctx.msm(s, offset=off)
+                assert inf == einf and np.array_equal(got, exp), (parts, tables, skew, "host")
+            t = ctx.msm_last_timing()
+            assert t["entries"] == n * t["windows"] and t["accumulate_ms"] > 0
+        z = np.zeros((n, 4), dtype=np.uint64)
+        got, inf = ctx.msm(to_dev(z), offset=off, n=n)
+        assert inf and not got.any()
+    finally:
+        ctx.set_msm_parts(1, 4, 19)
+        ctx.srs_precompute(-1)
+
+
 @pytest.mark.parametrize("rounds", [1, 3, 6])
 def test_pair_rounds_vs_oracle(ctx, rounds):
     """zkb_msm_set_mode(rounds): batched-affine pair rounds (csrc/msm_pairs.cuh) in front of the XYZZ accumulation give the

@@ -79,6 +79,7 @@ def load(curve="bn254"):
         "zkb_g1_fixed_base_mul_dev": (i, [vp, vp, vp, sz, vp]),
         "zkb_msm_set_window": (i, [vp, i]),
         "zkb_msm_set_mode": (i, [vp, i]),
+        "zkb_msm_set_parts": (i, [vp, i, i, i]),
         "zkb_test_fp_binop": (i, [vp, i, i, vp, vp, vp, sz]),
         "zkb_z1_evals_dev": (i, [vp, u, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "zkb_z2_evals_dev": (i, [vp, u, vp, vp, vp, vp, vp, vp, vp]),

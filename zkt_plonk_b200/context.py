@@ -239,6 +239,10 @@ class Context:
         self._check(self._lib.zkb_commit_finish_partials(self._h, _host_ptr(out)))
         return out[:count]
 
+    def set_msm_parts(self, dev_parts=1, host_parts=4, min_log=19):
+        """A large single MSM as point ranges through shared buckets (zkb_msm_set_parts); 1 = the whole MSM at once."""
+        self._check(self._lib.zkb_msm_set_parts(self._h, int(dev_parts), int(host_parts), int(min_log)))
+
     def set_msm_window(self, c):
         self._check(self._lib.zkb_msm_set_window(self._h, int(c)))
 

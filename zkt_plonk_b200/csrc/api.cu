@@ -1,4 +1,5 @@
 // api.cu -- extern "C" boundary of libzkb200.so (include/zkb200.h): context, memory, host-pointer wrappers.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -146,6 +147,13 @@ int zkb_ctx_create(int device, zkb_ctx **out) {
     const char *mode = getenv("ZKB_MSM_MODE");                  // pair rounds (msm_pairs.cuh): "0".."6", or "-1" / "auto"
     if (mode && mode[0] >= '0' && mode[0] <= '6' && mode[1] == 0) ctx->msm_mode = mode[0] - '0';
     else if (mode && (!strcmp(mode, "-1") || !strcmp(mode, "auto"))) ctx->msm_mode = -1;
+    const char *mp = getenv("ZKB_MSM_PARTS");                   // "dev_parts,host_parts,min_log": see zkb_msm_set_parts
+    if (mp) {
+        int d = 0, h = 0, m = 0;
+        if (sscanf(mp, "%d,%d,%d", &d, &h, &m) == 3 && d >= 1 && d <= 7 && h >= 1 && h <= 7 && m >= 4 && m <= 31) {
+            ctx->msm_parts_dev = d; ctx->msm_parts_host = h; ctx->msm_parts_min_log = m;
+        }
+    }
     const char *pf = getenv("ZKB_MSM_PF");                      // L2 prefetch distance of the accumulation's gathers (0..16)
     if (pf && atoi(pf) >= 0 && atoi(pf) <= 16) ctx->msm_prefetch = atoi(pf);
     const char *co = getenv("ZKB_MSM_COOP");                    // "0": one thread per addition in the binary reduction levels (A/B)

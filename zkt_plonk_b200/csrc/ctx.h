@@ -40,6 +40,8 @@ struct zkb_ctx {
     int msm_force_c = 0;         // 0 = cost model picks the window size
     int msm_prefetch = 0;        // L2 prefetch distance (points) of the bucket accumulation's gathers; 0 = none (measured best)
     int msm_coop = 1;            // binary levels of the bucket reduction with four lanes per addition (0: one thread per addition)
+    int msm_parts_dev = 1, msm_parts_host = 4, msm_parts_min_log = 19;   // a large single MSM as point ranges through shared
+                                 // buckets (msm.cu msm_run_parts; zkb_msm_set_parts)
     int msm_mode = 0;            // batched-affine pair rounds in front of the XYZZ accumulation (msm_pairs.cuh): 0 = none,
                                  // 1..6 = that many, -1 = chosen per MSM from the mean bucket load
 

@@ -99,8 +99,13 @@ struct MsmState {
     MsmSlot slot[2];                     // slot 0: single MSMs; slots 0/1 alternate in pipelined batches
     cudaStream_t tail_stream = nullptr;  // high-priority stream for the latency-bound tail of a pipelined MSM
     cudaStream_t copy_stream = nullptr;  // uploads of host scalars, overlapped with the MSM of the previous part
-    cudaEvent_t part_uploaded[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase boundaries of the last MSM
+    cudaEvent_t part_uploaded[8] = {};
+    static constexpr int MAX_PARTS = 8;
+    cudaEvent_t ev[MAX_PARTS][5] = {};   // phase boundaries of the last MSM, per part (a plain MSM is one part)
+    int ev_parts = 1;                    // parts of the last MSM
+    cudaStream_t sort_stream = nullptr;  // multi-part MSMs: the sort phase of part k + 1 runs here under the accumulation of part k
+    cudaEvent_t part_sorted[MAX_PARTS] = {}, part_acc[MAX_PARTS] = {};
+    DevBuf shared_buckets;               // multi-part MSMs: the dense bucket array all parts accumulate into
     cudaEvent_t ev_pairs[2] = {nullptr, nullptr};                        // around the pair rounds of the last MSM
     uint32_t last_rounds = 0;
     bool ev_valid = false;
@@ -345,7 +350,7 @@ __global__ void __launch_bounds__(128, ACC_CTAS_PER_SM) msm_accumulate_kernel(co
                                                              const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_base,
                                                              const uint2 *__restrict__ task_order, const uint32_t *__restrict__ misc,
                                                              uint32_t SEG, g1x_t *__restrict__ task_out, g1x_t *__restrict__ bucket_val,
-                                                             uint32_t PF) {
+                                                             uint32_t PF, uint32_t accum) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= misc[1]) return;
     uint2 task = task_order[t];
@@ -353,7 +358,10 @@ __global__ void __launch_bounds__(128, ACC_CTAS_PER_SM) msm_accumulate_kernel(co
     uint32_t cnt = min(SEG, counts[b] - s * SEG);
     const uint32_t *idx = sorted + starts[b] + s * SEG;
 
+    // accum: a later part of a multi-part MSM (msm_run_parts) -- the bucket already holds the sum of the earlier parts
+    const bool single = ntasks[b] == 1;
     g1x_t acc = g1x_inf();
+    if (accum && single) acc = g1x_load(bucket_val + b);
     // Gather pipeline: register load one point ahead, add the current point.  One addition of a warp takes ~10 us with four
     // warps per scheduler, ten times an HBM access, so the load issued one iteration ahead always arrives in time; the
     // optional L2 prefetch PF points ahead (round 1's default, PF = 6) buys nothing and `prefetch.global.L2` pulls whole
@@ -377,7 +385,7 @@ __global__ void __launch_bounds__(128, ACC_CTAS_PER_SM) msm_accumulate_kernel(co
         v = vn;
         p = pn;
     }
-    g1x_store(ntasks[b] == 1 ? bucket_val + b : task_out + task_base[b] + s, acc);
+    g1x_store(single ? bucket_val + b : task_out + task_base[b] + s, acc);
 }
 
 // one warp per oversized bucket: lanes stride over the bucket's task results, shuffle tree at the end
@@ -401,7 +409,7 @@ __device__ __forceinline__ g1x_t shfl_down_g1x(const g1x_t &p, int d) {
 // per addition -- the 14 products of an XYZZ addition as 4 rounds of one product per lane -- were measured here and in the
 // binary tail of the window reduction and dropped: a lone warp is bound by its instruction issue latency, and the exchange
 // by shuffles costs what the shorter product chain saves; profiles/r02f, r02g.)
-__device__ __forceinline__ void warp_fold_store(const g1x_t *base, uint32_t len, g1x_t *dst) {
+__device__ __forceinline__ void warp_fold_store(const g1x_t *base, uint32_t len, g1x_t *dst, bool add_dst = false) {
     const uint32_t lane = threadIdx.x & 31;
     g1x_t acc = g1x_inf();
     for (uint32_t k = lane; k < len; k += 32) g1x_add(acc, g1x_load(base + k));
@@ -411,30 +419,34 @@ __device__ __forceinline__ void warp_fold_store(const g1x_t *base, uint32_t len,
         if (lane < (uint32_t)d) g1x_add(acc, o);
     }
     __syncwarp();
-    if (lane == 0) g1x_store(dst, acc);
+    if (lane == 0) {
+        if (add_dst) g1x_add(acc, g1x_load(dst));                  // multi-part MSM: the bucket's sum over the earlier parts
+        g1x_store(dst, acc);
+    }
 }
 
 __global__ void __launch_bounds__(128) msm_combine_chunks_kernel(const uint32_t *misc, const uint32_t *heavy_list, const uint32_t *heavy_slot,
                                                                  const uint2 *chunk_items, const uint32_t *ntasks, const uint32_t *task_base,
-                                                                 const g1x_t *task_out, g1x_t *chunk_out, g1x_t *bucket_val) {
+                                                                 const g1x_t *task_out, g1x_t *chunk_out, g1x_t *bucket_val, uint32_t accum) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nitems = misc[2];
     for (uint32_t it = warp; it < nitems; it += nwarps) {
         const uint2 item = chunk_items[it];
         const uint32_t b = heavy_list[item.x], nt = ntasks[b], lo = item.y * HEAVY_CHUNK, len = min(HEAVY_CHUNK, nt - lo);
         const uint32_t slot = heavy_slot[item.x];
-        warp_fold_store(task_out + task_base[b] + lo, len, slot == 0xffffffffu ? bucket_val + b : chunk_out + slot + item.y);
+        warp_fold_store(task_out + task_base[b] + lo, len, slot == 0xffffffffu ? bucket_val + b : chunk_out + slot + item.y,
+                        accum && slot == 0xffffffffu);
     }
 }
 
 __global__ void __launch_bounds__(128) msm_combine_final_kernel(const uint32_t *misc, const uint32_t *heavy_list, const uint32_t *heavy_slot,
                                                                 const uint32_t *multi_list, const uint32_t *ntasks, const g1x_t *chunk_out,
-                                                                g1x_t *bucket_val) {
+                                                                g1x_t *bucket_val, uint32_t accum) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nmulti = misc[4];
     for (uint32_t it = warp; it < nmulti; it += nwarps) {
         const uint32_t h = multi_list[it], b = heavy_list[h], chunks = (ntasks[b] + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
-        warp_fold_store(chunk_out + heavy_slot[h], chunks, bucket_val + b);
+        warp_fold_store(chunk_out + heavy_slot[h], chunks, bucket_val + b, accum != 0);
     }
 }
 
@@ -822,15 +834,24 @@ MsmState *state(zkb_ctx *ctx) {
     return (MsmState *)ctx->msm_state;
 }
 
+// One part of a multi-part MSM (msm_run_parts): the parts are point ranges of ONE MSM that share the window plan and the
+// dense bucket array; every part sorts its own entries (on the sort stream, under the previous part's accumulation) and
+// accumulates INTO the buckets; only the last part runs the window reduction.
+struct PartCtl {
+    int part, parts;
+    g1x_t *buckets;                      // the shared bucket array
+    cudaEvent_t input_ready;             // this part's scalars are in place (may be null)
+};
+
 // Enqueue the whole MSM; the G group sums end up in the slot's pinned buffer.
 // fb == nullptr: bases are d_points[0..n); else: bases are fb rows, ids offset by `offset`.
 // pipelined == false: everything on ctx->stream.  pipelined == true: sorting + accumulation on ctx->stream, the
 // latency-bound tail (window reduction, final fold, D2H) on the high-priority tail stream so that it overlaps the
 // next MSM's sort and accumulation; the caller alternates slots and waits on slot.tail_done.
 int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, size_t n, int force_c, const FixedBase *fb,
-                size_t offset, MsmPlan *plan_out, int slot_id = 0, bool pipelined = false) {
+                size_t offset, MsmPlan *plan_out, int slot_id = 0, bool pipelined = false, const PartCtl *pc = nullptr) {
     if (n >= (1ull << 31)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n must be < 2^31");
-    MsmPlan pl = make_plan(n, force_c, fb, offset, ctx->sm_count, ctx->msm_mode);
+    MsmPlan pl = make_plan(n, force_c, fb, offset, ctx->sm_count, pc ? 0 : ctx->msm_mode);     // no pair rounds inside a multi-part MSM
     if ((uint64_t)n * pl.W >= (1ull << 32)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: n * windows must be < 2^32");
     MsmWs ws;
     uint64_t max_tasks, max_heavy;
@@ -853,18 +874,38 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
         ZKB_CUDA(ctx, cudaMallocHost(&sl.pinned, out_bytes));
         sl.pinned_bytes = out_bytes;
     }
-    cudaStream_t s = ctx->stream;
+    cudaStream_t const main_stream = ctx->stream;
     const uint32_t nb = (uint32_t)pl.nbuckets, n32 = (uint32_t)n;
     const uint32_t gstride = pl.G == 1 ? 0 : pl.B;
-    if (!st->ev[0]) {
-        for (int k = 0; k < 5; ++k) ZKB_CUDA(ctx, cudaEventCreate(&st->ev[k]));
+    if (!st->ev[0][0]) {
+        for (auto &part : st->ev) for (cudaEvent_t &e : part) ZKB_CUDA(ctx, cudaEventCreate(&e));
+        for (cudaEvent_t &e : st->part_sorted) ZKB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (cudaEvent_t &e : st->part_acc) ZKB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (int k = 0; k < 2; ++k) ZKB_CUDA(ctx, cudaEventCreate(&st->ev_pairs[k]));
     }
-    st->last_entries = (uint64_t)n * pl.W; st->last_c = pl.c; st->last_W = pl.W;
-    ZKB_CUDA(ctx, cudaEventRecord(st->ev[0], s));
+    const int part = pc ? pc->part : 0;
+    const bool first_part = part == 0, last_part = !pc || part == pc->parts - 1;
+    cudaEvent_t *ev = st->ev[part];
+    if (first_part) { st->last_entries = 0; st->ev_parts = pc ? pc->parts : 1; }
+    st->last_entries += (uint64_t)n * pl.W; st->last_c = pl.c; st->last_W = pl.W;
+    // sort phase: on the sort stream for the parts of a multi-part MSM (helpers enqueue on ctx->stream: swapped for the phase)
+    cudaStream_t s = main_stream;
+    if (pc) {
+        s = st->sort_stream;
+        ws.bucket_val = pc->buckets;
+        if (pc->input_ready) ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pc->input_ready, 0));
+        if (part >= 2) ZKB_CUDA(ctx, cudaStreamWaitEvent(s, st->part_acc[part - 2], 0));   // the slot's sort buffers are free again
+        else if (first_part) {                                              // everything enqueued before this MSM comes first
+            ZKB_CUDA(ctx, cudaEventRecord(st->part_acc[MsmState::MAX_PARTS - 1], main_stream));
+            ZKB_CUDA(ctx, cudaStreamWaitEvent(s, st->part_acc[MsmState::MAX_PARTS - 1], 0));
+        }
+        ctx->stream = s;
+    }
+    struct Restore { zkb_ctx *c; cudaStream_t m; ~Restore() { c->stream = m; } } restore{ctx, main_stream};
+    ZKB_CUDA(ctx, cudaEventRecord(ev[0], s));
 
     ZKB_CUDA(ctx, cudaMemsetAsync(ws.counts, 0, ws.zero_bytes, s));           // counts, size_hist, misc
-    ZKB_CUDA(ctx, cudaMemsetAsync(ws.bucket_val, 0, (size_t)nb * sizeof(g1x_t), s));
+    if (first_part) ZKB_CUDA(ctx, cudaMemsetAsync(ws.bucket_val, 0, (size_t)nb * sizeof(g1x_t), s));
     if (n32) msm_count_kernel<<<(n32 + 255) / 256, 256, 0, s>>>(d_scalars, n32, pl.c, pl.W, pl.wide, gstride, ws.counts);
     rc = exclusive_scan(ctx, ws.counts, ws.starts, nb, ws.scan_tmp, nullptr, ws.cursor);
     if (rc) return rc;
@@ -904,16 +945,31 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
     if (rc) return rc;
     scan_sums_kernel<<<1, 256, 0, s>>>(ws.size_hist, pl.seg + 1, nullptr);   // <= SEG_MAX + 1 bins: one CTA, in place (size_cursor == size_hist)
     msm_task_scatter_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.counts, ws.ntasks, nb, pl.seg, ws.size_cursor, ws.task_order);
-    ZKB_CUDA(ctx, cudaEventRecord(st->ev[1], s));
+    if (pc) {                                                           // accumulation: back on the main stream, after this part's sort
+        ZKB_CUDA(ctx, cudaEventRecord(st->part_sorted[part], s));
+        s = main_stream;
+        ctx->stream = main_stream;
+        ZKB_CUDA(ctx, cudaStreamWaitEvent(s, st->part_sorted[part], 0));
+    }
+    const uint32_t accum = first_part ? 0u : 1u;
+    ZKB_CUDA(ctx, cudaEventRecord(ev[1], s));
     msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, s>>>(d_points, pool, ws.sorted, ws.counts, ws.starts, ws.ntasks,
                                                                              ws.task_base, ws.task_order, ws.misc, pl.seg, ws.task_out,
-                                                                             ws.bucket_val, (uint32_t)ctx->msm_prefetch);
-    ZKB_CUDA(ctx, cudaEventRecord(st->ev[2], s));
+                                                                             ws.bucket_val, (uint32_t)ctx->msm_prefetch, accum);
+    ZKB_CUDA(ctx, cudaEventRecord(ev[2], s));
     msm_combine_chunks_kernel<<<ctx->sm_count * 2, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.heavy_slot, ws.chunk_items, ws.ntasks, ws.task_base,
-                                                                ws.task_out, ws.chunk_out, ws.bucket_val);
+                                                                ws.task_out, ws.chunk_out, ws.bucket_val, accum);
     msm_combine_final_kernel<<<ctx->sm_count, 128, 0, s>>>(ws.misc, ws.heavy_list, ws.heavy_slot, ws.multi_list, ws.ntasks, ws.chunk_out,
-                                                          ws.bucket_val);
-    ZKB_CUDA(ctx, cudaEventRecord(st->ev[3], s));
+                                                          ws.bucket_val, accum);
+    ZKB_CUDA(ctx, cudaEventRecord(ev[3], s));
+    if (pc) ZKB_CUDA(ctx, cudaEventRecord(st->part_acc[part], s));
+    if (!last_part) {                                                   // the window reduction belongs to the last part
+        ZKB_CUDA(ctx, cudaEventRecord(ev[4], s));
+        ZKB_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 14;
+        *plan_out = pl;
+        return ZKB_OK;
+    }
     cudaStream_t ts = s;
     if (pipelined) {
         ts = st->tail_stream;
@@ -936,7 +992,7 @@ int msm_enqueue(zkb_ctx *ctx, const g1a_t *d_points, const uint4 *d_scalars, siz
         else msm_wsum_level_kernel<false><<<grid, RED_THREADS, 0, ts>>>(level_in, m_in, m_out, 2, l, level_out);
         level_in = level_out;
     }
-    ZKB_CUDA(ctx, cudaEventRecord(st->ev[4], ts));
+    ZKB_CUDA(ctx, cudaEventRecord(ev[4], ts));
     ZKB_CUDA(ctx, cudaGetLastError());
     st->ev_valid = true;
     ctx->launches += 14 + pl.red_levels; // 2 scans x 3 kernels + the bin scan, count, scatter, ntasks, task_scatter, accumulate, heavy x 2, reduction levels
@@ -970,10 +1026,76 @@ hec::Pt msm_fold(const MsmPlan &pl, const void *pinned) {
 }
 
 // wait for the stream, fold the group sums on the host; result in XYZZ
-int msm_finish(zkb_ctx *ctx, const MsmPlan &pl, hec::Pt *out) {
+int msm_finish(zkb_ctx *ctx, const MsmPlan &pl, hec::Pt *out, int slot_id = 0) {
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *out = msm_fold(pl, state(ctx)->slot[0].pinned);
+    *out = msm_fold(pl, state(ctx)->slot[slot_id].pinned);
     return ZKB_OK;
+}
+
+// ONE MSM over resident points [offset, offset + n) cut into `parts` point ranges that share the window plan and the bucket
+// array (PartCtl).  What it buys: the sort phase (digit extraction, counting sort, task ordering: ~0.32 ms at 2^20, bound by
+// atomics and launch latency, not by the multiplier) of part k + 1 runs on its own stream under the accumulation of part k, and
+// with host scalars the upload of part k + 1 runs under both -- while the bucket reduction, the other fixed cost of an MSM, is
+// still paid once (cutting an MSM into independent MSMs pays it per range: measured slower beyond two ranges, profiles/r02g).
+// scalars_host != nullptr: canonical scalars in host memory, uploaded range by range on the copy stream into ctx->stage.
+int msm_run_parts(zkb_ctx *ctx, const uint64_t *scalars_dev, const uint64_t *scalars_host, size_t offset, size_t n, int parts, hec::Pt *out) {
+    MsmState *st = state(ctx);
+    if (parts > MsmState::MAX_PARTS - 1) parts = MsmState::MAX_PARTS - 1;
+    const FixedBase *fb = (const FixedBase *)st->fixed_base;
+    if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;
+    const MsmPlan whole = make_plan(n, ctx->msm_force_c, fb, offset, ctx->sm_count, 0);
+    const int force_c = (int)whole.c;                               // every part uses the whole MSM's window
+    if (!st->sort_stream) {
+        int lo_prio = 0, hi_prio = 0;
+        ZKB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        ZKB_CUDA(ctx, cudaStreamCreateWithPriority(&st->sort_stream, cudaStreamNonBlocking, hi_prio));
+    }
+    if (scalars_host && !st->copy_stream) ZKB_CUDA(ctx, cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : st->part_uploaded) if (!e) ZKB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // all memory up front: nothing may be reallocated while the streams of the earlier parts are still running
+    int rc = zkb_reserve(ctx, st->shared_buckets, whole.nbuckets * sizeof(g1x_t));
+    if (rc) return rc;
+    size_t lo[MsmState::MAX_PARTS + 1];
+    // Equal ranges.  A smaller first range (less to wait for before the GPU starts) measured SLOWER for host scalars at 2^20:
+    // 3.05 ms with four quarters, 3.14 / 3.17 / 3.23 ms with a first range of 12 / 8 / 5 % (profiles/r02am, r02an): every range
+    // costs a sort of ~12 launches, and the later, larger ranges then expose more of their own sort.  ZKB_MSM_FIRST_PCT keeps
+    // the knob for other hosts.
+    static const int first_pct_env = [] { const char *e = getenv("ZKB_MSM_FIRST_PCT"); int v = e ? atoi(e) : 0; return v >= 1 && v <= 90 ? v : 0; }();
+    const int first_pct = scalars_host && parts > 1 ? first_pct_env : 0;
+    lo[0] = 0;
+    const size_t first = first_pct ? n * (size_t)first_pct / 100 : n / (size_t)parts;
+    for (int k = 1; k < parts; ++k) lo[k] = first + (n - first) * (size_t)(k - 1) / (size_t)(parts - 1);
+    lo[parts] = n;
+    for (int k = 0; k < parts; ++k) {
+        MsmWs tmp;
+        uint64_t a, b;
+        const MsmPlan pk = make_plan(lo[k + 1] - lo[k], force_c, fb, offset + lo[k], ctx->sm_count, 0);
+        rc = carve_ws(ctx, st->slot[k & 1].ws, pk, lo[k + 1] - lo[k], tmp, &a, &b);
+        if (rc) return rc;
+    }
+    const uint4 *scal = (const uint4 *)scalars_dev;
+    if (scalars_host) {
+        rc = zkb_reserve(ctx, ctx->stage, n * 32 + 32);
+        if (rc) return rc;
+        scal = (const uint4 *)ctx->stage.p;
+        // the staging buffer may still be read by work enqueued earlier on the main stream: the copies wait for it
+        ZKB_CUDA(ctx, cudaEventRecord(st->part_uploaded[7], ctx->stream));
+        ZKB_CUDA(ctx, cudaStreamWaitEvent(st->copy_stream, st->part_uploaded[7], 0));
+    }
+    MsmPlan plan;
+    for (int k = 0; k < parts; ++k) {
+        const size_t cnt = lo[k + 1] - lo[k];
+        if (scalars_host) {
+            ZKB_CUDA(ctx, cudaMemcpyAsync((char *)ctx->stage.p + lo[k] * 32, scalars_host + 4 * lo[k], cnt * 32, cudaMemcpyHostToDevice, st->copy_stream));
+            ZKB_CUDA(ctx, cudaEventRecord(st->part_uploaded[k], st->copy_stream));
+        }
+        PartCtl pc{k, parts, (g1x_t *)st->shared_buckets.p, scalars_host ? st->part_uploaded[k] : nullptr};
+        const size_t off = offset + lo[k];
+        rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, scal + 2 * lo[k], cnt, 0, fb, off, &plan, k & 1, false, &pc)
+                : msm_enqueue(ctx, (const g1a_t *)ctx->srs.p + off, scal + 2 * lo[k], cnt, force_c, nullptr, 0, &plan, k & 1, false, &pc);
+        if (rc) { cudaStreamSynchronize(st->sort_stream); cudaStreamSynchronize(ctx->stream); return rc; }
+    }
+    return msm_finish(ctx, plan, out, (parts - 1) & 1);
 }
 
 }  // namespace
@@ -990,7 +1112,11 @@ void zkb_msm_release(zkb_ctx *ctx) {
     if (st->tail_stream) cudaStreamDestroy(st->tail_stream);
     if (st->copy_stream) cudaStreamDestroy(st->copy_stream);
     for (cudaEvent_t e : st->part_uploaded) if (e) cudaEventDestroy(e);
-    for (int k = 0; k < 5; ++k) if (st->ev[k]) cudaEventDestroy(st->ev[k]);
+    for (auto &part : st->ev) for (cudaEvent_t e : part) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : st->part_sorted) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : st->part_acc) if (e) cudaEventDestroy(e);
+    if (st->sort_stream) cudaStreamDestroy(st->sort_stream);
+    if (st->shared_buckets.p) cudaFree(st->shared_buckets.p);
     for (int k = 0; k < 2; ++k) if (st->ev_pairs[k]) cudaEventDestroy(st->ev_pairs[k]);
     if (st->fixed_base) {
         FixedBase *fb = (FixedBase *)st->fixed_base;
@@ -1091,6 +1217,19 @@ int zkb_msm_set_mode(zkb_ctx *ctx, int mode) {
     return ZKB_OK;
 }
 
+// A large single MSM runs as point ranges through shared buckets (msm_run_parts): `dev_parts` ranges when the scalars are in
+// HBM, `host_parts` when they come from host memory (1 = the whole MSM at once), for MSMs of at least 2^min_log points.
+// Defaults: 1 / 4 / 19 (ZKB_MSM_PARTS="d,h,min_log" in the environment overrides them at context creation).
+int zkb_msm_set_parts(zkb_ctx *ctx, int dev_parts, int host_parts, int min_log) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (dev_parts < 1 || dev_parts > 7 || host_parts < 1 || host_parts > 7 || min_log < 4 || min_log > 31)
+        ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_set_parts: parts in 1..7, min_log in 4..31");
+    ctx->msm_parts_dev = dev_parts;
+    ctx->msm_parts_host = host_parts;
+    ctx->msm_parts_min_log = min_log;
+    return ZKB_OK;
+}
+
 int zkb_msm_set_window(zkb_ctx *ctx, int c) {
     if (!ctx || c < 0 || c > 24 || c == 1) return ZKB_ERR_INVALID;
     state(ctx);
@@ -1105,6 +1244,13 @@ int zkb_msm_g1_dev_partial(zkb_ctx *ctx, const uint64_t *scalars_dev, size_t off
     if (!scalars_dev && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm: null scalars");
     if (!state(ctx)->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "a zkb_commit_push batch is open (its scalars and results live in the buffers this call would reuse): call zkb_commit_finish first");
     MsmPlan pl;
+    if (n >= ((size_t)1 << ctx->msm_parts_min_log) && ctx->msm_parts_dev > 1 && ctx->msm_mode == 0) {   // large: point ranges through shared buckets
+        hec::Pt total;
+        int rc = msm_run_parts(ctx, scalars_dev, nullptr, offset, n, ctx->msm_parts_dev, &total);
+        if (rc) return rc;
+        memcpy(out_xyzz, &total, XYZZ_BYTES);
+        return ZKB_OK;
+    }
     const FixedBase *fb = (const FixedBase *)state(ctx)->fixed_base;
     if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;      // forced window: plain path
     int rc = fb ? msm_enqueue(ctx, (const g1a_t *)fb->rows.p, (const uint4 *)scalars_dev, n, 0, fb, offset, &pl)
@@ -1153,14 +1299,20 @@ static int msm_host_partial(zkb_ctx *ctx, const uint64_t *scalars_host, size_t o
     int rc = zkb_reserve(ctx, ctx->stage, n * 32 + 32);
     if (rc) return rc;
     MsmState *st = state(ctx);
-    if (n < ((size_t)1 << 18)) {
+    if (n < ((size_t)1 << (ctx->msm_parts_min_log > 18 ? 18 : ctx->msm_parts_min_log))) {
         ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
         return zkb_msm_g1_dev_partial(ctx, (const uint64_t *)ctx->stage.p, offset, n, out_xyzz);
     }
-    if (!st->copy_stream) {
-        ZKB_CUDA(ctx, cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
-        for (cudaEvent_t &e : st->part_uploaded) ZKB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (ctx->msm_parts_host > 1 && ctx->msm_mode == 0) {           // ranges through shared buckets, uploads under the earlier ranges' work
+        hec::Pt total;
+        rc = msm_run_parts(ctx, nullptr, scalars_host, offset, n, ctx->msm_parts_host, &total);
+        if (rc) return rc;
+        memcpy(out_xyzz, &total, XYZZ_BYTES);
+        return ZKB_OK;
     }
+    // zkb_msm_set_parts(ctx, d, 1, ..): the earlier scheme -- two independent MSMs over two ranges (each with its own buckets and reduction)
+    if (!st->copy_stream) ZKB_CUDA(ctx, cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : st->part_uploaded) if (!e) ZKB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const FixedBase *fb = (const FixedBase *)st->fixed_base;
     if (fb && (ctx->msm_force_c > 0 || fb->n != ctx->srs_n)) fb = nullptr;
     // the staging buffer may still be read by work enqueued earlier on the main stream: the copies wait for it
@@ -1289,9 +1441,19 @@ int zkb_msm_last_timing(zkb_ctx *ctx, float out_ms[5], uint64_t info[3]) {
     if (!ctx || !out_ms) return ZKB_ERR_INVALID;
     MsmState *st = state(ctx);
     if (!st->ev_valid) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_last_timing: no MSM has run on this context");
-    ZKB_CUDA(ctx, cudaEventSynchronize(st->ev[4]));
-    for (int k = 0; k < 4; ++k) ZKB_CUDA(ctx, cudaEventElapsedTime(&out_ms[k], st->ev[k], st->ev[k + 1]));
-    ZKB_CUDA(ctx, cudaEventElapsedTime(&out_ms[4], st->ev[0], st->ev[4]));
+    // a multi-part MSM: the phases summed over the parts (their sort phases overlap the previous part's accumulation, so the
+    // sum of the phases can exceed the total); the total runs from the first part's start to the end of the reduction
+    const int P = st->ev_parts;
+    ZKB_CUDA(ctx, cudaEventSynchronize(st->ev[P - 1][4]));
+    for (int k = 0; k < 4; ++k) out_ms[k] = 0.f;
+    for (int p = 0; p < P; ++p)
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            if (k == 3 && p != P - 1) continue;
+            ZKB_CUDA(ctx, cudaEventElapsedTime(&ms, st->ev[p][k], st->ev[p][k + 1]));
+            out_ms[k] += ms;
+        }
+    ZKB_CUDA(ctx, cudaEventElapsedTime(&out_ms[4], st->ev[0][0], st->ev[P - 1][4]));
     if (info) { info[0] = st->last_entries; info[1] = st->last_c; info[2] = st->last_W; }
     return ZKB_OK;
 }
