@@ -14,9 +14,14 @@ import numpy as np
 
 from oracle import cref, pairing, pyref
 from zkt_plonk_b200 import field
-from zkt_plonk_b200.prover import (P, Poly, Proof, fr_to_limbs, ints_to_mont_array, limbs_to_fr, mont_array_to_ints,
+from zkt_plonk_b200.prover import (Poly, Proof, fr_to_limbs, ints_to_mont_array, limbs_to_fr, mont_array_to_ints,
                                     point_to_ints)
 from zkt_plonk_b200.transcript import TRANSCRIPTS
+
+def _o():
+    """the C oracle of the curve the Python mirror currently works on (field.use_curve)"""
+    return cref.oracle(field.CURVE)
+
 
 EPK_ORDER = ("q_m", "q_l", "q_r", "q_o", "q_c", "q_lookup", "q_table", "sigma1", "sigma2", "sigma3", "l1")
 WIT_ORDER = ("z1", "z2", "a", "b", "c", "pi", "t", "h1", "h2")
@@ -51,7 +56,7 @@ class OracleBackend:
     def ifft(self, evals, log_n, cap):
         n = 1 << log_n
         out = np.zeros((cap, 4), dtype=np.uint64)
-        out[:n] = cref.ntt(np.ascontiguousarray(evals[:n]), log_n, True)
+        out[:n] = _o().ntt(np.ascontiguousarray(evals[:n]), log_n, True)
         return out
 
     def effective_len(self, buf, n):
@@ -62,51 +67,51 @@ class OracleBackend:
         for i, b in enumerate(blinders):
             poly.data[poly.len + i] = fr_to_limbs(b)
         for i, b in enumerate(blinders):        # prove.rs:472-483: extend first, then coeffs[i] -= b_i for EVERY i < k
-            poly.data[i] = fr_to_limbs((limbs_to_fr(poly.data[i]) - b) % P)
+            poly.data[i] = fr_to_limbs((limbs_to_fr(poly.data[i]) - b) % field.R_MOD)
         poly.len += len(blinders)
 
     def commit(self, poly):
         if poly.len == 0:
             return None
-        sc = cref.from_mont(cref.FR, np.ascontiguousarray(poly.data[: poly.len]))
-        xy, inf = cref.msm_g1(self.srs[: poly.len], sc)
+        sc = _o().from_mont(cref.FR, np.ascontiguousarray(poly.data[: poly.len]))
+        xy, inf = _o().msm_g1(self.srs[: poly.len], sc)
         return point_to_ints(xy, inf)
 
     # -- argument math
     def z1_poly(self, log_n, beta, gamma, a, b, c, s1, s2, s3, cap):
         n = 1 << log_n
-        ev = cref.z1_evals(log_n, fr_to_limbs(beta), fr_to_limbs(gamma), *[np.ascontiguousarray(x[:n]) for x in (a, b, c, s1, s2, s3)])
+        ev = _o().z1_evals(log_n, fr_to_limbs(beta), fr_to_limbs(gamma), *[np.ascontiguousarray(x[:n]) for x in (a, b, c, s1, s2, s3)])
         return self.ifft(ev, log_n, cap)
 
     def z2_poly(self, log_n, delta, eps, f, t, h1, h2, cap):
         n = 1 << log_n
-        ev = cref.z2_evals(log_n, fr_to_limbs(delta), fr_to_limbs(eps), *[np.ascontiguousarray(x[:n]) for x in (f, t, h1, h2)])
+        ev = _o().z2_evals(log_n, fr_to_limbs(delta), fr_to_limbs(eps), *[np.ascontiguousarray(x[:n]) for x in (f, t, h1, h2)])
         return self.ifft(ev, log_n, cap)
 
     def _coset4(self, poly, log_n):
         buf = np.zeros((4 << log_n, 4), dtype=np.uint64)
         buf[: poly.len] = poly.data[: poly.len]
-        return cref.ntt(buf, log_n + 2, False, True)
+        return _o().ntt(buf, log_n + 2, False, True)
 
     def extend_prover_key(self, log_n, polys):
         epk = {name: self._coset4(polys[name], log_n) for name in EPK_ORDER[:-1]}
-        epk["x"], epk["zh"], epk["l1"] = cref.epk_free_tables(log_n)
+        epk["x"], epk["zh"], epk["l1"] = _o().epk_free_tables(log_n)
         return epk
 
     def quotient(self, log_n, epk, ch, polys):
         wit = {name: self._coset4(polys[name], log_n) for name in WIT_ORDER}
         chal = np.stack([fr_to_limbs(x) for x in ch])
-        ev = cref.quotient_evals(log_n, chal, wit, epk)
-        return cref.ntt(ev, log_n + 2, True, True)
+        ev = _o().quotient_evals(log_n, chal, wit, epk)
+        return _o().ntt(ev, log_n + 2, True, True)
 
     def evaluate(self, poly, z):
-        return limbs_to_fr(cref.poly_eval(poly.data[: poly.len], fr_to_limbs(z))) if poly.len else 0
+        return limbs_to_fr(_o().poly_eval(poly.data[: poly.len], fr_to_limbs(z))) if poly.len else 0
 
     def lincomb(self, polys, scalars, cap=None):
         m = max(p.len for p in polys)
-        sc = np.stack([fr_to_limbs(x % P) for x in scalars])
+        sc = np.stack([fr_to_limbs(x % field.R_MOD) for x in scalars])
         buf = np.zeros((cap or m, 4), dtype=np.uint64)
-        buf[:m] = cref.poly_lincomb([p.data[: p.len] for p in polys], sc, m)
+        buf[:m] = _o().poly_lincomb([p.data[: p.len] for p in polys], sc, m)
         return Poly(buf, m)
 
     def divide_linear(self, poly, z):
@@ -114,7 +119,7 @@ class OracleBackend:
         buf = np.zeros((max(m - 1, 1), 4), dtype=np.uint64)
         if m == 0:
             return Poly(buf, 0), 0
-        quot, ev = cref.poly_divide_linear(poly.data[:m], fr_to_limbs(z))
+        quot, ev = _o().poly_divide_linear(poly.data[:m], fr_to_limbs(z))
         if m > 1:
             buf[: m - 1] = quot
         return Poly(buf, m - 1), limbs_to_fr(ev)
@@ -128,7 +133,7 @@ class PythonIntPolyOps:
     def evaluate(coeffs, z):
         acc = 0
         for cf in reversed(coeffs):
-            acc = (acc * z + cf) % P
+            acc = (acc * z + cf) % field.R_MOD
         return acc
 
     @staticmethod
@@ -137,7 +142,7 @@ class PythonIntPolyOps:
         acc = [0] * m
         for p, s in zip(polys, scalars):
             for k, cf in enumerate(p):
-                acc[k] = (acc[k] + s * cf) % P
+                acc[k] = (acc[k] + s * cf) % field.R_MOD
         return acc
 
     @staticmethod
@@ -145,36 +150,37 @@ class PythonIntPolyOps:
         m = len(cf)
         w, carry = [0] * max(m - 1, 0), 0
         for k in range(m - 1, 0, -1):
-            carry = (cf[k] + z * carry) % P
+            carry = (cf[k] + z * carry) % field.R_MOD
             w[k - 1] = carry
-        return w, ((cf[0] if m else 0) + z * carry) % P
+        return w, ((cf[0] if m else 0) + z * carry) % field.R_MOD
 
 
 # ------------------------------------------------------------------------------------------------ verifier
 def _lagrange(n, point, zh_eval, tau):
     """util.rs:185-195 compute_lagrange_evaluation(n, point, zh_eval, tau)."""
-    return zh_eval * point % P * pow(n * (tau - point) % P, -1, P) % P
+    return zh_eval * point % field.R_MOD * pow(n * (tau - point) % field.R_MOD, -1, field.R_MOD) % field.R_MOD
 
 
 def _lin_comb_points(points, scalars):
     acc = None
     for pt, s in zip(points, scalars):
-        acc = pyref.g1_add(acc, pyref.g1_mul(s % P, pt) if pt is not None else None)
+        acc = pyref.g1_add(acc, pyref.g1_mul(s % field.R_MOD, pt) if pt is not None else None)
     return acc
 
 
 def make_cvk(tau):
+    assert field.CURVE == "bn254", "the restated pairing (oracle/pairing.py) is BN254's; other curves verify through the trapdoor"
     """The G2 half of sonic_pc::VerifierKey for a synthetic SRS: (h, beta_h) = (H, tau * H), H the alt_bn128 G2 generator
     (KZG10::setup draws h at random; any h gives the same accept / reject decisions)."""
-    return (pairing.G2_GEN, pairing.g2_mul(tau % P, pairing.G2_GEN))
+    return (pairing.G2_GEN, pairing.g2_mul(tau % field.R_MOD, pairing.G2_GEN))
 
 
 def _kzg_check(commits, point, values, w, eta, tau, cvk=None):
     """SonicKZG10::check for one query point: A = sum eta^i C_i - (sum eta^i v_i) G + z W, then
     e(A, h) * e(-W, beta_h) == 1 (cvk given) or, with the trapdoor in place of the pairing, tau * W == A."""
-    chal = [pow(eta, i, P) for i in range(len(commits))]
+    chal = [pow(eta, i, field.R_MOD) for i in range(len(commits))]
     c = _lin_comb_points(commits, chal)
-    v = sum(e * x for e, x in zip(chal, values)) % P
+    v = sum(e * x for e, x in zip(chal, values)) % field.R_MOD
     rhs = pyref.g1_add(pyref.g1_add(c, pyref.g1_neg(pyref.g1_mul(v, pyref.G1_GEN))), pyref.g1_mul(point, w) if w else None)
     if cvk is not None:
         return pairing.pairing_product_is_one([(rhs, cvk[0]), (pyref.g1_neg(w) if w else None, cvk[1])])
@@ -205,31 +211,31 @@ def verify(vk, proof, pub_inputs, tau=None, transcript="merlin", cvk=None):
     for k in ("q_lo", "q_mid", "q_hi"):
         tr.append_commitment(k + "_commit", C[k])
     xi = tr.challenge_scalar("xi")
-    zh = (pow(xi, n, P) - 1) % P
+    zh = (pow(xi, n, field.R_MOD) - 1) % field.R_MOD
     l1 = _lagrange(n, 1, zh, xi)
-    al2 = alpha * alpha % P
-    opd = (1 + delta) % P
-    eopd = epsilon * opd % P
+    al2 = alpha * alpha % field.R_MOD
+    opd = (1 + delta) % field.R_MOD
+    eopd = epsilon * opd % field.R_MOD
     # compute_r0 (proof.rs:163-217)
-    part1 = (-sum(_lagrange(n, pt, zh, xi) * pi for pi, pt in zip(pub_inputs, vk.pi_roots))) % P
-    part2 = alpha * E["z1_next"] % P * (E["a"] + beta * E["sigma1"] + gamma) % P * (E["b"] + beta * E["sigma2"] + gamma) % P * (E["c"] + gamma) % P
-    part3 = l1 * al2 % P
-    part4 = al2 * alpha % P * E["z2_next"] % P * (eopd + delta * E["h2"]) % P * (eopd + E["h2"] + delta * E["h1_next"]) % P
-    part5 = l1 * al2 % P * al2 % P
-    r0 = (part1 + part2 + part3 + part4 + part5) % P
+    part1 = (-sum(_lagrange(n, pt, zh, xi) * pi for pi, pt in zip(pub_inputs, vk.pi_roots))) % field.R_MOD
+    part2 = alpha * E["z1_next"] % field.R_MOD * (E["a"] + beta * E["sigma1"] + gamma) % field.R_MOD * (E["b"] + beta * E["sigma2"] + gamma) % field.R_MOD * (E["c"] + gamma) % field.R_MOD
+    part3 = l1 * al2 % field.R_MOD
+    part4 = al2 * alpha % field.R_MOD * E["z2_next"] % field.R_MOD * (eopd + delta * E["h2"]) % field.R_MOD * (eopd + E["h2"] + delta * E["h1_next"]) % field.R_MOD
+    part5 = l1 * al2 % field.R_MOD * al2 % field.R_MOD
+    r0 = (part1 + part2 + part3 + part4 + part5) % field.R_MOD
     # compute_linearization_commitment (proof.rs:220-282 with keys/*::compute_linearization_commitment)
     V = vk.commits
-    bz = beta * xi % P
-    al3, al4, al5 = al2 * alpha % P, al2 * al2 % P, al2 * al2 % P * alpha % P
-    scalars = [E["a"] * E["b"] % P, E["a"], E["b"], E["c"], 1,
-               (alpha * (bz + E["a"] + gamma) % P * (bz * field.K1 + E["b"] + gamma) % P * (bz * field.K2 + E["c"] + gamma) + l1 * al2) % P,
-               (-alpha * beta % P * E["z1_next"] % P * (beta * E["sigma1"] + E["a"] + gamma) % P * (beta * E["sigma2"] + E["b"] + gamma)) % P,
-               (al3 * opd % P * (epsilon + E["q_lookup"] * E["c"]) % P * (eopd + E["t"] + delta * E["t_next"]) + al4 * l1) % P,
-               (-al3 * E["z2_next"] % P * (eopd + E["h2"] + delta * E["h1_next"])) % P,
-               al5 * E["t"] % P]
+    bz = beta * xi % field.R_MOD
+    al3, al4, al5 = al2 * alpha % field.R_MOD, al2 * al2 % field.R_MOD, al2 * al2 % field.R_MOD * alpha % field.R_MOD
+    scalars = [E["a"] * E["b"] % field.R_MOD, E["a"], E["b"], E["c"], 1,
+               (alpha * (bz + E["a"] + gamma) % field.R_MOD * (bz * field.K1 + E["b"] + gamma) % field.R_MOD * (bz * field.K2 + E["c"] + gamma) + l1 * al2) % field.R_MOD,
+               (-alpha * beta % field.R_MOD * E["z1_next"] % field.R_MOD * (beta * E["sigma1"] + E["a"] + gamma) % field.R_MOD * (beta * E["sigma2"] + E["b"] + gamma)) % field.R_MOD,
+               (al3 * opd % field.R_MOD * (epsilon + E["q_lookup"] * E["c"]) % field.R_MOD * (eopd + E["t"] + delta * E["t_next"]) + al4 * l1) % field.R_MOD,
+               (-al3 * E["z2_next"] % field.R_MOD * (eopd + E["h2"] + delta * E["h1_next"])) % field.R_MOD,
+               al5 * E["t"] % field.R_MOD]
     points = [V["q_m"], V["q_l"], V["q_r"], V["q_o"], V["q_c"], C["z1"], V["sigma3"], C["z2"], C["h1"], V["q_table"]]
-    xn2 = (zh + 1) * xi % P * xi % P
-    scalars += [(-zh) % P, (-zh * xn2) % P, (-zh * xn2 % P * xn2) % P]
+    xn2 = (zh + 1) * xi % field.R_MOD * xi % field.R_MOD
+    scalars += [(-zh) % field.R_MOD, (-zh * xn2) % field.R_MOD, (-zh * xn2 % field.R_MOD * xn2) % field.R_MOD]
     points += [C["q_lo"], C["q_mid"], C["q_hi"]]
     r_commit = _lin_comb_points(points, scalars)
     for k in Proof.EVALS:
@@ -240,16 +246,17 @@ def verify(vk, proof, pub_inputs, tau=None, transcript="merlin", cvk=None):
     if not ok1:
         return 1
     w_n = field.root_of_unity(log_n)
-    ok2 = _kzg_check([C["z1"], C["z2"], C["t"], C["h1"]], xi * w_n % P,
+    ok2 = _kzg_check([C["z1"], C["z2"], C["t"], C["h1"]], xi * w_n % field.R_MOD,
                      [E["z1_next"], E["z2_next"], E["t_next"], E["h1_next"]], proof.saw, eta, tau, cvk)
     return 0 if ok2 else 2
 
 
 def make_srs_host(n_points, tau):
-    """[tau^i] G for i < n_points, Montgomery affine (n_points, 8) -- small sizes only (double-and-add per point)."""
-    G = cref.to_mont(cref.FQ, cref.ints_to_limbs([1, 2])).reshape(8)
+    """[tau^i] G for i < n_points, Montgomery affine (n_points, 2 * FQ_WORDS) -- small sizes only (double-and-add per point)."""
+    w = field.FQ_WORDS
+    G = _o().to_mont(cref.FQ, np.array([field.int_to_limbs(v, w) for v in field.G1_GENERATOR], dtype=np.uint64)).reshape(2 * w)
     powers, x = [], 1
     for _ in range(n_points):
         powers.append(x)
-        x = x * tau % P
-    return cref.g1_mul(G, cref.ints_to_limbs(powers))
+        x = x * tau % field.R_MOD
+    return _o().g1_mul(G, cref.ints_to_limbs(powers))

@@ -20,17 +20,33 @@ Call sites restated (reference file:line):
     keys/arithmetic.rs:67-81, keys/permutation.rs:97-137, keys/lookup.rs:81-122
 """
 
-# ---------------------------------------------------------------- BN254 constants (ark-bn254 0.3)
-R_MOD = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001  # Fr
-Q_MOD = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47  # Fq
-TWO_ADICITY = 28
-FR_GENERATOR = 5  # Fr::multiplicative_generator()
-TWO_ADIC_ROOT = pow(FR_GENERATOR, (R_MOD - 1) >> TWO_ADICITY, R_MOD)
-CURVE_B = 3
-G1_GEN = (1, 2)
+# ---------------------------------------------------------------- curve constants (ark-bn254 / ark-bls12-381 / ark-bls12-377 0.3)
+# BN254 unless use_curve selects another; the definitions below read these globals at call time.
+_CURVES = {
+    "bn254": (0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001,
+              0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47, 28, 5, 3, (1, 2)),
+    "bls12_381": (0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001,
+                  0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab, 32, 7, 4,
+                  (0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb,
+                   0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1)),
+    "bls12_377": (0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001,
+                  0x01ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001, 47, 22, 1,
+                  (0x008848defe740a67c8fc6225bf87ff5485951e2caa9d41bb188282c8bd37cb5cd5481512ffcd394eeab9b16eb21be9ef,
+                   0x01914a69c5102eff1f674f5d30afeec4bd7fb348ca3e52d96d182ad44fb82305c2fe3d3634a9591afd82de55559c8ea6)),
+}
 K1 = 7   # plonk-core/src/permutation/constants.rs:13-15
 K2 = 13  # plonk-core/src/permutation/constants.rs:18-20
-MONT_R = 1 << 256
+MONT_R = 1 << 256   # Fr (and BN254's Fq): four 64-bit limbs
+
+
+def use_curve(name):
+    global CURVE, R_MOD, Q_MOD, TWO_ADICITY, FR_GENERATOR, TWO_ADIC_ROOT, CURVE_B, G1_GEN
+    CURVE = name
+    R_MOD, Q_MOD, TWO_ADICITY, FR_GENERATOR, CURVE_B, G1_GEN = _CURVES[name]   # FR_GENERATOR: Fr::multiplicative_generator()
+    TWO_ADIC_ROOT = pow(FR_GENERATOR, (R_MOD - 1) >> TWO_ADICITY, R_MOD)
+
+
+use_curve("bn254")
 
 
 def to_mont(x, p):
@@ -47,7 +63,7 @@ def inv(x, p):
 
 # ---------------------------------------------------------------- domain
 def root_of_unity(log_n):
-    """Radix2EvaluationDomain::new: group_gen = TWO_ADIC_ROOT squared (28 - log_n) times."""
+    """Radix2EvaluationDomain::new: group_gen = TWO_ADIC_ROOT squared (TWO_ADICITY - log_n) times."""
     assert 0 <= log_n <= TWO_ADICITY
     w = TWO_ADIC_ROOT
     for _ in range(log_n, TWO_ADICITY):

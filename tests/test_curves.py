@@ -152,3 +152,57 @@ def test_every_build_exports_the_whole_abi(curve):
         n = ctypes.c_size_t(0)
         assert lib.zkb_ck_file_info(b"/nonexistent", ctypes.byref(n), ctypes.byref(n)) == _lib.ZKB_ERR_UNSUPPORTED
         assert lib.zkb_plonk_verify(0, None, 0, None, None, None, None, None, None, 0) == _lib.ZKB_ERR_UNSUPPORTED
+
+
+# ------------------------------------------------------------------------------------------------ the whole protocol on BLS12
+@pytest.fixture
+def on_curve(request):
+    """run a test with the Python mirror (field / pyref) switched to a curve, BN254 again afterwards"""
+    from oracle import pyref
+    from zkt_plonk_b200 import field
+    field.use_curve(request.param)
+    pyref.use_curve(request.param)
+    yield request.param
+    field.use_curve("bn254")
+    pyref.use_curve("bn254")
+
+
+@pytest.mark.parametrize("on_curve", BLS, indirect=True)
+def test_prove_verify_roundtrip_on_oracle_backend(on_curve):
+    """The reference's own acceptance test on these curves (plonk.rs:226-254 test_full on Bls12_381 / Bls12_377): the round
+    schedule (zkt_plonk_b200.prover) over the per-curve oracle gives a proof of 11 * 48 + 2 * 49 + 12 * 32 = 1010 bytes that the
+    restated verifier accepts (PC::check through the synthetic SRS's trapdoor: the restated pairing is BN254's), that parses back
+    to itself, and tampered proofs are rejected."""
+    from oracle import plonk_ref
+    from zkt_plonk_b200 import field, prover, synthetic
+    P = field.R_MOD
+    tau = 0x1D9E5F1B2C3A49587766554433221100FFEEDDCCBBAA99887766554433221101 % P
+    circ = synthetic.make_circuit(5, seed=5, table_size=4)
+    assert synthetic.check_gates(circ)
+    srs = plonk_ref.make_srs_host(circ.n + 8, tau)
+    assert srs.shape == (circ.n + 8, 12)
+    be = plonk_ref.OracleBackend(srs)
+    pk, vk = prover.setup(be, circ)
+    rnd = random.Random(7)
+    blinders = [rnd.randrange(P) for _ in range(19)]
+    proof = prover.prove(be, pk, vk, circ, blinders)
+    raw = proof.to_bytes()
+    assert len(raw) == 11 * 48 + 2 * 49 + 12 * 32
+    pub = list(circ.pi.values())
+    assert plonk_ref.verify(vk, proof, pub, tau) == 0
+    assert plonk_ref.verify(vk, proof, pub, tau + 1) == 1
+    back = prover.proof_from_bytes(raw)
+    assert back.to_bytes() == raw and back.commits == proof.commits and back.aw == proof.aw and back.evals == proof.evals
+    assert prover.prove(be, pk, vk, circ, blinders).to_bytes() == raw
+    bad = prover.Proof(dict(proof.commits), proof.aw, proof.saw, dict(proof.evals))
+    bad.evals["a"] = (bad.evals["a"] + 1) % P
+    assert plonk_ref.verify(vk, bad, pub, tau) != 0
+    assert plonk_ref.verify(vk, proof, [(pub[0] + 1) % P] + pub[1:], tau) != 0
+    bad = prover.Proof(dict(proof.commits), proof.aw, proof.saw, dict(proof.evals))
+    bad.commits["z1"] = proof.commits["z2"]
+    assert plonk_ref.verify(vk, bad, pub, tau) != 0
+    bad = prover.Proof(dict(proof.commits), proof.aw, proof.saw, dict(proof.evals))
+    bad.evals["h1_next"] = (bad.evals["h1_next"] + 1) % P                  # an evaluation of the second opening
+    assert plonk_ref.verify(vk, bad, pub, tau) != 0
+    bad = prover.Proof(dict(proof.commits), proof.aw, proof.aw, dict(proof.evals))   # the second witness replaced
+    assert plonk_ref.verify(vk, bad, pub, tau) == 2

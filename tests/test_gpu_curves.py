@@ -253,3 +253,56 @@ def test_protocol_driver_is_reported_unsupported(cv):
     out = ctypes.c_void_p()
     assert lib.zkb_plonk_setup(ctx._h, 4, None, None, 0, None, 0, ctypes.byref(out)) == -6
     assert lib.zkb_plonk_verify(0, None, 0, None, None, None, None, None, None, 0) == -6
+
+
+# ------------------------------------------------------------------------------------------------ whole proofs on the BLS12 curves
+@pytest.mark.parametrize("log_n,fixed_base", [(5, False), (10, True), (14, True)])
+def test_gpu_proof_is_byte_identical_and_verifies(cv, log_n, fixed_base):
+    """plonk.rs:226-254 (test_full on Bls12_381 / Bls12_377): the five-round schedule (zkt_plonk_b200.prover) over this curve's
+    build of the library against the same schedule over the per-curve CPU oracle -- same circuit, witness, SRS and blinders:
+    identical verifier keys, byte-identical 1010-byte proofs, accepted by the restated verifier (PC::check through the synthetic
+    SRS's trapdoor).  At 2^14 the CPU prover is skipped: the GPU proof is verified only."""
+    import random
+    import torch
+    import zkt_plonk_b200 as z
+    from oracle import plonk_ref, pyref
+    from zkt_plonk_b200 import field, prover, synthetic
+    ctx, o, c = cv
+    field.use_curve(ctx.curve)
+    pyref.use_curve(ctx.curve)
+    try:
+        P = field.R_MOD
+        tau = 0x2B7E151628AED2A6ABF7158809CF4F3C762E7160F38B4DA56A784D9045190CFE % P
+        circ = synthetic.make_circuit(log_n, seed=40 + log_n, table_size=min(64, (1 << log_n) // 4))
+        assert synthetic.check_gates(circ)
+        powers, x = [], 1
+        for _ in range(circ.n + 8):
+            powers.append(x)
+            x = x * tau % P
+        d_srs = torch.empty((circ.n + 8, ctx.aff_words), dtype=torch.int64, device="cuda")
+        ctx.g1_fixed_base_mul_dev(ctx.g1_generator(), to_dev(limbs(powers, 4)), circ.n + 8, d_srs)
+        torch.cuda.synchronize()
+        kzg = z.GpuKZG10(ctx)
+        kzg.load_committer_key(d_srs)
+        if fixed_base:
+            ctx.srs_precompute(0)
+        gbe = prover.GpuBackend(kzg)
+        rnd = random.Random(99)
+        blinders = [rnd.randrange(P) for _ in range(19)]
+        gpk, gvk = prover.setup(gbe, circ)
+        gproof = prover.prove(gbe, gpk, gvk, circ, blinders)
+        raw = gproof.to_bytes()
+        assert len(raw) == 1010
+        pub = list(circ.pi.values())
+        assert plonk_ref.verify(gvk, gproof, pub, tau) == 0
+        assert plonk_ref.verify(gvk, prover.proof_from_bytes(raw), pub, tau) == 0
+        assert plonk_ref.verify(gvk, gproof, [(pub[0] + 1) % P] + pub[1:], tau) != 0
+        if log_n <= 10:
+            obe = plonk_ref.OracleBackend(to_host(d_srs))
+            opk, ovk = prover.setup(obe, circ)
+            assert gvk.commits == ovk.commits and gvk.pi_roots == ovk.pi_roots
+            assert prover.prove(obe, opk, ovk, circ, blinders).to_bytes() == raw
+    finally:
+        ctx.srs_precompute(-1)
+        field.use_curve("bn254")
+        pyref.use_curve("bn254")

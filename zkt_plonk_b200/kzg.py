@@ -42,7 +42,7 @@ class GpuKZG10:
         if hi > self.ctx.srs_size():
             raise PCError(f"TooManyCoefficients: {hi} > {self.ctx.srs_size()}")
         if hi == lo:
-            return np.zeros(8, dtype=np.uint64), True
+            return np.zeros(self.ctx.aff_words, dtype=np.uint64), True
         import torch
         d = torch.from_numpy(np.ascontiguousarray(coeffs_mont[lo:hi]).view(np.int64)).to(f"cuda:{self.ctx.device}")
         return self.ctx.commit_dev(d, lo, hi - lo)
@@ -66,6 +66,6 @@ class GpuKZG10:
 
     def multi_scalar_mul(self, commitments, scalars_canonical):
         """HomomorphicCommitment::multi_scalar_mul (commitment.rs:31-46): sum_i scalars[i] * commitments[i]."""
-        pts = np.ascontiguousarray(commitments, dtype=np.uint64).reshape(-1, 8)
+        pts = np.ascontiguousarray(commitments, dtype=np.uint64).reshape(-1, self.ctx.aff_words)
         sc = np.ascontiguousarray(scalars_canonical, dtype=np.uint64).reshape(-1, 4)
         return self.ctx.msm_bases(pts, sc)

@@ -16,10 +16,17 @@ import numpy as np
 from . import field
 from .transcript import TRANSCRIPTS, MerlinTranscript, fr_bytes
 
-P = field.R_MOD
-Q = field.Q_MOD
-_RINV_R = pow(field.MONT_R, -1, P)
-_RINV_Q = pow(field.MONT_R, -1, Q)
+# The moduli and encodings are the selected curve's (field.use_curve / field.curve): BN254 by default; BLS12-381 / BLS12-377
+# (what plonk.rs:226-254 instantiates) through this Python round schedule -- the C++ driver behind NativeProver is BN254-only.
+
+
+def __getattr__(name):
+    """`prover.P` / `prover.Q`: r and q of the selected curve (BN254's unless field.use_curve chose another)."""
+    if name == "P":
+        return field.R_MOD
+    if name == "Q":
+        return field.Q_MOD
+    raise AttributeError(name)
 
 
 # ------------------------------------------------------------------------------------------------ conversions
@@ -29,12 +36,12 @@ def fr_to_limbs(x):
 
 
 def limbs_to_fr(l):
-    return field.limbs_to_int(l) * _RINV_R % P
+    return field.limbs_to_int(l) * field.RINV_R % field.R_MOD
 
 
 def ints_to_mont_array(vals):
     """list/array of canonical ints -> (n, 4) uint64 Montgomery limbs (vectorised over Python ints)."""
-    v = np.array([int(x) * field.MONT_R % P for x in vals], dtype=object)
+    v = np.array([int(x) * field.MONT_R % field.R_MOD for x in vals], dtype=object)
     out = np.empty((len(v), 4), dtype=np.uint64)
     m = (1 << 64) - 1
     for k in range(4):
@@ -47,27 +54,29 @@ def mont_array_to_ints(a):
     v = a[:, 0].astype(object)
     for k in range(1, 4):
         v = v + (a[:, k].astype(object) << (64 * k))
-    return [int(x) * _RINV_R % P for x in v]
+    return [int(x) * field.RINV_R % field.R_MOD for x in v]
 
 
 def point_to_ints(xy, is_inf):
-    """(8,) uint64 Montgomery affine -> (x, y) canonical ints, or None for the identity."""
+    """(2 * FQ_WORDS,) uint64 Montgomery affine -> (x, y) canonical ints, or None for the identity."""
     if is_inf:
         return None
-    return (field.limbs_to_int(xy[:4]) * _RINV_Q % Q, field.limbs_to_int(xy[4:]) * _RINV_Q % Q)
+    w = field.FQ_WORDS
+    return (field.limbs_to_int(xy[:w]) * field.RINV_Q % field.Q_MOD, field.limbs_to_int(xy[w:2 * w]) * field.RINV_Q % field.Q_MOD)
 
 
 def g1_compressed(pt):
-    """GroupAffine::serialize (ark-ec 0.3 / ark-serialize 0.3 SWFlags): x little endian with flags in the top two
-    bits of the last byte: bit 6 = infinity, bit 7 = (y > -y)."""
+    """GroupAffine::serialize (ark-ec 0.3 / ark-serialize 0.3 SWFlags): x little endian (32 bytes on BN254, 48 on the BLS12
+    curves) with flags in the top two bits of the last byte: bit 6 = infinity, bit 7 = (y > -y)."""
+    nb = field.FQ_BYTES
     if pt is None:
-        b = bytearray(32)
-        b[31] |= 1 << 6
+        b = bytearray(nb)
+        b[nb - 1] |= 1 << 6
         return bytes(b)
     x, y = pt
-    b = bytearray(int(x).to_bytes(32, "little"))
-    if y > (Q - y) % Q:
-        b[31] |= 1 << 7
+    b = bytearray(int(x).to_bytes(nb, "little"))
+    if y > (field.Q_MOD - y) % field.Q_MOD:
+        b[nb - 1] |= 1 << 7
     return bytes(b)
 
 
@@ -195,7 +204,7 @@ def lookup_f_array(q_lookup, c):
     other = np.flatnonzero(~(is_zero | is_one))
     if other.size:
         qi, ci = mont_array_to_ints(q_lookup[other]), mont_array_to_ints(c[other])
-        f[other] = ints_to_mont_array([a * b % P for a, b in zip(qi, ci)])
+        f[other] = ints_to_mont_array([a * b % field.R_MOD for a, b in zip(qi, ci)])
     return np.ascontiguousarray(f)
 
 
@@ -396,7 +405,7 @@ def setup(be, circuit):
     polys["q_table"] = _poly_from_evals(be, ints_to_mont_array(table_masks(circuit.table_size, n)), log_n, n)
     commits = dict(zip(VerifierKey.ORDER, _commit_all(be, [polys[name] for name in VerifierKey.ORDER])))
     w = field.root_of_unity(log_n)
-    pi_roots = [pow(w, pos, P) for pos in circuit.pi.keys()]
+    pi_roots = [pow(w, pos, field.R_MOD) for pos in circuit.pi.keys()]
     vk = VerifierKey(n, pi_roots, commits)
     evals = {"sigma1": be.from_host(circuit.sigma[0]), "sigma2": be.from_host(circuit.sigma[1]),
              "sigma3": be.from_host(circuit.sigma[2]), "q_lookup": sel["q_lookup"]}
@@ -503,9 +512,9 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     q_lo, q_mid, q_hi = parts
     b0, b1 = take(2)
     be.put(q_lo.data, q_lo.len, b0); q_lo.len += 1            # q_lo.coeffs.push(b0)
-    be.put(q_mid.data, 0, (be.get(q_mid.data, 0) - b0) % P)   # q_mid.coeffs[0] -= b0
+    be.put(q_mid.data, 0, (be.get(q_mid.data, 0) - b0) % field.R_MOD)   # q_mid.coeffs[0] -= b0
     be.put(q_mid.data, q_mid.len, b1); q_mid.len += 1
-    be.put(q_hi.data, 0, (be.get(q_hi.data, 0) - b1) % P)
+    be.put(q_hi.data, 0, (be.get(q_hi.data, 0) - b1) % field.R_MOD)
     polys.update(q_lo=q_lo, q_mid=q_mid, q_hi=q_hi)
     commits.update(zip(("q_lo", "q_mid", "q_hi"), _commit_all(be, [polys[k] for k in ("q_lo", "q_mid", "q_hi")])))
     for k in ("q_lo", "q_mid", "q_hi"):
@@ -514,9 +523,9 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     tick("round4_quotient_ms")
 
     # ---- round 5: linearisation (linearization_poly.rs:19-121) and openings
-    shifted = xi * w_n % P
-    zh = (pow(xi, n, P) - 1) % P
-    l1 = zh * pow(n * (xi - 1) % P, -1, P) % P
+    shifted = xi * w_n % field.R_MOD
+    zh = (pow(xi, n, field.R_MOD) - 1) % field.R_MOD
+    l1 = zh * pow(n * (xi - 1) % field.R_MOD, -1, field.R_MOD) % field.R_MOD
     kp = pk.polys
     ev = {"a": be.evaluate(polys["a"], xi), "b": be.evaluate(polys["b"], xi), "c": be.evaluate(polys["c"], xi),
           "sigma1": be.evaluate(kp["sigma1"], xi), "sigma2": be.evaluate(kp["sigma2"], xi),
@@ -525,20 +534,20 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
           "z2_next": be.evaluate(polys["z2"], shifted), "h1_next": be.evaluate(polys["h1"], shifted),
           "h2": be.evaluate(polys["h2"], xi)}
     a_, b_, c_ = ev["a"], ev["b"], ev["c"]
-    al2, al3 = alpha * alpha % P, pow(alpha, 3, P)
-    al4, al5 = pow(alpha, 4, P), pow(alpha, 5, P)
-    bxi = beta * xi % P
-    opd = (1 + delta) % P
-    eopd = epsilon * opd % P
-    s_z1 = (alpha * (bxi + a_ + gamma) % P * (bxi * field.K1 + b_ + gamma) % P * (bxi * field.K2 + c_ + gamma) + l1 * al2) % P
-    s_sigma3 = (-alpha * beta % P * ev["z1_next"] % P * (beta * ev["sigma1"] + a_ + gamma) % P * (beta * ev["sigma2"] + b_ + gamma)) % P
-    s_z2 = (al3 * opd % P * (epsilon + ev["q_lookup"] * c_) % P * (eopd + ev["t"] + delta * ev["t_next"]) + al4 * l1) % P
-    s_h1 = (-al3 * ev["z2_next"] % P * (eopd + ev["h2"] + delta * ev["h1_next"])) % P
-    s_qtable = al5 * ev["t"] % P
-    xn2 = (zh + 1) * xi % P * xi % P                           # xi^(n+2)
-    terms = [(kp["q_m"], a_ * b_ % P), (kp["q_l"], a_), (kp["q_r"], b_), (kp["q_o"], c_), (kp["q_c"], 1),
+    al2, al3 = alpha * alpha % field.R_MOD, pow(alpha, 3, field.R_MOD)
+    al4, al5 = pow(alpha, 4, field.R_MOD), pow(alpha, 5, field.R_MOD)
+    bxi = beta * xi % field.R_MOD
+    opd = (1 + delta) % field.R_MOD
+    eopd = epsilon * opd % field.R_MOD
+    s_z1 = (alpha * (bxi + a_ + gamma) % field.R_MOD * (bxi * field.K1 + b_ + gamma) % field.R_MOD * (bxi * field.K2 + c_ + gamma) + l1 * al2) % field.R_MOD
+    s_sigma3 = (-alpha * beta % field.R_MOD * ev["z1_next"] % field.R_MOD * (beta * ev["sigma1"] + a_ + gamma) % field.R_MOD * (beta * ev["sigma2"] + b_ + gamma)) % field.R_MOD
+    s_z2 = (al3 * opd % field.R_MOD * (epsilon + ev["q_lookup"] * c_) % field.R_MOD * (eopd + ev["t"] + delta * ev["t_next"]) + al4 * l1) % field.R_MOD
+    s_h1 = (-al3 * ev["z2_next"] % field.R_MOD * (eopd + ev["h2"] + delta * ev["h1_next"])) % field.R_MOD
+    s_qtable = al5 * ev["t"] % field.R_MOD
+    xn2 = (zh + 1) * xi % field.R_MOD * xi % field.R_MOD                           # xi^(n+2)
+    terms = [(kp["q_m"], a_ * b_ % field.R_MOD), (kp["q_l"], a_), (kp["q_r"], b_), (kp["q_o"], c_), (kp["q_c"], 1),
              (polys["z1"], s_z1), (kp["sigma3"], s_sigma3), (polys["z2"], s_z2), (polys["h1"], s_h1),
-             (kp["q_table"], s_qtable), (q_lo, (-zh) % P), (q_mid, (-zh * xn2) % P), (q_hi, (-zh * xn2 % P * xn2) % P)]
+             (kp["q_table"], s_qtable), (q_lo, (-zh) % field.R_MOD), (q_mid, (-zh * xn2) % field.R_MOD), (q_hi, (-zh * xn2 % field.R_MOD * xn2) % field.R_MOD)]
     r_poly = be.lincomb([t[0] for t in terms], [t[1] for t in terms])
     r_poly.len = be.effective_len(r_poly.data, r_poly.len)
 
@@ -547,7 +556,7 @@ def prove(be, pk, vk, circuit, blinders, transcript=None, timings=None):
     eta = tr.challenge_scalar("eta")
 
     def witness_of(plist, point):
-        comb = be.lincomb(plist, [pow(eta, i, P) for i in range(len(plist))])
+        comb = be.lincomb(plist, [pow(eta, i, field.R_MOD) for i in range(len(plist))])
         wit, _ = be.divide_linear(comb, point)
         wit.len = be.effective_len(wit.data, wit.len)
         return wit
@@ -618,7 +627,7 @@ class NativeProver:
         self.ctx._check(self.ctx._lib.zkb_plonk_vk_commitments(self._pk, xy.ctypes.data_as(ctypes.c_void_p), inf))
         commits = {name: point_to_ints(xy[k], bool(inf[k])) for k, name in enumerate(VerifierKey.ORDER)}
         w = field.root_of_unity(self.circuit.log_n)
-        return VerifierKey(self.circuit.n, [pow(w, p, P) for p in self.circuit.pi.keys()], commits)
+        return VerifierKey(self.circuit.n, [pow(w, p, field.R_MOD) for p in self.circuit.pi.keys()], commits)
 
     def set_wiring(self, wiring=None):
         """zkb_plonk_pk_set_wiring: the key keeps the circuit's wire maps; prove_bytes(..., from_vars=True) then uploads the
@@ -693,21 +702,24 @@ class NativeProver:
 
 def proof_from_bytes(raw):
     """Inverse of Proof.to_bytes for the verifier: decompress the 13 G1 points (y from x, sign from the flag bit)."""
-    assert len(raw) == 802
+    nb = field.FQ_BYTES                                            # 32 (BN254: 802-byte proofs) or 48 (BLS12: 1010 bytes)
+    assert len(raw) == 13 * nb + 2 + 12 * 32
+    top = 8 * nb - 2
 
     def point(b):
         v = int.from_bytes(b, "little")
-        if (v >> 254) & 1:
+        if (v >> top) & 1:
             return None
-        x = v & ((1 << 254) - 1)
-        y = pow((x * x * x + 3) % Q, (Q + 1) // 4, Q)              # q = 3 mod 4
-        assert y * y % Q == (x * x * x + 3) % Q, "x is not on the curve"
-        if (y > (Q - y) % Q) != bool((v >> 255) & 1):
-            y = (Q - y) % Q
+        x = v & ((1 << top) - 1)
+        y = field.sqrt_q(x * x * x + field.CURVE_B)
+        assert y is not None, "x is not on the curve"
+        if (y > (field.Q_MOD - y) % field.Q_MOD) != bool((v >> (top + 1)) & 1):
+            y = (field.Q_MOD - y) % field.Q_MOD
         return (x, y)
 
-    pts = [point(raw[32 * k: 32 * k + 32]) for k in range(11)]
-    aw, saw = point(raw[352:384]), point(raw[385:417])
-    assert raw[384] == 0 and raw[417] == 0
-    evals = [int.from_bytes(raw[418 + 32 * k: 450 + 32 * k], "little") for k in range(12)]
+    pts = [point(raw[nb * k: nb * k + nb]) for k in range(11)]
+    aw, saw = point(raw[11 * nb: 12 * nb]), point(raw[12 * nb + 1: 13 * nb + 1])
+    assert raw[12 * nb] == 0 and raw[13 * nb + 1] == 0
+    e0 = 13 * nb + 2
+    evals = [int.from_bytes(raw[e0 + 32 * k: e0 + 32 + 32 * k], "little") for k in range(12)]
     return Proof(dict(zip(Proof.COMMITS, pts)), aw, saw, dict(zip(Proof.EVALS, evals)))

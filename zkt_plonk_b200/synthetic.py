@@ -11,7 +11,6 @@ import numpy as np
 from . import field
 from .prover import Circuit, ints_to_mont_array
 
-P = field.R_MOD
 
 
 def make_circuit(log_n, seed=0, table_size=None, n_public=4, lookup_frac=0.01, fill=0.9):
@@ -33,7 +32,7 @@ def make_circuit(log_n, seed=0, table_size=None, n_public=4, lookup_frac=0.01, f
     pick = rng.integers(0, 1 << 30, size=(used, 2))
 
     def new_var(v):
-        values.append(v % P)
+        values.append(v % field.R_MOD)
         return len(values) - 1
 
     def old_or_new(i, k):
@@ -46,20 +45,20 @@ def make_circuit(log_n, seed=0, table_size=None, n_public=4, lookup_frac=0.01, f
         x, y = values[va], values[vb]
         if i < n_public:                                      # public input row: q_l * a + PI = 0
             q_l[i] = 1
-            pi[i] = (-x) % P
+            pi[i] = (-x) % field.R_MOD
             vc = 0
         elif i < n_public + n_lookup:                         # lookup row: c in table, arithmetic part c - c = 0
             vc = new_var(table[int(pick[i, 0]) % len(table)])
             q_lk[i] = 1
         elif kind[i] < 0.45:                                  # a + b - c = 0
-            q_l[i], q_r[i], q_o[i] = 1, 1, P - 1
+            q_l[i], q_r[i], q_o[i] = 1, 1, field.R_MOD - 1
             vc = new_var(x + y)
         elif kind[i] < 0.9:                                   # a * b - c = 0
-            q_m[i], q_o[i] = 1, P - 1
+            q_m[i], q_o[i] = 1, field.R_MOD - 1
             vc = new_var(x * y)
         else:                                                 # 3a + 5b + k - c = 0
             k = int(rnd[i, 2])
-            q_l[i], q_r[i], q_c[i], q_o[i] = 3, 5, k, P - 1
+            q_l[i], q_r[i], q_c[i], q_o[i] = 3, 5, k, field.R_MOD - 1
             vc = new_var(3 * x + 5 * y + k)
         var_a[i], var_b[i], var_c[i] = va, vb, vc
         a[i], b[i], c[i] = x, y, values[vc]
@@ -76,7 +75,7 @@ def _finish(log_n, var_ids, wires, sels, table, table_size, pi, values=None):
     w = field.root_of_unity(log_n)
     roots = [1] * n
     for i in range(1, n):
-        roots[i] = roots[i - 1] * w % P
+        roots[i] = roots[i - 1] * w % field.R_MOD
     ks = (1, field.K1, field.K2)
     var_of = np.array(list(var_a) + list(var_b) + list(var_c), dtype=np.int64)  # position p = wire * n + row
     order = np.argsort(var_of, kind="stable")
@@ -88,7 +87,7 @@ def _finish(log_n, var_ids, wires, sels, table, table_size, pi, values=None):
         grp = order[start:end]
         nxt[grp] = np.roll(grp, -1)
         start = end
-    sig = [ks[int(p) // n] * roots[int(p) % n] % P for p in nxt]
+    sig = [ks[int(p) // n] * roots[int(p) % n] % field.R_MOD for p in nxt]
     sigma = tuple(ints_to_mont_array(sig[k * n:(k + 1) * n]) for k in range(3))
 
     selectors = {"q_m": ints_to_mont_array(q_m), "q_l": ints_to_mont_array(q_l), "q_r": ints_to_mont_array(q_r),
@@ -110,7 +109,7 @@ def make_edge_circuit(log_n, kind, seed=0, table_size=4):
     vals = [0]
 
     def new_var(v):
-        vals.append(v % P)
+        vals.append(v % field.R_MOD)
         return len(vals) - 1
 
     q_m, q_l, q_r, q_o, q_c, q_lk = ([0] * n for _ in range(6))
@@ -125,13 +124,13 @@ def make_edge_circuit(log_n, kind, seed=0, table_size=4):
             x, y = vals[va], vals[vb]
             if i < 2:
                 q_l[i] = 1
-                pi[i] = (-x) % P
+                pi[i] = (-x) % field.R_MOD
                 vc = 0
             elif i % 2:
-                q_m[i], q_o[i] = 1, P - 1
+                q_m[i], q_o[i] = 1, field.R_MOD - 1
                 vc = new_var(x * y)
             else:
-                q_l[i], q_r[i], q_o[i] = 1, 1, P - 1
+                q_l[i], q_r[i], q_o[i] = 1, 1, field.R_MOD - 1
                 vc = new_var(x + y)
             var_a[i], var_b[i], var_c[i] = va, vb, vc
             a[i], b[i], c[i] = x, y, vals[vc]
@@ -141,7 +140,7 @@ def make_edge_circuit(log_n, kind, seed=0, table_size=4):
         for i in range(n):                                      # every row: 5 * b - c = 0, a is the same variable everywhere
             vb = new_var(int(rng.integers(1, 1 << 62)))
             vc = new_var(5 * vals[vb])
-            q_m[i], q_o[i] = 1, P - 1
+            q_m[i], q_o[i] = 1, field.R_MOD - 1
             var_a[i], var_b[i], var_c[i] = five, vb, vc
             a[i], b[i], c[i] = 5, vals[vb], vals[vc]
         table = []
@@ -159,9 +158,9 @@ def check_gates(circ):
     tset = set(circ.table) | {0}
     for i in range(circ.n):
         lhs = (s["q_m"][i] * a[i] * b[i] + s["q_l"][i] * a[i] + s["q_r"][i] * b[i] + s["q_o"][i] * c[i] + s["q_c"][i]
-               + circ.pi.get(i, 0)) % P
+               + circ.pi.get(i, 0)) % field.R_MOD
         if lhs:
             return False
-        if s["q_lookup"][i] and (s["q_lookup"][i] * c[i] % P) not in tset:
+        if s["q_lookup"][i] and (s["q_lookup"][i] * c[i] % field.R_MOD) not in tset:
             return False
     return True

@@ -133,11 +133,12 @@ def fr_bytes(x):
 
 
 def g1_write_bytes(pt):
-    """GroupAffine ToBytes::write: x || y || infinity (65 bytes).  pt: (x, y) canonical ints or None (identity,
-    which arkworks stores as (0, 1, true))."""
+    """GroupAffine ToBytes::write: x || y || infinity (65 bytes on BN254, 97 on the BLS12 curves).  pt: (x, y) canonical ints or
+    None (identity, which arkworks stores as (0, 1, true))."""
+    nb = field.FQ_BYTES
     if pt is None:
-        return (0).to_bytes(32, "little") + (1).to_bytes(32, "little") + b"\x01"
-    return int(pt[0]).to_bytes(32, "little") + int(pt[1]).to_bytes(32, "little") + b"\x00"
+        return (0).to_bytes(nb, "little") + (1).to_bytes(nb, "little") + b"\x01"
+    return int(pt[0]).to_bytes(nb, "little") + int(pt[1]).to_bytes(nb, "little") + b"\x00"
 
 
 class MerlinTranscript:
@@ -162,7 +163,7 @@ class MerlinTranscript:
         self.t.append_message(label.encode(), b"".join(g1_write_bytes(p) for p in pts))
 
     def challenge_scalar(self, label):
-        num_bytes = (254 + 7) // 8 - 1                      # (F::size_in_bits() + 7) / 8 - 1 = 31
+        num_bytes = (field.R_MOD.bit_length() + 7) // 8 - 1  # (F::size_in_bits() + 7) / 8 - 1 = 31 on all three curves
         return int.from_bytes(self.t.challenge_bytes(label.encode(), num_bytes), "little")   # from_random_bytes
 
 
