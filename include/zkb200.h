@@ -9,8 +9,8 @@
  * Curves.  The reference is generic over the pairing engine (its own full test runs on Bls12_381 and Bls12_377,
  * plonk-core/src/plonk.rs:226-254; the CLI fixes Bn254, bin/src/instance.rs:7-10) and Rust monomorphises per curve.  This library
  * is compiled once per curve with identical entry points: libzkb200.so (BN254: everything below), libzkb200_bls12_381.so and
- * libzkb200_bls12_377.so (context, memory, field hooks, NTT, MSM / commitments, polynomial kernels, multi-GPU; the protocol
- * driver, key files and pairing verifier return ZKB_ERR_UNSUPPORTED there).  zkb_curve_info tells a caller which one it loaded
+ * libzkb200_bls12_377.so (everything but the key files and the pairing verifier, which return ZKB_ERR_UNSUPPORTED there: the
+ * CLI's file formats and the restated pairing are BN254's).  zkb_curve_info tells a caller which one it loaded
  * and the element widths: array sizes written below as [8] / [16] / [80] are the BN254 ones (fq_words = 4); on the BLS12 curves
  * an affine point is 12 words and an XYZZ partial sum 24 (fq_words = 6).  Scalars are 4 words on every curve.
  *
@@ -67,7 +67,8 @@ ZKB_API const char *zkb_last_error(zkb_ctx *ctx);
 ZKB_API const char *zkb_version(void);
 /* Which curve this shared object was compiled for (the `E: PairingEngine` of the reference's generics): curve_id 0 = BN254,
  * 1 = BLS12-381, 2 = BLS12-377; 64-bit words of a scalar and of a base-field element; bit length of r; has_prover = 1 when
- * zkb_plonk_* / key files / zkb_plonk_verify are compiled in.  Any pointer may be NULL.  Needs no context and no GPU. */
+ * the protocol driver (zkb_plonk_setup / zkb_plonk_prove ..) is compiled in: every build; the key files and zkb_plonk_verify are
+ * BN254's.  Any pointer may be NULL.  Needs no context and no GPU. */
 ZKB_API int zkb_curve_info(int *curve_id, int *fr_words, int *fq_words, int *fr_bits, int *has_prover);
 /* The curve's G1 generator (ark-* 0.3 G1_GENERATOR_X / _Y), affine, Montgomery form: 2 x fq_words words. */
 ZKB_API int zkb_g1_generator(uint64_t *out_xy);
@@ -233,6 +234,9 @@ ZKB_API void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk);
  * the default binary's); kind 1: EthereumTranscript (gadgets/src/transcript.rs:8-90, bin feature "ethereum-transcript":
  * two chained Keccak-256 states, big-endian items, challenges below 2^253).  Applies to later zkb_plonk_prove calls. */
 ZKB_API int zkb_plonk_pk_set_transcript(zkb_plonk_pk *pk, int kind);
+/* Bytes of a serialised Proof on this build's curve (proof.rs:112-154: 11 compressed commitments, two openings, 12
+ * evaluations): 802 on BN254 -- the [802] written in the prototypes below -- and 1010 on BLS12-381 / BLS12-377. */
+ZKB_API size_t zkb_plonk_proof_bytes(void);
 /* VerifierKey commitments in seed_transcript order (keys/mod.rs:264-274): q_m q_l q_r q_o q_c sigma1 sigma2 sigma3
  * q_lookup q_table; 10 x (x || y) Montgomery. */
 ZKB_API int zkb_plonk_vk_commitments(const zkb_plonk_pk *pk, uint64_t out_xy[80], int is_inf[10]);

@@ -141,7 +141,8 @@ def test_every_build_exports_the_whole_abi(curve):
     assert not missing, missing
     cid, frw, fqw, bits, has_prover = _lib.curve_info(curve)
     assert (cid, frw) == (_lib.CURVE_IDS[curve], 4)
-    assert (fqw, bits, has_prover) == {"bn254": (4, 254, 1), "bls12_381": (6, 255, 0), "bls12_377": (6, 253, 0)}[curve]
+    assert (fqw, bits, has_prover) == {"bn254": (4, 254, 1), "bls12_381": (6, 255, 1), "bls12_377": (6, 253, 1)}[curve]
+    assert lib.zkb_plonk_proof_bytes() == (802 if curve == "bn254" else 1010)
     gen = np.zeros(2 * fqw, dtype=np.uint64)
     assert lib.zkb_g1_generator(ctypes.c_void_p(gen.ctypes.data)) == 0
     o = cref.oracle(curve)

@@ -27,7 +27,7 @@ def cv(request):
     import zkt_plonk_b200 as z
     c = z.Context(0, curve=request.param)
     c.set_stream(torch.cuda.current_stream())
-    assert (c.fq_words, c.has_prover) == (6, 0)
+    assert (c.fq_words, c.has_prover) == (6, 1)
     yield c, cref.oracle(request.param), CURVES[request.param]
     c.close()
 
@@ -246,12 +246,12 @@ def test_polynomial_utilities(cv):
     assert np.array_equal(ev, eev) and np.array_equal(to_host(quot), eq)
 
 
-def test_protocol_driver_is_reported_unsupported(cv):
-    """the BN254-only entry points answer ZKB_ERR_UNSUPPORTED on these builds (never a silent fallback)"""
+def test_bn254_only_entry_points_are_reported_unsupported(cv):
+    """the key files and the pairing verifier answer ZKB_ERR_UNSUPPORTED on these builds (never a silent fallback)"""
     ctx, _, _ = cv
     lib = ctx._lib
     out = ctypes.c_void_p()
-    assert lib.zkb_plonk_setup(ctx._h, 4, None, None, 0, None, 0, ctypes.byref(out)) == -6
+    assert lib.zkb_plonk_load_keys(ctx._h, b"/nonexistent", b"/nonexistent", 4, ctypes.byref(out)) == -6
     assert lib.zkb_plonk_verify(0, None, 0, None, None, None, None, None, None, 0) == -6
 
 
@@ -297,6 +297,16 @@ def test_gpu_proof_is_byte_identical_and_verifies(cv, log_n, fixed_base):
         assert plonk_ref.verify(gvk, gproof, pub, tau) == 0
         assert plonk_ref.verify(gvk, prover.proof_from_bytes(raw), pub, tau) == 0
         assert plonk_ref.verify(gvk, gproof, [(pub[0] + 1) % P] + pub[1:], tau) != 0
+        # the C++ round driver (zkb_plonk_setup / zkb_plonk_prove) of this curve's build: the same bytes, also from the variables
+        npv = prover.NativeProver(ctx, circ)
+        try:
+            assert npv.vk().commits == gvk.commits
+            assert npv.prove_bytes(blinders) == raw
+            if circ.wiring is not None:
+                npv.set_wiring()
+                assert npv.prove_bytes(blinders, from_vars=True) == raw
+        finally:
+            npv.close()
         if log_n <= 10:
             obe = plonk_ref.OracleBackend(to_host(d_srs))
             opk, ovk = prover.setup(obe, circ)

@@ -1,8 +1,8 @@
 """Loader for libzkb200.so (the C ABI of include/zkb200.h) and its per-curve builds.
 
 One shared object per curve, same entry points (the reference's generics monomorphise per pairing engine, plonk.rs:226-254):
-`lib()` / `lib("bn254")` is libzkb200.so (everything), `lib("bls12_381")` and `lib("bls12_377")` hold the field, NTT, MSM /
-commitment and polynomial kernels; their protocol-driver entry points return ZKB_ERR_UNSUPPORTED.
+`lib()` / `lib("bn254")` is libzkb200.so (everything), `lib("bls12_381")` and `lib("bls12_377")` hold everything but the key files and
+the pairing verifier (BN254's: ZKB_ERR_UNSUPPORTED there).
 
 There is NO CPU fallback: if the shared library is missing the import fails loudly, and if no CUDA device
 is present `Context()` raises.  Nothing under oracle/ is ever imported from here.
@@ -95,6 +95,7 @@ def load(curve="bn254"):
         "zkb_plonk_setup": (i, [vp, u, ctypes.POINTER(vp), ctypes.POINTER(vp), sz, ctypes.POINTER(sz), sz, ctypes.POINTER(vp)]),
         "zkb_plonk_pk_destroy": (None, [vp, vp]),
         "zkb_plonk_pk_set_transcript": (i, [vp, i]),
+        "zkb_plonk_proof_bytes": (sz, []),
         "zkb_test_transcript": (i, [i, vp, sz, vp, vp]),
         "zkb_plonk_vk_commitments": (i, [vp, vp, ctypes.POINTER(i)]),
         "zkb_plonk_prove": (i, [vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, ctypes.POINTER(ctypes.c_float)]),

@@ -335,6 +335,10 @@ class Context:
         return v.value
 
     # -- test hook
+    def proof_bytes(self):
+        """bytes of a serialised Proof on this context's curve: 802 (BN254) or 1010 (BLS12-381 / BLS12-377)"""
+        return int(self._lib.zkb_plonk_proof_bytes())
+
     def g1_generator(self):
         out = np.zeros(self.aff_words, dtype=np.uint64)
         self._check(self._lib.zkb_g1_generator(_host_ptr(out)))

@@ -13,6 +13,11 @@ namespace {
 
 using namespace zkb;
 using zkb::host::Fe;
+using zkb::host::Fq;
+constexpr int AFF_W = 2 * host::FQ_L;          // 64-bit words of an affine point at the C boundary (8 / 12)
+constexpr int FQB = 8 * host::FQ_L;           // bytes of a base-field element: 32 (BN254) or 48 (BLS12-381 / BLS12-377)
+// Proof (proof.rs:112-154): 11 compressed commitments, 2 x (compressed witness + the None tag of random_v), 12 evaluations
+constexpr size_t PROOF_BYTES = 11 * FQB + 2 * (FQB + 1) + 12 * 32;   // 802 on BN254, 1010 on the BLS12 curves
 
 // ================================================================================================ Keccak / STROBE / Merlin
 const uint64_t KECCAK_RC[24] = {
@@ -81,15 +86,18 @@ struct Strobe128 {
     void prf(uint8_t *d, size_t n) { begin_op(FLAG_I | FLAG_A | FLAG_C, false); squeeze(d, n); }
 };
 
-// canonical little-endian bytes of a Montgomery field element (ToBytes::write / CanonicalSerialize of Fp256)
-void fe_bytes(const Fe &m, const host::Params &P, uint8_t out[32]) {
-    Fe one = {{1, 0, 0, 0}};
-    Fe c = host::mul(m, one, P);
-    memcpy(out, c.l, 32);
+// canonical little-endian bytes of a Montgomery field element (ToBytes::write / CanonicalSerialize of Fp256 / Fp384): 8 L bytes
+template <int L>
+void fe_bytes(const host::FeT<L> &m, const host::ParamsT<L> &P, uint8_t *out) {
+    host::FeT<L> one;
+    memset(one.l, 0, sizeof one.l);
+    one.l[0] = 1;
+    host::FeT<L> c = host::mul(m, one, P);
+    memcpy(out, c.l, 8 * L);
 }
 
 struct Pt {                                   // affine G1, Montgomery; inf = identity
-    Fe x, y;
+    Fq x, y;
     bool inf;
 };
 
@@ -113,10 +121,11 @@ void keccak256(const uint8_t *data, size_t n, uint8_t out[32]) {
 }
 
 // canonical BIG-endian bytes (into_repr().to_bytes_be())
-void fe_bytes_be(const Fe &m, const host::Params &P, uint8_t out[32]) {
-    uint8_t le[32];
+template <int L>
+void fe_bytes_be(const host::FeT<L> &m, const host::ParamsT<L> &P, uint8_t *out) {
+    uint8_t le[8 * L];
     fe_bytes(m, P, le);
-    for (int i = 0; i < 32; ++i) out[i] = le[31 - i];
+    for (int i = 0; i < 8 * L; ++i) out[i] = le[8 * L - 1 - i];
 }
 
 // TranscriptProtocol for the reference's two transcripts.  kind 0: MerlinTranscript (plonk-core/src/transcript.rs:49-109,
@@ -176,20 +185,20 @@ struct Transcript {
     }
     void append_commitment(const char *label, const Pt &p) {
         if (kind == 1) {                                           // x then y, each its own item; arkworks' zero is (0, 1, true)
-            uint8_t bx[32], by[32];
-            memset(bx, 0, 32);
-            memset(by, 0, 32);
-            if (p.inf) by[31] = 1;
+            uint8_t bx[FQB], by[FQB];                              // (the reference binds this transcript to Bn254: 32-byte items)
+            memset(bx, 0, FQB);
+            memset(by, 0, FQB);
+            if (p.inf) by[FQB - 1] = 1;
             else { fe_bytes_be(p.x, host::FQ, bx); fe_bytes_be(p.y, host::FQ, by); }
-            eth_append(bx, 32);
-            eth_append(by, 32);
+            eth_append(bx, FQB);
+            eth_append(by, FQB);
             return;
         }
-        uint8_t b[65];                                             // GroupAffine::write: x || y || infinity
-        memset(b, 0, 65);
-        if (p.inf) { b[32] = 1; b[64] = 1; }
-        else { fe_bytes(p.x, host::FQ, b); fe_bytes(p.y, host::FQ, b + 32); }
-        append_message(label, b, 65);
+        uint8_t b[2 * FQB + 1];                                    // GroupAffine::write: x || y || infinity (65 / 97 bytes)
+        memset(b, 0, sizeof b);
+        if (p.inf) { b[FQB] = 1; b[2 * FQB] = 1; }
+        else { fe_bytes(p.x, host::FQ, b); fe_bytes(p.y, host::FQ, b + FQB); }
+        append_message(label, b, sizeof b);
     }
     Fe challenge_scalar(const char *label) {
         uint8_t b[32];
@@ -219,21 +228,24 @@ struct Transcript {
 
 // GroupAffine::serialize (ark-ec 0.3 / ark-serialize 0.3 SWFlags): x LE, bit 6 of the last byte = infinity,
 // bit 7 = (y > -y)
-void g1_compressed(const Pt &p, uint8_t out[32]) {
-    memset(out, 0, 32);
-    if (p.inf) { out[31] |= 1 << 6; return; }
+void g1_compressed(const Pt &p, uint8_t *out /* FQB bytes */) {
+    memset(out, 0, FQB);
+    if (p.inf) { out[FQB - 1] |= 1 << 6; return; }
     fe_bytes(p.x, host::FQ, out);
-    Fe one = {{1, 0, 0, 0}};
-    Fe y = host::mul(p.y, one, host::FQ), ny;
-    host::sub_raw(ny.l, host::FQ.p, y.l);
-    if (host::is_zero(y)) memset(ny.l, 0, 32);
+    Fq one;
+    memset(one.l, 0, sizeof one.l);
+    one.l[0] = 1;
+    Fq y = host::mul(p.y, one, host::FQ), ny;
+    host::sub_raw<host::FQ_L>(ny.l, host::FQ.p, y.l);
+    if (host::is_zero(y)) memset(ny.l, 0, sizeof ny.l);
     bool gt = false;
-    for (int i = 3; i >= 0; --i) if (y.l[i] != ny.l[i]) { gt = y.l[i] > ny.l[i]; break; }
-    if (gt) out[31] |= 1 << 7;
+    for (int i = host::FQ_L - 1; i >= 0; --i) if (y.l[i] != ny.l[i]) { gt = y.l[i] > ny.l[i]; break; }
+    if (gt) out[FQB - 1] |= 1 << 7;
 }
 
 // ================================================================================================ small helpers
 inline Fe fe_from(const uint64_t *p) { Fe f; memcpy(f.l, p, 32); return f; }
+inline Fq fq_from(const uint64_t *p) { Fq f; memcpy(f.l, p, FQB); return f; }
 inline Fe FR_ONE() { return host::one(host::FR); }
 inline Fe fadd(const Fe &a, const Fe &b) { return host::add(a, b, host::FR); }
 inline Fe fsub(const Fe &a, const Fe &b) { return host::sub(a, b, host::FR); }

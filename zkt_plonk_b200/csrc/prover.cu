@@ -185,14 +185,14 @@ int poly_from_evals_host(zkb_ctx *ctx, const uint64_t *evals_host, unsigned log_
 int commit_many(zkb_ctx *ctx, const DPoly *const *polys, size_t count, Pt *out) {
     std::vector<const uint64_t *> ptrs(count);
     std::vector<size_t> lens(count);
-    std::vector<uint64_t> xy(8 * count);
+    std::vector<uint64_t> xy(AFF_W * count);
     std::vector<int> inf(count);
     for (size_t k = 0; k < count; ++k) { ptrs[k] = polys[k]->d; lens[k] = polys[k]->len; }
     TRY(zkb_commit_batch_dev(ctx, ptrs.data(), nullptr, lens.data(), count, xy.data(), inf.data()));
     for (size_t k = 0; k < count; ++k) {
         out[k].inf = inf[k] != 0;
-        memcpy(out[k].x.l, &xy[8 * k], 32);
-        memcpy(out[k].y.l, &xy[8 * k + 4], 32);
+        memcpy(out[k].x.l, &xy[AFF_W * k], FQB);
+        memcpy(out[k].y.l, &xy[AFF_W * k + AFF_W / 2], FQB);
     }
     return ZKB_OK;
 }
@@ -222,13 +222,13 @@ __global__ void scatter_fe_rows_kernel(uint4 *dst, const uint32_t *rows, const u
 }
 
 int commit_finish_pts(zkb_ctx *ctx, size_t count, Pt *out) {
-    std::vector<uint64_t> xy(8 * count);
+    std::vector<uint64_t> xy(AFF_W * count);
     std::vector<int> inf(count);
     TRY(zkb_commit_finish(ctx, xy.data(), inf.data()));
     for (size_t k = 0; k < count; ++k) {
         out[k].inf = inf[k] != 0;
-        memcpy(out[k].x.l, &xy[8 * k], 32);
-        memcpy(out[k].y.l, &xy[8 * k + 4], 32);
+        memcpy(out[k].x.l, &xy[AFF_W * k], FQB);
+        memcpy(out[k].y.l, &xy[AFF_W * k + AFF_W / 2], FQB);
     }
     return ZKB_OK;
 }
@@ -291,11 +291,11 @@ int zkb_test_transcript(int kind, const uint8_t *ops, size_t n_ops, const uint64
     Transcript tr("test", kind);
     size_t n_ch = 0;
     for (size_t i = 0; i < n_ops; ++i) {
-        const uint64_t *a = args + 9 * i;
+        const uint64_t *a = args + (AFF_W + 1) * i;                // 9 words per op on BN254
         switch (ops[i]) {
             case 0: tr.append_u64("a", a[0]); break;
             case 1: tr.append_scalar("b", fe_from(a)); break;
-            case 2: { Pt p; p.x = fe_from(a); p.y = fe_from(a + 4); p.inf = a[8] != 0; tr.append_commitment("c", p); break; }
+            case 2: { Pt p; p.x = fq_from(a); p.y = fq_from(a + AFF_W / 2); p.inf = a[AFF_W] != 0; tr.append_commitment("c", p); break; }
             case 3: { Fe c = tr.challenge_scalar("a"); fe_bytes(c, host::FR, challenges_out + 32 * n_ch++); break; }
             default: return ZKB_ERR_INVALID;
         }
@@ -305,9 +305,13 @@ int zkb_test_transcript(int kind, const uint8_t *ops, size_t n_ops, const uint64
 
 int zkb_plonk_pk_set_transcript(zkb_plonk_pk *pk, int kind) {
     if (!pk || (kind != 0 && kind != 1)) return ZKB_ERR_INVALID;
+    if (kind == 1 && ZKB_CURVE != ZKB_CURVE_BN254) return ZKB_ERR_UNSUPPORTED;   // EthereumTranscript is bound to Bn254 upstream
     pk->transcript_kind = kind;
     return ZKB_OK;
 }
+
+// bytes of a serialised Proof on this build's curve (proof.rs:112-154): 802 on BN254, 1010 on BLS12-381 / BLS12-377
+size_t zkb_plonk_proof_bytes(void) { return PROOF_BYTES; }
 
 void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
     if (!pk) return;
@@ -498,8 +502,8 @@ int zkb_plonk_pk_from_polys(zkb_ctx *ctx, unsigned log_n, const uint64_t *const 
     }
     if (vk_xy) {
         for (int k = 0; k < 10; ++k) {
-            pk->vk[k].x = fe_from(vk_xy + 8 * k);
-            pk->vk[k].y = fe_from(vk_xy + 8 * k + 4);
+            pk->vk[k].x = fq_from(vk_xy + AFF_W * k);
+            pk->vk[k].y = fq_from(vk_xy + AFF_W * k + AFF_W / 2);
             pk->vk[k].inf = (vk_inf && vk_inf[k]) || (host::is_zero(pk->vk[k].x) && host::is_zero(pk->vk[k].y));
         }
     }
@@ -514,8 +518,9 @@ int zkb_plonk_pk_from_polys(zkb_ctx *ctx, unsigned log_n, const uint64_t *const 
 int zkb_plonk_load_keys(zkb_ctx *ctx, const char *pk_path, const char *vk_path, size_t table_size, zkb_plonk_pk **out) {
     if (!ctx || !out) return ZKB_ERR_INVALID;
     *out = nullptr;
+    if (ZKB_CURVE != ZKB_CURVE_BN254) ZKB_FAIL(ctx, ZKB_ERR_UNSUPPORTED, "zkb_plonk_load_keys: the key-file readers are BN254's (the CLI's curve)");
     size_t n = 0, n_roots = 0;
-    uint64_t vk_xy[80];
+    uint64_t vk_xy[10 * AFF_W];
     int vk_inf[10];
     if (zkb_vk_file_read(vk_path, &n, nullptr, 0, &n_roots, vk_xy, vk_inf) != ZKB_OK)
         ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_load_keys: not a VerifierKey file (ark-serialize unchecked, KZG10 / Bn254)");
@@ -560,6 +565,7 @@ int zkb_plonk_load_keys(zkb_ctx *ctx, const char *pk_path, const char *vk_path, 
 // What `compile` writes (main.rs:106-112), from a key built here: pk and vk files the reference's CLI can read.
 int zkb_plonk_save_keys(zkb_ctx *ctx, const zkb_plonk_pk *pk, const char *pk_path, const char *vk_path) {
     if (!ctx || !pk) return ZKB_ERR_INVALID;
+    if (ZKB_CURVE != ZKB_CURVE_BN254) ZKB_FAIL(ctx, ZKB_ERR_UNSUPPORTED, "zkb_plonk_save_keys: the key-file writers are BN254's (the CLI's curve)");
     if (pk_path) {
         const int file_to_key[10] = {P_QM, P_QL, P_QR, P_QO, P_QC, P_S1, P_S2, P_S3, P_QLK, P_QT};
         std::vector<std::vector<uint64_t>> store(10);
@@ -580,7 +586,7 @@ int zkb_plonk_save_keys(zkb_ctx *ctx, const zkb_plonk_pk *pk, const char *pk_pat
         const Fe w = host::fr_root_of_unity(pk->log_n);
         std::vector<Fe> roots(pk->pi_pos.size() ? pk->pi_pos.size() : 1);
         for (size_t i = 0; i < pk->pi_pos.size(); ++i) roots[i] = host::pow_u64(w, pk->pi_pos[i], host::FR);
-        uint64_t xy[80];
+        uint64_t xy[10 * AFF_W];
         int inf[10];
         zkb_plonk_vk_commitments(pk, xy, inf);
         if (zkb_vk_file_write(vk_path, pk->n, (const uint64_t *)roots.data(), pk->pi_pos.size(), xy, inf) != ZKB_OK)
@@ -592,9 +598,9 @@ int zkb_plonk_save_keys(zkb_ctx *ctx, const zkb_plonk_pk *pk, const char *pk_pat
 int zkb_plonk_vk_commitments(const zkb_plonk_pk *pk, uint64_t out_xy[80], int is_inf[10]) {
     if (!pk || !out_xy) return ZKB_ERR_INVALID;
     for (int k = 0; k < 10; ++k) {
-        memcpy(out_xy + 8 * k, pk->vk[k].x.l, 32);
-        memcpy(out_xy + 8 * k + 4, pk->vk[k].y.l, 32);
-        if (pk->vk[k].inf) memset(out_xy + 8 * k, 0, 64);
+        memcpy(out_xy + AFF_W * k, pk->vk[k].x.l, FQB);
+        memcpy(out_xy + AFF_W * k + AFF_W / 2, pk->vk[k].y.l, FQB);
+        if (pk->vk[k].inf) memset(out_xy + AFF_W * k, 0, 2 * FQB);
         if (is_inf) is_inf[k] = pk->vk[k].inf;
     }
     return ZKB_OK;
@@ -1064,8 +1070,8 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
     // ---- Proof (proof.rs:106-155): 11 compressed commitments, 2 x (w, None), 12 evaluations
     uint8_t *o = proof_out;
     const Pt *cm[11] = {&c_a[0], &c_a[1], &c_a[2], &c_t[0], &c_t[1], &c_t[2], &c_z[0], &c_z[1], &c_q[0], &c_q[1], &c_q[2]};
-    for (int k = 0; k < 11; ++k, o += 32) g1_compressed(*cm[k], o);
-    for (int k = 0; k < 2; ++k) { g1_compressed(c_w[k], o); o[32] = 0; o += 33; }
+    for (int k = 0; k < 11; ++k, o += FQB) g1_compressed(*cm[k], o);
+    for (int k = 0; k < 2; ++k) { g1_compressed(c_w[k], o); o[FQB] = 0; o += FQB + 1; }
     for (int k = 0; k < 12; ++k, o += 32) fe_bytes(ev[k], host::FR, o);
     if (timings_ms) timings_ms[7] = (float)(now_ms() - t_start);
     return ZKB_OK;

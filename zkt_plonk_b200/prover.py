@@ -622,7 +622,7 @@ class NativeProver:
 
     def vk(self):
         import ctypes
-        xy = np.zeros((10, 8), dtype=np.uint64)
+        xy = np.zeros((10, self.ctx.aff_words), dtype=np.uint64)
         inf = (ctypes.c_int * 10)()
         self.ctx._check(self.ctx._lib.zkb_plonk_vk_commitments(self._pk, xy.ctypes.data_as(ctypes.c_void_p), inf))
         commits = {name: point_to_ints(xy[k], bool(inf[k])) for k, name in enumerate(VerifierKey.ORDER)}
@@ -646,7 +646,7 @@ class NativeProver:
         a, b, cc = (np.ascontiguousarray(x, dtype=np.uint64) for x in (c.a, c.b, c.c))
         table, pi = self._table_pi()
         bl = ints_to_mont_array(blinders)
-        out = np.zeros(802, dtype=np.uint8)
+        out = np.zeros(self.ctx.proof_bytes(), dtype=np.uint8)
         tm = (ctypes.c_float * 8)() if timings else None
         vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
         self.ctx._check(self.ctx._lib.zkb_plonk_prove(self.ctx._h, self._pk, vp(a), vp(b), vp(cc), vp(table), len(c.table), vp(pi),
@@ -676,7 +676,7 @@ class NativeProver:
         vals = np.ascontiguousarray(c.var_values, dtype=np.uint64)
         table, pi = self._table_pi()
         bl = ints_to_mont_array(blinders)
-        out = np.zeros(802, dtype=np.uint8)
+        out = np.zeros(self.ctx.proof_bytes(), dtype=np.uint8)
         tm = (ctypes.c_float * 8)() if timings else None
         vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
         self.ctx._check(self.ctx._lib.zkb_plonk_prove_vars(self.ctx._h, self._pk, vp(vals), vals.shape[0], vp(table), len(c.table),
