@@ -732,11 +732,61 @@ def run_curve_extras(z, torch, dev, flush, int_peak, log_n):
                                                     "unit": "T int32 IMAD/s", "frac": 2.0 * prods * 136 / t_ntt / int_peak}},
                            "dtype": "Fr u32x8, Fq u32x12"}
             del P, x, s_dev
+            c.srs_precompute(-1)
+            torch.cuda.empty_cache()
+            try:
+                out[curve]["prove_2^18"] = _prove_on_curve(z, torch, dev, c, curve, 18)
+            except Exception as e:
+                out[curve]["prove_error"] = repr(e)
             c.close()
             torch.cuda.empty_cache()
         except Exception as e:  # the extras must never sink the headline
             out[curve] = {"error": repr(e)}
     return out
+
+
+def _prove_on_curve(z, torch, dev, ctx, curve, log_n):
+    """One Plonk+Plookup proof of 2^log_n gates on another curve (what plonk.rs:226-254 instantiates) through zkb_plonk_setup /
+    zkb_plonk_prove of that curve's build.  Checked here by a second driver in the product: the Python round schedule over the
+    same kernels (prover.GpuBackend) must give the same bytes; byte identity with the CPU oracle and acceptance by the restated
+    verifier are tests/test_gpu_curves.py's (the library's pairing verifier is BN254's)."""
+    from zkt_plonk_b200 import field, prover, synthetic
+    field.use_curve(curve)
+    try:
+        P = field.R_MOD
+        tau = 0x2B7E151628AED2A6ABF7158809CF4F3C762E7160F38B4DA56A784D9045190CFE % P
+        circ = synthetic.make_circuit(log_n, seed=1)
+        n = circ.n
+        pw = np.empty(n + 8, dtype=object)
+        x = 1
+        for i in range(n + 8):
+            pw[i] = x
+            x = x * tau % P
+        k = np.empty((n + 8, 4), dtype=np.uint64)
+        for j in range(4):
+            k[:, j] = ((pw >> (64 * j)) & ((1 << 64) - 1)).astype(np.uint64)
+        srs = torch.empty((n + 8, ctx.aff_words), dtype=torch.int64, device=dev)
+        ctx.g1_fixed_base_mul_dev(ctx.g1_generator(), torch.from_numpy(k.view(np.int64)).to(dev), n + 8, srs)
+        ctx.srs_load(srs)
+        ctx.srs_precompute(0)
+        native = prover.NativeProver(ctx, circ)
+        blinders = list(range(1000, 1019))
+        walls = []
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            raw = native.prove_bytes(blinders)
+            walls.append((time.perf_counter() - t0) * 1e3)
+        _, tm = native.prove_bytes(blinders, timings=True)
+        kzg = z.GpuKZG10(ctx)
+        gbe = prover.GpuBackend(kzg)
+        gpk, gvk = prover.setup(gbe, circ)
+        same = prover.prove(gbe, gpk, gvk, circ, blinders).to_bytes() == raw and native.vk().commits == gvk.commits
+        native.close()
+        return {"prove_ms": min(walls[1:]), "proof_bytes": len(raw), "rounds_ms": tm,
+                "same_bytes_as_python_round_schedule": bool(same), "driver": "zkb_plonk_prove (C++), wires from host memory"}
+    finally:
+        field.use_curve("bn254")
 
 
 def run_fixed_size_sweep(z, torch, dist, device, rank, world, P, k_host, G, flush, total_logs):
