@@ -48,7 +48,9 @@ constexpr uint32_t SEG_MAX = 1024;       // upper bound of the per-MSM task leng
 constexpr uint32_t RED_THREADS = 128;    // threads per CTA in the window reduction
 constexpr uint32_t RED_MAX_LEVELS = 26;  // levels of the weighted-sum recursion
 constexpr uint32_t RED_CTAS_PER_SM = FqP::N == 8 ? 3 : 2;   // resident CTAs of the wide level (<= 170 registers per thread; 255 with 12-limb coordinates)
-constexpr uint32_t ACC_CTAS_PER_SM = FqP::N == 8 ? 4 : 2;   // bucket accumulation: 128 registers per thread (255 with 12-limb coordinates)
+constexpr uint32_t ACC_CTAS_PER_SM = FqP::N == 8 ? 4 : 2;   // bucket accumulation: 128 registers per thread; 12-limb coordinates: 218 at
+                                                            // 2 CTAs per SM -- measured against 168 registers (76 bytes spilled) at 3 CTAs
+                                                            // per SM: 5.95 vs 6.18 ms at 2^20 on BLS12-381 (more warps do not pay for the spills)
 constexpr uint32_t SIGN_BIT = 0x80000000u;
 // widths at the C boundary, in 64-bit words: an affine point (x, y) and an un-normalised XYZZ partial sum (8 / 16 on BN254,
 // 12 / 24 on the BLS12 curves: zkb_curve_info reports them)
