@@ -699,9 +699,9 @@ def run_curve_extras(z, torch, dev, flush, int_peak, log_n):
                     acc.append(c.msm_last_timing()["accumulate_ms"])
             tm = c.msm_last_timing()
             ms = statistics.mean(ts)
-            # one mixed addition as implemented for 12 limbs: 8 products of 2 * 12^2 + 12 = 300 multiply-adds each (no dedicated
-            # squaring) and the fused a*b - c*d of Y3 with one shared reduction (2 * 144 + 156 = 444)
-            macs_per_add = 8 * 300 + 444
+            # one mixed addition as implemented for 12 limbs: 6 products of 2 * 12^2 + 12 = 300 multiply-adds, 2 dedicated
+            # squarings of 78 + 156 = 234 and the fused a*b - c*d of Y3 with one shared reduction (2 * 144 + 156 = 444)
+            macs_per_add = 6 * 300 + 2 * 234 + 444
             int_ops = 2.0 * n * tm["windows"] * macs_per_add
             acc_s = statistics.mean(acc) * 1e-3
             N = 1 << ln

@@ -316,3 +316,41 @@ def test_gpu_proof_is_byte_identical_and_verifies(cv, log_n, fixed_base):
         ctx.srs_precompute(-1)
         field.use_curve("bn254")
         pyref.use_curve("bn254")
+
+
+@pytest.mark.parametrize("world,tables", [(2, False), (3, True)])
+def test_range_commitments_add_up(cv, world, tables):
+    """SURVEY.md 8e on these curves: contexts that each hold one point range of the committer key (zkb_srs_set_range) commit to the
+    overlap of every polynomial with their range; the partial commitments (XYZZ sums of 24 words) add up to the commitment of
+    the unsharded key and to the oracle's MSM."""
+    import torch
+    import zkt_plonk_b200 as z
+    from zkt_plonk_b200.context import sum_partials
+    from zkt_plonk_b200.parallel import shard_bounds
+    ctx, o, _ = cv
+    n = 4099
+    d_pts, h_pts, _ = gpu_points(ctx, o, n, 11)
+    polys = [fr_mont(o, n, 21), fr_mont(o, n - 37, 22), fr_mont(o, 5, 23)]
+    polys[1][:100] = 0
+    lens = [p.shape[0] for p in polys]
+    devs = [to_dev(p) for p in polys]
+    ctx.srs_load(d_pts)
+    want = ctx.commit_batch_dev(devs, lens)
+    b = shard_bounds(n, world)
+    parts = []
+    for r in range(world):
+        c = z.Context(0, curve=ctx.curve)
+        c.set_stream(torch.cuda.current_stream())
+        c.srs_load(d_pts[b[r]:b[r + 1]].contiguous())
+        c.srs_set_range(b[r], n)
+        if tables:
+            c.srs_precompute(0)
+        for k in range(len(polys)):
+            c.commit_push(devs[k], lens[k])
+        parts.append(c.commit_finish_partials(len(polys)))
+        c.close()
+    for k in range(len(polys)):
+        got, inf = sum_partials(np.stack([parts[r][k] for r in range(world)]), curve=ctx.curve)
+        assert inf == want[k][1] and np.array_equal(got, want[k][0])
+        exp, einf = o.msm_g1(h_pts[:lens[k]], o.from_mont(cref.FR, polys[k]))
+        assert inf == einf and np.array_equal(got, exp)

@@ -240,6 +240,40 @@ def gen_wide(N=12):
               "        : " + ", ".join('"=r"(r[%d])' % i for i in range(N)) + ', "=r"(c)',
               "        : " + ", ".join('"r"(a[%d])' % i for i in range(N)) + ", " + ", ".join('"r"(b[%d])' % i for i in range(N)) + ");",
               "    return c;", "}", ""]
+    # triangular chains of the dedicated squaring: pairs below K0 hold no product of this row (their multiplicands are zero)
+    # and only ripple the carry; same operand numbering as wrow_mad_cin / wrow_mad_cout
+    o += ["// wtri_mad_cin<PAR, K0>: as wrow_mad_cin, but the products start at pair K0 (the pairs below it ripple the carry of lo += x)",
+          "template <int PAR, int K0>",
+          "__device__ __forceinline__ void wtri_mad_cin(uint32_t &lo, uint32_t x, uint32_t (&acc)[%d], const uint32_t (&a)[%d], uint32_t b) {" % (N, N),
+          "    static_assert(K0 >= 0 && K0 < %d, \"a chain has %d pairs\");" % (H, H)]
+    for K0 in range(H):
+        body = ['"add.cc.u32 %%%d, %%%d, %%%d;\\n\\t"' % (N, N, N + 1)]
+        for k in range(H):
+            last = k == H - 1
+            if k < K0:
+                body.append('"addc.cc.u32 %%%d, %%%d, 0;\\n\\t" "addc.cc.u32 %%%d, %%%d, 0;\\n\\t"' % (2 * k, 2 * k, 2 * k + 1, 2 * k + 1))
+            else:
+                body.append('"madc.lo.cc.u32 %%%d, %%%d, %%%d, %%%d;\\n\\t" "madc.hi%s.u32 %%%d, %%%d, %%%d, %%%d;%s"'
+                            % (2 * k, N + 2 + k, N + 2 + H, 2 * k, "" if last else ".cc", 2 * k + 1, N + 2 + k, N + 2 + H, 2 * k + 1,
+                               "" if last else "\\n\\t"))
+        o += ["    %sif constexpr (K0 == %d) {" % ("" if K0 == 0 else "else ", K0),
+              "        asm(" + "\n            ".join(body),
+              "            : " + acc_io + ', "+r"(lo)', '            : "r"(x), ' + a_ops() + ', "r"(b));', "    }"]
+    o += ["}", ""]
+    o += ["// wtri_mad_cout<PAR, K0>: as wrow_mad_cout, the products start at pair K0 (K0 == %d: the row has no limb of this parity left)" % H,
+          "template <int PAR, int K0>",
+          "__device__ __forceinline__ void wtri_mad_cout(uint32_t (&acc)[%d], uint32_t &top, const uint32_t (&a)[%d], uint32_t b) {" % (N, N),
+          "    static_assert(K0 >= 0 && K0 <= %d, \"a chain has %d pairs\");" % (H, H)]
+    for K0 in range(H):
+        body = []
+        for k in range(K0, H):
+            body.append('"%s.lo.cc.u32 %%%d, %%%d, %%%d, %%%d;\\n\\t" "madc.hi.cc.u32 %%%d, %%%d, %%%d, %%%d;\\n\\t"'
+                        % ("mad" if k == K0 else "madc", 2 * k, N + 1 + k, N + 1 + H, 2 * k, 2 * k + 1, N + 1 + k, N + 1 + H, 2 * k + 1))
+        body.append('"addc.u32 %%%d, %%%d, 0;"' % (N, N))
+        o += ["    %sif constexpr (K0 == %d) {" % ("" if K0 == 0 else "else ", K0),
+              "        asm(" + "\n            ".join(body),
+              "            : " + acc_io + ', "+r"(top)', "            : " + a_ops() + ', "r"(b));', "    }"]
+    o += ["}", ""]
     # merge: r = E + (O << 32) + x : r 0..N-1, E = N..2N-1, x = 2N, O = 2N+1 .. 3N-1 (O[0..N-2])
     body = []
     for k in range(N):

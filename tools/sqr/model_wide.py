@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Limb-level model of the 12-limb Montgomery product and of the fused a*b + c*d of csrc/ff.cuh (chains: csrc/ff_wide.cuh),
+"""Limb-level model of the 12-limb Montgomery product, of the dedicated squaring and of the fused a*b + c*d of csrc/ff.cuh (chains: csrc/ff_wide.cuh),
 chain by chain: every carry the device code drops is asserted to be zero, results are compared with Python integers.
 Run for the base fields of BLS12-381 and BLS12-377, random and extreme operands.
 
@@ -75,6 +75,47 @@ def fmadd(pairs, p):
     return r - p if r >= p else r
 
 
+def tri_chain(acc, k0, ms, b, cin):
+    """wtri_mad_cin / wtri_mad_cout: the pairs below k0 only ripple the carry, the products start at pair k0"""
+    c = cin
+    for k in range(N // 2):
+        if k < k0:
+            for j in (2 * k, 2 * k + 1):
+                t = acc[j] + c
+                acc[j], c = t & M32, t >> 32
+        else:
+            prod = ms[k] * b
+            t = acc[2 * k] + (prod & M32) + c
+            acc[2 * k], c = t & M32, t >> 32
+            t = acc[2 * k + 1] + (prod >> 32) + c
+            acc[2 * k + 1], c = t & M32, t >> 32
+    return c
+
+
+def fsqr(a, p):
+    """the dedicated squaring of csrc/ff.cuh (12 limbs)"""
+    inv = (-pow(p, -1, 1 << 32)) & M32
+    al, dl = limbs(a), limbs(2 * a)
+    assert 2 * a < 1 << (32 * N)
+    E, O, x = [0] * N, [0] * N, 0
+    for i in range(N):
+        v = [0 if j < i else al[i] if j == i else (dl[j] & ~1 & M32) if j == i + 1 else dl[j] for j in range(N)]
+        if i == 0:
+            assert chain(O, odd(v), al[0]) == 0 and chain(E, even(v), al[0]) == 0          # wrow_mul: no carries at all
+        else:
+            t = E[0] + x
+            E[0], c = t & M32, t >> 32
+            assert tri_chain(O, i // 2, odd(v), al[i], c) == 0, "wtri_mad_cin dropped a carry"
+            if (i + 1) // 2 < N // 2:
+                O[N - 1] += tri_chain(E, (i + 1) // 2, even(v), al[i], 0)                   # wtri_mad_cout: no carry in
+            assert O[N - 1] <= M32
+        E, O, x = reduce_shift(E, O, p, inv)
+    assert O[N - 1] == 0
+    r = sum(E[i] << (32 * i) for i in range(N)) + (sum(O[i] << (32 * i) for i in range(N - 1)) << 32) + x
+    assert r < 2 * p and r < 1 << (32 * N)
+    return r - p if r >= p else r
+
+
 if __name__ == "__main__":
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     rnd = random.Random(1)
@@ -87,4 +128,6 @@ if __name__ == "__main__":
         for a, b, c, d in cases:
             assert fmadd([(a, b)], p) == a * b * rinv % p
             assert fmadd([(a, b), (c, d)], p) == (a * b + c * d) * rinv % p
-    print("ff_wide model: fmul and fused a*b + c*d exact, no dropped carry, for the base fields of BLS12-381 and BLS12-377")
+            for v in (a, b, c, d):
+                assert fsqr(v, p) == v * v * rinv % p
+    print("ff_wide model: fmul, dedicated squaring and fused a*b + c*d exact, no dropped carry, for the base fields of BLS12-381 and BLS12-377")
