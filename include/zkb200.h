@@ -234,6 +234,17 @@ ZKB_API void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk);
  * the default binary's); kind 1: EthereumTranscript (gadgets/src/transcript.rs:8-90, bin feature "ethereum-transcript":
  * two chained Keccak-256 states, big-endian items, challenges below 2^253).  Applies to later zkb_plonk_prove calls. */
 ZKB_API int zkb_plonk_pk_set_transcript(zkb_plonk_pk *pk, int kind);
+/* Round 2's witness plumbing (prove.rs:145-167): LookupTable::into_multiset, f = q_lookup * c and MultiSet::combine_split
+ * (multiset.rs:103-146) either sparse on a host thread under round 1 (right while a few percent of the rows are lookup gates) or
+ * on the device (csrc/lookup.cu: one hash probe per row, bucket counts by atomics, offsets by one scan, halves by binary
+ * search).  mode 0 = the device path when more than n / 8 rows are lookup gates (default), 1 = host, 2 = device.  Same bytes. */
+ZKB_API int zkb_plonk_pk_set_lookup_mode(zkb_plonk_pk *pk, int mode);
+/* The device path on its own: t, f, h1, h2 (2^log_n Montgomery elements each, device) from the table (HOST pointer, table_len <= n
+ * elements in the composer's order), q_lookup's evaluations and the wire c (device).  Enqueued on the context's stream;
+ * *status_host (may be NULL) is valid after zkb_ctx_sync: 0 ok, bit 0 ElementNotIndexedInTable, bit 1 halves not n long. */
+ZKB_API int zkb_lookup_multisets_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t *table_host, size_t table_len,
+                                     const uint64_t *q_lookup_evals_dev, const uint64_t *c_evals_dev, uint64_t *t_dev, uint64_t *f_dev,
+                                     uint64_t *h1_dev, uint64_t *h2_dev, int *status_host);
 /* Bytes of a serialised Proof on this build's curve (proof.rs:112-154: 11 compressed commitments, two openings, 12
  * evaluations): 802 on BN254 -- the [802] written in the prototypes below -- and 1010 on BLS12-381 / BLS12-377. */
 ZKB_API size_t zkb_plonk_proof_bytes(void);

@@ -270,3 +270,84 @@ def test_native_driver_reuses_key_across_witnesses(ctx):
     native.circuit = circ
     assert native.prove_bytes(blinders) == prover.prove(gbe, gpk, gvk, circ, blinders).to_bytes()
     native.close()
+
+
+@pytest.mark.parametrize("log_n,table_len,dup", [(6, 9, False), (10, 300, True), (13, 1024, True)])
+def test_lookup_multisets_on_the_device_match_combine_split(ctx, log_n, table_len, dup):
+    """csrc/lookup.cu against the reference-shaped Python combine_split (multiset.rs:103-146): t = table || zeros,
+    f = q_lookup * c, h1 / h2 alternate over the buckets in order of first appearance in t -- dense lookups (60 % of the rows),
+    selectors other than 0 / 1, zero inside the table, duplicated table entries; then the two error reports."""
+    import torch
+    rnd = random.Random(log_n)
+    n = 1 << log_n
+    table = [rnd.randrange(1, P) for _ in range(table_len)]
+    table[2] = 0                                                 # a zero inside the table, before other entries
+    if dup:
+        table[7] = table[3]
+        table[-1] = table[0]
+    t = table + [0] * (n - table_len)
+    q = [rnd.choice([0, 1, 1, 1, 5]) if rnd.random() < 0.6 else 0 for _ in range(n)]
+    c = []
+    for qi in q:
+        if qi == 0:
+            c.append(rnd.randrange(P))                           # no lookup gate: c is free, f is zero
+        else:
+            v = rnd.choice(table)
+            c.append(v * pow(qi, -1, P) % P)                     # q * c lands in the table
+    f = [a * b % P for a, b in zip(q, c)]
+    e1, e2 = prover.combine_split(t, f)
+    dev = lambda v: to_dev(prover.ints_to_mont_array(v))
+    outs = [torch.empty((n, 4), dtype=torch.int64, device="cuda") for _ in range(4)]
+    st = ctx.lookup_multisets_dev(log_n, prover.ints_to_mont_array(table), dev(q), dev(c), *outs)
+    assert st == 0
+    got = [prover.mont_array_to_ints(to_host(o)) for o in outs]
+    assert got[0] == t and got[1] == f and got[2] == e1 and got[3] == e2
+    # an element the table does not hold (multiset.rs:121) / a zero in f that a full, zero-free table does not hold
+    c2 = list(c)
+    k = next(i for i, qi in enumerate(q) if qi == 1)
+    c2[k] = (max(table) + 12345) % P
+    assert ctx.lookup_multisets_dev(log_n, prover.ints_to_mont_array(table), dev(q), dev(c2), *outs) & 1
+    full = [rnd.randrange(1, P) for _ in range(n)]
+    assert ctx.lookup_multisets_dev(log_n, prover.ints_to_mont_array(full), dev([0] * n), dev(c), *outs) & 1
+
+
+@pytest.mark.parametrize("log_n,lookup_frac", [(6, 0.01), (10, 0.6), (12, 0.9)])
+def test_native_driver_lookup_paths_give_the_same_proof(ctx, log_n, lookup_frac):
+    """zkb_plonk_pk_set_lookup_mode: the sparse host path, the device path and the automatic choice (device above n / 8 lookup
+    rows) emit the same bytes -- the bytes of the oracle-backend schedule -- also from the variable assignment; a witness whose
+    lookup value is not in the table is refused on both paths."""
+    import zkt_plonk_b200 as z
+    circ = synthetic.make_circuit(log_n, seed=70 + log_n, table_size=min(64, (1 << log_n) // 4), lookup_frac=lookup_frac)
+    assert synthetic.check_gates(circ)
+    d_srs, h_srs = gpu_srs(ctx, circ.n + 8)
+    ctx.srs_load(d_srs)
+    rnd = random.Random(5)
+    blinders = [rnd.randrange(P) for _ in range(19)]
+    obe = plonk_ref.OracleBackend(h_srs)
+    opk, ovk = prover.setup(obe, circ)
+    want = prover.prove(obe, opk, ovk, circ, blinders).to_bytes()
+    native = prover.NativeProver(ctx, circ)
+    try:
+        for mode in (1, 2, 0):
+            native.set_lookup_mode(mode)
+            assert native.prove_bytes(blinders) == want, mode
+        if circ.wiring is not None:
+            native.set_wiring()
+            native.set_lookup_mode(2)
+            assert native.prove_bytes(blinders, from_vars=True) == want
+        # break one lookup row's output wire
+        rows = [i for i in range(circ.n) if prover.mont_array_to_ints(circ.selectors["q_lookup"][i:i + 1])[0]]
+        bad = synthetic.make_circuit(log_n, seed=70 + log_n, table_size=min(64, (1 << log_n) // 4), lookup_frac=lookup_frac)
+        bad.c = bad.c.copy()
+        bad.c[rows[0]] = prover.ints_to_mont_array([max(circ.table) + 7])[0]
+        nb = prover.NativeProver(ctx, bad)
+        try:
+            for mode in (1, 2):
+                nb.set_lookup_mode(mode)
+                with pytest.raises(z.ZkbError) as e:
+                    nb.prove_bytes(blinders)
+                assert e.value.code == -1 and "ElementNotIndexedInTable" in str(e.value)
+        finally:
+            nb.close()
+    finally:
+        native.close()

@@ -96,6 +96,8 @@ def load(curve="bn254"):
         "zkb_plonk_pk_destroy": (None, [vp, vp]),
         "zkb_plonk_pk_set_transcript": (i, [vp, i]),
         "zkb_plonk_proof_bytes": (sz, []),
+        "zkb_plonk_pk_set_lookup_mode": (i, [vp, i]),
+        "zkb_lookup_multisets_dev": (i, [vp, u, vp, sz, vp, vp, vp, vp, vp, vp, ctypes.POINTER(i)]),
         "zkb_test_transcript": (i, [i, vp, sz, vp, vp]),
         "zkb_plonk_vk_commitments": (i, [vp, vp, ctypes.POINTER(i)]),
         "zkb_plonk_prove": (i, [vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, ctypes.POINTER(ctypes.c_float)]),

@@ -277,6 +277,18 @@ class Context:
         self._check(self._lib.zkb_l1_coset_dev(self._h, log_n, _dev_ptr(out)))
         return out
 
+    def lookup_multisets_dev(self, log_n, table, q_lookup_evals, c_evals, t, f, h1, h2):
+        """Round 2's witness plumbing on the device (csrc/lookup.cu): t = table || zeros, f = q_lookup * c and
+        (h1, h2) = combine_split(t, f), n = 2^log_n elements each.  table: host (table_len, 4) Montgomery array; the rest are
+        device tensors.  Returns the status word (0 ok, bit 0 ElementNotIndexedInTable, bit 1 halves not n long) after a sync."""
+        table = np.ascontiguousarray(table, dtype=np.uint64).reshape(-1, 4)
+        status = ctypes.c_int(0)
+        self._check(self._lib.zkb_lookup_multisets_dev(self._h, log_n, _host_ptr(table) if table.shape[0] else None, table.shape[0],
+                                                       _dev_ptr(q_lookup_evals), _dev_ptr(c_evals), _dev_ptr(t), _dev_ptr(f),
+                                                       _dev_ptr(h1), _dev_ptr(h2), ctypes.byref(status)))
+        self.sync()
+        return int(status.value)
+
     def poly_eval_dev(self, coeffs, n, z):
         out = np.zeros(4, dtype=np.uint64)
         self._check(self._lib.zkb_poly_eval_dev(self._h, _dev_ptr(coeffs), n, _host_ptr(z), _host_ptr(out)))

@@ -172,7 +172,7 @@ void zkb_ctx_destroy(zkb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->tables) cudaFree(kv.second.p);
-    DevBuf *bufs[] = {&ctx->ntt_scratch, &ctx->stage, &ctx->ptr_stage, &ctx->srs, &ctx->poly_ws};
+    DevBuf *bufs[] = {&ctx->ntt_scratch, &ctx->stage, &ctx->ptr_stage, &ctx->srs, &ctx->poly_ws, &ctx->lookup_ws};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->len_slot) cudaFree(ctx->len_slot);
     zkb_msm_release(ctx);

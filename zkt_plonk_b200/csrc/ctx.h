@@ -60,6 +60,7 @@ struct zkb_ctx {
 
     // ---- elementwise / scan kernels (poly.cu)
     DevBuf poly_ws;
+    DevBuf lookup_ws;            // bucket tables of zkb_lookup_multisets_dev (lookup.cu)
     int gp_failed = 0;           // the last grand product met a zero denominator
     unsigned long long *len_slot = nullptr;   // device word of zkb_poly_effective_len_dev
 };

@@ -123,6 +123,9 @@ struct zkb_plonk_pk {
     uint64_t *epk[11] = {};                      // q_m q_l q_r q_o q_c q_lookup q_table sigma1 sigma2 sigma3 l_1 (4n cosets)
     std::vector<uint32_t> lookup_rows;           // rows with q_lookup != 0 (the lookup gates)
     std::vector<Fe> lookup_q;                    // q_lookup on those rows, for f = q_lookup * c
+    uint64_t *d_qlookup_evals = nullptr;         // q_lookup on the domain, in HBM: the device path of round 2's plumbing (lookup.cu)
+    int lookup_mode = 0;                         // 0: device path when more than n / 8 rows are lookup gates, 1: host, 2: device
+    int *lookup_status = nullptr;                // pinned word the device path reports into
     uint32_t *d_lookup_rows = nullptr;           // the same rows in HBM (f is scattered there from its compact upload)
     uint64_t *d_lookup_vals = nullptr;
     size_t dirty_t = 0;                          // non-zero regions the previous proof left in the pinned staging
@@ -303,6 +306,15 @@ int zkb_test_transcript(int kind, const uint8_t *ops, size_t n_ops, const uint64
     return ZKB_OK;
 }
 
+// Where round 2's witness plumbing (t, f = q_lookup * c, combine_split) runs: 0 = on the device when more than n / 8 rows are
+// lookup gates, else sparse on a host thread under round 1 (default); 1 = always the host path; 2 = always the device path.
+// The proof bytes are the same either way.
+int zkb_plonk_pk_set_lookup_mode(zkb_plonk_pk *pk, int mode) {
+    if (!pk || mode < 0 || mode > 2) return ZKB_ERR_INVALID;
+    pk->lookup_mode = mode;
+    return ZKB_OK;
+}
+
 int zkb_plonk_pk_set_transcript(zkb_plonk_pk *pk, int kind) {
     if (!pk || (kind != 0 && kind != 1)) return ZKB_ERR_INVALID;
     if (kind == 1 && ZKB_CURVE != ZKB_CURVE_BN254) return ZKB_ERR_UNSUPPORTED;   // EthereumTranscript is bound to Bn254 upstream
@@ -322,6 +334,7 @@ void zkb_plonk_pk_destroy(zkb_ctx *ctx, zkb_plonk_pk *pk) {
     if (pk->wire_stage) cudaFreeHost(pk->wire_stage);
     if (pk->d_vars) cudaFree(pk->d_vars);
     if (pk->copy_stream) cudaStreamDestroy(pk->copy_stream);
+    if (pk->lookup_status) cudaFreeHost(pk->lookup_status);
     if (pk->lookup_stream) cudaStreamDestroy(pk->lookup_stream);
     if (pk->lookup_uploaded) cudaEventDestroy(pk->lookup_uploaded);
     if (pk->wire_uploaded) cudaEventDestroy(pk->wire_uploaded);
@@ -333,7 +346,7 @@ namespace {
 
 // shared head of the two ways to build a key: argument checks and the empty key object
 int key_begin(zkb_ctx *ctx, unsigned log_n, size_t table_size, const size_t *pi_positions, size_t n_pi, zkb_plonk_pk **pk_out) {
-    if (log_n + 2 > 28 || log_n < 3) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_plonk_setup: need 8 <= n and 4n <= 2^28 (InvalidEvalDomainSize)");
+    if (log_n + 2 > host::FR_TWO_ADICITY || log_n + 2 > 30 || log_n < 3) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_plonk_setup: need 8 <= n and 4n <= 2^TWO_ADICITY (28 on BN254; InvalidEvalDomainSize)");
     const size_t n = (size_t)1 << log_n;
     if (table_size >= n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_setup: max table size is equal or larger than n (lookup/table.rs:43)");
     if (n + 8 > ctx->srs_global_n) ZKB_FAIL(ctx, ZKB_ERR_NO_SRS, "zkb_plonk_setup: the committer key must hold at least n + 8 powers");
@@ -364,6 +377,18 @@ int key_finish(zkb_ctx *ctx, zkb_plonk_pk *pk, bool have_vk) {
             ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_setup: H2D copy failed");
     }
     int rc;
+    {                                                                      // q_lookup on the domain (forward NTT of its coefficients)
+        const DPoly &p = pk->poly[P_QLK];
+        rc = dev_alloc_owned(ctx, pk, n * 32, &pk->d_qlookup_evals);
+        if (rc) return rc;
+        if (cudaMemsetAsync(pk->d_qlookup_evals, 0, n * 32, ctx->stream) != cudaSuccess ||
+            (p.len && cudaMemcpyAsync(pk->d_qlookup_evals, p.d, p.len * 32, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess))
+            ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_setup: device copy failed");
+        rc = zkb_ntt_dev(ctx, pk->d_qlookup_evals, p.len, log_n, 0, 0);
+        if (rc) return rc;
+        if (cudaMallocHost((void **)&pk->lookup_status, 64) != cudaSuccess) ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_plonk_setup: cannot allocate pinned staging");
+        *pk->lookup_status = 0;
+    }
     if (!have_vk) {                                                        // verifier key commitments in VerifierKey order (setup.rs:104-121)
         const int vk_order[10] = {P_QM, P_QL, P_QR, P_QO, P_QC, P_S1, P_S2, P_S3, P_QLK, P_QT};
         const DPoly *cp[10];
@@ -655,8 +680,12 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
     uint64_t *ev_a, *ev_b, *ev_c, *ev_t, *ev_f, *ev_h1, *ev_h2;
     TAKE(ev_a, n); TAKE(ev_b, n); TAKE(ev_c, n);
     TAKE(ev_t, n); TAKE(ev_f, n); TAKE(ev_h1, n); TAKE(ev_h2, n);
+    // Dense lookups: one hash probe per lookup row on one host thread would dominate the proof, so when more than n / 8 rows are
+    // lookup gates (or the caller says so: zkb_plonk_pk_set_lookup_mode) t, f, h1, h2 are built on the device instead (lookup.cu).
+    const bool dev_lookup = pk->lookup_mode == 2 || (pk->lookup_mode == 0 && pk->lookup_rows.size() > n / 8);
     std::atomic<int> lookup_status{0};
     std::thread lookup_worker([&]() {
+        if (dev_lookup) return;
         zkb_plonk_pk *mpk = const_cast<zkb_plonk_pk *>(pk);               // staging bookkeeping of the key object
         if (mpk->dirty_t > table_len) memset(t_vals + table_len, 0, (mpk->dirty_t - table_len) * sizeof(Fe));
         if (table_len) memcpy(t_vals, table, table_len * 32);           // LookupTable::into_multiset: entries then zeros
@@ -826,7 +855,12 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
     if (lookup_status.load() == 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "ElementNotIndexedInTable (lookup/multiset.rs:121)");
     if (lookup_status.load() == 2) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: combine_split halves are not n long");
     if (lookup_status.load() == 3) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "zkb_plonk_prove: upload of the lookup multisets failed");
-    ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->lookup_uploaded, 0));
+    if (dev_lookup) {                                                   // the wire c is in HBM by now: f, the bucket counts and the halves there
+        *pk->lookup_status = 0;
+        TRY(zkb_lookup_multisets_dev(ctx, log_n, table, table_len, pk->d_qlookup_evals, ev_c, ev_t, ev_f, ev_h1, ev_h2, pk->lookup_status));
+    } else {
+        ZKB_CUDA(ctx, cudaStreamWaitEvent(s, pk->lookup_uploaded, 0));
+    }
     tick(2);
     {
         const uint64_t *evs[3] = {ev_t, ev_h1, ev_h2};
@@ -884,6 +918,11 @@ static int prove_impl(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uint64_t *a, c
     {
         Pt six[6];
         TRY(commit_finish_pts(ctx, 6, six));
+        if (dev_lookup) {                                               // the status word crossed PCIe before the commitments finished
+            ZKB_CUDA(ctx, cudaStreamSynchronize(s));
+            if (*pk->lookup_status & 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "ElementNotIndexedInTable (lookup/multiset.rs:121)");
+            if (*pk->lookup_status & 2) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_plonk_prove: combine_split halves are not n long");
+        }
         for (int k = 0; k < 3; ++k) { c_a[k] = six[k]; c_t[k] = six[3 + k]; }
     }
     tr.append_commitment("a_commit", c_a[0]);

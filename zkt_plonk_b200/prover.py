@@ -616,6 +616,11 @@ class NativeProver:
         enc = lambda p: None if p is None else os.fsencode(p)
         self.ctx._check(self.ctx._lib.zkb_plonk_save_keys(self.ctx._h, self._pk, enc(pk_path), enc(vk_path)))
 
+    def set_lookup_mode(self, mode):
+        """Where round 2's witness plumbing runs (zkb_plonk_pk_set_lookup_mode): 0 = on the device when more than n / 8 rows are
+        lookup gates (default), 1 = sparse on a host thread, 2 = on the device.  The proof bytes do not depend on it."""
+        self.ctx._check(self.ctx._lib.zkb_plonk_pk_set_lookup_mode(self._pk, int(mode)))
+
     def set_transcript(self, name):
         """"merlin" (default) or "ethereum": which TranscriptProtocol later proofs use (zkb_plonk_pk_set_transcript)."""
         self.ctx._check(self.ctx._lib.zkb_plonk_pk_set_transcript(self._pk, TRANSCRIPTS[name][0]))
