@@ -19,7 +19,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--log-n", type=int, default=12)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--no-verify", action="store_true")
+ap.add_argument("--curve", default="bn254", choices=["bn254", "bls12_381", "bls12_377"])
 args = ap.parse_args()
+from zkt_plonk_b200 import field
+field.use_curve(args.curve)
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -27,8 +30,8 @@ P = prover.P
 TAU = 0x2B7E151628AED2A6ABF7158809CF4F3C762E7160F38B4DA56A784D9045190CFE % P
 n = 1 << args.log_n
 circ = synthetic.make_circuit(args.log_n, seed=3, table_size=min(1024, n // 4))
-ctx = z.Context(local); ctx.set_stream(torch.cuda.current_stream())
-G = ctx.fp_binop(1, 5, np.array([[1, 0, 0, 0], [2, 0, 0, 0]], dtype=np.uint64)).reshape(8)
+ctx = z.Context(local, curve=args.curve); ctx.set_stream(torch.cuda.current_stream())
+G = ctx.g1_generator()
 
 
 def srs_range(c, lo, hi):
@@ -39,7 +42,7 @@ def srs_range(c, lo, hi):
         for j in range(4):
             k[i, j] = (x >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
         x = x * TAU % P
-    out = torch.empty((hi - lo, 8), dtype=torch.int64, device=f"cuda:{local}")
+    out = torch.empty((hi - lo, c.aff_words), dtype=torch.int64, device=f"cuda:{local}")
     c.g1_fixed_base_mul_dev(G, torch.from_numpy(k.view(np.int64)).to(out.device), hi - lo, out)
     torch.cuda.synchronize()
     return out
@@ -50,7 +53,7 @@ blinders = list(range(500, 519))
 layouts = {}
 raw = None
 for layout in ("point_range", "replicated_fanout", "replicated_shard", "replicated_auto"):
-    c = ctx if layout == "point_range" else z.Context(local)
+    c = ctx if layout == "point_range" else z.Context(local, curve=args.curve)
     c.set_stream(torch.cuda.current_stream())
     if layout == "point_range":
         lo, hi = attach_sharded_srs(c, lambda a, b: srs_range(c, a, b), n + 8)
@@ -80,16 +83,17 @@ for layout in ("point_range", "replicated_fanout", "replicated_shard", "replicat
     else:
         nat.close(); c.close()
 if rank == 0:
-    res = {"world": world, "log_n": args.log_n, "range": [lo, hi], "prove_ms_by_layout": layouts, "ranks_agree": True, "layouts_byte_identical": True,
+    res = {"curve": args.curve, "world": world, "log_n": args.log_n, "range": [lo, hi], "prove_ms_by_layout": layouts, "ranks_agree": True, "layouts_byte_identical": True,
            "rounds_ms_rank0_with_syncs": {k: round(v, 3) for k, v in rounds.items()}}
-    ref_ctx = z.Context(local); ref_ctx.set_stream(torch.cuda.current_stream())
+    ref_ctx = z.Context(local, curve=args.curve); ref_ctx.set_stream(torch.cuda.current_stream())
     ref_ctx.srs_load(srs_range(ref_ctx, 0, n + 8)); ref_ctx.srs_precompute(0)
     ref = prover.NativeProver(ref_ctx, circ)
     raw_ref = ref.prove_bytes(blinders)
     t0 = time.perf_counter(); ref.prove_bytes(blinders); res["prove_ms_single_gpu"] = (time.perf_counter() - t0) * 1e3
     res["byte_identical_to_single_gpu"] = raw_ref == raw
     if not args.no_verify:
-        from oracle import plonk_ref
+        from oracle import plonk_ref, pyref
+        pyref.use_curve(args.curve)
         res["verifier_accepts"] = plonk_ref.verify(native.vk(), prover.proof_from_bytes(raw), list(circ.pi.values()), TAU) == 0
     print(json.dumps(res), flush=True)
     assert res["byte_identical_to_single_gpu"] and res.get("verifier_accepts", True)
