@@ -72,7 +72,7 @@ impl Drop for NativeKey<'_> {
 
 /// `proof_system::prove`: wires a, b, c (n each, padded), the lookup table's entries, one value per public-input
 /// row, the 19 blinders in the reference's draw order (a 2, b 2, c 2, h1 3, h2 2, z1 3, z2 3, b0, b1).
-/// Returns `Proof`'s 802 serialised bytes.
+/// Returns `Proof`'s serialised bytes: 802 on BN254, 1010 on the BLS12 builds (`zkb_plonk_proof_bytes`).
 pub fn prove_native(
     ctx: &Ctx,
     key: &NativeKey,
@@ -84,7 +84,7 @@ pub fn prove_native(
     blinders: &[Fr],
 ) -> Result<Vec<u8>, Error> {
     assert_eq!(blinders.len(), 19);
-    let mut out = vec![0u8; 802];
+    let mut out = vec![0u8; unsafe { sys::zkb_plonk_proof_bytes() }];
     let p = |v: &[Fr]| v.as_ptr() as *const u64; // Vec<Fr> is a dense array of 4 x u64 Montgomery limbs
     ctx.check(unsafe {
         sys::zkb_plonk_prove(
