@@ -6,13 +6,14 @@ CPU and compare the proof bytes with the CUDA path.  `verify` restates Proof::ve
 (plonk-core/src/proof_system/proof.rs:285-503), including compute_r0 (:163-217) and
 compute_linearization_commitment (:220-282).  PC::check (SonicKZG10::check's accumulate_elems / check_elems with no
 degree bounds and no hiding) is available in two forms: with `cvk = (H, beta H)` it is the reference's own product of
-pairings e(C - v*G + z*W, H) * e(-W, beta*H) == 1 on the restated BN254 pairing (oracle/pairing.py); without it,
+pairings e(C - v*G + z*W, H) * e(-W, beta*H) == 1 on the restated pairing of the selected curve (oracle/pairing.py for BN254,
+oracle/pairing_bls.py for BLS12-381 / BLS12-377); without it,
 because the synthetic SRS's trapdoor tau is known, the same equation is checked in G1 as  tau*W == C - v*G + z*W.
 PARITY UNPINNED against the Rust binary: see zkb_oracle.c's header.
 """
 import numpy as np
 
-from oracle import cref, pairing, pyref
+from oracle import cref, pairing, pairing_bls, pyref
 from zkt_plonk_b200 import field
 from zkt_plonk_b200.prover import (Poly, Proof, fr_to_limbs, ints_to_mont_array, limbs_to_fr, mont_array_to_ints,
                                     point_to_ints)
@@ -168,10 +169,22 @@ def _lin_comb_points(points, scalars):
     return acc
 
 
+_BLS_PAIRINGS = {}
+
+
+def _bls_pairing():
+    if field.CURVE not in _BLS_PAIRINGS:
+        _BLS_PAIRINGS[field.CURVE] = pairing_bls.Pairing(field.CURVE)
+    return _BLS_PAIRINGS[field.CURVE]
+
+
 def make_cvk(tau):
-    assert field.CURVE == "bn254", "the restated pairing (oracle/pairing.py) is BN254's; other curves verify through the trapdoor"
-    """The G2 half of sonic_pc::VerifierKey for a synthetic SRS: (h, beta_h) = (H, tau * H), H the alt_bn128 G2 generator
-    (KZG10::setup draws h at random; any h gives the same accept / reject decisions)."""
+    """The G2 half of sonic_pc::VerifierKey for a synthetic SRS: (h, beta_h) = (H, tau * H), H the alt_bn128 G2 generator on
+    BN254, the standard G2 generator on BLS12-381, a derived point of order r on BLS12-377 (oracle/pairing_bls.py).
+    KZG10::setup draws h at random; any h gives the same accept / reject decisions."""
+    if field.CURVE != "bn254":
+        e = _bls_pairing()
+        return (e.g2, e.g2_mul(tau % field.R_MOD, e.g2))
     return (pairing.G2_GEN, pairing.g2_mul(tau % field.R_MOD, pairing.G2_GEN))
 
 
@@ -183,7 +196,8 @@ def _kzg_check(commits, point, values, w, eta, tau, cvk=None):
     v = sum(e * x for e, x in zip(chal, values)) % field.R_MOD
     rhs = pyref.g1_add(pyref.g1_add(c, pyref.g1_neg(pyref.g1_mul(v, pyref.G1_GEN))), pyref.g1_mul(point, w) if w else None)
     if cvk is not None:
-        return pairing.pairing_product_is_one([(rhs, cvk[0]), (pyref.g1_neg(w) if w else None, cvk[1])])
+        check = pairing.pairing_product_is_one if field.CURVE == "bn254" else _bls_pairing().pairing_product_is_one
+        return check([(rhs, cvk[0]), (pyref.g1_neg(w) if w else None, cvk[1])])
     lhs = pyref.g1_mul(tau, w) if w else None
     return lhs == rhs
 

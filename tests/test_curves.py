@@ -172,8 +172,8 @@ def on_curve(request):
 def test_prove_verify_roundtrip_on_oracle_backend(on_curve):
     """The reference's own acceptance test on these curves (plonk.rs:226-254 test_full on Bls12_381 / Bls12_377): the round
     schedule (zkt_plonk_b200.prover) over the per-curve oracle gives a proof of 11 * 48 + 2 * 49 + 12 * 32 = 1010 bytes that the
-    restated verifier accepts (PC::check through the synthetic SRS's trapdoor: the restated pairing is BN254's), that parses back
-    to itself, and tampered proofs are rejected."""
+    restated verifier accepts (PC::check through the synthetic SRS's trapdoor and as the reference's product of pairings on the
+    curve's own pairing, oracle/pairing_bls.py), that parses back to itself, and tampered proofs are rejected."""
     from oracle import plonk_ref
     from zkt_plonk_b200 import field, prover, synthetic
     P = field.R_MOD
@@ -192,6 +192,10 @@ def test_prove_verify_roundtrip_on_oracle_backend(on_curve):
     pub = list(circ.pi.values())
     assert plonk_ref.verify(vk, proof, pub, tau) == 0
     assert plonk_ref.verify(vk, proof, pub, tau + 1) == 1
+    # the reference's own PC::check: a product of two pairings per opening on this curve's pairing, no trapdoor involved
+    cvk = plonk_ref.make_cvk(tau)
+    assert plonk_ref.verify(vk, proof, pub, cvk=cvk) == 0
+    assert plonk_ref.verify(vk, proof, pub, cvk=plonk_ref.make_cvk(tau + 1)) == 1
     back = prover.proof_from_bytes(raw)
     assert back.to_bytes() == raw and back.commits == proof.commits and back.aw == proof.aw and back.evals == proof.evals
     assert prover.prove(be, pk, vk, circ, blinders).to_bytes() == raw
