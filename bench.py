@@ -747,9 +747,9 @@ def run_curve_extras(z, torch, dev, flush, int_peak, log_n):
 
 def _prove_on_curve(z, torch, dev, ctx, curve, log_n):
     """One Plonk+Plookup proof of 2^log_n gates on another curve (what plonk.rs:226-254 instantiates) through zkb_plonk_setup /
-    zkb_plonk_prove of that curve's build.  Checked here by a second driver in the product: the Python round schedule over the
-    same kernels (prover.GpuBackend) must give the same bytes; byte identity with the CPU oracle and acceptance by the restated
-    verifier are tests/test_gpu_curves.py's (the library's pairing verifier is BN254's)."""
+    zkb_plonk_prove of that curve's build.  Checked here by the library's verifier (zkb_plonk_verify with the curve's pairing) and
+    by a second driver in the product: the Python round schedule over the same kernels (prover.GpuBackend) must give the same
+    bytes; byte identity with the CPU oracle is tests/test_gpu_curves.py's."""
     from zkt_plonk_b200 import field, prover, synthetic
     field.use_curve(curve)
     try:
@@ -782,8 +782,12 @@ def _prove_on_curve(z, torch, dev, ctx, curve, log_n):
         gbe = prover.GpuBackend(kzg)
         gpk, gvk = prover.setup(gbe, circ)
         same = prover.prove(gbe, gpk, gvk, circ, blinders).to_bytes() == raw and native.vk().commits == gvk.commits
+        from zkt_plonk_b200 import verifier                           # Proof::verify with this curve's pairing (csrc/verify.cu, host)
+        t0 = time.perf_counter()
+        verify_rc = int(verifier.verify(native.vk(), raw, list(circ.pi.values()), verifier.make_cvk(tau)))
+        verify_ms = (time.perf_counter() - t0) * 1e3
         native.close()
-        return {"prove_ms": min(walls[1:]), "proof_bytes": len(raw), "rounds_ms": tm,
+        return {"prove_ms": min(walls[1:]), "proof_bytes": len(raw), "rounds_ms": tm, "verify_rc": verify_rc, "verify_ms": verify_ms,
                 "same_bytes_as_python_round_schedule": bool(same), "driver": "zkb_plonk_prove (C++), wires from host memory"}
     finally:
         field.use_curve("bn254")

@@ -9,8 +9,8 @@
  * Curves.  The reference is generic over the pairing engine (its own full test runs on Bls12_381 and Bls12_377,
  * plonk-core/src/plonk.rs:226-254; the CLI fixes Bn254, bin/src/instance.rs:7-10) and Rust monomorphises per curve.  This library
  * is compiled once per curve with identical entry points: libzkb200.so (BN254: everything below), libzkb200_bls12_381.so and
- * libzkb200_bls12_377.so (everything but the key files and the pairing verifier, which return ZKB_ERR_UNSUPPORTED there: the
- * CLI's file formats and the restated pairing are BN254's).  zkb_curve_info tells a caller which one it loaded
+ * libzkb200_bls12_377.so (everything but the reference CLI's key files and EthereumTranscript, which are BN254's and return
+ * ZKB_ERR_UNSUPPORTED there).  zkb_curve_info tells a caller which one it loaded
  * and the element widths: array sizes written below as [8] / [16] / [80] are the BN254 ones (fq_words = 4); on the BLS12 curves
  * an affine point is 12 words and an XYZZ partial sum 24 (fq_words = 6).  Scalars are 4 words on every curve.
  *
@@ -67,7 +67,7 @@ ZKB_API const char *zkb_last_error(zkb_ctx *ctx);
 ZKB_API const char *zkb_version(void);
 /* Which curve this shared object was compiled for (the `E: PairingEngine` of the reference's generics): curve_id 0 = BN254,
  * 1 = BLS12-381, 2 = BLS12-377; 64-bit words of a scalar and of a base-field element; bit length of r; has_prover = 1 when
- * the protocol driver (zkb_plonk_setup / zkb_plonk_prove ..) is compiled in: every build; the key files and zkb_plonk_verify are
+ * the protocol driver (zkb_plonk_setup / zkb_plonk_prove ..) is compiled in: every build (as is the verifier with the curve's own pairing); the key files are
  * BN254's.  Any pointer may be NULL.  Needs no context and no GPU. */
 ZKB_API int zkb_curve_info(int *curve_id, int *fr_words, int *fq_words, int *fr_bits, int *has_prover);
 /* The curve's G1 generator (ark-* 0.3 G1_GENERATOR_X / _Y), affine, Montgomery form: 2 x fq_words words. */
@@ -277,17 +277,19 @@ ZKB_API int zkb_plonk_prove_vars(zkb_ctx *ctx, const zkb_plonk_pk *pk, const uin
  * the 13-point linearisation commitment (:220-282) and PC::check twice (:441-502), each the product of two pairings
  * e(sum eta^i C_i - (sum eta^i v_i) G + z W, h) * e(-W, beta_h) == 1 that SonicKZG10::check evaluates.
  * n, pi_roots (Montgomery Fr), vk_xy / vk_inf: the VerifierKey (zkb_vk_file_read / zkb_plonk_vk_commitments layout);
- * pub_inputs: one Montgomery Fr per root; proof: the 802 bytes of Proof's CanonicalSerialize; g2_h, g2_beta_h: the G2
- * half of sonic_pc::VerifierKey, each x.c0 x.c1 y.c0 y.c1 (4 limbs each, Montgomery Fq: arkworks' in-memory G2Affine);
+ * pub_inputs: one Montgomery Fr per root; proof: the zkb_plonk_proof_bytes() bytes of Proof's CanonicalSerialize (802 / 1010);
+ * g2_h, g2_beta_h: the G2 half of sonic_pc::VerifierKey, each x.c0 x.c1 y.c0 y.c1 (fq_words limbs each, Montgomery Fq: arkworks'
+ * in-memory G2Affine; 16 words on BN254, 24 on the BLS12 curves).  Every build verifies with its own curve's pairing;
  * transcript_kind as zkb_plonk_pk_set_transcript.
  * Returns 0 = accepted, 1 / 2 = Error::ProofVerificationError { step }, negative = malformed input (a point off its
  * curve, a non-canonical integer ...). */
 ZKB_API int zkb_plonk_verify(size_t n, const uint64_t *pi_roots_mont, size_t n_pi, const uint64_t vk_xy[80], const int vk_inf[10],
                      const uint64_t *pub_inputs_mont, const uint8_t proof[802], const uint64_t g2_h[16], const uint64_t g2_beta_h[16],
                      int transcript_kind);
-/* e(P, Q) on BN254 (optimal ate; ark-ec 0.3 PairingEngine::pairing): the 12 coefficients of the result in the basis
- * 1, w, .., w^11 of Fq12 = Fq[w] / (w^12 - 18 w^6 + 82), canonical integers (4 limbs each).  For tests against
- * oracle/pairing.py; zkb_pairing_product_is_one is what the verifier uses (PairingEngine::product_of_pairings == 1). */
+/* e(P, Q) on this build's curve (optimal ate; ark-ec 0.3 PairingEngine::pairing): the 12 coefficients of the result in the basis
+ * 1, w, .., w^11 of Fq12 = Fq[w] / (w^12 - 2 xi0 w^6 + xi0^2 + b) with w^6 = xi0 + i, i^2 = -b (BN254: w^12 - 18 w^6 + 82; BLS12-381:
+ * w^12 - 2 w^6 + 2; BLS12-377: w^12 + 5), canonical integers (fq_words limbs each).  For tests against oracle/pairing.py and
+ * oracle/pairing_bls.py; zkb_pairing_product_is_one is what the verifier uses (PairingEngine::product_of_pairings == 1). */
 ZKB_API int zkb_pairing(const uint64_t g1_xy[8], const uint64_t g2_xy[16], uint64_t out_canonical[48]);
 ZKB_API int zkb_pairing_product_is_one(const uint64_t *g1_xy, const uint64_t *g2_xy, size_t count, int *is_one);
 /* out = k * Q on G2 (k canonical, Q and out as x.c0 x.c1 y.c0 y.c1 Montgomery limbs; identity = zeros).  Host code, setup

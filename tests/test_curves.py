@@ -152,7 +152,6 @@ def test_every_build_exports_the_whole_abi(curve):
     if curve != "bn254":
         n = ctypes.c_size_t(0)
         assert lib.zkb_ck_file_info(b"/nonexistent", ctypes.byref(n), ctypes.byref(n)) == _lib.ZKB_ERR_UNSUPPORTED
-        assert lib.zkb_plonk_verify(0, None, 0, None, None, None, None, None, None, 0) == _lib.ZKB_ERR_UNSUPPORTED
 
 
 # ------------------------------------------------------------------------------------------------ the whole protocol on BLS12
@@ -196,6 +195,17 @@ def test_prove_verify_roundtrip_on_oracle_backend(on_curve):
     cvk = plonk_ref.make_cvk(tau)
     assert plonk_ref.verify(vk, proof, pub, cvk=cvk) == 0
     assert plonk_ref.verify(vk, proof, pub, cvk=plonk_ref.make_cvk(tau + 1)) == 1
+    # the library's verifier of this curve's build (csrc/verify.cu: host code, its own pairing) agrees
+    from zkt_plonk_b200 import verifier
+    lib_cvk = verifier.make_cvk(tau)
+    assert verifier.verify(vk, raw, pub, lib_cvk) == 0
+    assert verifier.verify(vk, raw, pub, verifier.make_cvk(tau + 1)) == 1
+    assert verifier.verify(vk, raw, [(pub[0] + 1) % P] + pub[1:], lib_cvk) != 0
+    flipped = bytearray(raw)
+    flipped[-1] ^= 1                                               # the last evaluation (h2)
+    assert verifier.verify(vk, bytes(flipped), pub, lib_cvk) != 0
+    swapped = raw[:12 * 48 + 1] + raw[11 * 48: 12 * 48] + raw[13 * 48 + 1:]       # the second witness replaced by the first
+    assert len(swapped) == len(raw) and verifier.verify(vk, swapped, pub, lib_cvk) == 2
     back = prover.proof_from_bytes(raw)
     assert back.to_bytes() == raw and back.commits == proof.commits and back.aw == proof.aw and back.evals == proof.evals
     assert prover.prove(be, pk, vk, circ, blinders).to_bytes() == raw

@@ -247,12 +247,11 @@ def test_polynomial_utilities(cv):
 
 
 def test_bn254_only_entry_points_are_reported_unsupported(cv):
-    """the key files and the pairing verifier answer ZKB_ERR_UNSUPPORTED on these builds (never a silent fallback)"""
+    """the reference CLI's key files answer ZKB_ERR_UNSUPPORTED on these builds (never a silent fallback)"""
     ctx, _, _ = cv
     lib = ctx._lib
     out = ctypes.c_void_p()
     assert lib.zkb_plonk_load_keys(ctx._h, b"/nonexistent", b"/nonexistent", 4, ctypes.byref(out)) == -6
-    assert lib.zkb_plonk_verify(0, None, 0, None, None, None, None, None, None, 0) == -6
 
 
 # ------------------------------------------------------------------------------------------------ whole proofs on the BLS12 curves
@@ -296,6 +295,9 @@ def test_gpu_proof_is_byte_identical_and_verifies(cv, log_n, fixed_base):
         pub = list(circ.pi.values())
         assert plonk_ref.verify(gvk, gproof, pub, tau) == 0
         assert plonk_ref.verify(gvk, prover.proof_from_bytes(raw), pub, tau) == 0
+        from zkt_plonk_b200 import verifier                            # the library's own verifier (pairings on this curve)
+        assert verifier.verify(gvk, raw, pub, verifier.make_cvk(tau)) == 0
+        assert verifier.verify(gvk, raw, pub, verifier.make_cvk(tau + 1)) == 1
         assert plonk_ref.verify(gvk, gproof, [(pub[0] + 1) % P] + pub[1:], tau) != 0
         # the C++ round driver (zkb_plonk_setup / zkb_plonk_prove) of this curve's build: the same bytes, also from the variables
         npv = prover.NativeProver(ctx, circ)

@@ -38,3 +38,42 @@ def test_bilinear_nondegenerate_order_r(curve):
     assert e.pairing_product_is_one([(A, e.g2), (negW, e.g2_mul(tau, e.g2))])
     assert not e.pairing_product_is_one([(A, e.g2), (negW, e.g2_mul(tau + 1, e.g2))])
     assert e.pairing(None, e.g2) == e.f12_one() and e.pairing(e.g1, None) == e.f12_one()
+
+
+# ------------------------------------------------------------------------------------------------ the library's pairing (csrc/verify.cu)
+@pytest.fixture
+def on_curve(request):
+    from oracle import pyref
+    from zkt_plonk_b200 import field
+    field.use_curve(request.param)
+    pyref.use_curve(request.param)
+    yield request.param
+    field.use_curve("bn254")
+    pyref.use_curve("bn254")
+
+
+@pytest.mark.parametrize("on_curve", ["bls12_381", "bls12_377"], indirect=True)
+def test_library_pairing_matches_the_python_restatement(on_curve):
+    """zkb_pairing / zkb_g2_mul / zkb_pairing_product_is_one of the curve's build (host code: no GPU) against oracle/pairing_bls.py:
+    the twelve Fq12 coefficients of e(aP, bQ) are equal one by one (same tower, same Miller function), the product check has the
+    shape of PC::check, points off their curves are refused."""
+    import numpy as np
+    from zkt_plonk_b200 import verifier, _lib
+    e = pairing_bls.Pairing(on_curve)
+    rnd = random.Random(11)
+    a, b = rnd.randrange(1, e.r), rnd.randrange(1, e.r)
+    P, Q = e.g1_mul(a, e.g1), e.g2_mul(b, e.g2)
+    assert verifier.pairing(e.g1, e.g2) == e.pairing(e.g1, e.g2)
+    assert verifier.pairing(P, Q) == e.pairing(P, Q)
+    got = verifier.g2_mul(b)                                      # b * (the curve's G2 point) through the ABI
+    assert np.array_equal(got, verifier.g2_array(Q))
+    tau, k = rnd.randrange(1, e.r), rnd.randrange(1, e.r)
+    W, A = e.g1_mul(k, e.g1), e.g1_mul(tau * k % e.r, e.g1)
+    negW = (W[0], -W[1] % e.q)
+    assert verifier.pairing_product_is_one([(A, e.g2), (negW, e.g2_mul(tau, e.g2))])
+    assert not verifier.pairing_product_is_one([(A, e.g2), (negW, e.g2_mul(tau + 1, e.g2))])
+    assert verifier.pairing_product_is_one([(None, e.g2), (A, None)])
+    with pytest.raises(_lib.ZkbError):
+        verifier.pairing((e.g1[0], (e.g1[1] + 1) % e.q), e.g2)
+    with pytest.raises(_lib.ZkbError):
+        verifier.pairing(e.g1, (e.g2[0], ((e.g2[1][0] + 1) % e.q, e.g2[1][1])))

@@ -26,6 +26,8 @@ CURVES = [
         q=0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47,
         b=3, gen=(1, 2), fr_gen=5,
         root=19103219067921713944291392827692070036145651957329286315305642004821462161904,
+        # pairing: BN family, x = 4965661367192848881; Fq2 = Fq[i] / (i^2 + 1), xi = 9 + i, D-type twist
+        family="bn", x=4965661367192848881, neg_beta=1, xi0=9, twist="D",
     ),
     dict(
         id=1, name="bls12_381",
@@ -36,6 +38,8 @@ CURVES = [
              0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1),
         fr_gen=7,
         root=10238227357739495823651030575849232062558860180284477541189508159991286009131,
+        # pairing: BLS12 family, x = -0xd201000000010000; Fq2 = Fq[i] / (i^2 + 1), xi = 1 + i, M-type twist
+        family="bls12", x=-0xd201000000010000, neg_beta=1, xi0=1, twist="M",
     ),
     dict(
         id=2, name="bls12_377",
@@ -46,6 +50,8 @@ CURVES = [
              0x01914a69c5102eff1f674f5d30afeec4bd7fb348ca3e52d96d182ad44fb82305c2fe3d3634a9591afd82de55559c8ea6),
         fr_gen=22,
         root=8065159656716812877374967518403273466521432693661810619979959746626482506078,
+        # pairing: BLS12 family, x = 0x8508c00000000001; Fq2 = Fq[i] / (i^2 + 5), xi = i, D-type twist
+        family="bls12", x=0x8508c00000000001, neg_beta=5, xi0=0, twist="D",
     ),
 ]
 
@@ -87,6 +93,36 @@ def check(c):
     c["s"], c["t"] = s, t
     assert pow(c["fr_gen"], (r - 1) // 2, r) == r - 1, "GENERATOR is a square"
     assert pow(c["fr_gen"], t, r) == c["root"], "TWO_ADIC_ROOT_OF_UNITY"
+
+
+def f2_mul(a, b, q, neg_beta):
+    return ((a[0] * b[0] - neg_beta * a[1] * b[1]) % q, (a[0] * b[1] + a[1] * b[0]) % q)
+
+
+def f2_pow(a, e, q, neg_beta):
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = f2_mul(r, a, q, neg_beta)
+        a = f2_mul(a, a, q, neg_beta)
+        e >>= 1
+    return r
+
+
+def pairing_params(c):
+    """Constants of the pairing (csrc/verify.cu), derived and checked: the family's polynomials give q and r from x; xi is
+    neither a square nor a cube in Fq2 (so w^6 = xi defines Fq12); zeta = xi^((q^2 - 1) / 6) lies in Fq (w^(q^2) = zeta w)."""
+    q, r, x = c["q"], c["r"], c["x"]
+    if c["family"] == "bn":
+        assert r == 36 * x ** 4 + 36 * x ** 3 + 18 * x ** 2 + 6 * x + 1 and q == 36 * x ** 4 + 36 * x ** 3 + 24 * x ** 2 + 6 * x + 1
+    else:
+        assert r == x ** 4 - x ** 2 + 1 and q == (x - 1) ** 2 * r // 3 + x
+    xi = (c["xi0"], 1)
+    assert f2_pow(xi, (q * q - 1) // 2, q, c["neg_beta"]) != (1, 0) and f2_pow(xi, (q * q - 1) // 3, q, c["neg_beta"]) != (1, 0)
+    zeta = f2_pow(xi, (q * q - 1) // 6, q, c["neg_beta"])
+    assert zeta[1] == 0
+    assert (q ** 4 - q ** 2 + 1) % r == 0
+    return dict(zeta=zeta[0], hard=(q ** 4 - q ** 2 + 1) // r, final=(q ** 12 - 1) // r)
 
 
 def limbs(x, n, bits):
@@ -160,6 +196,16 @@ def gen_params():
         o.append("constexpr uint64_t G1_COEFF_B = %d;" % c["b"])
         o.append("static const uint64_t G1_GEN_X[%d] = %s;" % (fq["n64"], host_arr(c["gen"][0] * (1 << (64 * fq["n64"])) % c["q"], fq["n64"])))
         o.append("static const uint64_t G1_GEN_Y[%d] = %s;" % (fq["n64"], host_arr(c["gen"][1] * (1 << (64 * fq["n64"])) % c["q"], fq["n64"])))
+        pp = pairing_params(c)
+        nh, nf = (pp["hard"].bit_length() + 63) // 64, (pp["final"].bit_length() + 63) // 64
+        o.append("// pairing (csrc/verify.cu): Fq2 = Fq[i] / (i^2 + %d), w^6 = xi = %d + i, %s-type twist, %s family with x = %s0x%x"
+                 % (c["neg_beta"], c["xi0"], c["twist"], c["family"].upper(), "-" if c["x"] < 0 else "", abs(c["x"])))
+        o.append("constexpr int PAIRING_IS_BLS12 = %d, PAIRING_TWIST_M = %d, PAIRING_X_NEG = %d;" % (c["family"] == "bls12", c["twist"] == "M", c["x"] < 0))
+        o.append("constexpr uint64_t FQ2_NEG_BETA = %d, PAIRING_XI0 = %d, PAIRING_X_ABS = 0x%016xULL;" % (c["neg_beta"], c["xi0"], abs(c["x"])))
+        o.append("static const uint64_t PAIRING_ZETA[%d] = %s;   // xi^((q^2 - 1) / 6), canonical: w^(q^2) = zeta w" % (fq["n64"], host_arr(pp["zeta"], fq["n64"])))
+        o.append("constexpr int PAIRING_HARD_EXP_LIMBS = %d, PAIRING_FINAL_EXP_LIMBS = %d;" % (nh, nf))
+        o.append("static const uint64_t PAIRING_HARD_EXP[%d] = %s;   // (q^4 - q^2 + 1) / r" % (nh, host_arr(pp["hard"], nh)))
+        o.append("static const uint64_t PAIRING_FINAL_EXP[%d] = %s;   // (q^12 - 1) / r" % (nf, host_arr(pp["final"], nf)))
         o.append("}  // namespace host")
     o += ["#else", '#error "ZKB_CURVE must be 0 (BN254), 1 (BLS12-381) or 2 (BLS12-377)"', "#endif", "",
           "}  // namespace zkb", "",

@@ -251,6 +251,6 @@ inline Fe fadd(const Fe &a, const Fe &b) { return host::add(a, b, host::FR); }
 inline Fe fsub(const Fe &a, const Fe &b) { return host::sub(a, b, host::FR); }
 inline Fe fmul(const Fe &a, const Fe &b) { return host::mul(a, b, host::FR); }
 inline Fe fneg(const Fe &a) { Fe z = {{0, 0, 0, 0}}; return host::sub(z, a, host::FR); }
-inline bool feq(const Fe &a, const Fe &b) { return memcmp(a.l, b.l, 32) == 0; }
+template <int L> inline bool feq(const host::FeT<L> &a, const host::FeT<L> &b) { return memcmp(a.l, b.l, 8 * L) == 0; }
 
 }  // namespace

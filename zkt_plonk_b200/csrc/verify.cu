@@ -5,13 +5,16 @@
 //                      :220-282 with keys/{arithmetic,permutation,lookup}.rs::compute_linearization_commitment), then
 //                      PC::check twice (:441-502) = SonicKZG10::check without degree bounds or hiding:
 //                      e(sum eta^i C_i - (sum eta^i v_i) G + z W, h) * e(-W, beta_h) == 1
-//   zkb_pairing        e(P, Q) on BN254 (ark-ec 0.3 / ark-bn254 0.3 are crates.io dependencies, un-vendored): optimal ate,
-//                      restated in its simplest exact form -- Fq12 = Fq[w] / (w^12 - 18 w^6 + 82), G2 arithmetic on the
-//                      twist in affine Fq2 coordinates, sparse line functions, the two Frobenius-twisted additions, final
-//                      exponentiation as one power (q^12 - 1) / r.  A product-of-pairings check has the same outcome under
-//                      any correct pairing, so arkworks' internal conventions cannot change accept / reject.
-// tests/test_verify.py compares zkb_pairing with the independent Python restatement (oracle/pairing.py) coefficient by
-// coefficient and zkb_plonk_verify with oracle/plonk_ref.py on accepted and tampered proofs.
+//   zkb_pairing        e(P, Q) on the curve of this build (ark-ec 0.3 / ark-bn254 / ark-bls12-381 / ark-bls12-377 0.3 are crates.io
+//                      dependencies, un-vendored): optimal ate, restated in its simplest exact form -- Fq2 = Fq[i] / (i^2 + b)
+//                      (b = 1, 1, 5), w^6 = xi = xi0 + i (9 + i, 1 + i, i), Fq12 = Fq[w] / (w^12 - 2 xi0 w^6 + xi0^2 + b) as twelve
+//                      coefficients in Fq (BN254: w^12 - 18 w^6 + 82), G2 arithmetic on the twist in affine Fq2 coordinates,
+//                      sparse line functions (D-type twist: BN254, BLS12-377; M-type: BLS12-381, lines times w^3), the Miller
+//                      loop over 6x + 2 with the two Frobenius-twisted additions (BN) or over |x| (BLS12), final exponentiation
+//                      (q^6 - 1)(q^2 + 1) and one power (q^4 - q^2 + 1) / r.  A product-of-pairings check has the same outcome
+//                      under any correct pairing, so arkworks' internal conventions cannot change accept / reject.
+// tests/test_verify.py compares zkb_pairing with the independent Python restatements (oracle/pairing.py, oracle/pairing_bls.py)
+// coefficient by coefficient and zkb_plonk_verify with oracle/plonk_ref.py on accepted and tampered proofs, on every curve.
 #include <string.h>
 
 #include <vector>
@@ -25,97 +28,94 @@ using host::FQ;
 using host::FR;
 
 // ================================================================================================ constants
-const uint64_t FINAL_EXP[44] = {
-    0x86964b64ca86f120ULL, 0x40a4efb7e54523a4ULL, 0x837fa97896e84abbULL, 0x361102b6b9b2b918ULL,
-    0xc0de81def35692daULL, 0xbe04c7e8a6c3c760ULL, 0xd766f9c9d570bb7fULL, 0xc230974d83561841ULL,
-    0x5bba1668c3be69a3ULL, 0x7f3811c410526294ULL, 0x29baee7ddadda71cULL, 0xbf813b8d145da900ULL,
-    0x641bbadf423f9a2cULL, 0xa80bb4ea44eacc5eULL, 0xcd65664814fde37cULL, 0x4a0364b9580291d2ULL,
-    0xee93dfb10826f0ddULL, 0x6b42db8dc5514724ULL, 0xbb10cf430b0f3785ULL, 0x40494e406f804216ULL,
-    0x55cfe107acf3aafbULL, 0x2088ec80e0ebae87ULL, 0x846a3ed011a337a0ULL, 0x48a45a4a1e3a5195ULL,
-    0xe5664568dfc50e16ULL, 0xab6a41294c0cc4ebULL, 0x82d0d602d268c7daULL, 0x6668449aed3cc48aULL,
-    0x5062cd0fb2015dfcULL, 0x7f2940a8b1ddb3d1ULL, 0x77f5b63a2a226448ULL, 0xfef0781361e443aeULL,
-    0xf977870e88d5c6c8ULL, 0x790364a61f676baaULL, 0x5887e72eceaddea3ULL, 0x1377e563a09a1b70ULL,
-    0x0c54efee1bd8c3b2ULL, 0x3ec3d15ad524d8f7ULL, 0xdaf15466b2383a5dULL, 0xe1e30a73bb94fec0ULL,
-    0x6a1c71015f3f7be2ULL, 0x842d43bf6369b1ffULL, 0x20fddadf107d20bcULL, 0x0000002f4b6dc970ULL};
-const uint64_t SQRT_EXP[4] = {0x4f082305b61f3f52ULL, 0x65e05aa45a1c72a3ULL, 0x6e14116da0605617ULL, 0x0c19139cb84c680aULL};   // (q + 1) / 4
+// (q^12 - 1) / r, (q^4 - q^2 + 1) / r, zeta = xi^((q^2 - 1) / 6), the twist and the family: curve_params.h (generated, checked there)
+using host::PAIRING_FINAL_EXP;
+using host::PAIRING_HARD_EXP;
+#if ZKB_CURVE == ZKB_CURVE_BN254
+// BN254 only: the Frobenius twists of the last two Miller steps and the loop count 6x + 2
 const uint64_t FROB_X_C0[4] = {0x99e39557176f553dULL, 0xb78cc310c2c3330cULL, 0x4c0bec3cf559b143ULL, 0x2fb347984f7911f7ULL};
 const uint64_t FROB_X_C1[4] = {0x1665d51c640fcba2ULL, 0x32ae2a1d0b7c9dceULL, 0x4ba4cc8bd75a0794ULL, 0x16c9e55061ebae20ULL};
 const uint64_t FROB_Y_C0[4] = {0xdc54014671a0135aULL, 0xdbaae0eda9c95998ULL, 0xdc5ec698b6e2f9b9ULL, 0x063cf305489af5dcULL};
 const uint64_t FROB_Y_C1[4] = {0x82d37f632623b0e3ULL, 0x21807dc98fa25bd2ULL, 0x0704b5a7ec796f2bULL, 0x07c03cbcac41049aULL};
 const uint64_t FROB2_X_C0[4] = {0xe4bd44e5607cfd48ULL, 0xc28f069fbb966e3dULL, 0x5e6dd9e7e0acccb0ULL, 0x30644e72e131a029ULL};
-const uint64_t HARD_EXP[12] = {0xe81bb482ccdf42b1ULL, 0x5abf5cc4f49c36d4ULL, 0xf1154e7e1da014fdULL, 0xdcc7b44c87cdbacfULL,
-                               0xaaa441e3954bcf8aULL, 0x6b887d56d5095f23ULL, 0x79581e16f3fd90c6ULL, 0x3b1b1355d189227dULL,
-                               0x4e529a5861876f6bULL, 0x6c0eb522d5b12278ULL, 0x331ec15183177fafULL, 0x01baaa710b0759adULL};   // (q^4 - q^2 + 1) / r
-const uint64_t ZETA_C0[4] = {0xe4bd44e5607cfd49ULL, 0xc28f069fbb966e3dULL, 0x5e6dd9e7e0acccb0ULL, 0x30644e72e131a029ULL};   // w^(q^2) = zeta w
 const uint64_t ATE_LOOP_LOW = 0x9d797039be763ba8ULL;      // 6x + 2 = 2^64 + this (x = 4965661367192848881): top bit implicit
 
-inline Fe q_from_canon(const uint64_t c[4]) { Fe f, r2; memcpy(f.l, c, 32); memcpy(r2.l, FQ.r2, 32); return host::mul(f, r2, FQ); }
-inline Fe q_small(uint64_t v) { return host::from_u64(v, FQ); }
-inline Fe qadd(const Fe &a, const Fe &b) { return host::add(a, b, FQ); }
-inline Fe qsub(const Fe &a, const Fe &b) { return host::sub(a, b, FQ); }
-inline Fe qmul(const Fe &a, const Fe &b) { return host::mul(a, b, FQ); }
-inline Fe qneg(const Fe &a) { Fe z = {{0, 0, 0, 0}}; return host::sub(z, a, FQ); }
-inline Fe qzero() { Fe z = {{0, 0, 0, 0}}; return z; }
+#endif
 
-// ================================================================================================ Fq2 = Fq[i] / (i^2 + 1)
-struct F2 { Fe c0, c1; };
+inline Fq q_from_canon(const uint64_t *c /* FQ_L words */) { Fq f, r2; memcpy(f.l, c, FQB); memcpy(r2.l, FQ.r2, FQB); return host::mul(f, r2, FQ); }
+inline Fq q_small(uint64_t v) { return host::from_u64(v, FQ); }
+inline Fq qadd(const Fq &a, const Fq &b) { return host::add(a, b, FQ); }
+inline Fq qsub(const Fq &a, const Fq &b) { return host::sub(a, b, FQ); }
+inline Fq qmul(const Fq &a, const Fq &b) { return host::mul(a, b, FQ); }
+inline Fq qzero() { Fq z; memset(z.l, 0, sizeof z.l); return z; }
+inline Fq qneg(const Fq &a) { return host::sub(qzero(), a, FQ); }
+inline bool qeq(const Fq &a, const Fq &b) { return memcmp(a.l, b.l, FQB) == 0; }
+inline Fq q_canonical(const Fq &m) { Fq one = qzero(); one.l[0] = 1; return host::mul(m, one, FQ); }
+
+// ================================================================================================ Fq2 = Fq[i] / (i^2 + b), b = FQ2_NEG_BETA
+inline Fq q_times_b(const Fq &a) { return host::FQ2_NEG_BETA == 1 ? a : qmul(q_small(host::FQ2_NEG_BETA), a); }
+struct F2 { Fq c0, c1; };
 inline F2 f2_add(const F2 &a, const F2 &b) { return {qadd(a.c0, b.c0), qadd(a.c1, b.c1)}; }
 inline F2 f2_sub(const F2 &a, const F2 &b) { return {qsub(a.c0, b.c0), qsub(a.c1, b.c1)}; }
 inline F2 f2_mul(const F2 &a, const F2 &b) {
-    return {qsub(qmul(a.c0, b.c0), qmul(a.c1, b.c1)), qadd(qmul(a.c0, b.c1), qmul(a.c1, b.c0))};
+    return {qsub(qmul(a.c0, b.c0), q_times_b(qmul(a.c1, b.c1))), qadd(qmul(a.c0, b.c1), qmul(a.c1, b.c0))};
 }
 inline F2 f2_conj(const F2 &a) { return {a.c0, qneg(a.c1)}; }
 inline F2 f2_inv(const F2 &a) {
-    Fe d = host::inv(qadd(qmul(a.c0, a.c0), qmul(a.c1, a.c1)), FQ);
+    Fq d = host::inv(qadd(qmul(a.c0, a.c0), q_times_b(qmul(a.c1, a.c1))), FQ);
     return {qmul(a.c0, d), qneg(qmul(a.c1, d))};
 }
 inline bool f2_is_zero(const F2 &a) { return host::is_zero(a.c0) && host::is_zero(a.c1); }
-inline bool f2_eq(const F2 &a, const F2 &b) { return feq(a.c0, b.c0) && feq(a.c1, b.c1); }
+inline bool f2_eq(const F2 &a, const F2 &b) { return qeq(a.c0, b.c0) && qeq(a.c1, b.c1); }
 
 struct G2 { F2 x, y; bool inf; };
 
-// y^2 = x^3 + 3 / (9 + i)
+// the twist: y^2 = x^3 + b / xi (D-type: BN254 3 / (9 + i), BLS12-377 1 / i) or y^2 = x^3 + b xi (M-type: BLS12-381 4 (1 + i))
 bool g2_on_curve(const G2 &p) {
     if (p.inf) return true;
-    F2 xi = {q_small(9), q_small(1)}, three = {q_small(3), qzero()};
-    F2 b2 = f2_mul(three, f2_inv(xi));
+    F2 xi = {q_small(host::PAIRING_XI0), q_small(1)}, bb = {q_small(host::G1_COEFF_B), qzero()};
+    F2 b2 = f2_mul(bb, host::PAIRING_TWIST_M ? xi : f2_inv(xi));
     return f2_eq(f2_sub(f2_mul(p.y, p.y), f2_mul(f2_mul(p.x, p.x), p.x)), b2);
 }
 
-// ================================================================================================ Fq12 = Fq[w] / (w^12 - 18 w^6 + 82)
-struct F12 { Fe c[12]; };
+// ================================================================================================ Fq12 = Fq[w] / (w^12 - A w^6 + C)
+// w^6 = xi0 + i and i^2 = -b give (w^6 - xi0)^2 = -b:  A = 2 xi0, C = xi0^2 + b  (BN254: 18, 82; BLS12-381: 2, 2; BLS12-377: 0, 5)
+constexpr uint64_t F12_A = 2 * host::PAIRING_XI0, F12_C = host::PAIRING_XI0 * host::PAIRING_XI0 + host::FQ2_NEG_BETA;
+struct F12 { Fq c[12]; };
 F12 f12_one() { F12 r; for (int i = 0; i < 12; ++i) r.c[i] = qzero(); r.c[0] = host::one(FQ); return r; }
-bool f12_eq(const F12 &a, const F12 &b) { for (int i = 0; i < 12; ++i) if (!feq(a.c[i], b.c[i])) return false; return true; }
+bool f12_eq(const F12 &a, const F12 &b) { for (int i = 0; i < 12; ++i) if (!qeq(a.c[i], b.c[i])) return false; return true; }
 
 F12 f12_mul(const F12 &a, const F12 &b) {
-    Fe t[23];
+    Fq t[23];
     for (int k = 0; k < 23; ++k) t[k] = qzero();
     for (int i = 0; i < 12; ++i) {
         if (host::is_zero(a.c[i])) continue;
         for (int j = 0; j < 12; ++j) t[i + j] = qadd(t[i + j], qmul(a.c[i], b.c[j]));
     }
-    const Fe k18 = q_small(18), k82 = q_small(82);
-    for (int k = 22; k >= 12; --k) {                       // w^12 = 18 w^6 - 82
+    const Fq kA = q_small(F12_A), kC = q_small(F12_C);
+    for (int k = 22; k >= 12; --k) {                       // w^12 = A w^6 - C
         if (host::is_zero(t[k])) continue;
-        t[k - 6] = qadd(t[k - 6], qmul(k18, t[k]));
-        t[k - 12] = qsub(t[k - 12], qmul(k82, t[k]));
+        if (F12_A) t[k - 6] = qadd(t[k - 6], qmul(kA, t[k]));
+        t[k - 12] = qsub(t[k - 12], qmul(kC, t[k]));
     }
     F12 r;
     for (int k = 0; k < 12; ++k) r.c[k] = t[k];
     return r;
 }
 
-// a * (l0 + l1 w + l3 w^3 + l7 w^7 + l9 w^9): the shape of a line function (60 products instead of 144)
+// a * line: a line function has five non-zero coefficients (60 products instead of 144) -- at w^0, w^1, w^3, w^7, w^9 on a
+// D-type twist, at w^0, w^2, w^3, w^6, w^8 (the line times w^3) on an M-type twist
 F12 f12_mul_line(const F12 &a, const F12 &l) {
-    static const int NZ[5] = {0, 1, 3, 7, 9};
-    Fe t[23];
+    static const int NZ_D[5] = {0, 1, 3, 7, 9}, NZ_M[5] = {0, 2, 3, 6, 8};
+    const int *NZ = host::PAIRING_TWIST_M ? NZ_M : NZ_D;
+    Fq t[23];
     for (int k = 0; k < 23; ++k) t[k] = qzero();
     for (int i = 0; i < 12; ++i)
         for (int jj = 0; jj < 5; ++jj) t[i + NZ[jj]] = qadd(t[i + NZ[jj]], qmul(a.c[i], l.c[NZ[jj]]));
-    const Fe k18 = q_small(18), k82 = q_small(82);
+    const Fq kA = q_small(F12_A), kC = q_small(F12_C);
     for (int k = 20; k >= 12; --k) {
-        t[k - 6] = qadd(t[k - 6], qmul(k18, t[k]));
-        t[k - 12] = qsub(t[k - 12], qmul(k82, t[k]));
+        if (F12_A) t[k - 6] = qadd(t[k - 6], qmul(kA, t[k]));
+        t[k - 12] = qsub(t[k - 12], qmul(kC, t[k]));
     }
     F12 r;
     for (int k = 0; k < 12; ++k) r.c[k] = t[k];
@@ -131,32 +131,32 @@ F12 f12_conj(const F12 &a) {
 
 // q^2-power Frobenius: the coefficients are in Fq and w^(q^2) = zeta w with zeta a sixth root of unity of Fq
 F12 f12_frob2(const F12 &a) {
-    const Fe zeta = q_from_canon(ZETA_C0);
+    const Fq zeta = q_from_canon(host::PAIRING_ZETA);
     F12 r = a;
-    Fe z = zeta;
+    Fq z = zeta;
     for (int k = 1; k < 12; ++k) { r.c[k] = qmul(a.c[k], z); z = qmul(z, zeta); }
     return r;
 }
 
-// a^-1 by the extended Euclidean algorithm in Fq[w] against w^12 - 18 w^6 + 82 (a != 0)
+// a^-1 by the extended Euclidean algorithm in Fq[w] against w^12 - A w^6 + C (a != 0)
 F12 f12_inv(const F12 &a) {
-    auto deg = [](const Fe *p) { int d = 12; while (d > 0 && host::is_zero(p[d])) --d; return d; };
-    Fe lm[13], hm[13], low[13], high[13];
+    auto deg = [](const Fq *p) { int d = 12; while (d > 0 && host::is_zero(p[d])) --d; return d; };
+    Fq lm[13], hm[13], low[13], high[13];
     for (int i = 0; i < 13; ++i) { lm[i] = qzero(); hm[i] = qzero(); low[i] = i < 12 ? a.c[i] : qzero(); high[i] = qzero(); }
     lm[0] = host::one(FQ);
-    high[0] = q_small(82); high[6] = qneg(q_small(18)); high[12] = host::one(FQ);
+    high[0] = q_small(F12_C); high[6] = qneg(q_small(F12_A)); high[12] = host::one(FQ);
     while (deg(low) > 0) {
         // r = high div low (quotient only), then (lm, low, hm, high) <- (hm - lm r, high - low r, lm, low)
-        Fe r[13], work[13];
+        Fq r[13], work[13];
         for (int i = 0; i < 13; ++i) { r[i] = qzero(); work[i] = high[i]; }
         const int dl = deg(low), dh = deg(high);
-        const Fe lead_inv = host::inv(low[dl], FQ);
+        const Fq lead_inv = host::inv(low[dl], FQ);
         for (int i = dh - dl; i >= 0; --i) {
-            Fe c = qmul(work[dl + i], lead_inv);
+            Fq c = qmul(work[dl + i], lead_inv);
             r[i] = c;
             if (!host::is_zero(c)) for (int j = 0; j <= dl; ++j) work[i + j] = qsub(work[i + j], qmul(c, low[j]));
         }
-        Fe nm[13], nw[13];
+        Fq nm[13], nw[13];
         for (int i = 0; i < 13; ++i) { nm[i] = hm[i]; nw[i] = high[i]; }
         for (int i = 0; i < 13; ++i)
             for (int j = 0; j + i < 13; ++j) {
@@ -165,7 +165,7 @@ F12 f12_inv(const F12 &a) {
             }
         for (int i = 0; i < 13; ++i) { hm[i] = lm[i]; high[i] = low[i]; lm[i] = nm[i]; low[i] = nw[i]; }
     }
-    const Fe inv0 = host::inv(low[0], FQ);
+    const Fq inv0 = host::inv(low[0], FQ);
     F12 out;
     for (int i = 0; i < 12; ++i) out.c[i] = qmul(lm[i], inv0);
     return out;
@@ -181,20 +181,28 @@ F12 f12_pow(const F12 &a, const uint64_t *e, int limbs) {
     return acc;
 }
 
-// Fq2 -> two Fq12 coefficients: a0 + a1 i = (a0 - 9 a1) + a1 w^6
-inline void embed(const F2 &a, Fe *lo, Fe *hi) {
-    *lo = qsub(a.c0, qmul(q_small(9), a.c1));
+// Fq2 -> two Fq12 coefficients: a0 + a1 i = (a0 - xi0 a1) + a1 w^6
+inline void embed(const F2 &a, Fq *lo, Fq *hi) {
+    *lo = host::PAIRING_XI0 ? qsub(a.c0, qmul(q_small(host::PAIRING_XI0), a.c1)) : a.c0;
     *hi = a.c1;
 }
 
 // line through the untwisted (xr, yr) with slope embed(lam) w, at P = (xp, yp) in E(Fq):
 //   -yp + xp embed(lam) w + embed(yr - lam xr) w^3      (coefficients at w^0, w^1, w^7, w^3, w^9)
-F12 sparse_line(const F2 &lam, const F2 &xr, const F2 &yr, const Fe &xp, const Fe &yp) {
+F12 sparse_line(const F2 &lam, const F2 &xr, const F2 &yr, const Fq &xp, const Fq &yp) {
     F12 l;
     for (int i = 0; i < 12; ++i) l.c[i] = qzero();
-    Fe l0, l1, c0, c1;
+    Fq l0, l1, c0, c1;
     embed(lam, &l0, &l1);
     embed(f2_sub(yr, f2_mul(lam, xr)), &c0, &c1);
+    if (host::PAIRING_TWIST_M) {                           // untwist (x', y') -> (x' / w^2, y' / w^3); the line times w^3 (an element
+        l.c[3] = qneg(yp);                                 // of Fq4: the final exponentiation kills it):
+        l.c[2] = qmul(l0, xp);                             //   -yp w^3 + xp embed(lam) w^2 + embed(yr - lam xr)
+        l.c[8] = qmul(l1, xp);
+        l.c[0] = c0;
+        l.c[6] = c1;
+        return l;
+    }
     l.c[0] = qneg(yp);
     l.c[1] = qmul(l0, xp);
     l.c[7] = qmul(l1, xp);
@@ -206,7 +214,7 @@ F12 sparse_line(const F2 &lam, const F2 &xr, const F2 &yr, const Fe &xp, const F
 struct Miller {
     F12 f;
     F2 xr, yr;
-    Fe xp, yp;
+    Fq xp, yp;
     // one step: tangent at R (square == true) or chord through R and (x2, y2); f <- f^2 * line or f * line; R <- 2R or R + Q
     void step(bool square, F2 x2, F2 y2) {
         F2 lam;
@@ -229,11 +237,22 @@ struct Miller {
 
 // Miller loop of the optimal ate pairing; the identity on either side gives 1.  (P, Q of prime order r: the chord / tangent
 // denominators cannot vanish inside the loop.)
-F12 miller_loop(const G2 &q, const Fe &xp, const Fe &yp, bool p_inf) {
+F12 miller_loop(const G2 &q, const Fq &xp, const Fq &yp, bool p_inf) {
     if (q.inf || p_inf) return f12_one();
     Miller m;
     m.f = f12_one();
     m.xr = q.x; m.yr = q.y; m.xp = xp; m.yp = yp;
+#if ZKB_CURVE != ZKB_CURVE_BN254
+    // BLS12: f_{|x|, Q}(P), bits of |x| below the leading one; x < 0: f_{-|x|} = 1 / f_{|x|} up to factors the final power
+    // kills, and on the values that survive it the inverse is the q^6 Frobenius w -> -w
+    int top = 63;
+    while (!((host::PAIRING_X_ABS >> top) & 1)) --top;
+    for (int i = top - 1; i >= 0; --i) {
+        m.step(true, q.x, q.y);
+        if ((host::PAIRING_X_ABS >> i) & 1) m.step(false, q.x, q.y);
+    }
+    return host::PAIRING_X_NEG ? f12_conj(m.f) : m.f;
+#else
     for (int i = 63; i >= 0; --i) {
         m.step(true, q.x, q.y);
         if ((ATE_LOOP_LOW >> i) & 1) m.step(false, q.x, q.y);
@@ -245,22 +264,23 @@ F12 miller_loop(const G2 &q, const Fe &xp, const Fe &yp, bool p_inf) {
     m.step(false, x1, y1);
     F2 lam = f2_mul(f2_sub(y2, m.yr), f2_inv(f2_sub(x2, m.xr)));
     return f12_mul_line(m.f, sparse_line(lam, m.xr, m.yr, xp, yp));
+#endif
 }
 
 // f^((q^12 - 1) / r) as (q^6 - 1) (q^2 + 1) ((q^4 - q^2 + 1) / r): two Frobenius maps, one inversion and a 761-bit power
 // instead of a 2790-bit one.  final_exponentiation_plain is the definition; zkb_pairing's tests see both agree.
-F12 final_exponentiation_plain(const F12 &f) { return f12_pow(f, FINAL_EXP, 44); }
+F12 final_exponentiation_plain(const F12 &f) { return f12_pow(f, PAIRING_FINAL_EXP, host::PAIRING_FINAL_EXP_LIMBS); }
 F12 final_exponentiation(const F12 &f) {
     bool zero = true;
     for (int i = 0; i < 12; ++i) if (!host::is_zero(f.c[i])) zero = false;
     if (zero) return f;                                    // cannot happen for points of order r; keep it total
     F12 t = f12_mul(f12_conj(f), f12_inv(f));
     t = f12_mul(f12_frob2(t), t);
-    return f12_pow(t, HARD_EXP, 12);
+    return f12_pow(t, PAIRING_HARD_EXP, host::PAIRING_HARD_EXP_LIMBS);
 }
 
 // ================================================================================================ G1 on the host (XYZZ)
-struct X1 { Fe x, y, zz, zzz; };
+struct X1 { Fq x, y, zz, zzz; };
 inline bool x1_inf(const X1 &p) { return host::is_zero(p.zz); }
 inline X1 x1_zero() { X1 p; memset(&p, 0, sizeof p); return p; }
 inline X1 x1_from(const Pt &a) {
@@ -269,8 +289,8 @@ inline X1 x1_from(const Pt &a) {
 }
 X1 x1_dbl(const X1 &p) {
     if (x1_inf(p)) return p;
-    Fe u = qadd(p.y, p.y), v = qmul(u, u), w = qmul(u, v), s = qmul(p.x, v);
-    Fe xx = qmul(p.x, p.x), m = qadd(qadd(xx, xx), xx);
+    Fq u = qadd(p.y, p.y), v = qmul(u, u), w = qmul(u, v), s = qmul(p.x, v);
+    Fq xx = qmul(p.x, p.x), m = qadd(qadd(xx, xx), xx);
     X1 r;
     r.x = qsub(qsub(qmul(m, m), s), s);
     r.y = qsub(qmul(m, qsub(s, r.x)), qmul(w, p.y));
@@ -281,10 +301,10 @@ X1 x1_dbl(const X1 &p) {
 X1 x1_add(const X1 &a, const X1 &b) {
     if (x1_inf(a)) return b;
     if (x1_inf(b)) return a;
-    Fe u1 = qmul(a.x, b.zz), u2 = qmul(b.x, a.zz), s1 = qmul(a.y, b.zzz), s2 = qmul(b.y, a.zzz);
-    Fe p = qsub(u2, u1), r = qsub(s2, s1);
+    Fq u1 = qmul(a.x, b.zz), u2 = qmul(b.x, a.zz), s1 = qmul(a.y, b.zzz), s2 = qmul(b.y, a.zzz);
+    Fq p = qsub(u2, u1), r = qsub(s2, s1);
     if (host::is_zero(p)) return host::is_zero(r) ? x1_dbl(a) : x1_zero();
-    Fe pp = qmul(p, p), ppp = qmul(p, pp), q = qmul(u1, pp);
+    Fq pp = qmul(p, p), ppp = qmul(p, pp), q = qmul(u1, pp);
     X1 o;
     o.x = qsub(qsub(qsub(qmul(r, r), ppp), q), q);
     o.y = qsub(qmul(r, qsub(q, o.x)), qmul(s1, ppp));
@@ -307,8 +327,8 @@ Pt x1_affine(const X1 &p) {
     Pt r;
     r.inf = x1_inf(p);
     if (r.inf) { r.x = qzero(); r.y = qzero(); return r; }
-    Fe zi = host::inv(p.zzz, FQ);
-    Fe zzi = qmul(zi, p.zz);
+    Fq zi = host::inv(p.zzz, FQ);
+    Fq zzi = qmul(zi, p.zz);
     zzi = qmul(zzi, zzi);
     r.x = qmul(p.x, zzi);
     r.y = qmul(p.y, zi);
@@ -317,44 +337,97 @@ Pt x1_affine(const X1 &p) {
 Pt pt_neg(const Pt &p) { Pt r = p; if (!p.inf) r.y = qneg(p.y); return r; }
 bool g1_on_curve(const Pt &p) {
     if (p.inf) return true;
-    return feq(qmul(p.y, p.y), qadd(qmul(qmul(p.x, p.x), p.x), q_small(3)));
+    return qeq(qmul(p.y, p.y), qadd(qmul(qmul(p.x, p.x), p.x), q_small(host::G1_COEFF_B)));
 }
 
-// GroupAffine::deserialize (compressed, ark-ec 0.3): x little endian, bit 6 of the last byte = infinity, bit 7 = (y > -y)
-bool g1_decompress(const uint8_t in[32], Pt *out) {
-    Fe x;
-    memcpy(x.l, in, 32);
-    const bool inf = (x.l[3] >> 62) & 1, positive = (x.l[3] >> 63) & 1;
-    x.l[3] &= ~(3ULL << 62);
+// a square root in Fq, if there is one: a^((q + 1) / 4) when q = 3 mod 4 (BN254, BLS12-381), Tonelli-Shanks otherwise
+// (BLS12-377: q - 1 = 2^46 t); the exponents are derived from the modulus
+bool fq_sqrt(const Fq &a, Fq *out) {
+    if (host::is_zero(a)) { *out = a; return true; }
+    constexpr int L = host::FQ_L;
+    auto shr = [](uint64_t *v, unsigned k) {                // v >>= k, 0 < k < 64
+        for (int i = 0; i < L; ++i) v[i] = (v[i] >> k) | (i + 1 < L ? v[i + 1] << (64 - k) : 0);
+    };
+    uint64_t e[L];
+    memcpy(e, FQ.p, sizeof e);
+    if ((FQ.p[0] & 3) == 3) {
+        e[0] += 1;                                          // q + 1: no carry, q ends in ...11
+        shr(e, 2);
+        Fq y = host::pow(a, e, FQ);
+        if (!qeq(qmul(y, y), a)) return false;
+        *out = y;
+        return true;
+    }
+    e[0] -= 1;                                              // q - 1 = 2^s t
+    unsigned sbits = 0;
+    while (!(e[0] & 1)) { shr(e, 1); ++sbits; }             // e = t (odd)
+    uint64_t half[L];
+    memcpy(half, FQ.p, sizeof half);
+    half[0] -= 1;
+    shr(half, 1);                                           // (q - 1) / 2: Euler's criterion
+    const Fq one = host::one(FQ), minus_one = qneg(one);
+    if (!qeq(host::pow(a, half, FQ), one)) return false;
+    Fq z = q_small(2);
+    while (!qeq(host::pow(z, half, FQ), minus_one)) z = qadd(z, one);
+    uint64_t t1[L];
+    memcpy(t1, e, sizeof t1);
+    t1[0] += 1;                                             // (t + 1) / 2
+    if (t1[0] == 0) for (int i = 1; i < L && ++t1[i] == 0; ++i) {}
+    shr(t1, 1);
+    unsigned m = sbits;
+    Fq c = host::pow(z, e, FQ), x = host::pow(a, t1, FQ), b = host::pow(a, e, FQ);
+    while (!qeq(b, one)) {
+        unsigned i = 0;
+        Fq b2 = b;
+        while (!qeq(b2, one)) { b2 = qmul(b2, b2); ++i; }
+        if (i >= m) return false;
+        Fq g = c;
+        for (unsigned k = 0; k + i + 1 < m; ++k) g = qmul(g, g);
+        m = i;
+        c = qmul(g, g);
+        x = qmul(x, g);
+        b = qmul(b, c);
+    }
+    *out = x;
+    return true;
+}
+
+// GroupAffine::deserialize (compressed, ark-ec 0.3): x little endian (32 / 48 bytes), bit 6 of the last byte = infinity,
+// bit 7 = (y > -y)
+bool g1_decompress(const uint8_t *in /* FQB bytes */, Pt *out) {
+    constexpr int L = host::FQ_L;
+    Fq x;
+    memcpy(x.l, in, FQB);
+    const bool inf = (x.l[L - 1] >> 62) & 1, positive = (x.l[L - 1] >> 63) & 1;
+    x.l[L - 1] &= ~(3ULL << 62);
     if (inf && positive) return false;                     // SWFlags::from_u8: both flag bits set is no valid flag
-    if (host::ge(x.l, FQ.p)) return false;                 // the x field must be canonical, also under the infinity flag
+    if (host::ge<L>(x.l, FQ.p)) return false;              // the x field must be canonical, also under the infinity flag
     if (inf) { out->inf = true; out->x = qzero(); out->y = qzero(); return true; }
-    Fe r2;
-    memcpy(r2.l, FQ.r2, 32);
-    Fe xm = host::mul(x, r2, FQ);
-    Fe rhs = qadd(qmul(qmul(xm, xm), xm), q_small(3));
-    Fe y = host::pow(rhs, SQRT_EXP, FQ);                  // q = 3 mod 4
-    if (!feq(qmul(y, y), rhs)) return false;               // x is not on the curve
-    Fe one = {{1, 0, 0, 0}};
-    Fe yc = host::mul(y, one, FQ), nyc;
-    host::sub_raw(nyc.l, FQ.p, yc.l);
-    if (host::is_zero(yc)) memset(nyc.l, 0, 32);
+    Fq xm = q_from_canon(x.l);
+    Fq rhs = qadd(qmul(qmul(xm, xm), xm), q_small(host::G1_COEFF_B));
+    Fq y;
+    if (!fq_sqrt(rhs, &y)) return false;                   // x is not on the curve
+    Fq yc = q_canonical(y), nyc;
+    host::sub_raw<L>(nyc.l, FQ.p, yc.l);
+    if (host::is_zero(yc)) memset(nyc.l, 0, sizeof nyc.l);
     bool gt = false;
-    for (int i = 3; i >= 0; --i) if (yc.l[i] != nyc.l[i]) { gt = yc.l[i] > nyc.l[i]; break; }
+    for (int i = L - 1; i >= 0; --i) if (yc.l[i] != nyc.l[i]) { gt = yc.l[i] > nyc.l[i]; break; }
     out->inf = false;
     out->x = xm;
     out->y = gt == positive ? y : qneg(y);
     return true;
 }
 
-G2 g2_from(const uint64_t v[16]) {
+constexpr int G2_W = 4 * host::FQ_L;          // 64-bit words of an affine G2 point at the C boundary: x.c0 x.c1 y.c0 y.c1 (16 / 24)
+G2 g2_from(const uint64_t *v /* G2_W words */) {
+    constexpr int L = host::FQ_L;
     G2 p;
-    p.x = {fe_from(v), fe_from(v + 4)};
-    p.y = {fe_from(v + 8), fe_from(v + 12)};
+    p.x = {fq_from(v), fq_from(v + L)};
+    p.y = {fq_from(v + 2 * L), fq_from(v + 3 * L)};
     p.inf = f2_is_zero(p.x) && f2_is_zero(p.y);
     return p;
 }
-bool fq_canonical_mont(const Fe &m) { return !host::ge(m.l, FQ.p); }
+bool fq_canonical_mont(const Fq &m) { return !host::ge<host::FQ_L>(m.l, FQ.p); }
 
 bool pairing_product_is_one(const Pt *g1, const G2 *g2, size_t k) {
     F12 f = f12_one();
@@ -377,8 +450,8 @@ bool kzg_check(const Pt *commits, const Fe *values, size_t k, const Fe &point, c
         v = fadd(v, fmul(chal, values[i]));
         chal = fmul(chal, eta);
     }
-    Pt gen;
-    gen.inf = false; gen.x = q_small(1); gen.y = q_small(2);
+    Pt gen;                                               // the G1 generator: powers_of_g[0] of the committer key
+    gen.inf = false; gen.x = fq_from(host::G1_GEN_X); gen.y = fq_from(host::G1_GEN_Y);
     X1 a = x1_add(x1_add(c, x1_mul(fneg(v), gen)), x1_mul(point, w));
     Pt g1s[2] = {x1_affine(a), pt_neg(w)};
     G2 g2s[2] = {h, beta_h};
@@ -389,9 +462,9 @@ bool kzg_check(const Pt *commits, const Fe *values, size_t k, const Fe &point, c
 
 extern "C" {
 
-// k * Q on the twist E'(Fq2): y^2 = x^3 + 3 / (9 + i), affine double-and-add (one Fq2 inversion per step; setup-time only).
+// k * Q on the twist E'(Fq2) (BN254: y^2 = x^3 + 3 / (9 + i)), affine double-and-add (one Fq2 inversion per step; setup-time only).
 // KZG10::setup's beta_h = beta * h for a synthetic SRS whose trapdoor is known (ark-poly-commit 0.3 kzg10::setup).
-int zkb_g2_mul(const uint64_t g2_xy[16], const uint64_t scalar_canonical[4], uint64_t out_xy[16]) {
+int zkb_g2_mul(const uint64_t *g2_xy, const uint64_t scalar_canonical[4], uint64_t *out_xy) {
     if (!g2_xy || !scalar_canonical || !out_xy) return ZKB_ERR_INVALID;
     const G2 q = g2_from(g2_xy);
     if (!g2_on_curve(q)) return ZKB_ERR_INVALID;
@@ -420,26 +493,26 @@ int zkb_g2_mul(const uint64_t g2_xy[16], const uint64_t scalar_canonical[4], uin
         acc = add(acc, acc);
         if ((scalar_canonical[bit >> 6] >> (bit & 63)) & 1) acc = add(acc, q);
     }
-    if (acc.inf) { memset(out_xy, 0, 128); return ZKB_OK; }
-    memcpy(out_xy, acc.x.c0.l, 32); memcpy(out_xy + 4, acc.x.c1.l, 32);
-    memcpy(out_xy + 8, acc.y.c0.l, 32); memcpy(out_xy + 12, acc.y.c1.l, 32);
+    if (acc.inf) { memset(out_xy, 0, 8 * G2_W); return ZKB_OK; }
+    constexpr int L = host::FQ_L;
+    memcpy(out_xy, acc.x.c0.l, FQB); memcpy(out_xy + L, acc.x.c1.l, FQB);
+    memcpy(out_xy + 2 * L, acc.y.c0.l, FQB); memcpy(out_xy + 3 * L, acc.y.c1.l, FQB);
     return ZKB_OK;
 }
 
-int zkb_pairing(const uint64_t g1_xy[8], const uint64_t g2_xy[16], uint64_t out_canonical[48]) {
+int zkb_pairing(const uint64_t *g1_xy, const uint64_t *g2_xy, uint64_t *out_canonical /* 12 x fq_words */) {
     if (!g1_xy || !g2_xy || !out_canonical) return ZKB_ERR_INVALID;
     Pt p;
-    p.x = fe_from(g1_xy); p.y = fe_from(g1_xy + 4);
+    p.x = fq_from(g1_xy); p.y = fq_from(g1_xy + AFF_W / 2);
     p.inf = host::is_zero(p.x) && host::is_zero(p.y);
     G2 q = g2_from(g2_xy);
     if (!fq_canonical_mont(p.x) || !fq_canonical_mont(p.y) || !g1_on_curve(p) || !g2_on_curve(q)) return ZKB_ERR_INVALID;
     const F12 ml = miller_loop(q, p.x, p.y, p.inf);
     F12 e = final_exponentiation(ml);
     if (!f12_eq(e, final_exponentiation_plain(ml))) return ZKB_ERR_INVALID;      // the split exponentiation against its definition
-    Fe one = {{1, 0, 0, 0}};
     for (int i = 0; i < 12; ++i) {
-        Fe c = host::mul(e.c[i], one, FQ);
-        memcpy(out_canonical + 4 * i, c.l, 32);
+        Fq c = q_canonical(e.c[i]);
+        memcpy(out_canonical + host::FQ_L * i, c.l, FQB);
     }
     return ZKB_OK;
 }
@@ -451,41 +524,43 @@ int zkb_pairing_product_is_one(const uint64_t *g1_xy, const uint64_t *g2_xy, siz
     std::vector<Pt> ps(count);
     std::vector<G2> qs(count);
     for (size_t i = 0; i < count; ++i) {
-        ps[i].x = fe_from(g1_xy + 8 * i); ps[i].y = fe_from(g1_xy + 8 * i + 4);
+        ps[i].x = fq_from(g1_xy + AFF_W * i); ps[i].y = fq_from(g1_xy + AFF_W * i + AFF_W / 2);
         ps[i].inf = host::is_zero(ps[i].x) && host::is_zero(ps[i].y);
-        qs[i] = g2_from(g2_xy + 16 * i);
+        qs[i] = g2_from(g2_xy + G2_W * i);
         if (!g1_on_curve(ps[i]) || !g2_on_curve(qs[i])) return ZKB_ERR_INVALID;
     }
     *is_one = pairing_product_is_one(ps.data(), qs.data(), count) ? 1 : 0;
     return ZKB_OK;
 }
 
-int zkb_plonk_verify(size_t n, const uint64_t *pi_roots_mont, size_t n_pi, const uint64_t vk_xy[80], const int vk_inf[10],
-                     const uint64_t *pub_inputs_mont, const uint8_t proof[802], const uint64_t g2_h[16], const uint64_t g2_beta_h[16],
+int zkb_plonk_verify(size_t n, const uint64_t *pi_roots_mont, size_t n_pi, const uint64_t *vk_xy, const int vk_inf[10],
+                     const uint64_t *pub_inputs_mont, const uint8_t *proof, const uint64_t *g2_h, const uint64_t *g2_beta_h,
                      int transcript_kind) {
     if (!vk_xy || !proof || !g2_h || !g2_beta_h || ((!pi_roots_mont || !pub_inputs_mont) && n_pi)) return ZKB_ERR_INVALID;
     if (n < 2 || (n & (n - 1)) || n > ((size_t)1 << 28) || (transcript_kind != 0 && transcript_kind != 1)) return ZKB_ERR_INVALID;
+    if (transcript_kind == 1 && ZKB_CURVE != ZKB_CURVE_BN254) return ZKB_ERR_UNSUPPORTED;          // EthereumTranscript is bound to Bn254 upstream
     unsigned log_n = 0;
     while (((size_t)1 << log_n) < n) ++log_n;
     // ---- inputs
     Pt V[10];                                             // q_m q_l q_r q_o q_c sigma1 sigma2 sigma3 q_lookup q_table
     for (int k = 0; k < 10; ++k) {
-        V[k].x = fe_from(vk_xy + 8 * k); V[k].y = fe_from(vk_xy + 8 * k + 4);
+        V[k].x = fq_from(vk_xy + AFF_W * k); V[k].y = fq_from(vk_xy + AFF_W * k + AFF_W / 2);
         V[k].inf = (vk_inf && vk_inf[k]) || (host::is_zero(V[k].x) && host::is_zero(V[k].y));
         if (!V[k].inf && (!fq_canonical_mont(V[k].x) || !fq_canonical_mont(V[k].y) || !g1_on_curve(V[k]))) return ZKB_ERR_INVALID;
     }
     const G2 h = g2_from(g2_h), beta_h = g2_from(g2_beta_h);
     if (!g2_on_curve(h) || !g2_on_curve(beta_h)) return ZKB_ERR_INVALID;
     Pt C[11], aw, saw;                                    // a b c t h1 h2 z1 z2 q_lo q_mid q_hi  (proof.rs:112-154)
-    for (int k = 0; k < 11; ++k) if (!g1_decompress(proof + 32 * k, &C[k])) return ZKB_ERR_INVALID;
-    if (!g1_decompress(proof + 352, &aw) || !g1_decompress(proof + 385, &saw) || proof[384] != 0 || proof[417] != 0) return ZKB_ERR_INVALID;
+    for (int k = 0; k < 11; ++k) if (!g1_decompress(proof + FQB * k, &C[k])) return ZKB_ERR_INVALID;
+    if (!g1_decompress(proof + 11 * FQB, &aw) || !g1_decompress(proof + 12 * FQB + 1, &saw) || proof[12 * FQB] != 0 || proof[13 * FQB + 1] != 0)
+        return ZKB_ERR_INVALID;                                   // kzg10::Proof { w, random_v: None } twice
     Fe E[12];                                             // a b c sigma1 sigma2 z1_next q_lookup t t_next z2_next h1_next h2
     {
         Fe r2;
         memcpy(r2.l, FR.r2, 32);
         for (int k = 0; k < 12; ++k) {
             Fe c;
-            memcpy(c.l, proof + 418 + 32 * k, 32);
+            memcpy(c.l, proof + 13 * FQB + 2 + 32 * k, 32);
             if (host::ge(c.l, FR.p)) return ZKB_ERR_INVALID;
             E[k] = host::mul(c, r2, FR);
         }
