@@ -162,7 +162,7 @@ int zkb_lookup_multisets_dev(zkb_ctx *ctx, unsigned log_n, const uint64_t *table
                              const uint64_t *c_evals_dev, uint64_t *t_dev, uint64_t *f_dev, uint64_t *h1_dev, uint64_t *h2_dev,
                              int *status_host) {
     if (!ctx) return ZKB_ERR_INVALID;
-    if (log_n > 31) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_lookup_multisets_dev: log_n out of range");
+    if (log_n > 30) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_lookup_multisets_dev: log_n out of range (the bucket counts are 32-bit: 2n must stay below 2^32)");
     const size_t n = (size_t)1 << log_n;
     if ((!table_host && table_len) || !q_lookup_evals_dev || !c_evals_dev || !t_dev || !f_dev || !h1_dev || !h2_dev)
         ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_lookup_multisets_dev: null argument");

@@ -17,7 +17,8 @@ from . import field
 from .transcript import TRANSCRIPTS, MerlinTranscript, fr_bytes
 
 # The moduli and encodings are the selected curve's (field.use_curve / field.curve): BN254 by default; BLS12-381 / BLS12-377
-# (what plonk.rs:226-254 instantiates) through this Python round schedule -- the C++ driver behind NativeProver is BN254-only.
+# (what plonk.rs:226-254 instantiates) run through this Python round schedule and through NativeProver (the C++ driver of that
+# curve's build of the library).
 
 
 def __getattr__(name):
