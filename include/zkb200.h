@@ -9,8 +9,8 @@
  * Curves.  The reference is generic over the pairing engine (its own full test runs on Bls12_381 and Bls12_377,
  * plonk-core/src/plonk.rs:226-254; the CLI fixes Bn254, bin/src/instance.rs:7-10) and Rust monomorphises per curve.  This library
  * is compiled once per curve with identical entry points: libzkb200.so (BN254: everything below), libzkb200_bls12_381.so and
- * libzkb200_bls12_377.so (everything but the reference CLI's key files and EthereumTranscript, which are BN254's and return
- * ZKB_ERR_UNSUPPORTED there).  zkb_curve_info tells a caller which one it loaded
+ * libzkb200_bls12_377.so (everything but EthereumTranscript, which is bound to Bn254 upstream and answers ZKB_ERR_UNSUPPORTED
+ * there; the key files are the same derive(CanonicalSerialize) layouts with 48-byte Fq).  zkb_curve_info tells a caller which one it loaded
  * and the element widths: array sizes written below as [8] / [16] / [80] are the BN254 ones (fq_words = 4); on the BLS12 curves
  * an affine point is 12 words and an XYZZ partial sum 24 (fq_words = 6).  Scalars are 4 words on every curve.
  *
@@ -67,8 +67,8 @@ ZKB_API const char *zkb_last_error(zkb_ctx *ctx);
 ZKB_API const char *zkb_version(void);
 /* Which curve this shared object was compiled for (the `E: PairingEngine` of the reference's generics): curve_id 0 = BN254,
  * 1 = BLS12-381, 2 = BLS12-377; 64-bit words of a scalar and of a base-field element; bit length of r; has_prover = 1 when
- * the protocol driver (zkb_plonk_setup / zkb_plonk_prove ..) is compiled in: every build (as is the verifier with the curve's own pairing); the key files are
- * BN254's.  Any pointer may be NULL.  Needs no context and no GPU. */
+ * the protocol driver (zkb_plonk_setup / zkb_plonk_prove ..) is compiled in: every build (as are the verifier with the curve's own pairing and the
+ * key-file readers / writers).  Any pointer may be NULL.  Needs no context and no GPU. */
 ZKB_API int zkb_curve_info(int *curve_id, int *fr_words, int *fq_words, int *fr_bits, int *has_prover);
 /* The curve's G1 generator (ark-* 0.3 G1_GENERATOR_X / _Y), affine, Montgomery form: 2 x fq_words words. */
 ZKB_API int zkb_g1_generator(uint64_t *out_xy);
@@ -303,7 +303,9 @@ ZKB_API int zkb_g2_mul(const uint64_t g2_xy[16], const uint64_t scalar_canonical
  * memory side: this library's forms (Montgomery limbs, identity = (0, 0)).  The *_file_* functions are host code
  * and need no GPU.  The epk file is never read: its coset tables are rebuilt in HBM (10 coset NTTs).
  * ck = sonic_pc::CommitterKey<Bn254> as PC::trim(pp, 4n, 0, None) leaves it (plonk.rs:79-85): powers_of_g,
- * powers_of_gamma_g, three `None`s, max_degree. */
+ * powers_of_gamma_g, three `None`s, max_degree.  On the BLS12 builds the same layouts with 48-byte base-field elements (a G1
+ * point is 96 file bytes and 12 words in memory, a G2 point 192 bytes and 24 words): the key types are generic over the pairing
+ * engine (keys/mod.rs:29-40,180-203).  Array sizes below are BN254's. */
 ZKB_API int zkb_ck_file_info(const char *path, size_t *n_powers, size_t *max_degree);
 ZKB_API int zkb_ck_file_read(const char *path, size_t first, size_t count, uint64_t *xy_mont_out);
 ZKB_API int zkb_ck_file_write(const char *path, const uint64_t *xy_mont, size_t n_powers, const uint64_t *gamma_xy_mont, size_t n_gamma,

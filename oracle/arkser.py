@@ -15,11 +15,24 @@ import struct
 
 Q = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
 R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+FQ_BYTES = 32            # base-field element: 32 bytes on BN254 (the CLI's curve), 48 on BLS12-381 / BLS12-377 (use_curve)
 PK_ORDER = ("q_m", "q_l", "q_r", "q_o", "q_c", "sigma1", "sigma2", "sigma3", "q_lookup", "q_table")
+
+
+def use_curve(name):
+    """the same derive(CanonicalSerialize) layouts on another curve the reference instantiates (plonk.rs:226-254)"""
+    global Q, R, FQ_BYTES
+    from oracle import pyref
+    R, Q = pyref._CURVES[name][0], pyref._CURVES[name][1]
+    FQ_BYTES = 8 * ((Q.bit_length() + 63) // 64)
 
 
 def u64(v):
     return struct.pack("<Q", v)
+
+
+def fq(v):
+    return int(v).to_bytes(FQ_BYTES, "little")
 
 
 def fe(v):
@@ -28,10 +41,10 @@ def fe(v):
 
 def g1(pt):
     if pt is None:
-        b = bytearray(fe(0) + fe(1))
-        b[63] |= 1 << 6
+        b = bytearray(fq(0) + fq(1))
+        b[-1] |= 1 << 6
         return bytes(b)
-    return fe(pt[0]) + fe(pt[1])
+    return fq(pt[0]) + fq(pt[1])
 
 
 def vec(items, enc):
@@ -66,17 +79,17 @@ def committer_key(powers, gamma_powers, max_degree):
 def g2(pt):
     """G2Affine, uncompressed: x.c0 x.c1 y.c0 y.c1, flags in the last byte."""
     if pt is None:
-        b = bytearray(fe(0) + fe(0) + fe(1) + fe(0))
-        b[127] |= 1 << 6
+        b = bytearray(fq(0) + fq(0) + fq(1) + fq(0))
+        b[-1] |= 1 << 6
         return bytes(b)
     (x0, x1), (y0, y1) = pt
-    return fe(x0) + fe(x1) + fe(y0) + fe(y1)
+    return fq(x0) + fq(x1) + fq(y0) + fq(y1)
 
 
 def sonic_verifier_key(g, gamma_g, h, beta_h, supported_degree, max_degree, n_ell=3):
     """cvk as sonic_pc::VerifierKey derives it; the two G2Prepared fields (Vec of Fq2 triples + infinity flag) are filled
     with placeholder coefficients: no reader in this repository looks past beta_h."""
-    prepared = vec([((1, 2), (3, 4), (5, 6))] * n_ell, lambda t: b"".join(fe(c) for pair in t for c in pair)) + b"\x00"
+    prepared = vec([((1, 2), (3, 4), (5, 6))] * n_ell, lambda t: b"".join(fq(c) for pair in t for c in pair)) + b"\x00"
     return g1(g) + g1(gamma_g) + g2(h) + g2(beta_h) + prepared + prepared + option(None, u64) + u64(supported_degree) + u64(max_degree)
 
 
@@ -100,10 +113,11 @@ class _Rd:
         return v
 
     def g1(self):
-        x = int.from_bytes(self.take(32), "little")
-        y = int.from_bytes(self.take(32), "little")
-        inf = (y >> 254) & 1
-        y &= (1 << 254) - 1
+        x = int.from_bytes(self.take(FQ_BYTES), "little")
+        y = int.from_bytes(self.take(FQ_BYTES), "little")
+        top = 8 * FQ_BYTES - 2
+        inf = (y >> top) & 1
+        y &= (1 << top) - 1
         return None if inf else (x, y)
 
 

@@ -246,12 +246,60 @@ def test_polynomial_utilities(cv):
     assert np.array_equal(ev, eev) and np.array_equal(to_host(quot), eq)
 
 
-def test_bn254_only_entry_points_are_reported_unsupported(cv):
-    """the reference CLI's key files answer ZKB_ERR_UNSUPPORTED on these builds (never a silent fallback)"""
-    ctx, _, _ = cv
-    lib = ctx._lib
-    out = ctypes.c_void_p()
-    assert lib.zkb_plonk_load_keys(ctx._h, b"/nonexistent", b"/nonexistent", 4, ctypes.byref(out)) == -6
+def test_key_files_drive_the_native_prover(cv, tmp_path):
+    """keys/mod.rs:29-40,180-203 on Bls12_381 / Bls12_377: the pk / vk files this curve's build writes equal the independent
+    Python serialisation of the oracle-backend keys (96-byte commitments); a key loaded back from them, with the committer key
+    read from a ck file, proves byte-identically to the key set up from the circuit's columns."""
+    import torch
+    import zkt_plonk_b200 as z
+    from oracle import arkser, plonk_ref, pyref
+    from zkt_plonk_b200 import field, prover, synthetic
+    ctx, o, c = cv
+    field.use_curve(ctx.curve)
+    pyref.use_curve(ctx.curve)
+    arkser.use_curve(ctx.curve)
+    try:
+        P = field.R_MOD
+        tau = 0x2B7E151628AED2A6ABF7158809CF4F3C762E7160F38B4DA56A784D9045190CFE % P
+        circ = synthetic.make_circuit(6, seed=33, table_size=16)
+        n_powers = 4 * circ.n + 1
+        powers, x = [], 1
+        for _ in range(n_powers):
+            powers.append(x)
+            x = x * tau % P
+        d_srs = torch.empty((n_powers, ctx.aff_words), dtype=torch.int64, device="cuda")
+        ctx.g1_fixed_base_mul_dev(ctx.g1_generator(), to_dev(limbs(powers, 4)), n_powers, d_srs)
+        torch.cuda.synchronize()
+        h_srs = to_host(d_srs)
+        kzg = z.GpuKZG10(ctx)
+        kzg.load_committer_key(d_srs)
+        blinders = list(range(900, 919))
+        native = prover.NativeProver(ctx, circ)
+        raw = native.prove_bytes(blinders)
+        pk_path, vk_path, ck_path = tmp_path / "pk", tmp_path / "vk", tmp_path / "ck"
+        native.save_keys(pk_path, vk_path)
+        native.close()
+        obe = plonk_ref.OracleBackend(h_srs)
+        opk, ovk = prover.setup(obe, circ)
+        polys = {name: prover.mont_array_to_ints(opk.polys[name].data[: opk.polys[name].len]) for name in arkser.PK_ORDER}
+        assert pk_path.read_bytes() == arkser.prover_key(polys)
+        assert vk_path.read_bytes() == arkser.verifier_key(ovk.n, ovk.pi_roots, ovk.commits)
+        pts = [prover.point_to_ints(row, not row.any()) for row in h_srs]
+        ck_path.write_bytes(arkser.committer_key(pts, pts[:2], n_powers - 1))
+        ctx.srs_load(d_srs[:8].contiguous())                               # forget the key, then read it from the file
+        kzg.load_committer_key_file(ck_path)
+        assert ctx.srs_size() == n_powers
+        loaded = prover.NativeProver(ctx, circ, key_files=(pk_path, vk_path))
+        try:
+            assert loaded.vk().commits == ovk.commits and loaded.vk().pi_roots == ovk.pi_roots
+            assert loaded.prove_bytes(blinders) == raw
+            assert raw == prover.prove(obe, opk, ovk, circ, blinders).to_bytes()
+        finally:
+            loaded.close()
+    finally:
+        field.use_curve("bn254")
+        pyref.use_curve("bn254")
+        arkser.use_curve("bn254")
 
 
 # ------------------------------------------------------------------------------------------------ whole proofs on the BLS12 curves

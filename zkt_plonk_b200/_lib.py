@@ -1,8 +1,8 @@
 """Loader for libzkb200.so (the C ABI of include/zkb200.h) and its per-curve builds.
 
 One shared object per curve, same entry points (the reference's generics monomorphise per pairing engine, plonk.rs:226-254):
-`lib()` / `lib("bn254")` is libzkb200.so (everything), `lib("bls12_381")` and `lib("bls12_377")` hold everything but the key files and
-the pairing verifier (BN254's: ZKB_ERR_UNSUPPORTED there).
+`lib()` / `lib("bn254")` is libzkb200.so (everything), `lib("bls12_381")` and `lib("bls12_377")` hold everything but
+EthereumTranscript (bound to Bn254 upstream: ZKB_ERR_UNSUPPORTED there).
 
 There is NO CPU fallback: if the shared library is missing the import fails loudly, and if no CUDA device
 is present `Context()` raises.  Nothing under oracle/ is ever imported from here.

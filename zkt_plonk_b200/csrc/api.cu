@@ -117,7 +117,7 @@ const char *zkb_version(void) { return "zkb200 0.1 (sm_100a, " ZKB_CURVE_NAME ")
 // The curve this library was compiled for (one shared object per curve, same entry points): 0 BN254, 1 BLS12-381, 2 BLS12-377;
 // 64-bit words of a scalar (always 4) and of a base-field element (4 or 6: an affine point is twice, an XYZZ partial sum four
 // times that); bit length of the scalar field's modulus; 1 when the prover driver (zkb_plonk_setup / zkb_plonk_prove) is compiled in
-// (every build; the key files and the pairing verifier are BN254's: ZKB_ERR_UNSUPPORTED elsewhere).
+// (every build, like the key files and the pairing verifier; only EthereumTranscript is BN254's: ZKB_ERR_UNSUPPORTED elsewhere).
 int zkb_curve_info(int *curve_id, int *fr_words, int *fq_words, int *fr_bits, int *has_prover) {
     if (curve_id) *curve_id = ZKB_CURVE;
     if (fr_words) *fr_words = host::FR_L;

@@ -6,8 +6,10 @@
 //   usize / u64          8 bytes little endian
 //   bool                 1 byte; Option<T> = bool + T when Some
 //   Vec<T>, String       u64 length + the items (String: its UTF-8 bytes)
-//   Fp256                32 bytes little endian, CANONICAL (not Montgomery) integer
-//   GroupAffine (unchecked = uncompressed)   x (32 B) || y (32 B), SWFlags in the top bits of the last byte:
+//   Fp256 / Fp384        32 / 48 bytes little endian, CANONICAL (not Montgomery) integer (Fr is 32 bytes on every curve; Fq is
+//                        32 bytes on BN254 -- the CLI's curve -- and 48 on BLS12-381 / BLS12-377, the other curves plonk.rs:226-254
+//                        instantiates: the same derive(CanonicalSerialize) layouts with wider base-field elements)
+//   GroupAffine (unchecked = uncompressed)   x || y (FQB bytes each), SWFlags in the top bits of the last byte:
 //                        bit 6 = infinity (arkworks stores the identity as (0, 1, true)); bit 7 unused here
 //   Rc<T>, PhantomData   as T / nothing
 // Types:
@@ -23,7 +25,7 @@
 //         lookup { q_lookup q_table } } of kzg10::Commitment(G1Affine)   (keys/mod.rs:180-203)
 //   cvk = sonic_pc::VerifierKey<Bn254> { g: G1Affine, gamma_g: G1Affine, h: G2Affine, beta_h: G2Affine, prepared_h,
 //         prepared_beta_h: G2Prepared, degree_bounds_and_neg_powers_of_h: Option<..>, supported_degree, max_degree }
-//         [ark-poly-commit 0.3: recalled].  Only the first four fields are read (384 bytes: the verifier needs h and
+//         [ark-poly-commit 0.3: recalled].  Only the first four fields are read (12 FQB = 384 bytes on BN254: the verifier needs h and
 //         beta_h, and derives its own line coefficients); G2Affine = x.c0 x.c1 y.c0 y.c1, flags in the last byte of y.c1.
 // The in-memory side of every function is this library's usual form (Montgomery limbs, identity = (0, 0)).
 // The epk file (13 coset tables, 1.7 GiB at n = 2^20) is never read: the key loader rebuilds those tables in HBM
@@ -40,6 +42,10 @@
 
 using namespace zkb;
 using host::Fe;
+using host::Fq;
+constexpr int QL = host::FQ_L;                // 64-bit words of a base-field element
+constexpr size_t FQB = 8 * QL, PT_BYTES = 2 * FQB;   // bytes of a base-field element / of an uncompressed G1 point in a file
+constexpr int AFF_W = 2 * QL;                 // words of an affine point at the C boundary
 
 namespace {
 
@@ -57,48 +63,50 @@ struct File {
     bool at_eof() { int c = fgetc(f); if (c == EOF) return true; ungetc(c, f); return false; }
 };
 
-inline Fe to_mont(const Fe &canon, const host::Params &P) {
-    Fe r2;
-    memcpy(r2.l, P.r2, 32);
+template <int L> inline host::FeT<L> to_mont(const host::FeT<L> &canon, const host::ParamsT<L> &P) {
+    host::FeT<L> r2;
+    memcpy(r2.l, P.r2, 8 * L);
     return host::mul(canon, r2, P);
 }
-inline Fe from_mont(const Fe &m, const host::Params &P) {
-    Fe one = {{1, 0, 0, 0}};
+template <int L> inline host::FeT<L> from_mont(const host::FeT<L> &m, const host::ParamsT<L> &P) {
+    host::FeT<L> one;
+    memset(one.l, 0, sizeof one.l);
+    one.l[0] = 1;
     return host::mul(m, one, P);
 }
 
-// 64 file bytes -> x || y Montgomery (identity -> zeros).  false: a coordinate is not below the modulus.
+// PT_BYTES file bytes -> x || y Montgomery (identity -> zeros).  false: a coordinate is not below the modulus.
 bool point_from_file(const uint8_t *src, uint64_t *xy) {
-    Fe x, y;
-    memcpy(x.l, src, 32);
-    memcpy(y.l, src + 32, 32);
-    const bool inf = (y.l[3] >> 62) & 1;
-    if (inf && ((y.l[3] >> 63) & 1)) return false;                // SWFlags::from_u8: both flag bits set is no valid flag
-    y.l[3] &= ~(3ULL << 62);
-    if (host::ge(x.l, host::FQ.p) || host::ge(y.l, host::FQ.p)) return false;
-    if (inf) { memset(xy, 0, 64); return true; }
+    Fq x, y;
+    memcpy(x.l, src, FQB);
+    memcpy(y.l, src + FQB, FQB);
+    const bool inf = (y.l[QL - 1] >> 62) & 1;
+    if (inf && ((y.l[QL - 1] >> 63) & 1)) return false;           // SWFlags::from_u8: both flag bits set is no valid flag
+    y.l[QL - 1] &= ~(3ULL << 62);
+    if (host::ge<QL>(x.l, host::FQ.p) || host::ge<QL>(y.l, host::FQ.p)) return false;
+    if (inf) { memset(xy, 0, PT_BYTES); return true; }
     x = to_mont(x, host::FQ);
     y = to_mont(y, host::FQ);
-    memcpy(xy, x.l, 32);
-    memcpy(xy + 4, y.l, 32);
+    memcpy(xy, x.l, FQB);
+    memcpy(xy + QL, y.l, FQB);
     return true;
 }
 void point_to_file(const uint64_t *xy, bool inf, uint8_t *dst) {
     bool zero = inf;
-    if (!zero) { zero = true; for (int i = 0; i < 8; ++i) if (xy[i]) zero = false; }
+    if (!zero) { zero = true; for (int i = 0; i < AFF_W; ++i) if (xy[i]) zero = false; }
     if (zero) {
-        memset(dst, 0, 64);
-        dst[32] = 1;                                              // (0, 1, true)
-        dst[63] |= 1 << 6;
+        memset(dst, 0, PT_BYTES);
+        dst[FQB] = 1;                                             // (0, 1, true)
+        dst[PT_BYTES - 1] |= 1 << 6;
         return;
     }
-    Fe x, y;
-    memcpy(x.l, xy, 32);
-    memcpy(y.l, xy + 4, 32);
+    Fq x, y;
+    memcpy(x.l, xy, FQB);
+    memcpy(y.l, xy + QL, FQB);
     x = from_mont(x, host::FQ);
     y = from_mont(y, host::FQ);
-    memcpy(dst, x.l, 32);
-    memcpy(dst + 32, y.l, 32);
+    memcpy(dst, x.l, FQB);
+    memcpy(dst + FQB, y.l, FQB);
 }
 
 // `count` points, in parallel over a few host threads (2^20 points = 4 M host products).
@@ -109,7 +117,7 @@ bool points_from_file(const uint8_t *src, size_t count, uint64_t *xy) {
     std::vector<std::thread> th;
     for (size_t t = 0; t < T; ++t) {
         const size_t lo = count * t / T, hi = count * (t + 1) / T;
-        auto work = [=, &ok]() { for (size_t i = lo; i < hi; ++i) if (!point_from_file(src + 64 * i, xy + 8 * i)) ok[t] = 0; };
+        auto work = [=, &ok]() { for (size_t i = lo; i < hi; ++i) if (!point_from_file(src + PT_BYTES * i, xy + AFF_W * i)) ok[t] = 0; };
         if (T == 1) work(); else th.emplace_back(work);
     }
     for (auto &x : th) x.join();
@@ -138,7 +146,7 @@ int zkb_ck_file_info(const char *path, size_t *n_powers, size_t *max_degree) {
     uint64_t n, ng, md;
     int rc = ck_open(F, &n);
     if (rc) return rc;
-    if (!F.skip(64 * n) || !F.rd_u64(&ng) || ng > (1ULL << 32) || !F.skip(64 * ng)) return ZKB_ERR_INVALID;
+    if (!F.skip(PT_BYTES * n) || !F.rd_u64(&ng) || ng > (1ULL << 32) || !F.skip(PT_BYTES * ng)) return ZKB_ERR_INVALID;
     // PC::trim without enforced degree bounds: the three Options are None (a key with degree bounds is not one the
     // reference writes; refuse it instead of guessing)
     if (!read_none(F) || !read_none(F) || !read_none(F) || !F.rd_u64(&md) || !F.at_eof()) return ZKB_ERR_INVALID;
@@ -153,12 +161,12 @@ int zkb_ck_file_read(const char *path, size_t first, size_t count, uint64_t *xy_
     uint64_t n;
     int rc = ck_open(F, &n);
     if (rc) return rc;
-    if (first > n || count > n - first || !F.skip(64 * (uint64_t)first)) return ZKB_ERR_INVALID;
+    if (first > n || count > n - first || !F.skip(PT_BYTES * (uint64_t)first)) return ZKB_ERR_INVALID;
     const size_t CH = 1 << 16;
-    std::vector<uint8_t> buf(64 * (count < CH ? count : CH));
+    std::vector<uint8_t> buf(PT_BYTES * (count < CH ? count : CH));
     for (size_t done = 0; done < count;) {
         const size_t m = count - done < CH ? count - done : CH;
-        if (!F.rd(buf.data(), 64 * m) || !points_from_file(buf.data(), m, xy_mont_out + 8 * done)) return ZKB_ERR_INVALID;
+        if (!F.rd(buf.data(), PT_BYTES * m) || !points_from_file(buf.data(), m, xy_mont_out + AFF_W * done)) return ZKB_ERR_INVALID;
         done += m;
     }
     return ZKB_OK;
@@ -169,11 +177,11 @@ int zkb_ck_file_write(const char *path, const uint64_t *xy_mont, size_t n_powers
     if ((!xy_mont && n_powers) || (!gamma_xy_mont && n_gamma)) return ZKB_ERR_INVALID;
     File F(path, "wb");
     if (!F.f) return ZKB_ERR_INVALID;
-    uint8_t b[64];
+    uint8_t b[PT_BYTES];
     bool ok = F.wr_u64(n_powers);
-    for (size_t i = 0; ok && i < n_powers; ++i) { point_to_file(xy_mont + 8 * i, false, b); ok = F.wr(b, 64); }
+    for (size_t i = 0; ok && i < n_powers; ++i) { point_to_file(xy_mont + AFF_W * i, false, b); ok = F.wr(b, PT_BYTES); }
     ok = ok && F.wr_u64(n_gamma);
-    for (size_t i = 0; ok && i < n_gamma; ++i) { point_to_file(gamma_xy_mont + 8 * i, false, b); ok = F.wr(b, 64); }
+    for (size_t i = 0; ok && i < n_gamma; ++i) { point_to_file(gamma_xy_mont + AFF_W * i, false, b); ok = F.wr(b, PT_BYTES); }
     const uint8_t none[3] = {0, 0, 0};
     ok = ok && F.wr(none, 3) && F.wr_u64(max_degree);
     return ok ? ZKB_OK : ZKB_ERR_INVALID;
@@ -189,7 +197,7 @@ int zkb_srs_load_ck_file(zkb_ctx *ctx, const char *path, size_t max_points) {
     if (n == 0) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_srs_load_ck_file: the key holds no powers");
     std::vector<uint64_t> xy;
     try {
-        xy.resize(8 * n);                                          // nothing may throw across the C boundary
+        xy.resize((size_t)AFF_W * n);                              // nothing may throw across the C boundary
     } catch (const std::bad_alloc &) {
         ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_srs_load_ck_file: not enough host memory for the committer key");
     }
@@ -199,26 +207,26 @@ int zkb_srs_load_ck_file(zkb_ctx *ctx, const char *path, size_t max_points) {
 }
 
 // ---- cvk: g, gamma_g (G1) and h, beta_h (G2) from the head of the file
-int zkb_cvk_file_read(const char *path, uint64_t g_xy[8], uint64_t gamma_g_xy[8], uint64_t h_xy[16], uint64_t beta_h_xy[16]) {
+int zkb_cvk_file_read(const char *path, uint64_t *g_xy, uint64_t *gamma_g_xy, uint64_t *h_xy, uint64_t *beta_h_xy) {
     if (!h_xy || !beta_h_xy) return ZKB_ERR_INVALID;
     File F(path, "rb");
     if (!F.f) return ZKB_ERR_INVALID;
-    uint8_t b[384];
-    if (!F.rd(b, 384)) return ZKB_ERR_INVALID;
-    uint64_t tmp[8];
-    if (!point_from_file(b, g_xy ? g_xy : tmp) || !point_from_file(b + 64, gamma_g_xy ? gamma_g_xy : tmp)) return ZKB_ERR_INVALID;
+    uint8_t b[12 * FQB];                                          // g, gamma_g (2 FQB each), h, beta_h (4 FQB each)
+    if (!F.rd(b, sizeof b)) return ZKB_ERR_INVALID;
+    uint64_t tmp[AFF_W];
+    if (!point_from_file(b, g_xy ? g_xy : tmp) || !point_from_file(b + PT_BYTES, gamma_g_xy ? gamma_g_xy : tmp)) return ZKB_ERR_INVALID;
     uint64_t *dst[2] = {h_xy, beta_h_xy};
     for (int k = 0; k < 2; ++k) {
-        const uint8_t *src = b + 128 + 128 * k;
-        Fe c[4];
-        memcpy(c, src, 128);
-        const bool inf = (c[3].l[3] >> 62) & 1;
-        c[3].l[3] &= ~(3ULL << 62);
+        const uint8_t *src = b + 2 * PT_BYTES + 4 * FQB * k;
+        Fq c[4];
+        memcpy(c, src, 4 * FQB);
+        const bool inf = (c[3].l[QL - 1] >> 62) & 1;
+        c[3].l[QL - 1] &= ~(3ULL << 62);
         for (int j = 0; j < 4; ++j) {
-            if (host::ge(c[j].l, host::FQ.p)) return ZKB_ERR_INVALID;
+            if (host::ge<QL>(c[j].l, host::FQ.p)) return ZKB_ERR_INVALID;
             c[j] = to_mont(c[j], host::FQ);
         }
-        if (inf) memset(dst[k], 0, 128); else memcpy(dst[k], c, 128);
+        if (inf) memset(dst[k], 0, 4 * FQB); else memcpy(dst[k], c, 4 * FQB);
     }
     return ZKB_OK;
 }
@@ -286,7 +294,7 @@ int zkb_pk_file_write(const char *path, const uint64_t *const coeffs_mont[10], c
 }
 
 // ---- vk
-int zkb_vk_file_read(const char *path, size_t *n, uint64_t *pi_roots_mont, size_t cap_roots, size_t *n_roots, uint64_t commits_xy[80],
+int zkb_vk_file_read(const char *path, size_t *n, uint64_t *pi_roots_mont, size_t cap_roots, size_t *n_roots, uint64_t *commits_xy,
                      int is_inf[10]) {
     if (!n || !n_roots || !commits_xy) return ZKB_ERR_INVALID;
     File F(path, "rb");
@@ -301,15 +309,15 @@ int zkb_vk_file_read(const char *path, size_t *n, uint64_t *pi_roots_mont, size_
         if (pi_roots_mont && i < cap_roots) { c = to_mont(c, host::FR); memcpy(pi_roots_mont + 4 * i, c.l, 32); }
     }
     for (int k = 0; k < 10; ++k) {
-        uint8_t b[64];
-        if (!F.rd(b, 64)) return ZKB_ERR_INVALID;
-        if (is_inf) is_inf[k] = (b[63] >> 6) & 1;
-        if (!point_from_file(b, commits_xy + 8 * k)) return ZKB_ERR_INVALID;
+        uint8_t b[PT_BYTES];
+        if (!F.rd(b, PT_BYTES)) return ZKB_ERR_INVALID;
+        if (is_inf) is_inf[k] = (b[PT_BYTES - 1] >> 6) & 1;
+        if (!point_from_file(b, commits_xy + AFF_W * k)) return ZKB_ERR_INVALID;
     }
     return F.at_eof() ? ZKB_OK : ZKB_ERR_INVALID;
 }
 
-int zkb_vk_file_write(const char *path, size_t n, const uint64_t *pi_roots_mont, size_t n_roots, const uint64_t commits_xy[80],
+int zkb_vk_file_write(const char *path, size_t n, const uint64_t *pi_roots_mont, size_t n_roots, const uint64_t *commits_xy,
                       const int is_inf[10]) {
     if ((!pi_roots_mont && n_roots) || !commits_xy) return ZKB_ERR_INVALID;
     File F(path, "wb");
@@ -322,9 +330,9 @@ int zkb_vk_file_write(const char *path, size_t n, const uint64_t *pi_roots_mont,
         ok = F.wr(c.l, 32);
     }
     for (int k = 0; ok && k < 10; ++k) {
-        uint8_t b[64];
-        point_to_file(commits_xy + 8 * k, is_inf && is_inf[k], b);
-        ok = F.wr(b, 64);
+        uint8_t b[PT_BYTES];
+        point_to_file(commits_xy + AFF_W * k, is_inf && is_inf[k], b);
+        ok = F.wr(b, PT_BYTES);
     }
     return ok ? ZKB_OK : ZKB_ERR_INVALID;
 }

@@ -543,7 +543,6 @@ int zkb_plonk_pk_from_polys(zkb_ctx *ctx, unsigned log_n, const uint64_t *const 
 int zkb_plonk_load_keys(zkb_ctx *ctx, const char *pk_path, const char *vk_path, size_t table_size, zkb_plonk_pk **out) {
     if (!ctx || !out) return ZKB_ERR_INVALID;
     *out = nullptr;
-    if (ZKB_CURVE != ZKB_CURVE_BN254) ZKB_FAIL(ctx, ZKB_ERR_UNSUPPORTED, "zkb_plonk_load_keys: the key-file readers are BN254's (the CLI's curve)");
     size_t n = 0, n_roots = 0;
     uint64_t vk_xy[10 * AFF_W];
     int vk_inf[10];
@@ -590,7 +589,6 @@ int zkb_plonk_load_keys(zkb_ctx *ctx, const char *pk_path, const char *vk_path, 
 // What `compile` writes (main.rs:106-112), from a key built here: pk and vk files the reference's CLI can read.
 int zkb_plonk_save_keys(zkb_ctx *ctx, const zkb_plonk_pk *pk, const char *pk_path, const char *vk_path) {
     if (!ctx || !pk) return ZKB_ERR_INVALID;
-    if (ZKB_CURVE != ZKB_CURVE_BN254) ZKB_FAIL(ctx, ZKB_ERR_UNSUPPORTED, "zkb_plonk_save_keys: the key-file writers are BN254's (the CLI's curve)");
     if (pk_path) {
         const int file_to_key[10] = {P_QM, P_QL, P_QR, P_QO, P_QC, P_S1, P_S2, P_S3, P_QLK, P_QT};
         std::vector<std::vector<uint64_t>> store(10);
