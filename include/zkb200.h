@@ -134,6 +134,10 @@ ZKB_API int zkb_g1_sum_partials(const uint64_t *xyzz, size_t count, uint64_t out
  * HomomorphicCommitment::multi_scalar_mul (commitment.rs:31-46).  Uses min(len) = n pairs. */
 ZKB_API int zkb_msm_g1_bases(zkb_ctx *ctx, const uint64_t *points_host, const uint64_t *scalars_host, size_t n,
                      uint64_t out_xy[8], int *is_inf);
+/* The same with the bases in HBM too (caller-held points: any committer key, e.g. ipa_pc's ck.comm_key or the folded keys of its
+ * opening rounds).  scalars_mont != 0: the scalars are Montgomery-form coefficients (converted like into_repr first). */
+ZKB_API int zkb_msm_g1_points_dev(zkb_ctx *ctx, const uint64_t *points_dev, const uint64_t *scalars_dev, size_t n, int scalars_mont,
+                          uint64_t out_xy[8], int *is_inf);
 /* kzg10::commit for one polynomial resident in HBM (Montgomery coefficients, as produced by the iNTT):
  * into_repr conversion + MSM against SRS[offset .. offset+n).  Reference: ark-poly-commit 0.3 kzg10::commit as
  * reached from prove.rs:133-135,178-180,249-251,306-308,373-375 (the caller skips leading zero coefficients by
@@ -295,6 +299,21 @@ ZKB_API int zkb_pairing_product_is_one(const uint64_t *g1_xy, const uint64_t *g2
 /* out = k * Q on G2 (k canonical, Q and out as x.c0 x.c1 y.c0 y.c1 Montgomery limbs; identity = zeros).  Host code, setup
  * time only: ark-poly-commit 0.3 kzg10::setup's beta_h = beta * h, needed to verify against a synthetic SRS (bench.py). */
 ZKB_API int zkb_g2_mul(const uint64_t g2_xy[16], const uint64_t scalar_canonical[4], uint64_t out_xy[16]);
+
+/* ---- inner-product-argument commitments (the reference's second PC) ------------------------------------- */
+/* `IPA<G, D>` (plonk-core/src/commitment.rs:49-86) = ark-poly-commit 0.3 ipa_pc::InnerProductArgPC over G1 (the PC of half of
+ * plonk-core/src/test.rs's runs, :73,84).  commit = the MSM above over ck.comm_key.  open folds three vectors of length n = d + 1
+ * (coefficients c, powers of the point z, key G) log2 n times; per round
+ *     L = <c_r, G_l> + <c_r, z_l> h',  R = <c_l, G_r> + <c_l, z_r> h',  x = H(x_prev, L, R),
+ *     c_l += x^-1 c_r,  z_l += x z_r,  G_l += x G_r.
+ * zkb_ipa_round_lr_dev returns the two MSMs and the two inner products of a round (the caller adds the h' terms and hashes:
+ * the transcript stays in the host language); zkb_ipa_round_fold_dev folds in place -- afterwards the first n / 2 entries of
+ * each vector are the next round's.  All vectors live in HBM: c, z = n x 4 words Montgomery, G = n affine points.  n: a power
+ * of two >= 2.  x, x_inv Montgomery (x * x_inv == 1 is checked).  Results are field / group elements: identical to the CPU's. */
+ZKB_API int zkb_ipa_round_lr_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, const uint64_t *z_dev, const uint64_t *key_dev, size_t n,
+                         uint64_t l_xy[8], int *l_inf, uint64_t r_xy[8], int *r_inf, uint64_t ip_l[4], uint64_t ip_r[4]);
+ZKB_API int zkb_ipa_round_fold_dev(zkb_ctx *ctx, uint64_t *coeffs_dev, uint64_t *z_dev, uint64_t *key_dev, size_t n, const uint64_t x[4],
+                           const uint64_t x_inv[4]);
 
 /* ---- the reference CLI's key files ---------------------------------------------------------------------- */
 /* `compile` writes ck / cvk / pk / epk / vk with ark-serialize 0.3 serialize_unchecked (bin/src/parser.rs:16-29,

@@ -1,0 +1,251 @@
+"""The inner-product-argument commitment scheme (the reference's second PC: plonk-core/src/commitment.rs:49-86, run by
+plonk-core/src/test.rs:73,84).
+
+CPU: the restated protocol (oracle/ipa_ref.py) against its defining properties -- an opening checks, anything tampered does
+not, the folded key has its closed form.  GPU (`-m gpu`): the library's round entry points (csrc/ipa.cu, through the C ABI)
+against big-integer definitions bit for bit, and whole openings by zkt_plonk_b200.ipa.GpuIPA equal to the restated ones on
+every curve the reference instantiates.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import ipa_ref, pyref
+
+CURVES = ["bn254", "bls12_381", "bls12_377"]
+
+
+@pytest.fixture
+def on_curve(request):
+    from zkt_plonk_b200 import field
+    field.use_curve(request.param)
+    pyref.use_curve(request.param)
+    yield request.param
+    field.use_curve("bn254")
+    pyref.use_curve("bn254")
+
+
+def host_key(n, seed):
+    rnd = random.Random(seed)
+    ks = [rnd.randrange(1, pyref.R_MOD) for _ in range(n + 1)]
+    pts = [pyref.g1_mul(k, pyref.G1_GEN) for k in ks]
+    return pts[:n], pts[n]
+
+
+# ------------------------------------------------------------------------------------------------ CPU: the restated protocol
+@pytest.mark.parametrize("on_curve", ["bn254", "bls12_381"], indirect=True)
+def test_restated_protocol_properties(on_curve):
+    r = pyref.R_MOD
+    rnd = random.Random(3)
+    n = 8
+    key, h = host_key(n, 11)
+    coeffs = [rnd.randrange(r) for _ in range(6)]                  # shorter than the key: padded with zeros
+    point = rnd.randrange(r)
+    value = sum(c * pow(point, i, r) for i, c in enumerate(coeffs)) % r
+    C = ipa_ref.commit(key, coeffs)
+    assert C == pyref.msm_naive(key[:6], coeffs)
+    proof, challenges = ipa_ref.open_(key, h, coeffs, C, point)
+    l_vec, r_vec, final_key, c = proof
+    assert len(l_vec) == len(r_vec) == 3 and len(set(challenges)) == 3
+    # closed forms of what the folding leaves: G_final = <h-coefficients, G>, c = <coeffs, h-coefficients with inverted challenges>
+    hc = ipa_ref.check_poly_coeffs(challenges)
+    assert final_key == pyref.msm_naive(key, hc)
+    assert ipa_ref.check_poly_eval(challenges, point) == sum(v * pow(point, i, r) for i, v in enumerate(hc)) % r
+    inv_hc = ipa_ref.check_poly_coeffs([pow(x, -1, r) for x in challenges])
+    assert c == sum(a * b for a, b in zip(coeffs + [0, 0], inv_hc)) % r
+    assert ipa_ref.check(key, h, C, point, value, proof)
+    # soundness smoke: every part of the statement and of the proof matters
+    assert not ipa_ref.check(key, h, C, point, (value + 1) % r, proof)
+    assert not ipa_ref.check(key, h, C, (point + 1) % r, value, proof)
+    assert not ipa_ref.check(key, h, pyref.g1_add(C, key[0]), point, value, proof)
+    assert not ipa_ref.check(key, h, C, point, value, (l_vec, r_vec, final_key, (c + 1) % r))
+    assert not ipa_ref.check(key, h, C, point, value, ([l_vec[1], l_vec[0], l_vec[2]], r_vec, final_key, c))
+    assert not ipa_ref.check(key, h, C, point, value, (l_vec, r_vec, pyref.g1_add(final_key, key[1]), c))
+    assert not ipa_ref.check(key, h, C, point, value, (l_vec[:2], r_vec[:2], final_key, c))
+    # the hash is injectable (the byte encodings in front of it are the one recalled part): any oracle gives a sound protocol
+    ctr = [0]
+
+    def other(data):
+        ctr[0] += 1
+        return (int.from_bytes(data[:16], "little") * 2654435761 + ctr[0]) % r or 1
+
+    C2 = ipa_ref.commit(key, coeffs)
+    ctr[0] = 0
+    proof2, ch2 = ipa_ref.open_(key, h, coeffs, C2, point, oracle=other)
+    ctr[0] = 0
+    assert ipa_ref.check(key, h, C2, point, value, proof2, oracle=other) and ch2 != challenges
+    # the zero polynomial: identity commitment, identity cross terms
+    proof0, _ = ipa_ref.open_(key, h, [], None, point)
+    assert proof0[3] == 0 and all(p is None for p in proof0[0]) and ipa_ref.check(key, h, None, point, 0, proof0)
+
+
+def test_challenge_derivation():
+    """compute_random_oracle_challenge: masked Blake2s digests, retried with the next counter until below the modulus."""
+    import hashlib
+    r = pyref.R_MOD
+    seen_retry = False
+    for k in range(64):
+        data = bytes([k]) * 7
+        v = ipa_ref.random_oracle_challenge(data)
+        assert 0 <= v < r
+        first = int.from_bytes(hashlib.blake2s(data + (0).to_bytes(8, "little")).digest(), "little") & ((1 << r.bit_length()) - 1)
+        if first >= r:
+            seen_retry = True
+            assert v != first
+        else:
+            assert v == first
+    assert seen_retry                                              # BN254's r is 0.76 of 2^254: a quarter of the digests retry
+    from zkt_plonk_b200 import ipa
+    assert all(ipa.random_oracle_challenge(bytes([k]) * 7) == ipa_ref.random_oracle_challenge(bytes([k]) * 7) for k in range(16))
+    assert ipa.g1_bytes(None) == ipa_ref.g1_bytes(None) and ipa.g1_bytes((5, 9)) == ipa_ref.g1_bytes((5, 9))
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _ctx(curve):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import zkt_plonk_b200 as z
+    c = z.Context(0, curve=curve)
+    c.set_stream(torch.cuda.current_stream())
+    return c
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to("cuda")
+
+
+def _fr_arr(vals, mont=True):
+    from zkt_plonk_b200 import field
+    return np.array([field.int_to_limbs(field.to_mont(v) if mont else v) for v in vals], dtype=np.uint64).reshape(-1, 4)
+
+
+def _fr_ints(arr):
+    from zkt_plonk_b200 import field
+    a = np.ascontiguousarray(arr).view(np.uint64).reshape(-1, 4)
+    return [field.from_mont(field.limbs_to_int(row)) for row in a]
+
+
+def _device_key(ctx, n, seed):
+    """k_i * G built in HBM; returns (device tensor of n + 1 points, the points as canonical ints)"""
+    import torch
+    from zkt_plonk_b200 import field
+    rnd = random.Random(seed)
+    ks = [rnd.randrange(1, field.R_MOD) for _ in range(n + 1)]
+    out = torch.empty((n + 1, ctx.aff_words), dtype=torch.int64, device="cuda")
+    ctx.g1_fixed_base_mul_dev(ctx.g1_generator(), _dev(_fr_arr(ks, mont=False)), n + 1, out)
+    torch.cuda.synchronize()
+    w = field.FQ_WORDS
+    host = out.cpu().numpy().view(np.uint64)
+    pts = [(field.from_mont(field.limbs_to_int(row[:w]), field.Q_MOD), field.from_mont(field.limbs_to_int(row[w:]), field.Q_MOD)) for row in host]
+    return out, pts, ks
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("on_curve", CURVES, indirect=True)
+def test_gpu_rounds_match_the_definitions(on_curve):
+    """zkb_ipa_round_lr_dev / zkb_ipa_round_fold_dev against Python integers: cross terms, inner products and all three folds,
+    over two consecutive rounds (the second one runs on the folded vectors), n = 2 included."""
+    import torch
+    from zkt_plonk_b200 import field
+    from zkt_plonk_b200.ipa import GpuIPA
+    ctx = _ctx(on_curve)
+    try:
+        r = field.R_MOD
+        rnd = random.Random(17)
+        helper = GpuIPA(ctx)
+        for n in (2, 16, 64):
+            d_key, pts, ks = _device_key(ctx, n, 100 + n)
+            assert pts[0] == pyref.g1_mul(ks[0], pyref.G1_GEN)
+            key = list(pts[:n])
+            c = [rnd.randrange(r) for _ in range(n)]
+            z = [rnd.randrange(r) for _ in range(n)]
+            c[0], z[1 % n] = 0, r - 1
+            d_c, d_z, d_k = _dev(_fr_arr(c)), _dev(_fr_arr(z)), d_key[:n].clone()
+            m = n
+            while m > 1:
+                half = m // 2
+                (l_xy, l_inf), (r_xy, r_inf), ip_l, ip_r = ctx.ipa_round_lr_dev(d_c, d_z, d_k, m)
+                assert helper._pt_ints(l_xy, l_inf) == pyref.msm_naive(key[:half], c[half:m])
+                assert helper._pt_ints(r_xy, r_inf) == pyref.msm_naive(key[half:m], c[:half])
+                assert _fr_ints(ip_l) == [ipa_ref.inner(c[half:m], z[:half])] and _fr_ints(ip_r) == [ipa_ref.inner(c[:half], z[half:m])]
+                x = rnd.randrange(1, r) if m != 16 else 1            # x = 1: the fold is a plain addition
+                xi = pow(x, -1, r)
+                ctx.ipa_round_fold_dev(d_c, d_z, d_k, m, _fr_arr([x])[0], _fr_arr([xi])[0])
+                c = [(a + xi * b) % r for a, b in zip(c[:half], c[half:m])]
+                z = [(a + x * b) % r for a, b in zip(z[:half], z[half:m])]
+                key = [pyref.g1_add(a, pyref.g1_mul(x, b)) for a, b in zip(key[:half], key[half:m])]
+                torch.cuda.synchronize()
+                assert _fr_ints(d_c[:half].cpu().numpy()) == c and _fr_ints(d_z[:half].cpu().numpy()) == z
+                got = d_k[:half].cpu().numpy().view(np.uint64)
+                assert [helper._pt_ints(row, not row.any()) for row in got] == key
+                m = half
+        # the fold's special cases: G_l = -x G_r gives the identity (zeros), G_l = x G_r doubles
+        d_key, pts, ks = _device_key(ctx, 3, 5)
+        x = 12345
+        a = pyref.g1_mul(x, pts[2])
+        arr = helper._pt_array([pyref.g1_neg(a), a, pts[2], pts[2]])
+        d_k = _dev(arr)
+        d_c, d_z = _dev(_fr_arr([1, 2, 3, 4])), _dev(_fr_arr([5, 6, 7, 8]))
+        ctx.ipa_round_fold_dev(d_c, d_z, d_k, 4, _fr_arr([x])[0], _fr_arr([pow(x, -1, r)])[0])
+        torch.cuda.synchronize()
+        got = d_k[:2].cpu().numpy().view(np.uint64)
+        assert not got[0].any() and helper._pt_ints(got[1], False) == pyref.g1_add(a, a)
+        # argument checks: not a power of two, x * x_inv != 1
+        from zkt_plonk_b200._lib import ZkbError
+        with pytest.raises(ZkbError):
+            ctx.ipa_round_lr_dev(d_c, d_z, d_k, 3)
+        with pytest.raises(ZkbError):
+            ctx.ipa_round_fold_dev(d_c, d_z, d_k, 4, _fr_arr([5])[0], _fr_arr([6])[0])
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("on_curve", CURVES, indirect=True)
+def test_gpu_opening_equals_the_restated_one(on_curve):
+    """GpuIPA.open over the device rounds gives the proof the restated CPU protocol gives (same L, R, final key, c), its check
+    accepts it and rejects tampered statements; a 2^12 opening round-trips on the GPU alone."""
+    import torch
+    from zkt_plonk_b200 import field
+    from zkt_plonk_b200.ipa import GpuIPA, IpaProof
+    ctx = _ctx(on_curve)
+    try:
+        r = field.R_MOD
+        rnd = random.Random(23)
+        for n, length in ((16, 16), (32, 21)):
+            d_key, pts, _ = _device_key(ctx, n, 200 + n)
+            pc = GpuIPA(ctx)
+            pc.load_committer_key(d_key[:n].contiguous(), pts[n])
+            coeffs = [rnd.randrange(r) for _ in range(length)]
+            d_coeffs = _dev(_fr_arr(coeffs))
+            point = rnd.randrange(r)
+            C = pc.commit_dev(d_coeffs, length)
+            assert C == ipa_ref.commit(pts[:n], coeffs)
+            proof, value = pc.open(d_coeffs, length, C, point)
+            assert value == sum(c * pow(point, i, r) for i, c in enumerate(coeffs)) % r
+            ref, _ = ipa_ref.open_(pts[:n], pts[n], coeffs, C, point)
+            assert (proof.l_vec, proof.r_vec, proof.final_comm_key, proof.c) == ref
+            assert pc.check(C, point, value, proof) and ipa_ref.check(pts[:n], pts[n], C, point, value, ref)
+            assert not pc.check(C, point, (value + 1) % r, proof)
+            assert not pc.check(C, (point + 1) % r, value, proof)
+            assert not pc.check(C, point, value, IpaProof(proof.l_vec, proof.r_vec, proof.final_comm_key, (proof.c + 1) % r))
+            assert not pc.check(C, point, value, IpaProof(proof.r_vec, proof.l_vec, proof.final_comm_key, proof.c))
+            assert not pc.check(C, point, value, IpaProof(proof.l_vec, proof.r_vec, pts[0], proof.c))
+            assert _fr_ints(d_coeffs.cpu().numpy()) == coeffs          # the caller's polynomial is untouched
+        n = 1 << 12
+        d_key, pts, _ = _device_key(ctx, n, 77)
+        pc = GpuIPA(ctx)
+        pc.load_committer_key(d_key[:n].contiguous(), pts[n])
+        big = np.random.default_rng(5).integers(0, 1 << 62, size=(n, 4), dtype=np.int64)
+        big[:, 3] &= (1 << 58) - 1                                     # below every curve's r: valid Montgomery forms
+        d_coeffs = torch.from_numpy(big).to("cuda")
+        point = rnd.randrange(r)
+        C = pc.commit_dev(d_coeffs, n)
+        proof, value = pc.open(d_coeffs, n, C, point)
+        assert len(proof.l_vec) == 12 and pc.check(C, point, value, proof)
+        assert not pc.check(C, point, (value + 1) % r, proof)
+    finally:
+        ctx.close()

@@ -156,6 +156,29 @@ class Context:
                                                ctypes.byref(inf)))
         return out, bool(inf.value)
 
+    def msm_points_dev(self, points_dev, scalars_dev, n, scalars_mont=True):
+        """MSM over caller-held device points (n affine points) and device scalars (Montgomery coefficients by default)."""
+        out = np.zeros(self.aff_words, dtype=np.uint64)
+        inf = ctypes.c_int(0)
+        self._check(self._lib.zkb_msm_g1_points_dev(self._h, _dev_ptr(points_dev), _dev_ptr(scalars_dev), n, int(bool(scalars_mont)),
+                                                    _host_ptr(out), ctypes.byref(inf)))
+        return out, bool(inf.value)
+
+    # -- inner-product-argument rounds (csrc/ipa.cu)
+    def ipa_round_lr_dev(self, coeffs_dev, z_dev, key_dev, n):
+        """((L affine, is_inf), (R affine, is_inf), <c_r, z_l>, <c_l, z_r>) of one opening round over vectors of length n."""
+        l, r = np.zeros(self.aff_words, dtype=np.uint64), np.zeros(self.aff_words, dtype=np.uint64)
+        li, ri = ctypes.c_int(0), ctypes.c_int(0)
+        ipl, ipr = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+        self._check(self._lib.zkb_ipa_round_lr_dev(self._h, _dev_ptr(coeffs_dev), _dev_ptr(z_dev), _dev_ptr(key_dev), n, _host_ptr(l),
+                                                   ctypes.byref(li), _host_ptr(r), ctypes.byref(ri), _host_ptr(ipl), _host_ptr(ipr)))
+        return (l, bool(li.value)), (r, bool(ri.value)), ipl, ipr
+
+    def ipa_round_fold_dev(self, coeffs_dev, z_dev, key_dev, n, x_mont, x_inv_mont):
+        """c_l += x^-1 c_r, z_l += x z_r, G_l += x G_r in place (x, x_inv: (4,) uint64 Montgomery)."""
+        self._check(self._lib.zkb_ipa_round_fold_dev(self._h, _dev_ptr(coeffs_dev), _dev_ptr(z_dev), _dev_ptr(key_dev), n,
+                                                     _host_ptr(x_mont), _host_ptr(x_inv_mont)))
+
     def commit_dev(self, coeffs_mont_dev, offset, n):
         out = np.zeros(self.aff_words, dtype=np.uint64)
         inf = ctypes.c_int(0)

@@ -1,0 +1,166 @@
+// ipa.cu -- the folding rounds of the inner-product-argument commitment scheme on the device, for sm_100a.
+//
+// The reference's second `PC` (plonk-core/src/commitment.rs:49-86: `IPA<G, D>` = ark-poly-commit 0.3
+// `ipa_pc::InnerProductArgPC`, run by every test of plonk-core/src/test.rs:73,84 on Bls12_381 / Bls12_377 G1) commits with the
+// same MSM as KZG10 (over `ck.comm_key`) and opens with log2(d + 1) folding rounds.  One round of `open`, as the dependency
+// runs it on the CPU over vectors of length n (coefficients c, powers of the point z, committer key G):
+//     L = <c_r, G_l> + <c_r, z_l> h'      R = <c_l, G_r> + <c_l, z_r> h'          (two MSMs of n / 2, two inner products)
+//     x = H(x_prev, L, R)                                                          (stays with the caller: a hash)
+//     c_l += x^-1 c_r      z_l += x z_r      G_l += x G_r  (then batch-normalised to affine)
+// zkb_ipa_round_lr_dev is the first line without the h' term (one fixed point times a scalar: the caller's), and
+// zkb_ipa_round_fold_dev the third.  All three vectors stay in HBM across the rounds; the caller sees two points and two field
+// elements per round.  Results are group / field elements, so they equal the CPU's bit for bit in affine / Montgomery form.
+//
+// The key fold is the expensive half: n / 2 scalar multiplications by the SAME 255-bit challenge per round (n in total over an
+// opening).  One thread per point runs double-and-add over the challenge's bits (uniform across the grid: no divergence) in XYZZ
+// coordinates and normalises its own result.
+#include "ctx.h"
+#include "ec.cuh"
+
+using namespace zkb;
+typedef FrP F;
+
+namespace {
+
+constexpr int AFF_W = 2 * host::FQ_L;
+
+struct Bits256 { uint32_t w[8]; };
+
+// partial[2 * cta] = sum c_r[i] z_l[i], partial[2 * cta + 1] = sum c_l[i] z_r[i] over the CTA's i < half
+__global__ void __launch_bounds__(256) ipa_dots_partial_kernel(const uint4 *c, const uint4 *z, size_t half, uint4 *partial) {
+    __shared__ fe_t sm[2][8];
+    fe_t a0 = fzero<F>(), a1 = fzero<F>();
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < half; i += (size_t)gridDim.x * 256) {
+        const fe_t cl = fload_ro(c + 2 * i), cr = fload_ro(c + 2 * (half + i));
+        const fe_t zl = fload_ro(z + 2 * i), zr = fload_ro(z + 2 * (half + i));
+        a0 = fadd<F>(a0, fmul<F>(cr, zl));
+        a1 = fadd<F>(a1, fmul<F>(cl, zr));
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        fe_t o0, o1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            o0.v[k] = __shfl_down_sync(0xffffffffu, a0.v[k], d);
+            o1.v[k] = __shfl_down_sync(0xffffffffu, a1.v[k], d);
+        }
+        a0 = fadd<F>(a0, o0);
+        a1 = fadd<F>(a1, o1);
+    }
+    if (lane == 0) { sm[0][wid] = a0; sm[1][wid] = a1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        fe_t s = sm[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) s = fadd<F>(s, sm[threadIdx.x][w]);
+        fstore(partial + 2 * (2 * (size_t)blockIdx.x + threadIdx.x), s);
+    }
+}
+
+// out[k] = sum over ctas of partial[2 * cta + k], k = 0, 1 (one CTA of 64 threads: a warp per sum)
+__global__ void __launch_bounds__(64) ipa_dots_total_kernel(const uint4 *partial, uint32_t ctas, uint4 *out) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    fe_t acc = fzero<F>();
+    for (uint32_t i = lane; i < ctas; i += 32) acc = fadd<F>(acc, fload(partial + 2 * (2 * (size_t)i + k)));
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        fe_t o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = __shfl_down_sync(0xffffffffu, acc.v[j], d);
+        acc = fadd<F>(acc, o);
+    }
+    if (lane == 0) fstore(out + 2 * k, acc);
+}
+
+// c_l += x^-1 c_r, z_l += x z_r
+__global__ void __launch_bounds__(256) ipa_fold_scalars_kernel(uint4 *c, uint4 *z, size_t half, fe_t x, fe_t x_inv) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= half) return;
+    fstore(c + 2 * i, fadd<F>(fload(c + 2 * i), fmul<F>(x_inv, fload_ro(c + 2 * (half + i)))));
+    fstore(z + 2 * i, fadd<F>(fload(z + 2 * i), fmul<F>(x, fload_ro(z + 2 * (half + i)))));
+}
+
+// G_l[i] = G_l[i] + x * G_r[i], affine.  `bits` = x as a canonical integer, `top` = index of its highest set bit.
+__global__ void __launch_bounds__(128) ipa_fold_key_kernel(g1a_t *key, uint32_t half, const __grid_constant__ Bits256 bits, int top) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    const g1a_t r = g1a_load(key + half + i);
+    g1x_t acc = g1x_from_affine(r);                               // the top bit
+    for (int b = top - 1; b >= 0; --b) {
+        acc = g1x_double(acc);
+        if ((bits.w[b >> 5] >> (b & 31)) & 1) g1x_add_mixed(acc, r);
+    }
+    g1a_t l;                                                      // this thread overwrites the entry: not through the read-only path
+    l.x = floadn<FqP::N>(&key[i].x);
+    l.y = floadn<FqP::N>(&key[i].y);
+    g1x_add_mixed(acc, l);
+    const g1a_t a = g1x_to_affine(acc);
+    fstore(&key[i].x, a.x);
+    fstore(&key[i].y, a.y);
+}
+
+bool pow2(size_t n) { return n >= 2 && (n & (n - 1)) == 0; }
+
+}  // namespace
+
+// One round's cross terms over c, z (n Montgomery field elements each) and G (n affine points), all in HBM, n a power of two:
+// l_xy = <c_r, G_l>, r_xy = <c_l, G_r> (affine, Montgomery; identity = zeros and *_inf = 1), ip_l = <c_r, z_l>, ip_r = <c_l, z_r>
+// (Montgomery).  The caller adds ip * h' to each point and hashes.
+int zkb_ipa_round_lr_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, const uint64_t *z_dev, const uint64_t *key_dev, size_t n,
+                         uint64_t *l_xy, int *l_inf, uint64_t *r_xy, int *r_inf, uint64_t ip_l[4], uint64_t ip_r[4]) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (!coeffs_dev || !z_dev || !key_dev || !l_xy || !r_xy || !ip_l || !ip_r) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ipa_round_lr_dev: null argument");
+    if (!pow2(n) || n > ((size_t)1 << 30)) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ipa_round_lr_dev: n must be a power of two, 2 <= n <= 2^30");
+    const size_t half = n / 2;
+    uint32_t ctas = (uint32_t)((half + 255) / 256);
+    const uint32_t cap = (uint32_t)ctx->sm_count * 8;
+    if (ctas > cap) ctas = cap;
+    int rc = zkb_reserve(ctx, ctx->poly_ws, ((size_t)2 * ctas + 2) * 32);
+    if (rc) return rc;
+    uint4 *partial = (uint4 *)ctx->poly_ws.p, *total = partial + 2 * (size_t)2 * ctas;
+    ipa_dots_partial_kernel<<<ctas, 256, 0, ctx->stream>>>((const uint4 *)coeffs_dev, (const uint4 *)z_dev, half, partial);
+    ipa_dots_total_kernel<<<1, 64, 0, ctx->stream>>>(partial, ctas, total);
+    ctx->launches += 2;
+    ZKB_CUDA(ctx, cudaGetLastError());
+    uint64_t ips[8];
+    ZKB_CUDA(ctx, cudaMemcpyAsync(ips, total, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    // the MSMs synchronise the stream, which also lands the inner products
+    rc = zkb_msm_g1_points_dev(ctx, key_dev, coeffs_dev + 4 * half, half, 1, l_xy, l_inf);
+    if (rc) return rc;
+    rc = zkb_msm_g1_points_dev(ctx, key_dev + (size_t)AFF_W * half, coeffs_dev, half, 1, r_xy, r_inf);
+    if (rc) return rc;
+    memcpy(ip_l, ips, 32);
+    memcpy(ip_r, ips + 4, 32);
+    return ZKB_OK;
+}
+
+// The round's fold, in place: afterwards the first n / 2 entries of each vector are the next round's vectors.
+// x, x_inv: the round challenge and its inverse, Montgomery form (x * x_inv == 1 is checked).
+int zkb_ipa_round_fold_dev(zkb_ctx *ctx, uint64_t *coeffs_dev, uint64_t *z_dev, uint64_t *key_dev, size_t n, const uint64_t x[4],
+                           const uint64_t x_inv[4]) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (!coeffs_dev || !z_dev || !key_dev || !x || !x_inv) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ipa_round_fold_dev: null argument");
+    if (!pow2(n) || n > ((size_t)1 << 30)) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ipa_round_fold_dev: n must be a power of two, 2 <= n <= 2^30");
+    host::Fe hx, hxi, one;
+    memcpy(hx.l, x, 32);
+    memcpy(hxi.l, x_inv, 32);
+    memset(one.l, 0, 32);
+    one.l[0] = 1;
+    if (host::ge<host::FR_L>(hx.l, host::FR.p) || host::ge<host::FR_L>(hxi.l, host::FR.p)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ipa_round_fold_dev: challenge not reduced");
+    const host::Fe prod = host::mul(host::mul(hx, hxi, host::FR), one, host::FR);      // canonical x * x_inv
+    if (memcmp(prod.l, one.l, 32) != 0) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ipa_round_fold_dev: x * x_inv != 1");
+    const host::Fe canon = host::mul(hx, one, host::FR);
+    Bits256 bits;
+    memcpy(bits.w, canon.l, 32);
+    int top = 255;
+    while (top > 0 && !((bits.w[top >> 5] >> (top & 31)) & 1)) --top;
+    fe_t dx, dxi;
+    memcpy(dx.v, x, 32);
+    memcpy(dxi.v, x_inv, 32);
+    const size_t half = n / 2;
+    ipa_fold_scalars_kernel<<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>((uint4 *)coeffs_dev, (uint4 *)z_dev, half, dx, dxi);
+    ipa_fold_key_kernel<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>((g1a_t *)key_dev, (uint32_t)half, bits, top);
+    ctx->launches += 2;
+    ZKB_CUDA(ctx, cudaGetLastError());
+    return ZKB_OK;
+}

@@ -1396,6 +1396,32 @@ int zkb_msm_g1_bases(zkb_ctx *ctx, const uint64_t *points_host, const uint64_t *
     return ZKB_OK;
 }
 
+// MSM over points the CALLER holds in HBM (any key: the folded committer keys of the inner-product argument's rounds, ipa.cu):
+// scalars on the device too, canonical integers or (scalars_mont != 0) Montgomery form as polynomial coefficients are kept.
+int zkb_msm_g1_points_dev(zkb_ctx *ctx, const uint64_t *points_dev, const uint64_t *scalars_dev, size_t n, int scalars_mont,
+                          uint64_t *out_xy /* AFF_W words */, int *is_inf) {
+    if (!ctx || !out_xy) return ZKB_ERR_INVALID;
+    if ((!points_dev || !scalars_dev) && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1_points_dev: null input");
+    if (!state(ctx)->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "a zkb_commit_push batch is open (its scalars and results live in the buffers this call would reuse): call zkb_commit_finish first");
+    const uint4 *sc = (const uint4 *)scalars_dev;
+    if (scalars_mont && n) {
+        int rc = zkb_reserve(ctx, ctx->stage, n * 32 + 32);
+        if (rc) return rc;
+        fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(sc, (uint4 *)ctx->stage.p, (uint32_t)n);
+        ctx->launches += 1;
+        ZKB_CUDA(ctx, cudaGetLastError());
+        sc = (const uint4 *)ctx->stage.p;
+    }
+    MsmPlan pl;
+    int rc = msm_enqueue(ctx, (const g1a_t *)points_dev, sc, n, ctx->msm_force_c, nullptr, 0, &pl);
+    if (rc) return rc;
+    hec::Pt total;
+    rc = msm_finish(ctx, pl, &total);
+    if (rc) return rc;
+    hec::to_affine(total, out_xy, is_inf);
+    return ZKB_OK;
+}
+
 // sum of `count` XYZZ partial results (multi-GPU combine after the all-gather), affine out
 int zkb_g1_sum_partials(const uint64_t *xyzz, size_t count, uint64_t *out_xy /* AFF_W words */, int *is_inf) {
     if ((!xyzz && count) || !out_xy) return ZKB_ERR_INVALID;
