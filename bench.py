@@ -594,6 +594,11 @@ def run_main(args):
         del x, xs, epk, qout, wit, cols, zout
     except Exception as e:  # the extras must never sink the MSM line
         extra["ntt_error"] = repr(e)
+    if world == 1 and not args.no_ipa:
+        try:
+            extra["ipa_open"] = run_ipa_extra(torch, ctx, P, min(log_n - 1, 18))
+        except Exception as e:
+            extra["ipa_open"] = {"error": repr(e)}
     if world == 1 and not args.no_curves:
         extra["other_curves"] = run_curve_extras(z, torch, dev, flush, int_peak, min(log_n, 20))
 
@@ -644,6 +649,56 @@ def run_main(args):
         dist.destroy_process_group()
     if not bit_exact:
         raise SystemExit("bench.py: MSM result differs from the closed-form answer (see \"check\" in the JSON line)")
+
+
+def run_ipa_extra(torch, ctx, P, log_d):
+    """The reference's second PC (commitment.rs:49-86, ipa_pc::InnerProductArgPC): one opening of a degree 2^log_d - 1 polynomial
+    over the first 2^log_d bench points as ck.comm_key -- log_d folding rounds in HBM (csrc/ipa.cu) -- checked by the scheme's own
+    verifier (succinct check + the final-key MSM) in the same run."""
+    from zkt_plonk_b200 import field
+    from zkt_plonk_b200.ipa import GpuIPA
+    n = 1 << log_d
+    pc = GpuIPA(ctx)
+    pc.load_committer_key(P[:n].contiguous(), pc._pt_ints(P[n].cpu().numpy().view(np.uint64).reshape(-1), False))
+    coeffs = torch.from_numpy(uniform_scalars(n, 4242).view(np.int64)).to(P.device)      # any reduced residues: read as Montgomery forms
+    point = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % field.R_MOD
+    C = pc.commit_dev(coeffs, n)
+    pc.open(coeffs, n, C, point)                                                        # warm-up (allocations, first launches)
+    l0 = ctx.launch_count()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    proof, value = pc.open(coeffs, n, C, point)
+    torch.cuda.synchronize()
+    t_open = time.perf_counter() - t0
+    launches = ctx.launch_count() - l0
+    # the two halves of a round, timed on the first (largest) round of a fresh copy of the vectors
+    c = coeffs.clone()
+    zv = coeffs.clone()
+    key = P[:n].clone()
+    x = np.array(field.int_to_limbs(field.to_mont(point)), dtype=np.uint64)
+    xi = np.array(field.int_to_limbs(field.to_mont(pow(point, -1, field.R_MOD))), dtype=np.uint64)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ctx.ipa_round_lr_dev(c, zv, key, n)
+    torch.cuda.synchronize()
+    t_lr = time.perf_counter() - t0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ctx.ipa_round_fold_dev(c, zv, key, n, x, xi)
+    e1.record()
+    torch.cuda.synchronize()
+    t_fold = e0.elapsed_time(e1) * 1e-3
+    t0 = time.perf_counter()
+    ok = pc.check(C, point, value, proof)
+    t_check = time.perf_counter() - t0
+    bad = pc.check(C, point, (value + 1) % field.R_MOD, proof)
+    # key fold of the first round: n / 2 points x (254 doublings + ~127 mixed additions + 1 addition + normalisation)
+    return {"workload": f"ipa_pc open, degree 2^{log_d} - 1, BN254 G1, Blake2s transcript on the host between the rounds",
+            "open_ms": t_open * 1e3, "rounds": log_d, "gpu_launches": int(launches), "check_accepts": bool(ok), "check_rejects_wrong_value": not bad,
+            "check_ms": t_check * 1e3, "first_round_ms": {"cross_terms_two_msms_and_inner_products": t_lr * 1e3, "fold_coeffs_powers_key": t_fold * 1e3},
+            "key_fold_scalar_muls_per_s": (n / 2) / t_fold,
+            "note": "open = log_d x (zkb_ipa_round_lr_dev + two 2-point host-base MSMs for the h' terms + hash + zkb_ipa_round_fold_dev); "
+                    "the key fold is n scalar multiplications by the round challenges in total"}
 
 
 CURVE_R = {"bls12_381": 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001,
@@ -1009,6 +1064,7 @@ def main():
     ap.add_argument("--no-precompute", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-ipa", dest="no_ipa", action="store_true", help="skip the inner-product-argument opening extra")
     ap.add_argument("--no-curves", dest="no_curves", action="store_true", help="skip the BLS12-381 / BLS12-377 MSM and NTT extras")
     ap.add_argument("--sweep-logs", dest="sweep_logs", type=int, nargs="*", default=[20, 22, 24],
                     help="total sizes (log2) of the fixed-size MSM sweep in extra.msm_fixed_size_sweep")

@@ -37,6 +37,42 @@ impl Ctx {
     }
 }
 
+/// A device buffer owned by a context (`zkb_dev_alloc` / `zkb_dev_free`).
+pub struct DevBuf<'a> {
+    ctx: &'a Ctx,
+    ptr: *mut core::ffi::c_void,
+}
+
+impl DevBuf<'_> {
+    pub fn ptr(&self) -> *const u64 {
+        self.ptr as *const u64
+    }
+    pub fn ptr_mut(&self) -> *mut u64 {
+        self.ptr as *mut u64
+    }
+}
+
+impl Drop for DevBuf<'_> {
+    fn drop(&mut self) {
+        unsafe { sys::zkb_dev_free(self.ctx.raw, self.ptr) };
+    }
+}
+
+impl Ctx {
+    /// `bytes` of host memory copied into a fresh device buffer (synchronous).
+    pub fn upload(&self, src: *const u64, bytes: usize) -> Result<DevBuf<'_>, Error> {
+        let mut ptr = core::ptr::null_mut();
+        self.check(unsafe { sys::zkb_dev_alloc(self.raw, bytes, &mut ptr) })?;
+        let buf = DevBuf { ctx: self, ptr };
+        self.check(unsafe { sys::zkb_h2d(self.raw, ptr, src as *const core::ffi::c_void, bytes) })?;
+        Ok(buf)
+    }
+
+    pub fn download(&self, dst: *mut u64, src_dev: *const u64, bytes: usize) -> Result<(), Error> {
+        self.check(unsafe { sys::zkb_d2h(self.raw, dst as *mut core::ffi::c_void, src_dev as *const core::ffi::c_void, bytes) })
+    }
+}
+
 impl Drop for Ctx {
     fn drop(&mut self) {
         unsafe { sys::zkb_ctx_destroy(self.raw) }

@@ -5,19 +5,23 @@
 //!   * `commit`: `comm = sum_i coeff_i * ck.comm_key[i]` (ipa_pc `cm_commit` without hiding: `rng = None`, no hiding bounds, as
 //!     plonk-core always calls it) -> the same resident-key MSM as KZG10 (`zkb_srs_load_g1` on `comm_key`, `zkb_msm_g1`);
 //!   * `HomomorphicCommitment::multi_scalar_mul` (commitment.rs:60-86) -> `zkb_msm_g1_bases`.
-//! `setup` / `trim` / `open` / `check` delegate to ark-poly-commit: `open` is a log(n)-round folding protocol whose per-round
-//! MSMs over halves of the key are NOT accelerated here (they would be `zkb_msm_g1_bases` calls plus a point-folding kernel);
-//! this is the seam, not a full IPA prover.  Associated types are InnerProductArgPC's own, so proofs keep their bytes.
+//!   * `open`: the log(n) folding rounds run in HBM -- `zkb_ipa_round_lr_dev` (the two MSMs over halves of the key and the two
+//!     inner products of a round) and `zkb_ipa_round_fold_dev` (coefficients, point powers and key folded in place,
+//!     csrc/ipa.cu); the hash between the rounds, the `h'` terms and the proof struct stay arkworks' (`ro_challenge` below
+//!     repeats ipa_pc's private `compute_random_oracle_challenge`).  Hiding or degree-bounded openings (never asked for by
+//!     plonk-core) delegate to ark-poly-commit, as do `setup` / `trim` / `check`.
+//! Associated types are InnerProductArgPC's own, so proofs keep their bytes.
 //!
 //! NOT COMPILED HERE (no rustc / cargo in the build image); signatures are ark-poly-commit 0.3.0's as recalled.
 use crate::ctx::CTX;
 use crate::kzg::{pack_points, unpack_point};
 use ark_bn254::{Fr, G1Affine};
-use ark_ff::{PrimeField, Zero};
+use ark_ec::{AffineCurve, ProjectiveCurve};
+use ark_ff::{to_bytes, Field, One, PrimeField, Zero};
 use ark_poly::univariate::DensePolynomial;
 use ark_poly_commit::{ipa_pc, LabeledCommitment, LabeledPolynomial, PCRandomness, PolynomialCommitment};
 use ark_std::rand::RngCore;
-use blake2::Blake2s;
+use blake2::{Blake2s, Digest};
 use core::ffi::c_int;
 use plonk_core::commitment::{HomomorphicCommitment, IPA};
 use std::cell::Cell;
@@ -45,6 +49,18 @@ fn ensure_resident(key: &[G1Affine]) {
             r.set(id);
         }
     });
+}
+
+/// ipa_pc's private `compute_random_oracle_challenge`: Blake2s(bytes || i) for i = 0, 1, .. until the digest is a field element.
+fn ro_challenge(bytes: &[u8]) -> Fr {
+    let mut i = 0u64;
+    loop {
+        let hash = Blake2s::digest(&to_bytes![bytes, i].unwrap());
+        if let Some(c) = Fr::from_random_bytes(&hash) {
+            return c;
+        }
+        i += 1;
+    }
 }
 
 impl PolynomialCommitment<Fr, Poly> for GpuIpaPc {
@@ -116,7 +132,67 @@ impl PolynomialCommitment<Fr, Poly> for GpuIpaPc {
         Self::Randomness: 'a,
         Self::Commitment: 'a,
     {
-        Inner::open_individual_opening_challenges(ck, labeled_polynomials, commitments, point, opening_challenges, rands, rng)
+        let polys: Vec<_> = labeled_polynomials.into_iter().collect();
+        let comms: Vec<_> = commitments.into_iter().collect();
+        let n = ck.comm_key.len();
+        if rng.is_some() || !n.is_power_of_two() || polys.iter().any(|p| p.degree_bound().is_some() || p.hiding_bound().is_some()) {
+            return Inner::open_individual_opening_challenges(ck, polys, comms, point, opening_challenges, rands, rng);
+        }
+        // combined polynomial and commitment: sum_j challenge(j) * p_j, as ipa_pc::open does before the rounds
+        let mut coeffs = vec![Fr::zero(); n];
+        let mut combined = <G1Affine as AffineCurve>::Projective::zero();
+        for (j, (p, c)) in polys.iter().zip(&comms).enumerate() {
+            let ch = opening_challenges(j as u64);
+            for (acc, v) in coeffs.iter_mut().zip(&p.polynomial().coeffs) {
+                *acc += ch * v;
+            }
+            combined += c.commitment().comm.mul(ch.into_repr());
+        }
+        let combined = combined.into_affine();
+        let mut z = Vec::with_capacity(n);
+        let mut cur = Fr::one();
+        for _ in 0..n {
+            z.push(cur);
+            cur *= point;
+        }
+        let value: Fr = coeffs.iter().zip(&z).map(|(a, b)| *a * b).sum();
+        let mut x = ro_challenge(&to_bytes![combined, point, value].unwrap());
+        let h_prime = ck.h.mul(x.into_repr()).into_affine();
+        let (mut l_vec, mut r_vec) = (Vec::new(), Vec::new());
+        let (final_comm_key, c) = CTX.with(|ctx| -> Result<(G1Affine, Fr), crate::ctx::Error> {
+            // Fr / G1Affine are Montgomery limbs in memory: uploaded as they are
+            let d_c = ctx.upload(coeffs.as_ptr() as *const u64, 32 * n)?;
+            let d_z = ctx.upload(z.as_ptr() as *const u64, 32 * n)?;
+            let key_xy = pack_points(&ck.comm_key);
+            let d_k = ctx.upload(key_xy.as_ptr(), 8 * key_xy.len())?;
+            let mut m = n;
+            while m > 1 {
+                let (mut lxy, mut rxy, mut li, mut ri) = ([0u64; 8], [0u64; 8], 0 as c_int, 0 as c_int);
+                let (mut ipl, mut ipr) = (Fr::zero(), Fr::zero());
+                ctx.check(unsafe {
+                    sys::zkb_ipa_round_lr_dev(ctx.raw(), d_c.ptr(), d_z.ptr(), d_k.ptr(), m, lxy.as_mut_ptr(), &mut li, rxy.as_mut_ptr(), &mut ri,
+                                              &mut ipl as *mut Fr as *mut u64, &mut ipr as *mut Fr as *mut u64)
+                })?;
+                let l = (unpack_point(&lxy, li).into_projective() + h_prime.mul(ipl.into_repr())).into_affine();
+                let r = (unpack_point(&rxy, ri).into_projective() + h_prime.mul(ipr.into_repr())).into_affine();
+                x = ro_challenge(&to_bytes![x, l, r].unwrap());
+                let x_inv = x.inverse().unwrap();
+                ctx.check(unsafe {
+                    sys::zkb_ipa_round_fold_dev(ctx.raw(), d_c.ptr_mut(), d_z.ptr_mut(), d_k.ptr_mut(), m, &x as *const Fr as *const u64,
+                                                &x_inv as *const Fr as *const u64)
+                })?;
+                l_vec.push(l);
+                r_vec.push(r);
+                m /= 2;
+            }
+            let (mut c, mut kxy) = (Fr::zero(), [0u64; 8]);
+            ctx.download(&mut c as *mut Fr as *mut u64, d_c.ptr(), 32)?;
+            ctx.download(kxy.as_mut_ptr(), d_k.ptr(), 64)?;
+            Ok((unpack_point(&kxy, 0), c))
+        })
+        .expect("zkb200: inner-product-argument rounds failed");
+        let _ = rands;
+        Ok(ipa_pc::Proof { l_vec, r_vec, final_comm_key, c, hiding_comm: None, rand: None })
     }
 
     fn check_individual_opening_challenges<'a>(
