@@ -697,7 +697,7 @@ def run_ipa_extra(torch, ctx, P, log_d):
             "open_ms": t_open * 1e3, "rounds": log_d, "gpu_launches": int(launches), "check_accepts": bool(ok), "check_rejects_wrong_value": not bad,
             "check_ms": t_check * 1e3, "first_round_ms": {"cross_terms_two_msms_and_inner_products": t_lr * 1e3, "fold_coeffs_powers_key": t_fold * 1e3},
             "key_fold_scalar_muls_per_s": (n / 2) / t_fold,
-            "note": "open = log_d x (zkb_ipa_round_lr_dev + two 2-point host-base MSMs for the h' terms + hash + zkb_ipa_round_fold_dev); "
+            "note": "open = log_d x (zkb_ipa_round_lr_dev + hash + zkb_ipa_round_fold_dev); "
                     "the key fold is n scalar multiplications by the round challenges in total"}
 
 

@@ -306,12 +306,14 @@ ZKB_API int zkb_g2_mul(const uint64_t g2_xy[16], const uint64_t scalar_canonical
  * (coefficients c, powers of the point z, key G) log2 n times; per round
  *     L = <c_r, G_l> + <c_r, z_l> h',  R = <c_l, G_r> + <c_l, z_r> h',  x = H(x_prev, L, R),
  *     c_l += x^-1 c_r,  z_l += x z_r,  G_l += x G_r.
- * zkb_ipa_round_lr_dev returns the two MSMs and the two inner products of a round (the caller adds the h' terms and hashes:
- * the transcript stays in the host language); zkb_ipa_round_fold_dev folds in place -- afterwards the first n / 2 entries of
+ * zkb_ipa_round_lr_dev returns L, R and the two inner products of a round (h_prime_xy: h' = x_0 h as an affine Montgomery point
+ * in host memory, or NULL for the two MSMs alone; the caller hashes: the transcript stays in the host language);
+ * zkb_ipa_round_fold_dev folds in place -- afterwards the first n / 2 entries of
  * each vector are the next round's.  All vectors live in HBM: c, z = n x 4 words Montgomery, G = n affine points.  n: a power
  * of two >= 2.  x, x_inv Montgomery (x * x_inv == 1 is checked).  Results are field / group elements: identical to the CPU's. */
 ZKB_API int zkb_ipa_round_lr_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, const uint64_t *z_dev, const uint64_t *key_dev, size_t n,
-                         uint64_t l_xy[8], int *l_inf, uint64_t r_xy[8], int *r_inf, uint64_t ip_l[4], uint64_t ip_r[4]);
+                         const uint64_t *h_prime_xy, uint64_t l_xy[8], int *l_inf, uint64_t r_xy[8], int *r_inf, uint64_t ip_l[4],
+                         uint64_t ip_r[4]);
 ZKB_API int zkb_ipa_round_fold_dev(zkb_ctx *ctx, uint64_t *coeffs_dev, uint64_t *z_dev, uint64_t *key_dev, size_t n, const uint64_t x[4],
                            const uint64_t x_inv[4]);
 

@@ -5,9 +5,9 @@
 //!   * `commit`: `comm = sum_i coeff_i * ck.comm_key[i]` (ipa_pc `cm_commit` without hiding: `rng = None`, no hiding bounds, as
 //!     plonk-core always calls it) -> the same resident-key MSM as KZG10 (`zkb_srs_load_g1` on `comm_key`, `zkb_msm_g1`);
 //!   * `HomomorphicCommitment::multi_scalar_mul` (commitment.rs:60-86) -> `zkb_msm_g1_bases`.
-//!   * `open`: the log(n) folding rounds run in HBM -- `zkb_ipa_round_lr_dev` (the two MSMs over halves of the key and the two
-//!     inner products of a round) and `zkb_ipa_round_fold_dev` (coefficients, point powers and key folded in place,
-//!     csrc/ipa.cu); the hash between the rounds, the `h'` terms and the proof struct stay arkworks' (`ro_challenge` below
+//!   * `open`: the log(n) folding rounds run in HBM -- `zkb_ipa_round_lr_dev` (L and R of a round: the two MSMs over halves of the key,
+//!     the two inner products and the `h'` terms) and `zkb_ipa_round_fold_dev` (coefficients, point powers and key folded in place,
+//!     csrc/ipa.cu); the hash between the rounds and the proof struct stay arkworks' (`ro_challenge` below
 //!     repeats ipa_pc's private `compute_random_oracle_challenge`).  Hiding or degree-bounded openings (never asked for by
 //!     plonk-core) delegate to ark-poly-commit, as do `setup` / `trim` / `check`.
 //! Associated types are InnerProductArgPC's own, so proofs keep their bytes.
@@ -165,16 +165,16 @@ impl PolynomialCommitment<Fr, Poly> for GpuIpaPc {
             let d_z = ctx.upload(z.as_ptr() as *const u64, 32 * n)?;
             let key_xy = pack_points(&ck.comm_key);
             let d_k = ctx.upload(key_xy.as_ptr(), 8 * key_xy.len())?;
+            let h_prime_xy = pack_points(&[h_prime]);
             let mut m = n;
             while m > 1 {
                 let (mut lxy, mut rxy, mut li, mut ri) = ([0u64; 8], [0u64; 8], 0 as c_int, 0 as c_int);
                 let (mut ipl, mut ipr) = (Fr::zero(), Fr::zero());
                 ctx.check(unsafe {
-                    sys::zkb_ipa_round_lr_dev(ctx.raw(), d_c.ptr(), d_z.ptr(), d_k.ptr(), m, lxy.as_mut_ptr(), &mut li, rxy.as_mut_ptr(), &mut ri,
-                                              &mut ipl as *mut Fr as *mut u64, &mut ipr as *mut Fr as *mut u64)
+                    sys::zkb_ipa_round_lr_dev(ctx.raw(), d_c.ptr(), d_z.ptr(), d_k.ptr(), m, h_prime_xy.as_ptr(), lxy.as_mut_ptr(), &mut li,
+                                              rxy.as_mut_ptr(), &mut ri, &mut ipl as *mut Fr as *mut u64, &mut ipr as *mut Fr as *mut u64)
                 })?;
-                let l = (unpack_point(&lxy, li).into_projective() + h_prime.mul(ipl.into_repr())).into_affine();
-                let r = (unpack_point(&rxy, ri).into_projective() + h_prime.mul(ipr.into_repr())).into_affine();
+                let (l, r) = (unpack_point(&lxy, li), unpack_point(&rxy, ri));       // the h' terms are already inside
                 x = ro_challenge(&to_bytes![x, l, r].unwrap());
                 let x_inv = x.inverse().unwrap();
                 ctx.check(unsafe {

@@ -168,9 +168,15 @@ def test_gpu_rounds_match_the_definitions(on_curve):
             while m > 1:
                 half = m // 2
                 (l_xy, l_inf), (r_xy, r_inf), ip_l, ip_r = ctx.ipa_round_lr_dev(d_c, d_z, d_k, m)
-                assert helper._pt_ints(l_xy, l_inf) == pyref.msm_naive(key[:half], c[half:m])
-                assert helper._pt_ints(r_xy, r_inf) == pyref.msm_naive(key[half:m], c[:half])
-                assert _fr_ints(ip_l) == [ipa_ref.inner(c[half:m], z[:half])] and _fr_ints(ip_r) == [ipa_ref.inner(c[:half], z[half:m])]
+                exp_l, exp_r = pyref.msm_naive(key[:half], c[half:m]), pyref.msm_naive(key[half:m], c[:half])
+                assert helper._pt_ints(l_xy, l_inf) == exp_l and helper._pt_ints(r_xy, r_inf) == exp_r
+                ipl, ipr = ipa_ref.inner(c[half:m], z[:half]), ipa_ref.inner(c[:half], z[half:m])
+                assert _fr_ints(ip_l) == [ipl] and _fr_ints(ip_r) == [ipr]
+                # with h': L = <c_r, G_l> + <c_r, z_l> h', R = <c_l, G_r> + <c_l, z_r> h' (h' = the key's spare point)
+                (l_xy, l_inf), (r_xy, r_inf), ip_l2, ip_r2 = ctx.ipa_round_lr_dev(d_c, d_z, d_k, m, helper._pt_array([pts[n]])[0])
+                assert helper._pt_ints(l_xy, l_inf) == pyref.g1_add(exp_l, pyref.g1_mul(ipl, pts[n]))
+                assert helper._pt_ints(r_xy, r_inf) == pyref.g1_add(exp_r, pyref.g1_mul(ipr, pts[n]))
+                assert np.array_equal(ip_l2, ip_l) and np.array_equal(ip_r2, ip_r)
                 x = rnd.randrange(1, r) if m != 16 else 1            # x = 1: the fold is a plain addition
                 xi = pow(x, -1, r)
                 ctx.ipa_round_fold_dev(d_c, d_z, d_k, m, _fr_arr([x])[0], _fr_arr([xi])[0])

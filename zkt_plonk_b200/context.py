@@ -165,12 +165,14 @@ class Context:
         return out, bool(inf.value)
 
     # -- inner-product-argument rounds (csrc/ipa.cu)
-    def ipa_round_lr_dev(self, coeffs_dev, z_dev, key_dev, n):
-        """((L affine, is_inf), (R affine, is_inf), <c_r, z_l>, <c_l, z_r>) of one opening round over vectors of length n."""
+    def ipa_round_lr_dev(self, coeffs_dev, z_dev, key_dev, n, h_prime=None):
+        """((L affine, is_inf), (R affine, is_inf), <c_r, z_l>, <c_l, z_r>) of one opening round over vectors of length n;
+        h_prime: (aff_words,) uint64 affine Montgomery point, or None for the two MSMs without the h' terms."""
         l, r = np.zeros(self.aff_words, dtype=np.uint64), np.zeros(self.aff_words, dtype=np.uint64)
         li, ri = ctypes.c_int(0), ctypes.c_int(0)
         ipl, ipr = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
-        self._check(self._lib.zkb_ipa_round_lr_dev(self._h, _dev_ptr(coeffs_dev), _dev_ptr(z_dev), _dev_ptr(key_dev), n, _host_ptr(l),
+        self._check(self._lib.zkb_ipa_round_lr_dev(self._h, _dev_ptr(coeffs_dev), _dev_ptr(z_dev), _dev_ptr(key_dev), n,
+                                                   _host_ptr(h_prime) if h_prime is not None else None, _host_ptr(l),
                                                    ctypes.byref(li), _host_ptr(r), ctypes.byref(ri), _host_ptr(ipl), _host_ptr(ipr)))
         return (l, bool(li.value)), (r, bool(ri.value)), ipl, ipr
 

@@ -122,3 +122,7 @@ int zkb_pow2lvl_cached(zkb_ctx *ctx, uint64_t key, unsigned lm, const zkb::host:
                        const void **out, uint32_t *s_out);
 int zkb_pow2lvl_build(zkb_ctx *ctx, void *out, unsigned lm, const zkb::host::Fe &base, const zkb::host::Fe &hi_scale,
                       uint32_t *s_out);
+
+// library-internal (msm.cu): <scalars, points> over caller-held device points plus extra_scalar * extra on the host
+int zkb_msm_points_plus(zkb_ctx *ctx, const uint64_t *points_dev, const uint64_t *scalars_dev, size_t n, int scalars_mont,
+                        const uint64_t *extra_xy, const uint64_t *extra_scalar_canon, uint64_t *out_xy, int *is_inf);

@@ -7,15 +7,17 @@
 //     L = <c_r, G_l> + <c_r, z_l> h'      R = <c_l, G_r> + <c_l, z_r> h'          (two MSMs of n / 2, two inner products)
 //     x = H(x_prev, L, R)                                                          (stays with the caller: a hash)
 //     c_l += x^-1 c_r      z_l += x z_r      G_l += x G_r  (then batch-normalised to affine)
-// zkb_ipa_round_lr_dev is the first line without the h' term (one fixed point times a scalar: the caller's), and
+// zkb_ipa_round_lr_dev is the first line (the h' terms: two host scalar multiplications under the MSMs), and
 // zkb_ipa_round_fold_dev the third.  All three vectors stay in HBM across the rounds; the caller sees two points and two field
 // elements per round.  Results are group / field elements, so they equal the CPU's bit for bit in affine / Montgomery form.
 //
 // The key fold is the expensive half: n / 2 scalar multiplications by the SAME 255-bit challenge per round (n in total over an
-// opening).  One thread per point runs double-and-add over the challenge's bits (uniform across the grid: no divergence) in XYZZ
-// coordinates and normalises its own result.
+// opening).  One thread per point runs double-and-add over the challenge's non-adjacent form (recoded once on the host; uniform
+// across the grid: no divergence) in XYZZ coordinates and normalises its own result.
 #include "ctx.h"
 #include "ec.cuh"
+
+#include <stdlib.h>
 
 using namespace zkb;
 typedef FrP F;
@@ -80,15 +82,21 @@ __global__ void __launch_bounds__(256) ipa_fold_scalars_kernel(uint4 *c, uint4 *
     fstore(z + 2 * i, fadd<F>(fload(z + 2 * i), fmul<F>(x, fload_ro(z + 2 * (half + i)))));
 }
 
-// G_l[i] = G_l[i] + x * G_r[i], affine.  `bits` = x as a canonical integer, `top` = index of its highest set bit.
-__global__ void __launch_bounds__(128) ipa_fold_key_kernel(g1a_t *key, uint32_t half, const __grid_constant__ Bits256 bits, int top) {
+// G_l[i] = G_l[i] + x * G_r[i], affine.  x arrives in non-adjacent form: digit b is +1 where `pos` has bit b, -1 where `neg` has
+// it (never both, never two neighbours), `top` = index of the highest digit (always +1).  A third of the digits are non-zero
+// against half of the bits, and -P is free on a short Weierstrass curve: ~85 mixed additions per point instead of ~127.
+__global__ void __launch_bounds__(128) ipa_fold_key_kernel(g1a_t *key, uint32_t half, const __grid_constant__ Bits256 pos,
+                                                           const __grid_constant__ Bits256 neg, int top) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= half) return;
     const g1a_t r = g1a_load(key + half + i);
-    g1x_t acc = g1x_from_affine(r);                               // the top bit
+    const g1a_t rn = g1a_neg(r);
+    g1x_t acc = g1x_from_affine(r);                               // the top digit
     for (int b = top - 1; b >= 0; --b) {
         acc = g1x_double(acc);
-        if ((bits.w[b >> 5] >> (b & 31)) & 1) g1x_add_mixed(acc, r);
+        const uint32_t m = 1u << (b & 31);
+        if (pos.w[b >> 5] & m) g1x_add_mixed(acc, r);
+        else if (neg.w[b >> 5] & m) g1x_add_mixed(acc, rn);
     }
     g1a_t l;                                                      // this thread overwrites the entry: not through the read-only path
     l.x = floadn<FqP::N>(&key[i].x);
@@ -99,15 +107,38 @@ __global__ void __launch_bounds__(128) ipa_fold_key_kernel(g1a_t *key, uint32_t 
     fstore(&key[i].y, a.y);
 }
 
+// Non-adjacent form of a canonical scalar below 2^255: with t = 3 x, digit b is +1 where bit b + 1 of t is set and that of x is
+// not, -1 the other way round (Reitwiesner).  Returns the index of the top digit (x != 0).
+int naf_of(const uint64_t x[4], Bits256 *pos, Bits256 *neg) {
+    uint64_t xe[5] = {x[0], x[1], x[2], x[3], 0}, t[5], p[5], q[5];
+    unsigned __int128 carry = 0;
+    for (int k = 0; k < 5; ++k) {
+        carry += (unsigned __int128)xe[k] * 3;
+        t[k] = (uint64_t)carry;
+        carry >>= 64;
+    }
+    for (int k = 0; k < 5; ++k) { p[k] = t[k] & ~xe[k]; q[k] = ~t[k] & xe[k]; }
+    for (int k = 0; k < 4; ++k) {                                 // >> 1 across the five words; the result fits four
+        const uint64_t pk = (p[k] >> 1) | (p[k + 1] << 63), qk = (q[k] >> 1) | (q[k + 1] << 63);
+        pos->w[2 * k] = (uint32_t)pk; pos->w[2 * k + 1] = (uint32_t)(pk >> 32);
+        neg->w[2 * k] = (uint32_t)qk; neg->w[2 * k + 1] = (uint32_t)(qk >> 32);
+    }
+    int top = 255;
+    while (top > 0 && !((pos->w[top >> 5] >> (top & 31)) & 1)) --top;
+    return top;
+}
+
 bool pow2(size_t n) { return n >= 2 && (n & (n - 1)) == 0; }
 
 }  // namespace
 
 // One round's cross terms over c, z (n Montgomery field elements each) and G (n affine points), all in HBM, n a power of two:
-// l_xy = <c_r, G_l>, r_xy = <c_l, G_r> (affine, Montgomery; identity = zeros and *_inf = 1), ip_l = <c_r, z_l>, ip_r = <c_l, z_r>
-// (Montgomery).  The caller adds ip * h' to each point and hashes.
+// ip_l = <c_r, z_l>, ip_r = <c_l, z_r> (Montgomery), l_xy = <c_r, G_l> + ip_l h', r_xy = <c_l, G_r> + ip_r h' (affine, Montgomery;
+// identity = zeros and *_inf = 1).  h_prime_xy: the round-independent point h' = x_0 h in host memory, or NULL to get the two
+// MSMs alone.  The h' terms are two host scalar multiplications run while the GPU is inside the MSMs.  The caller hashes.
 int zkb_ipa_round_lr_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, const uint64_t *z_dev, const uint64_t *key_dev, size_t n,
-                         uint64_t *l_xy, int *l_inf, uint64_t *r_xy, int *r_inf, uint64_t ip_l[4], uint64_t ip_r[4]) {
+                         const uint64_t *h_prime_xy, uint64_t *l_xy, int *l_inf, uint64_t *r_xy, int *r_inf, uint64_t ip_l[4],
+                         uint64_t ip_r[4]) {
     if (!ctx) return ZKB_ERR_INVALID;
     if (!coeffs_dev || !z_dev || !key_dev || !l_xy || !r_xy || !ip_l || !ip_r) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ipa_round_lr_dev: null argument");
     if (!pow2(n) || n > ((size_t)1 << 30)) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ipa_round_lr_dev: n must be a power of two, 2 <= n <= 2^30");
@@ -124,10 +155,18 @@ int zkb_ipa_round_lr_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, const uint64_
     ZKB_CUDA(ctx, cudaGetLastError());
     uint64_t ips[8];
     ZKB_CUDA(ctx, cudaMemcpyAsync(ips, total, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    // the MSMs synchronise the stream, which also lands the inner products
-    rc = zkb_msm_g1_points_dev(ctx, key_dev, coeffs_dev + 4 * half, half, 1, l_xy, l_inf);
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    host::Fe one, canon[2];
+    memset(one.l, 0, 32);
+    one.l[0] = 1;
+    for (int k = 0; k < 2; ++k) {                                  // canonical integers: the scalars of the h' terms
+        host::Fe m;
+        memcpy(m.l, ips + 4 * k, 32);
+        canon[k] = host::mul(m, one, host::FR);
+    }
+    rc = zkb_msm_points_plus(ctx, key_dev, coeffs_dev + 4 * half, half, 1, h_prime_xy, canon[0].l, l_xy, l_inf);
     if (rc) return rc;
-    rc = zkb_msm_g1_points_dev(ctx, key_dev + (size_t)AFF_W * half, coeffs_dev, half, 1, r_xy, r_inf);
+    rc = zkb_msm_points_plus(ctx, key_dev + (size_t)AFF_W * half, coeffs_dev, half, 1, h_prime_xy, canon[1].l, r_xy, r_inf);
     if (rc) return rc;
     memcpy(ip_l, ips, 32);
     memcpy(ip_r, ips + 4, 32);
@@ -150,16 +189,21 @@ int zkb_ipa_round_fold_dev(zkb_ctx *ctx, uint64_t *coeffs_dev, uint64_t *z_dev, 
     const host::Fe prod = host::mul(host::mul(hx, hxi, host::FR), one, host::FR);      // canonical x * x_inv
     if (memcmp(prod.l, one.l, 32) != 0) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ipa_round_fold_dev: x * x_inv != 1");
     const host::Fe canon = host::mul(hx, one, host::FR);
-    Bits256 bits;
-    memcpy(bits.w, canon.l, 32);
-    int top = 255;
-    while (top > 0 && !((bits.w[top >> 5] >> (top & 31)) & 1)) --top;
+    Bits256 pos, neg;
+    int top = naf_of(canon.l, &pos, &neg);
+    const char *plain = getenv("ZKB_IPA_NAF");                    // A/B: ZKB_IPA_NAF=0 walks the plain binary expansion (same results)
+    if (plain && plain[0] == '0') {
+        memcpy(pos.w, canon.l, 32);
+        memset(neg.w, 0, 32);
+        top = 255;
+        while (top > 0 && !((pos.w[top >> 5] >> (top & 31)) & 1)) --top;
+    }
     fe_t dx, dxi;
     memcpy(dx.v, x, 32);
     memcpy(dxi.v, x_inv, 32);
     const size_t half = n / 2;
     ipa_fold_scalars_kernel<<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>((uint4 *)coeffs_dev, (uint4 *)z_dev, half, dx, dxi);
-    ipa_fold_key_kernel<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>((g1a_t *)key_dev, (uint32_t)half, bits, top);
+    ipa_fold_key_kernel<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>((g1a_t *)key_dev, (uint32_t)half, pos, neg, top);
     ctx->launches += 2;
     ZKB_CUDA(ctx, cudaGetLastError());
     return ZKB_OK;

@@ -668,6 +668,14 @@ inline Pt mul_small(const Pt &p, uint32_t k) {                   // k * p, doubl
     }
     return acc;
 }
+inline Pt mul_scalar(const Pt &p, const uint64_t k[4]) {           // k * p for a canonical 256-bit scalar (host, a few per call)
+    Pt acc = inf();
+    for (int bit = 255; bit >= 0; --bit) {
+        acc = dbl(acc);
+        if ((k[bit >> 6] >> (bit & 63)) & 1) acc = add(acc, p);
+    }
+    return acc;
+}
 inline void to_affine(const Pt &p, uint64_t *out_xy /* AFF_W words */, int *is_inf_out) {
     if (is_inf(p)) { memset(out_xy, 0, AFF_BYTES); if (is_inf_out) *is_inf_out = 1; return; }
     Fe zi = host::inv(p.zzz, FQ);
@@ -1400,6 +1408,15 @@ int zkb_msm_g1_bases(zkb_ctx *ctx, const uint64_t *points_host, const uint64_t *
 // scalars on the device too, canonical integers or (scalars_mont != 0) Montgomery form as polynomial coefficients are kept.
 int zkb_msm_g1_points_dev(zkb_ctx *ctx, const uint64_t *points_dev, const uint64_t *scalars_dev, size_t n, int scalars_mont,
                           uint64_t *out_xy /* AFF_W words */, int *is_inf) {
+    return zkb_msm_points_plus(ctx, points_dev, scalars_dev, n, scalars_mont, nullptr, nullptr, out_xy, is_inf);
+}
+
+// The same plus one term on the host: out = <scalars, points> + extra_scalar * extra (affine Montgomery point and canonical
+// scalar in host memory; either NULL: no extra term).  The inner-product argument's L and R are such sums (ipa.cu): the extra
+// multiplication is ~380 host group operations, cheaper than a second trip through the bucket pipeline for one point.
+// Library-internal (declared in ctx.h), not part of the C ABI.
+extern "C++" int zkb_msm_points_plus(zkb_ctx *ctx, const uint64_t *points_dev, const uint64_t *scalars_dev, size_t n, int scalars_mont,
+                                     const uint64_t *extra_xy, const uint64_t *extra_scalar_canon, uint64_t *out_xy, int *is_inf) {
     if (!ctx || !out_xy) return ZKB_ERR_INVALID;
     if ((!points_dev || !scalars_dev) && n) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_msm_g1_points_dev: null input");
     if (!state(ctx)->pipe_partial.empty()) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "a zkb_commit_push batch is open (its scalars and results live in the buffers this call would reuse): call zkb_commit_finish first");
@@ -1415,10 +1432,23 @@ int zkb_msm_g1_points_dev(zkb_ctx *ctx, const uint64_t *points_dev, const uint64
     MsmPlan pl;
     int rc = msm_enqueue(ctx, (const g1a_t *)points_dev, sc, n, ctx->msm_force_c, nullptr, 0, &pl);
     if (rc) return rc;
+    hec::Pt extra = hec::inf();
+    if (extra_xy && extra_scalar_canon) {                          // on the host while the GPU runs the MSM
+        bool zero = true;
+        for (int i = 0; i < AFF_W; ++i) zero = zero && extra_xy[i] == 0;
+        if (!zero) {
+            hec::Pt e;
+            memcpy(e.x.l, extra_xy, AFF_BYTES / 2);
+            memcpy(e.y.l, extra_xy + AFF_W / 2, AFF_BYTES / 2);
+            e.zz = host::one(host::FQ);
+            e.zzz = e.zz;
+            extra = hec::mul_scalar(e, extra_scalar_canon);
+        }
+    }
     hec::Pt total;
     rc = msm_finish(ctx, pl, &total);
     if (rc) return rc;
-    hec::to_affine(total, out_xy, is_inf);
+    hec::to_affine(hec::add(total, extra), out_xy, is_inf);
     return ZKB_OK;
 }
 

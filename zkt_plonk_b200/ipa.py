@@ -113,13 +113,11 @@ class GpuIPA:
         value = field.from_mont(field.limbs_to_int(ctx.poly_eval_dev(c, n, _fr_limbs(point))))
         key = self.key.clone()
         x = oracle(g1_bytes(commitment) + fr_bytes(point) + fr_bytes(value))
-        h_prime = self.lincomb([self.h], [x])
+        h_prime = self._pt_array([self.lincomb([self.h], [x])])[0]
         l_vec, r_vec = [], []
         while n > 1:
-            (l_xy, l_inf), (r_xy, r_inf), ip_l, ip_r = ctx.ipa_round_lr_dev(c, z, key, n)
-            ipl, ipr = field.from_mont(field.limbs_to_int(ip_l)), field.from_mont(field.limbs_to_int(ip_r))
-            L = self.lincomb([self._pt_ints(l_xy, l_inf), h_prime], [1, ipl])
-            R = self.lincomb([self._pt_ints(r_xy, r_inf), h_prime], [1, ipr])
+            (l_xy, l_inf), (r_xy, r_inf), _, _ = ctx.ipa_round_lr_dev(c, z, key, n, h_prime)
+            L, R = self._pt_ints(l_xy, l_inf), self._pt_ints(r_xy, r_inf)
             l_vec.append(L)
             r_vec.append(R)
             x = oracle(fr_bytes(x) + g1_bytes(L) + g1_bytes(R))
