@@ -402,6 +402,8 @@ ZKB_API int zkb_test_combine_split(const uint64_t *table, size_t table_len, size
 
 /* Test hook: set rank / world of a context without creating a communicator (single-GPU tests of the multi-GPU layouts:
  * zkb_commit_push + zkb_commit_finish_partials only). */
+/* the split k = k1 + lambda k2 (mod r) of csrc/ipa.cu's key fold (magnitudes and signs; returns 1 when short and verified) */
+ZKB_API int zkb_test_glv_split(const uint64_t k[4], uint64_t m1[4], int *neg1, uint64_t m2[4], int *neg2);
 ZKB_API int zkb_test_set_rank_world(zkb_ctx *ctx, int rank, int world);
 /* Host only (no GPU): [lo, hi) of commitment k (of a batch of E, `len` coefficients at SRS offset `offset`) that `rank` of
  * `world` computes over a replicated key (zkb_srs_set_replicated); fanout as there.  lo == hi: nothing. */

@@ -101,6 +101,42 @@ def test_challenge_derivation():
     assert ipa.g1_bytes(None) == ipa_ref.g1_bytes(None) and ipa.g1_bytes((5, 9)) == ipa_ref.g1_bytes((5, 9))
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_glv_split_of_the_key_fold(curve):
+    """The key fold multiplies by a challenge through the curve's endomorphism: the library's split k = k1 + lambda k2 (host
+    multi-word arithmetic, csrc/ipa.cu glv_split) against the generator's big-integer version (tools/gen_curves.py glv_params):
+    same halves, short, and lambda acts on G1 as (x, y) -> (beta x, y)."""
+    import ctypes
+    import importlib.util
+    import os
+    from zkt_plonk_b200 import _lib
+    spec = importlib.util.spec_from_file_location("gen_curves", os.path.join(os.path.dirname(__file__), "..", "tools", "gen_curves.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    c = [x for x in gen.CURVES if x["name"] == curve][0]
+    gen.check(c)
+    g = gen.glv_params(c, trials=50)
+    r, lam = c["r"], g["lam"]
+    assert gen.ec_mul(lam, c["gen"], c["q"]) == (g["beta"] * c["gen"][0] % c["q"], c["gen"][1])
+    lib = _lib.lib(curve)
+    rnd = random.Random(8)
+    for i in range(400):
+        k = [0, 1, r - 1, lam, r - lam, (r - 1) // 2, 2, (1 << 128) % r][i] if i < 8 else rnd.randrange(r)
+        kk = np.array([(k >> (64 * j)) & (2**64 - 1) for j in range(4)], dtype=np.uint64)
+        m1, m2 = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+        n1, n2 = ctypes.c_int(0), ctypes.c_int(0)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        assert lib.zkb_test_glv_split(vp(kk), vp(m1), ctypes.byref(n1), vp(m2), ctypes.byref(n2)) == 1
+        a = sum(int(v) << (64 * j) for j, v in enumerate(m1)) * (-1 if n1.value else 1)
+        b = sum(int(v) << (64 * j) for j, v in enumerate(m2)) * (-1 if n2.value else 1)
+        assert (a + lam * b) % r == k and abs(a) < 1 << 130 and abs(b) < 1 << 130
+        k2 = (((k * g["g1"]) >> 384) * g["m1"] + ((k * g["g2"]) >> 384) * g["m2"]) % r
+        k1 = (k - lam * k2) % r
+        assert a % r == k1 and b % r == k2
+    bad = np.array([2**64 - 1] * 4, dtype=np.uint64)                 # not below r
+    assert lib.zkb_test_glv_split(vp(bad), vp(m1), ctypes.byref(n1), vp(m2), ctypes.byref(n2)) == _lib.ZKB_ERR_INVALID
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _ctx(curve):
     import torch
@@ -156,7 +192,12 @@ def test_gpu_rounds_match_the_definitions(on_curve):
         r = field.R_MOD
         rnd = random.Random(17)
         helper = GpuIPA(ctx)
-        for n in (2, 16, 64):
+        import os
+        plain, binary = {"ZKB_IPA_GLV": "0"}, {"ZKB_IPA_NAF": "0"}       # A/B knobs of the key fold, read per call: same results
+        for n, knobs in ((2, {}), (16, {}), (64, {}), (16, plain), (16, binary), (8, {**plain, **binary})):
+            for name in ("ZKB_IPA_GLV", "ZKB_IPA_NAF"):
+                os.environ.pop(name, None)
+            os.environ.update(knobs)
             d_key, pts, ks = _device_key(ctx, n, 100 + n)
             assert pts[0] == pyref.g1_mul(ks[0], pyref.G1_GEN)
             key = list(pts[:n])
@@ -188,6 +229,8 @@ def test_gpu_rounds_match_the_definitions(on_curve):
                 got = d_k[:half].cpu().numpy().view(np.uint64)
                 assert [helper._pt_ints(row, not row.any()) for row in got] == key
                 m = half
+        for name in ("ZKB_IPA_GLV", "ZKB_IPA_NAF"):
+            os.environ.pop(name, None)
         # the fold's special cases: G_l = -x G_r gives the identity (zeros), G_l = x G_r doubles
         d_key, pts, ks = _device_key(ctx, 3, 5)
         x = 12345
@@ -199,6 +242,11 @@ def test_gpu_rounds_match_the_definitions(on_curve):
         torch.cuda.synchronize()
         got = d_k[:2].cpu().numpy().view(np.uint64)
         assert not got[0].any() and helper._pt_ints(got[1], False) == pyref.g1_add(a, a)
+        d_k = _dev(helper._pt_array([pts[0], pts[1], None, None]))       # identity entries in G_r: G_l stays
+        ctx.ipa_round_fold_dev(d_c, d_z, d_k, 4, _fr_arr([x])[0], _fr_arr([pow(x, -1, r)])[0])
+        torch.cuda.synchronize()
+        got = d_k[:2].cpu().numpy().view(np.uint64)
+        assert [helper._pt_ints(row, False) for row in got] == [pts[0], pts[1]]
         # argument checks: not a power of two, x * x_inv != 1
         from zkt_plonk_b200._lib import ZkbError
         with pytest.raises(ZkbError):

@@ -164,6 +164,54 @@ def host_params(name, f):
             % (f["n64"], name, host_arr(f["p"], f["n64"]), host_arr(f["one"], f["n64"]), host_arr(f["r2"], f["n64"]), f["inv64"]))
 
 
+def glv_params(c, trials=2000):
+    """Constants of the G1 endomorphism phi(x, y) = (beta x, y) = lambda (x, y) (q = r = 1 mod 3 on all three curves) and of the
+    split k = k1 + lambda k2 (mod r) with |k1|, |k2| ~ sqrt(r) (Gallant-Lambert-Vanstone): a short basis (a1, b1), (a2, b2) of the
+    lattice {(a, b): a + b lambda = 0 mod r} from the extended Euclid sequence of (r, lambda); rounding by multiply-and-shift,
+    C1 = (k G1) >> 384 with G1 = round(2^384 |b2| / r), C2 likewise with |b1|; k2 = C1 M1 + C2 M2, k1 = k - lambda k2 (mod r) with
+    the signs folded into M1 = -sign(b2) b1, M2 = sign(b1) b2.  Checked here on random and edge scalars: the halves stay below
+    2^130 (csrc/ipa.cu re-checks every split at run time and falls back to the plain scalar if one is not short)."""
+    import random
+    q, r, G = c["q"], c["r"], c["gen"]
+
+    def root3(p):
+        g = 2
+        while pow(g, (p - 1) // 3, p) == 1:
+            g += 1
+        return pow(g, (p - 1) // 3, p)
+
+    beta, lam = root3(q), root3(r)
+    if ec_mul(lam, G, q) != (beta * G[0] % q, G[1]):
+        beta = beta * beta % q
+    assert ec_mul(lam, G, q) == (beta * G[0] % q, G[1]) and (lam * lam + lam + 1) % r == 0 and (beta * beta + beta + 1) % q == 0
+    rows, r0, r1, t0, t1 = [(r, 0)], r, lam, 0, 1
+    while r1:
+        k = r0 // r1
+        r0, r1, t0, t1 = r1, r0 - k * r1, t1, t0 - k * t1
+        rows.append((r0, t0))
+    l = max(i for i, (ri, _) in enumerate(rows) if ri * ri >= r)
+    v1 = (rows[l + 1][0], -rows[l + 1][1])
+    cands = [(rows[l][0], -rows[l][1])] + ([(rows[l + 2][0], -rows[l + 2][1])] if l + 2 < len(rows) else [])
+    v2 = min(cands, key=lambda v: v[0] * v[0] + v[1] * v[1])
+    (a1, b1), (a2, b2) = v1, v2
+    assert (a1 + b1 * lam) % r == 0 and (a2 + b2 * lam) % r == 0 and a1 * b2 - a2 * b1 in (r, -r)
+    sg = lambda v: -1 if v < 0 else 1
+    g1, g2 = ((abs(b2) << 384) + r // 2) // r, ((abs(b1) << 384) + r // 2) // r
+    m1, m2 = (-sg(b2) * b1) % r, (sg(b1) * b2) % r
+    assert g1 < 1 << 320 and g2 < 1 << 320
+    rnd = random.Random(c["id"])
+    worst = 0
+    for i in range(trials):
+        k = [0, 1, r - 1, lam, r - lam, (r - 1) // 2][i] if i < 6 else rnd.randrange(r)
+        k2 = (((k * g1) >> 384) * m1 + ((k * g2) >> 384) * m2) % r
+        k1 = (k - lam * k2) % r
+        s1, s2 = min(k1, r - k1), min(k2, r - k2)
+        worst = max(worst, s1, s2)
+        assert (k1 + lam * k2) % r == k
+    assert worst < 1 << 130, worst.bit_length()
+    return dict(beta=beta, lam=lam, g1=g1, g2=g2, m1=m1, m2=m2, bits=worst.bit_length())
+
+
 def gen_params():
     o = ["// curve_params.h -- GENERATED by tools/gen_curves.py (do not edit): field and group constants of the curves the",
          "// library can be compiled for.  The reference is generic over the pairing engine (plonk.rs:226-254 runs its full test on",
@@ -196,6 +244,16 @@ def gen_params():
         o.append("constexpr uint64_t G1_COEFF_B = %d;" % c["b"])
         o.append("static const uint64_t G1_GEN_X[%d] = %s;" % (fq["n64"], host_arr(c["gen"][0] * (1 << (64 * fq["n64"])) % c["q"], fq["n64"])))
         o.append("static const uint64_t G1_GEN_Y[%d] = %s;" % (fq["n64"], host_arr(c["gen"][1] * (1 << (64 * fq["n64"])) % c["q"], fq["n64"])))
+        gl = glv_params(c)
+        R4 = 1 << 256
+        o.append("// GLV split for the key fold of csrc/ipa.cu: phi(x, y) = (beta x, y) = lambda (x, y); k2 = C1 M1 + C2 M2, k1 = k - lambda k2 with")
+        o.append("// C = (k G) >> 384; halves below 2^%d on %d generator-checked scalars (tools/gen_curves.py glv_params)" % (gl["bits"], 2000))
+        o.append("static const uint64_t GLV_BETA[%d] = %s;   // Montgomery" % (fq["n64"], host_arr(gl["beta"] * (1 << (64 * fq["n64"])) % c["q"], fq["n64"])))
+        o.append("static const uint64_t GLV_LAMBDA_MONT[4] = %s;" % host_arr(gl["lam"] * R4 % c["r"], 4))
+        o.append("static const uint64_t GLV_M1_MONT[4] = %s;" % host_arr(gl["m1"] * R4 % c["r"], 4))
+        o.append("static const uint64_t GLV_M2_MONT[4] = %s;" % host_arr(gl["m2"] * R4 % c["r"], 4))
+        o.append("static const uint64_t GLV_G1[5] = %s;" % host_arr(gl["g1"], 5))
+        o.append("static const uint64_t GLV_G2[5] = %s;" % host_arr(gl["g2"], 5))
         pp = pairing_params(c)
         nh, nf = (pp["hard"].bit_length() + 63) // 64, (pp["final"].bit_length() + 63) // 64
         o.append("// pairing (csrc/verify.cu): Fq2 = Fq[i] / (i^2 + %d), w^6 = xi = %d + i, %s-type twist, %s family with x = %s0x%x"

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) ipa_fold_key_kernel(g1a_t *key, uint32_t 
 }
 
 // Non-adjacent form of a canonical scalar below 2^255: with t = 3 x, digit b is +1 where bit b + 1 of t is set and that of x is
-// not, -1 the other way round (Reitwiesner).  Returns the index of the top digit (x != 0).
+// not, -1 the other way round (Reitwiesner).  Returns the index of the top digit (-1 for x = 0).
 int naf_of(const uint64_t x[4], Bits256 *pos, Bits256 *neg) {
     uint64_t xe[5] = {x[0], x[1], x[2], x[3], 0}, t[5], p[5], q[5];
     unsigned __int128 carry = 0;
@@ -124,13 +124,108 @@ int naf_of(const uint64_t x[4], Bits256 *pos, Bits256 *neg) {
         neg->w[2 * k] = (uint32_t)qk; neg->w[2 * k + 1] = (uint32_t)(qk >> 32);
     }
     int top = 255;
-    while (top > 0 && !((pos->w[top >> 5] >> (top & 31)) & 1)) --top;
-    return top;
+    while (top >= 0 && !((pos->w[top >> 5] >> (top & 31)) & 1)) --top;
+    return top;                                                   // -1 for x = 0
+}
+
+// The same fold through the curve's endomorphism: x = k1 + lambda k2 (mod r) with |k1|, |k2| < 2^130 and lambda (x, y) = (beta x, y), so
+// x P = k1 P + k2 (beta P.x, P.y): half the doublings (and half the dependent chain, which is what a small round waits for).  Both
+// halves arrive in non-adjacent form (p1 / n1, p2 / n2); flip1 / flip2: the half is negative (its point is negated instead).
+__global__ void __launch_bounds__(128) ipa_fold_key_glv_kernel(g1a_t *key, uint32_t half, const __grid_constant__ Bits256 p1,
+                                                               const __grid_constant__ Bits256 n1, const __grid_constant__ Bits256 p2,
+                                                               const __grid_constant__ Bits256 n2, int top, int flip1, int flip2,
+                                                               const __grid_constant__ fq_t beta) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    const g1a_t r = g1a_load(key + half + i);
+    g1x_t acc = g1x_inf();
+    if (!g1a_is_inf(r)) {
+        g1a_t a, an, b, bn;                                       // +-k1's point, +-k2's point: the four share two x and two y
+        a.x = r.x;
+        a.y = flip1 ? fneg<Q>(r.y) : r.y;
+        an.x = r.x;
+        an.y = flip1 ? r.y : fneg<Q>(r.y);
+        b.x = fmul<Q>(r.x, beta);
+        b.y = flip2 ? fneg<Q>(r.y) : r.y;
+        bn.x = b.x;
+        bn.y = flip2 ? r.y : fneg<Q>(r.y);
+        for (int bit = top; bit >= 0; --bit) {
+            acc = g1x_double(acc);
+            const uint32_t m = 1u << (bit & 31), w = bit >> 5;
+            if (p1.w[w] & m) g1x_add_mixed(acc, a);
+            else if (n1.w[w] & m) g1x_add_mixed(acc, an);
+            if (p2.w[w] & m) g1x_add_mixed(acc, b);
+            else if (n2.w[w] & m) g1x_add_mixed(acc, bn);
+        }
+    }
+    g1a_t l;
+    l.x = floadn<FqP::N>(&key[i].x);
+    l.y = floadn<FqP::N>(&key[i].y);
+    g1x_add_mixed(acc, l);
+    const g1a_t o = g1x_to_affine(acc);
+    fstore(&key[i].x, o.x);
+    fstore(&key[i].y, o.y);
+}
+
+// (k G) >> 384 for a 4-word k and a 5-word G: the rounding of the GLV split (three words at most; callers check the size)
+void mulshift384(const uint64_t k[4], const uint64_t g[5], uint64_t out[4]) {
+    uint64_t prod[9] = {0};
+    for (int i = 0; i < 4; ++i) {
+        unsigned __int128 carry = 0;
+        for (int j = 0; j < 5; ++j) {
+            carry += (unsigned __int128)k[i] * g[j] + prod[i + j];
+            prod[i + j] = (uint64_t)carry;
+            carry >>= 64;
+        }
+        prod[i + 5] = (uint64_t)carry;
+    }
+    out[0] = prod[6]; out[1] = prod[7]; out[2] = prod[8]; out[3] = 0;
+}
+
+// |v| and sign of a residue read as the signed integer of smallest magnitude; false when that is not below 2^136
+bool short_signed(const host::Fe &v, uint64_t mag[4], int *neg) {
+    host::Fe zero, m;
+    memset(zero.l, 0, 32);
+    m = host::sub(zero, v, host::FR);                              // r - v (0 for v = 0)
+    *neg = !host::ge<host::FR_L>(m.l, v.l);                        // r - v < v: the negative reading is the short one
+    memcpy(mag, *neg ? m.l : v.l, 32);
+    return mag[3] == 0 && mag[2] < 256;
+}
+
+// k (canonical, below r) = k1 + lambda k2 (mod r), the halves as magnitude and sign.  The result is verified; false: not short.
+bool glv_split(const uint64_t k[4], uint64_t m1[4], int *neg1, uint64_t m2[4], int *neg2) {
+    host::Fe c1, c2, kk, lam, mm1, mm2;
+    mulshift384(k, host::GLV_G1, c1.l);
+    mulshift384(k, host::GLV_G2, c2.l);
+    memcpy(kk.l, k, 32);
+    memcpy(lam.l, host::GLV_LAMBDA_MONT, 32);
+    memcpy(mm1.l, host::GLV_M1_MONT, 32);
+    memcpy(mm2.l, host::GLV_M2_MONT, 32);
+    if (host::ge<host::FR_L>(c1.l, host::FR.p) || host::ge<host::FR_L>(c2.l, host::FR.p)) return false;
+    // a canonical integer times a Montgomery form is the canonical product
+    const host::Fe k2 = host::add(host::mul(c1, mm1, host::FR), host::mul(c2, mm2, host::FR), host::FR);
+    const host::Fe k1 = host::sub(kk, host::mul(k2, lam, host::FR), host::FR);
+    if (!short_signed(k1, m1, neg1) || !short_signed(k2, m2, neg2)) return false;
+    // verify: (+-m1) + lambda (+-m2) == k
+    host::Fe zero, a, b;
+    memset(zero.l, 0, 32);
+    memcpy(a.l, m1, 32);
+    memcpy(b.l, m2, 32);
+    if (*neg1) a = host::sub(zero, a, host::FR);
+    if (*neg2) b = host::sub(zero, b, host::FR);
+    const host::Fe back = host::add(a, host::mul(b, lam, host::FR), host::FR);
+    return memcmp(back.l, k, 32) == 0;
 }
 
 bool pow2(size_t n) { return n >= 2 && (n & (n - 1)) == 0; }
 
 }  // namespace
+
+// Test hook (host only): the GLV split of a canonical scalar as the key fold uses it; returns 1 when it is short and verified.
+int zkb_test_glv_split(const uint64_t k[4], uint64_t m1[4], int *neg1, uint64_t m2[4], int *neg2) {
+    if (!k || !m1 || !neg1 || !m2 || !neg2 || host::ge<host::FR_L>(k, host::FR.p)) return ZKB_ERR_INVALID;
+    return glv_split(k, m1, neg1, m2, neg2) ? 1 : 0;
+}
 
 // One round's cross terms over c, z (n Montgomery field elements each) and G (n affine points), all in HBM, n a power of two:
 // ip_l = <c_r, z_l>, ip_r = <c_l, z_r> (Montgomery), l_xy = <c_r, G_l> + ip_l h', r_xy = <c_l, G_r> + ip_r h' (affine, Montgomery;
@@ -189,21 +284,44 @@ int zkb_ipa_round_fold_dev(zkb_ctx *ctx, uint64_t *coeffs_dev, uint64_t *z_dev, 
     const host::Fe prod = host::mul(host::mul(hx, hxi, host::FR), one, host::FR);      // canonical x * x_inv
     if (memcmp(prod.l, one.l, 32) != 0) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ipa_round_fold_dev: x * x_inv != 1");
     const host::Fe canon = host::mul(hx, one, host::FR);
-    Bits256 pos, neg;
-    int top = naf_of(canon.l, &pos, &neg);
-    const char *plain = getenv("ZKB_IPA_NAF");                    // A/B: ZKB_IPA_NAF=0 walks the plain binary expansion (same results)
-    if (plain && plain[0] == '0') {
-        memcpy(pos.w, canon.l, 32);
-        memset(neg.w, 0, 32);
-        top = 255;
-        while (top > 0 && !((pos.w[top >> 5] >> (top & 31)) & 1)) --top;
+    // key fold: through the endomorphism (half the doublings) unless ZKB_IPA_GLV=0 or the split is not short (never, for the
+    // generated constants); ZKB_IPA_NAF=0 walks plain binary expansions instead of non-adjacent forms (A/B knobs, same results)
+    const char *e_glv = getenv("ZKB_IPA_GLV"), *e_naf = getenv("ZKB_IPA_NAF");
+    const bool use_naf = !(e_naf && e_naf[0] == '0');
+    auto digits = [&](const uint64_t v[4], Bits256 *pos, Bits256 *neg) {
+        int top = naf_of(v, pos, neg);
+        if (!use_naf) {
+            memcpy(pos->w, v, 32);
+            memset(neg->w, 0, 32);
+            top = 255;
+            while (top >= 0 && !((pos->w[top >> 5] >> (top & 31)) & 1)) --top;
+        }
+        return top;
+    };
+    uint64_t m1[4], m2[4];
+    int neg1 = 0, neg2 = 0;
+    const bool use_glv = !(e_glv && e_glv[0] == '0') && glv_split(canon.l, m1, &neg1, m2, &neg2);
+    Bits256 pos, neg, pos2, neg2b;
+    int top = 0, top2 = -1;
+    if (use_glv) {
+        top = digits(m1, &pos, &neg);
+        top2 = digits(m2, &pos2, &neg2b);
+    } else {
+        top = digits(canon.l, &pos, &neg);
     }
     fe_t dx, dxi;
     memcpy(dx.v, x, 32);
     memcpy(dxi.v, x_inv, 32);
     const size_t half = n / 2;
     ipa_fold_scalars_kernel<<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>((uint4 *)coeffs_dev, (uint4 *)z_dev, half, dx, dxi);
-    ipa_fold_key_kernel<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>((g1a_t *)key_dev, (uint32_t)half, pos, neg, top);
+    if (use_glv) {
+        fq_t beta;
+        memcpy(beta.v, host::GLV_BETA, sizeof beta.v);
+        ipa_fold_key_glv_kernel<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>((g1a_t *)key_dev, (uint32_t)half, pos, neg, pos2, neg2b,
+                                                                                         top > top2 ? top : top2, neg1, neg2, beta);
+    } else {
+        ipa_fold_key_kernel<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>((g1a_t *)key_dev, (uint32_t)half, pos, neg, top);
+    }
     ctx->launches += 2;
     ZKB_CUDA(ctx, cudaGetLastError());
     return ZKB_OK;
