@@ -185,6 +185,23 @@ def test_msm_2_20_vs_oracle(ctx):
     ctx.srs_precompute(-1)
 
 
+def test_msm_2_22_vs_oracle(ctx):
+    """The north star's target size: a 2^22-point MSM, uniform scalars, bit-exact against the VariableBaseMSM restatement --
+    plain bases (cost-model window) and fixed-base tables."""
+    n = 1 << 22
+    dP, P = gpu_points(ctx, n, 201)
+    ctx.srs_load(dP)
+    s = cref.rand_fe(cref.FR, n, 202)
+    exp, einf = cref.msm_g1(P, s)
+    got, inf = ctx.msm(s)
+    assert inf == einf and np.array_equal(got, exp)
+    ctx.srs_precompute(0)
+    got, inf = ctx.msm(s)
+    assert inf == einf and np.array_equal(got, exp)
+    ctx.srs_precompute(-1)
+    ctx.srs_load(dP[:8].contiguous())          # give the 256 MiB key back
+
+
 def test_commit_push_finish_matches_batch(ctx):
     """zkb_commit_push / zkb_commit_finish (the incremental form of zkb_commit_batch_dev the round driver uses to
     overlap uploads with commitments): same commitments as the batch call and as the oracle, for more pushes than
