@@ -316,6 +316,11 @@ ZKB_API int zkb_ipa_round_lr_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, const
                          uint64_t ip_r[4]);
 ZKB_API int zkb_ipa_round_fold_dev(zkb_ctx *ctx, uint64_t *coeffs_dev, uint64_t *z_dev, uint64_t *key_dev, size_t n, const uint64_t x[4],
                            const uint64_t x_inv[4]);
+/* The verifier's linear-time step (ipa_pc::check after succinct_check): <h, G> over the whole key, h(X) = prod_j (1 + x_j X^(2^(k-1-j)))
+ * expanded in HBM (SuccinctCheckPolynomial::compute_coeffs); equals the proof's final_comm_key for an honest proof.
+ * challenges_mont: the k = log2 n round challenges in proof order, Montgomery form. */
+ZKB_API int zkb_ipa_final_key_dev(zkb_ctx *ctx, const uint64_t *key_dev, size_t n, const uint64_t *challenges_mont, uint64_t out_xy[8],
+                          int *is_inf);
 
 /* ---- the reference CLI's key files ---------------------------------------------------------------------- */
 /* `compile` writes ck / cvk / pk / epk / vk with ark-serialize 0.3 serialize_unchecked (bin/src/parser.rs:16-29,

@@ -280,8 +280,11 @@ def test_gpu_opening_equals_the_restated_one(on_curve):
             assert C == ipa_ref.commit(pts[:n], coeffs)
             proof, value = pc.open(d_coeffs, length, C, point)
             assert value == sum(c * pow(point, i, r) for i, c in enumerate(coeffs)) % r
-            ref, _ = ipa_ref.open_(pts[:n], pts[n], coeffs, C, point)
+            ref, challenges = ipa_ref.open_(pts[:n], pts[n], coeffs, C, point)
             assert (proof.l_vec, proof.r_vec, proof.final_comm_key, proof.c) == ref
+            # the verifier's linear-time step on the device: <h-coefficients, G> for the check polynomial of the challenges
+            fk = pc._pt_ints(*ctx.ipa_final_key_dev(pc.key, n, _fr_arr(challenges)))
+            assert fk == pyref.msm_naive(pts[:n], ipa_ref.check_poly_coeffs(challenges)) == proof.final_comm_key
             assert pc.check(C, point, value, proof) and ipa_ref.check(pts[:n], pts[n], C, point, value, ref)
             assert not pc.check(C, point, (value + 1) % r, proof)
             assert not pc.check(C, (point + 1) % r, value, proof)

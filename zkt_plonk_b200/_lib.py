@@ -74,6 +74,7 @@ def load(curve="bn254"):
         "zkb_msm_g1_bases": (i, [vp, vp, vp, sz, vp, ctypes.POINTER(i)]),
         "zkb_msm_g1_points_dev": (i, [vp, vp, vp, sz, i, vp, ctypes.POINTER(i)]),
         "zkb_ipa_round_lr_dev": (i, [vp, vp, vp, vp, sz, vp, vp, ctypes.POINTER(i), vp, ctypes.POINTER(i), vp, vp]),
+        "zkb_ipa_final_key_dev": (i, [vp, vp, sz, vp, vp, ctypes.POINTER(i)]),
         "zkb_test_glv_split": (i, [vp, vp, ctypes.POINTER(i), vp, ctypes.POINTER(i)]),
         "zkb_ipa_round_fold_dev": (i, [vp, vp, vp, vp, sz, vp, vp]),
         "zkb_commit_batch_dev": (i, [vp, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, vp, ctypes.POINTER(i)]),

@@ -176,6 +176,13 @@ class Context:
                                                    ctypes.byref(li), _host_ptr(r), ctypes.byref(ri), _host_ptr(ipl), _host_ptr(ipr)))
         return (l, bool(li.value)), (r, bool(ri.value)), ipl, ipr
 
+    def ipa_final_key_dev(self, key_dev, n, challenges_mont):
+        """<h, G> for the check polynomial of the round challenges ((log2 n, 4) uint64 Montgomery, proof order): (affine, is_inf)."""
+        out = np.zeros(self.aff_words, dtype=np.uint64)
+        inf = ctypes.c_int(0)
+        self._check(self._lib.zkb_ipa_final_key_dev(self._h, _dev_ptr(key_dev), n, _host_ptr(challenges_mont), _host_ptr(out), ctypes.byref(inf)))
+        return out, bool(inf.value)
+
     def ipa_round_fold_dev(self, coeffs_dev, z_dev, key_dev, n, x_mont, x_inv_mont):
         """c_l += x^-1 c_r, z_l += x z_r, G_l += x G_r in place (x, x_inv: (4,) uint64 Montgomery)."""
         self._check(self._lib.zkb_ipa_round_fold_dev(self._h, _dev_ptr(coeffs_dev), _dev_ptr(z_dev), _dev_ptr(key_dev), n,

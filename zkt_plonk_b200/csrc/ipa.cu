@@ -224,6 +224,18 @@ bool glv_split(const uint64_t k[4], uint64_t m1[4], int *neg1, uint64_t m2[4], i
     return memcmp(back.l, k, 32) == 0;
 }
 
+// Coefficients of the verifier's check polynomial h(X) = prod_j (1 + x_j X^(2^(k-1-j))) (ipa_pc SuccinctCheckPolynomial::compute_coeffs):
+// coefficient i is the product of the challenges whose bit (k - 1 - j) is set in i.  One thread per coefficient, <= k products.
+struct CheckChallenges { fe_t x[30]; };
+__global__ void __launch_bounds__(256) ipa_check_coeffs_kernel(uint4 *out, uint32_t k, const __grid_constant__ CheckChallenges ch) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >> k) return;
+    fe_t acc = fone<F>();
+    for (uint32_t j = 0; j < k; ++j)
+        if ((i >> (k - 1 - j)) & 1) acc = fmul<F>(acc, ch.x[j]);
+    fstore(out + 2 * i, acc);
+}
+
 bool pow2(size_t n) { return n >= 2 && (n & (n - 1)) == 0; }
 
 }  // namespace
@@ -273,6 +285,28 @@ int zkb_ipa_round_lr_dev(zkb_ctx *ctx, const uint64_t *coeffs_dev, const uint64_
     memcpy(ip_l, ips, 32);
     memcpy(ip_r, ips + 4, 32);
     return ZKB_OK;
+}
+
+// The linear-time half of the verifier (ipa_pc check after succinct_check): <h-coefficients, G> over the whole committer key, to be
+// compared with the proof's final_comm_key.  challenges_mont: the log2 n round challenges in proof order, Montgomery form.
+int zkb_ipa_final_key_dev(zkb_ctx *ctx, const uint64_t *key_dev, size_t n, const uint64_t *challenges_mont, uint64_t *out_xy, int *is_inf) {
+    if (!ctx) return ZKB_ERR_INVALID;
+    if (!key_dev || !challenges_mont || !out_xy) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ipa_final_key_dev: null argument");
+    if (!pow2(n) || n > ((size_t)1 << 30)) ZKB_FAIL(ctx, ZKB_ERR_DOMAIN, "zkb_ipa_final_key_dev: n must be a power of two, 2 <= n <= 2^30");
+    uint32_t k = 0;
+    while (((size_t)1 << k) < n) ++k;
+    CheckChallenges ch;
+    memset(&ch, 0, sizeof ch);
+    for (uint32_t j = 0; j < k; ++j) {
+        if (host::ge<host::FR_L>(challenges_mont + 4 * j, host::FR.p)) ZKB_FAIL(ctx, ZKB_ERR_INVALID, "zkb_ipa_final_key_dev: challenge not reduced");
+        memcpy(ch.x[j].v, challenges_mont + 4 * j, 32);
+    }
+    int rc = zkb_reserve(ctx, ctx->poly_ws, n * 32);
+    if (rc) return rc;
+    ipa_check_coeffs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint4 *)ctx->poly_ws.p, k, ch);
+    ctx->launches += 1;
+    ZKB_CUDA(ctx, cudaGetLastError());
+    return zkb_msm_points_plus(ctx, key_dev, (const uint64_t *)ctx->poly_ws.p, n, 1, nullptr, nullptr, out_xy, is_inf);
 }
 
 // The round's fold, in place: afterwards the first n / 2 entries of each vector are the next round's vectors.

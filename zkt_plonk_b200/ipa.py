@@ -129,8 +129,8 @@ class GpuIPA:
         return IpaProof(l_vec, r_vec, final_key, c0), value
 
     def check(self, commitment, point, value, proof, oracle=random_oracle_challenge):
-        """succinct_check (log n group operations) and the final-key check (one MSM of n over ck.comm_key)."""
-        import torch
+        """succinct_check (log n group operations) and the final-key check (zkb_ipa_final_key_dev: the check polynomial's
+        coefficients expanded in HBM and one MSM of n over ck.comm_key)."""
         r = field.R_MOD
         k = len(proof.l_vec)
         if 1 << k != self.n or len(proof.r_vec) != k:
@@ -148,9 +148,5 @@ class GpuIPA:
             h_at_point = h_at_point * (1 + ch * pow(point, 1 << (k - 1 - i), r)) % r
         if self.lincomb(pts, sc) != self.lincomb([proof.final_comm_key, h_prime], [proof.c, proof.c * h_at_point % r]):
             return False
-        coeffs = [1]
-        for ch in reversed(challenges):
-            coeffs = coeffs + [v * ch % r for v in coeffs]
-        h_coeffs = np.array([field.int_to_limbs(field.to_mont(v)) for v in coeffs], dtype=np.uint64)
-        d = torch.from_numpy(h_coeffs.view(np.int64)).to(self.key.device)
-        return self._pt_ints(*self.ctx.msm_points_dev(self.key, d, self.n)) == proof.final_comm_key
+        ch_arr = np.array([field.int_to_limbs(field.to_mont(v)) for v in challenges], dtype=np.uint64).reshape(-1, 4)
+        return self._pt_ints(*self.ctx.ipa_final_key_dev(self.key, self.n, ch_arr)) == proof.final_comm_key
