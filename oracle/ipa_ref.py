@@ -110,6 +110,22 @@ def open_(comm_key, h, coeffs, commitment, point, oracle=random_oracle_challenge
     return (l_vec, r_vec, key[0], c[0]), challenges
 
 
+def combine(polys, commitments, values, opening_challenge):
+    """What open / check do with several polynomials at one point: weights xi^(2 j) for polynomial j -- ipa_pc draws two opening
+    challenges per polynomial, the odd one for the shifted polynomial of a degree bound (none here); opening_challenges(i) =
+    xi^i (ark-poly-commit 0.3 PolynomialCommitment::open)."""
+    r = pyref.R_MOD
+    n = max((len(p) for p in polys), default=0)
+    coeffs, C, v = [0] * n, None, 0
+    for j, p in enumerate(polys):
+        w = pow(opening_challenge, 2 * j, r)
+        for i, c in enumerate(p):
+            coeffs[i] = (coeffs[i] + w * c) % r
+        C = pyref.g1_add(C, pyref.g1_mul(w, commitments[j]))
+        v = (v + w * values[j]) % r
+    return coeffs, C, v
+
+
 def check(comm_key, h, commitment, point, value, proof, oracle=random_oracle_challenge):
     """succinct_check followed by the linear-time check of the final key."""
     r = pyref.R_MOD

@@ -142,7 +142,9 @@ impl PolynomialCommitment<Fr, Poly> for GpuIpaPc {
         let mut coeffs = vec![Fr::zero(); n];
         let mut combined = <G1Affine as AffineCurve>::Projective::zero();
         for (j, (p, c)) in polys.iter().zip(&comms).enumerate() {
-            let ch = opening_challenges(j as u64);
+            // ipa_pc draws TWO opening challenges per polynomial (the second one is for its shifted polynomial, unused without a
+            // degree bound): polynomial j is weighted by challenge 2 j
+            let ch = opening_challenges(2 * j as u64);
             for (acc, v) in coeffs.iter_mut().zip(&p.polynomial().coeffs) {
                 *acc += ch * v;
             }

@@ -75,6 +75,17 @@ def test_restated_protocol_properties(on_curve):
     proof2, ch2 = ipa_ref.open_(key, h, coeffs, C2, point, oracle=other)
     ctr[0] = 0
     assert ipa_ref.check(key, h, C2, point, value, proof2, oracle=other) and ch2 != challenges
+    # several polynomials at one point (how the prover calls PC::open): one opening of sum_j xi^(2 j) p_j
+    polys = [coeffs, [rnd.randrange(r) for _ in range(8)], [rnd.randrange(r) for _ in range(3)]]
+    comms = [ipa_ref.commit(key, p) for p in polys]
+    vals = [sum(c * pow(point, i, r) for i, c in enumerate(p)) % r for p in polys]
+    xi = rnd.randrange(r)
+    cc, CC, vv = ipa_ref.combine(polys, comms, vals, xi)
+    assert CC == ipa_ref.commit(key, cc) and vv == sum(c * pow(point, i, r) for i, c in enumerate(cc)) % r
+    assert cc[7] == (pow(xi, 2, r) * polys[1][7]) % r
+    proof_c, _ = ipa_ref.open_(key, h, cc, CC, point)
+    assert ipa_ref.check(key, h, CC, point, vv, proof_c)
+    assert not ipa_ref.check(key, h, ipa_ref.combine(polys, comms, vals, xi + 1)[1], point, vv, proof_c)
     # the zero polynomial: identity commitment, identity cross terms
     proof0, _ = ipa_ref.open_(key, h, [], None, point)
     assert proof0[3] == 0 and all(p is None for p in proof0[0]) and ipa_ref.check(key, h, None, point, 0, proof0)
@@ -292,6 +303,23 @@ def test_gpu_opening_equals_the_restated_one(on_curve):
             assert not pc.check(C, point, value, IpaProof(proof.r_vec, proof.l_vec, proof.final_comm_key, proof.c))
             assert not pc.check(C, point, value, IpaProof(proof.l_vec, proof.r_vec, pts[0], proof.c))
             assert _fr_ints(d_coeffs.cpu().numpy()) == coeffs          # the caller's polynomial is untouched
+        # several polynomials at one point, as the prover calls PC::open: equal to the restated combination's opening
+        n = 16
+        d_key, pts, _ = _device_key(ctx, n, 300)
+        pc = GpuIPA(ctx)
+        pc.load_committer_key(d_key[:n].contiguous(), pts[n])
+        polys = [[rnd.randrange(r) for _ in range(m)] for m in (16, 9, 1)]
+        d_polys = [_dev(_fr_arr(p)) for p in polys]
+        comms = [pc.commit_dev(d, len(p)) for d, p in zip(d_polys, polys)]
+        point, xi = rnd.randrange(r), rnd.randrange(r)
+        proof, values = pc.open_many(d_polys, [len(p) for p in polys], comms, point, xi)
+        assert values == [sum(c * pow(point, i, r) for i, c in enumerate(p)) % r for p in polys]
+        cc, CC, vv = ipa_ref.combine(polys, comms, values, xi)
+        ref, _ = ipa_ref.open_(pts[:n], pts[n], cc, CC, point)
+        assert (proof.l_vec, proof.r_vec, proof.final_comm_key, proof.c) == ref
+        assert pc.check_many(comms, point, values, proof, xi)
+        assert not pc.check_many(comms, point, [values[0], values[2], values[1]], proof, xi)
+        assert not pc.check_many(comms, point, values, proof, (xi + 1) % r)
         n = 1 << 12
         d_key, pts, _ = _device_key(ctx, n, 77)
         pc = GpuIPA(ctx)

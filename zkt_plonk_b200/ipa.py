@@ -128,6 +128,32 @@ class GpuIPA:
         c0 = field.from_mont(field.limbs_to_int(c[0].cpu().numpy().view(np.uint64)))
         return IpaProof(l_vec, r_vec, final_key, c0), value
 
+    def open_many(self, polys_dev, lengths, commitments, point, opening_challenge, oracle=random_oracle_challenge):
+        """PC::open(ck, polys, commitments, point, opening_challenge, ..) as the prover calls it (prove.rs:381-451): one opening
+        of sum_j xi^(2 j) p_j (ipa_pc draws two opening challenges per polynomial; the odd ones belong to degree-bounded
+        polynomials' shifts, of which plonk-core has none).  Returns (IpaProof, [p_j(point)])."""
+        import torch
+        r = field.R_MOD
+        k = len(polys_dev)
+        n = max(lengths)
+        weights = [pow(opening_challenge, 2 * j, r) for j in range(k)]
+        combined = torch.empty((n, 4), dtype=torch.int64, device=self.key.device)
+        w_arr = np.array([field.int_to_limbs(field.to_mont(w)) for w in weights], dtype=np.uint64).reshape(k, 4)
+        self.ctx.poly_lincomb_dev(list(polys_dev), list(lengths), w_arr, combined, n)
+        C = self.lincomb(list(commitments), weights)
+        pts = np.tile(_fr_limbs(point), (k, 1))
+        values = [field.from_mont(field.limbs_to_int(v)) for v in self.ctx.poly_eval_many_dev(list(polys_dev), list(lengths), pts)]
+        proof, value = self.open(combined, n, C, point, oracle)
+        assert value == sum(w * v for w, v in zip(weights, values)) % r
+        return proof, values
+
+    def check_many(self, commitments, point, values, proof, opening_challenge, oracle=random_oracle_challenge):
+        """PC::check for the same batch: the commitments and values combined with xi^(2 j), then `check`."""
+        r = field.R_MOD
+        weights = [pow(opening_challenge, 2 * j, r) for j in range(len(commitments))]
+        C = self.lincomb(list(commitments), weights)
+        return self.check(C, point, sum(w * v for w, v in zip(weights, values)) % r, proof, oracle)
+
     def check(self, commitment, point, value, proof, oracle=random_oracle_challenge):
         """succinct_check (log n group operations) and the final-key check (zkb_ipa_final_key_dev: the check polynomial's
         coefficients expanded in HBM and one MSM of n over ck.comm_key)."""
