@@ -302,5 +302,29 @@ def test_key_files_on_the_bls12_curves(on_curve, tmp_path):
         pub = list(circ.pi.values())
         assert verifier.verify(vk, raw, pub, (h_arr, bh_arr)) == 0
         assert verifier.verify(vk, raw, pub, (h_arr, h_arr)) != 0
+        # mutated files (byte flips, truncations, inflated length fields, garbage tails): an error or a parse, never a crash
+        files = {"pk": (ref_pk, keyfile.pk_read), "vk": (ref_vk, keyfile.vk_read), "ck": (ref_ck, keyfile.ck_read),
+                 "cvk": ((tmp_path / "cvk").read_bytes(), keyfile.cvk_read)}
+        refused = 0
+        for name, (good, reader) in files.items():
+            for trial in range(60):
+                data = bytearray(good)
+                kind = trial % 4
+                if kind == 0:
+                    for _ in range(rnd.randrange(1, 4)):
+                        data[rnd.randrange(len(data))] ^= 1 << rnd.randrange(8)
+                elif kind == 1:
+                    data = data[: rnd.randrange(len(data))]
+                elif kind == 2:
+                    off = rnd.choice([0, 8, 11, 19])
+                    data[off: off + 8] = rnd.choice([1 << 40, (1 << 64) - 1, 1 << 31]).to_bytes(8, "little")
+                else:
+                    data += bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 40)))
+                (tmp_path / "mut").write_bytes(bytes(data))
+                try:
+                    reader(tmp_path / "mut")
+                except _lib.ZkbError:
+                    refused += 1
+        assert refused > 50
     finally:
         arkser.use_curve("bn254")
