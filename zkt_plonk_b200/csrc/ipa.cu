@@ -12,8 +12,11 @@
 // elements per round.  Results are group / field elements, so they equal the CPU's bit for bit in affine / Montgomery form.
 //
 // The key fold is the expensive half: n / 2 scalar multiplications by the SAME 255-bit challenge per round (n in total over an
-// opening).  One thread per point runs double-and-add over the challenge's non-adjacent form (recoded once on the host; uniform
-// across the grid: no divergence) in XYZZ coordinates and normalises its own result.
+// opening).  The challenge is recoded once on the host -- split through the curve's endomorphism into two 128-bit halves
+// (x = k1 + lambda k2, glv_split), each in non-adjacent form -- and is uniform across the grid (no divergence); one thread per
+// point runs 128 doublings with the halves' additions interleaved, in XYZZ coordinates, and normalises its own result
+// (ipa_fold_key_glv_kernel; ipa_fold_key_kernel is the plain fold, kept as the fallback and for A/B).
+// zkb_ipa_final_key_dev is the verifier's linear-time step: the check polynomial's coefficients expanded in HBM + one MSM.
 #include "ctx.h"
 #include "ec.cuh"
 
